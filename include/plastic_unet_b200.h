@@ -1,0 +1,198 @@
+/*
+ * plastic_unet_b200.h — C-ABI of the B200-native Plastic U-Net hot path.
+ *
+ * Drop-in boundary: the reference has no FFI; its hot path sits behind the
+ * Python nn.Module surface of package `unet` (reference src/unet/__init__.py:1-2).  Every
+ * entry point below replaces one stock-PyTorch call site inside that package; the reference
+ * file:line it replaces is cited per function.  The Python side (plastic-unet_b200/pu_b200)
+ * binds these with ctypes and wraps them as torch.library custom ops.
+ *
+ * Conventions
+ *  - All tensors are fp32, device-resident, **NHWC** (channels contiguous) unless stated.
+ *  - The caller (PyTorch) owns every buffer; the library allocates nothing persistent.
+ *  - Every call is asynchronous on `stream` (a cudaStream_t passed as void*); no internal
+ *    synchronisation, safe under CUDA-graph capture.
+ *  - Return 0 on success, negative pu_status otherwise; pu_last_error() has the text.
+ *    No exception or abort crosses this boundary.
+ *  - A "view" (H?,W?,oy?,ox?) describes a tensor [B,H?,W?,C?] of which the op uses the window
+ *    starting at pixel (oy?,ox?) of extent H x W (crop fused as a pointer offset;
+ *    reference unet_p.py:161-165, unet_p_res.py:215-218).
+ */
+#ifndef PLASTIC_UNET_B200_H_
+#define PLASTIC_UNET_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  PU_OK = 0,
+  PU_ERR_BAD_ARG = -1,      /* null pointer / non-positive dim / misaligned */
+  PU_ERR_UNSUPPORTED = -2,  /* shape outside what the kernel family handles  */
+  PU_ERR_CUDA = -3,         /* CUDA runtime/driver error captured at launch  */
+  PU_ERR_NO_DEVICE = -4
+} pu_status;
+
+#define PU_RULE_HEBB 0
+#define PU_RULE_OJA 1
+
+/* conv3x3 math modes */
+#define PU_MATH_FP32 0 /* CUDA-core FFMA, strict fp32 (parity mode, any shape)        */
+#define PU_MATH_TF32 1 /* tcgen05 kind::tf32 implicit GEMM, fp32 accumulate in TMEM   */
+
+/* ---- library management --------------------------------------------------------------- */
+int pu_version(void);
+const char* pu_last_error(void);
+/* number of kernels this library has launched (or captured) since load / last reset */
+long long pu_launch_count(void);
+void pu_reset_launch_count(void);
+/* 1 if the tcgen05/TMA conv path is usable on the current device (sm_100, driver entry points) */
+int pu_tc_available(void);
+
+/* ---- layout -----------------------------------------------------------------------------
+ * NCHW <-> NHWC (module entry/exit when n_channels > 1; reference keeps NCHW throughout). */
+int pu_nchw_to_nhwc(const float* x, float* y, int B, int C, int H, int W, void* stream);
+int pu_nhwc_to_nchw(const float* x, float* y, int B, int C, int H, int W, void* stream);
+
+/* ---- 3x3 convolution, stride 1, pad 1 -----------------------------------------------------
+ * replaces nn.Conv2d(k=3,padding=1) (+ReLU, +residual add, +torch.cat/F.pad crop) at
+ * reference unet_p.py:105-116,161-166 and unet_p_res.py:150-158,186-189,215-219,230,264.
+ *
+ * pu_pack_w3x3: OIHW weight [Cout,Cin,3,3] -> packed [9][Cin][Cout] (transpose=0, forward)
+ *               or [9][Cout][Cin] with taps flipped (transpose=1, operand of dgrad).       */
+int pu_pack_w3x3(const float* w_oihw, float* w_packed, int Cout, int Cin, int transpose, void* stream);
+
+/* y = act( conv3x3(cat[src0,src1]) + bias + res ), written channel-split into dst0|dst1.
+ * src1, bias, res, dst1 may be NULL.  wp is the packed weight [9][C0+C1][Cout].
+ * dst views may be larger than HxW (their border is NOT written — caller zero-fills).    */
+int pu_conv3x3_fwd(const float* src0, int H0, int W0, int C0, int oy0, int ox0,
+                   const float* src1, int H1, int W1, int C1, int oy1, int ox1,
+                   const float* wp, const float* bias, const float* res, int relu,
+                   float* dst0, int Hd0, int Wd0, int Cd0, int oyd0, int oxd0,
+                   float* dst1, int Hd1, int Wd1, int Cd1, int oyd1, int oxd1,
+                   int B, int H, int W, int Cout, int math, void* stream);
+
+/* dw_oihw[Cout, C0+C1, 3, 3] = sum_{b,y,x} g[b,y,x,co] * cat[src0,src1][b,y+ky-1,x+kx-1,ci]
+ * (overwrites dw).  g is [B,H,W,Cout] dense.                                               */
+int pu_conv3x3_wgrad(const float* src0, int H0, int W0, int C0, int oy0, int ox0,
+                     const float* src1, int H1, int W1, int C1, int oy1, int ox1,
+                     const float* g, float* dw_oihw, int B, int H, int W, int Cout,
+                     int math, void* stream);
+
+/* g = relu ? dy * (y > 0) : dy ; dbias[c] = sum_pixels g  (g may alias dy; dbias may be NULL;
+ * y may be NULL iff relu == 0).  Autograd of the fused ReLU + bias epilogue above.          */
+int pu_relu_bwd_bias(const float* dy, const float* y, float* g, float* dbias,
+                     long long npix, int C, int relu, void* stream);
+
+/* ---- 1x1 convolution (reference unet_p.py:173, unet_p_res.py:194; CoordConv stem
+ * coord_conv_script.py:104-126).  coords != 0 appends the AddCoords channels
+ * (coord_conv_script.py:69-96): xx = 2*j/(W-1)-1, yy = 2*i/(H-1)-1, [rr if coords == 3]
+ * analytically — they are never materialised.  w is [Cout, Cin + coords].                  */
+int pu_conv1x1_fwd(const float* x, const float* w, const float* bias, float* y,
+                   int B, int H, int W, int Cin, int Cout, int coords, int relu, void* stream);
+/* g is the (already ReLU-masked) output gradient.  dx and db may be NULL. dw [Cout,Cin+coords], db [Cout]
+ * overwritten.  ws: caller-provided scratch of Cout*(Cin+coords+1) floats (<= 256).              */
+int pu_conv1x1_bwd(const float* x, const float* w, const float* g, float* dx, float* dw, float* db, float* ws,
+                   int B, int H, int W, int Cin, int Cout, int coords, void* stream);
+
+/* ---- transposed convolutions ---------------------------------------------------------------
+ * 2x2 stride 2 (reference unet_p.py:155): w is PyTorch [Cin,Cout,2,2]; y is [B,2H,2W,Cout]. */
+int pu_convT2x2s2_fwd(const float* x, const float* w, const float* bias, float* y,
+                      int B, int H, int W, int Cin, int Cout, void* stream);
+int pu_convT2x2s2_bwd(const float* x, const float* w, const float* dy, float* dx, float* dw, float* db,
+                      int B, int H, int W, int Cin, int Cout, void* stream);
+/* 3x3 stride 2 pad 0 (reference unet_p_res.py:207): full output is (2H+1)x(2W+1); the op writes
+ * only the window [oy,oy+Ho) x [ox,ox+Wo) of it (the F.pad crop of unet_p_res.py:215-217 fused).
+ * chan_scale (may be NULL) is a per-(b,co) multiplier [B,Cout] applied after bias (Dropout2d). */
+int pu_convT3x3s2_fwd(const float* x, const float* w, const float* bias, const float* chan_scale, float* y,
+                      int B, int H, int W, int Cin, int Cout, int Ho, int Wo, int oy, int ox, void* stream);
+int pu_convT3x3s2_bwd(const float* x, const float* w, const float* dy, const float* chan_scale,
+                      float* dx, float* dw, float* db,
+                      int B, int H, int W, int Cin, int Cout, int Ho, int Wo, int oy, int ox, void* stream);
+
+/* ---- pooling / resampling --------------------------------------------------------------------
+ * MaxPool2d(2) floor mode (reference unet_p.py:139, unet_p_res.py:247) with the Dropout2d of
+ * pool_drop (unet_p_res.py:248) fused as an optional per-(b,c) scale [B,C].                   */
+int pu_maxpool2_fwd(const float* x, const float* chan_scale, float* y, int B, int H, int W, int C, void* stream);
+/* dx gets dy*scale at the first maximum (row-major scan, ATen tie-break) and 0 elsewhere.    */
+int pu_maxpool2_bwd(const float* x, const float* chan_scale, const float* dy, float* dx,
+                    int B, int H, int W, int C, void* stream);
+/* nn.Upsample(scale_factor=2, bilinear, align_corners=True) (reference unet_p.py:153)        */
+int pu_bilinear2x_fwd(const float* x, float* y, int B, int H, int W, int C, void* stream);
+int pu_bilinear2x_bwd(const float* dy, float* dx, int B, int H, int W, int C, void* stream);
+
+/* ---- concat / channel scale (only materialised in Dropout2d training mode) ------------------- */
+int pu_concat_scale_fwd(const float* src0, int H0, int W0, int C0, int oy0, int ox0,
+                        const float* src1, int H1, int W1, int C1, int oy1, int ox1,
+                        const float* chan_scale, float* y, int B, int H, int W, void* stream);
+/* inverse: dx0|dx1 windows receive dy[..., :C0]*scale | dy[..., C0:]*scale (either may be NULL; borders
+ * outside the window are NOT written — caller zero-fills). */
+int pu_concat_scale_bwd(const float* dy, const float* chan_scale,
+                        float* dx0, int H0, int W0, int C0, int oy0, int ox0,
+                        float* dx1, int H1, int W1, int C1, int oy1, int ox1, int B, int H, int W, void* stream);
+/* y[b,p,c] = x[b,p,c] * scale[b,c]  (y may alias x) */
+int pu_chan_scale(const float* x, const float* chan_scale, float* y, int B, long long hw, int C, void* stream);
+
+/* ---- BatchNorm2d (optional, reference unet_p.py:106,109; unet_p_res.py:151,175) -------------- */
+/* training forward: batch statistics; writes mean/invstd [C] (saved for backward) and updates the running
+ * stats (may be NULL); y = (x-mean)*invstd*gamma+beta, optional fused ReLU.  ws: scratch of 2*C doubles. */
+int pu_bn_train_fwd(const float* x, const float* gamma, const float* beta, float* y,
+                    float* save_mean, float* save_invstd, float* running_mean, float* running_var, double* ws,
+                    float momentum, float eps, long long npix, int C, int relu, void* stream);
+int pu_bn_eval_fwd(const float* x, const float* gamma, const float* beta, const float* running_mean,
+                   const float* running_var, float* y, float eps, long long npix, int C, int relu, void* stream);
+/* dy is grad wrt y (post-ReLU if relu); y needed iff relu. train!=0 uses the batch-statistics backward,
+ * train==0 treats mean/invstd as constants (eval).  dgamma/dbeta may be NULL.  ws: 2*C doubles.          */
+int pu_bn_bwd(const float* x, const float* y, const float* dy, const float* gamma,
+              const float* mean, const float* invstd, float* dx, float* dgamma, float* dbeta, double* ws,
+              long long npix, int C, int relu, int train, void* stream);
+/* running_mean/var <- (1-momentum)*running + momentum*(batch mean / unbiased batch var recovered from invstd) */
+int pu_bn_update_running(const float* mean, const float* invstd, float* running_mean, float* running_var,
+                         float momentum, float eps, long long npix, int C, void* stream);
+/* invstd[c] = rsqrt(running_var[c] + eps) (eval-mode backward helper) */
+int pu_bn_invstd(const float* running_var, float* invstd, float eps, int C, void* stream);
+
+/* ---- plastic head (reference unet_p.py:70-79 == unet_p_res.py:116-125) ------------------------
+ * X [B*N, N] (the B output maps viewed as N x N), Weff = w + alpha*hebb, A = X @ Weff, S = sigmoid(A).
+ * weff_out [N,N] is scratch that backward re-uses.                                              */
+int pu_plastic_head_fwd(const float* X, const float* w, const float* alpha, const float* hebb,
+                        float* weff_out, float* S, int B, int N, void* stream);
+/* gA = gS*S*(1-S); gX = gA @ Weff^T; gWeff = X^T @ gA; gw = gWeff; galpha = gWeff*hebb; ghebb = gWeff*alpha.
+ * gA_ws is [B*N,N] scratch. galpha/ghebb may be NULL.                                           */
+int pu_plastic_head_bwd(const float* X, const float* S, const float* gS, const float* weff,
+                        const float* alpha, const float* hebb, float* gA_ws,
+                        float* gX, float* gw, float* galpha, float* ghebb, int B, int N, void* stream);
+
+/* ---- plastic trace update (reference unet_p.py:81-84 == unet_p_res.py:127-130) ----------------
+ * pre/post are the stacked pre-/post-synaptic rows [K, N] (parity mode: K = B, row 0 of every
+ * map, given as pointers to map b's first row with row stride `ld` floats).
+ * One fused pass:  delta = pre^T @ post (contraction over K), q = sum_k post^2,
+ *   hebb: out = (1-eta)*hebb + eta*delta/K
+ *   oja : out = hebb*(1 - eta*q/K) + eta*delta/K
+ * which is exactly the reference at K == 1.  eta is a device scalar.                            */
+int pu_trace_update_fwd(const float* hebb, const float* pre, const float* post, long long ld, int K,
+                        const float* eta, int rule, float* out, int N, void* stream);
+/* data-parallel split form: delta_q = [N*N + N] floats = (sum_k outer, sum_k post^2) — all-reduced
+ * over ranks by the caller — then the epilogue with K_global.                                   */
+int pu_trace_delta(const float* pre, const float* post, long long ld, int K, float* delta_q, int N, void* stream);
+int pu_trace_apply(const float* hebb, const float* delta_q, int K_global, const float* eta, int rule,
+                   float* out, int N, void* stream);
+/* backward of the fused update w.r.t. hebb, pre, post, eta (closed forms) */
+int pu_trace_update_bwd(const float* hebb, const float* pre, const float* post, long long ld, int K,
+                        const float* eta, int rule, const float* gout,
+                        float* ghebb, float* gpre, float* gpost, float* geta, int N, void* stream);
+
+/* ---- train-step tail (reference train.py:66-70,101-112) ------------------ */
+/* loss = mean BCE(S, T) with log clamped at -100 (nn.BCELoss); gS = dloss/dS. loss is a device scalar. */
+int pu_bce_fwd_bwd(const float* S, const float* T, float* loss, float* gS, long long n, void* stream);
+/* Adam over one flat arena (torch.optim.Adam defaults; step_count is a device float scalar that is incremented) */
+int pu_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* step_count,
+                 const float* lr, float beta1, float beta2, float eps, float grad_scale, long long n, void* stream);
+
+/* elementwise helpers for autograd glue */
+int pu_add(const float* a, const float* b, float* out, long long n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLASTIC_UNET_B200_H_ */

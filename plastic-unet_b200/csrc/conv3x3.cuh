@@ -1,0 +1,31 @@
+// Argument blocks shared by the conv3x3 kernel families (FFMA fp32 and tcgen05 tf32).
+#pragma once
+#include "pu_common.cuh"
+
+namespace pu {
+
+struct Conv3x3Args {
+  View s0, s1;        // concatenated sources (s1.p may be null)
+  const float* wp;    // packed weights [9][Cin][Cout]
+  const float* bias;  // [Cout] | null
+  const float* res;   // [B,H,W,Cout] | null, added before the ReLU
+  ViewW d0, d1;       // channel-split destinations (d1.p may be null)
+  int B, H, W, Cin, Cout, relu;
+  int tilesX, tilesY;
+};
+
+struct WgradArgs {
+  View s0, s1;
+  const float* g;  // [B,H,W,Cout]
+  float* dw;       // OIHW
+  int B, H, W, Cin, Cout;
+  int tilesX, tilesY, ntiles;
+};
+
+int conv3x3_fwd_ffma(const Conv3x3Args& a, cudaStream_t st);
+int conv3x3_wgrad_ffma(const WgradArgs& a, cudaStream_t st);
+// tcgen05 path (conv3x3_tc.cu); returns PU_ERR_UNSUPPORTED when the shape does not fit it
+int conv3x3_fwd_tc(const Conv3x3Args& a, cudaStream_t st);
+bool conv3x3_tc_supported(const Conv3x3Args& a);
+
+}  // namespace pu

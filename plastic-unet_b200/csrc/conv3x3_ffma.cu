@@ -1,0 +1,507 @@
+// conv3x3_ffma.cu — strict-fp32 CUDA-core 3x3 convolution family (NHWC), sm_100a.
+//
+// This is the parity path (PU_MATH_FP32) and the small-shape path (C_in = 1 stem, ragged channel
+// counts, 6x6 / 8x8 bottlenecks).  Forward, dgrad (same kernel, transposed+flipped packed weights)
+// and wgrad.  Replaces nn.Conv2d(k=3,pad=1) + ReLU + residual add + cat/crop at
+// reference unet_p.py:105-116,161-166; unet_p_res.py:150-158,186-189,215-219,230,264.
+//
+// Forward tiling: one CTA = TH x TW output pixels x 8 output channels.  Input channels are staged
+// 8 at a time into shared memory as channel planes [ci][hy][hx] (halo included, zero padded), so the
+// per-lane reads are stride-1 (bank-conflict free); weights [tap][ci][8 co] are read as two
+// broadcast LDS.128.  Each thread owns RP rows x 1 column x 8 channels = RP*8 fp32 accumulators:
+// per input channel 3*(RP+2) scalar LDS + 18 LDS.128 feed 72*RP FFMA.
+#include "pu_common.cuh"
+#include "conv3x3.cuh"
+
+namespace pu {
+
+template <int TW, int RP, int NT>
+__global__ void __launch_bounds__(NT) conv3x3_ffma_kernel(const Conv3x3Args a) {
+  constexpr int TH = (NT / TW) * RP;
+  constexpr int HW_ = TW + 2;  // halo width
+  constexpr int HH_ = TH + 2;
+  constexpr int PLANE = HH_ * HW_;
+  __shared__ float in_s[8 * PLANE];
+  __shared__ __align__(16) float w_s[9 * 8 * 8];
+
+  const int tid = threadIdx.x;
+  int t = blockIdx.x;
+  const int tx = t % a.tilesX;
+  t /= a.tilesX;
+  const int ty = t % a.tilesY;
+  const int b = t / a.tilesY;
+  const int x0 = tx * TW, y0 = ty * TH;
+  const int co0 = blockIdx.y * 8;
+
+  const int px = tid % TW;
+  const int r0 = (tid / TW) * RP;
+
+  float acc[RP][8];
+#pragma unroll
+  for (int r = 0; r < RP; ++r)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[r][j] = 0.f;
+
+  int cbase = 0;  // channel index in the concatenated input
+  for (int s = 0; s < 2; ++s) {
+    const View v = s == 0 ? a.s0 : a.s1;
+    if (v.p == nullptr || v.C == 0) continue;
+    const bool vec = (v.C % 4 == 0);
+    for (int c0 = 0; c0 < v.C; c0 += 8) {
+      const int cc = min(8, v.C - c0);
+      __syncthreads();  // previous chunk fully consumed
+      // ---- stage the input halo tile as channel planes
+      for (int i = tid; i < PLANE; i += NT) {
+        const int hy = i / HW_, hx = i - hy * HW_;
+        const int gy = y0 + hy - 1, gx = x0 + hx - 1;
+        float vals[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) vals[c] = 0.f;
+        if (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W) {
+          const float* p = v.p + (((size_t)b * v.Hs + (gy + v.oy)) * v.Ws + (gx + v.ox)) * v.C + c0;
+          if (vec) {
+            const float4 q0 = ldg4(p);
+            vals[0] = q0.x; vals[1] = q0.y; vals[2] = q0.z; vals[3] = q0.w;
+            if (cc > 4) {
+              const float4 q1 = ldg4(p + 4);
+              vals[4] = q1.x; vals[5] = q1.y; vals[6] = q1.z; vals[7] = q1.w;
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+              if (c < cc) vals[c] = __ldg(p + c);
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) in_s[c * PLANE + i] = vals[c];
+      }
+      // ---- stage the weights of this chunk: w_s[tap][ci][j]
+      for (int i = tid; i < 9 * 8 * 8; i += NT) {
+        const int j = i & 7, ci = (i >> 3) & 7, tap = i >> 6;
+        float wv = 0.f;
+        if (ci < cc && co0 + j < a.Cout) wv = __ldg(a.wp + ((size_t)tap * a.Cin + cbase + c0 + ci) * a.Cout + co0 + j);
+        w_s[i] = wv;
+      }
+      __syncthreads();
+      // ---- accumulate
+      for (int ci = 0; ci < cc; ++ci) {
+        float xin[RP + 2][3];
+        const float* ip = in_s + ci * PLANE + r0 * HW_ + px;
+#pragma unroll
+        for (int i = 0; i < RP + 2; ++i)
+#pragma unroll
+          for (int j = 0; j < 3; ++j) xin[i][j] = ip[i * HW_ + j];
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            const float4 wa = *reinterpret_cast<const float4*>(w_s + ((ky * 3 + kx) * 8 + ci) * 8);
+            const float4 wb = *reinterpret_cast<const float4*>(w_s + ((ky * 3 + kx) * 8 + ci) * 8 + 4);
+#pragma unroll
+            for (int r = 0; r < RP; ++r) {
+              const float xv = xin[r + ky][kx];
+              acc[r][0] = fmaf(xv, wa.x, acc[r][0]);
+              acc[r][1] = fmaf(xv, wa.y, acc[r][1]);
+              acc[r][2] = fmaf(xv, wa.z, acc[r][2]);
+              acc[r][3] = fmaf(xv, wa.w, acc[r][3]);
+              acc[r][4] = fmaf(xv, wb.x, acc[r][4]);
+              acc[r][5] = fmaf(xv, wb.y, acc[r][5]);
+              acc[r][6] = fmaf(xv, wb.z, acc[r][6]);
+              acc[r][7] = fmaf(xv, wb.w, acc[r][7]);
+            }
+          }
+      }
+    }
+    cbase += v.C;
+  }
+
+  // ---- epilogue: bias + residual + ReLU, channel-split store
+  const int gx = x0 + px;
+  if (gx >= a.W) return;
+  float bv[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) bv[j] = (a.bias != nullptr && co0 + j < a.Cout) ? __ldg(a.bias + co0 + j) : 0.f;
+  const bool vec_res = (a.Cout % 4 == 0);
+#pragma unroll
+  for (int r = 0; r < RP; ++r) {
+    const int gy = y0 + r0 + r;
+    if (gy >= a.H) continue;
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = acc[r][j] + bv[j];
+    if (a.res != nullptr) {
+      const float* rp = a.res + (((size_t)b * a.H + gy) * a.W + gx) * a.Cout + co0;
+      if (vec_res) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+          if (co0 + 4 * h < a.Cout) {
+            const float4 q = ldg4(rp + 4 * h);
+            o[4 * h + 0] += q.x; o[4 * h + 1] += q.y; o[4 * h + 2] += q.z; o[4 * h + 3] += q.w;
+          }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (co0 + j < a.Cout) o[j] += __ldg(rp + j);
+      }
+    }
+    if (a.relu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int co = co0 + 4 * h;
+      if (co >= a.Cout) continue;
+      // destination select (channel split)
+      const bool first = co < a.d0.C;
+      const ViewW d = first ? a.d0 : a.d1;
+      const int cd = first ? co : co - a.d0.C;
+      float* dp = d.p + (((size_t)b * d.Hs + (gy + d.oy)) * d.Ws + (gx + d.ox)) * d.C + cd;
+      if ((d.C % 4 == 0) && (a.d0.C % 4 == 0) && (co + 3 < a.Cout)) {
+        *reinterpret_cast<float4*>(dp) = make_float4(o[4 * h], o[4 * h + 1], o[4 * h + 2], o[4 * h + 3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c = co + j;
+          if (c >= a.Cout) continue;
+          const bool f2 = c < a.d0.C;
+          const ViewW d2 = f2 ? a.d0 : a.d1;
+          const int c2 = f2 ? c : c - a.d0.C;
+          d2.p[(((size_t)b * d2.Hs + (gy + d2.oy)) * d2.Ws + (gx + d2.ox)) * d2.C + c2] = o[4 * h + j];
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// wgrad: dw[co][ci][ky][kx] = sum_{b,y,x} g[b,y,x,co] * in[b,y+ky-1,x+kx-1,ci]
+// CTA = (pixel-tile group, 8-channel ci chunk, 8-channel co chunk).  Thread = (ci, co quad, row
+// partition): 36 accumulators (9 taps x 4 co), sliding 3x3 input window along x.
+template <int TW, int TH>
+__global__ void __launch_bounds__(256) conv3x3_wgrad_ffma_kernel(const WgradArgs a) {
+  constexpr int HW_ = TW + 2;
+  constexpr int HH_ = TH + 2;
+  constexpr int PLANE0 = HH_ * HW_;
+  constexpr int PLANE = PLANE0 + ((4 - (PLANE0 % 32)) + 32) % 32;  // PLANE % 32 == 4: 8 planes hit distinct banks
+  constexpr int NPART = 16;
+  constexpr int RED_LD = 8 * 2 * 36 + 1;
+  constexpr int STAGE_F = 8 * PLANE + TH * TW * 8;
+  constexpr int SMEM_F = STAGE_F > 8 * RED_LD ? STAGE_F : 8 * RED_LD;
+  static_assert((8 * PLANE) % 4 == 0, "g_s must stay 16-byte aligned");
+  static_assert(SMEM_F * 4 <= 48 * 1024, "static shared memory budget");
+  __shared__ __align__(16) float smem[SMEM_F];
+  float* in_s = smem;
+  float* g_s = smem + 8 * PLANE;
+  float (*red_s)[RED_LD] = reinterpret_cast<float (*)[RED_LD]>(smem);  // aliases the staging buffers after the main loop
+
+  const int tid = threadIdx.x;
+  const int ci = tid & 7;
+  const int quad = (tid >> 3) & 1;
+  const int part = tid >> 4;  // 0..15
+
+  // which input chunk
+  int cchunk = blockIdx.y;
+  const int nchunk0 = (a.s0.C + 7) / 8;
+  const View v = cchunk < nchunk0 ? a.s0 : a.s1;
+  const int cbase = cchunk < nchunk0 ? 0 : a.s0.C;
+  if (cchunk >= nchunk0) cchunk -= nchunk0;
+  const int c0 = cchunk * 8;
+  const int cc = min(8, v.C - c0);
+  const bool vec = (v.C % 4 == 0);
+  const int co0 = blockIdx.z * 8;
+  const bool gvec = (a.Cout % 4 == 0);
+
+  float acc[9][4];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[t][q] = 0.f;
+
+  for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+    int t = tile;
+    const int tx = t % a.tilesX;
+    t /= a.tilesX;
+    const int ty = t % a.tilesY;
+    const int b = t / a.tilesY;
+    const int x0 = tx * TW, y0 = ty * TH;
+    __syncthreads();
+    for (int i = tid; i < PLANE0; i += 256) {
+      const int hy = i / HW_, hx = i - hy * HW_;
+      const int gy = y0 + hy - 1, gx = x0 + hx - 1;
+      float vals[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) vals[c] = 0.f;
+      if (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W) {
+        const float* p = v.p + (((size_t)b * v.Hs + (gy + v.oy)) * v.Ws + (gx + v.ox)) * v.C + c0;
+        if (vec) {
+          const float4 q0 = ldg4(p);
+          vals[0] = q0.x; vals[1] = q0.y; vals[2] = q0.z; vals[3] = q0.w;
+          if (cc > 4) {
+            const float4 q1 = ldg4(p + 4);
+            vals[4] = q1.x; vals[5] = q1.y; vals[6] = q1.z; vals[7] = q1.w;
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            if (c < cc) vals[c] = __ldg(p + c);
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 8; ++c) in_s[c * PLANE + i] = vals[c];
+    }
+    for (int i = tid; i < TH * TW; i += 256) {
+      const int yy = i / TW, xx = i - yy * TW;
+      const int gy = y0 + yy, gx = x0 + xx;
+      float vals[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) vals[c] = 0.f;
+      if (gy < a.H && gx < a.W) {
+        const float* p = a.g + (((size_t)b * a.H + gy) * a.W + gx) * a.Cout + co0;
+        if (gvec) {
+          const float4 q0 = ldg4(p);
+          vals[0] = q0.x; vals[1] = q0.y; vals[2] = q0.z; vals[3] = q0.w;
+          if (co0 + 4 < a.Cout) {
+            const float4 q1 = ldg4(p + 4);
+            vals[4] = q1.x; vals[5] = q1.y; vals[6] = q1.z; vals[7] = q1.w;
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            if (co0 + c < a.Cout) vals[c] = __ldg(p + c);
+        }
+      }
+      *reinterpret_cast<float4*>(g_s + i * 8) = make_float4(vals[0], vals[1], vals[2], vals[3]);
+      *reinterpret_cast<float4*>(g_s + i * 8 + 4) = make_float4(vals[4], vals[5], vals[6], vals[7]);
+    }
+    __syncthreads();
+    // rows of this partition
+    for (int yy = part; yy < TH; yy += NPART) {
+      const float* ip = in_s + ci * PLANE + yy * HW_;
+      float win[3][3];
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        win[ky][1] = ip[ky * HW_ + 0];
+        win[ky][2] = ip[ky * HW_ + 1];
+      }
+#pragma unroll 4
+      for (int xx = 0; xx < TW; ++xx) {
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+          win[ky][0] = win[ky][1];
+          win[ky][1] = win[ky][2];
+          win[ky][2] = ip[ky * HW_ + xx + 2];
+        }
+        const float4 gv = *reinterpret_cast<const float4*>(g_s + (yy * TW + xx) * 8 + quad * 4);
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            const float xv = win[ky][kx];
+            acc[ky * 3 + kx][0] = fmaf(xv, gv.x, acc[ky * 3 + kx][0]);
+            acc[ky * 3 + kx][1] = fmaf(xv, gv.y, acc[ky * 3 + kx][1]);
+            acc[ky * 3 + kx][2] = fmaf(xv, gv.z, acc[ky * 3 + kx][2]);
+            acc[ky * 3 + kx][3] = fmaf(xv, gv.w, acc[ky * 3 + kx][3]);
+          }
+      }
+    }
+  }
+
+  // ---- reduce the 16 row partitions (two rounds through shared memory), then one atomic per output
+  const int slot = (ci * 2 + quad) * 36;
+  __syncthreads();
+  if (part >= 8) {
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) red_s[part - 8][slot + t * 4 + q] = acc[t][q];
+  }
+  __syncthreads();
+  if (part < 8) {
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[t][q] += red_s[part][slot + t * 4 + q];
+  }
+  __syncthreads();
+  if (part < 8) {
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) red_s[part][slot + t * 4 + q] = acc[t][q];
+  }
+  __syncthreads();
+  for (int i = tid; i < 8 * 2 * 36; i += 256) {
+    float s = 0.f;
+#pragma unroll
+    for (int p = 0; p < 8; ++p) s += red_s[p][i];
+    const int q = i & 3, tap = (i >> 2) % 9, cq = i / 36;
+    const int ci_ = cq >> 1, quad_ = cq & 1;
+    const int co = co0 + quad_ * 4 + q;
+    if (ci_ < cc && co < a.Cout) atomicAdd(a.dw + ((size_t)co * a.Cin + cbase + c0 + ci_) * 9 + tap, s);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_w3x3_kernel(const float* __restrict__ w, float* __restrict__ out, int Cout, int Cin, int transpose) {
+  const int n = Cout * Cin * 9;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int tap = i % 9;
+    const int ci = (i / 9) % Cin;
+    const int co = i / (9 * Cin);
+    const float v = w[i];
+    if (!transpose) {
+      out[((size_t)tap * Cin + ci) * Cout + co] = v;  // [9][Cin][Cout]
+    } else {
+      out[((size_t)(8 - tap) * Cout + co) * Cin + ci] = v;  // [9 flipped][Cout][Cin]
+    }
+  }
+}
+
+__global__ void relu_bwd_bias_kernel(const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ g,
+                                     float* __restrict__ dbias, long long npix, int C, int relu) {
+  // generic scalar version: thread -> channel c = idx % C over a strided set of pixels
+  extern __shared__ float red[];
+  const int c4n = C;  // scalar granularity
+  const long long total = npix * c4n;
+  const long long stride = (long long)gridDim.x * blockDim.x;  // multiple of C by construction
+  float s = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    float v = dy[i];
+    if (relu) v = y[i] > 0.f ? v : 0.f;
+    if (g != nullptr) g[i] = v;
+    s += v;
+  }
+  if (dbias == nullptr) return;
+  red[threadIdx.x] = s;
+  __syncthreads();
+  // threads with equal (threadIdx.x % C) own the same channel
+  if ((int)threadIdx.x < C) {
+    float t = 0.f;
+    for (int j = threadIdx.x; j < (int)blockDim.x; j += C) t += red[j];
+    atomicAdd(dbias + threadIdx.x, t);
+  }
+}
+
+__global__ void relu_bwd_bias_vec4_kernel(const float4* __restrict__ dy, const float4* __restrict__ y, float4* __restrict__ g,
+                                          float* __restrict__ dbias, long long n4, int C4, int relu) {
+  // blockDim.x * gridDim.x is a multiple of C4 => each thread stays on one channel quad
+  __shared__ float4 red[256];
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 v = dy[i];
+    if (relu) {
+      const float4 m = y[i];
+      v.x = m.x > 0.f ? v.x : 0.f;
+      v.y = m.y > 0.f ? v.y : 0.f;
+      v.z = m.z > 0.f ? v.z : 0.f;
+      v.w = m.w > 0.f ? v.w : 0.f;
+    }
+    if (g != nullptr) g[i] = v;
+    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+  }
+  if (dbias == nullptr) return;
+  red[threadIdx.x] = s;
+  __syncthreads();
+  if ((int)threadIdx.x < C4) {
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = threadIdx.x; j < (int)blockDim.x; j += C4) {
+      const float4 r = red[j];
+      t.x += r.x; t.y += r.y; t.z += r.z; t.w += r.w;
+    }
+    atomicAdd(dbias + threadIdx.x * 4 + 0, t.x);
+    atomicAdd(dbias + threadIdx.x * 4 + 1, t.y);
+    atomicAdd(dbias + threadIdx.x * 4 + 2, t.z);
+    atomicAdd(dbias + threadIdx.x * 4 + 3, t.w);
+  }
+}
+
+// host-side launchers ---------------------------------------------------------------------------
+int conv3x3_fwd_ffma(const Conv3x3Args& a0, cudaStream_t st) {
+  Conv3x3Args a = a0;
+  const int cog = cdiv(a.Cout, 8);
+  if (a.W > 16) {
+    a.tilesX = cdiv(a.W, 32); a.tilesY = cdiv(a.H, 32);
+    dim3 grid(a.tilesX * a.tilesY * a.B, cog);
+    conv3x3_ffma_kernel<32, 4, 256><<<grid, 256, 0, st>>>(a);
+  } else if (a.W > 8) {
+    a.tilesX = cdiv(a.W, 16); a.tilesY = cdiv(a.H, 16);
+    dim3 grid(a.tilesX * a.tilesY * a.B, cog);
+    conv3x3_ffma_kernel<16, 2, 128><<<grid, 128, 0, st>>>(a);
+  } else {
+    a.tilesX = cdiv(a.W, 8); a.tilesY = cdiv(a.H, 8);
+    dim3 grid(a.tilesX * a.tilesY * a.B, cog);
+    conv3x3_ffma_kernel<8, 1, 64><<<grid, 64, 0, st>>>(a);
+  }
+  return post_launch("conv3x3_fwd_ffma");
+}
+
+int conv3x3_wgrad_ffma(const WgradArgs& a0, cudaStream_t st) {
+  WgradArgs a = a0;
+  cudaError_t e = cudaMemsetAsync(a.dw, 0, sizeof(float) * (size_t)a.Cout * a.Cin * 9, st);
+  if (e != cudaSuccess) {
+    set_error("conv3x3_wgrad memset: %s", cudaGetErrorString(e));
+    return PU_ERR_CUDA;
+  }
+  const int nci = cdiv(a.s0.C, 8) + ((a.s1.p != nullptr && a.s1.C > 0) ? cdiv(a.s1.C, 8) : 0);
+  const int nco = cdiv(a.Cout, 8);
+  if (a.W > 16) {
+    a.tilesX = cdiv(a.W, 32); a.tilesY = cdiv(a.H, 16);
+    a.ntiles = a.tilesX * a.tilesY * a.B;
+    const int gx = max(1, min(a.ntiles, (4 * kNumSMs) / max(1, nci * nco)));
+    dim3 grid(gx, nci, nco);
+    conv3x3_wgrad_ffma_kernel<32, 16><<<grid, 256, 0, st>>>(a);
+  } else {
+    a.tilesX = cdiv(a.W, 16); a.tilesY = cdiv(a.H, 16);
+    a.ntiles = a.tilesX * a.tilesY * a.B;
+    const int gx = max(1, min(a.ntiles, (8 * kNumSMs) / max(1, nci * nco)));
+    dim3 grid(gx, nci, nco);
+    conv3x3_wgrad_ffma_kernel<16, 16><<<grid, 256, 0, st>>>(a);
+  }
+  return post_launch("conv3x3_wgrad_ffma");
+}
+
+}  // namespace pu
+
+extern "C" {
+
+int pu_pack_w3x3(const float* w, float* out, int Cout, int Cin, int transpose, void* stream) {
+  PU_REQUIRE(w && out && Cout > 0 && Cin > 0, PU_ERR_BAD_ARG, "pu_pack_w3x3: bad argument");
+  const int n = Cout * Cin * 9;
+  pu::pack_w3x3_kernel<<<pu::cdiv(n, 256) > 592 ? 592 : pu::cdiv(n, 256), 256, 0, pu::as_stream(stream)>>>(w, out, Cout, Cin, transpose);
+  return pu::post_launch("pu_pack_w3x3");
+}
+
+int pu_relu_bwd_bias(const float* dy, const float* y, float* g, float* dbias, long long npix, int C, int relu, void* stream) {
+  PU_REQUIRE(dy && npix > 0 && C > 0 && (y || !relu), PU_ERR_BAD_ARG, "pu_relu_bwd_bias: bad argument");
+  PU_REQUIRE(g || dbias, PU_ERR_BAD_ARG, "pu_relu_bwd_bias: nothing to compute");
+  cudaStream_t st = pu::as_stream(stream);
+  if (dbias) {
+    cudaError_t e = cudaMemsetAsync(dbias, 0, sizeof(float) * C, st);
+    if (e != cudaSuccess) {
+      pu::set_error("pu_relu_bwd_bias memset: %s", cudaGetErrorString(e));
+      return PU_ERR_CUDA;
+    }
+  }
+  const bool pow2 = (C & (C - 1)) == 0;
+  if (C % 4 == 0 && pow2 && C / 4 <= 256 && pu::aligned16(dy) && (!y || pu::aligned16(y)) && (!g || pu::aligned16(g))) {
+    const long long n4 = npix * (C / 4);
+    int grid = (int)((n4 + 256 * 8 - 1) / (256 * 8));
+    grid = grid < 1 ? 1 : (grid > 8 * pu::kNumSMs ? 8 * pu::kNumSMs : grid);
+    pu::relu_bwd_bias_vec4_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const float4*>(dy), reinterpret_cast<const float4*>(y),
+                                                        reinterpret_cast<float4*>(g), dbias, n4, C / 4, relu);
+  } else {
+    // block size = multiple of C so that a thread keeps its channel
+    PU_REQUIRE(C <= 1024, PU_ERR_UNSUPPORTED, "pu_relu_bwd_bias: C=%d > 1024 with ragged channel count", C);
+    int bs = (256 / C) * C;
+    if (bs == 0) bs = C;
+    const long long total = npix * C;
+    int grid = (int)((total + (long long)bs * 8 - 1) / ((long long)bs * 8));
+    grid = grid < 1 ? 1 : (grid > 8 * pu::kNumSMs ? 8 * pu::kNumSMs : grid);
+    pu::relu_bwd_bias_kernel<<<grid, bs, bs * sizeof(float), st>>>(dy, y, g, dbias, npix, C, relu);
+  }
+  return pu::post_launch("pu_relu_bwd_bias");
+}
+
+}  // extern "C"

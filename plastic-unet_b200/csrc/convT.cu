@@ -1,0 +1,404 @@
+// convT.cu — transposed convolutions of the decoder (NHWC fp32), sm_100a CUDA-core kernels.
+//   2x2 stride 2 (reference unet_p.py:155):    a per-pixel [Cin]->[4*Cout] product + pixel-shuffle store.
+//   3x3 stride 2 pad 0 (unet_p_res.py:207):    gather form over the (2H+1)x(2W+1) output, with the
+//                                              F.pad crop (unet_p_res.py:215-217) fused as a window.
+// These are ~4 % of the model FLOPs; they are written for coalesced NHWC traffic,
+// weights staged in shared memory per 8-channel output block.
+#include "pu_common.cuh"
+
+namespace pu {
+
+// ---------------- 2x2 stride 2 -----------------------------------------------------------------
+// thread = (output pixel, block of 8 co).  w is [Cin][Cout][2][2].
+__global__ void convT2x2_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                                    float* __restrict__ y, int B, int H, int W, int Cin, int Cout) {
+  extern __shared__ float ws[];  // [4][Cin][8]
+  const int co0 = blockIdx.y * 8;
+  for (int i = threadIdx.x; i < 4 * Cin * 8; i += blockDim.x) {
+    const int j = i & 7, ci = (i >> 3) % Cin, ac = i / (8 * Cin);
+    ws[i] = (co0 + j < Cout) ? w[((size_t)ci * Cout + co0 + j) * 4 + ac] : 0.f;
+  }
+  __syncthreads();
+  const int Ho = 2 * H, Wo = 2 * W;
+  const long long npix = (long long)B * Ho * Wo;
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npix) return;
+  const int ox = (int)(p % Wo);
+  const int oy = (int)((p / Wo) % Ho);
+  const int b = (int)(p / ((long long)Wo * Ho));
+  const int ac = (oy & 1) * 2 + (ox & 1);
+  const float* xp = x + (((size_t)b * H + (oy >> 1)) * W + (ox >> 1)) * Cin;
+  const float* wp = ws + ac * Cin * 8;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = (bias != nullptr && co0 + j < Cout) ? bias[co0 + j] : 0.f;
+  if (Cin % 4 == 0) {
+    for (int c = 0; c < Cin; c += 4) {
+      const float4 v = ldg4(xp + c);
+      const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(vv[u], wp[(c + u) * 8 + j], acc[j]);
+    }
+  } else {
+    for (int c = 0; c < Cin; ++c) {
+      const float v = __ldg(xp + c);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaf(v, wp[c * 8 + j], acc[j]);
+    }
+  }
+  float* yp = y + p * Cout + co0;
+  if (Cout % 4 == 0 && co0 + 8 <= Cout) {
+    *reinterpret_cast<float4*>(yp) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    *reinterpret_cast<float4*>(yp + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (co0 + j < Cout) yp[j] = acc[j];
+  }
+}
+
+// dx[b,i,j,ci] = sum_{a,c,co} dy[b,2i+a,2j+c,co] w[ci][co][a][c];  thread = (input pixel, block of 8 ci)
+__global__ void convT2x2_dx_kernel(const float* __restrict__ dy, const float* __restrict__ w, float* __restrict__ dx,
+                                   int B, int H, int W, int Cin, int Cout) {
+  extern __shared__ float ws[];  // [4][Cout][8 ci]
+  const int ci0 = blockIdx.y * 8;
+  for (int i = threadIdx.x; i < 4 * Cout * 8; i += blockDim.x) {
+    const int j = i & 7, co = (i >> 3) % Cout, ac = i / (8 * Cout);
+    ws[i] = (ci0 + j < Cin) ? w[((size_t)(ci0 + j) * Cout + co) * 4 + ac] : 0.f;
+  }
+  __syncthreads();
+  const long long npix = (long long)B * H * W;
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npix) return;
+  const int jx = (int)(p % W);
+  const int iy = (int)((p / W) % H);
+  const int b = (int)(p / ((long long)W * H));
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (int ac = 0; ac < 4; ++ac) {
+    const float* gp = dy + (((size_t)b * 2 * H + 2 * iy + (ac >> 1)) * 2 * W + 2 * jx + (ac & 1)) * Cout;
+    const float* wp = ws + ac * Cout * 8;
+    for (int co = 0; co < Cout; ++co) {
+      const float v = __ldg(gp + co);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaf(v, wp[co * 8 + j], acc[j]);
+    }
+  }
+  float* dp = dx + p * Cin + ci0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if (ci0 + j < Cin) dp[j] = acc[j];
+}
+
+// dw[ci][co][a][c] = sum_{b,i,j} x[b,i,j,ci] dy[b,2i+a,2j+c,co]; one thread per output element,
+// pixel range split over blockIdx.y, fp32 atomics into the pre-zeroed dw.
+__global__ void convT2x2_dw_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw,
+                                   int B, int H, int W, int Cin, int Cout) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nout = Cin * Cout * 4;
+  if (e >= nout) return;
+  // element order chosen so that adjacent threads read adjacent co of dy: e = ((ci*4 + ac)*Cout + co)
+  const int co = e % Cout;
+  const int ac = (e / Cout) & 3;
+  const int ci = e / (4 * Cout);
+  const long long npix = (long long)B * H * W;
+  const long long per = (npix + gridDim.y - 1) / gridDim.y;
+  const long long p0 = (long long)blockIdx.y * per;
+  const long long p1 = p0 + per < npix ? p0 + per : npix;
+  float acc = 0.f;
+  for (long long p = p0; p < p1; ++p) {
+    const int jx = (int)(p % W);
+    const int iy = (int)((p / W) % H);
+    const int b = (int)(p / ((long long)W * H));
+    const float xv = __ldg(x + p * Cin + ci);
+    const float gv = __ldg(dy + (((size_t)b * 2 * H + 2 * iy + (ac >> 1)) * 2 * W + 2 * jx + (ac & 1)) * Cout + co);
+    acc = fmaf(xv, gv, acc);
+  }
+  atomicAdd(dw + ((size_t)ci * Cout + co) * 4 + ac, acc);
+}
+
+// ---------------- 3x3 stride 2 pad 0, cropped window ----------------------------------------------
+// thread = (window pixel, block of 8 co).  w is [Cin][Cout][3][3]; full output (fy,fx) = (oy+wy, ox+wx);
+// contributing taps have (fy-ky) even and 0 <= (fy-ky)/2 < H.
+__global__ void convT3x3_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                                    const float* __restrict__ scale, float* __restrict__ y, int B, int H, int W, int Cin, int Cout,
+                                    int Ho, int Wo, int oy, int ox) {
+  extern __shared__ float ws[];  // [9][CK][8], CK = channel chunk
+  constexpr int CK = 32;
+  const int co0 = blockIdx.y * 8;
+  const long long npix = (long long)B * Ho * Wo;
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = p < npix;
+  int wx = 0, wy = 0, b = 0;
+  if (active) {
+    wx = (int)(p % Wo);
+    wy = (int)((p / Wo) % Ho);
+    b = (int)(p / ((long long)Wo * Ho));
+  }
+  const int fy = wy + oy, fx = wx + ox;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (int c0 = 0; c0 < Cin; c0 += CK) {
+    const int cc = min(CK, Cin - c0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 9 * CK * 8; i += blockDim.x) {
+      const int j = i & 7, ci = (i >> 3) % CK, tap = i / (8 * CK);
+      ws[i] = (ci < cc && co0 + j < Cout) ? w[((size_t)(c0 + ci) * Cout + co0 + j) * 9 + tap] : 0.f;
+    }
+    __syncthreads();
+    if (!active) continue;
+    for (int ky = 0; ky < 3; ++ky) {
+      const int ty = fy - ky;
+      if (ty < 0 || (ty & 1) || (ty >> 1) >= H) continue;
+      for (int kx = 0; kx < 3; ++kx) {
+        const int tx = fx - kx;
+        if (tx < 0 || (tx & 1) || (tx >> 1) >= W) continue;
+        const float* xp = x + (((size_t)b * H + (ty >> 1)) * W + (tx >> 1)) * Cin + c0;
+        const float* wp = ws + (ky * 3 + kx) * CK * 8;
+        for (int c = 0; c < cc; ++c) {
+          const float v = __ldg(xp + c);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = fmaf(v, wp[c * 8 + j], acc[j]);
+        }
+      }
+    }
+  }
+  if (!active) return;
+  float* yp = y + p * Cout + co0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    if (co0 + j < Cout) {
+      float v = acc[j] + (bias != nullptr ? bias[co0 + j] : 0.f);
+      if (scale != nullptr) v *= __ldg(scale + (size_t)b * Cout + co0 + j);
+      yp[j] = v;
+    }
+  }
+}
+
+// dx[b,i,j,ci] = sum_{ky,kx,co} dywin[b,2i+ky-oy,2j+kx-ox,co] * s[b,co] * w[ci][co][ky][kx]
+__global__ void convT3x3_dx_kernel(const float* __restrict__ dy, const float* __restrict__ w, const float* __restrict__ scale,
+                                   float* __restrict__ dx, int B, int H, int W, int Cin, int Cout, int Ho, int Wo, int oy, int ox) {
+  extern __shared__ float ws[];  // [9][CK co][8 ci]
+  constexpr int CK = 32;
+  const int ci0 = blockIdx.y * 8;
+  const long long npix = (long long)B * H * W;
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = p < npix;
+  int jx = 0, iy = 0, b = 0;
+  if (active) {
+    jx = (int)(p % W);
+    iy = (int)((p / W) % H);
+    b = (int)(p / ((long long)W * H));
+  }
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (int c0 = 0; c0 < Cout; c0 += CK) {
+    const int cc = min(CK, Cout - c0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 9 * CK * 8; i += blockDim.x) {
+      const int j = i & 7, co = (i >> 3) % CK, tap = i / (8 * CK);
+      ws[i] = (co < cc && ci0 + j < Cin) ? w[((size_t)(ci0 + j) * Cout + c0 + co) * 9 + tap] : 0.f;
+    }
+    __syncthreads();
+    if (!active) continue;
+    for (int ky = 0; ky < 3; ++ky) {
+      const int wy = 2 * iy + ky - oy;
+      if (wy < 0 || wy >= Ho) continue;
+      for (int kx = 0; kx < 3; ++kx) {
+        const int wx = 2 * jx + kx - ox;
+        if (wx < 0 || wx >= Wo) continue;
+        const float* gp = dy + (((size_t)b * Ho + wy) * Wo + wx) * Cout + c0;
+        const float* sp = scale != nullptr ? scale + (size_t)b * Cout + c0 : nullptr;
+        const float* wp = ws + (ky * 3 + kx) * CK * 8;
+        for (int c = 0; c < cc; ++c) {
+          float v = __ldg(gp + c);
+          if (sp != nullptr) v *= __ldg(sp + c);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = fmaf(v, wp[c * 8 + j], acc[j]);
+        }
+      }
+    }
+  }
+  if (!active) return;
+  float* dp = dx + p * Cin + ci0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if (ci0 + j < Cin) dp[j] = acc[j];
+}
+
+// dw[ci][co][ky][kx] = sum_{b,i,j} x[b,i,j,ci] * dywin[b,2i+ky-oy,2j+kx-ox,co]*s[b,co]
+// thread = output element e = ((ci*9 + tap)*Cout + co); input-pixel range split over blockIdx.y.
+__global__ void convT3x3_dw_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ scale,
+                                   float* __restrict__ dw, int B, int H, int W, int Cin, int Cout, int Ho, int Wo, int oy, int ox) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long nout = (long long)Cin * Cout * 9;
+  if (e >= nout) return;
+  const int co = (int)(e % Cout);
+  const int tap = (int)((e / Cout) % 9);
+  const int ci = (int)(e / (9LL * Cout));
+  const int ky = tap / 3, kx = tap - ky * 3;
+  const long long npix = (long long)B * H * W;
+  const long long per = (npix + gridDim.y - 1) / gridDim.y;
+  const long long p0 = (long long)blockIdx.y * per;
+  const long long p1 = p0 + per < npix ? p0 + per : npix;
+  float acc = 0.f;
+  for (long long p = p0; p < p1; ++p) {
+    const int jx = (int)(p % W);
+    const int iy = (int)((p / W) % H);
+    const int b = (int)(p / ((long long)W * H));
+    const int wy = 2 * iy + ky - oy, wx = 2 * jx + kx - ox;
+    if (wy < 0 || wy >= Ho || wx < 0 || wx >= Wo) continue;
+    float gv = __ldg(dy + (((size_t)b * Ho + wy) * Wo + wx) * Cout + co);
+    if (scale != nullptr) gv *= __ldg(scale + (size_t)b * Cout + co);
+    acc = fmaf(__ldg(x + p * Cin + ci), gv, acc);
+  }
+  atomicAdd(dw + ((size_t)ci * Cout + co) * 9 + tap, acc);
+}
+
+// db[co] = sum_{b,pixels} dy[b,p,co] * s[b,co]
+__global__ void bias_grad_scaled_kernel(const float* __restrict__ dy, const float* __restrict__ scale, float* __restrict__ db,
+                                        int B, long long hw, int C) {
+  // block handles a slab of pixels; thread -> channel (threadIdx.x % C), sub-stream threadIdx.x / C
+  extern __shared__ float red[];
+  const int c = threadIdx.x % C;
+  const int sub = threadIdx.x / C;
+  const int nsub = blockDim.x / C;
+  const long long npix = (long long)B * hw;
+  float acc = 0.f;
+  if (sub < nsub) {
+    for (long long p = (long long)blockIdx.x * nsub + sub; p < npix; p += (long long)gridDim.x * nsub) {
+      float v = __ldg(dy + p * C + c);
+      if (scale != nullptr) v *= __ldg(scale + (p / hw) * C + c);
+      acc += v;
+    }
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  if (sub == 0) {
+    float s = 0.f;
+    for (int u = 0; u < nsub; ++u) s += red[u * C + c];
+    atomicAdd(db + c, s);
+  }
+}
+
+static int launch_bias_grad(const float* dy, const float* scale, float* db, int B, long long hw, int C, cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(db, 0, sizeof(float) * C, st);
+  if (e != cudaSuccess) {
+    set_error("bias_grad memset: %s", cudaGetErrorString(e));
+    return PU_ERR_CUDA;
+  }
+  PU_REQUIRE(C <= 1024, PU_ERR_UNSUPPORTED, "bias_grad: C=%d > 1024", C);
+  int bs = C >= 256 ? C : (256 / C) * C;
+  const int nsub = bs / C;
+  const long long npix = (long long)B * hw;
+  long long blocks = (npix + (long long)nsub * 32 - 1) / ((long long)nsub * 32);
+  if (blocks < 1) blocks = 1;
+  if (blocks > 4 * kNumSMs) blocks = 4 * kNumSMs;
+  bias_grad_scaled_kernel<<<(unsigned)blocks, bs, bs * sizeof(float), st>>>(dy, scale, db, B, hw, C);
+  return post_launch("bias_grad");
+}
+
+static int split_for(long long nout_blocks, long long npix) {
+  long long want = (4LL * kNumSMs + nout_blocks - 1) / nout_blocks;
+  if (want < 1) want = 1;
+  long long maxsplit = (npix + 15) / 16;  // at least 16 pixels per split
+  if (maxsplit < 1) maxsplit = 1;
+  if (want > maxsplit) want = maxsplit;
+  if (want > 65535) want = 65535;
+  return (int)want;
+}
+
+}  // namespace pu
+
+extern "C" {
+
+int pu_convT2x2s2_fwd(const float* x, const float* w, const float* bias, float* y, int B, int H, int W, int Cin, int Cout, void* stream) {
+  PU_REQUIRE(x && w && y && B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, PU_ERR_BAD_ARG, "pu_convT2x2s2_fwd: bad argument");
+  const size_t smem = (size_t)4 * Cin * 8 * sizeof(float);
+  PU_REQUIRE(smem <= 48 * 1024, PU_ERR_UNSUPPORTED, "pu_convT2x2s2_fwd: Cin=%d > 384", Cin);
+  PU_REQUIRE(pu::aligned16(x) && pu::aligned16(y), PU_ERR_BAD_ARG, "pu_convT2x2s2_fwd: pointers not 16-byte aligned");
+  const long long npix = (long long)B * 4 * H * W;
+  dim3 grid((unsigned)((npix + 255) / 256), pu::cdiv(Cout, 8));
+  pu::convT2x2_fwd_kernel<<<grid, 256, smem, pu::as_stream(stream)>>>(x, w, bias, y, B, H, W, Cin, Cout);
+  return pu::post_launch("pu_convT2x2s2_fwd");
+}
+
+int pu_convT2x2s2_bwd(const float* x, const float* w, const float* dy, float* dx, float* dw, float* db, int B, int H, int W,
+                      int Cin, int Cout, void* stream) {
+  PU_REQUIRE(x && w && dy && B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, PU_ERR_BAD_ARG, "pu_convT2x2s2_bwd: bad argument");
+  cudaStream_t st = pu::as_stream(stream);
+  const long long npix = (long long)B * H * W;
+  if (dx != nullptr) {
+    const size_t smem = (size_t)4 * Cout * 8 * sizeof(float);
+    PU_REQUIRE(smem <= 48 * 1024, PU_ERR_UNSUPPORTED, "pu_convT2x2s2_bwd: Cout=%d > 384", Cout);
+    dim3 grid((unsigned)((npix + 255) / 256), pu::cdiv(Cin, 8));
+    pu::convT2x2_dx_kernel<<<grid, 256, smem, st>>>(dy, w, dx, B, H, W, Cin, Cout);
+    int rc = pu::post_launch("pu_convT2x2s2_bwd dx");
+    if (rc) return rc;
+  }
+  if (dw != nullptr) {
+    const int nout = Cin * Cout * 4;
+    cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * nout, st);
+    if (e != cudaSuccess) {
+      pu::set_error("pu_convT2x2s2_bwd memset: %s", cudaGetErrorString(e));
+      return PU_ERR_CUDA;
+    }
+    const int nb = pu::cdiv(nout, 256);
+    dim3 grid(nb, pu::split_for(nb, npix));
+    pu::convT2x2_dw_kernel<<<grid, 256, 0, st>>>(x, dy, dw, B, H, W, Cin, Cout);
+    int rc = pu::post_launch("pu_convT2x2s2_bwd dw");
+    if (rc) return rc;
+  }
+  if (db != nullptr) return pu::launch_bias_grad(dy, nullptr, db, B, 4LL * H * W, Cout, st);
+  return PU_OK;
+}
+
+int pu_convT3x3s2_fwd(const float* x, const float* w, const float* bias, const float* chan_scale, float* y, int B, int H, int W,
+                      int Cin, int Cout, int Ho, int Wo, int oy, int ox, void* stream) {
+  PU_REQUIRE(x && w && y && B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, PU_ERR_BAD_ARG, "pu_convT3x3s2_fwd: bad argument");
+  PU_REQUIRE(oy >= 0 && ox >= 0 && Ho > 0 && Wo > 0 && oy + Ho <= 2 * H + 1 && ox + Wo <= 2 * W + 1, PU_ERR_BAD_ARG,
+             "pu_convT3x3s2_fwd: window (%d+%d,%d+%d) exceeds %dx%d", oy, Ho, ox, Wo, 2 * H + 1, 2 * W + 1);
+  const size_t smem = (size_t)9 * 32 * 8 * sizeof(float);
+  const long long npix = (long long)B * Ho * Wo;
+  dim3 grid((unsigned)((npix + 127) / 128), pu::cdiv(Cout, 8));
+  pu::convT3x3_fwd_kernel<<<grid, 128, smem, pu::as_stream(stream)>>>(x, w, bias, chan_scale, y, B, H, W, Cin, Cout, Ho, Wo, oy, ox);
+  return pu::post_launch("pu_convT3x3s2_fwd");
+}
+
+int pu_convT3x3s2_bwd(const float* x, const float* w, const float* dy, const float* chan_scale, float* dx, float* dw, float* db,
+                      int B, int H, int W, int Cin, int Cout, int Ho, int Wo, int oy, int ox, void* stream) {
+  PU_REQUIRE(x && w && dy && B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, PU_ERR_BAD_ARG, "pu_convT3x3s2_bwd: bad argument");
+  PU_REQUIRE(oy >= 0 && ox >= 0 && Ho > 0 && Wo > 0 && oy + Ho <= 2 * H + 1 && ox + Wo <= 2 * W + 1, PU_ERR_BAD_ARG,
+             "pu_convT3x3s2_bwd: window exceeds output");
+  cudaStream_t st = pu::as_stream(stream);
+  const long long npix = (long long)B * H * W;
+  if (dx != nullptr) {
+    const size_t smem = (size_t)9 * 32 * 8 * sizeof(float);
+    dim3 grid((unsigned)((npix + 127) / 128), pu::cdiv(Cin, 8));
+    pu::convT3x3_dx_kernel<<<grid, 128, smem, st>>>(dy, w, chan_scale, dx, B, H, W, Cin, Cout, Ho, Wo, oy, ox);
+    int rc = pu::post_launch("pu_convT3x3s2_bwd dx");
+    if (rc) return rc;
+  }
+  if (dw != nullptr) {
+    const long long nout = (long long)Cin * Cout * 9;
+    cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * nout, st);
+    if (e != cudaSuccess) {
+      pu::set_error("pu_convT3x3s2_bwd memset: %s", cudaGetErrorString(e));
+      return PU_ERR_CUDA;
+    }
+    const long long nb = (nout + 255) / 256;
+    dim3 grid((unsigned)nb, pu::split_for(nb, npix));
+    pu::convT3x3_dw_kernel<<<grid, 256, 0, st>>>(x, dy, chan_scale, dw, B, H, W, Cin, Cout, Ho, Wo, oy, ox);
+    int rc = pu::post_launch("pu_convT3x3s2_bwd dw");
+    if (rc) return rc;
+  }
+  if (db != nullptr) return pu::launch_bias_grad(dy, chan_scale, db, B, (long long)Ho * Wo, Cout, st);
+  return PU_OK;
+}
+
+}  // extern "C"

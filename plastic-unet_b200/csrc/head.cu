@@ -1,0 +1,333 @@
+// head.cu — the plastic output head and its Hebb / Oja trace (reference unet_p.py:70-88 ==
+// unet_p_res.py:116-134), batched over B maps of N x N.
+//
+//   Weff = w + alpha*hebb ; A = X @ Weff ; S = sigmoid(A)                       (forward)
+//   gA = gS*S*(1-S) ; gX = gA @ Weff^T ; gWeff = X^T @ gA (split-K) ;
+//   gw = gWeff ; galpha = gWeff*hebb ; ghebb = gWeff*alpha                      (backward)
+//   trace: out = decay*hebb + eta/K * pre^T @ post, decay = 1-eta (Hebb) or 1 - eta*q_j/K (Oja),
+//          one fused pass (contraction + epilogue), exactly the reference at K == 1.
+//
+// The GEMMs are strict-fp32 shared-memory-tiled FFMA kernels (64x64x16 tiles, 4x4 per thread):
+// the head is < 1 % of the step (N^3 MACs) and its logits decide the
+// thresholded masks, so it stays in full fp32.
+#include "pu_common.cuh"
+
+namespace pu {
+
+enum { EPI_STORE = 0, EPI_SIGMOID = 1, EPI_ATOMIC = 2 };
+
+// C[M,N] (row-major, ldc) (+)= sum_k A(m,k) B(k,n), A(m,k) = A[m*sam + k*sak], B(k,n) = B[k*sbk + n*sbn]
+template <int EPI>
+__global__ void __launch_bounds__(256) gemm_ffma_kernel(const float* __restrict__ A, long long sam, long long sak,
+                                                        const float* __restrict__ Bm, long long sbk, long long sbn,
+                                                        float* __restrict__ C, long long ldc, int M, int N, int K, int kper) {
+  constexpr int BM = 64, BN = 64, BK = 16;
+  __shared__ __align__(16) float As[BK][BM + 4];
+  __shared__ __align__(16) float Bs[BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int m_blk = blockIdx.y * BM, n_blk = blockIdx.x * BN;
+  const int k_begin = blockIdx.z * kper;
+  const int k_end = min(K, k_begin + kper);
+  const int tx = tid & 15, ty = tid >> 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = k_begin; k0 < k_end; k0 += BK) {
+    // A tile
+#pragma unroll
+    for (int r = 0; r < (BM * BK) / 256; ++r) {
+      const int i = tid + r * 256;
+      int m, k;
+      if (sak == 1) { m = i / BK; k = i % BK; } else { k = i / BM; m = i % BM; }
+      const int gm = m_blk + m, gk = k0 + k;
+      As[k][m] = (gm < M && gk < k_end) ? __ldg(A + gm * sam + gk * sak) : 0.f;
+    }
+#pragma unroll
+    for (int r = 0; r < (BN * BK) / 256; ++r) {
+      const int i = tid + r * 256;
+      int n, k;
+      if (sbk == 1) { n = i / BK; k = i % BK; } else { k = i / BN; n = i % BN; }
+      const int gn = n_blk + n, gk = k0 + k;
+      Bs[k][n] = (gn < N && gk < k_end) ? __ldg(Bm + gk * sbk + gn * sbn) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int gm = m_blk + ty * 4 + i;
+    if (gm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gn = n_blk + tx * 4 + j;
+      if (gn >= N) continue;
+      float v = acc[i][j];
+      if (EPI == EPI_SIGMOID) v = 1.f / (1.f + expf(-v));
+      if (EPI == EPI_ATOMIC) atomicAdd(C + gm * ldc + gn, v);
+      else C[gm * ldc + gn] = v;
+    }
+  }
+}
+
+__global__ void weff_kernel(const float* __restrict__ w, const float* __restrict__ alpha, const float* __restrict__ hebb,
+                            float* __restrict__ weff, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) weff[i] = fmaf(alpha[i], hebb[i], w[i]);
+}
+
+__global__ void sigmoid_bwd_kernel(const float* __restrict__ S, const float* __restrict__ gS, float* __restrict__ gA, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float s = S[i];
+    gA[i] = gS[i] * s * (1.f - s);
+  }
+}
+
+__global__ void head_param_grads_kernel(const float* __restrict__ gw, const float* __restrict__ alpha, const float* __restrict__ hebb,
+                                        float* __restrict__ galpha, float* __restrict__ ghebb, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float g = gw[i];
+  if (galpha != nullptr) galpha[i] = g * hebb[i];
+  if (ghebb != nullptr) ghebb[i] = g * alpha[i];
+}
+
+// ---- trace --------------------------------------------------------------------------------------
+// mode 0: fused update (out = decay*hebb + eta/K*delta); mode 1: write delta_q only (DP split form)
+__global__ void trace_contract_kernel(const float* __restrict__ hebb, const float* __restrict__ pre, const float* __restrict__ post,
+                                      long long ld, int K, const float* __restrict__ eta_p, int rule, float* __restrict__ out,
+                                      float* __restrict__ delta_q, int N, int Kdiv, int mode) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.y * blockDim.y + threadIdx.y;
+  if (i >= N || j >= N) return;
+  float d = 0.f, q = 0.f;
+  for (int k = 0; k < K; ++k) {
+    const float a = __ldg(pre + k * ld + i);
+    const float b = __ldg(post + k * ld + j);
+    d = fmaf(a, b, d);
+    q = fmaf(b, b, q);
+  }
+  if (mode == 1) {
+    delta_q[(size_t)i * N + j] = d;
+    if (i == 0) delta_q[(size_t)N * N + j] = q;
+    return;
+  }
+  const float eta = __ldg(eta_p);
+  const float invK = 1.f / (float)Kdiv;
+  const float h = hebb[(size_t)i * N + j];
+  const float decay = rule == PU_RULE_HEBB ? 1.f - eta : 1.f - eta * q * invK;
+  out[(size_t)i * N + j] = fmaf(decay, h, eta * d * invK);
+}
+
+__global__ void trace_apply_kernel(const float* __restrict__ hebb, const float* __restrict__ delta_q, int Kdiv,
+                                   const float* __restrict__ eta_p, int rule, float* __restrict__ out, int N) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.y * blockDim.y + threadIdx.y;
+  if (i >= N || j >= N) return;
+  const float eta = __ldg(eta_p);
+  const float invK = 1.f / (float)Kdiv;
+  const float d = delta_q[(size_t)i * N + j];
+  const float q = delta_q[(size_t)N * N + j];
+  const float h = hebb[(size_t)i * N + j];
+  const float decay = rule == PU_RULE_HEBB ? 1.f - eta : 1.f - eta * q * invK;
+  out[(size_t)i * N + j] = fmaf(decay, h, eta * d * invK);
+}
+
+// backward, part 1: ghebb and geta
+__global__ void trace_bwd_hebb_eta_kernel(const float* __restrict__ hebb, const float* __restrict__ pre, const float* __restrict__ post,
+                                          long long ld, int K, const float* __restrict__ eta_p, int rule, const float* __restrict__ D,
+                                          float* __restrict__ ghebb, float* __restrict__ geta, int N) {
+  __shared__ float red[8];
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.y * blockDim.y + threadIdx.y;
+  float contrib = 0.f;
+  if (i < N && j < N) {
+    float d = 0.f, q = 0.f;
+    for (int k = 0; k < K; ++k) {
+      const float a = __ldg(pre + k * ld + i);
+      const float b = __ldg(post + k * ld + j);
+      d = fmaf(a, b, d);
+      q = fmaf(b, b, q);
+    }
+    const float eta = __ldg(eta_p);
+    const float invK = 1.f / (float)K;
+    const float h = hebb[(size_t)i * N + j];
+    const float g = D[(size_t)i * N + j];
+    const float decay = rule == PU_RULE_HEBB ? 1.f - eta : 1.f - eta * q * invK;
+    if (ghebb != nullptr) ghebb[(size_t)i * N + j] = g * decay;
+    contrib = rule == PU_RULE_HEBB ? g * (d * invK - h) : g * (d * invK - h * q * invK);
+  }
+  if (geta == nullptr) return;
+  contrib = warp_sum(contrib);
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  if ((tid & 31) == 0) red[tid >> 5] = contrib;
+  __syncthreads();
+  if (tid == 0) {
+    float s = 0.f;
+    for (int u = 0; u < (int)(blockDim.x * blockDim.y) / 32; ++u) s += red[u];
+    atomicAdd(geta, s);
+  }
+}
+
+// gpre[k][i] = eta/K * sum_j D[i][j] post[k][j]
+__global__ void trace_bwd_pre_kernel(const float* __restrict__ post, long long ld, int K, const float* __restrict__ eta_p,
+                                     const float* __restrict__ D, float* __restrict__ gpre, int N) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = blockIdx.y;
+  if (i >= N) return;
+  float s = 0.f;
+  for (int j = 0; j < N; ++j) s = fmaf(__ldg(D + (size_t)i * N + j), __ldg(post + k * ld + j), s);
+  gpre[(size_t)k * N + i] = __ldg(eta_p) / (float)K * s;
+}
+
+// gpost[k][j] = eta/K * sum_i D[i][j] * (pre[k][i] - (oja ? 2*hebb[i][j]*post[k][j] : 0))
+__global__ void trace_bwd_post_kernel(const float* __restrict__ hebb, const float* __restrict__ pre, const float* __restrict__ post,
+                                      long long ld, int K, const float* __restrict__ eta_p, int rule, const float* __restrict__ D,
+                                      float* __restrict__ gpost, int N) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = blockIdx.y;
+  if (j >= N) return;
+  const float pj = __ldg(post + k * ld + j);
+  float s = 0.f;
+  for (int i = 0; i < N; ++i) {
+    const float g = __ldg(D + (size_t)i * N + j);
+    float t = __ldg(pre + k * ld + i);
+    if (rule == PU_RULE_OJA) t -= 2.f * __ldg(hebb + (size_t)i * N + j) * pj;
+    s = fmaf(g, t, s);
+  }
+  gpost[(size_t)k * N + j] = __ldg(eta_p) / (float)K * s;
+}
+
+}  // namespace pu
+
+extern "C" {
+
+int pu_plastic_head_fwd(const float* X, const float* w, const float* alpha, const float* hebb, float* weff_out, float* S, int B,
+                        int N, void* stream) {
+  PU_REQUIRE(X && w && alpha && hebb && weff_out && S && B > 0 && N > 0, PU_ERR_BAD_ARG, "pu_plastic_head_fwd: bad argument");
+  cudaStream_t st = pu::as_stream(stream);
+  pu::weff_kernel<<<pu::cdiv((long long)N * N, 256), 256, 0, st>>>(w, alpha, hebb, weff_out, N * N);
+  int rc = pu::post_launch("pu_plastic_head_fwd weff");
+  if (rc) return rc;
+  const int M = B * N;
+  dim3 grid(pu::cdiv(N, 64), pu::cdiv(M, 64), 1);
+  PU_REQUIRE(grid.y <= 65535, PU_ERR_UNSUPPORTED, "pu_plastic_head_fwd: B*N too large");
+  pu::gemm_ffma_kernel<pu::EPI_SIGMOID><<<grid, 256, 0, st>>>(X, N, 1, weff_out, N, 1, S, N, M, N, N, N);
+  return pu::post_launch("pu_plastic_head_fwd gemm");
+}
+
+int pu_plastic_head_bwd(const float* X, const float* S, const float* gS, const float* weff, const float* alpha, const float* hebb,
+                        float* gA_ws, float* gX, float* gw, float* galpha, float* ghebb, int B, int N, void* stream) {
+  PU_REQUIRE(X && S && gS && weff && alpha && hebb && gA_ws && gw && B > 0 && N > 0, PU_ERR_BAD_ARG, "pu_plastic_head_bwd: bad argument");
+  cudaStream_t st = pu::as_stream(stream);
+  const int M = B * N;
+  const long long n = (long long)M * N;
+  int g = (int)((n + 1023) / 1024);
+  g = g < 1 ? 1 : (g > 16 * pu::kNumSMs ? 16 * pu::kNumSMs : g);
+  pu::sigmoid_bwd_kernel<<<g, 256, 0, st>>>(S, gS, gA_ws, n);
+  int rc = pu::post_launch("pu_plastic_head_bwd gA");
+  if (rc) return rc;
+  if (gX != nullptr) {
+    dim3 grid(pu::cdiv(N, 64), pu::cdiv(M, 64), 1);
+    // gX[m][n] = sum_k gA[m][k] * weff[n][k]
+    pu::gemm_ffma_kernel<pu::EPI_STORE><<<grid, 256, 0, st>>>(gA_ws, N, 1, weff, 1, N, gX, N, M, N, N, N);
+    rc = pu::post_launch("pu_plastic_head_bwd gX");
+    if (rc) return rc;
+  }
+  cudaError_t e = cudaMemsetAsync(gw, 0, sizeof(float) * N * N, st);
+  if (e != cudaSuccess) {
+    pu::set_error("pu_plastic_head_bwd memset: %s", cudaGetErrorString(e));
+    return PU_ERR_CUDA;
+  }
+  {
+    // gW[i][j] = sum_m X[m][i] * gA[m][j], split over m
+    const int tiles = pu::cdiv(N, 64) * pu::cdiv(N, 64);
+    int splits = (2 * pu::kNumSMs + tiles - 1) / tiles;
+    int kper = (M + splits - 1) / splits;
+    kper = ((kper + 15) / 16) * 16;
+    splits = (M + kper - 1) / kper;
+    dim3 grid(pu::cdiv(N, 64), pu::cdiv(N, 64), splits);
+    pu::gemm_ffma_kernel<pu::EPI_ATOMIC><<<grid, 256, 0, st>>>(X, 1, N, gA_ws, N, 1, gw, N, N, N, M, kper);
+    rc = pu::post_launch("pu_plastic_head_bwd gW");
+    if (rc) return rc;
+  }
+  if (galpha != nullptr || ghebb != nullptr) {
+    pu::head_param_grads_kernel<<<pu::cdiv((long long)N * N, 256), 256, 0, st>>>(gw, alpha, hebb, galpha, ghebb, N * N);
+    rc = pu::post_launch("pu_plastic_head_bwd param grads");
+    if (rc) return rc;
+  }
+  return PU_OK;
+}
+
+int pu_trace_update_fwd(const float* hebb, const float* pre, const float* post, long long ld, int K, const float* eta, int rule,
+                        float* out, int N, void* stream) {
+  PU_REQUIRE(hebb && pre && post && eta && out && K > 0 && N > 0 && ld >= N, PU_ERR_BAD_ARG, "pu_trace_update_fwd: bad argument");
+  PU_REQUIRE(rule == PU_RULE_HEBB || rule == PU_RULE_OJA, PU_ERR_BAD_ARG, "pu_trace_update_fwd: unknown rule %d", rule);
+  dim3 block(32, 8), grid(pu::cdiv(N, 32), pu::cdiv(N, 8));
+  pu::trace_contract_kernel<<<grid, block, 0, pu::as_stream(stream)>>>(hebb, pre, post, ld, K, eta, rule, out, nullptr, N, K, 0);
+  return pu::post_launch("pu_trace_update_fwd");
+}
+
+int pu_trace_delta(const float* pre, const float* post, long long ld, int K, float* delta_q, int N, void* stream) {
+  PU_REQUIRE(pre && post && delta_q && K > 0 && N > 0 && ld >= N, PU_ERR_BAD_ARG, "pu_trace_delta: bad argument");
+  dim3 block(32, 8), grid(pu::cdiv(N, 32), pu::cdiv(N, 8));
+  pu::trace_contract_kernel<<<grid, block, 0, pu::as_stream(stream)>>>(nullptr, pre, post, ld, K, nullptr, 0, nullptr, delta_q, N, K, 1);
+  return pu::post_launch("pu_trace_delta");
+}
+
+int pu_trace_apply(const float* hebb, const float* delta_q, int K_global, const float* eta, int rule, float* out, int N, void* stream) {
+  PU_REQUIRE(hebb && delta_q && eta && out && K_global > 0 && N > 0, PU_ERR_BAD_ARG, "pu_trace_apply: bad argument");
+  PU_REQUIRE(rule == PU_RULE_HEBB || rule == PU_RULE_OJA, PU_ERR_BAD_ARG, "pu_trace_apply: unknown rule %d", rule);
+  dim3 block(32, 8), grid(pu::cdiv(N, 32), pu::cdiv(N, 8));
+  pu::trace_apply_kernel<<<grid, block, 0, pu::as_stream(stream)>>>(hebb, delta_q, K_global, eta, rule, out, N);
+  return pu::post_launch("pu_trace_apply");
+}
+
+int pu_trace_update_bwd(const float* hebb, const float* pre, const float* post, long long ld, int K, const float* eta, int rule,
+                        const float* gout, float* ghebb, float* gpre, float* gpost, float* geta, int N, void* stream) {
+  PU_REQUIRE(hebb && pre && post && eta && gout && K > 0 && N > 0 && ld >= N, PU_ERR_BAD_ARG, "pu_trace_update_bwd: bad argument");
+  PU_REQUIRE(rule == PU_RULE_HEBB || rule == PU_RULE_OJA, PU_ERR_BAD_ARG, "pu_trace_update_bwd: unknown rule %d", rule);
+  PU_REQUIRE(K <= 65535, PU_ERR_UNSUPPORTED, "pu_trace_update_bwd: K=%d > 65535", K);
+  cudaStream_t st = pu::as_stream(stream);
+  int rc;
+  if (ghebb != nullptr || geta != nullptr) {
+    if (geta != nullptr) {
+      cudaError_t e = cudaMemsetAsync(geta, 0, sizeof(float), st);
+      if (e != cudaSuccess) {
+        pu::set_error("pu_trace_update_bwd memset: %s", cudaGetErrorString(e));
+        return PU_ERR_CUDA;
+      }
+    }
+    dim3 block(32, 8), grid(pu::cdiv(N, 32), pu::cdiv(N, 8));
+    pu::trace_bwd_hebb_eta_kernel<<<grid, block, 0, st>>>(hebb, pre, post, ld, K, eta, rule, gout, ghebb, geta, N);
+    rc = pu::post_launch("pu_trace_update_bwd hebb/eta");
+    if (rc) return rc;
+  }
+  if (gpre != nullptr) {
+    dim3 grid(pu::cdiv(N, 128), K);
+    pu::trace_bwd_pre_kernel<<<grid, 128, 0, st>>>(post, ld, K, eta, gout, gpre, N);
+    rc = pu::post_launch("pu_trace_update_bwd pre");
+    if (rc) return rc;
+  }
+  if (gpost != nullptr) {
+    dim3 grid(pu::cdiv(N, 128), K);
+    pu::trace_bwd_post_kernel<<<grid, 128, 0, st>>>(hebb, pre, post, ld, K, eta, rule, gout, gpost, N);
+    rc = pu::post_launch("pu_trace_update_bwd post");
+    if (rc) return rc;
+  }
+  return PU_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,214 @@
+// pool.cu — MaxPool2d(2) (+ fused Dropout2d channel scale) and bilinear x2 upsampling, NHWC fp32.
+// HBM-bound elementwise kernels: one float4 (4 channels) per thread access, grid-stride.
+// reference unet_p.py:139,153; unet_p_res.py:240-253.
+#include "pu_common.cuh"
+
+namespace pu {
+
+// V = 4 (float4 path, C % 4 == 0) or 1 (scalar)
+template <int V>
+__global__ void maxpool2_fwd_kernel(const float* __restrict__ x, const float* __restrict__ scale, float* __restrict__ y,
+                                    int B, int H, int W, int C) {
+  const int Ho = H / 2, Wo = W / 2, CV = C / V;
+  const long long n = (long long)B * Ho * Wo * CV;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % CV);
+    long long p = i / CV;
+    const int ox = (int)(p % Wo);
+    p /= Wo;
+    const int oy = (int)(p % Ho);
+    const int b = (int)(p / Ho);
+    const float* xp = x + (((size_t)b * H + 2 * oy) * W + 2 * ox) * C + cv * V;
+    float m[V];
+#pragma unroll
+    for (int u = 0; u < V; ++u) m[u] = -INFINITY;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const float* q = xp + ((size_t)dy * W + dx) * C;
+        if (V == 4) {
+          const float4 v = ldg4(q);
+          const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int u = 0; u < V; ++u)
+            if (vv[u] > m[u] || vv[u] != vv[u]) m[u] = vv[u];
+        } else {
+          const float v = __ldg(q);
+          if (v > m[0] || v != v) m[0] = v;
+        }
+      }
+    if (scale != nullptr) {
+#pragma unroll
+      for (int u = 0; u < V; ++u) m[u] *= __ldg(scale + (size_t)b * C + cv * V + u);
+    }
+    float* yp = y + i * V;
+    if (V == 4) *reinterpret_cast<float4*>(yp) = make_float4(m[0], m[1 % V], m[2 % V], m[3 % V]);
+    else yp[0] = m[0];
+  }
+}
+
+// one thread per pooling window (and channel vector): recompute the arg-max with ATen's tie-break
+// (first element in (dy,dx) row-major scan that is strictly greater / NaN) and route dy*scale there.
+template <int V>
+__global__ void maxpool2_bwd_kernel(const float* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ dy,
+                                    float* __restrict__ dx, int B, int H, int W, int C) {
+  const int Ho = H / 2, Wo = W / 2, CV = C / V;
+  const long long n = (long long)B * Ho * Wo * CV;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % CV);
+    long long p = i / CV;
+    const int ox = (int)(p % Wo);
+    p /= Wo;
+    const int oy = (int)(p % Ho);
+    const int b = (int)(p / Ho);
+    const size_t base = (((size_t)b * H + 2 * oy) * W + 2 * ox) * C + cv * V;
+    float m[V];
+    int arg[V];
+    float vals[4][V];
+#pragma unroll
+    for (int u = 0; u < V; ++u) { m[u] = -INFINITY; arg[u] = 0; }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float* q = x + base + ((size_t)(k >> 1) * W + (k & 1)) * C;
+      if (V == 4) {
+        const float4 v = ldg4(q);
+        vals[k][0] = v.x; vals[k][1 % V] = v.y; vals[k][2 % V] = v.z; vals[k][3 % V] = v.w;
+      } else {
+        vals[k][0] = __ldg(q);
+      }
+#pragma unroll
+      for (int u = 0; u < V; ++u)
+        if (vals[k][u] > m[u] || vals[k][u] != vals[k][u]) { m[u] = vals[k][u]; arg[u] = k; }
+    }
+    float g[V];
+    if (V == 4) {
+      const float4 v = ldg4(dy + i * V);
+      g[0] = v.x; g[1 % V] = v.y; g[2 % V] = v.z; g[3 % V] = v.w;
+    } else {
+      g[0] = __ldg(dy + i);
+    }
+    if (scale != nullptr) {
+#pragma unroll
+      for (int u = 0; u < V; ++u) g[u] *= __ldg(scale + (size_t)b * C + cv * V + u);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float o[V];
+#pragma unroll
+      for (int u = 0; u < V; ++u) o[u] = arg[u] == k ? g[u] : 0.f;
+      float* q = dx + base + ((size_t)(k >> 1) * W + (k & 1)) * C;
+      if (V == 4) *reinterpret_cast<float4*>(q) = make_float4(o[0], o[1 % V], o[2 % V], o[3 % V]);
+      else q[0] = o[0];
+    }
+  }
+}
+
+// bilinear x2, align_corners=True: src = dst * (in-1)/(out-1)
+__global__ void bilinear2x_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int H, int W, int C) {
+  const int Ho = 2 * H, Wo = 2 * W;
+  const float ry = Ho > 1 ? (float)(H - 1) / (float)(Ho - 1) : 0.f;
+  const float rx = Wo > 1 ? (float)(W - 1) / (float)(Wo - 1) : 0.f;
+  const long long n = (long long)B * Ho * Wo * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    long long p = i / C;
+    const int ox = (int)(p % Wo);
+    p /= Wo;
+    const int oy = (int)(p % Ho);
+    const int b = (int)(p / Ho);
+    const float sy = ry * oy, sx = rx * ox;
+    const int y0 = (int)sy, x0 = (int)sx;
+    const int y1 = y0 + (y0 < H - 1 ? 1 : 0), x1 = x0 + (x0 < W - 1 ? 1 : 0);
+    const float ly = sy - y0, lx = sx - x0;
+    const float* xb = x + (size_t)b * H * W * C + c;
+    const float v00 = __ldg(xb + ((size_t)y0 * W + x0) * C), v01 = __ldg(xb + ((size_t)y0 * W + x1) * C);
+    const float v10 = __ldg(xb + ((size_t)y1 * W + x0) * C), v11 = __ldg(xb + ((size_t)y1 * W + x1) * C);
+    y[i] = (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
+  }
+}
+
+__global__ void bilinear2x_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int B, int H, int W, int C) {
+  const int Ho = 2 * H, Wo = 2 * W;
+  const float ry = Ho > 1 ? (float)(H - 1) / (float)(Ho - 1) : 0.f;
+  const float rx = Wo > 1 ? (float)(W - 1) / (float)(Wo - 1) : 0.f;
+  const long long n = (long long)B * Ho * Wo * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    long long p = i / C;
+    const int ox = (int)(p % Wo);
+    p /= Wo;
+    const int oy = (int)(p % Ho);
+    const int b = (int)(p / Ho);
+    const float sy = ry * oy, sx = rx * ox;
+    const int y0 = (int)sy, x0 = (int)sx;
+    const int y1 = y0 + (y0 < H - 1 ? 1 : 0), x1 = x0 + (x0 < W - 1 ? 1 : 0);
+    const float ly = sy - y0, lx = sx - x0;
+    const float g = dy[i];
+    float* db = dx + (size_t)b * H * W * C + c;
+    atomicAdd(db + ((size_t)y0 * W + x0) * C, (1.f - ly) * (1.f - lx) * g);
+    atomicAdd(db + ((size_t)y0 * W + x1) * C, (1.f - ly) * lx * g);
+    atomicAdd(db + ((size_t)y1 * W + x0) * C, ly * (1.f - lx) * g);
+    atomicAdd(db + ((size_t)y1 * W + x1) * C, ly * lx * g);
+  }
+}
+
+static inline int grid_for(long long n) {
+  long long g = (n + 255) / 256;
+  if (g < 1) g = 1;
+  if (g > 16LL * kNumSMs) g = 16LL * kNumSMs;
+  return (int)g;
+}
+
+}  // namespace pu
+
+extern "C" {
+
+int pu_maxpool2_fwd(const float* x, const float* chan_scale, float* y, int B, int H, int W, int C, void* stream) {
+  PU_REQUIRE(x && y && B > 0 && H >= 2 && W >= 2 && C > 0, PU_ERR_BAD_ARG, "pu_maxpool2_fwd: bad argument");
+  cudaStream_t st = pu::as_stream(stream);
+  const long long nwin = (long long)B * (H / 2) * (W / 2);
+  if (C % 4 == 0 && pu::aligned16(x) && pu::aligned16(y))
+    pu::maxpool2_fwd_kernel<4><<<pu::grid_for(nwin * (C / 4)), 256, 0, st>>>(x, chan_scale, y, B, H, W, C);
+  else
+    pu::maxpool2_fwd_kernel<1><<<pu::grid_for(nwin * C), 256, 0, st>>>(x, chan_scale, y, B, H, W, C);
+  return pu::post_launch("pu_maxpool2_fwd");
+}
+
+int pu_maxpool2_bwd(const float* x, const float* chan_scale, const float* dy, float* dx, int B, int H, int W, int C, void* stream) {
+  PU_REQUIRE(x && dy && dx && B > 0 && H >= 2 && W >= 2 && C > 0, PU_ERR_BAD_ARG, "pu_maxpool2_bwd: bad argument");
+  cudaStream_t st = pu::as_stream(stream);
+  if ((H & 1) || (W & 1)) {  // floor mode leaves the last row/column unpooled: their gradient is zero
+    cudaError_t e = cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)B * H * W * C, st);
+    if (e != cudaSuccess) {
+      pu::set_error("pu_maxpool2_bwd memset: %s", cudaGetErrorString(e));
+      return PU_ERR_CUDA;
+    }
+  }
+  const long long nwin = (long long)B * (H / 2) * (W / 2);
+  if (C % 4 == 0 && pu::aligned16(x) && pu::aligned16(dy) && pu::aligned16(dx))
+    pu::maxpool2_bwd_kernel<4><<<pu::grid_for(nwin * (C / 4)), 256, 0, st>>>(x, chan_scale, dy, dx, B, H, W, C);
+  else
+    pu::maxpool2_bwd_kernel<1><<<pu::grid_for(nwin * C), 256, 0, st>>>(x, chan_scale, dy, dx, B, H, W, C);
+  return pu::post_launch("pu_maxpool2_bwd");
+}
+
+int pu_bilinear2x_fwd(const float* x, float* y, int B, int H, int W, int C, void* stream) {
+  PU_REQUIRE(x && y && B > 0 && H > 0 && W > 0 && C > 0, PU_ERR_BAD_ARG, "pu_bilinear2x_fwd: bad argument");
+  pu::bilinear2x_fwd_kernel<<<pu::grid_for((long long)B * 4 * H * W * C), 256, 0, pu::as_stream(stream)>>>(x, y, B, H, W, C);
+  return pu::post_launch("pu_bilinear2x_fwd");
+}
+
+int pu_bilinear2x_bwd(const float* dy, float* dx, int B, int H, int W, int C, void* stream) {
+  PU_REQUIRE(dy && dx && B > 0 && H > 0 && W > 0 && C > 0, PU_ERR_BAD_ARG, "pu_bilinear2x_bwd: bad argument");
+  cudaStream_t st = pu::as_stream(stream);
+  cudaError_t e = cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)B * H * W * C, st);
+  if (e != cudaSuccess) {
+    pu::set_error("pu_bilinear2x_bwd memset: %s", cudaGetErrorString(e));
+    return PU_ERR_CUDA;
+  }
+  pu::bilinear2x_bwd_kernel<<<pu::grid_for((long long)B * 4 * H * W * C), 256, 0, st>>>(dy, dx, B, H, W, C);
+  return pu::post_launch("pu_bilinear2x_bwd");
+}
+
+}  // extern "C"

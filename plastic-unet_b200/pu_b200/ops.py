@@ -1,0 +1,731 @@
+"""torch.library custom ops over the C-ABI kernels (namespace ``pu``).
+
+Every op inside the Plastic U-Net modules is one of these: a ``torch.library.custom_op`` with a fake
+(meta) implementation and an autograd formula whose backward is again a registered custom op.  All
+tensors are fp32 CUDA tensors of logical shape [B, H, W, C] (NHWC, contiguous).  There is no CPU,
+cuDNN or Triton fallback: a non-CUDA tensor raises.
+"""
+from typing import List, Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+
+MATH_FP32 = 0
+MATH_TF32 = 1
+RULE_HEBB = 0
+RULE_OJA = 1
+
+
+def _s() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _chk(*ts: Optional[Tensor]) -> None:
+    for t in ts:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("pu_b200 ops run only on CUDA tensors (sm_100a); there is no CPU fallback")
+        if t.dtype != torch.float32:
+            raise RuntimeError(f"pu_b200 ops are fp32; got {t.dtype}")
+        if not t.is_contiguous():
+            raise RuntimeError("pu_b200 ops need contiguous NHWC tensors")
+
+
+def _dims(t: Optional[Tensor]) -> Tuple[int, int, int]:
+    """(H, W, C) of an NHWC tensor, zeros for None."""
+    if t is None:
+        return 0, 0, 0
+    return t.shape[1], t.shape[2], t.shape[3]
+
+
+# =================================================================================================
+# conv3x3 (+ concat/crop of two sources, + bias, + residual, + ReLU)
+# =================================================================================================
+@torch.library.custom_op("pu::conv3x3", mutates_args=())
+def conv3x3(x0: Tensor, x1: Optional[Tensor], weight: Tensor, bias: Optional[Tensor], res: Optional[Tensor],
+            relu: bool, H: int, W: int, oy0: int, ox0: int, oy1: int, ox1: int, math: int) -> Tensor:
+    _chk(x0, x1, weight, bias, res)
+    B = x0.shape[0]
+    Cout, Cin = weight.shape[0], weight.shape[1]
+    H0, W0, C0 = _dims(x0)
+    H1, W1, C1 = _dims(x1)
+    if C0 + C1 != Cin:
+        raise RuntimeError(f"conv3x3: weight expects {Cin} input channels, sources have {C0}+{C1}")
+    wp = torch.empty(9 * Cin * Cout, device=x0.device, dtype=torch.float32)
+    _lib.call("pu_pack_w3x3", weight.data_ptr(), wp.data_ptr(), Cout, Cin, 0, _s())
+    y = torch.empty((B, H, W, Cout), device=x0.device, dtype=torch.float32)
+    _lib.call("pu_conv3x3_fwd", x0.data_ptr(), H0, W0, C0, oy0, ox0, _p(x1), H1, W1, C1, oy1, ox1,
+              wp.data_ptr(), _p(bias), _p(res), int(relu),
+              y.data_ptr(), H, W, Cout, 0, 0, None, 0, 0, 0, 0, 0, B, H, W, Cout, math, _s())
+    return y
+
+
+@conv3x3.register_fake
+def _(x0, x1, weight, bias, res, relu, H, W, oy0, ox0, oy1, ox1, math):
+    return x0.new_empty((x0.shape[0], H, W, weight.shape[0]))
+
+
+@torch.library.custom_op("pu::conv3x3_bwd", mutates_args=())
+def conv3x3_bwd(dy: Tensor, y: Tensor, x0: Tensor, x1: Optional[Tensor], weight: Tensor, has_bias: bool, relu: bool,
+                H: int, W: int, oy0: int, ox0: int, oy1: int, ox1: int, math: int,
+                need_dx: bool, need_dw: bool) -> List[Tensor]:
+    """-> [g, dx0, dx1, dw, db]; g = dy masked by the fused ReLU (== dy when relu is False)."""
+    _chk(dy, y, x0, x1, weight)
+    dev = dy.device
+    B = x0.shape[0]
+    Cout, Cin = weight.shape[0], weight.shape[1]
+    H0, W0, C0 = _dims(x0)
+    H1, W1, C1 = _dims(x1)
+    npix = B * H * W
+    empty = torch.empty(0, device=dev, dtype=torch.float32)
+    db = torch.empty(Cout, device=dev, dtype=torch.float32) if has_bias else empty
+    if relu:
+        g = torch.empty_like(dy)
+        _lib.call("pu_relu_bwd_bias", dy.data_ptr(), y.data_ptr(), g.data_ptr(), _p(db) if has_bias else None, npix, Cout, 1, _s())
+    else:
+        g = dy
+        if has_bias:
+            _lib.call("pu_relu_bwd_bias", dy.data_ptr(), None, None, db.data_ptr(), npix, Cout, 0, _s())
+    dx0, dx1 = empty, empty
+    if need_dx:
+        wpt = torch.empty(9 * Cin * Cout, device=dev, dtype=torch.float32)
+        _lib.call("pu_pack_w3x3", weight.data_ptr(), wpt.data_ptr(), Cout, Cin, 1, _s())
+        full0 = (H0 == H and W0 == W)
+        dx0 = (torch.empty if full0 else torch.zeros)((B, H0, W0, C0), device=dev, dtype=torch.float32)
+        if x1 is not None:
+            full1 = (H1 == H and W1 == W)
+            dx1 = (torch.empty if full1 else torch.zeros)((B, H1, W1, C1), device=dev, dtype=torch.float32)
+        _lib.call("pu_conv3x3_fwd", g.data_ptr(), H, W, Cout, 0, 0, None, 0, 0, 0, 0, 0,
+                  wpt.data_ptr(), None, None, 0,
+                  dx0.data_ptr(), H0, W0, C0, oy0, ox0,
+                  dx1.data_ptr() if x1 is not None else None, H1, W1, C1, oy1, ox1,
+                  B, H, W, Cin, math, _s())
+    dw = empty
+    if need_dw:
+        dw = torch.empty_like(weight)
+        _lib.call("pu_conv3x3_wgrad", x0.data_ptr(), H0, W0, C0, oy0, ox0, _p(x1), H1, W1, C1, oy1, ox1,
+                  g.data_ptr(), dw.data_ptr(), B, H, W, Cout, math, _s())
+    g_out = g if relu else empty  # never return an alias of an input
+    return [g_out, dx0, dx1, dw, db]
+
+
+@conv3x3_bwd.register_fake
+def _(dy, y, x0, x1, weight, has_bias, relu, H, W, oy0, ox0, oy1, ox1, math, need_dx, need_dw):
+    e = dy.new_empty(0)
+    return [torch.empty_like(dy) if relu else e,
+            torch.empty_like(x0) if need_dx else e,
+            torch.empty_like(x1) if (need_dx and x1 is not None) else e,
+            torch.empty_like(weight) if need_dw else e,
+            dy.new_empty(weight.shape[0]) if has_bias else e]
+
+
+def _conv3x3_setup(ctx, inputs, output):
+    x0, x1, weight, bias, res, relu, H, W, oy0, ox0, oy1, ox1, math = inputs
+    ctx.save_for_backward(x0, x1, weight, output)
+    ctx.cfg = (bias is not None, res is not None, relu, H, W, oy0, ox0, oy1, ox1, math)
+
+
+def _conv3x3_backward(ctx, dy):
+    x0, x1, weight, y = ctx.saved_tensors
+    has_bias, has_res, relu, H, W, oy0, ox0, oy1, ox1, math = ctx.cfg
+    need = ctx.needs_input_grad
+    need_dx = need[0] or (x1 is not None and need[1])
+    dy = dy.contiguous()
+    g, dx0, dx1, dw, db = conv3x3_bwd(dy, y, x0, x1, weight, has_bias and need[3], relu, H, W, oy0, ox0, oy1, ox1, math,
+                                      need_dx, need[2])
+    gres = None
+    if has_res and need[4]:
+        gres = g if relu else dy
+    return (dx0 if need[0] else None, dx1 if (x1 is not None and need[1]) else None, dw if need[2] else None,
+            db if (has_bias and need[3]) else None, gres, None, None, None, None, None, None, None, None)
+
+
+conv3x3.register_autograd(_conv3x3_backward, setup_context=_conv3x3_setup)
+
+
+# =================================================================================================
+# conv1x1 (+ analytic CoordConv channels, + ReLU)
+# =================================================================================================
+@torch.library.custom_op("pu::conv1x1", mutates_args=())
+def conv1x1(x: Tensor, weight: Tensor, bias: Optional[Tensor], coords: int, relu: bool) -> Tensor:
+    _chk(x, weight, bias)
+    B, H, W, Cin = x.shape
+    Cout = weight.shape[0]
+    if weight.shape[1] != Cin + coords:
+        raise RuntimeError("conv1x1: weight/in-channel mismatch")
+    y = torch.empty((B, H, W, Cout), device=x.device, dtype=torch.float32)
+    _lib.call("pu_conv1x1_fwd", x.data_ptr(), weight.data_ptr(), _p(bias), y.data_ptr(), B, H, W, Cin, Cout, coords, int(relu), _s())
+    return y
+
+
+@conv1x1.register_fake
+def _(x, weight, bias, coords, relu):
+    return x.new_empty((x.shape[0], x.shape[1], x.shape[2], weight.shape[0]))
+
+
+@torch.library.custom_op("pu::conv1x1_bwd", mutates_args=())
+def conv1x1_bwd(dy: Tensor, y: Tensor, x: Tensor, weight: Tensor, coords: int, relu: bool, need_dx: bool) -> List[Tensor]:
+    _chk(dy, y, x, weight)
+    B, H, W, Cin = x.shape
+    Cout = weight.shape[0]
+    dev = x.device
+    g = dy
+    if relu:
+        g = torch.empty_like(dy)
+        _lib.call("pu_relu_bwd_bias", dy.data_ptr(), y.data_ptr(), g.data_ptr(), None, B * H * W, Cout, 1, _s())
+    dx = torch.empty_like(x) if need_dx else torch.empty(0, device=dev)
+    dw = torch.empty_like(weight)
+    db = torch.empty(Cout, device=dev, dtype=torch.float32)
+    ws = torch.empty(Cout * (Cin + coords + 1), device=dev, dtype=torch.float32)
+    _lib.call("pu_conv1x1_bwd", x.data_ptr(), weight.data_ptr(), g.data_ptr(), dx.data_ptr() if need_dx else None,
+              dw.data_ptr(), db.data_ptr(), ws.data_ptr(), B, H, W, Cin, Cout, coords, _s())
+    return [dx, dw, db]
+
+
+@conv1x1_bwd.register_fake
+def _(dy, y, x, weight, coords, relu, need_dx):
+    return [torch.empty_like(x) if need_dx else x.new_empty(0), torch.empty_like(weight), x.new_empty(weight.shape[0])]
+
+
+def _conv1x1_setup(ctx, inputs, output):
+    x, weight, bias, coords, relu = inputs
+    ctx.save_for_backward(x, weight, output)
+    ctx.cfg = (bias is not None, coords, relu)
+
+
+def _conv1x1_backward(ctx, dy):
+    x, weight, y = ctx.saved_tensors
+    has_bias, coords, relu = ctx.cfg
+    need = ctx.needs_input_grad
+    dx, dw, db = conv1x1_bwd(dy.contiguous(), y, x, weight, coords, relu, need[0])
+    return dx if need[0] else None, dw if need[1] else None, db if (has_bias and need[2]) else None, None, None
+
+
+conv1x1.register_autograd(_conv1x1_backward, setup_context=_conv1x1_setup)
+
+
+# =================================================================================================
+# transposed convolutions
+# =================================================================================================
+@torch.library.custom_op("pu::convT2x2s2", mutates_args=())
+def convT2x2s2(x: Tensor, weight: Tensor, bias: Optional[Tensor]) -> Tensor:
+    _chk(x, weight, bias)
+    B, H, W, Cin = x.shape
+    Cout = weight.shape[1]
+    y = torch.empty((B, 2 * H, 2 * W, Cout), device=x.device, dtype=torch.float32)
+    _lib.call("pu_convT2x2s2_fwd", x.data_ptr(), weight.data_ptr(), _p(bias), y.data_ptr(), B, H, W, Cin, Cout, _s())
+    return y
+
+
+@convT2x2s2.register_fake
+def _(x, weight, bias):
+    return x.new_empty((x.shape[0], 2 * x.shape[1], 2 * x.shape[2], weight.shape[1]))
+
+
+@torch.library.custom_op("pu::convT2x2s2_bwd", mutates_args=())
+def convT2x2s2_bwd(dy: Tensor, x: Tensor, weight: Tensor, need_dx: bool, need_dw: bool, need_db: bool) -> List[Tensor]:
+    _chk(dy, x, weight)
+    B, H, W, Cin = x.shape
+    Cout = weight.shape[1]
+    e = torch.empty(0, device=x.device)
+    dx = torch.empty_like(x) if need_dx else e
+    dw = torch.empty_like(weight) if need_dw else e
+    db = torch.empty(Cout, device=x.device, dtype=torch.float32) if need_db else e
+    _lib.call("pu_convT2x2s2_bwd", x.data_ptr(), weight.data_ptr(), dy.data_ptr(), dx.data_ptr() if need_dx else None,
+              dw.data_ptr() if need_dw else None, db.data_ptr() if need_db else None, B, H, W, Cin, Cout, _s())
+    return [dx, dw, db]
+
+
+@convT2x2s2_bwd.register_fake
+def _(dy, x, weight, need_dx, need_dw, need_db):
+    e = x.new_empty(0)
+    return [torch.empty_like(x) if need_dx else e, torch.empty_like(weight) if need_dw else e,
+            x.new_empty(weight.shape[1]) if need_db else e]
+
+
+def _convT2_setup(ctx, inputs, output):
+    x, weight, bias = inputs
+    ctx.save_for_backward(x, weight)
+    ctx.has_bias = bias is not None
+
+
+def _convT2_backward(ctx, dy):
+    x, weight = ctx.saved_tensors
+    need = ctx.needs_input_grad
+    dx, dw, db = convT2x2s2_bwd(dy.contiguous(), x, weight, need[0], need[1], ctx.has_bias and need[2])
+    return dx if need[0] else None, dw if need[1] else None, db if (ctx.has_bias and need[2]) else None
+
+
+convT2x2s2.register_autograd(_convT2_backward, setup_context=_convT2_setup)
+
+
+@torch.library.custom_op("pu::convT3x3s2", mutates_args=())
+def convT3x3s2(x: Tensor, weight: Tensor, bias: Optional[Tensor], chan_scale: Optional[Tensor],
+               Ho: int, Wo: int, oy: int, ox: int) -> Tensor:
+    _chk(x, weight, bias, chan_scale)
+    B, H, W, Cin = x.shape
+    Cout = weight.shape[1]
+    y = torch.empty((B, Ho, Wo, Cout), device=x.device, dtype=torch.float32)
+    _lib.call("pu_convT3x3s2_fwd", x.data_ptr(), weight.data_ptr(), _p(bias), _p(chan_scale), y.data_ptr(),
+              B, H, W, Cin, Cout, Ho, Wo, oy, ox, _s())
+    return y
+
+
+@convT3x3s2.register_fake
+def _(x, weight, bias, chan_scale, Ho, Wo, oy, ox):
+    return x.new_empty((x.shape[0], Ho, Wo, weight.shape[1]))
+
+
+@torch.library.custom_op("pu::convT3x3s2_bwd", mutates_args=())
+def convT3x3s2_bwd(dy: Tensor, x: Tensor, weight: Tensor, chan_scale: Optional[Tensor], oy: int, ox: int,
+                   need_dx: bool, need_dw: bool, need_db: bool) -> List[Tensor]:
+    _chk(dy, x, weight, chan_scale)
+    B, H, W, Cin = x.shape
+    Cout = weight.shape[1]
+    Ho, Wo = dy.shape[1], dy.shape[2]
+    e = torch.empty(0, device=x.device)
+    dx = torch.empty_like(x) if need_dx else e
+    dw = torch.empty_like(weight) if need_dw else e
+    db = torch.empty(Cout, device=x.device, dtype=torch.float32) if need_db else e
+    _lib.call("pu_convT3x3s2_bwd", x.data_ptr(), weight.data_ptr(), dy.data_ptr(), _p(chan_scale),
+              dx.data_ptr() if need_dx else None, dw.data_ptr() if need_dw else None, db.data_ptr() if need_db else None,
+              B, H, W, Cin, Cout, Ho, Wo, oy, ox, _s())
+    return [dx, dw, db]
+
+
+@convT3x3s2_bwd.register_fake
+def _(dy, x, weight, chan_scale, oy, ox, need_dx, need_dw, need_db):
+    e = x.new_empty(0)
+    return [torch.empty_like(x) if need_dx else e, torch.empty_like(weight) if need_dw else e,
+            x.new_empty(weight.shape[1]) if need_db else e]
+
+
+def _convT3_setup(ctx, inputs, output):
+    x, weight, bias, chan_scale, Ho, Wo, oy, ox = inputs
+    ctx.save_for_backward(x, weight, chan_scale)
+    ctx.cfg = (bias is not None, oy, ox)
+
+
+def _convT3_backward(ctx, dy):
+    x, weight, chan_scale = ctx.saved_tensors
+    has_bias, oy, ox = ctx.cfg
+    need = ctx.needs_input_grad
+    dx, dw, db = convT3x3s2_bwd(dy.contiguous(), x, weight, chan_scale, oy, ox, need[0], need[1], has_bias and need[2])
+    return dx if need[0] else None, dw if need[1] else None, db if (has_bias and need[2]) else None, None, None, None, None, None
+
+
+convT3x3s2.register_autograd(_convT3_backward, setup_context=_convT3_setup)
+
+
+# =================================================================================================
+# pooling / resampling
+# =================================================================================================
+@torch.library.custom_op("pu::maxpool2", mutates_args=())
+def maxpool2(x: Tensor, chan_scale: Optional[Tensor]) -> Tensor:
+    _chk(x, chan_scale)
+    B, H, W, C = x.shape
+    y = torch.empty((B, H // 2, W // 2, C), device=x.device, dtype=torch.float32)
+    _lib.call("pu_maxpool2_fwd", x.data_ptr(), _p(chan_scale), y.data_ptr(), B, H, W, C, _s())
+    return y
+
+
+@maxpool2.register_fake
+def _(x, chan_scale):
+    return x.new_empty((x.shape[0], x.shape[1] // 2, x.shape[2] // 2, x.shape[3]))
+
+
+@torch.library.custom_op("pu::maxpool2_bwd", mutates_args=())
+def maxpool2_bwd(dy: Tensor, x: Tensor, chan_scale: Optional[Tensor]) -> Tensor:
+    _chk(dy, x, chan_scale)
+    B, H, W, C = x.shape
+    dx = torch.empty_like(x)
+    _lib.call("pu_maxpool2_bwd", x.data_ptr(), _p(chan_scale), dy.data_ptr(), dx.data_ptr(), B, H, W, C, _s())
+    return dx
+
+
+@maxpool2_bwd.register_fake
+def _(dy, x, chan_scale):
+    return torch.empty_like(x)
+
+
+def _pool_setup(ctx, inputs, output):
+    x, chan_scale = inputs
+    ctx.save_for_backward(x, chan_scale)
+
+
+def _pool_backward(ctx, dy):
+    x, chan_scale = ctx.saved_tensors
+    return maxpool2_bwd(dy.contiguous(), x, chan_scale), None
+
+
+maxpool2.register_autograd(_pool_backward, setup_context=_pool_setup)
+
+
+@torch.library.custom_op("pu::bilinear2x", mutates_args=())
+def bilinear2x(x: Tensor) -> Tensor:
+    _chk(x)
+    B, H, W, C = x.shape
+    y = torch.empty((B, 2 * H, 2 * W, C), device=x.device, dtype=torch.float32)
+    _lib.call("pu_bilinear2x_fwd", x.data_ptr(), y.data_ptr(), B, H, W, C, _s())
+    return y
+
+
+@bilinear2x.register_fake
+def _(x):
+    return x.new_empty((x.shape[0], 2 * x.shape[1], 2 * x.shape[2], x.shape[3]))
+
+
+@torch.library.custom_op("pu::bilinear2x_bwd", mutates_args=())
+def bilinear2x_bwd(dy: Tensor) -> Tensor:
+    _chk(dy)
+    B, Ho, Wo, C = dy.shape
+    dx = torch.empty((B, Ho // 2, Wo // 2, C), device=dy.device, dtype=torch.float32)
+    _lib.call("pu_bilinear2x_bwd", dy.data_ptr(), dx.data_ptr(), B, Ho // 2, Wo // 2, C, _s())
+    return dx
+
+
+@bilinear2x_bwd.register_fake
+def _(dy):
+    return dy.new_empty((dy.shape[0], dy.shape[1] // 2, dy.shape[2] // 2, dy.shape[3]))
+
+
+bilinear2x.register_autograd(lambda ctx, dy: bilinear2x_bwd(dy.contiguous()), setup_context=lambda ctx, inputs, output: None)
+
+
+# =================================================================================================
+# concat + crop + channel scale (materialised only in Dropout2d training mode)
+# =================================================================================================
+@torch.library.custom_op("pu::concat_scale", mutates_args=())
+def concat_scale(x0: Tensor, x1: Tensor, chan_scale: Optional[Tensor], H: int, W: int,
+                 oy0: int, ox0: int, oy1: int, ox1: int) -> Tensor:
+    _chk(x0, x1, chan_scale)
+    B = x0.shape[0]
+    H0, W0, C0 = _dims(x0)
+    H1, W1, C1 = _dims(x1)
+    y = torch.empty((B, H, W, C0 + C1), device=x0.device, dtype=torch.float32)
+    _lib.call("pu_concat_scale_fwd", x0.data_ptr(), H0, W0, C0, oy0, ox0, x1.data_ptr(), H1, W1, C1, oy1, ox1,
+              _p(chan_scale), y.data_ptr(), B, H, W, _s())
+    return y
+
+
+@concat_scale.register_fake
+def _(x0, x1, chan_scale, H, W, oy0, ox0, oy1, ox1):
+    return x0.new_empty((x0.shape[0], H, W, x0.shape[3] + x1.shape[3]))
+
+
+@torch.library.custom_op("pu::concat_scale_bwd", mutates_args=())
+def concat_scale_bwd(dy: Tensor, chan_scale: Optional[Tensor], shape0: List[int], shape1: List[int],
+                     oy0: int, ox0: int, oy1: int, ox1: int) -> List[Tensor]:
+    _chk(dy, chan_scale)
+    B, H, W, _ = dy.shape
+    dev = dy.device
+    _, H0, W0, C0 = shape0
+    _, H1, W1, C1 = shape1
+    dx0 = (torch.empty if (H0 == H and W0 == W) else torch.zeros)(shape0, device=dev, dtype=torch.float32)
+    dx1 = (torch.empty if (H1 == H and W1 == W) else torch.zeros)(shape1, device=dev, dtype=torch.float32)
+    _lib.call("pu_concat_scale_bwd", dy.data_ptr(), _p(chan_scale), dx0.data_ptr(), H0, W0, C0, oy0, ox0,
+              dx1.data_ptr(), H1, W1, C1, oy1, ox1, B, H, W, _s())
+    return [dx0, dx1]
+
+
+@concat_scale_bwd.register_fake
+def _(dy, chan_scale, shape0, shape1, oy0, ox0, oy1, ox1):
+    return [dy.new_empty(shape0), dy.new_empty(shape1)]
+
+
+def _cat_setup(ctx, inputs, output):
+    x0, x1, chan_scale, H, W, oy0, ox0, oy1, ox1 = inputs
+    ctx.save_for_backward(chan_scale)
+    ctx.cfg = (list(x0.shape), list(x1.shape), oy0, ox0, oy1, ox1)
+
+
+def _cat_backward(ctx, dy):
+    (chan_scale,) = ctx.saved_tensors
+    s0, s1, oy0, ox0, oy1, ox1 = ctx.cfg
+    dx0, dx1 = concat_scale_bwd(dy.contiguous(), chan_scale, s0, s1, oy0, ox0, oy1, ox1)
+    return dx0, dx1, None, None, None, None, None, None, None
+
+
+concat_scale.register_autograd(_cat_backward, setup_context=_cat_setup)
+
+
+# =================================================================================================
+# BatchNorm2d (optional)
+# =================================================================================================
+@torch.library.custom_op("pu::batchnorm", mutates_args=())
+def batchnorm(x: Tensor, gamma: Tensor, beta: Tensor, running_mean: Tensor, running_var: Tensor,
+              train: bool, momentum: float, eps: float, relu: bool) -> Tuple[Tensor, Tensor, Tensor]:
+    """-> [y, mean, invstd] (the statistics the backward needs)."""
+    _chk(x, gamma, beta, running_mean, running_var)
+    C = x.shape[-1]
+    npix = x.numel() // C
+    y = torch.empty_like(x)
+    mean = torch.empty(C, device=x.device, dtype=torch.float32)
+    invstd = torch.empty(C, device=x.device, dtype=torch.float32)
+    if train:
+        ws = torch.empty(2 * C, device=x.device, dtype=torch.float64)
+        _lib.call("pu_bn_train_fwd", x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), mean.data_ptr(),
+                  invstd.data_ptr(), None, None, ws.data_ptr(),
+                  float(momentum), float(eps), npix, C, int(relu), _s())
+    else:
+        _lib.call("pu_bn_eval_fwd", x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), running_mean.data_ptr(),
+                  running_var.data_ptr(), y.data_ptr(), float(eps), npix, C, int(relu), _s())
+        mean.copy_(running_mean)
+        _lib.call("pu_bn_invstd", running_var.data_ptr(), invstd.data_ptr(), float(eps), C, _s())
+    return y, mean, invstd
+
+
+@torch.library.custom_op("pu::bn_update_running", mutates_args=("running_mean", "running_var"))
+def bn_update_running(mean: Tensor, invstd: Tensor, running_mean: Tensor, running_var: Tensor,
+                      momentum: float, eps: float, npix: int) -> None:
+    """Running-statistics side effect of a training-mode BatchNorm (kept out of the functional op)."""
+    _chk(mean, invstd, running_mean, running_var)
+    _lib.call("pu_bn_update_running", mean.data_ptr(), invstd.data_ptr(), running_mean.data_ptr(), running_var.data_ptr(),
+              float(momentum), float(eps), npix, mean.shape[0], _s())
+
+
+@batchnorm.register_fake
+def _(x, gamma, beta, running_mean, running_var, train, momentum, eps, relu):
+    C = x.shape[-1]
+    return torch.empty_like(x), x.new_empty(C), x.new_empty(C)
+
+
+@torch.library.custom_op("pu::batchnorm_bwd", mutates_args=())
+def batchnorm_bwd(dy: Tensor, x: Tensor, y: Tensor, gamma: Tensor, mean: Tensor, invstd: Tensor,
+                  relu: bool, train: bool) -> List[Tensor]:
+    _chk(dy, x, y, gamma, mean, invstd)
+    C = x.shape[-1]
+    npix = x.numel() // C
+    dx = torch.empty_like(x)
+    dgamma = torch.empty(C, device=x.device, dtype=torch.float32)
+    dbeta = torch.empty(C, device=x.device, dtype=torch.float32)
+    ws = torch.empty(2 * C, device=x.device, dtype=torch.float64)
+    _lib.call("pu_bn_bwd", x.data_ptr(), y.data_ptr(), dy.data_ptr(), gamma.data_ptr(), mean.data_ptr(), invstd.data_ptr(),
+              dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), ws.data_ptr(), npix, C, int(relu), int(train), _s())
+    return [dx, dgamma, dbeta]
+
+
+@batchnorm_bwd.register_fake
+def _(dy, x, y, gamma, mean, invstd, relu, train):
+    C = x.shape[-1]
+    return [torch.empty_like(x), x.new_empty(C), x.new_empty(C)]
+
+
+def _bn_setup(ctx, inputs, output):
+    x, gamma, beta, running_mean, running_var, train, momentum, eps, relu = inputs
+    y, mean, invstd = output
+    ctx.save_for_backward(x, y, gamma, mean, invstd)
+    ctx.cfg = (relu, train)
+
+
+def _bn_backward(ctx, dy, _dmean, _dinvstd):
+    x, y, gamma, mean, invstd = ctx.saved_tensors
+    relu, train = ctx.cfg
+    dx, dgamma, dbeta = batchnorm_bwd(dy.contiguous(), x, y, gamma, mean, invstd, relu, train)
+    return dx, dgamma, dbeta, None, None, None, None, None, None
+
+
+batchnorm.register_autograd(_bn_backward, setup_context=_bn_setup)
+
+
+# =================================================================================================
+# layout
+# =================================================================================================
+@torch.library.custom_op("pu::nchw_to_nhwc", mutates_args=())
+def nchw_to_nhwc(x: Tensor) -> Tensor:
+    _chk(x)
+    B, C, H, W = x.shape
+    y = torch.empty((B, H, W, C), device=x.device, dtype=torch.float32)
+    _lib.call("pu_nchw_to_nhwc", x.data_ptr(), y.data_ptr(), B, C, H, W, _s())
+    return y
+
+
+@nchw_to_nhwc.register_fake
+def _(x):
+    B, C, H, W = x.shape
+    return x.new_empty((B, H, W, C))
+
+
+@torch.library.custom_op("pu::nhwc_to_nchw", mutates_args=())
+def nhwc_to_nchw(x: Tensor) -> Tensor:
+    _chk(x)
+    B, H, W, C = x.shape
+    y = torch.empty((B, C, H, W), device=x.device, dtype=torch.float32)
+    _lib.call("pu_nhwc_to_nchw", x.data_ptr(), y.data_ptr(), B, C, H, W, _s())
+    return y
+
+
+@nhwc_to_nchw.register_fake
+def _(x):
+    B, H, W, C = x.shape
+    return x.new_empty((B, C, H, W))
+
+
+nchw_to_nhwc.register_autograd(lambda ctx, dy: nhwc_to_nchw(dy.contiguous()), setup_context=lambda ctx, inputs, output: None)
+nhwc_to_nchw.register_autograd(lambda ctx, dy: nchw_to_nhwc(dy.contiguous()), setup_context=lambda ctx, inputs, output: None)
+
+
+# =================================================================================================
+# plastic head + trace
+# =================================================================================================
+@torch.library.custom_op("pu::plastic_head", mutates_args=())
+def plastic_head(X: Tensor, w: Tensor, alpha: Tensor, hebb: Tensor) -> Tuple[Tensor, Tensor]:
+    """X [B*N, N] -> [S = sigmoid(X @ (w + alpha*hebb)) [B*N, N], Weff [N, N]]   (unet_p.py:70-79)"""
+    _chk(X, w, alpha, hebb)
+    N = w.shape[0]
+    B = X.shape[0] // N
+    S = torch.empty_like(X)
+    weff = torch.empty_like(w)
+    _lib.call("pu_plastic_head_fwd", X.data_ptr(), w.data_ptr(), alpha.data_ptr(), hebb.data_ptr(), weff.data_ptr(),
+              S.data_ptr(), B, N, _s())
+    return S, weff
+
+
+@plastic_head.register_fake
+def _(X, w, alpha, hebb):
+    return torch.empty_like(X), torch.empty_like(w)
+
+
+@torch.library.custom_op("pu::plastic_head_bwd", mutates_args=())
+def plastic_head_bwd(gS: Tensor, X: Tensor, S: Tensor, weff: Tensor, alpha: Tensor, hebb: Tensor,
+                     need_gx: bool, need_galpha: bool, need_ghebb: bool) -> List[Tensor]:
+    _chk(gS, X, S, weff, alpha, hebb)
+    N = weff.shape[0]
+    B = X.shape[0] // N
+    e = torch.empty(0, device=X.device)
+    gA = torch.empty_like(X)
+    gX = torch.empty_like(X) if need_gx else e
+    gw = torch.empty_like(weff)
+    galpha = torch.empty_like(weff) if need_galpha else e
+    ghebb = torch.empty_like(weff) if need_ghebb else e
+    _lib.call("pu_plastic_head_bwd", X.data_ptr(), S.data_ptr(), gS.data_ptr(), weff.data_ptr(), alpha.data_ptr(), hebb.data_ptr(),
+              gA.data_ptr(), gX.data_ptr() if need_gx else None, gw.data_ptr(), galpha.data_ptr() if need_galpha else None,
+              ghebb.data_ptr() if need_ghebb else None, B, N, _s())
+    return [gX, gw, galpha, ghebb]
+
+
+@plastic_head_bwd.register_fake
+def _(gS, X, S, weff, alpha, hebb, need_gx, need_galpha, need_ghebb):
+    e = X.new_empty(0)
+    return [torch.empty_like(X) if need_gx else e, torch.empty_like(weff),
+            torch.empty_like(weff) if need_galpha else e, torch.empty_like(weff) if need_ghebb else e]
+
+
+def _head_setup(ctx, inputs, output):
+    X, w, alpha, hebb = inputs
+    S, weff = output
+    ctx.save_for_backward(X, S, weff, alpha, hebb)
+
+
+def _head_backward(ctx, gS, _gweff):
+    X, S, weff, alpha, hebb = ctx.saved_tensors
+    need = ctx.needs_input_grad
+    gX, gw, galpha, ghebb = plastic_head_bwd(gS.contiguous(), X, S, weff, alpha, hebb, need[0], need[2], need[3])
+    return gX if need[0] else None, gw if need[1] else None, galpha if need[2] else None, ghebb if need[3] else None
+
+
+plastic_head.register_autograd(_head_backward, setup_context=_head_setup)
+
+
+@torch.library.custom_op("pu::trace_update", mutates_args=())
+def trace_update(hebb: Tensor, pre: Tensor, post: Tensor, eta: Tensor, rule: int, ld: int, K: int) -> Tensor:
+    """Fused Hebb/Oja update over K (pre, post) row pairs, rows k at pre[k*ld : k*ld+N]  (unet_p.py:81-84)."""
+    _chk(hebb, pre, post, eta)
+    N = hebb.shape[0]
+    if pre.numel() < (K - 1) * ld + N or post.numel() < (K - 1) * ld + N:
+        raise RuntimeError("trace_update: pre/post too small for (K, ld)")
+    out = torch.empty_like(hebb)
+    _lib.call("pu_trace_update_fwd", hebb.data_ptr(), pre.data_ptr(), post.data_ptr(), ld, K, eta.data_ptr(), rule,
+              out.data_ptr(), N, _s())
+    return out
+
+
+@trace_update.register_fake
+def _(hebb, pre, post, eta, rule, ld, K):
+    return torch.empty_like(hebb)
+
+
+@torch.library.custom_op("pu::trace_update_bwd", mutates_args=())
+def trace_update_bwd(gout: Tensor, hebb: Tensor, pre: Tensor, post: Tensor, eta: Tensor, rule: int, ld: int, K: int) -> List[Tensor]:
+    """-> [ghebb [N,N], gpre (shape of pre, zero outside the K rows), gpost (same), geta [1]]"""
+    _chk(gout, hebb, pre, post, eta)
+    N = hebb.shape[0]
+    dev = hebb.device
+    ghebb = torch.empty_like(hebb)
+    geta = torch.empty(1, device=dev, dtype=torch.float32)
+    gpre_rows = torch.empty((K, N), device=dev, dtype=torch.float32)
+    gpost_rows = torch.empty((K, N), device=dev, dtype=torch.float32)
+    _lib.call("pu_trace_update_bwd", hebb.data_ptr(), pre.data_ptr(), post.data_ptr(), ld, K, eta.data_ptr(), rule,
+              gout.data_ptr(), ghebb.data_ptr(), gpre_rows.data_ptr(), gpost_rows.data_ptr(), geta.data_ptr(), N, _s())
+    return [ghebb, gpre_rows, gpost_rows, geta]
+
+
+@trace_update_bwd.register_fake
+def _(gout, hebb, pre, post, eta, rule, ld, K):
+    N = hebb.shape[0]
+    return [torch.empty_like(hebb), hebb.new_empty((K, N)), hebb.new_empty((K, N)), hebb.new_empty(1)]
+
+
+def _trace_setup(ctx, inputs, output):
+    hebb, pre, post, eta, rule, ld, K = inputs
+    ctx.save_for_backward(hebb, pre, post, eta)
+    ctx.cfg = (rule, ld, K)
+
+
+def _scatter_rows(rows: Tensor, like: Tensor, ld: int, K: int) -> Tensor:
+    """Place the K gradient rows at stride ld inside a zero tensor shaped like the flat pre/post buffer."""
+    N = rows.shape[1]
+    flat = torch.zeros(like.numel(), device=like.device, dtype=like.dtype)
+    if ld == N:
+        flat[: K * N] = rows.reshape(-1)
+    else:
+        flat.as_strided((K, N), (ld, 1)).copy_(rows)
+    return flat.view(like.shape)
+
+
+def _trace_backward(ctx, gout):
+    hebb, pre, post, eta = ctx.saved_tensors
+    rule, ld, K = ctx.cfg
+    need = ctx.needs_input_grad
+    ghebb, gpre_rows, gpost_rows, geta = trace_update_bwd(gout.contiguous(), hebb, pre, post, eta, rule, ld, K)
+    gpre = _scatter_rows(gpre_rows, pre, ld, K) if need[1] else None
+    gpost = _scatter_rows(gpost_rows, post, ld, K) if need[2] else None
+    return (ghebb if need[0] else None, gpre, gpost, geta.view(eta.shape) if need[3] else None, None, None, None)
+
+
+trace_update.register_autograd(_trace_backward, setup_context=_trace_setup)
+
+
+# ---- data-parallel split form (no autograd: the trace is detached between steps, train.py:99) ----
+@torch.library.custom_op("pu::trace_delta", mutates_args=())
+def trace_delta(pre: Tensor, post: Tensor, N: int, ld: int, K: int) -> Tensor:
+    """-> [N*N + N] = (sum_k outer(pre_k, post_k), sum_k post_k^2): the all-reduce payload."""
+    _chk(pre, post)
+    out = torch.empty(N * N + N, device=pre.device, dtype=torch.float32)
+    _lib.call("pu_trace_delta", pre.data_ptr(), post.data_ptr(), ld, K, out.data_ptr(), N, _s())
+    return out
+
+
+@trace_delta.register_fake
+def _(pre, post, N, ld, K):
+    return pre.new_empty(N * N + N)
+
+
+@torch.library.custom_op("pu::trace_apply", mutates_args=())
+def trace_apply(hebb: Tensor, delta_q: Tensor, eta: Tensor, rule: int, K_global: int) -> Tensor:
+    _chk(hebb, delta_q, eta)
+    out = torch.empty_like(hebb)
+    _lib.call("pu_trace_apply", hebb.data_ptr(), delta_q.data_ptr(), K_global, eta.data_ptr(), rule, out.data_ptr(), hebb.shape[0], _s())
+    return out
+
+
+@trace_apply.register_fake
+def _(hebb, delta_q, eta, rule, K_global):
+    return torch.empty_like(hebb)
