@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""bench.py — the Plastic U-Net hot path on B200: train images/sec (fwd + bwd + plastic update + Adam).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (CUDA kernels, one process per GPU)
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path (oracle port) on host cores
+
+Workload at N=1 (BASELINE.json configs[1]): Plastic U-Net (UNetp), Oja rule, 128x128, batch 64 per GPU,
+synthetic 1-channel images (uniform [0,1) 101x101 zero-padded to 128x128) and Bernoulli masks, random-init
+weights (torch.manual_seed(0)).  N>1: same per-GPU batch (weak scaling), gradient + trace-delta all-reduce.
+
+One "step" = one optimisation step over one batch.  `value` is whole-job images/s with the batch already
+resident in HBM (a device pool larger than L2 is rotated through); `e2e` is the same step through the
+public API with pinned HOST batches (H2D copy of images+masks and D2H read of the loss inside the timed
+region, every step).  Timing: CUDA events on the launching stream, barrier + synchronize on both sides,
+max over ranks.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import contextlib
+import io
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (os.path.join(ROOT, "plastic-unet_b200"), os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+METRIC = "train images/sec (fwd+bwd+plastic update) @128x128"
+UNIT = "images/s"
+L2_BYTES = 126 * 1024 * 1024
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            j = json.load(f)
+        return float(j["hbm_gbs"]), float(j.get("bf16_tflops", 1590.0)), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
+
+
+def quiet(fn, *a, **k):
+    with contextlib.redirect_stdout(io.StringIO()):
+        return fn(*a, **k)
+
+
+def synth_batch(n, size, gen, pad_from=101):
+    """Synthetic seismic-shaped data: uniform images pad_from^2 zero-padded to size^2, Bernoulli(0.25) masks."""
+    if size == 128 and pad_from == 101:
+        img = torch.zeros(n, 1, 128, 128)
+        img[:, :, 13:114, 13:114] = torch.rand(n, 1, 101, 101, generator=gen)
+        msk = torch.zeros(n, 128, 128)
+        msk[:, 13:114, 13:114] = (torch.rand(n, 101, 101, generator=gen) < 0.25).float()
+    else:
+        img = torch.rand(n, 1, size, size, generator=gen)
+        msk = (torch.rand(n, size, size, generator=gen) < 0.25).float()
+    return img, msk
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.path = "/tmp/pu_clocks_%d_%d.csv" % (os.getpid(), index)
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        with open(self.path) as f:
+            for line in f:
+                parts = [p.strip() for p in line.split(",")]
+                if len(parts) < 9:
+                    continue
+                try:
+                    sm.append(float(parts[1]))
+                    mx.append(float(parts[2]))
+                except ValueError:
+                    continue
+                for nm, val in zip(names, parts[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(nm)
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own algorithm (oracle port of train.py:91-112) on the host cores
+# --------------------------------------------------------------------------------------------------
+def cpu_train_images_per_s(n_images, size, rule, warm=3, seed=0):
+    """B=1 sequential steps exactly like train.py:91-112 on the oracle; -> (images/s, n_images, threads)."""
+    import plastic_unet_oracle as orc
+    from pu_b200 import UNetp
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    torch.manual_seed(seed)
+    net = quiet(UNetp, 1, 1, torch.device("cpu"), rule=rule, nbf=size)  # parameter container only (never run on CPU)
+    sd = orc.leaf_state(net.state_dict())
+    gen = torch.Generator().manual_seed(1234)
+    imgs, msks = synth_batch(n_images + warm, size, gen)
+    params = [v for v in sd.values() if v.is_floating_point() and v.requires_grad]
+    opt = torch.optim.Adam(params, lr=1e-4)
+    crit = torch.nn.BCELoss()
+    hebb = torch.zeros(size, size)
+    t0 = None
+    for i in range(n_images + warm):
+        if i == warm:
+            t0 = time.perf_counter()
+        opt.zero_grad()
+        _, y, hebb = orc.forward("unetp", sd, imgs[i:i + 1], hebb.detach(), rule=rule)
+        loss = crit(y.view(-1), msks[i].view(-1))
+        loss.item()
+        loss.backward()
+        opt.step()
+    dt = time.perf_counter() - t0
+    return n_images / dt, n_images, threads
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; the reference is pure Python
+    + PyTorch CPU ops, there is nothing to compile), all host threads, bounded sample per step."""
+    if rank != 0:
+        return
+    per_step = args.ref_images_per_step
+    threads = os.cpu_count() or 1
+    # warm-up steps + timed steps, each step = per_step sequential B=1 train iterations
+    ips_w, _, _ = cpu_train_images_per_s(max(1, args.warmup) * per_step, args.size, args.rule)
+    t0 = time.perf_counter()
+    ips, n, threads = cpu_train_images_per_s(args.steps * per_step, args.size, args.rule, warm=0)
+    dt = time.perf_counter() - t0
+    line = {
+        "impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "UNetp Oja 128x128 (101x101 zero-padded), B=1 sequential steps as train.py:91-112, "
+                               "%d images per step" % per_step},
+        "cpu_baseline": {"value": ips, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": "%d sequential single-image train steps (fwd+BCE+bwd+Adam+trace) of the oracle port" % n},
+        "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# dominant-kernel roofline (measured live with CUDA events on the launching stream)
+# --------------------------------------------------------------------------------------------------
+def dominant_kernel_roofline(batch, size, math, dev, hbm_peak, peak_src):
+    """Times the full-resolution 16->8 conv3x3 (+bias+ReLU, two-source concat: up4.0, the largest single layer of
+    UNetp: SURVEY.md §8d) in isolation, rotating over buffers larger than L2.  Algorithmic bytes per launch =
+    pixels * (C_in + C_out) * 4 (input read once + output written once)."""
+    from pu_b200 import ops
+    C0, C1, Cout = 8, 8, 8
+    nbuf = max(2, int(2 * L2_BYTES // (batch * size * size * (C0 + C1 + Cout) * 4)) + 1)
+    xs0 = [torch.rand(batch, size, size, C0, device=dev) for _ in range(nbuf)]
+    xs1 = [torch.rand(batch, size, size, C1, device=dev) for _ in range(nbuf)]
+    w = torch.randn(Cout, C0 + C1, 3, 3, device=dev) * 0.1
+    b = torch.zeros(Cout, device=dev)
+    with torch.no_grad():
+        for i in range(3):
+            ops.conv3x3(xs0[i % nbuf], xs1[i % nbuf], w, b, None, True, size, size, 0, 0, 0, 0, math)
+        torch.cuda.synchronize()
+        iters = 20
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(iters):
+            ops.conv3x3(xs0[i % nbuf], xs1[i % nbuf], w, b, None, True, size, size, 0, 0, 0, 0, math)
+        e1.record()
+        torch.cuda.synchronize()
+    # each op call = weight-pack (tiny) + the conv kernel; the pack kernel moves 4.6 KB and is < 1 % of the time
+    ms = e0.elapsed_time(e1) / iters
+    alg_bytes = batch * size * size * (C0 + C1 + Cout) * 4
+    achieved = alg_bytes / (ms * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": "conv3x3 fwd 16->8 @%dx%d (up4.0, %s)" % (size, size, "tf32 tcgen05" if math else "fp32 ffma"),
+            "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+            "peak_source": peak_src, "us_per_launch": ms * 1e3, "algorithmic_bytes_per_launch": alg_bytes}
+
+
+# --------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="per-GPU batch")
+    ap.add_argument("--size", type=int, default=128)
+    ap.add_argument("--rule", default="oja")
+    ap.add_argument("--math", default=os.environ.get("PU_CONV_MATH", "fp32"), choices=["fp32", "tf32"])
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-images-per-step", type=int, default=16)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    from pu_b200 import dp
+    if args.impl == "reference":
+        rank = int(os.environ.get("RANK", "0"))
+        run_reference(args, rank, int(os.environ.get("WORLD_SIZE", "1")))
+        return
+
+    import torch.distributed as dist
+    from pu_b200 import UNetp, _lib
+    from pu_b200.trainer import TrainStep
+
+    rank, world, local_rank = dp.init_from_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    hbm_peak, _, peak_src = measured_peaks()
+
+    torch.manual_seed(0)
+    net = quiet(UNetp, 1, 1, dev, rule=args.rule, nbf=args.size, batched=True)
+    net.conv_math = args.math
+    net.train()
+    group = dist.group.WORLD if world > 1 else None
+    dp.attach(net, group)
+    dp.broadcast_parameters(net, 0, group)
+    B = args.batch
+    ts = TrainStep(net, B, args.size, lr=1e-4, use_graph=not args.no_graph, dp_group=group)
+
+    # ---- data: device pool larger than L2 (rotated) + pinned host pool for the e2e leg
+    gen = torch.Generator().manual_seed(1234 + rank)
+    per_batch = B * args.size * args.size * 4 * 2
+    npool = max(4, int(1.5 * L2_BYTES // per_batch) + 1)
+    pool = [synth_batch(B, args.size, gen) for _ in range(npool)]
+    dpool = [(x.to(dev), t.to(dev)) for x, t in pool]
+    hpool = [(x.pin_memory(), t.pin_memory()) for x, t in pool]
+    ts.capture()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    # ---- warm-up
+    for i in range(args.warmup):
+        ts.step(*dpool[i % npool])
+    torch.cuda.synchronize()
+
+    # ---- timed: device-resident inputs
+    sampler = ClockSampler(local_rank)
+    barrier()
+    torch.cuda.synchronize()
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        ts.step(*dpool[i % npool])
+    e1.record()
+    torch.cuda.synchronize()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    eager_launches = _lib.launch_count() - launches0
+    loss_end = float(ts.loss)
+
+    # ---- timed: end to end from pinned host memory, loss read back every step
+    loss_host = torch.zeros(1).pin_memory()
+    for i in range(2):
+        ts.step(*hpool[i % npool])
+    torch.cuda.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        ts.step(*hpool[i % npool])
+        loss_host.copy_(ts.loss, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        _ = float(loss_host)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+
+    # ---- max over ranks
+    times = torch.tensor([ms, e2e_s * 1000.0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    ms_max, e2e_ms_max = float(times[0]), float(times[1])
+
+    if rank == 0:
+        images = B * world * args.steps
+        value = images / (ms_max * 1e-3)
+        e2e_value = images / (e2e_ms_max * 1e-3)
+        kps = ts.kernels_per_step or 0
+        roof = dominant_kernel_roofline(B, args.size, 1 if args.math == "tf32" else 0, dev, hbm_peak, peak_src)
+        # whole-step figure against the layer-fused algorithmic bound of SURVEY.md §8d (28.39 MB / image @128)
+        alg_mb_per_img = 28.39 * (args.size / 128.0) ** 2
+        step_gbs = alg_mb_per_img * 1e6 * B / (ms_max / args.steps * 1e-3) / 1e9
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            ips0, _, thr = cpu_train_images_per_s(4, args.size, args.rule, warm=1)
+            n = int(min(256, max(8, ips0 * 12)))  # ~12 s of CPU work
+            ips, n, thr = cpu_train_images_per_s(n, args.size, args.rule)
+            cpu = {"value": ips, "unit": UNIT, "cores": thr, "kind": "port",
+                   "sample": "%d sequential single-image train steps (fwd+BCE+bwd+Adam+trace, train.py:91-112) of the "
+                             "oracle port, same synthetic 128x128 data" % n}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "tf32" if args.math == "tf32" else "f32", "data": "synthetic",
+            "config": {"workload": "UNetp (Plastic U-Net) Oja rule, 1x101x101 zero-padded to 128x128, batch %d per GPU, "
+                                   "fwd+BCE+bwd+Adam+trace update" % B,
+                       "global_batch": B * world, "parallelism": "dp%d" % world, "conv_math": args.math,
+                       "cuda_graph": not args.no_graph,
+                       "l2": "inputs rotate over a %d-batch device pool (%.0f MB > 126 MB L2); per-step activation "
+                             "working set %.0f MB" % (npool, npool * per_batch / 1e6, 9.49 * B * (args.size / 128.0) ** 2)},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": per_batch * world, "d2h_bytes_per_step": 4 * world,
+                    "ms_per_step": e2e_ms_max / args.steps},
+            "gpu_launches": kps * args.steps,
+            "kernels_per_step": kps,
+            "roofline": roof,
+            "step_roofline": {"bound": "hbm", "achieved": step_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": step_gbs / hbm_peak,
+                              "note": "whole step vs the layer-fused algorithmic bytes of SURVEY.md 8d (%.2f MB/image)" % alg_mb_per_img},
+            "cpu_baseline": cpu,
+            "clocks": clocks,
+            "final_loss": loss_end,
+            "eager_launches_in_timed_region": eager_launches,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

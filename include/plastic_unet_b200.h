@@ -36,6 +36,10 @@ typedef enum {
 #define PU_RULE_HEBB 0
 #define PU_RULE_OJA 1
 
+/* op flags */
+#define PU_FLAG_RELU 1       /* fused ReLU in the epilogue                                            */
+#define PU_FLAG_ROUND_TF32 2 /* round the op's output to TF32 (RN): producers of tensor-core operands  */
+
 /* conv3x3 math modes */
 #define PU_MATH_FP32 0 /* CUDA-core FFMA, strict fp32 (parity mode, any shape)        */
 #define PU_MATH_TF32 1 /* tcgen05 kind::tf32 implicit GEMM, fp32 accumulate in TMEM   */
@@ -58,16 +62,23 @@ int pu_nhwc_to_nchw(const float* x, float* y, int B, int C, int H, int W, void* 
  * replaces nn.Conv2d(k=3,padding=1) (+ReLU, +residual add, +torch.cat/F.pad crop) at
  * reference unet_p.py:105-116,161-166 and unet_p_res.py:150-158,186-189,215-219,230,264.
  *
- * pu_pack_w3x3: OIHW weight [Cout,Cin,3,3] -> packed [9][Cin][Cout] (transpose=0, forward)
- *               or [9][Cout][Cin] with taps flipped (transpose=1, operand of dgrad).       */
-int pu_pack_w3x3(const float* w_oihw, float* w_packed, int Cout, int Cin, int transpose, void* stream);
+ * pu_pack_w3x3: OIHW weight [Cout,Cin,3,3] -> the operand layout of the conv that will consume it:
+ *   transpose=0: the forward conv (input channels Cin split C0 | Cin-C0 over the two sources, output Cout);
+ *   transpose=1: its dgrad (a conv with Cout input channels, Cin output channels, taps flipped; C0 ignored).
+ *   math=PU_MATH_FP32: [9][Cin'][Cout'];  math=PU_MATH_TF32: the tcgen05 B-operand tiles
+ *   [co block][K chunk][tap][channel group][N][4], rounded to TF32 (requires pu_conv3x3_tc_ok).          */
+int pu_pack_w3x3(const float* w_oihw, float* w_packed, int Cout, int Cin, int transpose, int math, int C0, void* stream);
+/* floats needed for the packed buffer of the call above */
+long long pu_pack_w3x3_floats(int Cout, int Cin, int transpose, int math, int C0);
+/* 1 if a conv with these source / destination channel counts can run on the tcgen05 path (PU_MATH_TF32) */
+int pu_conv3x3_tc_ok(int C0, int C1, int Cout, int Cd0, int Cd1);
 
-/* y = act( conv3x3(cat[src0,src1]) + bias + res ), written channel-split into dst0|dst1.
+/* y = act( conv3x3(cat[src0,src1]) + bias + res ), written channel-split into dst0|dst1 (flags: PU_FLAG_*).
  * src1, bias, res, dst1 may be NULL.  wp is the packed weight [9][C0+C1][Cout].
  * dst views may be larger than HxW (their border is NOT written — caller zero-fills).    */
 int pu_conv3x3_fwd(const float* src0, int H0, int W0, int C0, int oy0, int ox0,
                    const float* src1, int H1, int W1, int C1, int oy1, int ox1,
-                   const float* wp, const float* bias, const float* res, int relu,
+                   const float* wp, const float* bias, const float* res, int flags,
                    float* dst0, int Hd0, int Wd0, int Cd0, int oyd0, int oxd0,
                    float* dst1, int Hd1, int Wd1, int Cd1, int oyd1, int oxd1,
                    int B, int H, int W, int Cout, int math, void* stream);
@@ -79,17 +90,17 @@ int pu_conv3x3_wgrad(const float* src0, int H0, int W0, int C0, int oy0, int ox0
                      const float* g, float* dw_oihw, int B, int H, int W, int Cout,
                      int math, void* stream);
 
-/* g = relu ? dy * (y > 0) : dy ; dbias[c] = sum_pixels g  (g may alias dy; dbias may be NULL;
- * y may be NULL iff relu == 0).  Autograd of the fused ReLU + bias epilogue above.          */
+/* g = (flags & RELU) ? dy * (y > 0) : dy [rounded to TF32 if flags & ROUND]; dbias[c] = sum_pixels g  (g may alias
+ * dy; dbias may be NULL; y may be NULL iff no RELU flag).  Autograd of the fused ReLU + bias epilogue above.          */
 int pu_relu_bwd_bias(const float* dy, const float* y, float* g, float* dbias,
-                     long long npix, int C, int relu, void* stream);
+                     long long npix, int C, int flags, void* stream);
 
 /* ---- 1x1 convolution (reference unet_p.py:173, unet_p_res.py:194; CoordConv stem
  * coord_conv_script.py:104-126).  coords != 0 appends the AddCoords channels
  * (coord_conv_script.py:69-96): xx = 2*j/(W-1)-1, yy = 2*i/(H-1)-1, [rr if coords == 3]
  * analytically — they are never materialised.  w is [Cout, Cin + coords].                  */
 int pu_conv1x1_fwd(const float* x, const float* w, const float* bias, float* y,
-                   int B, int H, int W, int Cin, int Cout, int coords, int relu, void* stream);
+                   int B, int H, int W, int Cin, int Cout, int coords, int flags, void* stream);
 /* g is the (already ReLU-masked) output gradient.  dx and db may be NULL. dw [Cout,Cin+coords], db [Cout]
  * overwritten.  ws: caller-provided scratch of Cout*(Cin+coords+1) floats (<= 256).              */
 int pu_conv1x1_bwd(const float* x, const float* w, const float* g, float* dx, float* dw, float* db, float* ws,
@@ -98,14 +109,14 @@ int pu_conv1x1_bwd(const float* x, const float* w, const float* g, float* dx, fl
 /* ---- transposed convolutions ---------------------------------------------------------------
  * 2x2 stride 2 (reference unet_p.py:155): w is PyTorch [Cin,Cout,2,2]; y is [B,2H,2W,Cout]. */
 int pu_convT2x2s2_fwd(const float* x, const float* w, const float* bias, float* y,
-                      int B, int H, int W, int Cin, int Cout, void* stream);
+                      int B, int H, int W, int Cin, int Cout, int flags, void* stream);
 int pu_convT2x2s2_bwd(const float* x, const float* w, const float* dy, float* dx, float* dw, float* db,
                       int B, int H, int W, int Cin, int Cout, void* stream);
 /* 3x3 stride 2 pad 0 (reference unet_p_res.py:207): full output is (2H+1)x(2W+1); the op writes
  * only the window [oy,oy+Ho) x [ox,ox+Wo) of it (the F.pad crop of unet_p_res.py:215-217 fused).
  * chan_scale (may be NULL) is a per-(b,co) multiplier [B,Cout] applied after bias (Dropout2d). */
 int pu_convT3x3s2_fwd(const float* x, const float* w, const float* bias, const float* chan_scale, float* y,
-                      int B, int H, int W, int Cin, int Cout, int Ho, int Wo, int oy, int ox, void* stream);
+                      int B, int H, int W, int Cin, int Cout, int Ho, int Wo, int oy, int ox, int flags, void* stream);
 int pu_convT3x3s2_bwd(const float* x, const float* w, const float* dy, const float* chan_scale,
                       float* dx, float* dw, float* db,
                       int B, int H, int W, int Cin, int Cout, int Ho, int Wo, int oy, int ox, void* stream);
@@ -124,7 +135,7 @@ int pu_bilinear2x_bwd(const float* dy, float* dx, int B, int H, int W, int C, vo
 /* ---- concat / channel scale (only materialised in Dropout2d training mode) ------------------- */
 int pu_concat_scale_fwd(const float* src0, int H0, int W0, int C0, int oy0, int ox0,
                         const float* src1, int H1, int W1, int C1, int oy1, int ox1,
-                        const float* chan_scale, float* y, int B, int H, int W, void* stream);
+                        const float* chan_scale, float* y, int B, int H, int W, int flags, void* stream);
 /* inverse: dx0|dx1 windows receive dy[..., :C0]*scale | dy[..., C0:]*scale (either may be NULL; borders
  * outside the window are NOT written — caller zero-fills). */
 int pu_concat_scale_bwd(const float* dy, const float* chan_scale,
@@ -138,9 +149,9 @@ int pu_chan_scale(const float* x, const float* chan_scale, float* y, int B, long
  * stats (may be NULL); y = (x-mean)*invstd*gamma+beta, optional fused ReLU.  ws: scratch of 2*C doubles. */
 int pu_bn_train_fwd(const float* x, const float* gamma, const float* beta, float* y,
                     float* save_mean, float* save_invstd, float* running_mean, float* running_var, double* ws,
-                    float momentum, float eps, long long npix, int C, int relu, void* stream);
+                    float momentum, float eps, long long npix, int C, int flags, void* stream);
 int pu_bn_eval_fwd(const float* x, const float* gamma, const float* beta, const float* running_mean,
-                   const float* running_var, float* y, float eps, long long npix, int C, int relu, void* stream);
+                   const float* running_var, float* y, float eps, long long npix, int C, int flags, void* stream);
 /* dy is grad wrt y (post-ReLU if relu); y needed iff relu. train!=0 uses the batch-statistics backward,
  * train==0 treats mean/invstd as constants (eval).  dgamma/dbeta may be NULL.  ws: 2*C doubles.          */
 int pu_bn_bwd(const float* x, const float* y, const float* dy, const float* gamma,

@@ -49,12 +49,13 @@ __global__ void bn_finalize_kernel(const double* __restrict__ acc, float* __rest
 // mode 0: mean/invstd given; mode 1: running_mean/running_var given (invstd computed on the fly)
 __global__ void bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                                 const float* __restrict__ mean, const float* __restrict__ stat2, float* __restrict__ y, float eps,
-                                long long n, int C, int relu, int mode) {
+                                long long n, int C, int flags, int mode) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
     const float is = mode == 0 ? __ldg(stat2 + c) : rsqrtf(__ldg(stat2 + c) + eps);
     float v = (x[i] - __ldg(mean + c)) * is * __ldg(gamma + c) + __ldg(beta + c);
-    if (relu) v = fmaxf(v, 0.f);
+    if (flags & PU_FLAG_RELU) v = fmaxf(v, 0.f);
+    if (flags & PU_FLAG_ROUND_TF32) v = round_tf32(v);
     y[i] = v;
   }
 }
@@ -159,7 +160,7 @@ extern "C" {
 // ws: caller-provided scratch of 2*C doubles (fp64 sum / sum-of-squares accumulators).
 int pu_bn_train_fwd(const float* x, const float* gamma, const float* beta, float* y, float* save_mean, float* save_invstd,
                        float* running_mean, float* running_var, double* ws, float momentum, float eps, long long npix, int C,
-                       int relu, void* stream) {
+                       int flags, void* stream) {
   PU_REQUIRE(x && gamma && beta && y && save_mean && save_invstd && ws && npix > 0 && C > 0, PU_ERR_BAD_ARG, "pu_bn_train_fwd: bad argument");
   cudaStream_t st = pu::as_stream(stream);
   cudaError_t e = cudaMemsetAsync(ws, 0, sizeof(double) * 2 * C, st);
@@ -176,15 +177,15 @@ int pu_bn_train_fwd(const float* x, const float* gamma, const float* beta, float
   pu::bn_finalize_kernel<<<pu::cdiv(C, 128), 128, 0, st>>>(ws, save_mean, save_invstd, running_mean, running_var, momentum, eps, npix, C);
   rc = pu::post_launch("pu_bn_train_fwd finalize");
   if (rc) return rc;
-  pu::bn_apply_kernel<<<pu::ew_grid(npix * C), 256, 0, st>>>(x, gamma, beta, save_mean, save_invstd, y, eps, npix * C, C, relu, 0);
+  pu::bn_apply_kernel<<<pu::ew_grid(npix * C), 256, 0, st>>>(x, gamma, beta, save_mean, save_invstd, y, eps, npix * C, C, flags, 0);
   return pu::post_launch("pu_bn_train_fwd apply");
 }
 
 int pu_bn_eval_fwd(const float* x, const float* gamma, const float* beta, const float* running_mean, const float* running_var,
-                   float* y, float eps, long long npix, int C, int relu, void* stream) {
+                   float* y, float eps, long long npix, int C, int flags, void* stream) {
   PU_REQUIRE(x && gamma && beta && running_mean && running_var && y && npix > 0 && C > 0, PU_ERR_BAD_ARG, "pu_bn_eval_fwd: bad argument");
   pu::bn_apply_kernel<<<pu::ew_grid(npix * C), 256, 0, pu::as_stream(stream)>>>(x, gamma, beta, running_mean, running_var, y, eps,
-                                                                               npix * C, C, relu, 1);
+                                                                               npix * C, C, flags, 1);
   return pu::post_launch("pu_bn_eval_fwd");
 }
 

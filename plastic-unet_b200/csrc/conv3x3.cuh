@@ -10,7 +10,7 @@ struct Conv3x3Args {
   const float* bias;  // [Cout] | null
   const float* res;   // [B,H,W,Cout] | null, added before the ReLU
   ViewW d0, d1;       // channel-split destinations (d1.p may be null)
-  int B, H, W, Cin, Cout, relu;
+  int B, H, W, Cin, Cout, relu, round_out;
   int tilesX, tilesY;
 };
 
@@ -26,6 +26,8 @@ int conv3x3_fwd_ffma(const Conv3x3Args& a, cudaStream_t st);
 int conv3x3_wgrad_ffma(const WgradArgs& a, cudaStream_t st);
 // tcgen05 path (conv3x3_tc.cu); returns PU_ERR_UNSUPPORTED when the shape does not fit it
 int conv3x3_fwd_tc(const Conv3x3Args& a, cudaStream_t st);
-bool conv3x3_tc_supported(const Conv3x3Args& a);
+bool conv3x3_tc_ok(int C0, int C1, int Cout, int Cd0, int Cd1);
+long long conv3x3_tc_weight_floats(int C0, int C1, int Cout);
+int conv3x3_tc_pack(const float* w_oihw, float* out, int Cout_w, int Cin_w, int transpose, int C0, cudaStream_t st);
 
 }  // namespace pu

@@ -18,7 +18,7 @@ extern "C" {
 
 int pu_conv3x3_fwd(const float* src0, int H0, int W0, int C0, int oy0, int ox0,
                    const float* src1, int H1, int W1, int C1, int oy1, int ox1,
-                   const float* wp, const float* bias, const float* res, int relu,
+                   const float* wp, const float* bias, const float* res, int flags,
                    float* dst0, int Hd0, int Wd0, int Cd0, int oyd0, int oxd0,
                    float* dst1, int Hd1, int Wd1, int Cd1, int oyd1, int oxd1,
                    int B, int H, int W, int Cout, int math, void* stream) {
@@ -50,9 +50,12 @@ int pu_conv3x3_fwd(const float* src0, int H0, int W0, int C0, int oy0, int ox0,
   a.res = res;
   a.d0 = pu::ViewW{dst0, Hd0, Wd0, Cd0, oyd0, oxd0};
   a.d1 = pu::ViewW{dst1, Hd1, Wd1, Cd1, oyd1, oxd1};
-  a.B = B; a.H = H; a.W = W; a.Cin = C0 + C1; a.Cout = Cout; a.relu = relu;
+  a.B = B; a.H = H; a.W = W; a.Cin = C0 + C1; a.Cout = Cout;
+  a.relu = (flags & PU_FLAG_RELU) ? 1 : 0;
+  a.round_out = (flags & PU_FLAG_ROUND_TF32) ? 1 : 0;
   a.tilesX = a.tilesY = 0;
-  if (math == PU_MATH_TF32 && pu::conv3x3_tc_supported(a)) return pu::conv3x3_fwd_tc(a, pu::as_stream(stream));
+  // no silent fallback: PU_MATH_TF32 means the tcgen05 kernel (wp must be in its layout) or an error
+  if (math == PU_MATH_TF32) return pu::conv3x3_fwd_tc(a, pu::as_stream(stream));
   return pu::conv3x3_fwd_ffma(a, pu::as_stream(stream));
 }
 
@@ -79,5 +82,7 @@ int pu_conv3x3_wgrad(const float* src0, int H0, int W0, int C0, int oy0, int ox0
   a.tilesX = a.tilesY = a.ntiles = 0;
   return pu::conv3x3_wgrad_ffma(a, pu::as_stream(stream));
 }
+
+int pu_conv3x3_tc_ok(int C0, int C1, int Cout, int Cd0, int Cd1) { return pu::conv3x3_tc_ok(C0, C1, Cout, Cd0, Cd1) ? 1 : 0; }
 
 }  // extern "C"

@@ -148,6 +148,10 @@ __global__ void __launch_bounds__(NT) conv3x3_ffma_kernel(const Conv3x3Args a) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
     }
+    if (a.round_out) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = round_tf32(o[j]);
+    }
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int co = co0 + 4 * h;
@@ -359,7 +363,8 @@ __global__ void pack_w3x3_kernel(const float* __restrict__ w, float* __restrict_
 }
 
 __global__ void relu_bwd_bias_kernel(const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ g,
-                                     float* __restrict__ dbias, long long npix, int C, int relu) {
+                                     float* __restrict__ dbias, long long npix, int C, int flags) {
+  const int relu = flags & PU_FLAG_RELU, rnd = flags & PU_FLAG_ROUND_TF32;
   // generic scalar version: thread -> channel c = idx % C over a strided set of pixels
   extern __shared__ float red[];
   const int c4n = C;  // scalar granularity
@@ -369,8 +374,9 @@ __global__ void relu_bwd_bias_kernel(const float* __restrict__ dy, const float* 
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
     float v = dy[i];
     if (relu) v = y[i] > 0.f ? v : 0.f;
-    if (g != nullptr) g[i] = v;
     s += v;
+    if (rnd) v = round_tf32(v);
+    if (g != nullptr) g[i] = v;
   }
   if (dbias == nullptr) return;
   red[threadIdx.x] = s;
@@ -384,7 +390,8 @@ __global__ void relu_bwd_bias_kernel(const float* __restrict__ dy, const float* 
 }
 
 __global__ void relu_bwd_bias_vec4_kernel(const float4* __restrict__ dy, const float4* __restrict__ y, float4* __restrict__ g,
-                                          float* __restrict__ dbias, long long n4, int C4, int relu) {
+                                          float* __restrict__ dbias, long long n4, int C4, int flags) {
+  const int relu = flags & PU_FLAG_RELU, rnd = flags & PU_FLAG_ROUND_TF32;
   // blockDim.x * gridDim.x is a multiple of C4 => each thread stays on one channel quad
   __shared__ float4 red[256];
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -398,8 +405,9 @@ __global__ void relu_bwd_bias_vec4_kernel(const float4* __restrict__ dy, const f
       v.z = m.z > 0.f ? v.z : 0.f;
       v.w = m.w > 0.f ? v.w : 0.f;
     }
-    if (g != nullptr) g[i] = v;
     s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    if (rnd) v = make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
+    if (g != nullptr) g[i] = v;
   }
   if (dbias == nullptr) return;
   red[threadIdx.x] = s;
@@ -466,15 +474,26 @@ int conv3x3_wgrad_ffma(const WgradArgs& a0, cudaStream_t st) {
 
 extern "C" {
 
-int pu_pack_w3x3(const float* w, float* out, int Cout, int Cin, int transpose, void* stream) {
+long long pu_pack_w3x3_floats(int Cout, int Cin, int transpose, int math, int C0) {
+  if (math == PU_MATH_TF32) {
+    const long long n = transpose ? pu::conv3x3_tc_weight_floats(Cout, 0, Cin) : pu::conv3x3_tc_weight_floats(C0, Cin - C0, Cout);
+    if (n > 0) return n;
+  }
+  return 9LL * Cin * Cout;
+}
+
+int pu_pack_w3x3(const float* w, float* out, int Cout, int Cin, int transpose, int math, int C0, void* stream) {
   PU_REQUIRE(w && out && Cout > 0 && Cin > 0, PU_ERR_BAD_ARG, "pu_pack_w3x3: bad argument");
+  PU_REQUIRE(math == PU_MATH_FP32 || math == PU_MATH_TF32, PU_ERR_BAD_ARG, "pu_pack_w3x3: unknown math mode %d", math);
+  if (math == PU_MATH_TF32) return pu::conv3x3_tc_pack(w, out, Cout, Cin, transpose, C0, pu::as_stream(stream));
   const int n = Cout * Cin * 9;
   pu::pack_w3x3_kernel<<<pu::cdiv(n, 256) > 592 ? 592 : pu::cdiv(n, 256), 256, 0, pu::as_stream(stream)>>>(w, out, Cout, Cin, transpose);
   return pu::post_launch("pu_pack_w3x3");
 }
 
-int pu_relu_bwd_bias(const float* dy, const float* y, float* g, float* dbias, long long npix, int C, int relu, void* stream) {
-  PU_REQUIRE(dy && npix > 0 && C > 0 && (y || !relu), PU_ERR_BAD_ARG, "pu_relu_bwd_bias: bad argument");
+int pu_relu_bwd_bias(const float* dy, const float* y, float* g, float* dbias, long long npix, int C, int flags, void* stream) {
+  const int relu = flags;  // forwarded as the flag word
+  PU_REQUIRE(dy && npix > 0 && C > 0 && (y || !(flags & PU_FLAG_RELU)), PU_ERR_BAD_ARG, "pu_relu_bwd_bias: bad argument");
   PU_REQUIRE(g || dbias, PU_ERR_BAD_ARG, "pu_relu_bwd_bias: nothing to compute");
   cudaStream_t st = pu::as_stream(stream);
   if (dbias) {

@@ -1,12 +1,509 @@
-// conv3x3_tc.cu — tcgen05/TMEM implicit-GEMM 3x3 convolution (placeholder until the kernel lands).
+// conv3x3_tc.cu — tcgen05 / TMEM / TMA implicit-GEMM 3x3 convolution for sm_100a (PU_MATH_TF32).
+//
+//   D[pixel, co] += A[pixel, ci] * W[ci, co]   per filter tap, kind::tf32, fp32 accumulation in TMEM.
+//
+// Layout trick ("flattened padded rows"): the CTA's input halo tile (TH+2 rows x PW pixels, PW = tile width
+// + halo rounded up to 8) is brought in by ONE 5-D TMA box per source with the tensor map dims ordered
+// (4 floats of a channel group, x, y, channel group, image), so shared memory holds channel-group planes
+// [cg][pixel][4 floats] and out-of-bounds coordinates zero-fill — that is the conv's zero padding and the crop
+// window for free.  In that layout the A operand of output-pixel block r..r+127 for tap (ky,kx) is the
+// canonical no-swizzle K-major UMMA layout starting at pixel r + ky*PW + kx: core matrices (8 pixels x 16 B)
+// are contiguous (SBO = 128 B) and the two 16-byte K chunks of a K=8 MMA are one plane apart (LBO = plane
+// bytes).  Every tap therefore re-reads the SAME staged tile through a shifted descriptor — the input
+// crosses L2->SMEM once, not nine times — and any image width works (garbage columns x >= TW are computed
+// and dropped in the epilogue).  Skip-concat is a second tensor map whose planes land behind the first.
+//
+// CTA = 128 threads: thread 0 issues TMA + bulk weight copy, waits the full barrier, issues all
+// tcgen05.mma (one accumulator of N columns per 128-pixel block, up to 256 TMEM columns) and commits;
+// the 4 warps then drain TMEM with tcgen05.ld (warp w owns lanes 32w..32w+31 = pixel rows) and apply the
+// fused epilogue: bias + residual + ReLU (+ RN rounding to TF32 so that the next layer's operands are exact
+// TF32 values: the MMA truncates fp32 operands, unrounded inputs would bias every product towards zero) and a
+// channel-split, fully coalesced NHWC store.  Two CTAs per SM overlap one tile's epilogue with the next
+// tile's loads.  All waits are bounded (trap instead of hanging the GPU).
+//
+// Replaces nn.Conv2d(k=3,p=1)+ReLU(+add, +cat/crop) of reference unet_p.py:105-116,161-166 and
+// unet_p_res.py:150-158,186-189,215-219 for channel counts that are multiples of 8; dgrad is the same kernel
+// on transposed/flipped packed weights.
+#include <cuda.h>
+#include <mutex>
 #include "conv3x3.cuh"
 
 namespace pu {
-bool conv3x3_tc_supported(const Conv3x3Args&) { return false; }
-int conv3x3_fwd_tc(const Conv3x3Args&, cudaStream_t) {
-  set_error("conv3x3_fwd_tc: not built");
-  return PU_ERR_UNSUPPORTED;
+
+constexpr int kMaxChunks = 48;
+constexpr int kCoBlk = 64;  // output channels per CTA (grid.z splits larger Cout)
+
+struct TcChunk {
+  int cgA, nA;  // planes [0, nA): channel groups cgA.. of source srcA
+  int cgB, nB;  // planes [nA, nA+nB): channel groups cgB.. of source 1 (only in a combined chunk)
+  int srcA;
+  unsigned w_off;  // byte offset of this chunk's weights inside one co-block of the packed buffer
+};
+
+struct TcArgs {
+  const float* wpk;
+  const float* bias;
+  const float* res;
+  ViewW d0, d1;
+  int B, H, W, Cout, relu, round_out;
+  int TH, TW, PW, tilesX, tilesY;
+  int nmb, nmma, plane_bytes, a_bytes, w_bytes_max, tmem_cols, nchunks;
+  unsigned w_coblk_stride;  // bytes
+  TcChunk chunks[kMaxChunks];
+};
+
+// ---- PTX wrappers -------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// bounded wait: a lost TMA transaction or MMA commit must not hang the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t it = 0; it < (1u << 22); ++it) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+  }
+  printf("pu conv3x3_tc: mbarrier wait timed out (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x);
+  asm volatile("trap;");
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// SWIZZLE_NONE K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout, version 1)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) |
+         (1ull << 46);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// ---- the kernel ---------------------------------------------------------------------------------
+template <int COLS>
+__global__ void __launch_bounds__(128) conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
+                                                         const TcArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* smA = smem;
+  uint8_t* smW = smem + a.a_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + a.a_bytes + a.w_bytes_max);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  const uint32_t full_bar = smem_u32(&bars[0]), mma_bar = smem_u32(&bars[1]), done_bar = smem_u32(&bars[2]);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tx = blockIdx.x % a.tilesX, ty = blockIdx.x / a.tilesX;
+  const int b = blockIdx.y, coblk = blockIdx.z;
+  const int x0 = tx * a.TW, y0 = ty * a.TH;
+
+  if (warp == 0) {
+    if (tid == 0) {
+      mbar_init(full_bar, 1);
+      mbar_init(mma_bar, 1);
+      mbar_init(done_bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)a.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (tid == 0) {
+    // instruction descriptor: D=f32, A=B=tf32, K-major both, N = nmma, M = 128 (cute::UMMA::InstrDescriptor)
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.nmma >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t sA = smem_u32(smA), sW = smem_u32(smW);
+    const uint8_t* wblk = reinterpret_cast<const uint8_t*>(a.wpk) + (size_t)coblk * a.w_coblk_stride;
+    uint32_t full_phase = 0, mma_phase = 0;
+    for (int c = 0; c < a.nchunks; ++c) {
+      const TcChunk ch = a.chunks[c];
+      if (c > 0) {  // the previous chunk's MMAs must have finished reading shared memory
+        mbar_wait(mma_bar, mma_phase);
+        mma_phase ^= 1;
+      }
+      const int ncg = ch.nA + ch.nB;
+      const uint32_t w_bytes = (uint32_t)(9 * ncg * a.nmma * 16);
+      mbar_expect_tx(full_bar, (uint32_t)(ncg * a.plane_bytes) + w_bytes);
+      tma_load_5d(sA, ch.srcA == 0 ? &tm0 : &tm1, full_bar, 0, x0 - 1, y0 - 1, ch.cgA, b);
+      if (ch.nB > 0) tma_load_5d(sA + ch.nA * a.plane_bytes, &tm1, full_bar, 0, x0 - 1, y0 - 1, ch.cgB, b);
+      bulk_load(sW, wblk + ch.w_off, w_bytes, full_bar);
+      mbar_wait(full_bar, full_phase);
+      full_phase ^= 1;
+      tc_fence_after();
+      const int ksteps = ncg >> 1;
+      for (int mb = 0; mb < a.nmb; ++mb) {
+        const uint32_t d = tmem_base + (uint32_t)(mb * a.nmma);
+        for (int tap = 0; tap < 9; ++tap) {
+          const int ky = tap / 3, kx = tap - 3 * ky;
+          const uint32_t a0 = sA + (uint32_t)((mb * 128 + ky * a.PW + kx) * 16);
+          const uint32_t b0 = sW + (uint32_t)(tap * ncg * a.nmma * 16);
+          for (int ks = 0; ks < ksteps; ++ks) {
+            const uint64_t ad = umma_desc(a0 + (uint32_t)(2 * ks * a.plane_bytes), (uint32_t)a.plane_bytes, 128);
+            const uint64_t bd = umma_desc(b0 + (uint32_t)(2 * ks * a.nmma * 16), (uint32_t)(a.nmma * 16), 128);
+            umma_tf32(d, ad, bd, idesc, (c | tap | ks) ? 1u : 0u);
+          }
+        }
+      }
+      tc_commit(mma_bar);
+    }
+    tc_commit(done_bar);
+  }
+  __syncwarp();
+
+  // ---- epilogue: TMEM -> registers -> bias/residual/ReLU -> NHWC global
+  mbar_wait(done_bar, 0);
+  tc_fence_after();
+  const int co_base = coblk * kCoBlk;
+  float bv[COLS];
+#pragma unroll
+  for (int j = 0; j < COLS; ++j) bv[j] = (a.bias != nullptr && co_base + j < a.Cout) ? __ldg(a.bias + co_base + j) : 0.f;
+  for (int mb = 0; mb < a.nmb; ++mb) {
+    uint32_t v[COLS];
+    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mb * a.nmma);
+    if (COLS == 8) {
+      tmem_ld8(taddr, v);
+    } else {
+#pragma unroll
+      for (int q = 0; q < COLS / 16; ++q) tmem_ld16(taddr + 16 * q, v + 16 * q);
+    }
+    tmem_ld_wait();
+    const int r = mb * 128 + tid;
+    const int yy = r / a.PW, xx = r - yy * a.PW;
+    const int gy = y0 + yy, gx = x0 + xx;
+    if (yy >= a.TH || xx >= a.TW || gy >= a.H || gx >= a.W) continue;
+    const float* rp = a.res != nullptr ? a.res + (((size_t)b * a.H + gy) * a.W + gx) * a.Cout + co_base : nullptr;
+#pragma unroll
+    for (int q = 0; q < COLS / 4; ++q) {
+      const int co = co_base + 4 * q;
+      if (co >= a.Cout) break;
+      float o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[j] = __uint_as_float(v[4 * q + j]) + bv[4 * q + j];
+      if (rp != nullptr) {
+        const float4 rr = ldg4(rp + 4 * q);
+        o[0] += rr.x; o[1] += rr.y; o[2] += rr.z; o[3] += rr.w;
+      }
+      if (a.relu) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = fmaxf(o[j], 0.f);
+      }
+      if (a.round_out) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = round_tf32(o[j]);
+      }
+      const bool first = co < a.d0.C;
+      const ViewW dd = first ? a.d0 : a.d1;
+      const int cd = first ? co : co - a.d0.C;
+      float* dp = dd.p + (((size_t)b * dd.Hs + (gy + dd.oy)) * dd.Ws + (gx + dd.ox)) * dd.C + cd;
+      *reinterpret_cast<float4*>(dp) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)a.tmem_cols) : "memory");
+  }
+}
+
+// ---- weight packing for the tensor-core path ------------------------------------------------------
+// out[coblk][chunk][tap][plane][n][4]  (n < nmma rows, zero beyond the co-block's valid channels), RN-rounded to TF32
+struct TcPackArgs {
+  const float* w;  // OIHW [Cout_w][Cin_w][3][3]
+  float* out;
+  int Cout_w, Cin_w, transpose;  // transpose: conv computes dgrad (input channels = Cout_w, output = Cin_w, taps flipped)
+  int Cin, Cout, C0, nmma, nchunks, ncoblk;
+  unsigned w_coblk_stride;
+  TcChunk chunks[kMaxChunks];
+};
+
+__global__ void pack_w3x3_tc_kernel(const TcPackArgs a) {
+  const int coblk = blockIdx.y, c = blockIdx.z;
+  const TcChunk ch = a.chunks[c];
+  const int ncg = ch.nA + ch.nB;
+  const int n_el = 9 * ncg * a.nmma * 4;
+  float* out = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(a.out) + (size_t)coblk * a.w_coblk_stride + ch.w_off);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_el; i += gridDim.x * blockDim.x) {
+    const int j = i & 3;
+    const int n = (i >> 2) % a.nmma;
+    const int pl = (i / (4 * a.nmma)) % ncg;
+    const int tap = i / (4 * a.nmma * ncg);
+    int ci;  // channel in the concatenated input
+    if (pl < ch.nA) ci = (ch.srcA == 0 ? 0 : a.C0) + (ch.cgA + pl) * 4 + j;
+    else ci = a.C0 + (ch.cgB + pl - ch.nA) * 4 + j;
+    const int co = coblk * kCoBlk + n;
+    float v = 0.f;
+    if (co < a.Cout && n < kCoBlk && ci < a.Cin) {
+      if (!a.transpose) v = a.w[((size_t)co * a.Cin_w + ci) * 9 + tap];
+      else v = a.w[((size_t)ci * a.Cin_w + co) * 9 + (8 - tap)];
+    }
+    out[i] = round_tf32(v);
+  }
+}
+
+// ---- host side ------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn g_encode = nullptr;
+static int g_tc_state = -1;  // -1 unknown, 0 unavailable, 1 available
+static std::mutex g_tc_mu;
+
+static bool tc_init() {
+  std::lock_guard<std::mutex> lk(g_tc_mu);
+  if (g_tc_state >= 0) return g_tc_state == 1;
+  g_tc_state = 0;
+  int dev = 0;
+  cudaDeviceProp prop;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  if (prop.major != 10) return false;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || fn == nullptr ||
+      qres != cudaDriverEntryPointSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  g_tc_state = 1;
+  return true;
+}
+
+struct TcPlan {
+  int TH, TW, PW, tilesX, tilesY, nmb, nmma, cols, plane_bytes, a_bytes, w_bytes_max, tmem_cols, nchunks, ncoblk, kcg0, kcg1;
+  unsigned w_coblk_stride;
+  size_t smem_bytes;
+  TcChunk chunks[kMaxChunks];
+};
+
+static int next_pow2_cols(int c) {
+  int p = 32;
+  while (p < c) p <<= 1;
+  return p;
+}
+
+// returns false if the shape does not fit the tensor-core path
+static bool tc_plan(int B, int H, int W, int C0, int C1, int Cout, TcPlan* p) {
+  if (C0 < 8 || C0 % 8 != 0 || C1 % 8 != 0 || Cout % 8 != 0) return false;
+  const int cg0 = C0 / 4, cg1 = C1 / 4;
+  // chunks of at most 8 channel groups (32 channels); small concat pairs share one chunk
+  p->nchunks = 0;
+  p->kcg0 = cg0 < 8 ? cg0 : 8;
+  p->kcg1 = cg1 == 0 ? 0 : (cg1 < 8 ? cg1 : 8);
+  if (cg0 % p->kcg0 != 0 || (cg1 > 0 && cg1 % p->kcg1 != 0)) return false;
+  const int cout_blk = Cout < kCoBlk ? Cout : kCoBlk;
+  p->cols = cout_blk <= 8 ? 8 : (cout_blk <= 16 ? 16 : (cout_blk <= 32 ? 32 : 64));
+  p->nmma = p->cols < 16 ? 16 : p->cols;
+  p->ncoblk = (Cout + kCoBlk - 1) / kCoBlk;
+  unsigned woff = 0;
+  int max_ncg = 0;
+  auto add = [&](int srcA, int cgA, int nA, int cgB, int nB) {
+    TcChunk& ch = p->chunks[p->nchunks++];
+    ch.srcA = srcA; ch.cgA = cgA; ch.nA = nA; ch.cgB = cgB; ch.nB = nB; ch.w_off = woff;
+    woff += (unsigned)(9 * (nA + nB) * p->nmma * 16);
+    if (nA + nB > max_ncg) max_ncg = nA + nB;
+  };
+  if (cg1 > 0 && cg0 + cg1 <= 8) {
+    add(0, 0, cg0, 0, cg1);
+  } else {
+    if (cg0 / p->kcg0 + (cg1 ? cg1 / p->kcg1 : 0) > kMaxChunks) return false;
+    for (int c = 0; c < cg0; c += p->kcg0) add(0, c, p->kcg0, 0, 0);
+    for (int c = 0; c < cg1; c += p->kcg1) add(1, c, p->kcg1, 0, 0);
+  }
+  p->w_coblk_stride = woff;
+  p->w_bytes_max = ((9 * max_ncg * p->nmma * 16) + 127) / 128 * 128;
+  // tile geometry
+  p->tilesX = (W + 247) / 248;
+  p->TW = (W + p->tilesX - 1) / p->tilesX;
+  p->PW = (p->TW + 2 + 7) / 8 * 8;
+  if (p->PW > 256) return false;
+  const size_t smem_soft = 108 * 1024, smem_hard = 220 * 1024;
+  int best = 0;
+  size_t best_smem = 0;
+  for (int pass = 0; pass < 2 && best == 0; ++pass) {
+    const size_t lim = pass == 0 ? smem_soft : smem_hard;
+    for (int th = (H < 48 ? H : 48); th >= 1; --th) {
+      const int nmb = (th * p->PW + 127) / 128;
+      if (nmb * p->nmma > 256) continue;
+      const int plane_pix = (th + 2) * p->PW;
+      int tail = nmb * 128 + 2 * p->PW + 2 - plane_pix;
+      if (tail < 0) tail = 0;
+      const size_t a_bytes = ((size_t)max_ncg * plane_pix * 16 + (size_t)tail * 16 + 127) / 128 * 128;
+      const size_t total = a_bytes + p->w_bytes_max + 64;
+      if (total > lim) continue;
+      // prefer the largest tile that still gives every SM at least two tiles
+      const long long tiles = (long long)B * ((H + th - 1) / th) * p->tilesX;
+      if (best == 0) { best = th; best_smem = total; }
+      if (tiles >= 2LL * kNumSMs) { best = th; best_smem = total; break; }
+      best = th; best_smem = total;  // keep shrinking until there are enough tiles (or th == 1)
+    }
+  }
+  if (best == 0) return false;
+  p->TH = best;
+  p->tilesY = (H + best - 1) / best;
+  p->nmb = (best * p->PW + 127) / 128;
+  p->plane_bytes = (best + 2) * p->PW * 16;
+  int tail = p->nmb * 128 + 2 * p->PW + 2 - (best + 2) * p->PW;
+  if (tail < 0) tail = 0;
+  p->a_bytes = (int)(((size_t)max_ncg * p->plane_bytes + (size_t)tail * 16 + 127) / 128 * 128);
+  p->tmem_cols = next_pow2_cols(p->nmb * p->nmma);
+  p->smem_bytes = best_smem;
+  (void)best_smem;
+  p->smem_bytes = (size_t)p->a_bytes + p->w_bytes_max + 64;
+  return true;
+}
+
+static int make_tmap(CUtensorMap* tm, const View& v, int B, int H, int W, int PW, int TH, int kcg) {
+  // dims, innermost first: (4 floats, x, y, channel group, image) over the HxW window of the tensor
+  const float* base = v.p + ((size_t)v.oy * v.Ws + v.ox) * v.C;
+  cuuint64_t dims[5] = {4, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(v.C / 4), (cuuint64_t)B};
+  cuuint64_t strides[4] = {(cuuint64_t)v.C * 4, (cuuint64_t)v.Ws * v.C * 4, 16, (cuuint64_t)v.Hs * v.Ws * v.C * 4};
+  cuuint32_t box[5] = {4, (cuuint32_t)PW, (cuuint32_t)(TH + 2), (cuuint32_t)kcg, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("conv3x3_tc: cuTensorMapEncodeTiled failed (CUresult %d) for window %dx%d C=%d box (4,%d,%d,%d,1)", (int)r, H, W, v.C,
+              PW, TH + 2, kcg);
+    return PU_ERR_CUDA;
+  }
+  return PU_OK;
+}
+
+bool conv3x3_tc_ok(int C0, int C1, int Cout, int Cd0, int Cd1) {
+  if (!tc_init()) return false;
+  TcPlan p;
+  if (!tc_plan(1, 8, 8, C0, C1, Cout, &p)) return false;
+  if (Cd0 % 4 != 0 || Cd1 % 4 != 0 || Cd0 + Cd1 != Cout) return false;
+  return true;
+}
+
+long long conv3x3_tc_weight_floats(int C0, int C1, int Cout) {
+  TcPlan p;
+  if (!tc_plan(1, 8, 8, C0, C1, Cout, &p)) return 0;
+  return (long long)p.w_coblk_stride * p.ncoblk / 4;
+}
+
+int conv3x3_tc_pack(const float* w_oihw, float* out, int Cout_w, int Cin_w, int transpose, int C0, cudaStream_t st) {
+  // roles of the conv that will consume the packed weights
+  const int cin = transpose ? Cout_w : Cin_w;
+  const int cout = transpose ? Cin_w : Cout_w;
+  const int c0 = transpose ? Cout_w : C0;
+  TcPlan p;
+  if (!tc_plan(1, 8, 8, c0, cin - c0, cout, &p)) {
+    set_error("pu_pack_w3x3: channels (%d|%d -> %d) do not fit the tcgen05 path", c0, cin - c0, cout);
+    return PU_ERR_UNSUPPORTED;
+  }
+  TcPackArgs pa;
+  pa.w = w_oihw; pa.out = out; pa.Cout_w = Cout_w; pa.Cin_w = Cin_w; pa.transpose = transpose;
+  pa.Cin = cin; pa.Cout = cout; pa.C0 = c0; pa.nmma = p.nmma; pa.nchunks = p.nchunks; pa.ncoblk = p.ncoblk;
+  pa.w_coblk_stride = p.w_coblk_stride;
+  for (int i = 0; i < p.nchunks; ++i) pa.chunks[i] = p.chunks[i];
+  dim3 g(4, p.ncoblk, p.nchunks);
+  pack_w3x3_tc_kernel<<<g, 256, 0, st>>>(pa);
+  return post_launch("pu_pack_w3x3 (tc)");
+}
+
+template <int COLS>
+static int launch_tc(const CUtensorMap& tm0, const CUtensorMap& tm1, const TcArgs& ta, dim3 grid, size_t smem, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel<COLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    if (e != cudaSuccess) {
+      set_error("conv3x3_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return PU_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  conv3x3_tc_kernel<COLS><<<grid, 128, smem, st>>>(tm0, tm1, ta);
+  return post_launch("conv3x3_tc");
+}
+
+int conv3x3_fwd_tc(const Conv3x3Args& a, cudaStream_t st) {
+  if (!tc_init()) {
+    set_error("pu_conv3x3_fwd: PU_MATH_TF32 requested but the tcgen05/TMA path is unavailable on this device");
+    return PU_ERR_UNSUPPORTED;
+  }
+  TcPlan p;
+  const int C1 = (a.s1.p != nullptr) ? a.s1.C : 0;
+  if (!tc_plan(a.B, a.H, a.W, a.s0.C, C1, a.Cout, &p) || a.d0.C % 4 != 0 || (a.d1.p != nullptr && a.d1.C % 4 != 0) || a.B > 65535) {
+    set_error("pu_conv3x3_fwd: PU_MATH_TF32 does not support this shape (C %d|%d -> %d, %dx%d); check pu_conv3x3_tc_ok", a.s0.C, C1,
+              a.Cout, a.H, a.W);
+    return PU_ERR_UNSUPPORTED;
+  }
+  CUtensorMap tm0, tm1;
+  int rc = make_tmap(&tm0, a.s0, a.B, a.H, a.W, p.PW, p.TH, p.kcg0);
+  if (rc) return rc;
+  if (C1 > 0) {
+    rc = make_tmap(&tm1, a.s1, a.B, a.H, a.W, p.PW, p.TH, p.kcg1);
+    if (rc) return rc;
+  } else {
+    tm1 = tm0;
+  }
+  TcArgs ta;
+  ta.wpk = a.wp; ta.bias = a.bias; ta.res = a.res; ta.d0 = a.d0; ta.d1 = a.d1;
+  ta.B = a.B; ta.H = a.H; ta.W = a.W; ta.Cout = a.Cout; ta.relu = a.relu; ta.round_out = a.round_out;
+  ta.TH = p.TH; ta.TW = p.TW; ta.PW = p.PW; ta.tilesX = p.tilesX; ta.tilesY = p.tilesY;
+  ta.nmb = p.nmb; ta.nmma = p.nmma; ta.plane_bytes = p.plane_bytes; ta.a_bytes = p.a_bytes; ta.w_bytes_max = p.w_bytes_max;
+  ta.tmem_cols = p.tmem_cols; ta.nchunks = p.nchunks; ta.w_coblk_stride = p.w_coblk_stride;
+  for (int i = 0; i < p.nchunks; ++i) ta.chunks[i] = p.chunks[i];
+  dim3 grid(p.tilesX * p.tilesY, a.B, p.ncoblk);
+  switch (p.cols) {
+    case 8: return launch_tc<8>(tm0, tm1, ta, grid, p.smem_bytes, st);
+    case 16: return launch_tc<16>(tm0, tm1, ta, grid, p.smem_bytes, st);
+    case 32: return launch_tc<32>(tm0, tm1, ta, grid, p.smem_bytes, st);
+    default: return launch_tc<64>(tm0, tm1, ta, grid, p.smem_bytes, st);
+  }
+}
+
 }  // namespace pu
 
-extern "C" int pu_tc_available(void) { return 0; }
+extern "C" int pu_tc_available(void) { return pu::tc_init() ? 1 : 0; }

@@ -11,7 +11,7 @@ namespace pu {
 // ---------------- 2x2 stride 2 -----------------------------------------------------------------
 // thread = (output pixel, block of 8 co).  w is [Cin][Cout][2][2].
 __global__ void convT2x2_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
-                                    float* __restrict__ y, int B, int H, int W, int Cin, int Cout) {
+                                    float* __restrict__ y, int B, int H, int W, int Cin, int Cout, int flags) {
   extern __shared__ float ws[];  // [4][Cin][8]
   const int co0 = blockIdx.y * 8;
   for (int i = threadIdx.x; i < 4 * Cin * 8; i += blockDim.x) {
@@ -47,6 +47,10 @@ __global__ void convT2x2_fwd_kernel(const float* __restrict__ x, const float* __
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] = fmaf(v, wp[c * 8 + j], acc[j]);
     }
+  }
+  if (flags & PU_FLAG_ROUND_TF32) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = round_tf32(acc[j]);
   }
   float* yp = y + p * Cout + co0;
   if (Cout % 4 == 0 && co0 + 8 <= Cout) {
@@ -93,14 +97,75 @@ __global__ void convT2x2_dx_kernel(const float* __restrict__ dy, const float* __
     if (ci0 + j < Cin) dp[j] = acc[j];
 }
 
-// dw[ci][co][a][c] = sum_{b,i,j} x[b,i,j,ci] dy[b,2i+a,2j+c,co]; one thread per output element,
-// pixel range split over blockIdx.y, fp32 atomics into the pre-zeroed dw.
+// dw[ci][co][a][c] = sum_{b,i,j} x[b,i,j,ci] dy[b,2i+a,2j+c,co].
+// A [Cin x P] . [P x 4*Cout] contraction over the P input pixels.  Block = 256 threads, each owning one
+// (ci, ac, 4 consecutive co) slice = 1024 outputs per block; the block walks its pixel range in chunks
+// staged through shared memory (x rows and the four dy rows of every pixel, coalesced 128-bit loads), so each
+// thread does 1 LDS + 1 LDS.128 per 4 FMA.  Pixel range split over blockIdx.y, fp32 atomics at the end.
+__global__ void __launch_bounds__(256) convT2x2_dw_tiled_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                                float* __restrict__ dw, int B, int H, int W, int Cin, int Cout,
+                                                                int pch) {
+  extern __shared__ __align__(16) float sm[];
+  float* xs = sm;                 // [pch][Cin]
+  float* ds = sm + pch * Cin;     // [pch][4][Cout]
+  const int co4n = Cout >> 2;
+  const long long e = (long long)blockIdx.x * 256 + threadIdx.x;  // ((ci*4 + ac)*co4n + co4)
+  const int co4 = (int)(e % co4n);
+  const int ac = (int)((e / co4n) & 3);
+  const int ci = (int)(e / (4 * co4n));
+  const bool valid = ci < Cin;
+  const long long npix = (long long)B * H * W;
+  const long long per = (npix + gridDim.y - 1) / gridDim.y;
+  const long long p0 = (long long)blockIdx.y * per;
+  const long long p1 = p0 + per < npix ? p0 + per : npix;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int cin4 = Cin >> 2;
+  for (long long pc = p0; pc < p1; pc += pch) {
+    const int np = (int)((p1 - pc) < pch ? (p1 - pc) : pch);
+    __syncthreads();
+    // stage x rows: np * Cin floats, contiguous in global memory
+    for (int i = threadIdx.x; i < np * cin4; i += 256)
+      reinterpret_cast<float4*>(xs)[i] = ldg4(x + pc * Cin + 4 * (size_t)i);
+    // stage the 4 dy rows of every pixel
+    for (int i = threadIdx.x; i < np * 4 * co4n; i += 256) {
+      const int c4 = i % co4n;
+      const int a = (i / co4n) & 3;
+      const int pp = i / (4 * co4n);
+      const long long p = pc + pp;
+      const int jx = (int)(p % W);
+      const int iy = (int)((p / W) % H);
+      const int b = (int)(p / ((long long)W * H));
+      reinterpret_cast<float4*>(ds)[i] =
+          ldg4(dy + (((size_t)b * 2 * H + 2 * iy + (a >> 1)) * 2 * W + 2 * jx + (a & 1)) * Cout + 4 * c4);
+    }
+    __syncthreads();
+    if (valid) {
+#pragma unroll 4
+      for (int pp = 0; pp < np; ++pp) {
+        const float xv = xs[pp * Cin + ci];
+        const float4 g = *reinterpret_cast<const float4*>(ds + ((size_t)pp * 4 + ac) * Cout + 4 * co4);
+        acc.x = fmaf(xv, g.x, acc.x);
+        acc.y = fmaf(xv, g.y, acc.y);
+        acc.z = fmaf(xv, g.z, acc.z);
+        acc.w = fmaf(xv, g.w, acc.w);
+      }
+    }
+  }
+  if (valid) {
+    float* o = dw + ((size_t)ci * Cout + 4 * co4) * 4 + ac;
+    atomicAdd(o + 0, acc.x);
+    atomicAdd(o + 4, acc.y);
+    atomicAdd(o + 8, acc.z);
+    atomicAdd(o + 12, acc.w);
+  }
+}
+
+// generic fallback (ragged channel counts): one thread per output element, pixel range split over blockIdx.y
 __global__ void convT2x2_dw_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw,
                                    int B, int H, int W, int Cin, int Cout) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   const int nout = Cin * Cout * 4;
   if (e >= nout) return;
-  // element order chosen so that adjacent threads read adjacent co of dy: e = ((ci*4 + ac)*Cout + co)
   const int co = e % Cout;
   const int ac = (e / Cout) & 3;
   const int ci = e / (4 * Cout);
@@ -125,7 +190,7 @@ __global__ void convT2x2_dw_kernel(const float* __restrict__ x, const float* __r
 // contributing taps have (fy-ky) even and 0 <= (fy-ky)/2 < H.
 __global__ void convT3x3_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                                     const float* __restrict__ scale, float* __restrict__ y, int B, int H, int W, int Cin, int Cout,
-                                    int Ho, int Wo, int oy, int ox) {
+                                    int Ho, int Wo, int oy, int ox, int flags) {
   extern __shared__ float ws[];  // [9][CK][8], CK = channel chunk
   constexpr int CK = 32;
   const int co0 = blockIdx.y * 8;
@@ -174,6 +239,7 @@ __global__ void convT3x3_fwd_kernel(const float* __restrict__ x, const float* __
     if (co0 + j < Cout) {
       float v = acc[j] + (bias != nullptr ? bias[co0 + j] : 0.f);
       if (scale != nullptr) v *= __ldg(scale + (size_t)b * Cout + co0 + j);
+      if (flags & PU_FLAG_ROUND_TF32) v = round_tf32(v);
       yp[j] = v;
     }
   }
@@ -317,14 +383,15 @@ static int split_for(long long nout_blocks, long long npix) {
 
 extern "C" {
 
-int pu_convT2x2s2_fwd(const float* x, const float* w, const float* bias, float* y, int B, int H, int W, int Cin, int Cout, void* stream) {
+int pu_convT2x2s2_fwd(const float* x, const float* w, const float* bias, float* y, int B, int H, int W, int Cin, int Cout, int flags,
+                      void* stream) {
   PU_REQUIRE(x && w && y && B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, PU_ERR_BAD_ARG, "pu_convT2x2s2_fwd: bad argument");
   const size_t smem = (size_t)4 * Cin * 8 * sizeof(float);
   PU_REQUIRE(smem <= 48 * 1024, PU_ERR_UNSUPPORTED, "pu_convT2x2s2_fwd: Cin=%d > 384", Cin);
   PU_REQUIRE(pu::aligned16(x) && pu::aligned16(y), PU_ERR_BAD_ARG, "pu_convT2x2s2_fwd: pointers not 16-byte aligned");
   const long long npix = (long long)B * 4 * H * W;
   dim3 grid((unsigned)((npix + 255) / 256), pu::cdiv(Cout, 8));
-  pu::convT2x2_fwd_kernel<<<grid, 256, smem, pu::as_stream(stream)>>>(x, w, bias, y, B, H, W, Cin, Cout);
+  pu::convT2x2_fwd_kernel<<<grid, 256, smem, pu::as_stream(stream)>>>(x, w, bias, y, B, H, W, Cin, Cout, flags);
   return pu::post_launch("pu_convT2x2s2_fwd");
 }
 
@@ -348,9 +415,24 @@ int pu_convT2x2s2_bwd(const float* x, const float* w, const float* dy, float* dx
       pu::set_error("pu_convT2x2s2_bwd memset: %s", cudaGetErrorString(e));
       return PU_ERR_CUDA;
     }
-    const int nb = pu::cdiv(nout, 256);
-    dim3 grid(nb, pu::split_for(nb, npix));
-    pu::convT2x2_dw_kernel<<<grid, 256, 0, st>>>(x, dy, dw, B, H, W, Cin, Cout);
+    if (Cin % 4 == 0 && Cout % 4 == 0 && pu::aligned16(x) && pu::aligned16(dy)) {
+      int pch = 10240 / (Cin + 4 * Cout);
+      pch = pch > 64 ? 64 : (pch < 4 ? 4 : pch);
+      const size_t smem = (size_t)pch * (Cin + 4 * Cout) * sizeof(float);
+      PU_REQUIRE(smem <= 48 * 1024, PU_ERR_UNSUPPORTED, "pu_convT2x2s2_bwd: Cin+4*Cout=%d too large", Cin + 4 * Cout);
+      const int nb = pu::cdiv((long long)Cin * Cout, 256);  // 4 outputs per thread
+      long long splits = (4LL * pu::kNumSMs + nb - 1) / nb;
+      const long long maxsplit = (npix + pch - 1) / pch;
+      if (splits > maxsplit) splits = maxsplit;
+      if (splits < 1) splits = 1;
+      if (splits > 65535) splits = 65535;
+      dim3 grid(nb, (unsigned)splits);
+      pu::convT2x2_dw_tiled_kernel<<<grid, 256, smem, st>>>(x, dy, dw, B, H, W, Cin, Cout, pch);
+    } else {
+      const int nb = pu::cdiv(nout, 256);
+      dim3 grid(nb, pu::split_for(nb, npix));
+      pu::convT2x2_dw_kernel<<<grid, 256, 0, st>>>(x, dy, dw, B, H, W, Cin, Cout);
+    }
     int rc = pu::post_launch("pu_convT2x2s2_bwd dw");
     if (rc) return rc;
   }
@@ -359,14 +441,14 @@ int pu_convT2x2s2_bwd(const float* x, const float* w, const float* dy, float* dx
 }
 
 int pu_convT3x3s2_fwd(const float* x, const float* w, const float* bias, const float* chan_scale, float* y, int B, int H, int W,
-                      int Cin, int Cout, int Ho, int Wo, int oy, int ox, void* stream) {
+                      int Cin, int Cout, int Ho, int Wo, int oy, int ox, int flags, void* stream) {
   PU_REQUIRE(x && w && y && B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, PU_ERR_BAD_ARG, "pu_convT3x3s2_fwd: bad argument");
   PU_REQUIRE(oy >= 0 && ox >= 0 && Ho > 0 && Wo > 0 && oy + Ho <= 2 * H + 1 && ox + Wo <= 2 * W + 1, PU_ERR_BAD_ARG,
              "pu_convT3x3s2_fwd: window (%d+%d,%d+%d) exceeds %dx%d", oy, Ho, ox, Wo, 2 * H + 1, 2 * W + 1);
   const size_t smem = (size_t)9 * 32 * 8 * sizeof(float);
   const long long npix = (long long)B * Ho * Wo;
   dim3 grid((unsigned)((npix + 127) / 128), pu::cdiv(Cout, 8));
-  pu::convT3x3_fwd_kernel<<<grid, 128, smem, pu::as_stream(stream)>>>(x, w, bias, chan_scale, y, B, H, W, Cin, Cout, Ho, Wo, oy, ox);
+  pu::convT3x3_fwd_kernel<<<grid, 128, smem, pu::as_stream(stream)>>>(x, w, bias, chan_scale, y, B, H, W, Cin, Cout, Ho, Wo, oy, ox, flags);
   return pu::post_launch("pu_convT3x3s2_fwd");
 }
 

@@ -34,7 +34,7 @@ __device__ __forceinline__ float coord_val(int k, int i, int j, int H, int W) {
 // y[p][co] = act( sum_ci x[p][ci] w[co][ci] + sum_k coord_k(p) w[co][Cin+k] + bias[co] )
 // thread = (pixel, block of 8 co); weights of the co block staged in smem as ws[ci][8]
 __global__ void conv1x1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
-                                   float* __restrict__ y, long long npix, int H, int W, int Cin, int Cout, int coords, int relu) {
+                                   float* __restrict__ y, long long npix, int H, int W, int Cin, int Cout, int coords, int flags) {
   extern __shared__ float ws[];  // [(Cin+coords)][8]
   const int K = Cin + coords;
   const int co0 = blockIdx.y * 8;
@@ -78,7 +78,8 @@ __global__ void conv1x1_fwd_kernel(const float* __restrict__ x, const float* __r
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     if (co0 + j < Cout) {
-      const float v = relu ? fmaxf(acc[j], 0.f) : acc[j];
+      float v = (flags & PU_FLAG_RELU) ? fmaxf(acc[j], 0.f) : acc[j];
+      if (flags & PU_FLAG_ROUND_TF32) v = round_tf32(v);
       yp[j] = v;
     }
   }
@@ -159,7 +160,8 @@ __global__ void chan_scale_kernel(const float* __restrict__ x, const float* __re
   }
 }
 
-__global__ void concat_scale_kernel(View s0, View s1, const float* __restrict__ scale, float* __restrict__ y, int B, int H, int W) {
+__global__ void concat_scale_kernel(View s0, View s1, const float* __restrict__ scale, float* __restrict__ y, int B, int H, int W,
+                                    int flags) {
   const int C = s0.C + s1.C;
   const long long n = (long long)B * H * W * C;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -173,6 +175,7 @@ __global__ void concat_scale_kernel(View s0, View s1, const float* __restrict__ 
     if (c < s0.C) v = __ldg(s0.p + (((size_t)b * s0.Hs + yy + s0.oy) * s0.Ws + xx + s0.ox) * s0.C + c);
     else v = __ldg(s1.p + (((size_t)b * s1.Hs + yy + s1.oy) * s1.Ws + xx + s1.ox) * s1.C + (c - s0.C));
     if (scale != nullptr) v *= __ldg(scale + (size_t)b * C + c);
+    if (flags & PU_FLAG_ROUND_TF32) v = round_tf32(v);
     y[i] = v;
   }
 }
@@ -239,7 +242,7 @@ int pu_nhwc_to_nchw(const float* x, float* y, int B, int C, int H, int W, void* 
 }
 
 int pu_conv1x1_fwd(const float* x, const float* w, const float* bias, float* y, int B, int H, int W, int Cin, int Cout,
-                   int coords, int relu, void* stream) {
+                   int coords, int flags, void* stream) {
   PU_REQUIRE(x && w && y && B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, PU_ERR_BAD_ARG, "pu_conv1x1_fwd: bad argument");
   PU_REQUIRE(coords == 0 || coords == 2 || coords == 3, PU_ERR_BAD_ARG, "pu_conv1x1_fwd: coords must be 0, 2 or 3");
   const size_t smem = (size_t)(Cin + coords) * 8 * sizeof(float);
@@ -247,7 +250,7 @@ int pu_conv1x1_fwd(const float* x, const float* w, const float* bias, float* y, 
   PU_REQUIRE(Cin % 4 != 0 || pu::aligned16(x), PU_ERR_BAD_ARG, "pu_conv1x1_fwd: x not 16-byte aligned");
   const long long npix = (long long)B * H * W;
   dim3 grid((unsigned)((npix + 255) / 256), pu::cdiv(Cout, 8));
-  pu::conv1x1_fwd_kernel<<<grid, 256, smem, pu::as_stream(stream)>>>(x, w, bias, y, npix, H, W, Cin, Cout, coords, relu);
+  pu::conv1x1_fwd_kernel<<<grid, 256, smem, pu::as_stream(stream)>>>(x, w, bias, y, npix, H, W, Cin, Cout, coords, flags);
   return pu::post_launch("pu_conv1x1_fwd");
 }
 
@@ -293,13 +296,13 @@ int pu_chan_scale(const float* x, const float* s, float* y, int B, long long hw,
 }
 
 int pu_concat_scale_fwd(const float* src0, int H0, int W0, int C0, int oy0, int ox0, const float* src1, int H1, int W1, int C1,
-                        int oy1, int ox1, const float* chan_scale, float* y, int B, int H, int W, void* stream) {
+                        int oy1, int ox1, const float* chan_scale, float* y, int B, int H, int W, int flags, void* stream) {
   PU_REQUIRE(src0 && src1 && y && B > 0 && H > 0 && W > 0 && C0 > 0 && C1 > 0, PU_ERR_BAD_ARG, "pu_concat_scale_fwd: bad argument");
   PU_REQUIRE(oy0 >= 0 && ox0 >= 0 && oy0 + H <= H0 && ox0 + W <= W0 && oy1 >= 0 && ox1 >= 0 && oy1 + H <= H1 && ox1 + W <= W1,
              PU_ERR_BAD_ARG, "pu_concat_scale_fwd: window exceeds source");
   pu::View s0{src0, H0, W0, C0, oy0, ox0}, s1{src1, H1, W1, C1, oy1, ox1};
   const long long n = (long long)B * H * W * (C0 + C1);
-  pu::concat_scale_kernel<<<pu::ew_grid(n), 256, 0, pu::as_stream(stream)>>>(s0, s1, chan_scale, y, B, H, W);
+  pu::concat_scale_kernel<<<pu::ew_grid(n), 256, 0, pu::as_stream(stream)>>>(s0, s1, chan_scale, y, B, H, W, flags);
   return pu::post_launch("pu_concat_scale_fwd");
 }
 

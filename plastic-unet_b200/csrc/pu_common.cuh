@@ -49,6 +49,14 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
+// round-to-nearest to TF32 precision (10-bit mantissa).  tcgen05 kind::tf32 TRUNCATES fp32 operands, so every
+// tensor that feeds a tensor-core conv is stored already rounded by its producer's epilogue.
+__device__ __forceinline__ float round_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
 // streaming (read-once) 128-bit load that does not allocate in L1
 __device__ __forceinline__ float4 ldg4_stream(const float* p) {
   float4 r;

@@ -41,13 +41,14 @@ def _c3(x0, conv, relu, x1=None, res=None, H=None, W=None, off0=(0, 0), off1=(0,
     return ops.conv3x3(x0, x1, conv.weight, conv.bias, res, relu, H, W, off0[0], off0[1], off1[0], off1[1], math)
 
 
-def _bn(x, bn, relu):
+def _bn(x, bn, relu, math=ops.MATH_FP32):
     """BatchNorm2d over NHWC with the parameters/buffers held by `bn` (+ optional fused ReLU)."""
     train = bn.training or (bn.running_mean is None)
     if train and bn.track_running_stats and bn.num_batches_tracked is not None:
         bn.num_batches_tracked.add_(1)
     momentum = 0.1 if bn.momentum is None else bn.momentum
-    y, mean, invstd = ops.batchnorm(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, train, momentum, bn.eps, relu)
+    y, mean, invstd = ops.batchnorm(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, train, momentum, bn.eps, relu,
+                                    math == ops.MATH_TF32)
     if train and bn.track_running_stats:
         ops.bn_update_running(mean.detach(), invstd.detach(), bn.running_mean, bn.running_var, momentum, bn.eps,
                               x.numel() // x.shape[-1])
@@ -158,9 +159,9 @@ class double_conv(nn.Module):
     def run(self, x0, math, x1=None, H=None, W=None, off0=(0, 0), off1=(0, 0)):
         if self.batch_norm:
             y = _c3(x0, self.conv[0], False, x1=x1, H=H, W=W, off0=off0, off1=off1, math=math)
-            y = _bn(y, self.conv[1], True)
+            y = _bn(y, self.conv[1], True, math)
             y = _c3(y, self.conv[3], False, math=math)
-            return _bn(y, self.conv[4], True)
+            return _bn(y, self.conv[4], True, math)
         y = _c3(x0, self.conv[0], True, x1=x1, H=H, W=W, off0=off0, off1=off1, math=math)
         return _c3(y, self.conv[2], True, math=math)
 
@@ -197,7 +198,7 @@ class up(nn.Module):
         self.conv = double_conv(in_ch, out_ch, batch_norm)
 
     def run(self, x1, x2, math):
-        u = ops.bilinear2x(x1) if self.bilinear else ops.convT2x2s2(x1, self.up.weight, self.up.bias)
+        u = ops.bilinear2x(x1) if self.bilinear else ops.convT2x2s2(x1, self.up.weight, self.up.bias, math == ops.MATH_TF32)
         diffX = u.shape[1] - x2.shape[1]  # reference names: size()[2] == H
         diffY = u.shape[2] - x2.shape[2]
         # F.pad(x2, (diffX//2, int(diffX/2), diffY//2, int(diffY/2))): first pair pads W, second pair pads H
@@ -281,7 +282,7 @@ class conv_module(nn.Module):
     def run(self, x, math, res=None, relu_after_res=False):
         if self.batch_norm:
             y = _c3(x, self.conv[0], False, math=math)
-            y = _bn(y, self.conv[1], self.activation)
+            y = _bn(y, self.conv[1], self.activation, math)
             if res is not None:
                 raise RuntimeError("conv_module with BN cannot fuse a residual")
             return y
@@ -307,7 +308,7 @@ class residual_block(nn.Module):
     def run(self, r, math):
         """r is already relu(input).  Returns relu(conv2(relu(conv1([BN] r))) + r)."""
         if self.batch_norm:
-            a = self.conv[2].run(_bn(r, self.conv[1], False), math)
+            a = self.conv[2].run(_bn(r, self.conv[1], False, math), math)
             return self.conv[3].run(a, math, res=r, relu_after_res=True)
         a = self.conv[1].run(r, math)
         return self.conv[2].run(a, math, res=r, relu_after_res=True)
@@ -382,11 +383,11 @@ class res_up(nn.Module):
         if Ho != x2.shape[1] or Wo != x2.shape[2]:
             raise RuntimeError("Sizes of tensors must match except in dimension 1")
         oy, ox = -(diffY // 2), -(diffX // 2)
-        u = ops.convT3x3s2(x1, self.dconv.weight, self.dconv.bias, None, Ho, Wo, oy, ox)
+        u = ops.convT3x3s2(x1, self.dconv.weight, self.dconv.bias, None, Ho, Wo, oy, ox, math == ops.MATH_TF32)
         p = self.uconv[0].p
         if self.training and p > 0:
             scale = _feature_noise(u.shape[0], u.shape[3] + x2.shape[3], p, u.device)
-            cat = ops.concat_scale(u, x2, scale, Ho, Wo, 0, 0, 0, 0)
+            cat = ops.concat_scale(u, x2, scale, Ho, Wo, 0, 0, 0, 0, math == ops.MATH_TF32)
             return self.uconv[1].run(cat, math)
         return self.uconv[1].run(u, math, x1=x2, H=Ho, W=Wo)
 
@@ -445,9 +446,9 @@ class coord_stem(nn.Module):
         self.coords = 3 if with_r else 2
         self.conv = nn.Conv2d(in_ch + self.coords, out_ch, 1)
 
-    def run(self, x):
+    def run(self, x, math=ops.MATH_FP32):
         w = self.conv.weight
-        return ops.conv1x1(x, w.view(w.shape[0], w.shape[1]), self.conv.bias, self.coords, True)
+        return ops.conv1x1(x, w.view(w.shape[0], w.shape[1]), self.conv.bias, self.coords, True, math == ops.MATH_TF32)
 
 
 class coord_up(nn.Module):
@@ -459,7 +460,7 @@ class coord_up(nn.Module):
         self.conv = double_conv(2 * out_ch, out_ch, False)
 
     def run(self, x1, x2, math):
-        u = ops.convT2x2s2(x1, self.up.weight, self.up.bias)
+        u = ops.convT2x2s2(x1, self.up.weight, self.up.bias, math == ops.MATH_TF32)
         if u.shape[1] != x2.shape[1] or u.shape[2] != x2.shape[2]:
             raise RuntimeError("UNetpCoord needs H, W divisible by 16 (Keras 'same' padding has no crop)")
         return self.conv.run(u, math, x1=x2)
@@ -489,7 +490,7 @@ class UNetpCoord(_PlasticBase):
             raise ValueError("Only batch size: 1 is supported, but was: %d" % x.shape[0])
         m = self._math
         x = self._to_nhwc(x)
-        feats = [self.enc0.run(self.stem.run(x), m)]
+        feats = [self.enc0.run(self.stem.run(x, m), m)]
         for k in range(1, self.depth + 1):
             feats.append(getattr(self, "enc%d" % k).run(feats[-1], m))
         y = feats[-1]

@@ -12,10 +12,28 @@ from torch import Tensor
 
 from . import _lib
 
+import functools
+
 MATH_FP32 = 0
 MATH_TF32 = 1
 RULE_HEBB = 0
 RULE_OJA = 1
+FLAG_RELU = 1
+FLAG_ROUND_TF32 = 2
+
+
+@functools.lru_cache(maxsize=None)
+def _tc_ok(C0: int, C1: int, Cout: int, Cd0: int, Cd1: int) -> bool:
+    """Can a conv3x3 with these source/destination channel splits run on the tcgen05 path?"""
+    return bool(_lib.load().pu_conv3x3_tc_ok(C0, C1, Cout, Cd0, Cd1))
+
+
+def _pack_w(weight: Tensor, transpose: int, math: int, C0: int) -> Tensor:
+    Cout, Cin = weight.shape[0], weight.shape[1]
+    n = int(_lib.load().pu_pack_w3x3_floats(Cout, Cin, transpose, math, C0))
+    wp = torch.empty(n, device=weight.device, dtype=torch.float32)
+    _lib.call("pu_pack_w3x3", weight.data_ptr(), wp.data_ptr(), Cout, Cin, transpose, math, C0, _s())
+    return wp
 
 
 def _s() -> int:
@@ -38,6 +56,11 @@ def _chk(*ts: Optional[Tensor]) -> None:
             raise RuntimeError("pu_b200 ops need contiguous NHWC tensors")
 
 
+def _e(dev) -> Tensor:
+    """A fresh empty placeholder (custom-op outputs may not alias each other)."""
+    return torch.empty(0, device=dev, dtype=torch.float32)
+
+
 def _dims(t: Optional[Tensor]) -> Tuple[int, int, int]:
     """(H, W, C) of an NHWC tensor, zeros for None."""
     if t is None:
@@ -58,12 +81,14 @@ def conv3x3(x0: Tensor, x1: Optional[Tensor], weight: Tensor, bias: Optional[Ten
     H1, W1, C1 = _dims(x1)
     if C0 + C1 != Cin:
         raise RuntimeError(f"conv3x3: weight expects {Cin} input channels, sources have {C0}+{C1}")
-    wp = torch.empty(9 * Cin * Cout, device=x0.device, dtype=torch.float32)
-    _lib.call("pu_pack_w3x3", weight.data_ptr(), wp.data_ptr(), Cout, Cin, 0, _s())
+    # PU_MATH_TF32: tcgen05 kernel where the channel counts allow, fp32 FFMA kernel (output rounded to TF32) elsewhere
+    m = MATH_TF32 if (math == MATH_TF32 and _tc_ok(C0, C1, Cout, Cout, 0)) else MATH_FP32
+    flags = (FLAG_RELU if relu else 0) | (FLAG_ROUND_TF32 if math == MATH_TF32 else 0)
+    wp = _pack_w(weight, 0, m, C0)
     y = torch.empty((B, H, W, Cout), device=x0.device, dtype=torch.float32)
     _lib.call("pu_conv3x3_fwd", x0.data_ptr(), H0, W0, C0, oy0, ox0, _p(x1), H1, W1, C1, oy1, ox1,
-              wp.data_ptr(), _p(bias), _p(res), int(relu),
-              y.data_ptr(), H, W, Cout, 0, 0, None, 0, 0, 0, 0, 0, B, H, W, Cout, math, _s())
+              wp.data_ptr(), _p(bias), _p(res), flags,
+              y.data_ptr(), H, W, Cout, 0, 0, None, 0, 0, 0, 0, 0, B, H, W, Cout, m, _s())
     return y
 
 
@@ -84,42 +109,44 @@ def conv3x3_bwd(dy: Tensor, y: Tensor, x0: Tensor, x1: Optional[Tensor], weight:
     H0, W0, C0 = _dims(x0)
     H1, W1, C1 = _dims(x1)
     npix = B * H * W
-    empty = torch.empty(0, device=dev, dtype=torch.float32)
-    db = torch.empty(Cout, device=dev, dtype=torch.float32) if has_bias else empty
-    if relu:
+    db = torch.empty(Cout, device=dev, dtype=torch.float32) if has_bias else _e(dev)
+    tf32 = math == MATH_TF32
+    fresh_g = relu or tf32  # tensor-core operands are stored rounded to TF32 by their producer
+    if fresh_g:
         g = torch.empty_like(dy)
-        _lib.call("pu_relu_bwd_bias", dy.data_ptr(), y.data_ptr(), g.data_ptr(), _p(db) if has_bias else None, npix, Cout, 1, _s())
+        _lib.call("pu_relu_bwd_bias", dy.data_ptr(), y.data_ptr() if relu else None, g.data_ptr(), _p(db) if has_bias else None,
+                  npix, Cout, (FLAG_RELU if relu else 0) | (FLAG_ROUND_TF32 if tf32 else 0), _s())
     else:
         g = dy
         if has_bias:
             _lib.call("pu_relu_bwd_bias", dy.data_ptr(), None, None, db.data_ptr(), npix, Cout, 0, _s())
-    dx0, dx1 = empty, empty
+    dx0, dx1 = _e(dev), _e(dev)
     if need_dx:
-        wpt = torch.empty(9 * Cin * Cout, device=dev, dtype=torch.float32)
-        _lib.call("pu_pack_w3x3", weight.data_ptr(), wpt.data_ptr(), Cout, Cin, 1, _s())
+        md = MATH_TF32 if (tf32 and _tc_ok(Cout, 0, Cin, C0, C1)) else MATH_FP32
+        wpt = _pack_w(weight, 1, md, 0)
         full0 = (H0 == H and W0 == W)
         dx0 = (torch.empty if full0 else torch.zeros)((B, H0, W0, C0), device=dev, dtype=torch.float32)
         if x1 is not None:
             full1 = (H1 == H and W1 == W)
             dx1 = (torch.empty if full1 else torch.zeros)((B, H1, W1, C1), device=dev, dtype=torch.float32)
         _lib.call("pu_conv3x3_fwd", g.data_ptr(), H, W, Cout, 0, 0, None, 0, 0, 0, 0, 0,
-                  wpt.data_ptr(), None, None, 0,
+                  wpt.data_ptr(), None, None, FLAG_ROUND_TF32 if tf32 else 0,
                   dx0.data_ptr(), H0, W0, C0, oy0, ox0,
                   dx1.data_ptr() if x1 is not None else None, H1, W1, C1, oy1, ox1,
-                  B, H, W, Cin, math, _s())
-    dw = empty
+                  B, H, W, Cin, md, _s())
+    dw = _e(dev)
     if need_dw:
         dw = torch.empty_like(weight)
         _lib.call("pu_conv3x3_wgrad", x0.data_ptr(), H0, W0, C0, oy0, ox0, _p(x1), H1, W1, C1, oy1, ox1,
-                  g.data_ptr(), dw.data_ptr(), B, H, W, Cout, math, _s())
-    g_out = g if relu else empty  # never return an alias of an input
+                  g.data_ptr(), dw.data_ptr(), B, H, W, Cout, MATH_FP32, _s())
+    g_out = g if fresh_g else _e(dev)  # never return an alias of an input
     return [g_out, dx0, dx1, dw, db]
 
 
 @conv3x3_bwd.register_fake
 def _(dy, y, x0, x1, weight, has_bias, relu, H, W, oy0, ox0, oy1, ox1, math, need_dx, need_dw):
     e = dy.new_empty(0)
-    return [torch.empty_like(dy) if relu else e,
+    return [torch.empty_like(dy) if (relu or math == MATH_TF32) else e,
             torch.empty_like(x0) if need_dx else e,
             torch.empty_like(x1) if (need_dx and x1 is not None) else e,
             torch.empty_like(weight) if need_dw else e,
@@ -142,7 +169,7 @@ def _conv3x3_backward(ctx, dy):
                                       need_dx, need[2])
     gres = None
     if has_res and need[4]:
-        gres = g if relu else dy
+        gres = g if (relu or math == MATH_TF32) else dy
     return (dx0 if need[0] else None, dx1 if (x1 is not None and need[1]) else None, dw if need[2] else None,
             db if (has_bias and need[3]) else None, gres, None, None, None, None, None, None, None, None)
 
@@ -154,19 +181,20 @@ conv3x3.register_autograd(_conv3x3_backward, setup_context=_conv3x3_setup)
 # conv1x1 (+ analytic CoordConv channels, + ReLU)
 # =================================================================================================
 @torch.library.custom_op("pu::conv1x1", mutates_args=())
-def conv1x1(x: Tensor, weight: Tensor, bias: Optional[Tensor], coords: int, relu: bool) -> Tensor:
+def conv1x1(x: Tensor, weight: Tensor, bias: Optional[Tensor], coords: int, relu: bool, round_out: bool = False) -> Tensor:
     _chk(x, weight, bias)
     B, H, W, Cin = x.shape
     Cout = weight.shape[0]
     if weight.shape[1] != Cin + coords:
         raise RuntimeError("conv1x1: weight/in-channel mismatch")
     y = torch.empty((B, H, W, Cout), device=x.device, dtype=torch.float32)
-    _lib.call("pu_conv1x1_fwd", x.data_ptr(), weight.data_ptr(), _p(bias), y.data_ptr(), B, H, W, Cin, Cout, coords, int(relu), _s())
+    _lib.call("pu_conv1x1_fwd", x.data_ptr(), weight.data_ptr(), _p(bias), y.data_ptr(), B, H, W, Cin, Cout, coords,
+              (FLAG_RELU if relu else 0) | (FLAG_ROUND_TF32 if round_out else 0), _s())
     return y
 
 
 @conv1x1.register_fake
-def _(x, weight, bias, coords, relu):
+def _(x, weight, bias, coords, relu, round_out=False):
     return x.new_empty((x.shape[0], x.shape[1], x.shape[2], weight.shape[0]))
 
 
@@ -180,7 +208,7 @@ def conv1x1_bwd(dy: Tensor, y: Tensor, x: Tensor, weight: Tensor, coords: int, r
     if relu:
         g = torch.empty_like(dy)
         _lib.call("pu_relu_bwd_bias", dy.data_ptr(), y.data_ptr(), g.data_ptr(), None, B * H * W, Cout, 1, _s())
-    dx = torch.empty_like(x) if need_dx else torch.empty(0, device=dev)
+    dx = torch.empty_like(x) if need_dx else _e(dev)
     dw = torch.empty_like(weight)
     db = torch.empty(Cout, device=dev, dtype=torch.float32)
     ws = torch.empty(Cout * (Cin + coords + 1), device=dev, dtype=torch.float32)
@@ -195,7 +223,7 @@ def _(dy, y, x, weight, coords, relu, need_dx):
 
 
 def _conv1x1_setup(ctx, inputs, output):
-    x, weight, bias, coords, relu = inputs
+    x, weight, bias, coords, relu, _round = inputs
     ctx.save_for_backward(x, weight, output)
     ctx.cfg = (bias is not None, coords, relu)
 
@@ -205,7 +233,7 @@ def _conv1x1_backward(ctx, dy):
     has_bias, coords, relu = ctx.cfg
     need = ctx.needs_input_grad
     dx, dw, db = conv1x1_bwd(dy.contiguous(), y, x, weight, coords, relu, need[0])
-    return dx if need[0] else None, dw if need[1] else None, db if (has_bias and need[2]) else None, None, None
+    return dx if need[0] else None, dw if need[1] else None, db if (has_bias and need[2]) else None, None, None, None
 
 
 conv1x1.register_autograd(_conv1x1_backward, setup_context=_conv1x1_setup)
@@ -215,17 +243,18 @@ conv1x1.register_autograd(_conv1x1_backward, setup_context=_conv1x1_setup)
 # transposed convolutions
 # =================================================================================================
 @torch.library.custom_op("pu::convT2x2s2", mutates_args=())
-def convT2x2s2(x: Tensor, weight: Tensor, bias: Optional[Tensor]) -> Tensor:
+def convT2x2s2(x: Tensor, weight: Tensor, bias: Optional[Tensor], round_out: bool = False) -> Tensor:
     _chk(x, weight, bias)
     B, H, W, Cin = x.shape
     Cout = weight.shape[1]
     y = torch.empty((B, 2 * H, 2 * W, Cout), device=x.device, dtype=torch.float32)
-    _lib.call("pu_convT2x2s2_fwd", x.data_ptr(), weight.data_ptr(), _p(bias), y.data_ptr(), B, H, W, Cin, Cout, _s())
+    _lib.call("pu_convT2x2s2_fwd", x.data_ptr(), weight.data_ptr(), _p(bias), y.data_ptr(), B, H, W, Cin, Cout,
+              FLAG_ROUND_TF32 if round_out else 0, _s())
     return y
 
 
 @convT2x2s2.register_fake
-def _(x, weight, bias):
+def _(x, weight, bias, round_out=False):
     return x.new_empty((x.shape[0], 2 * x.shape[1], 2 * x.shape[2], weight.shape[1]))
 
 
@@ -234,10 +263,9 @@ def convT2x2s2_bwd(dy: Tensor, x: Tensor, weight: Tensor, need_dx: bool, need_dw
     _chk(dy, x, weight)
     B, H, W, Cin = x.shape
     Cout = weight.shape[1]
-    e = torch.empty(0, device=x.device)
-    dx = torch.empty_like(x) if need_dx else e
-    dw = torch.empty_like(weight) if need_dw else e
-    db = torch.empty(Cout, device=x.device, dtype=torch.float32) if need_db else e
+    dx = torch.empty_like(x) if need_dx else _e(x.device)
+    dw = torch.empty_like(weight) if need_dw else _e(x.device)
+    db = torch.empty(Cout, device=x.device, dtype=torch.float32) if need_db else _e(x.device)
     _lib.call("pu_convT2x2s2_bwd", x.data_ptr(), weight.data_ptr(), dy.data_ptr(), dx.data_ptr() if need_dx else None,
               dw.data_ptr() if need_dw else None, db.data_ptr() if need_db else None, B, H, W, Cin, Cout, _s())
     return [dx, dw, db]
@@ -251,7 +279,7 @@ def _(dy, x, weight, need_dx, need_dw, need_db):
 
 
 def _convT2_setup(ctx, inputs, output):
-    x, weight, bias = inputs
+    x, weight, bias, _round = inputs
     ctx.save_for_backward(x, weight)
     ctx.has_bias = bias is not None
 
@@ -260,7 +288,7 @@ def _convT2_backward(ctx, dy):
     x, weight = ctx.saved_tensors
     need = ctx.needs_input_grad
     dx, dw, db = convT2x2s2_bwd(dy.contiguous(), x, weight, need[0], need[1], ctx.has_bias and need[2])
-    return dx if need[0] else None, dw if need[1] else None, db if (ctx.has_bias and need[2]) else None
+    return dx if need[0] else None, dw if need[1] else None, db if (ctx.has_bias and need[2]) else None, None
 
 
 convT2x2s2.register_autograd(_convT2_backward, setup_context=_convT2_setup)
@@ -268,18 +296,18 @@ convT2x2s2.register_autograd(_convT2_backward, setup_context=_convT2_setup)
 
 @torch.library.custom_op("pu::convT3x3s2", mutates_args=())
 def convT3x3s2(x: Tensor, weight: Tensor, bias: Optional[Tensor], chan_scale: Optional[Tensor],
-               Ho: int, Wo: int, oy: int, ox: int) -> Tensor:
+               Ho: int, Wo: int, oy: int, ox: int, round_out: bool = False) -> Tensor:
     _chk(x, weight, bias, chan_scale)
     B, H, W, Cin = x.shape
     Cout = weight.shape[1]
     y = torch.empty((B, Ho, Wo, Cout), device=x.device, dtype=torch.float32)
     _lib.call("pu_convT3x3s2_fwd", x.data_ptr(), weight.data_ptr(), _p(bias), _p(chan_scale), y.data_ptr(),
-              B, H, W, Cin, Cout, Ho, Wo, oy, ox, _s())
+              B, H, W, Cin, Cout, Ho, Wo, oy, ox, FLAG_ROUND_TF32 if round_out else 0, _s())
     return y
 
 
 @convT3x3s2.register_fake
-def _(x, weight, bias, chan_scale, Ho, Wo, oy, ox):
+def _(x, weight, bias, chan_scale, Ho, Wo, oy, ox, round_out=False):
     return x.new_empty((x.shape[0], Ho, Wo, weight.shape[1]))
 
 
@@ -290,10 +318,9 @@ def convT3x3s2_bwd(dy: Tensor, x: Tensor, weight: Tensor, chan_scale: Optional[T
     B, H, W, Cin = x.shape
     Cout = weight.shape[1]
     Ho, Wo = dy.shape[1], dy.shape[2]
-    e = torch.empty(0, device=x.device)
-    dx = torch.empty_like(x) if need_dx else e
-    dw = torch.empty_like(weight) if need_dw else e
-    db = torch.empty(Cout, device=x.device, dtype=torch.float32) if need_db else e
+    dx = torch.empty_like(x) if need_dx else _e(x.device)
+    dw = torch.empty_like(weight) if need_dw else _e(x.device)
+    db = torch.empty(Cout, device=x.device, dtype=torch.float32) if need_db else _e(x.device)
     _lib.call("pu_convT3x3s2_bwd", x.data_ptr(), weight.data_ptr(), dy.data_ptr(), _p(chan_scale),
               dx.data_ptr() if need_dx else None, dw.data_ptr() if need_dw else None, db.data_ptr() if need_db else None,
               B, H, W, Cin, Cout, Ho, Wo, oy, ox, _s())
@@ -308,7 +335,7 @@ def _(dy, x, weight, chan_scale, oy, ox, need_dx, need_dw, need_db):
 
 
 def _convT3_setup(ctx, inputs, output):
-    x, weight, bias, chan_scale, Ho, Wo, oy, ox = inputs
+    x, weight, bias, chan_scale, Ho, Wo, oy, ox, _round = inputs
     ctx.save_for_backward(x, weight, chan_scale)
     ctx.cfg = (bias is not None, oy, ox)
 
@@ -318,7 +345,7 @@ def _convT3_backward(ctx, dy):
     has_bias, oy, ox = ctx.cfg
     need = ctx.needs_input_grad
     dx, dw, db = convT3x3s2_bwd(dy.contiguous(), x, weight, chan_scale, oy, ox, need[0], need[1], has_bias and need[2])
-    return dx if need[0] else None, dw if need[1] else None, db if (has_bias and need[2]) else None, None, None, None, None, None
+    return dx if need[0] else None, dw if need[1] else None, db if (has_bias and need[2]) else None, None, None, None, None, None, None
 
 
 convT3x3s2.register_autograd(_convT3_backward, setup_context=_convT3_setup)
@@ -404,19 +431,19 @@ bilinear2x.register_autograd(lambda ctx, dy: bilinear2x_bwd(dy.contiguous()), se
 # =================================================================================================
 @torch.library.custom_op("pu::concat_scale", mutates_args=())
 def concat_scale(x0: Tensor, x1: Tensor, chan_scale: Optional[Tensor], H: int, W: int,
-                 oy0: int, ox0: int, oy1: int, ox1: int) -> Tensor:
+                 oy0: int, ox0: int, oy1: int, ox1: int, round_out: bool = False) -> Tensor:
     _chk(x0, x1, chan_scale)
     B = x0.shape[0]
     H0, W0, C0 = _dims(x0)
     H1, W1, C1 = _dims(x1)
     y = torch.empty((B, H, W, C0 + C1), device=x0.device, dtype=torch.float32)
     _lib.call("pu_concat_scale_fwd", x0.data_ptr(), H0, W0, C0, oy0, ox0, x1.data_ptr(), H1, W1, C1, oy1, ox1,
-              _p(chan_scale), y.data_ptr(), B, H, W, _s())
+              _p(chan_scale), y.data_ptr(), B, H, W, FLAG_ROUND_TF32 if round_out else 0, _s())
     return y
 
 
 @concat_scale.register_fake
-def _(x0, x1, chan_scale, H, W, oy0, ox0, oy1, ox1):
+def _(x0, x1, chan_scale, H, W, oy0, ox0, oy1, ox1, round_out=False):
     return x0.new_empty((x0.shape[0], H, W, x0.shape[3] + x1.shape[3]))
 
 
@@ -441,7 +468,7 @@ def _(dy, chan_scale, shape0, shape1, oy0, ox0, oy1, ox1):
 
 
 def _cat_setup(ctx, inputs, output):
-    x0, x1, chan_scale, H, W, oy0, ox0, oy1, ox1 = inputs
+    x0, x1, chan_scale, H, W, oy0, ox0, oy1, ox1, _round = inputs
     ctx.save_for_backward(chan_scale)
     ctx.cfg = (list(x0.shape), list(x1.shape), oy0, ox0, oy1, ox1)
 
@@ -450,7 +477,7 @@ def _cat_backward(ctx, dy):
     (chan_scale,) = ctx.saved_tensors
     s0, s1, oy0, ox0, oy1, ox1 = ctx.cfg
     dx0, dx1 = concat_scale_bwd(dy.contiguous(), chan_scale, s0, s1, oy0, ox0, oy1, ox1)
-    return dx0, dx1, None, None, None, None, None, None, None
+    return dx0, dx1, None, None, None, None, None, None, None, None
 
 
 concat_scale.register_autograd(_cat_backward, setup_context=_cat_setup)
@@ -461,7 +488,7 @@ concat_scale.register_autograd(_cat_backward, setup_context=_cat_setup)
 # =================================================================================================
 @torch.library.custom_op("pu::batchnorm", mutates_args=())
 def batchnorm(x: Tensor, gamma: Tensor, beta: Tensor, running_mean: Tensor, running_var: Tensor,
-              train: bool, momentum: float, eps: float, relu: bool) -> Tuple[Tensor, Tensor, Tensor]:
+              train: bool, momentum: float, eps: float, relu: bool, round_out: bool = False) -> Tuple[Tensor, Tensor, Tensor]:
     """-> [y, mean, invstd] (the statistics the backward needs)."""
     _chk(x, gamma, beta, running_mean, running_var)
     C = x.shape[-1]
@@ -469,14 +496,15 @@ def batchnorm(x: Tensor, gamma: Tensor, beta: Tensor, running_mean: Tensor, runn
     y = torch.empty_like(x)
     mean = torch.empty(C, device=x.device, dtype=torch.float32)
     invstd = torch.empty(C, device=x.device, dtype=torch.float32)
+    fl = (FLAG_RELU if relu else 0) | (FLAG_ROUND_TF32 if round_out else 0)
     if train:
         ws = torch.empty(2 * C, device=x.device, dtype=torch.float64)
         _lib.call("pu_bn_train_fwd", x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), mean.data_ptr(),
                   invstd.data_ptr(), None, None, ws.data_ptr(),
-                  float(momentum), float(eps), npix, C, int(relu), _s())
+                  float(momentum), float(eps), npix, C, fl, _s())
     else:
         _lib.call("pu_bn_eval_fwd", x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), running_mean.data_ptr(),
-                  running_var.data_ptr(), y.data_ptr(), float(eps), npix, C, int(relu), _s())
+                  running_var.data_ptr(), y.data_ptr(), float(eps), npix, C, fl, _s())
         mean.copy_(running_mean)
         _lib.call("pu_bn_invstd", running_var.data_ptr(), invstd.data_ptr(), float(eps), C, _s())
     return y, mean, invstd
@@ -492,7 +520,7 @@ def bn_update_running(mean: Tensor, invstd: Tensor, running_mean: Tensor, runnin
 
 
 @batchnorm.register_fake
-def _(x, gamma, beta, running_mean, running_var, train, momentum, eps, relu):
+def _(x, gamma, beta, running_mean, running_var, train, momentum, eps, relu, round_out=False):
     C = x.shape[-1]
     return torch.empty_like(x), x.new_empty(C), x.new_empty(C)
 
@@ -519,7 +547,7 @@ def _(dy, x, y, gamma, mean, invstd, relu, train):
 
 
 def _bn_setup(ctx, inputs, output):
-    x, gamma, beta, running_mean, running_var, train, momentum, eps, relu = inputs
+    x, gamma, beta, running_mean, running_var, train, momentum, eps, relu, _round = inputs
     y, mean, invstd = output
     ctx.save_for_backward(x, y, gamma, mean, invstd)
     ctx.cfg = (relu, train)
@@ -529,7 +557,7 @@ def _bn_backward(ctx, dy, _dmean, _dinvstd):
     x, y, gamma, mean, invstd = ctx.saved_tensors
     relu, train = ctx.cfg
     dx, dgamma, dbeta = batchnorm_bwd(dy.contiguous(), x, y, gamma, mean, invstd, relu, train)
-    return dx, dgamma, dbeta, None, None, None, None, None, None
+    return dx, dgamma, dbeta, None, None, None, None, None, None, None
 
 
 batchnorm.register_autograd(_bn_backward, setup_context=_bn_setup)
@@ -599,12 +627,11 @@ def plastic_head_bwd(gS: Tensor, X: Tensor, S: Tensor, weff: Tensor, alpha: Tens
     _chk(gS, X, S, weff, alpha, hebb)
     N = weff.shape[0]
     B = X.shape[0] // N
-    e = torch.empty(0, device=X.device)
     gA = torch.empty_like(X)
-    gX = torch.empty_like(X) if need_gx else e
+    gX = torch.empty_like(X) if need_gx else _e(X.device)
     gw = torch.empty_like(weff)
-    galpha = torch.empty_like(weff) if need_galpha else e
-    ghebb = torch.empty_like(weff) if need_ghebb else e
+    galpha = torch.empty_like(weff) if need_galpha else _e(X.device)
+    ghebb = torch.empty_like(weff) if need_ghebb else _e(X.device)
     _lib.call("pu_plastic_head_bwd", X.data_ptr(), S.data_ptr(), gS.data_ptr(), weff.data_ptr(), alpha.data_ptr(), hebb.data_ptr(),
               gA.data_ptr(), gX.data_ptr() if need_gx else None, gw.data_ptr(), galpha.data_ptr() if need_galpha else None,
               ghebb.data_ptr() if need_ghebb else None, B, N, _s())

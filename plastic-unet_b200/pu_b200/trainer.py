@@ -1,0 +1,152 @@
+"""The batched train step of the hot path: forward + BCE + backward + (DP all-reduce) + Adam + plastic-trace
+carry, captured once into a CUDA graph and replayed (no tracing compiler; reference loop: train.py:91-112).
+
+All parameters live in ONE flat arena (and their gradients in another), so the optimizer is a single
+pu_adam_step launch and the data-parallel gradient exchange is a single all-reduce.
+"""
+import torch
+import torch.distributed as dist
+
+from . import _lib
+
+
+class TrainStep:
+    """step(x, target) -> device scalar loss.  x: [B, C, H, W] float32 (device or pinned host), target: [B, nbf, nbf].
+
+    The trace `hebb` is carried (detached) from step to step like train.py:99 and reset by reset_trace()
+    (train.py:88 resets it every epoch)."""
+
+    def __init__(self, net, batch, in_hw, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, use_graph=True, dp_group=None, warmup=3):
+        self.net = net
+        self.dev = next(net.parameters()).device
+        self.batch = batch
+        self.world = dist.get_world_size(dp_group) if (dist.is_initialized() and dp_group is not None) else 1
+        self.dp_group = dp_group if self.world > 1 else None
+        self.betas, self.eps = betas, eps
+        params = [p for p in net.parameters()]
+        total = sum(p.numel() for p in params)
+        # ---- flat arenas (16-byte aligned slots)
+        self.offsets = []
+        off = 0
+        for p in params:
+            self.offsets.append(off)
+            off += (p.numel() + 3) // 4 * 4
+        self.n_flat = off
+        self.flat_p = torch.zeros(off, device=self.dev)
+        self.flat_g = torch.zeros(off, device=self.dev)
+        self.m = torch.zeros(off, device=self.dev)
+        self.v = torch.zeros(off, device=self.dev)
+        for p, o in zip(params, self.offsets):
+            self.flat_p[o:o + p.numel()].copy_(p.data.reshape(-1))
+            p.data = self.flat_p[o:o + p.numel()].view_as(p)
+            p.grad = self.flat_g[o:o + p.numel()].view_as(p)
+        self.n_params = total
+        self.step_count = torch.zeros(1, device=self.dev)
+        self.lr = torch.full((1,), float(lr), device=self.dev)
+        C = net.n_channels
+        self.x = torch.zeros((batch, C, in_hw, in_hw), device=self.dev)
+        self.target = torch.zeros((batch, net.nbf, net.nbf), device=self.dev)
+        self.hebb = net.initialZeroHebb()
+        self.loss = torch.zeros(1, device=self.dev)
+        self.graph = None
+        self.kernels_per_step = None
+        self.use_graph = use_graph
+        self._warm = warmup
+
+    # -------------------------------------------------------------------------------------------
+    def _step_body(self):
+        st = torch.cuda.current_stream().cuda_stream
+        self.flat_g.zero_()
+        out, hebb_new = self.net(self.x, self.hebb)
+        gS = torch.empty_like(out)
+        n = out.numel()
+        _lib.call("pu_bce_fwd_bwd", out.data_ptr(), self.target.data_ptr(), self.loss.data_ptr(), gS.data_ptr(), n, st)
+        out.backward(gS)
+        if self.dp_group is not None:
+            dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.dp_group)
+        _lib.call("pu_adam_step", self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
+                  self.step_count.data_ptr(), self.lr.data_ptr(), self.betas[0], self.betas[1], self.eps,
+                  1.0 / self.world, self.n_flat, st)
+        self.hebb.copy_(hebb_new.detach())
+
+    def capture(self):
+        """Warm up on a side stream, then capture one step into a CUDA graph."""
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(self._warm):
+                self._step_body()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        if not self.use_graph:
+            before = _lib.launch_count()
+            self._step_body()
+            self.kernels_per_step = _lib.launch_count() - before
+            return self
+        self.graph = torch.cuda.CUDAGraph()
+        before = _lib.launch_count()
+        with torch.cuda.graph(self.graph):
+            self._step_body()
+        self.kernels_per_step = _lib.launch_count() - before
+        return self
+
+    def reset_trace(self):
+        self.hebb.zero_()
+
+    def set_lr(self, lr):
+        self.lr.fill_(float(lr))
+
+    def step(self, x=None, target=None):
+        """One optimisation step.  Host (pinned) or device tensors are copied into the static buffers first."""
+        if x is not None:
+            self.x.copy_(x, non_blocking=True)
+        if target is not None:
+            self.target.copy_(target, non_blocking=True)
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._step_body()
+        return self.loss
+
+
+class InferStep:
+    """Batched forward-only step (eval.py:81-90 / infer.py:42-47 semantics: trace zero, hebb' discarded)."""
+
+    def __init__(self, net, batch, in_hw, use_graph=True):
+        self.net = net.eval()
+        self.dev = next(net.parameters()).device
+        self.x = torch.zeros((batch, net.n_channels, in_hw, in_hw), device=self.dev)
+        self.hebb = net.initialZeroHebb()
+        self.out = None
+        self.graph = None
+        self.use_graph = use_graph
+        self.kernels_per_step = None
+
+    def capture(self):
+        with torch.no_grad():
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                for _ in range(3):
+                    self.out, _ = self.net(self.x, self.hebb)
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            before = _lib.launch_count()
+            if self.use_graph:
+                self.graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph):
+                    self.out, _ = self.net(self.x, self.hebb)
+            else:
+                self.out, _ = self.net(self.x, self.hebb)
+            self.kernels_per_step = _lib.launch_count() - before
+        return self
+
+    def step(self, x=None):
+        if x is not None:
+            self.x.copy_(x, non_blocking=True)
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            with torch.no_grad():
+                self.out, _ = self.net(self.x, self.hebb)
+        return self.out

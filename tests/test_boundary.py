@@ -25,7 +25,7 @@ def test_bad_arguments_fail_loudly_without_gpu():
     lib = _lib.load()
     # null pointers / non-positive dims are rejected before any CUDA call
     with pytest.raises(_lib.PuError, match="bad"):
-        _lib.call("pu_pack_w3x3", None, None, 8, 8, 0, None)
+        _lib.call("pu_pack_w3x3", None, None, 8, 8, 0, 0, 8, None)
     with pytest.raises(_lib.PuError):
         _lib.call("pu_maxpool2_fwd", None, None, None, 1, 4, 4, 8, None)
     with pytest.raises(_lib.PuError, match="rule"):

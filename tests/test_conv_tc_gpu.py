@@ -1,0 +1,129 @@
+"""GPU tests of the tcgen05/TMEM/TMA implicit-GEMM conv3x3 (PU_MATH_TF32).
+
+The kernel multiplies TF32 operands exactly and accumulates in fp32, so against a float64 convolution of the
+SAME TF32-rounded inputs and weights the only differences are fp32 accumulation order and the final RN
+rounding of the stored output to TF32 (2^-11 relative): tolerance 6e-4 of max|y| on outputs, and the
+un-rounded comparison (dgrad/wgrad of the autograd path) within 2e-3."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def tf32_round(x):
+    """round-to-nearest (ties away) to a 10-bit mantissa, like cvt.rna.tf32.f32"""
+    i = x.contiguous().view(torch.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def nchw(x):
+    return x.permute(0, 3, 1, 2).contiguous()
+
+
+def test_tc_path_is_available_on_b200():
+    from pu_b200 import _lib
+    assert _lib.tc_available(), "tcgen05/TMA conv path must be usable on the B200 box"
+
+
+SHAPES = [
+    # B, C0, C1, Cout, H, W, relu, res
+    (2, 8, 0, 8, 128, 128, True, False),    # inc.2 / up4.2
+    (2, 8, 8, 8, 128, 128, True, False),    # up4.0: fused concat
+    (3, 16, 0, 16, 64, 64, True, True),     # residual epilogue
+    (2, 32, 32, 16, 32, 32, True, False),   # two chunks (one per source)
+    (4, 64, 0, 64, 16, 16, True, False),    # N = 64, K chunks of 32
+    (2, 128, 0, 32, 8, 8, False, False),    # 4 K chunks, tiny spatial
+    (1, 16, 0, 24, 101, 101, True, True),   # odd sizes (UNetpRes@101), Cout = 24
+    (2, 8, 8, 8, 25, 25, False, False),
+    (1, 64, 64, 128, 12, 12, True, False),  # Cout > 64: two co blocks
+    (1, 8, 0, 8, 6, 300, True, False),      # W > 248: x tiling
+]
+
+
+@pytest.mark.parametrize("B,C0,C1,Cout,H,W,relu,res", SHAPES)
+def test_conv3x3_tc_forward(B, C0, C1, Cout, H, W, relu, res):
+    from pu_b200 import ops
+    g = torch.Generator().manual_seed(C0 * 7 + C1 + Cout + H)
+    Cin = C0 + C1
+    x0 = tf32_round(torch.randn(B, C0, H + 1, W + 2, generator=g))
+    x1 = tf32_round(torch.randn(B, C1, H, W, generator=g)) if C1 else None
+    w = torch.randn(Cout, Cin, 3, 3, generator=g) / (3 * Cin ** 0.5)
+    b = torch.randn(Cout, generator=g)
+    r = torch.randn(B, Cout, H, W, generator=g) if res else None
+    cat = x0[:, :, 1:, 1:W + 1].double()
+    if C1:
+        cat = torch.cat([cat, x1.double()], 1)
+    yr = F.conv2d(cat, tf32_round(w).double(), b.double(), padding=1)
+    if res:
+        yr = yr + r.double()
+    if relu:
+        yr = F.relu(yr)
+    with torch.no_grad():
+        yo = ops.conv3x3(nhwc(x0).to(DEV), nhwc(x1).to(DEV) if C1 else None, w.to(DEV), b.to(DEV), nhwc(r).to(DEV) if res else None,
+                         relu, H, W, 1, 1, 0, 0, ops.MATH_TF32)
+    torch.cuda.synchronize()
+    e = rel_err(nchw(yo), yr)
+    assert e[0] < 6e-4, "max-rel %g l2-rel %g" % e
+    # the stored output is exactly TF32-representable
+    assert torch.equal(tf32_round(yo.cpu()), yo.cpu())
+
+
+@pytest.mark.parametrize("C0,C1,Cout,H,W", [(8, 8, 8, 64, 64), (16, 0, 16, 32, 32), (32, 32, 16, 16, 16), (64, 0, 64, 8, 8)])
+def test_conv3x3_tc_autograd_vs_fp32_path(C0, C1, Cout, H, W):
+    """Forward + dgrad (tcgen05) + wgrad through autograd in TF32 mode vs the strict-fp32 CUDA-core path."""
+    from pu_b200 import ops
+    g = torch.Generator().manual_seed(C0 + Cout + H)
+    B = 2
+    x0 = tf32_round(torch.randn(B, H, W, C0, generator=g))
+    x1 = tf32_round(torch.randn(B, H, W, C1, generator=g)) if C1 else None
+    w = tf32_round(torch.randn(Cout, C0 + C1, 3, 3, generator=g) / (3 * (C0 + C1) ** 0.5))
+    b = torch.randn(Cout, generator=g)
+    R = tf32_round(torch.randn(B, H, W, Cout, generator=g))
+    outs = {}
+    for math in (ops.MATH_FP32, ops.MATH_TF32):
+        x0d = x0.to(DEV).requires_grad_(True)
+        x1d = x1.to(DEV).requires_grad_(True) if C1 else None
+        wd, bd = w.to(DEV).requires_grad_(True), b.to(DEV).requires_grad_(True)
+        y = ops.conv3x3(x0d, x1d, wd, bd, None, True, H, W, 0, 0, 0, 0, math)
+        (y * R.to(DEV)).sum().backward()
+        outs[math] = (y.detach(), x0d.grad, x1d.grad if C1 else None, wd.grad, bd.grad)
+    torch.cuda.synchronize()
+    names = ["y", "dx0", "dx1", "dw", "db"]
+    for n, a, bb in zip(names, outs[ops.MATH_TF32], outs[ops.MATH_FP32]):
+        if a is None:
+            continue
+        e = rel_err(a, bb)
+        assert e[0] < 2e-3, "%s: max-rel %g l2-rel %g" % (n, e[0], e[1])
+
+
+def test_tf32_mode_whole_model_close_to_fp32():
+    """UNetp in TF32 mode (tcgen05 convs) vs strict fp32: logits/trace/gradients within the north-star 1e-3 (L2)."""
+    import contextlib
+    import io
+    from pu_b200 import UNetp
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        net = UNetp(1, 1, torch.device(DEV), rule="oja", nbf=64, batched=True)
+    g = torch.Generator().manual_seed(1)
+    x = torch.rand(4, 1, 64, 64, generator=g).to(DEV)
+    hebb = (0.05 * torch.randn(64, 64, generator=g)).to(DEV)
+    target = (torch.rand(4, 64, 64, generator=g) > 0.6).float().to(DEV)
+    res = {}
+    for mode in ("fp32", "tf32"):
+        net.conv_math = mode
+        net.zero_grad(set_to_none=True)
+        out, hn = net(x, hebb)
+        torch.nn.BCELoss()(out.reshape(-1), target.reshape(-1)).backward()
+        res[mode] = (out.detach().clone(), hn.detach().clone(), {k: p.grad.clone() for k, p in net.named_parameters() if p.grad is not None})
+    assert rel_err(res["tf32"][0], res["fp32"][0])[1] < 1e-3
+    assert rel_err(res["tf32"][1], res["fp32"][1])[1] < 1e-3
+    worst = max(rel_err(res["tf32"][2][k], res["fp32"][2][k])[1] for k in res["fp32"][2])
+    assert worst < 5e-3, "worst parameter-gradient L2 error %g" % worst

@@ -55,10 +55,13 @@ def test_golden_forward_backward(name):
     assert rel_err(x.grad, c.t("grad_x"))[0] < 10 * TOL
     assert rel_err(hebb.grad, c.t("grad_hebb"))[0] < 10 * TOL
     grads = dict(net.named_parameters())
+    # gradients that are analytically zero (a conv bias in front of a BatchNorm) are pure rounding noise on both
+    # sides: allow an absolute floor of 1e-6 of the largest gradient norm of the net
+    floor = 1e-6 * float(np.max(c.z["grad_l2"]))
     for k, l2 in zip([str(k) for k in c.z["grad_keys"]], c.z["grad_l2"]):
         g = grads[k].grad
         assert g is not None, "no gradient for " + k
-        assert abs(float(g.double().norm()) - l2) <= 1e-3 * max(l2, 1e-10), "%s: |g| %g vs %g" % (k, float(g.norm()), l2)
+        assert abs(float(g.double().norm()) - l2) <= 1e-3 * l2 + floor, "%s: |g| %g vs %g" % (k, float(g.norm()), l2)
     for k in c.z.files:
         if k.startswith("grad::"):
             assert rel_err(grads[k[6:]].grad, c.t(k))[0] < 10 * TOL, k
