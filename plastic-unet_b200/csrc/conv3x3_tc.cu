@@ -88,6 +88,11 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -120,26 +125,44 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // ---- the kernel ---------------------------------------------------------------------------------
-template <int COLS>
-__global__ void __launch_bounds__(128) conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
-                                                         const TcArgs a) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* smA = smem;
-  uint8_t* smW = smem + a.a_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + a.a_bytes + a.w_bytes_max);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
-  const uint32_t full_bar = smem_u32(&bars[0]), mma_bar = smem_u32(&bars[1]), done_bar = smem_u32(&bars[2]);
+// Persistent and warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..5 = epilogue (TMEM lane
+// quarter = warp % 4).  kStages shared-memory stages (A chunk planes + that chunk's weights) cycle between
+// producer and MMA warp through full/empty mbarriers; two TMEM accumulator buffers cycle between the MMA warp
+// and the epilogue through tmem_full/tmem_empty, so tile i's epilogue overlaps tile i+1's MMAs and tile i+2's
+// loads.  Tiles are scheduled statically: tile = blockIdx.x + k * gridDim.x.
+constexpr int kStages = 2;
+constexpr int kTcThreads = 192;
 
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const int tx = blockIdx.x % a.tilesX, ty = blockIdx.x / a.tilesX;
-  const int b = blockIdx.y, coblk = blockIdx.z;
-  const int x0 = tx * a.TW, y0 = ty * a.TH;
+template <int COLS>
+__global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm0,
+                                                                   const __grid_constant__ CUtensorMap tm1, const TcArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int stage_bytes = a.a_bytes + a.w_bytes_max;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * stage_bytes);
+  // bars: [0,kStages) full, [kStages,2kStages) empty, then tmem_full[2], tmem_empty[2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_bar = [&](int st) { return bar0 + 8u * st; };
+  auto empty_bar = [&](int st) { return bar0 + 8u * (kStages + st); };
+  auto tfull_bar = [&](int as) { return bar0 + 8u * (2 * kStages + as); };
+  auto tempty_bar = [&](int as) { return bar0 + 8u * (2 * kStages + 2 + as); };
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int coblk = blockIdx.y;
+  const int tiles_per_img = a.tilesX * a.tilesY;
+  const int ntiles = tiles_per_img * a.B;
+  const int acc_cols = a.nmb * a.nmma;  // TMEM columns of one accumulator buffer
 
   if (warp == 0) {
-    if (tid == 0) {
-      mbar_init(full_bar, 1);
-      mbar_init(mma_bar, 1);
-      mbar_init(done_bar, 1);
+    if (lane == 0) {
+      for (int i = 0; i < kStages; ++i) {
+        mbar_init(full_bar(i), 1);
+        mbar_init(empty_bar(i), 1);
+      }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(tfull_bar(i), 1);
+        mbar_init(tempty_bar(i), 4);  // one arrival per epilogue warp
+      }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
@@ -152,93 +175,154 @@ __global__ void __launch_bounds__(128) conv3x3_tc_kernel(const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (tid == 0) {
+  if (warp == 0) {
+    // ================= TMA producer =================
+    const uint8_t* wblk = reinterpret_cast<const uint8_t*>(a.wpk) + (size_t)coblk * a.w_coblk_stride;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int b = tile / tiles_per_img;
+      const int tr = tile - b * tiles_per_img;
+      const int ty = tr / a.tilesX, tx = tr - ty * a.tilesX;
+      const int x0 = tx * a.TW, y0 = ty * a.TH;
+      for (int c = 0; c < a.nchunks; ++c, ++it) {
+        const int st = it % kStages;
+        const uint32_t ph = (it / kStages) & 1;
+        mbar_wait(empty_bar(st), ph ^ 1);  // passes immediately on a fresh barrier
+        if (elect_one()) {
+          const TcChunk ch = a.chunks[c];
+          const int ncg = ch.nA + ch.nB;
+          const uint32_t w_bytes = (uint32_t)(9 * ncg * a.nmma * 16);
+          const uint32_t sA = smem_u32(smem + st * stage_bytes);
+          mbar_expect_tx(full_bar(st), (uint32_t)(ncg * a.plane_bytes) + w_bytes);
+          tma_load_5d(sA, ch.srcA == 0 ? &tm0 : &tm1, full_bar(st), 0, x0 - 1, y0 - 1, ch.cgA, b);
+          if (ch.nB > 0) tma_load_5d(sA + ch.nA * a.plane_bytes, &tm1, full_bar(st), 0, x0 - 1, y0 - 1, ch.cgB, b);
+          bulk_load(sA + a.a_bytes, wblk + ch.w_off, w_bytes, full_bar(st));
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    // The whole warp runs the warp-uniform loop and one elected lane executes each tcgen05 instruction, so the
+    // descriptors live in uniform registers.  M blocks are innermost: consecutive MMAs write different
+    // accumulators and are not serialised on the accumulate dependency of one small TMEM tile.
     // instruction descriptor: D=f32, A=B=tf32, K-major both, N = nmma, M = 128 (cute::UMMA::InstrDescriptor)
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.nmma >> 3) << 17) | ((128u >> 4) << 24);
-    const uint32_t sA = smem_u32(smA), sW = smem_u32(smW);
-    const uint8_t* wblk = reinterpret_cast<const uint8_t*>(a.wpk) + (size_t)coblk * a.w_coblk_stride;
-    uint32_t full_phase = 0, mma_phase = 0;
-    for (int c = 0; c < a.nchunks; ++c) {
-      const TcChunk ch = a.chunks[c];
-      if (c > 0) {  // the previous chunk's MMAs must have finished reading shared memory
-        mbar_wait(mma_bar, mma_phase);
-        mma_phase ^= 1;
-      }
-      const int ncg = ch.nA + ch.nB;
-      const uint32_t w_bytes = (uint32_t)(9 * ncg * a.nmma * 16);
-      mbar_expect_tx(full_bar, (uint32_t)(ncg * a.plane_bytes) + w_bytes);
-      tma_load_5d(sA, ch.srcA == 0 ? &tm0 : &tm1, full_bar, 0, x0 - 1, y0 - 1, ch.cgA, b);
-      if (ch.nB > 0) tma_load_5d(sA + ch.nA * a.plane_bytes, &tm1, full_bar, 0, x0 - 1, y0 - 1, ch.cgB, b);
-      bulk_load(sW, wblk + ch.w_off, w_bytes, full_bar);
-      mbar_wait(full_bar, full_phase);
-      full_phase ^= 1;
+    const uint32_t a_kstep = (uint32_t)(2 * a.plane_bytes) >> 4;  // two channel-group planes per K=8 step (16-byte units)
+    const uint32_t b_kstep = (uint32_t)(2 * a.nmma);
+    const bool leader = elect_one();  // elected once: the issue loop must stay a handful of instructions per MMA
+    const uint32_t nmma = (uint32_t)a.nmma;
+    uint32_t it = 0, tcount = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+      const int as = tcount & 1;
+      const uint32_t aph = (tcount >> 1) & 1;
+      mbar_wait(tempty_bar(as), aph ^ 1);  // the epilogue has drained this accumulator buffer
       tc_fence_after();
-      const int ksteps = ncg >> 1;
-      for (int mb = 0; mb < a.nmb; ++mb) {
-        const uint32_t d = tmem_base + (uint32_t)(mb * a.nmma);
-        for (int tap = 0; tap < 9; ++tap) {
-          const int ky = tap / 3, kx = tap - 3 * ky;
-          const uint32_t a0 = sA + (uint32_t)((mb * 128 + ky * a.PW + kx) * 16);
-          const uint32_t b0 = sW + (uint32_t)(tap * ncg * a.nmma * 16);
-          for (int ks = 0; ks < ksteps; ++ks) {
-            const uint64_t ad = umma_desc(a0 + (uint32_t)(2 * ks * a.plane_bytes), (uint32_t)a.plane_bytes, 128);
-            const uint64_t bd = umma_desc(b0 + (uint32_t)(2 * ks * a.nmma * 16), (uint32_t)(a.nmma * 16), 128);
-            umma_tf32(d, ad, bd, idesc, (c | tap | ks) ? 1u : 0u);
+      const uint32_t d0 = tmem_base + (uint32_t)(as * acc_cols);
+      for (int c = 0; c < a.nchunks; ++c, ++it) {
+        const int st = it % kStages;
+        const uint32_t ph = (it / kStages) & 1;
+        const int ncg = a.chunks[c].nA + a.chunks[c].nB;
+        mbar_wait(full_bar(st), ph);
+        tc_fence_after();
+        const uint32_t sA = smem_u32(smem + st * stage_bytes);
+        const uint64_t a_base = umma_desc(sA, (uint32_t)a.plane_bytes, 128);
+        const uint64_t b_base = umma_desc(sA + a.a_bytes, (uint32_t)(a.nmma * 16), 128);
+        const int ksteps = ncg >> 1;
+        const uint32_t b_tap = (uint32_t)(ncg * a.nmma);
+        uint32_t b_off = 0;
+        for (int ky = 0; ky < 3; ++ky) {
+          for (int kx = 0; kx < 3; ++kx) {
+            const uint32_t a_tap = (uint32_t)(ky * a.PW + kx);
+            for (int ks = 0; ks < ksteps; ++ks) {
+              const uint64_t bd = b_base + (uint64_t)(b_off + ks * b_kstep);
+              uint64_t ad = a_base + (uint64_t)(a_tap + ks * a_kstep);
+              uint32_t d = d0;
+              const uint32_t acc = (c | ky | kx | ks) ? 1u : 0u;
+#pragma unroll 4
+              for (int mb = 0; mb < a.nmb; ++mb) {
+                if (leader) umma_tf32(d, ad, bd, idesc, acc);
+                d += nmma;
+                ad += 128;  // next 128-pixel block: 128 * 16 B, in 16-byte descriptor units
+              }
+            }
+            b_off += b_tap;
           }
         }
+        if (leader) tc_commit(empty_bar(st));  // frees the stage once these MMAs have read it
+        __syncwarp();
       }
-      tc_commit(mma_bar);
+      if (leader) tc_commit(tfull_bar(as));  // accumulator complete
+      __syncwarp();
     }
-    tc_commit(done_bar);
-  }
-  __syncwarp();
-
-  // ---- epilogue: TMEM -> registers -> bias/residual/ReLU -> NHWC global
-  mbar_wait(done_bar, 0);
-  tc_fence_after();
-  const int co_base = coblk * kCoBlk;
-  float bv[COLS];
+  } else {
+    // ================= epilogue: TMEM -> registers -> bias/residual/ReLU -> NHWC global =================
+    const int quarter = warp & 3;           // TMEM lanes [32*quarter, 32*quarter+32)
+    const int row = quarter * 32 + lane;    // row of the 128-pixel block owned by this thread
+    const int co_base = coblk * kCoBlk;
+    float bv[COLS];
 #pragma unroll
-  for (int j = 0; j < COLS; ++j) bv[j] = (a.bias != nullptr && co_base + j < a.Cout) ? __ldg(a.bias + co_base + j) : 0.f;
-  for (int mb = 0; mb < a.nmb; ++mb) {
-    uint32_t v[COLS];
-    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mb * a.nmma);
-    if (COLS == 8) {
-      tmem_ld8(taddr, v);
-    } else {
+    for (int j = 0; j < COLS; ++j) bv[j] = (a.bias != nullptr && co_base + j < a.Cout) ? __ldg(a.bias + co_base + j) : 0.f;
+    const int step_y = 128 / a.PW, step_x = 128 - step_y * a.PW;
+    uint32_t tcount = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+      const int b = tile / tiles_per_img;
+      const int tr = tile - b * tiles_per_img;
+      const int ty = tr / a.tilesX, tx = tr - ty * a.tilesX;
+      const int x0 = tx * a.TW, y0 = ty * a.TH;
+      const int as = tcount & 1;
+      const uint32_t aph = (tcount >> 1) & 1;
+      mbar_wait(tfull_bar(as), aph);
+      tc_fence_after();
+      int yy = row / a.PW, xx = row - yy * a.PW;
+      for (int mb = 0; mb < a.nmb; ++mb) {
+        uint32_t v[COLS];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * acc_cols + mb * a.nmma);
+        if (COLS == 8) {
+          tmem_ld8(taddr, v);
+        } else {
 #pragma unroll
-      for (int q = 0; q < COLS / 16; ++q) tmem_ld16(taddr + 16 * q, v + 16 * q);
-    }
-    tmem_ld_wait();
-    const int r = mb * 128 + tid;
-    const int yy = r / a.PW, xx = r - yy * a.PW;
-    const int gy = y0 + yy, gx = x0 + xx;
-    if (yy >= a.TH || xx >= a.TW || gy >= a.H || gx >= a.W) continue;
-    const float* rp = a.res != nullptr ? a.res + (((size_t)b * a.H + gy) * a.W + gx) * a.Cout + co_base : nullptr;
+          for (int q = 0; q < COLS / 16; ++q) tmem_ld16(taddr + 16 * q, v + 16 * q);
+        }
+        tmem_ld_wait();
+        const int gy = y0 + yy, gx = x0 + xx;
+        if (yy < a.TH && xx < a.TW && gy < a.H && gx < a.W) {
+          const float* rp = a.res != nullptr ? a.res + (((size_t)b * a.H + gy) * a.W + gx) * a.Cout + co_base : nullptr;
 #pragma unroll
-    for (int q = 0; q < COLS / 4; ++q) {
-      const int co = co_base + 4 * q;
-      if (co >= a.Cout) break;
-      float o[4];
+          for (int q = 0; q < COLS / 4; ++q) {
+            const int co = co_base + 4 * q;
+            if (co < a.Cout) {
+              float o[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) o[j] = __uint_as_float(v[4 * q + j]) + bv[4 * q + j];
-      if (rp != nullptr) {
-        const float4 rr = ldg4(rp + 4 * q);
-        o[0] += rr.x; o[1] += rr.y; o[2] += rr.z; o[3] += rr.w;
+              for (int j = 0; j < 4; ++j) o[j] = __uint_as_float(v[4 * q + j]) + bv[4 * q + j];
+              if (rp != nullptr) {
+                const float4 rr = ldg4(rp + 4 * q);
+                o[0] += rr.x; o[1] += rr.y; o[2] += rr.z; o[3] += rr.w;
+              }
+              if (a.relu) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) o[j] = fmaxf(o[j], 0.f);
+              }
+              if (a.round_out) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) o[j] = round_tf32(o[j]);
+              }
+              const bool first = co < a.d0.C;
+              const ViewW dd = first ? a.d0 : a.d1;
+              const int cd = first ? co : co - a.d0.C;
+              float* dp = dd.p + (((size_t)b * dd.Hs + (gy + dd.oy)) * dd.Ws + (gx + dd.ox)) * dd.C + cd;
+              *reinterpret_cast<float4*>(dp) = make_float4(o[0], o[1], o[2], o[3]);
+            }
+          }
+        }
+        // next 128-pixel block: advance (yy, xx) without a division
+        yy += step_y;
+        xx += step_x;
+        if (xx >= a.PW) { xx -= a.PW; ++yy; }
       }
-      if (a.relu) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) o[j] = fmaxf(o[j], 0.f);
-      }
-      if (a.round_out) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) o[j] = round_tf32(o[j]);
-      }
-      const bool first = co < a.d0.C;
-      const ViewW dd = first ? a.d0 : a.d1;
-      const int cd = first ? co : co - a.d0.C;
-      float* dp = dd.p + (((size_t)b * dd.Hs + (gy + dd.oy)) * dd.Ws + (gx + dd.ox)) * dd.C + cd;
-      *reinterpret_cast<float4*>(dp) = make_float4(o[0], o[1], o[2], o[3]);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty_bar(as)) : "memory");
     }
   }
 
@@ -364,9 +448,9 @@ static bool tc_plan(int B, int H, int W, int C0, int C1, int Cout, TcPlan* p) {
   p->TW = (W + p->tilesX - 1) / p->tilesX;
   p->PW = (p->TW + 2 + 7) / 8 * 8;
   if (p->PW > 256) return false;
-  const size_t smem_soft = 108 * 1024, smem_hard = 220 * 1024;
+  // one CTA per SM: kStages stages of (A planes + weights) and two TMEM accumulator buffers of <= 256 columns
+  const size_t smem_soft = (216 * 1024) / kStages, smem_hard = (216 * 1024) / kStages;
   int best = 0;
-  size_t best_smem = 0;
   for (int pass = 0; pass < 2 && best == 0; ++pass) {
     const size_t lim = pass == 0 ? smem_soft : smem_hard;
     for (int th = (H < 48 ? H : 48); th >= 1; --th) {
@@ -376,13 +460,12 @@ static bool tc_plan(int B, int H, int W, int C0, int C1, int Cout, TcPlan* p) {
       int tail = nmb * 128 + 2 * p->PW + 2 - plane_pix;
       if (tail < 0) tail = 0;
       const size_t a_bytes = ((size_t)max_ncg * plane_pix * 16 + (size_t)tail * 16 + 127) / 128 * 128;
-      const size_t total = a_bytes + p->w_bytes_max + 64;
+      const size_t total = a_bytes + p->w_bytes_max;
       if (total > lim) continue;
-      // prefer the largest tile that still gives every SM at least two tiles
+      // prefer the largest tile that still gives every SM at least two tiles; never shrink below two M blocks
       const long long tiles = (long long)B * ((H + th - 1) / th) * p->tilesX;
-      if (best == 0) { best = th; best_smem = total; }
-      if (tiles >= 2LL * kNumSMs) { best = th; best_smem = total; break; }
-      best = th; best_smem = total;  // keep shrinking until there are enough tiles (or th == 1)
+      best = th;
+      if (tiles >= 2LL * kNumSMs || th * p->PW <= 256) break;
     }
   }
   if (best == 0) return false;
@@ -393,10 +476,8 @@ static bool tc_plan(int B, int H, int W, int C0, int C1, int Cout, TcPlan* p) {
   int tail = p->nmb * 128 + 2 * p->PW + 2 - (best + 2) * p->PW;
   if (tail < 0) tail = 0;
   p->a_bytes = (int)(((size_t)max_ncg * p->plane_bytes + (size_t)tail * 16 + 127) / 128 * 128);
-  p->tmem_cols = next_pow2_cols(p->nmb * p->nmma);
-  p->smem_bytes = best_smem;
-  (void)best_smem;
-  p->smem_bytes = (size_t)p->a_bytes + p->w_bytes_max + 64;
+  p->tmem_cols = next_pow2_cols(2 * p->nmb * p->nmma);
+  p->smem_bytes = (size_t)kStages * ((size_t)p->a_bytes + p->w_bytes_max) + 128;
   return true;
 }
 
@@ -463,7 +544,7 @@ static int launch_tc(const CUtensorMap& tm0, const CUtensorMap& tm1, const TcArg
     }
     attr_set = true;
   }
-  conv3x3_tc_kernel<COLS><<<grid, 128, smem, st>>>(tm0, tm1, ta);
+  conv3x3_tc_kernel<COLS><<<grid, kTcThreads, smem, st>>>(tm0, tm1, ta);
   return post_launch("conv3x3_tc");
 }
 
@@ -495,7 +576,8 @@ int conv3x3_fwd_tc(const Conv3x3Args& a, cudaStream_t st) {
   ta.nmb = p.nmb; ta.nmma = p.nmma; ta.plane_bytes = p.plane_bytes; ta.a_bytes = p.a_bytes; ta.w_bytes_max = p.w_bytes_max;
   ta.tmem_cols = p.tmem_cols; ta.nchunks = p.nchunks; ta.w_coblk_stride = p.w_coblk_stride;
   for (int i = 0; i < p.nchunks; ++i) ta.chunks[i] = p.chunks[i];
-  dim3 grid(p.tilesX * p.tilesY, a.B, p.ncoblk);
+  const int ntiles = p.tilesX * p.tilesY * a.B;
+  dim3 grid(ntiles < kNumSMs ? ntiles : kNumSMs, p.ncoblk);
   switch (p.cols) {
     case 8: return launch_tc<8>(tm0, tm1, ta, grid, p.smem_bytes, st);
     case 16: return launch_tc<16>(tm0, tm1, ta, grid, p.smem_bytes, st);
