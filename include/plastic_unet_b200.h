@@ -40,6 +40,11 @@ typedef enum {
 #define PU_FLAG_RELU 1       /* fused ReLU in the epilogue                                            */
 #define PU_FLAG_ROUND_TF32 2 /* round the op's output to TF32 (RN): producers of tensor-core operands  */
 
+/* conv3x3 weight operand formats */
+#define PU_W_PACKED 0
+#define PU_W_OIHW 1
+#define PU_W_OIHW_DGRAD 2
+
 /* conv3x3 math modes */
 #define PU_MATH_FP32 0 /* CUDA-core FFMA, strict fp32 (parity mode, any shape)        */
 #define PU_MATH_TF32 1 /* tcgen05 kind::tf32 implicit GEMM, fp32 accumulate in TMEM   */
@@ -72,8 +77,14 @@ int pu_pack_w3x3(const float* w_oihw, float* w_packed, int Cout, int Cin, int tr
 long long pu_pack_w3x3_floats(int Cout, int Cin, int transpose, int math, int C0);
 /* 1 if a conv with these source / destination channel counts can run on the tcgen05 path (PU_MATH_TF32) */
 int pu_conv3x3_tc_ok(int C0, int C1, int Cout, int Cd0, int Cd1);
+/* 1 if, additionally, the tcgen05 kernel can build its weight tiles from the raw OIHW tensor (they fit in shared memory) */
+int pu_conv3x3_tc_resident(int C0, int C1, int Cout);
 
 /* y = act( conv3x3(cat[src0,src1]) + bias + res ), written channel-split into dst0|dst1 (flags: PU_FLAG_*).
+ * wfmt selects what `wp` points at: PU_W_PACKED (output of pu_pack_w3x3 for this math mode), PU_W_OIHW (the raw
+ * [Cout, C0+C1, 3, 3] weight: operand tiles are built inside the kernel, no pack launch) or PU_W_OIHW_DGRAD (the
+ * raw [C0, Cout, 3, 3] weight of the forward conv whose dgrad this call computes).  With PU_MATH_TF32 the raw
+ * formats need pu_conv3x3_tc_resident(C0, C1, Cout).
  * src1, bias, res, dst1 may be NULL.  wp is the packed weight [9][C0+C1][Cout].
  * dst views may be larger than HxW (their border is NOT written — caller zero-fills).    */
 int pu_conv3x3_fwd(const float* src0, int H0, int W0, int C0, int oy0, int ox0,
@@ -81,7 +92,7 @@ int pu_conv3x3_fwd(const float* src0, int H0, int W0, int C0, int oy0, int ox0,
                    const float* wp, const float* bias, const float* res, int flags,
                    float* dst0, int Hd0, int Wd0, int Cd0, int oyd0, int oxd0,
                    float* dst1, int Hd1, int Wd1, int Cd1, int oyd1, int oxd1,
-                   int B, int H, int W, int Cout, int math, void* stream);
+                   int B, int H, int W, int Cout, int math, int wfmt, void* stream);
 
 /* dw_oihw[Cout, C0+C1, 3, 3] = sum_{b,y,x} g[b,y,x,co] * cat[src0,src1][b,y+ky-1,x+kx-1,ci]
  * (overwrites dw).  g is [B,H,W,Cout] dense.                                               */

@@ -21,8 +21,9 @@ int pu_conv3x3_fwd(const float* src0, int H0, int W0, int C0, int oy0, int ox0,
                    const float* wp, const float* bias, const float* res, int flags,
                    float* dst0, int Hd0, int Wd0, int Cd0, int oyd0, int oxd0,
                    float* dst1, int Hd1, int Wd1, int Cd1, int oyd1, int oxd1,
-                   int B, int H, int W, int Cout, int math, void* stream) {
+                   int B, int H, int W, int Cout, int math, int wfmt, void* stream) {
   PU_REQUIRE(B > 0 && H > 0 && W > 0 && Cout > 0 && wp != nullptr, PU_ERR_BAD_ARG, "pu_conv3x3_fwd: bad dims");
+  PU_REQUIRE(wfmt >= 0 && wfmt <= 2, PU_ERR_BAD_ARG, "pu_conv3x3_fwd: unknown weight format %d", wfmt);
   int rc = check_view("pu_conv3x3_fwd src0", src0, H0, W0, C0, oy0, ox0, H, W);
   if (rc) return rc;
   if (src1 != nullptr) {
@@ -53,6 +54,7 @@ int pu_conv3x3_fwd(const float* src0, int H0, int W0, int C0, int oy0, int ox0,
   a.B = B; a.H = H; a.W = W; a.Cin = C0 + C1; a.Cout = Cout;
   a.relu = (flags & PU_FLAG_RELU) ? 1 : 0;
   a.round_out = (flags & PU_FLAG_ROUND_TF32) ? 1 : 0;
+  a.wfmt = wfmt;
   a.tilesX = a.tilesY = 0;
   // no silent fallback: PU_MATH_TF32 means the tcgen05 kernel (wp must be in its layout) or an error
   if (math == PU_MATH_TF32) return pu::conv3x3_fwd_tc(a, pu::as_stream(stream));
@@ -84,5 +86,7 @@ int pu_conv3x3_wgrad(const float* src0, int H0, int W0, int C0, int oy0, int ox0
 }
 
 int pu_conv3x3_tc_ok(int C0, int C1, int Cout, int Cd0, int Cd1) { return pu::conv3x3_tc_ok(C0, C1, Cout, Cd0, Cd1) ? 1 : 0; }
+
+int pu_conv3x3_tc_resident(int C0, int C1, int Cout) { return pu::conv3x3_tc_resident(C0, C1, Cout) ? 1 : 0; }
 
 }  // extern "C"

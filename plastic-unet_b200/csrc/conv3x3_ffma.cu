@@ -79,7 +79,12 @@ __global__ void __launch_bounds__(NT) conv3x3_ffma_kernel(const Conv3x3Args a) {
       for (int i = tid; i < 9 * 8 * 8; i += NT) {
         const int j = i & 7, ci = (i >> 3) & 7, tap = i >> 6;
         float wv = 0.f;
-        if (ci < cc && co0 + j < a.Cout) wv = __ldg(a.wp + ((size_t)tap * a.Cin + cbase + c0 + ci) * a.Cout + co0 + j);
+        if (ci < cc && co0 + j < a.Cout) {
+          const int cig = cbase + c0 + ci, cog = co0 + j;
+          if (a.wfmt == 0) wv = __ldg(a.wp + ((size_t)tap * a.Cin + cig) * a.Cout + cog);           // packed [9][Cin][Cout]
+          else if (a.wfmt == 1) wv = __ldg(a.wp + ((size_t)cog * a.Cin + cig) * 9 + tap);           // raw OIHW, forward
+          else wv = __ldg(a.wp + ((size_t)cig * a.Cout + cog) * 9 + (8 - tap));                     // raw OIHW, dgrad
+        }
         w_s[i] = wv;
       }
       __syncthreads();

@@ -25,13 +25,15 @@
 // unet_p_res.py:150-158,186-189,215-219 for channel counts that are multiples of 8; dgrad is the same kernel
 // on transposed/flipped packed weights.
 #include <cuda.h>
+#include <stdlib.h>
 #include <mutex>
 #include "conv3x3.cuh"
 
 namespace pu {
 
 constexpr int kMaxChunks = 48;
-constexpr int kCoBlk = 64;  // output channels per CTA (grid.z splits larger Cout)
+constexpr int kCoBlk = 64;  // output channels per CTA (grid.y splits larger Cout)
+constexpr unsigned kMaxResidentW = 40 * 1024;  // largest weight image kept resident in shared memory
 
 struct TcChunk {
   int cgA, nA;  // planes [0, nA): channel groups cgA.. of source srcA
@@ -48,6 +50,13 @@ struct TcArgs {
   int B, H, W, Cout, relu, round_out;
   int TH, TW, PW, tilesX, tilesY;
   int nmb, nmma, plane_bytes, a_bytes, w_bytes_max, tmem_cols, nchunks;
+  int wfmt;       // 0: wpk holds the packed B tiles (streamed per stage); 1/2: wpk is the raw OIHW weight (forward / dgrad)
+                  // and the B tiles are built in shared memory once per CTA (resident)
+  int Cin, C0;    // concatenated input channels and the split point (for the in-kernel weight build)
+  int w_res_bytes;  // bytes of the resident weight image (0 in streamed mode)
+  View s0, s1;      // the two sources (cp.async loader path)
+  int loader;       // 1: one 5-D TMA box per source (default); 0: 4 loader warps with 16-byte cp.async
+  int debug;  // PU_TC_DEBUG experiments: 1 = skip MMAs, 2 = skip epilogue stores, 4 = load only the first stage
   unsigned w_coblk_stride;  // bytes
   TcChunk chunks[kMaxChunks];
 };
@@ -123,6 +132,16 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
         "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr));
 }
+__device__ __forceinline__ void ldg8(const float* p, float* r) {
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void stg8(float* p, const float* r) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(r[0]), "f"(r[1]), "f"(r[2]), "f"(r[3]), "f"(r[4]),
+               "f"(r[5]), "f"(r[6]), "f"(r[7])
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // ---- the kernel ---------------------------------------------------------------------------------
 // Persistent and warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..5 = epilogue (TMEM lane
@@ -131,14 +150,20 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // and the epilogue through tmem_full/tmem_empty, so tile i's epilogue overlaps tile i+1's MMAs and tile i+2's
 // loads.  Tiles are scheduled statically: tile = blockIdx.x + k * gridDim.x.
 constexpr int kStages = 2;
-constexpr int kTcThreads = 192;
+constexpr int kLoadWarps = 4;                       // loader warps (cp.async path); warp 0 alone drives the TMA path
+constexpr int kMmaWarps = 4;                        // MMA-issuing warps: warp m owns the 128-pixel blocks mb = m (mod 4)
+constexpr int kEpiWarps = 8;                        // two warps per TMEM lane quarter, alternating 128-pixel blocks
+constexpr int kMmaWarp0 = kLoadWarps;
+constexpr int kEpiWarp0 = kLoadWarps + kMmaWarps;   // first epilogue warp (multiple of 4: quarter = warp & 3)
+constexpr int kTcThreads = 32 * (kLoadWarps + kMmaWarps + kEpiWarps);
 
 template <int COLS>
 __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm0,
                                                                    const __grid_constant__ CUtensorMap tm1, const TcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const int stage_bytes = a.a_bytes + a.w_bytes_max;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * stage_bytes);
+  const int stage_bytes = a.a_bytes + a.w_bytes_max;  // w_bytes_max == 0 when the weights are resident
+  uint8_t* smWres = smem + kStages * stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smWres + a.w_res_bytes);
   // bars: [0,kStages) full, [kStages,2kStages) empty, then tmem_full[2], tmem_empty[2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
   const uint32_t bar0 = smem_u32(bars);
@@ -156,12 +181,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const __grid_
   if (warp == 0) {
     if (lane == 0) {
       for (int i = 0; i < kStages; ++i) {
-        mbar_init(full_bar(i), 1);
-        mbar_init(empty_bar(i), 1);
+        mbar_init(full_bar(i), a.loader == 0 ? 32 * kLoadWarps : 1);
+        mbar_init(empty_bar(i), kMmaWarps);  // one tcgen05.commit per MMA warp
       }
       for (int i = 0; i < 2; ++i) {
-        mbar_init(tfull_bar(i), 1);
-        mbar_init(tempty_bar(i), 4);  // one arrival per epilogue warp
+        mbar_init(tfull_bar(i), kMmaWarps);
+        mbar_init(tempty_bar(i), kEpiWarps);  // one arrival per epilogue warp
       }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -170,13 +195,113 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const __grid_
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  if (a.wfmt != 0) {
+    // Build the tf32 B-operand tiles of every K chunk straight from the OIHW weight tensor (no pack kernel):
+    // image layout [chunk][tap][channel-group plane][N rows][4], identical to pu_pack_w3x3's.
+    const float* __restrict__ w = a.wpk;
+    const int co_base_w = coblk * kCoBlk;
+    for (int c = 0; c < a.nchunks; ++c) {
+      const TcChunk ch = a.chunks[c];
+      const int ncg = ch.nA + ch.nB;
+      const int n_el = 9 * ncg * a.nmma * 4;
+      float* out = reinterpret_cast<float*>(smWres + ch.w_off);
+      for (int i = tid; i < n_el; i += kTcThreads) {
+        const int j = i & 3;
+        const int n = (i >> 2) % a.nmma;
+        const int pl = (i / (4 * a.nmma)) % ncg;
+        const int tap = i / (4 * a.nmma * ncg);
+        int ci;
+        if (pl < ch.nA) ci = (ch.srcA == 0 ? 0 : a.C0) + (ch.cgA + pl) * 4 + j;
+        else ci = a.C0 + (ch.cgB + pl - ch.nA) * 4 + j;
+        const int co = co_base_w + n;
+        float v = 0.f;
+        if (co < a.Cout && n < kCoBlk && ci < a.Cin) {
+          v = a.wfmt == 1 ? __ldg(w + ((size_t)co * a.Cin + ci) * 9 + tap) : __ldg(w + ((size_t)ci * a.Cout + co) * 9 + (8 - tap));
+        }
+        out[i] = round_tf32(v);
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tensor-core (async proxy) reads
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
-    // ================= TMA producer =================
+  if (warp < kLoadWarps && a.loader == 0) {
+    // ================= cp.async loaders (4 warps) =================
+    // 16-byte LDGSTS per thread: consecutive threads read consecutive 16 bytes of an NHWC halo row (fully coalesced,
+    // every 32-byte sector used once) and scatter them into the channel-group planes; out-of-image pixels are
+    // zero-filled by src-size 0.  Measured on B200 this path is SLOWER than the 5-D TMA box (43.6 vs 25.4 us for
+    // 8->8 @128x128 B=64: the per-copy index arithmetic of 128 threads costs more than TMA's 16-byte rows), so it
+    // is only kept as an alternative loader (PU_TC_LOADER=cpasync).
+    const int ltid = tid;  // 0..127
+    const uint8_t* wblk = reinterpret_cast<const uint8_t*>(a.wpk) + (size_t)coblk * a.w_coblk_stride;
+    const int halo_rows = a.TH + 2;
+    uint32_t it = 0;
+    int prev_st = -1;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int b = tile / tiles_per_img;
+      const int tr = tile - b * tiles_per_img;
+      const int ty = tr / a.tilesX, tx = tr - ty * a.tilesX;
+      const int x0 = tx * a.TW, y0 = ty * a.TH;
+      for (int c = 0; c < a.nchunks; ++c, ++it) {
+        const int st = it % kStages;
+        const uint32_t ph = (it / kStages) & 1;
+        mbar_wait(empty_bar(st), ph ^ 1);
+        const TcChunk ch = a.chunks[c];
+        const uint32_t sA = smem_u32(smem + st * stage_bytes);
+        if (!((a.debug & 4) && it >= (uint32_t)kStages)) {
+#pragma unroll 1
+          for (int part = 0; part < 2; ++part) {
+            const int nX = part == 0 ? ch.nA : ch.nB;
+            if (nX == 0) continue;
+            const View v = (part == 0 && ch.srcA == 0) ? a.s0 : a.s1;
+            const int cgX = part == 0 ? ch.cgA : ch.cgB;
+            const uint32_t dplane = sA + (uint32_t)((part == 0 ? 0 : ch.nA) * a.plane_bytes);
+            const int units = a.PW * nX;  // 16-byte units per halo row
+            const bool pow2 = (nX & (nX - 1)) == 0;
+            const int sh = 31 - __clz(nX);
+            for (int hy = 0; hy < halo_rows; ++hy) {
+              const int gy = y0 - 1 + hy;
+              const bool rowok = gy >= 0 && gy < a.H;
+              const float* rowp = v.p + (((size_t)b * v.Hs + (rowok ? gy + v.oy : 0)) * v.Ws + v.ox) * v.C + cgX * 4;
+              const uint32_t drow = dplane + (uint32_t)(hy * a.PW * 16);
+              for (int u = ltid; u < units; u += 32 * kLoadWarps) {
+                const int hx = pow2 ? (u >> sh) : (u / nX);
+                const int cgl = u - hx * nX;
+                const int gx = x0 - 1 + hx;
+                const bool ok = rowok && gx >= 0 && gx < a.W;
+                const float* src = ok ? rowp + (size_t)gx * v.C + cgl * 4 : v.p;
+                const uint32_t dst = drow + (uint32_t)(cgl * a.plane_bytes + hx * 16);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16 : 0) : "memory");
+              }
+            }
+          }
+          if (a.wfmt == 0) {  // streamed weights: plain 16-byte cp.async as well
+            const int ncg = ch.nA + ch.nB;
+            const int wunits = 9 * ncg * a.nmma;
+            const uint8_t* wsrc = wblk + ch.w_off;
+            for (int u = ltid; u < wunits; u += 32 * kLoadWarps)
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16, 16;" ::"r"(sA + a.a_bytes + u * 16), "l"(wsrc + (size_t)u * 16) : "memory");
+          }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (prev_st >= 0) {  // the previous stage's copies have landed: publish it to the MMA warps
+          asm volatile("cp.async.wait_group 1;" ::: "memory");
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full_bar(prev_st)) : "memory");
+        }
+        prev_st = st;
+      }
+    }
+    if (prev_st >= 0) {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full_bar(prev_st)) : "memory");
+    }
+  } else if (warp == 0) {
+    // ================= TMA producer (loader == 1) =================
     const uint8_t* wblk = reinterpret_cast<const uint8_t*>(a.wpk) + (size_t)coblk * a.w_coblk_stride;
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -193,16 +318,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const __grid_
           const int ncg = ch.nA + ch.nB;
           const uint32_t w_bytes = (uint32_t)(9 * ncg * a.nmma * 16);
           const uint32_t sA = smem_u32(smem + st * stage_bytes);
-          mbar_expect_tx(full_bar(st), (uint32_t)(ncg * a.plane_bytes) + w_bytes);
+          if ((a.debug & 4) && it >= (uint32_t)kStages) {
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full_bar(st)) : "memory");
+          } else {
+          mbar_expect_tx(full_bar(st), (uint32_t)(ncg * a.plane_bytes) + (a.wfmt == 0 ? w_bytes : 0u));
           tma_load_5d(sA, ch.srcA == 0 ? &tm0 : &tm1, full_bar(st), 0, x0 - 1, y0 - 1, ch.cgA, b);
           if (ch.nB > 0) tma_load_5d(sA + ch.nA * a.plane_bytes, &tm1, full_bar(st), 0, x0 - 1, y0 - 1, ch.cgB, b);
-          bulk_load(sA + a.a_bytes, wblk + ch.w_off, w_bytes, full_bar(st));
+          if (a.wfmt == 0) bulk_load(sA + a.a_bytes, wblk + ch.w_off, w_bytes, full_bar(st));
+          }
         }
         __syncwarp();
       }
     }
-  } else if (warp == 1) {
-    // ================= MMA issuer =================
+  } else if (warp >= kMmaWarp0 && warp < kEpiWarp0) {
+    // ================= MMA issuers =================
+    // A tcgen05.mma of this conv is tiny (N = 16..64 columns, 8-32 tensor-pipe cycles) and a single warp needs
+    // ~30 cycles of scalar work per issue, so the 128-pixel blocks are dealt round-robin to kMmaWarps issuing warps.
+    const int mw = warp - kMmaWarp0;
     // The whole warp runs the warp-uniform loop and one elected lane executes each tcgen05 instruction, so the
     // descriptors live in uniform registers.  M blocks are innermost: consecutive MMAs write different
     // accumulators and are not serialised on the accumulate dependency of one small TMEM tile.
@@ -227,7 +359,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const __grid_
         tc_fence_after();
         const uint32_t sA = smem_u32(smem + st * stage_bytes);
         const uint64_t a_base = umma_desc(sA, (uint32_t)a.plane_bytes, 128);
-        const uint64_t b_base = umma_desc(sA + a.a_bytes, (uint32_t)(a.nmma * 16), 128);
+        const uint64_t b_base = umma_desc(a.wfmt == 0 ? sA + a.a_bytes : smem_u32(smWres) + a.chunks[c].w_off, (uint32_t)(a.nmma * 16), 128);
         const int ksteps = ncg >> 1;
         const uint32_t b_tap = (uint32_t)(ncg * a.nmma);
         uint32_t b_off = 0;
@@ -236,14 +368,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const __grid_
             const uint32_t a_tap = (uint32_t)(ky * a.PW + kx);
             for (int ks = 0; ks < ksteps; ++ks) {
               const uint64_t bd = b_base + (uint64_t)(b_off + ks * b_kstep);
-              uint64_t ad = a_base + (uint64_t)(a_tap + ks * a_kstep);
-              uint32_t d = d0;
+              uint64_t ad = a_base + (uint64_t)(a_tap + ks * a_kstep + mw * 128);
+              uint32_t d = d0 + mw * nmma;
               const uint32_t acc = (c | ky | kx | ks) ? 1u : 0u;
 #pragma unroll 4
-              for (int mb = 0; mb < a.nmb; ++mb) {
-                if (leader) umma_tf32(d, ad, bd, idesc, acc);
-                d += nmma;
-                ad += 128;  // next 128-pixel block: 128 * 16 B, in 16-byte descriptor units
+              for (int mb = mw; mb < a.nmb; mb += kMmaWarps) {
+                if (leader && !(a.debug & 1)) umma_tf32(d, ad, bd, idesc, acc);
+                d += kMmaWarps * nmma;
+                ad += kMmaWarps * 128;  // this warp's next 128-pixel block: 128 * 16 B each, in 16-byte descriptor units
               }
             }
             b_off += b_tap;
@@ -255,15 +387,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const __grid_
       if (leader) tc_commit(tfull_bar(as));  // accumulator complete
       __syncwarp();
     }
-  } else {
+  } else if (warp >= kEpiWarp0) {
     // ================= epilogue: TMEM -> registers -> bias/residual/ReLU -> NHWC global =================
-    const int quarter = warp & 3;           // TMEM lanes [32*quarter, 32*quarter+32)
-    const int row = quarter * 32 + lane;    // row of the 128-pixel block owned by this thread
+    // 8 warps: warp e handles TMEM lane quarter (warp % 4) of the 128-pixel blocks mb = set, set+2, ... (set = e / 4);
+    // G blocks are fetched per tcgen05.wait::ld so that the TMEM read latency is paid once per group.
+    constexpr int G = COLS <= 16 ? 4 : (COLS == 32 ? 2 : 1);
+    const int quarter = warp & 3;
+    const int set = (warp - kEpiWarp0) >> 2;
+    const int row = quarter * 32 + lane;
     const int co_base = coblk * kCoBlk;
     float bv[COLS];
 #pragma unroll
     for (int j = 0; j < COLS; ++j) bv[j] = (a.bias != nullptr && co_base + j < a.Cout) ? __ldg(a.bias + co_base + j) : 0.f;
-    const int step_y = 128 / a.PW, step_x = 128 - step_y * a.PW;
+    const int step_y = 256 / a.PW, step_x = 256 - step_y * a.PW;  // this warp advances two 128-pixel blocks at a time
+    // 256-bit stores need 32-byte aligned channel groups in both destinations
+    const bool vec8 = (a.d0.C % 8 == 0) && (a.d1.p == nullptr || a.d1.C % 8 == 0);
+    const int row0 = set * 128 + row;
+    const int yy0 = row0 / a.PW, xx0 = row0 - yy0 * a.PW;
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
       const int b = tile / tiles_per_img;
@@ -274,51 +414,78 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const __grid_
       const uint32_t aph = (tcount >> 1) & 1;
       mbar_wait(tfull_bar(as), aph);
       tc_fence_after();
-      int yy = row / a.PW, xx = row - yy * a.PW;
-      for (int mb = 0; mb < a.nmb; ++mb) {
-        uint32_t v[COLS];
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * acc_cols + mb * a.nmma);
-        if (COLS == 8) {
-          tmem_ld8(taddr, v);
-        } else {
+      int yy = yy0, xx = xx0;
+      const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * acc_cols);
+      for (int mb0 = set; mb0 < a.nmb; mb0 += 2 * G) {
+        uint32_t v[G][COLS];
 #pragma unroll
-          for (int q = 0; q < COLS / 16; ++q) tmem_ld16(taddr + 16 * q, v + 16 * q);
-        }
-        tmem_ld_wait();
-        const int gy = y0 + yy, gx = x0 + xx;
-        if (yy < a.TH && xx < a.TW && gy < a.H && gx < a.W) {
-          const float* rp = a.res != nullptr ? a.res + (((size_t)b * a.H + gy) * a.W + gx) * a.Cout + co_base : nullptr;
+        for (int g = 0; g < G; ++g) {
+          const int mb = mb0 + 2 * g;
+          if (mb < a.nmb) {  // warp-uniform
+            const uint32_t taddr = tbase + (uint32_t)(mb * a.nmma);
+            if (COLS == 8) {
+              tmem_ld8(taddr, v[g]);
+            } else {
 #pragma unroll
-          for (int q = 0; q < COLS / 4; ++q) {
-            const int co = co_base + 4 * q;
-            if (co < a.Cout) {
-              float o[4];
-#pragma unroll
-              for (int j = 0; j < 4; ++j) o[j] = __uint_as_float(v[4 * q + j]) + bv[4 * q + j];
-              if (rp != nullptr) {
-                const float4 rr = ldg4(rp + 4 * q);
-                o[0] += rr.x; o[1] += rr.y; o[2] += rr.z; o[3] += rr.w;
-              }
-              if (a.relu) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) o[j] = fmaxf(o[j], 0.f);
-              }
-              if (a.round_out) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) o[j] = round_tf32(o[j]);
-              }
-              const bool first = co < a.d0.C;
-              const ViewW dd = first ? a.d0 : a.d1;
-              const int cd = first ? co : co - a.d0.C;
-              float* dp = dd.p + (((size_t)b * dd.Hs + (gy + dd.oy)) * dd.Ws + (gx + dd.ox)) * dd.C + cd;
-              *reinterpret_cast<float4*>(dp) = make_float4(o[0], o[1], o[2], o[3]);
+              for (int q = 0; q < COLS / 16; ++q) tmem_ld16(taddr + 16 * q, v[g] + 16 * q);
             }
           }
         }
-        // next 128-pixel block: advance (yy, xx) without a division
-        yy += step_y;
-        xx += step_x;
-        if (xx >= a.PW) { xx -= a.PW; ++yy; }
+        tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          const int mb = mb0 + 2 * g;
+          if (mb < a.nmb) {
+            const int gy = y0 + yy, gx = x0 + xx;
+            if (yy < a.TH && xx < a.TW && gy < a.H && gx < a.W && !(a.debug & 2)) {
+              const float* rp = a.res != nullptr ? a.res + (((size_t)b * a.H + gy) * a.W + gx) * a.Cout + co_base : nullptr;
+#pragma unroll
+              for (int q = 0; q < COLS / 8; ++q) {  // 8 channels = one 32-byte sector per 256-bit access
+                const int co = co_base + 8 * q;
+                if (co < a.Cout) {
+                  float o[8];
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) o[j] = __uint_as_float(v[g][8 * q + j]) + bv[8 * q + j];
+                  if (rp != nullptr) {
+                    float rr[8];
+                    ldg8(rp + 8 * q, rr);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) o[j] += rr[j];
+                  }
+                  if (a.relu) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
+                  }
+                  if (a.round_out) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) o[j] = round_tf32(o[j]);
+                  }
+                  // an 8-channel group may straddle the d0|d1 split only at a multiple of 4
+                  if (vec8) {
+                    const bool first = co < a.d0.C;
+                    const ViewW dd = first ? a.d0 : a.d1;
+                    const int cd = first ? co : co - a.d0.C;
+                    stg8(dd.p + (((size_t)b * dd.Hs + (gy + dd.oy)) * dd.Ws + (gx + dd.ox)) * dd.C + cd, o);
+                  } else {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                      const int c4 = co + 4 * h;
+                      const bool first = c4 < a.d0.C;
+                      const ViewW dd = first ? a.d0 : a.d1;
+                      const int cd = first ? c4 : c4 - a.d0.C;
+                      float* dp = dd.p + (((size_t)b * dd.Hs + (gy + dd.oy)) * dd.Ws + (gx + dd.ox)) * dd.C + cd;
+                      *reinterpret_cast<float4*>(dp) = make_float4(o[4 * h], o[4 * h + 1], o[4 * h + 2], o[4 * h + 3]);
+                    }
+                  }
+                }
+              }
+            }
+            // next block of this warp (two 128-pixel blocks further): advance (yy, xx) without a division
+            yy += step_y;
+            xx += step_x;
+            if (xx >= a.PW) { xx -= a.PW; ++yy; }
+          }
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -401,7 +568,7 @@ static bool tc_init() {
 }
 
 struct TcPlan {
-  int TH, TW, PW, tilesX, tilesY, nmb, nmma, cols, plane_bytes, a_bytes, w_bytes_max, tmem_cols, nchunks, ncoblk, kcg0, kcg1;
+  int TH, TW, PW, tilesX, tilesY, nmb, nmma, cols, plane_bytes, a_bytes, w_bytes_max, w_res_bytes, tmem_cols, nchunks, ncoblk, kcg0, kcg1;
   unsigned w_coblk_stride;
   size_t smem_bytes;
   TcChunk chunks[kMaxChunks];
@@ -414,7 +581,7 @@ static int next_pow2_cols(int c) {
 }
 
 // returns false if the shape does not fit the tensor-core path
-static bool tc_plan(int B, int H, int W, int C0, int C1, int Cout, TcPlan* p) {
+static bool tc_plan(int B, int H, int W, int C0, int C1, int Cout, TcPlan* p, bool resident = false) {
   if (C0 < 8 || C0 % 8 != 0 || C1 % 8 != 0 || Cout % 8 != 0) return false;
   const int cg0 = C0 / 4, cg1 = C1 / 4;
   // chunks of at most 8 channel groups (32 channels); small concat pairs share one chunk
@@ -443,13 +610,19 @@ static bool tc_plan(int B, int H, int W, int C0, int C1, int Cout, TcPlan* p) {
   }
   p->w_coblk_stride = woff;
   p->w_bytes_max = ((9 * max_ncg * p->nmma * 16) + 127) / 128 * 128;
+  p->w_res_bytes = 0;
+  if (resident) {  // weights built in shared memory once per CTA: no per-stage weight slot
+    if (woff > kMaxResidentW) return false;
+    p->w_res_bytes = (int)((woff + 127) / 128 * 128);
+    p->w_bytes_max = 0;
+  }
   // tile geometry
   p->tilesX = (W + 247) / 248;
   p->TW = (W + p->tilesX - 1) / p->tilesX;
   p->PW = (p->TW + 2 + 7) / 8 * 8;
   if (p->PW > 256) return false;
   // one CTA per SM: kStages stages of (A planes + weights) and two TMEM accumulator buffers of <= 256 columns
-  const size_t smem_soft = (216 * 1024) / kStages, smem_hard = (216 * 1024) / kStages;
+  const size_t smem_soft = (216 * 1024 - (size_t)p->w_res_bytes) / kStages, smem_hard = smem_soft;
   int best = 0;
   for (int pass = 0; pass < 2 && best == 0; ++pass) {
     const size_t lim = pass == 0 ? smem_soft : smem_hard;
@@ -477,7 +650,7 @@ static bool tc_plan(int B, int H, int W, int C0, int C1, int Cout, TcPlan* p) {
   if (tail < 0) tail = 0;
   p->a_bytes = (int)(((size_t)max_ncg * p->plane_bytes + (size_t)tail * 16 + 127) / 128 * 128);
   p->tmem_cols = next_pow2_cols(2 * p->nmb * p->nmma);
-  p->smem_bytes = (size_t)kStages * ((size_t)p->a_bytes + p->w_bytes_max) + 128;
+  p->smem_bytes = (size_t)kStages * ((size_t)p->a_bytes + p->w_bytes_max) + p->w_res_bytes + 128;
   return true;
 }
 
@@ -505,6 +678,11 @@ bool conv3x3_tc_ok(int C0, int C1, int Cout, int Cd0, int Cd1) {
   if (!tc_plan(1, 8, 8, C0, C1, Cout, &p)) return false;
   if (Cd0 % 4 != 0 || Cd1 % 4 != 0 || Cd0 + Cd1 != Cout) return false;
   return true;
+}
+
+bool conv3x3_tc_resident(int C0, int C1, int Cout) {
+  TcPlan p;
+  return tc_init() && tc_plan(1, 8, 8, C0, C1, Cout, &p, true);
 }
 
 long long conv3x3_tc_weight_floats(int C0, int C1, int Cout) {
@@ -555,7 +733,7 @@ int conv3x3_fwd_tc(const Conv3x3Args& a, cudaStream_t st) {
   }
   TcPlan p;
   const int C1 = (a.s1.p != nullptr) ? a.s1.C : 0;
-  if (!tc_plan(a.B, a.H, a.W, a.s0.C, C1, a.Cout, &p) || a.d0.C % 4 != 0 || (a.d1.p != nullptr && a.d1.C % 4 != 0) || a.B > 65535) {
+  if (!tc_plan(a.B, a.H, a.W, a.s0.C, C1, a.Cout, &p, a.wfmt != 0) || a.d0.C % 4 != 0 || (a.d1.p != nullptr && a.d1.C % 4 != 0)) {
     set_error("pu_conv3x3_fwd: PU_MATH_TF32 does not support this shape (C %d|%d -> %d, %dx%d); check pu_conv3x3_tc_ok", a.s0.C, C1,
               a.Cout, a.H, a.W);
     return PU_ERR_UNSUPPORTED;
@@ -575,6 +753,16 @@ int conv3x3_fwd_tc(const Conv3x3Args& a, cudaStream_t st) {
   ta.TH = p.TH; ta.TW = p.TW; ta.PW = p.PW; ta.tilesX = p.tilesX; ta.tilesY = p.tilesY;
   ta.nmb = p.nmb; ta.nmma = p.nmma; ta.plane_bytes = p.plane_bytes; ta.a_bytes = p.a_bytes; ta.w_bytes_max = p.w_bytes_max;
   ta.tmem_cols = p.tmem_cols; ta.nchunks = p.nchunks; ta.w_coblk_stride = p.w_coblk_stride;
+  ta.wfmt = a.wfmt; ta.Cin = a.Cin; ta.C0 = a.s0.C; ta.w_res_bytes = p.w_res_bytes;
+  ta.s0 = a.s0; ta.s1 = a.s1;
+  {
+    const char* ld = getenv("PU_TC_LOADER");
+    ta.loader = (ld != nullptr && ld[0] == 'c') ? 0 : 1;  // default: one 5-D TMA box per source; PU_TC_LOADER=cpasync: 4 LDGSTS warps
+  }
+  {
+    const char* dbg = getenv("PU_TC_DEBUG");
+    ta.debug = dbg ? atoi(dbg) : 0;
+  }
   for (int i = 0; i < p.nchunks; ++i) ta.chunks[i] = p.chunks[i];
   const int ntiles = p.tilesX * p.tilesY * a.B;
   dim3 grid(ntiles < kNumSMs ? ntiles : kNumSMs, p.ncoblk);
