@@ -36,11 +36,12 @@ __global__ void __launch_bounds__(NT) conv3x3_ffma_kernel(const Conv3x3Args a) {
   const int px = tid % TW;
   const int r0 = (tid / TW) * RP;
 
-  float acc[RP][8];
+  // packed fp32 FMA (FFMA2: two FMAs per issue slot on sm_100): accumulators as float2 pairs of output channels
+  float2 acc2[RP][4];
 #pragma unroll
   for (int r = 0; r < RP; ++r)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[r][j] = 0.f;
+    for (int j = 0; j < 4; ++j) acc2[r][j] = make_float2(0.f, 0.f);
 
   int cbase = 0;  // channel index in the concatenated input
   for (int s = 0; s < 2; ++s) {
@@ -102,17 +103,15 @@ __global__ void __launch_bounds__(NT) conv3x3_ffma_kernel(const Conv3x3Args a) {
           for (int kx = 0; kx < 3; ++kx) {
             const float4 wa = *reinterpret_cast<const float4*>(w_s + ((ky * 3 + kx) * 8 + ci) * 8);
             const float4 wb = *reinterpret_cast<const float4*>(w_s + ((ky * 3 + kx) * 8 + ci) * 8 + 4);
+            const float2 w01 = make_float2(wa.x, wa.y), w23 = make_float2(wa.z, wa.w);
+            const float2 w45 = make_float2(wb.x, wb.y), w67 = make_float2(wb.z, wb.w);
 #pragma unroll
             for (int r = 0; r < RP; ++r) {
-              const float xv = xin[r + ky][kx];
-              acc[r][0] = fmaf(xv, wa.x, acc[r][0]);
-              acc[r][1] = fmaf(xv, wa.y, acc[r][1]);
-              acc[r][2] = fmaf(xv, wa.z, acc[r][2]);
-              acc[r][3] = fmaf(xv, wa.w, acc[r][3]);
-              acc[r][4] = fmaf(xv, wb.x, acc[r][4]);
-              acc[r][5] = fmaf(xv, wb.y, acc[r][5]);
-              acc[r][6] = fmaf(xv, wb.z, acc[r][6]);
-              acc[r][7] = fmaf(xv, wb.w, acc[r][7]);
+              const float2 xv = make_float2(xin[r + ky][kx], xin[r + ky][kx]);
+              acc2[r][0] = __ffma2_rn(xv, w01, acc2[r][0]);
+              acc2[r][1] = __ffma2_rn(xv, w23, acc2[r][1]);
+              acc2[r][2] = __ffma2_rn(xv, w45, acc2[r][2]);
+              acc2[r][3] = __ffma2_rn(xv, w67, acc2[r][3]);
             }
           }
       }
@@ -133,7 +132,10 @@ __global__ void __launch_bounds__(NT) conv3x3_ffma_kernel(const Conv3x3Args a) {
     if (gy >= a.H) continue;
     float o[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = acc[r][j] + bv[j];
+    for (int j = 0; j < 4; ++j) {
+      o[2 * j] = acc2[r][j].x + bv[2 * j];
+      o[2 * j + 1] = acc2[r][j].y + bv[2 * j + 1];
+    }
     if (a.res != nullptr) {
       const float* rp = a.res + (((size_t)b * a.H + gy) * a.W + gx) * a.Cout + co0;
       if (vec_res) {
@@ -221,11 +223,9 @@ __global__ void __launch_bounds__(256) conv3x3_wgrad_ffma_kernel(const WgradArgs
   const int co0 = blockIdx.z * 8;
   const bool gvec = (a.Cout % 4 == 0);
 
-  float acc[9][4];
+  float2 acc2[9][2];  // FFMA2: (co, co+1) pairs
 #pragma unroll
-  for (int t = 0; t < 9; ++t)
-#pragma unroll
-    for (int q = 0; q < 4; ++q) acc[t][q] = 0.f;
+  for (int t = 0; t < 9; ++t) acc2[t][0] = acc2[t][1] = make_float2(0.f, 0.f);
 
   for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
     int t = tile;
@@ -302,21 +302,25 @@ __global__ void __launch_bounds__(256) conv3x3_wgrad_ffma_kernel(const WgradArgs
           win[ky][2] = ip[ky * HW_ + xx + 2];
         }
         const float4 gv = *reinterpret_cast<const float4*>(g_s + (yy * TW + xx) * 8 + quad * 4);
+        const float2 g01 = make_float2(gv.x, gv.y), g23 = make_float2(gv.z, gv.w);
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
           for (int kx = 0; kx < 3; ++kx) {
-            const float xv = win[ky][kx];
-            acc[ky * 3 + kx][0] = fmaf(xv, gv.x, acc[ky * 3 + kx][0]);
-            acc[ky * 3 + kx][1] = fmaf(xv, gv.y, acc[ky * 3 + kx][1]);
-            acc[ky * 3 + kx][2] = fmaf(xv, gv.z, acc[ky * 3 + kx][2]);
-            acc[ky * 3 + kx][3] = fmaf(xv, gv.w, acc[ky * 3 + kx][3]);
+            const float2 xv = make_float2(win[ky][kx], win[ky][kx]);
+            acc2[ky * 3 + kx][0] = __ffma2_rn(xv, g01, acc2[ky * 3 + kx][0]);
+            acc2[ky * 3 + kx][1] = __ffma2_rn(xv, g23, acc2[ky * 3 + kx][1]);
           }
       }
     }
   }
 
   // ---- reduce the 16 row partitions (two rounds through shared memory), then one atomic per output
+  float acc[9][4];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    acc[t][0] = acc2[t][0].x; acc[t][1] = acc2[t][0].y; acc[t][2] = acc2[t][1].x; acc[t][3] = acc2[t][1].y;
+  }
   const int slot = (ci * 2 + quad) * 36;
   __syncthreads();
   if (part >= 8) {
@@ -348,6 +352,163 @@ __global__ void __launch_bounds__(256) conv3x3_wgrad_ffma_kernel(const WgradArgs
     const int ci_ = cq >> 1, quad_ = cq & 1;
     const int co = co0 + quad_ * 4 + q;
     if (ci_ < cc && co < a.Cout) atomicAdd(a.dw + ((size_t)co * a.Cin + cbase + c0 + ci_) * 9 + tap, s);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// wgrad, pipelined version for channel counts that are multiples of 8: both operand tiles stay PIXEL-major in
+// shared memory ([pixel][8 channels], exactly as they sit in the NHWC tensors), so they are staged with plain
+// 16-byte cp.async (zero-fill outside the image) into a two-stage ring: tile n+1 streams in while tile n is
+// reduced.  Thread = (ci, co quad, row partition) as above; the 8 ci lanes of a pixel read 8 consecutive words
+// and the two partitions of a warp sit (TW+2)*8 words apart (16 banks for TW = 32, 16), i.e. conflict-free.
+template <int TW, int TH>
+__global__ void __launch_bounds__(256, 2) conv3x3_wgrad_pipe_kernel(const WgradArgs a) {
+  constexpr int HW_ = TW + 2, HH_ = TH + 2;
+  constexpr int XPIX = HH_ * HW_, GPIX = TH * TW;
+  constexpr int STAGE_F = (XPIX + GPIX) * 8;
+  constexpr int HALF_W = TW / 2;
+  constexpr int RED_LD = 8 * 72 + 1;  // 8 ci x (9 taps x 8 co); 256 threads = 8 ci x 32 (row, column half) partitions
+  extern __shared__ __align__(16) float dsm[];  // [2][STAGE_F]; the reduction buffer aliases it at the end
+  static_assert(TH == 16, "one partition per (row, half)");
+  static_assert(2 * STAGE_F >= 16 * RED_LD, "reduction buffer must fit in the staging ring");
+
+  const int tid = threadIdx.x;
+  const int ci = tid & 7, part = tid >> 3;  // thread = one input channel x all 8 output channels x 9 taps
+  const int prow = part & 15, phalf = part >> 4;
+  int cchunk = blockIdx.y;
+  const int nchunk0 = a.s0.C / 8;
+  const View v = cchunk < nchunk0 ? a.s0 : a.s1;
+  const int cbase = cchunk < nchunk0 ? 0 : a.s0.C;
+  if (cchunk >= nchunk0) cchunk -= nchunk0;
+  const int c0 = cchunk * 8;
+  const int co0 = blockIdx.z * 8;
+
+  auto issue = [&](int tile, int stage) {
+    int t = tile;
+    const int tx = t % a.tilesX;
+    t /= a.tilesX;
+    const int ty = t % a.tilesY;
+    const int b = t / a.tilesY;
+    const int x0 = tx * TW, y0 = ty * TH;
+    float* xs = dsm + stage * STAGE_F;
+    float* gs = xs + XPIX * 8;
+    for (int i = tid; i < XPIX * 2; i += 256) {  // two 16-byte halves per halo pixel
+      const int pix = i >> 1, half = i & 1;
+      const int hy = pix / HW_, hx = pix - hy * HW_;
+      const int gy = y0 + hy - 1, gx = x0 + hx - 1;
+      const bool ok = gy >= 0 && gy < a.H && gx >= 0 && gx < a.W;
+      const float* src = ok ? v.p + (((size_t)b * v.Hs + (gy + v.oy)) * v.Ws + (gx + v.ox)) * v.C + c0 + half * 4 : v.p;
+      const unsigned dst = (unsigned)__cvta_generic_to_shared(xs + pix * 8 + half * 4);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16 : 0) : "memory");
+    }
+    for (int i = tid; i < GPIX * 2; i += 256) {
+      const int pix = i >> 1, half = i & 1;
+      const int yy = pix / TW, xx = pix - yy * TW;
+      const int gy = y0 + yy, gx = x0 + xx;
+      const bool ok = gy < a.H && gx < a.W;
+      const float* src = ok ? a.g + (((size_t)b * a.H + gy) * a.W + gx) * a.Cout + co0 + half * 4 : a.g;
+      const unsigned dst = (unsigned)__cvta_generic_to_shared(gs + pix * 8 + half * 4);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16 : 0) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  float2 acc2[9][4];  // FFMA2 accumulators: 9 taps x (co pairs 01,23,45,67)
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc2[t][q] = make_float2(0.f, 0.f);
+
+  int stage = 0;
+  if ((int)blockIdx.x < a.ntiles) issue(blockIdx.x, 0);
+  for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, stage ^= 1) {
+    const int next = tile + gridDim.x;
+    if (next < a.ntiles) {
+      issue(next, stage ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const float* xs = dsm + stage * STAGE_F;
+    const float* gs = xs + XPIX * 8;
+    {
+      const int xbeg = phalf * HALF_W;
+      const float* ip = xs + (prow * HW_ + xbeg) * 8 + ci;
+      const float* gp = gs + (prow * TW + xbeg) * 8;
+      float win[3][3];
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        win[ky][1] = ip[(ky * HW_ + 0) * 8];
+        win[ky][2] = ip[(ky * HW_ + 1) * 8];
+      }
+#pragma unroll 4
+      for (int xx = 0; xx < HALF_W; ++xx) {
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+          win[ky][0] = win[ky][1];
+          win[ky][1] = win[ky][2];
+          win[ky][2] = ip[(ky * HW_ + xx + 2) * 8];
+        }
+        const float4 ga = *reinterpret_cast<const float4*>(gp + xx * 8);
+        const float4 gb = *reinterpret_cast<const float4*>(gp + xx * 8 + 4);
+        const float2 g01 = make_float2(ga.x, ga.y), g23 = make_float2(ga.z, ga.w);
+        const float2 g45 = make_float2(gb.x, gb.y), g67 = make_float2(gb.z, gb.w);
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            const float2 xv = make_float2(win[ky][kx], win[ky][kx]);
+            acc2[ky * 3 + kx][0] = __ffma2_rn(xv, g01, acc2[ky * 3 + kx][0]);
+            acc2[ky * 3 + kx][1] = __ffma2_rn(xv, g23, acc2[ky * 3 + kx][1]);
+            acc2[ky * 3 + kx][2] = __ffma2_rn(xv, g45, acc2[ky * 3 + kx][2]);
+            acc2[ky * 3 + kx][3] = __ffma2_rn(xv, g67, acc2[ky * 3 + kx][3]);
+          }
+      }
+    }
+    __syncthreads();  // everyone is done with `stage` before the next iteration refills it
+  }
+
+  // ---- reduce the 32 partitions through shared memory (16 slots, two folding rounds), then one atomic per output
+  float (*red_s)[RED_LD] = reinterpret_cast<float (*)[RED_LD]>(dsm);
+  const int slot = ci * 72;
+  __syncthreads();
+  if (part >= 16) {
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        red_s[part - 16][slot + t * 8 + 2 * q] = acc2[t][q].x;
+        red_s[part - 16][slot + t * 8 + 2 * q + 1] = acc2[t][q].y;
+      }
+  }
+  __syncthreads();
+  if (part < 16) {
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        acc2[t][q].x += red_s[part][slot + t * 8 + 2 * q];
+        acc2[t][q].y += red_s[part][slot + t * 8 + 2 * q + 1];
+      }
+  }
+  __syncthreads();
+  if (part < 16) {
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        red_s[part][slot + t * 8 + 2 * q] = acc2[t][q].x;
+        red_s[part][slot + t * 8 + 2 * q + 1] = acc2[t][q].y;
+      }
+  }
+  __syncthreads();
+  for (int i = tid; i < 8 * 72; i += 256) {
+    float sum = 0.f;
+#pragma unroll
+    for (int p = 0; p < 16; ++p) sum += red_s[p][i];
+    const int co = co0 + (i & 7), tap = (i >> 3) % 9, ci_ = i / 72;
+    atomicAdd(a.dw + ((size_t)co * a.Cin + cbase + c0 + ci_) * 9 + tap, sum);
   }
 }
 
@@ -459,6 +620,38 @@ int conv3x3_wgrad_ffma(const WgradArgs& a0, cudaStream_t st) {
   }
   const int nci = cdiv(a.s0.C, 8) + ((a.s1.p != nullptr && a.s1.C > 0) ? cdiv(a.s1.C, 8) : 0);
   const int nco = cdiv(a.Cout, 8);
+  const bool have1 = a.s1.p != nullptr && a.s1.C > 0;
+  if (a.s0.C % 8 == 0 && (!have1 || a.s1.C % 8 == 0) && a.Cout % 8 == 0) {
+    // pipelined cp.async kernel (2 CTAs / SM, 72 accumulators per thread)
+    if (a.W > 16) {
+      constexpr int TW = 32, TH = 16;
+      a.tilesX = cdiv(a.W, TW); a.tilesY = cdiv(a.H, TH);
+      a.ntiles = a.tilesX * a.tilesY * a.B;
+      const size_t smem = 2 * ((TH + 2) * (TW + 2) + TH * TW) * 8 * sizeof(float);
+      static bool attr = false;
+      if (!attr) {
+        cudaFuncSetAttribute(conv3x3_wgrad_pipe_kernel<TW, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr = true;
+      }
+      const int gx = max(1, min(a.ntiles, (2 * kNumSMs) / max(1, nci * nco)));
+      dim3 grid(gx, nci, nco);
+      conv3x3_wgrad_pipe_kernel<TW, TH><<<grid, 256, smem, st>>>(a);
+    } else {
+      constexpr int TW = 16, TH = 16;
+      a.tilesX = cdiv(a.W, TW); a.tilesY = cdiv(a.H, TH);
+      a.ntiles = a.tilesX * a.tilesY * a.B;
+      const size_t smem = 2 * ((TH + 2) * (TW + 2) + TH * TW) * 8 * sizeof(float);
+      static bool attr = false;
+      if (!attr) {
+        cudaFuncSetAttribute(conv3x3_wgrad_pipe_kernel<TW, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr = true;
+      }
+      const int gx = max(1, min(a.ntiles, (4 * kNumSMs) / max(1, nci * nco)));
+      dim3 grid(gx, nci, nco);
+      conv3x3_wgrad_pipe_kernel<TW, TH><<<grid, 256, smem, st>>>(a);
+    }
+    return post_launch("conv3x3_wgrad_pipe");
+  }
   if (a.W > 16) {
     a.tilesX = cdiv(a.W, 32); a.tilesY = cdiv(a.H, 16);
     a.ntiles = a.tilesX * a.tilesY * a.B;
