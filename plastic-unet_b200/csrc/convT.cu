@@ -12,7 +12,7 @@ namespace pu {
 // thread = (output pixel, block of 8 co).  w is [Cin][Cout][2][2].
 __global__ void convT2x2_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                                     float* __restrict__ y, int B, int H, int W, int Cin, int Cout, int flags) {
-  extern __shared__ float ws[];  // [4][Cin][8]
+  extern __shared__ __align__(16) float ws[];  // [4][Cin][8]
   const int co0 = blockIdx.y * 8;
   for (int i = threadIdx.x; i < 4 * Cin * 8; i += blockDim.x) {
     const int j = i & 7, ci = (i >> 3) % Cin, ac = i / (8 * Cin);
@@ -33,14 +33,23 @@ __global__ void convT2x2_fwd_kernel(const float* __restrict__ x, const float* __
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = (bias != nullptr && co0 + j < Cout) ? bias[co0 + j] : 0.f;
   if (Cin % 4 == 0) {
+    float2 a2[4] = {make_float2(acc[0], acc[1]), make_float2(acc[2], acc[3]), make_float2(acc[4], acc[5]), make_float2(acc[6], acc[7])};
     for (int c = 0; c < Cin; c += 4) {
       const float4 v = ldg4(xp + c);
       const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = fmaf(vv[u], wp[(c + u) * 8 + j], acc[j]);
+      for (int u = 0; u < 4; ++u) {
+        const float4 wa = *reinterpret_cast<const float4*>(wp + (c + u) * 8);
+        const float4 wb = *reinterpret_cast<const float4*>(wp + (c + u) * 8 + 4);
+        const float2 xv = make_float2(vv[u], vv[u]);
+        a2[0] = __ffma2_rn(xv, make_float2(wa.x, wa.y), a2[0]);
+        a2[1] = __ffma2_rn(xv, make_float2(wa.z, wa.w), a2[1]);
+        a2[2] = __ffma2_rn(xv, make_float2(wb.x, wb.y), a2[2]);
+        a2[3] = __ffma2_rn(xv, make_float2(wb.z, wb.w), a2[3]);
+      }
     }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { acc[2 * j] = a2[j].x; acc[2 * j + 1] = a2[j].y; }
   } else {
     for (int c = 0; c < Cin; ++c) {
       const float v = __ldg(xp + c);
@@ -66,7 +75,7 @@ __global__ void convT2x2_fwd_kernel(const float* __restrict__ x, const float* __
 // dx[b,i,j,ci] = sum_{a,c,co} dy[b,2i+a,2j+c,co] w[ci][co][a][c];  thread = (input pixel, block of 8 ci)
 __global__ void convT2x2_dx_kernel(const float* __restrict__ dy, const float* __restrict__ w, float* __restrict__ dx,
                                    int B, int H, int W, int Cin, int Cout) {
-  extern __shared__ float ws[];  // [4][Cout][8 ci]
+  extern __shared__ __align__(16) float ws[];  // [4][Cout][8 ci]
   const int ci0 = blockIdx.y * 8;
   for (int i = threadIdx.x; i < 4 * Cout * 8; i += blockDim.x) {
     const int j = i & 7, co = (i >> 3) % Cout, ac = i / (8 * Cout);
@@ -82,19 +91,48 @@ __global__ void convT2x2_dx_kernel(const float* __restrict__ dy, const float* __
   float acc[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-  for (int ac = 0; ac < 4; ++ac) {
-    const float* gp = dy + (((size_t)b * 2 * H + 2 * iy + (ac >> 1)) * 2 * W + 2 * jx + (ac & 1)) * Cout;
-    const float* wp = ws + ac * Cout * 8;
-    for (int co = 0; co < Cout; ++co) {
-      const float v = __ldg(gp + co);
+  if (Cout % 4 == 0) {
+    float2 a2[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+    for (int ac = 0; ac < 4; ++ac) {
+      const float* gp = dy + (((size_t)b * 2 * H + 2 * iy + (ac >> 1)) * 2 * W + 2 * jx + (ac & 1)) * Cout;
+      const float* wp = ws + ac * Cout * 8;
+      for (int co = 0; co < Cout; co += 4) {
+        const float4 gv = ldg4(gp + co);
+        const float vv[4] = {gv.x, gv.y, gv.z, gv.w};
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = fmaf(v, wp[co * 8 + j], acc[j]);
+        for (int u = 0; u < 4; ++u) {
+          const float4 wa = *reinterpret_cast<const float4*>(wp + (co + u) * 8);
+          const float4 wb = *reinterpret_cast<const float4*>(wp + (co + u) * 8 + 4);
+          const float2 xv = make_float2(vv[u], vv[u]);
+          a2[0] = __ffma2_rn(xv, make_float2(wa.x, wa.y), a2[0]);
+          a2[1] = __ffma2_rn(xv, make_float2(wa.z, wa.w), a2[1]);
+          a2[2] = __ffma2_rn(xv, make_float2(wb.x, wb.y), a2[2]);
+          a2[3] = __ffma2_rn(xv, make_float2(wb.z, wb.w), a2[3]);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { acc[2 * j] = a2[j].x; acc[2 * j + 1] = a2[j].y; }
+  } else {
+    for (int ac = 0; ac < 4; ++ac) {
+      const float* gp = dy + (((size_t)b * 2 * H + 2 * iy + (ac >> 1)) * 2 * W + 2 * jx + (ac & 1)) * Cout;
+      const float* wp = ws + ac * Cout * 8;
+      for (int co = 0; co < Cout; ++co) {
+        const float v = __ldg(gp + co);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(v, wp[co * 8 + j], acc[j]);
+      }
     }
   }
   float* dp = dx + p * Cin + ci0;
+  if (Cin % 4 == 0 && ci0 + 8 <= Cin) {
+    *reinterpret_cast<float4*>(dp) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    *reinterpret_cast<float4*>(dp + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+  } else {
 #pragma unroll
-  for (int j = 0; j < 8; ++j)
-    if (ci0 + j < Cin) dp[j] = acc[j];
+    for (int j = 0; j < 8; ++j)
+      if (ci0 + j < Cin) dp[j] = acc[j];
+  }
 }
 
 // dw[ci][co][a][c] = sum_{b,i,j} x[b,i,j,ci] dy[b,2i+a,2j+c,co].

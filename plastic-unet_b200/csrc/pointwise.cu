@@ -140,6 +140,49 @@ __global__ void conv1x1_dw_kernel(const float* __restrict__ x, const float* __re
   }
 }
 
+// outc backward (Cout == 1, no coords), one pass: dx[p][k] = g[p]*w[k]; dw[k] = sum_p g[p]*x[p][k]; db = sum_p g[p].
+// thread = pixel (grid-stride), 128-bit loads/stores, per-thread accumulators reduced by warp shuffles + atomics
+// into dwb = [CIN + 1] (pre-zeroed).
+template <int CIN>
+__global__ void __launch_bounds__(256) conv1x1_bwd_c1_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                             const float* __restrict__ g, float* __restrict__ dx,
+                                                             float* __restrict__ dwb, long long npix) {
+  __shared__ float red[8][CIN + 1];
+  float wv[CIN];
+#pragma unroll
+  for (int k = 0; k < CIN; ++k) wv[k] = __ldg(w + k);
+  float acc[CIN + 1];
+#pragma unroll
+  for (int k = 0; k <= CIN; ++k) acc[k] = 0.f;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += (long long)gridDim.x * blockDim.x) {
+    const float gv = __ldg(g + p);
+    acc[CIN] += gv;
+#pragma unroll
+    for (int k = 0; k < CIN; k += 4) {
+      const float4 xv = ldg4(x + p * CIN + k);
+      acc[k] = fmaf(gv, xv.x, acc[k]);
+      acc[k + 1] = fmaf(gv, xv.y, acc[k + 1]);
+      acc[k + 2] = fmaf(gv, xv.z, acc[k + 2]);
+      acc[k + 3] = fmaf(gv, xv.w, acc[k + 3]);
+      if (dx != nullptr)
+        *reinterpret_cast<float4*>(dx + p * CIN + k) = make_float4(gv * wv[k], gv * wv[k + 1], gv * wv[k + 2], gv * wv[k + 3]);
+    }
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k <= CIN; ++k) {
+    const float v = warp_sum(acc[k]);
+    if (lane == 0) red[wid][k] = v;
+  }
+  __syncthreads();
+  if ((int)threadIdx.x <= CIN) {
+    float sum = 0.f;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) sum += red[u][threadIdx.x];
+    atomicAdd(dwb + threadIdx.x, sum);
+  }
+}
+
 // scatter the [co][K+1] accumulator into dw [Cout][K] and db [Cout]
 __global__ void conv1x1_dw_finish_kernel(const float* __restrict__ dwb, float* __restrict__ dw, float* __restrict__ db, int Cout, int K) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -263,17 +306,33 @@ int pu_conv1x1_bwd(const float* x, const float* w, const float* g, float* dx, fl
   const int K = Cin + coords;
   const int npairs = Cout * (K + 1);
   PU_REQUIRE(npairs <= 256, PU_ERR_UNSUPPORTED, "pu_conv1x1_bwd: Cout*(Cin+coords+1)=%d > 256", npairs);
-  if (dx != nullptr) {
-    const size_t smem = (size_t)Cout * Cin * sizeof(float);
-    pu::conv1x1_dx_kernel<<<(unsigned)((npix + 255) / 256), 256, smem, st>>>(g, w, dx, npix, Cin, Cout, K);
-    int rc = pu::post_launch("pu_conv1x1_bwd dx");
-    if (rc) return rc;
-  }
   float* scratch = ws;  // caller-provided [Cout*(Cin+coords+1)] accumulator
   cudaError_t e = cudaMemsetAsync(scratch, 0, npairs * sizeof(float), st);
   if (e != cudaSuccess) {
     pu::set_error("pu_conv1x1_bwd memset: %s", cudaGetErrorString(e));
     return PU_ERR_CUDA;
+  }
+  if (Cout == 1 && coords == 0 && (Cin == 8 || Cin == 16 || Cin == 32 || Cin == 64) && pu::aligned16(x) && (dx == nullptr || pu::aligned16(dx))) {
+    // fused single pass for the output conv: dx, dw and db together
+    long long blocks = (npix + 256 * 4 - 1) / (256 * 4);
+    if (blocks < 1) blocks = 1;
+    if (blocks > 8 * pu::kNumSMs) blocks = 8 * pu::kNumSMs;
+    switch (Cin) {
+      case 8: pu::conv1x1_bwd_c1_kernel<8><<<(unsigned)blocks, 256, 0, st>>>(x, w, g, dx, scratch, npix); break;
+      case 16: pu::conv1x1_bwd_c1_kernel<16><<<(unsigned)blocks, 256, 0, st>>>(x, w, g, dx, scratch, npix); break;
+      case 32: pu::conv1x1_bwd_c1_kernel<32><<<(unsigned)blocks, 256, 0, st>>>(x, w, g, dx, scratch, npix); break;
+      default: pu::conv1x1_bwd_c1_kernel<64><<<(unsigned)blocks, 256, 0, st>>>(x, w, g, dx, scratch, npix); break;
+    }
+    int rc1 = pu::post_launch("pu_conv1x1_bwd fused");
+    if (rc1) return rc1;
+    pu::conv1x1_dw_finish_kernel<<<pu::cdiv(npairs, 256), 256, 0, st>>>(scratch, dw, db, Cout, K);
+    return pu::post_launch("pu_conv1x1_bwd finish");
+  }
+  if (dx != nullptr) {
+    const size_t smem = (size_t)Cout * Cin * sizeof(float);
+    pu::conv1x1_dx_kernel<<<(unsigned)((npix + 255) / 256), 256, smem, st>>>(g, w, dx, npix, Cin, Cout, K);
+    int rc = pu::post_launch("pu_conv1x1_bwd dx");
+    if (rc) return rc;
   }
   int P = 1;
   while (P < npairs) P <<= 1;  // pad pairs to a power of two <= 256
