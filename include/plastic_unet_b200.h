@@ -78,13 +78,13 @@ long long pu_pack_w3x3_floats(int Cout, int Cin, int transpose, int math, int C0
 /* 1 if a conv with these source / destination channel counts can run on the tcgen05 path (PU_MATH_TF32) */
 int pu_conv3x3_tc_ok(int C0, int C1, int Cout, int Cd0, int Cd1);
 /* 1 if, additionally, the tcgen05 kernel can build its weight tiles from the raw OIHW tensor (they fit in shared memory) */
-int pu_conv3x3_tc_resident(int C0, int C1, int Cout);
+int pu_conv3x3_tc_resident(int C0, int C1, int Cout, int H, int W);
 
 /* y = act( conv3x3(cat[src0,src1]) + bias + res ), written channel-split into dst0|dst1 (flags: PU_FLAG_*).
  * wfmt selects what `wp` points at: PU_W_PACKED (output of pu_pack_w3x3 for this math mode), PU_W_OIHW (the raw
  * [Cout, C0+C1, 3, 3] weight: operand tiles are built inside the kernel, no pack launch) or PU_W_OIHW_DGRAD (the
  * raw [C0, Cout, 3, 3] weight of the forward conv whose dgrad this call computes).  With PU_MATH_TF32 the raw
- * formats need pu_conv3x3_tc_resident(C0, C1, Cout).
+ * formats need pu_conv3x3_tc_resident(C0, C1, Cout, H, W).
  * src1, bias, res, dst1 may be NULL.  wp is the packed weight [9][C0+C1][Cout].
  * dst views may be larger than HxW (their border is NOT written — caller zero-fills).    */
 int pu_conv3x3_fwd(const float* src0, int H0, int W0, int C0, int oy0, int ox0,
@@ -210,6 +210,10 @@ int pu_bce_fwd_bwd(const float* S, const float* T, float* loss, float* gS, long 
 /* Adam over one flat arena (torch.optim.Adam defaults; step_count is a device float scalar that is incremented) */
 int pu_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* step_count,
                  const float* lr, float beta1, float beta2, float eps, float grad_scale, long long n, void* stream);
+
+/* table: n rows of (source device pointer, destination offset in floats, element count) as int64 on the device;
+ * copies every source tensor into flat[offset ...] with one launch (gradient tensors -> flat gradient arena). */
+int pu_gather_flat(const long long* table, int n, float* flat, void* stream);
 
 /* elementwise helpers for autograd glue */
 int pu_add(const float* a, const float* b, float* out, long long n, void* stream);

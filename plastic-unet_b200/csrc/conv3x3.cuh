@@ -28,7 +28,7 @@ int conv3x3_wgrad_ffma(const WgradArgs& a, cudaStream_t st);
 // tcgen05 path (conv3x3_tc.cu); returns PU_ERR_UNSUPPORTED when the shape does not fit it
 int conv3x3_fwd_tc(const Conv3x3Args& a, cudaStream_t st);
 bool conv3x3_tc_ok(int C0, int C1, int Cout, int Cd0, int Cd1);
-bool conv3x3_tc_resident(int C0, int C1, int Cout);
+bool conv3x3_tc_resident(int C0, int C1, int Cout, int H, int W);
 long long conv3x3_tc_weight_floats(int C0, int C1, int Cout);
 int conv3x3_tc_pack(const float* w_oihw, float* out, int Cout_w, int Cin_w, int transpose, int C0, cudaStream_t st);
 

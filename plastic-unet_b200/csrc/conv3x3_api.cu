@@ -87,6 +87,6 @@ int pu_conv3x3_wgrad(const float* src0, int H0, int W0, int C0, int oy0, int ox0
 
 int pu_conv3x3_tc_ok(int C0, int C1, int Cout, int Cd0, int Cd1) { return pu::conv3x3_tc_ok(C0, C1, Cout, Cd0, Cd1) ? 1 : 0; }
 
-int pu_conv3x3_tc_resident(int C0, int C1, int Cout) { return pu::conv3x3_tc_resident(C0, C1, Cout) ? 1 : 0; }
+int pu_conv3x3_tc_resident(int C0, int C1, int Cout, int H, int W) { return pu::conv3x3_tc_resident(C0, C1, Cout, H, W) ? 1 : 0; }
 
 }  // extern "C"

@@ -33,7 +33,7 @@ namespace pu {
 
 constexpr int kMaxChunks = 48;
 constexpr int kCoBlk = 64;  // output channels per CTA (grid.y splits larger Cout)
-constexpr unsigned kMaxResidentW = 40 * 1024;  // largest weight image kept resident in shared memory
+constexpr unsigned kMaxResidentW = 40 * 1024;  // largest weight image kept resident in shared memory (per co block)
 
 struct TcChunk {
   int cgA, nA;  // planes [0, nA): channel groups cgA.. of source srcA
@@ -203,22 +203,31 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const __grid_
     for (int c = 0; c < a.nchunks; ++c) {
       const TcChunk ch = a.chunks[c];
       const int ncg = ch.nA + ch.nB;
-      const int n_el = 9 * ncg * a.nmma * 4;
-      float* out = reinterpret_cast<float*>(smWres + ch.w_off);
-      for (int i = tid; i < n_el; i += kTcThreads) {
-        const int j = i & 3;
-        const int n = (i >> 2) % a.nmma;
-        const int pl = (i / (4 * a.nmma)) % ncg;
-        const int tap = i / (4 * a.nmma * ncg);
-        int ci;
-        if (pl < ch.nA) ci = (ch.srcA == 0 ? 0 : a.C0) + (ch.cgA + pl) * 4 + j;
-        else ci = a.C0 + (ch.cgB + pl - ch.nA) * 4 + j;
+      const int units = ncg * a.nmma;  // 16-byte units per tap: [plane][n]
+      float4* out = reinterpret_cast<float4*>(smWres + ch.w_off);
+      const int nsh = 31 - __clz(a.nmma);  // nmma is 16, 32 or 64
+      for (int u = tid; u < units; u += kTcThreads) {
+        const int n = u & (a.nmma - 1), pl = u >> nsh;
+        int ci0;
+        if (pl < ch.nA) ci0 = (ch.srcA == 0 ? 0 : a.C0) + (ch.cgA + pl) * 4;
+        else ci0 = a.C0 + (ch.cgB + pl - ch.nA) * 4;
         const int co = co_base_w + n;
-        float v = 0.f;
-        if (co < a.Cout && n < kCoBlk && ci < a.Cin) {
-          v = a.wfmt == 1 ? __ldg(w + ((size_t)co * a.Cin + ci) * 9 + tap) : __ldg(w + ((size_t)ci * a.Cout + co) * 9 + (8 - tap));
+        const bool ok = co < a.Cout && n < kCoBlk;
+        // forward: w[co][ci][tap]; dgrad: w[ci][co][8 - tap]  (ci = conv input channel, co = conv output channel)
+        const float* base = a.wfmt == 1 ? w + ((size_t)co * a.Cin + ci0) * 9 : w + ((size_t)ci0 * a.Cout + co) * 9;
+        const size_t cstride = a.wfmt == 1 ? 9 : (size_t)a.Cout * 9;
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          const int t = a.wfmt == 1 ? tap : 8 - tap;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ok) {
+            v.x = round_tf32(__ldg(base + t));
+            v.y = round_tf32(__ldg(base + cstride + t));
+            v.z = round_tf32(__ldg(base + 2 * cstride + t));
+            v.w = round_tf32(__ldg(base + 3 * cstride + t));
+          }
+          out[tap * units + u] = v;
         }
-        out[i] = round_tf32(v);
       }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tensor-core (async proxy) reads
@@ -515,23 +524,27 @@ __global__ void pack_w3x3_tc_kernel(const TcPackArgs a) {
   const int coblk = blockIdx.y, c = blockIdx.z;
   const TcChunk ch = a.chunks[c];
   const int ncg = ch.nA + ch.nB;
-  const int n_el = 9 * ncg * a.nmma * 4;
-  float* out = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(a.out) + (size_t)coblk * a.w_coblk_stride + ch.w_off);
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_el; i += gridDim.x * blockDim.x) {
-    const int j = i & 3;
-    const int n = (i >> 2) % a.nmma;
-    const int pl = (i / (4 * a.nmma)) % ncg;
-    const int tap = i / (4 * a.nmma * ncg);
-    int ci;  // channel in the concatenated input
-    if (pl < ch.nA) ci = (ch.srcA == 0 ? 0 : a.C0) + (ch.cgA + pl) * 4 + j;
-    else ci = a.C0 + (ch.cgB + pl - ch.nA) * 4 + j;
+  const int units = ncg * a.nmma;  // 16-byte units per tap: [plane][n]
+  float4* out = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(a.out) + (size_t)coblk * a.w_coblk_stride + ch.w_off);
+  const int nsh = 31 - __clz(a.nmma);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 9 * units; i += gridDim.x * blockDim.x) {
+    const int tap = i / units, u = i - tap * units;
+    const int n = u & (a.nmma - 1), pl = u >> nsh;
+    int ci0;
+    if (pl < ch.nA) ci0 = (ch.srcA == 0 ? 0 : a.C0) + (ch.cgA + pl) * 4;
+    else ci0 = a.C0 + (ch.cgB + pl - ch.nA) * 4;
     const int co = coblk * kCoBlk + n;
-    float v = 0.f;
-    if (co < a.Cout && n < kCoBlk && ci < a.Cin) {
-      if (!a.transpose) v = a.w[((size_t)co * a.Cin_w + ci) * 9 + tap];
-      else v = a.w[((size_t)ci * a.Cin_w + co) * 9 + (8 - tap)];
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (co < a.Cout && n < kCoBlk) {
+      // forward: w[co][ci][tap]; dgrad: w[ci][co][8 - tap] of the OIHW tensor [Cout_w][Cin_w]
+      const float* base = !a.transpose ? a.w + ((size_t)co * a.Cin_w + ci0) * 9 + tap : a.w + ((size_t)ci0 * a.Cin_w + co) * 9 + (8 - tap);
+      const size_t cs = !a.transpose ? 9 : (size_t)a.Cin_w * 9;
+      v.x = round_tf32(__ldg(base));
+      v.y = round_tf32(__ldg(base + cs));
+      v.z = round_tf32(__ldg(base + 2 * cs));
+      v.w = round_tf32(__ldg(base + 3 * cs));
     }
-    out[i] = round_tf32(v);
+    out[i] = v;
   }
 }
 
@@ -680,9 +693,9 @@ bool conv3x3_tc_ok(int C0, int C1, int Cout, int Cd0, int Cd1) {
   return true;
 }
 
-bool conv3x3_tc_resident(int C0, int C1, int Cout) {
+bool conv3x3_tc_resident(int C0, int C1, int Cout, int H, int W) {
   TcPlan p;
-  return tc_init() && tc_plan(1, 8, 8, C0, C1, Cout, &p, true);
+  return tc_init() && tc_plan(1, H, W, C0, C1, Cout, &p, true);
 }
 
 long long conv3x3_tc_weight_floats(int C0, int C1, int Cout) {
@@ -706,7 +719,7 @@ int conv3x3_tc_pack(const float* w_oihw, float* out, int Cout_w, int Cin_w, int 
   pa.Cin = cin; pa.Cout = cout; pa.C0 = c0; pa.nmma = p.nmma; pa.nchunks = p.nchunks; pa.ncoblk = p.ncoblk;
   pa.w_coblk_stride = p.w_coblk_stride;
   for (int i = 0; i < p.nchunks; ++i) pa.chunks[i] = p.chunks[i];
-  dim3 g(4, p.ncoblk, p.nchunks);
+  dim3 g(8, p.ncoblk, p.nchunks);
   pack_w3x3_tc_kernel<<<g, 256, 0, st>>>(pa);
   return post_launch("pu_pack_w3x3 (tc)");
 }

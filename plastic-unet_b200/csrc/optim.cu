@@ -48,6 +48,17 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
 }
 
+// flat[dst_off[t] + i] = src[t][i]: gathers the per-parameter gradient tensors autograd produced into the flat
+// gradient arena with ONE launch (blockIdx.y = tensor), instead of one accumulate kernel per parameter.
+__global__ void gather_flat_kernel(const long long* __restrict__ table, int n, float* __restrict__ flat) {
+  const int t = blockIdx.y;
+  if (t >= n) return;
+  const float* src = reinterpret_cast<const float*>(table[3 * t]);
+  const long long off = table[3 * t + 1], size = table[3 * t + 2];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < size; i += (long long)gridDim.x * blockDim.x)
+    flat[off + i] = src[i];
+}
+
 }  // namespace pu
 
 extern "C" {
@@ -64,6 +75,13 @@ int pu_bce_fwd_bwd(const float* S, const float* T, float* loss, float* gS, long 
   g = g < 1 ? 1 : (g > 4 * pu::kNumSMs ? 4 * pu::kNumSMs : g);
   pu::bce_kernel<<<g, 256, 0, st>>>(S, T, loss, gS, n);
   return pu::post_launch("pu_bce_fwd_bwd");
+}
+
+int pu_gather_flat(const long long* table, int n, float* flat, void* stream) {
+  PU_REQUIRE(table && flat && n > 0 && n <= 65535, PU_ERR_BAD_ARG, "pu_gather_flat: bad argument");
+  dim3 grid(8, n);
+  pu::gather_flat_kernel<<<grid, 256, 0, pu::as_stream(stream)>>>(table, n, flat);
+  return pu::post_launch("pu_gather_flat");
 }
 
 int pu_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* step_count, const float* lr, float beta1,

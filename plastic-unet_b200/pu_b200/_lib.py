@@ -19,6 +19,7 @@ _CTYPE = {
     "const float*": ctypes.c_void_p,
     "float*": ctypes.c_void_p,
     "const double*": ctypes.c_void_p,
+    "const long long*": ctypes.c_void_p,
     "double*": ctypes.c_void_p,
     "void*": ctypes.c_void_p,
     "int": ctypes.c_int,

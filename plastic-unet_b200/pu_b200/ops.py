@@ -29,17 +29,17 @@ def _tc_ok(C0: int, C1: int, Cout: int, Cd0: int, Cd1: int) -> bool:
 
 
 @functools.lru_cache(maxsize=None)
-def _tc_resident(C0: int, C1: int, Cout: int) -> bool:
-    return bool(_lib.load().pu_conv3x3_tc_resident(C0, C1, Cout))
+def _tc_resident(C0: int, C1: int, Cout: int, H: int, W: int) -> bool:
+    return bool(_lib.load().pu_conv3x3_tc_resident(C0, C1, Cout, H, W))
 
 
 W_PACKED, W_OIHW, W_OIHW_DGRAD = 0, 1, 2
 
 
-def _weight_operand(weight: Tensor, transpose: int, math: int, C0: int, C1: int, Cout_conv: int):
+def _weight_operand(weight: Tensor, transpose: int, math: int, C0: int, C1: int, Cout_conv: int, H: int, W: int):
     """-> (tensor, wfmt): the raw OIHW weight whenever the kernel can build its operand tiles itself (every FFMA
     conv, and tcgen05 convs whose weight image fits in shared memory), else the pu_pack_w3x3 buffer."""
-    if math == MATH_FP32 or _tc_resident(C0, C1, Cout_conv):
+    if math == MATH_FP32 or _tc_resident(C0, C1, Cout_conv, H, W):
         return weight, (W_OIHW_DGRAD if transpose else W_OIHW)
     return _pack_w(weight, transpose, math, C0), W_PACKED
 
@@ -100,7 +100,7 @@ def conv3x3(x0: Tensor, x1: Optional[Tensor], weight: Tensor, bias: Optional[Ten
     # PU_MATH_TF32: tcgen05 kernel where the channel counts allow, fp32 FFMA kernel (output rounded to TF32) elsewhere
     m = MATH_TF32 if (math == MATH_TF32 and _tc_ok(C0, C1, Cout, Cout, 0)) else MATH_FP32
     flags = (FLAG_RELU if relu else 0) | (FLAG_ROUND_TF32 if math == MATH_TF32 else 0)
-    wp, wfmt = _weight_operand(weight, 0, m, C0, C1, Cout)
+    wp, wfmt = _weight_operand(weight, 0, m, C0, C1, Cout, H, W)
     y = torch.empty((B, H, W, Cout), device=x0.device, dtype=torch.float32)
     _lib.call("pu_conv3x3_fwd", x0.data_ptr(), H0, W0, C0, oy0, ox0, _p(x1), H1, W1, C1, oy1, ox1,
               wp.data_ptr(), _p(bias), _p(res), flags,
@@ -139,7 +139,7 @@ def conv3x3_bwd(dy: Tensor, y: Tensor, x0: Tensor, x1: Optional[Tensor], weight:
     dx0, dx1 = _e(dev), _e(dev)
     if need_dx:
         md = MATH_TF32 if (tf32 and _tc_ok(Cout, 0, Cin, C0, C1)) else MATH_FP32
-        wpt, wfmt = _weight_operand(weight, 1, md, Cout, 0, Cin)
+        wpt, wfmt = _weight_operand(weight, 1, md, Cout, 0, Cin, H, W)
         full0 = (H0 == H and W0 == W)
         dx0 = (torch.empty if full0 else torch.zeros)((B, H0, W0, C0), device=dev, dtype=torch.float32)
         if x1 is not None:

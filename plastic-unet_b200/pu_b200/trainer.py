@@ -36,10 +36,14 @@ class TrainStep:
         self.flat_g = torch.zeros(off, device=self.dev)
         self.m = torch.zeros(off, device=self.dev)
         self.v = torch.zeros(off, device=self.dev)
+        self.params = params
         for p, o in zip(params, self.offsets):
             self.flat_p[o:o + p.numel()].copy_(p.data.reshape(-1))
             p.data = self.flat_p[o:o + p.numel()].view_as(p)
-            p.grad = self.flat_g[o:o + p.numel()].view_as(p)
+            p.grad = None
+        # (pointer, offset, size) table of the gradient tensors, rebuilt by every eager/captured step body
+        self.table_host = torch.zeros((len(params), 3), dtype=torch.int64).pin_memory()
+        self.table_dev = torch.zeros((len(params), 3), dtype=torch.int64, device=self.dev)
         self.n_params = total
         self.step_count = torch.zeros(1, device=self.dev)
         self.lr = torch.full((1,), float(lr), device=self.dev)
@@ -56,12 +60,24 @@ class TrainStep:
     # -------------------------------------------------------------------------------------------
     def _step_body(self):
         st = torch.cuda.current_stream().cuda_stream
+        for p in self.params:
+            p.grad = None  # autograd then hands over its gradient tensors instead of launching one add per parameter
         self.flat_g.zero_()
         out, hebb_new = self.net(self.x, self.hebb)
         gS = torch.empty_like(out)
         n = out.numel()
         _lib.call("pu_bce_fwd_bwd", out.data_ptr(), self.target.data_ptr(), self.loss.data_ptr(), gS.data_ptr(), n, st)
         out.backward(gS)
+        # gather every parameter gradient into the flat arena with one launch (parameters without a gradient, e.g.
+        # eta in the reference loop, keep their zeroed slot)
+        n = 0
+        for p, o in zip(self.params, self.offsets):
+            if p.grad is not None:
+                g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
+                self.table_host[n, 0], self.table_host[n, 1], self.table_host[n, 2] = g.data_ptr(), o, g.numel()
+                n += 1
+        self.table_dev.copy_(self.table_host, non_blocking=torch.cuda.is_current_stream_capturing())
+        _lib.call("pu_gather_flat", self.table_dev.data_ptr(), n, self.flat_g.data_ptr(), st)
         if self.dp_group is not None:
             dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.dp_group)
         _lib.call("pu_adam_step", self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
