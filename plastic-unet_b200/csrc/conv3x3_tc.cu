@@ -509,6 +509,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const __grid_
   }
 }
 
+
 // ---- weight packing for the tensor-core path ------------------------------------------------------
 // out[coblk][chunk][tap][plane][n][4]  (n < nmma rows, zero beyond the co-block's valid channels), RN-rounded to TF32
 struct TcPackArgs {
@@ -786,6 +787,7 @@ int conv3x3_fwd_tc(const Conv3x3Args& a, cudaStream_t st) {
     default: return launch_tc<64>(tm0, tm1, ta, grid, p.smem_bytes, st);
   }
 }
+
 
 }  // namespace pu
 

@@ -154,7 +154,7 @@ def conv3x3_bwd(dy: Tensor, y: Tensor, x0: Tensor, x1: Optional[Tensor], weight:
     if need_dw:
         dw = torch.empty_like(weight)
         _lib.call("pu_conv3x3_wgrad", x0.data_ptr(), H0, W0, C0, oy0, ox0, _p(x1), H1, W1, C1, oy1, ox1,
-                  g.data_ptr(), dw.data_ptr(), B, H, W, Cout, MATH_FP32, _s())
+                  g.data_ptr(), dw.data_ptr(), B, H, W, Cout, math, _s())
     g_out = g if fresh_g else _e(dev)  # never return an alias of an input
     return [g_out, dx0, dx1, dw, db]
 

@@ -9,6 +9,7 @@ import torch  # noqa: E402
 from pu_b200 import _lib  # noqa: E402
 
 C0, C1, Cout, size, B = [int(v) for v in (sys.argv[1:6] + ["8", "0", "8", "128", "64"][len(sys.argv[1:6]):])]
+MATH = int(os.environ.get("WG_MATH", "0"))
 dev = "cuda"
 nbuf = 4
 xs0 = [torch.rand(B, size, size, C0, device=dev) for _ in range(nbuf)]
@@ -20,7 +21,7 @@ dw = torch.empty(Cout, C0 + C1, 3, 3, device=dev)
 def run(i):
     x1 = xs1[i % nbuf]
     _lib.call("pu_conv3x3_wgrad", xs0[i % nbuf].data_ptr(), size, size, C0, 0, 0, x1.data_ptr() if C1 else None, size, size, C1, 0, 0,
-              gs[i % nbuf].data_ptr(), dw.data_ptr(), B, size, size, Cout, 0, torch.cuda.current_stream().cuda_stream)
+              gs[i % nbuf].data_ptr(), dw.data_ptr(), B, size, size, Cout, MATH, torch.cuda.current_stream().cuda_stream)
 
 
 ITERS = 20

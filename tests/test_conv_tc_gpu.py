@@ -76,7 +76,8 @@ def test_conv3x3_tc_forward(B, C0, C1, Cout, H, W, relu, res):
     assert torch.equal(tf32_round(yo.cpu()), yo.cpu())
 
 
-@pytest.mark.parametrize("C0,C1,Cout,H,W", [(8, 8, 8, 64, 64), (16, 0, 16, 32, 32), (32, 32, 16, 16, 16), (64, 0, 64, 8, 8)])
+@pytest.mark.parametrize("C0,C1,Cout,H,W", [(8, 8, 8, 64, 64), (16, 0, 16, 32, 32), (32, 32, 16, 16, 16), (64, 0, 64, 8, 8),
+                                             (32, 0, 32, 32, 32), (64, 64, 32, 16, 16), (128, 0, 64, 12, 12), (64, 0, 128, 6, 6)])
 def test_conv3x3_tc_autograd_vs_fp32_path(C0, C1, Cout, H, W):
     """Forward + dgrad (tcgen05) + wgrad through autograd in TF32 mode vs the strict-fp32 CUDA-core path."""
     from pu_b200 import ops
