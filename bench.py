@@ -227,6 +227,12 @@ def main():
     ap.add_argument("--size", type=int, default=128)
     ap.add_argument("--rule", default="oja")
     ap.add_argument("--math", default=os.environ.get("PU_CONV_MATH", "tf32"), choices=["fp32", "tf32"])
+    ap.add_argument("--model", default="unetp", choices=["unetp", "res", "coord"], help="configs[1] is unetp; the others are the variants of configs[2..4]")
+    ap.add_argument("--neurons", type=int, default=16)
+    ap.add_argument("--depth", type=int, default=4)
+    ap.add_argument("--base", type=int, default=8)
+    ap.add_argument("--dropout", type=float, default=0.5)
+    ap.add_argument("--infer", action="store_true", help="time the batched forward-only step instead of the train step")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-images-per-step", type=int, default=16)
@@ -240,8 +246,8 @@ def main():
         return
 
     import torch.distributed as dist
-    from pu_b200 import UNetp, _lib
-    from pu_b200.trainer import TrainStep
+    from pu_b200 import UNetp, UNetpCoord, UNetpRes, _lib
+    from pu_b200.trainer import InferStep, TrainStep
 
     rank, world, local_rank = dp.init_from_env()
     if not torch.cuda.is_available():
@@ -251,14 +257,30 @@ def main():
     hbm_peak, _, peak_src = measured_peaks()
 
     torch.manual_seed(0)
-    net = quiet(UNetp, 1, 1, dev, rule=args.rule, nbf=args.size, batched=True)
+    if args.model == "unetp":
+        net = quiet(UNetp, 1, 1, dev, rule=args.rule, nbf=args.size, batched=True, depth=args.depth, base=args.base)
+        model_name = "UNetp (Plastic U-Net)" + ("" if (args.depth, args.base) == (4, 8) else " depth %d base %d" % (args.depth, args.base))
+    elif args.model == "res":
+        net = quiet(UNetpRes, 1, 1, dev, neurons=args.neurons, dropout_ratio=args.dropout, rule=args.rule, nbf=args.size, batched=True,
+                    depth=args.depth)
+        model_name = "UNetpRes (residual Plastic U-Net) neurons %d dropout %.2f depth %d" % (args.neurons, args.dropout, args.depth)
+    else:
+        net = quiet(UNetpCoord, 1, 1, dev, rule=args.rule, nbf=args.size, batched=True, depth=args.depth, base=args.base)
+        model_name = "UNetpCoord (coord-conv Plastic U-Net)"
     net.conv_math = args.math
     net.train()
     group = dist.group.WORLD if world > 1 else None
     dp.attach(net, group)
     dp.broadcast_parameters(net, 0, group)
     B = args.batch
-    ts = TrainStep(net, B, args.size, lr=1e-4, use_graph=not args.no_graph, dp_group=group)
+    if args.infer:
+        net.eval()
+        ts = InferStep(net, B, args.size, use_graph=not args.no_graph)
+        ts.loss = torch.zeros(1, device=dev)
+        _step = ts.step
+        ts.step = lambda x=None, t=None: (_step(x), ts.loss)[1]
+    else:
+        ts = TrainStep(net, B, args.size, lr=1e-4, use_graph=not args.no_graph, dp_group=group)
 
     # ---- data: device pool larger than L2 (rotated) + pinned host pool for the e2e leg
     gen = torch.Generator().manual_seed(1234 + rank)
@@ -296,6 +318,8 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     eager_launches = _lib.launch_count() - launches0
     loss_end = float(ts.loss)
+    if not args.infer and not (loss_end == loss_end and abs(loss_end) < 1e3):
+        raise SystemExit("bench.py: training diverged / produced a non-finite loss (%r)" % loss_end)
 
     # ---- timed: end to end from pinned host memory, loss read back every step
     loss_host = torch.zeros(1).pin_memory()
@@ -326,10 +350,10 @@ def main():
         kps = ts.kernels_per_step or 0
         roof = dominant_kernel_roofline(B, args.size, 1 if args.math == "tf32" else 0, dev, hbm_peak, peak_src)
         # whole-step figure against the layer-fused algorithmic bound of SURVEY.md §8d (28.39 MB / image @128)
-        alg_mb_per_img = 28.39 * (args.size / 128.0) ** 2
+        alg_mb_per_img = (9.49 if args.infer else 28.39) * (args.size / 128.0) ** 2  # UNetp figures; other models: indicative only
         step_gbs = alg_mb_per_img * 1e6 * B / (ms_max / args.steps * 1e-3) / 1e9
         cpu = None
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and args.model == "unetp" and not args.infer and (args.depth, args.base) == (4, 8):
             ips0, _, thr = cpu_train_images_per_s(4, args.size, args.rule, warm=1)
             n = int(min(256, max(8, ips0 * 12)))  # ~12 s of CPU work
             ips, n, thr = cpu_train_images_per_s(n, args.size, args.rule)
@@ -340,8 +364,9 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "tf32" if args.math == "tf32" else "f32", "data": "synthetic",
-            "config": {"workload": "UNetp (Plastic U-Net) Oja rule, 1x101x101 zero-padded to 128x128, batch %d per GPU, "
-                                   "fwd+BCE+bwd+Adam+trace update" % B,
+            "config": {"workload": "%s %s rule, %s, batch %d per GPU, %s"
+                                   % (model_name, args.rule, "1x101x101 zero-padded to 128x128" if args.size == 128 else "1x%dx%d" % (args.size, args.size),
+                                      B, "batched inference (forward, zero trace)" if args.infer else "fwd+BCE+bwd+Adam+trace update"),
                        "global_batch": B * world, "parallelism": "dp%d" % world, "conv_math": args.math,
                        "cuda_graph": not args.no_graph,
                        "l2": "inputs rotate over a %d-batch device pool (%.0f MB > 126 MB L2); per-step activation "

@@ -595,13 +595,23 @@ static int next_pow2_cols(int c) {
 }
 
 // returns false if the shape does not fit the tensor-core path
+static bool tc_plan_k(int B, int H, int W, int C0, int C1, int Cout, TcPlan* p, bool resident, int maxcg);
+
+// K chunks of at most 8 channel groups (32 channels); if a stage does not fit in shared memory (wide images with
+// streamed weights) retry with 16- and 8-channel chunks
 static bool tc_plan(int B, int H, int W, int C0, int C1, int Cout, TcPlan* p, bool resident = false) {
+  for (int maxcg = 8; maxcg >= 2; maxcg >>= 1)
+    if (tc_plan_k(B, H, W, C0, C1, Cout, p, resident, maxcg)) return true;
+  return false;
+}
+
+static bool tc_plan_k(int B, int H, int W, int C0, int C1, int Cout, TcPlan* p, bool resident, int maxcg) {
   if (C0 < 8 || C0 % 8 != 0 || C1 % 8 != 0 || Cout % 8 != 0) return false;
   const int cg0 = C0 / 4, cg1 = C1 / 4;
   // chunks of at most 8 channel groups (32 channels); small concat pairs share one chunk
   p->nchunks = 0;
-  p->kcg0 = cg0 < 8 ? cg0 : 8;
-  p->kcg1 = cg1 == 0 ? 0 : (cg1 < 8 ? cg1 : 8);
+  p->kcg0 = cg0 < maxcg ? cg0 : maxcg;
+  p->kcg1 = cg1 == 0 ? 0 : (cg1 < maxcg ? cg1 : maxcg);
   if (cg0 % p->kcg0 != 0 || (cg1 > 0 && cg1 % p->kcg1 != 0)) return false;
   const int cout_blk = Cout < kCoBlk ? Cout : kCoBlk;
   p->cols = cout_blk <= 8 ? 8 : (cout_blk <= 16 ? 16 : (cout_blk <= 32 ? 32 : 64));
@@ -615,7 +625,7 @@ static bool tc_plan(int B, int H, int W, int C0, int C1, int Cout, TcPlan* p, bo
     woff += (unsigned)(9 * (nA + nB) * p->nmma * 16);
     if (nA + nB > max_ncg) max_ncg = nA + nB;
   };
-  if (cg1 > 0 && cg0 + cg1 <= 8) {
+  if (cg1 > 0 && cg0 + cg1 <= maxcg) {
     add(0, 0, cg0, 0, cg1);
   } else {
     if (cg0 / p->kcg0 + (cg1 ? cg1 / p->kcg1 : 0) > kMaxChunks) return false;

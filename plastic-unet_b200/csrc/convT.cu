@@ -364,6 +364,76 @@ __global__ void convT3x3_dw_kernel(const float* __restrict__ x, const float* __r
   atomicAdd(dw + ((size_t)ci * Cout + co) * 9 + tap, acc);
 }
 
+// Tiled version for channel counts that are multiples of 4: per tap a [Cin x P] . [P x Cout] contraction over the input
+// pixels.  Block = 64 ci x 64 co outputs of ONE tap over a slice of the pixels; 256 threads x (4 ci x 4 co) register
+// tiles; x rows and the tap's (gathered, scaled, zero-filled) dy rows are staged 16 pixels at a time.
+__global__ void __launch_bounds__(256) convT3x3_dw_tiled_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                                const float* __restrict__ scale, float* __restrict__ dw, int B, int H,
+                                                                int W, int Cin, int Cout, int Ho, int Wo, int oy, int ox, int nsplit) {
+  constexpr int PC = 16;
+  __shared__ __align__(16) float xs[PC][64];
+  __shared__ __align__(16) float ds[PC][64];
+  const int tid = threadIdx.x;
+  const int ci_blk = blockIdx.x * 64, co_blk = blockIdx.y * 64;
+  const int tap = blockIdx.z % 9, split = blockIdx.z / 9;
+  const int ky = tap / 3, kx = tap - 3 * ky;
+  const int tci = (tid & 15) * 4, tco = (tid >> 4) * 4;  // this thread's 4x4 outputs inside the 64x64 tile
+  const long long npix = (long long)B * H * W;
+  const long long per = (npix + nsplit - 1) / nsplit;
+  const long long p0 = (long long)split * per;
+  const long long p1 = p0 + per < npix ? p0 + per : npix;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (long long pc = p0; pc < p1; pc += PC) {
+    __syncthreads();
+    {  // stage: 16 pixels x 16 float4 for x and for dy = 512 float4, two per thread
+      const int pp = tid >> 4, c4 = (tid & 15) * 4;
+      const long long p = pc + pp;
+      float4 xv = make_float4(0.f, 0.f, 0.f, 0.f), dv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p < p1) {
+        const int jx = (int)(p % W);
+        const int iy = (int)((p / W) % H);
+        const int b = (int)(p / ((long long)W * H));
+        if (ci_blk + c4 < Cin) xv = ldg4(x + p * Cin + ci_blk + c4);
+        const int wy = 2 * iy + ky - oy, wx = 2 * jx + kx - ox;
+        if (wy >= 0 && wy < Ho && wx >= 0 && wx < Wo && co_blk + c4 < Cout) {
+          dv = ldg4(dy + (((size_t)b * Ho + wy) * Wo + wx) * Cout + co_blk + c4);
+          if (scale != nullptr) {
+            const float4 sv = ldg4(scale + (size_t)b * Cout + co_blk + c4);
+            dv.x *= sv.x; dv.y *= sv.y; dv.z *= sv.z; dv.w *= sv.w;
+          }
+        }
+      }
+      *reinterpret_cast<float4*>(&xs[pp][c4]) = xv;
+      *reinterpret_cast<float4*>(&ds[pp][c4]) = dv;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int pp = 0; pp < PC; ++pp) {
+      const float4 a = *reinterpret_cast<const float4*>(&xs[pp][tci]);
+      const float4 d = *reinterpret_cast<const float4*>(&ds[pp][tco]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, dv[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], dv[j], acc[i][j]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int ci = ci_blk + tci + i;
+    if (ci >= Cin) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int co = co_blk + tco + j;
+      if (co < Cout) atomicAdd(dw + ((size_t)ci * Cout + co) * 9 + tap, acc[i][j]);
+    }
+  }
+}
+
 // db[co] = sum_{b,pixels} dy[b,p,co] * s[b,co]
 __global__ void bias_grad_scaled_kernel(const float* __restrict__ dy, const float* __restrict__ scale, float* __restrict__ db,
                                         int B, long long hw, int C) {
@@ -511,9 +581,20 @@ int pu_convT3x3s2_bwd(const float* x, const float* w, const float* dy, const flo
       pu::set_error("pu_convT3x3s2_bwd memset: %s", cudaGetErrorString(e));
       return PU_ERR_CUDA;
     }
-    const long long nb = (nout + 255) / 256;
-    dim3 grid((unsigned)nb, pu::split_for(nb, npix));
-    pu::convT3x3_dw_kernel<<<grid, 256, 0, st>>>(x, dy, chan_scale, dw, B, H, W, Cin, Cout, Ho, Wo, oy, ox);
+    if (Cin % 4 == 0 && Cout % 4 == 0 && pu::aligned16(x) && pu::aligned16(dy)) {
+      const int gx = pu::cdiv(Cin, 64), gy = pu::cdiv(Cout, 64);
+      long long nsplit = (4LL * pu::kNumSMs + 9LL * gx * gy - 1) / (9LL * gx * gy);
+      const long long maxsplit = (npix + 63) / 64;
+      if (nsplit > maxsplit) nsplit = maxsplit;
+      if (nsplit < 1) nsplit = 1;
+      if (9 * nsplit > 65535) nsplit = 65535 / 9;
+      dim3 grid(gx, gy, (unsigned)(9 * nsplit));
+      pu::convT3x3_dw_tiled_kernel<<<grid, 256, 0, st>>>(x, dy, chan_scale, dw, B, H, W, Cin, Cout, Ho, Wo, oy, ox, (int)nsplit);
+    } else {
+      const long long nb = (nout + 255) / 256;
+      dim3 grid((unsigned)nb, pu::split_for(nb, npix));
+      pu::convT3x3_dw_kernel<<<grid, 256, 0, st>>>(x, dy, chan_scale, dw, B, H, W, Cin, Cout, Ho, Wo, oy, ox);
+    }
     int rc = pu::post_launch("pu_convT3x3s2_bwd dw");
     if (rc) return rc;
   }

@@ -79,7 +79,7 @@ int pu_bce_fwd_bwd(const float* S, const float* T, float* loss, float* gS, long 
 
 int pu_gather_flat(const long long* table, int n, float* flat, void* stream) {
   PU_REQUIRE(table && flat && n > 0 && n <= 65535, PU_ERR_BAD_ARG, "pu_gather_flat: bad argument");
-  dim3 grid(8, n);
+  dim3 grid(32, n);
   pu::gather_flat_kernel<<<grid, 256, 0, pu::as_stream(stream)>>>(table, n, flat);
   return pu::post_launch("pu_gather_flat");
 }
