@@ -24,7 +24,7 @@ struct WgradArgs {
 };
 
 int conv3x3_fwd_ffma(const Conv3x3Args& a, cudaStream_t st);
-int conv3x3_wgrad_ffma(const WgradArgs& a, cudaStream_t st);
+int conv3x3_wgrad_ffma(const WgradArgs& a, cudaStream_t st, int math);
 // tcgen05 path (conv3x3_tc.cu); returns PU_ERR_UNSUPPORTED when the shape does not fit it
 int conv3x3_fwd_tc(const Conv3x3Args& a, cudaStream_t st);
 bool conv3x3_tc_ok(int C0, int C1, int Cout, int Cd0, int Cd1);

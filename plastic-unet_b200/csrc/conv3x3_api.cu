@@ -81,11 +81,11 @@ int pu_conv3x3_wgrad(const float* src0, int H0, int W0, int C0, int oy0, int ox0
   a.dw = dw_oihw;
   a.B = B; a.H = H; a.W = W; a.Cin = C0 + C1; a.Cout = Cout;
   a.tilesX = a.tilesY = a.ntiles = 0;
-  // wgrad accumulates in fp32 on the CUDA cores in both math modes.  A tcgen05 wgrad (K = pixels) needs MN-major
-  // tf32 operands; measured on B200: kind::tf32 with a_major/b_major = MN and SWIZZLE_NONE descriptors returns zeros
-  // (CUTLASS only offers SWIZZLE_128B_BASE32B atoms for 32-bit MN-major operands) -> next round, see DESIGN.md.
-  (void)math;
-  return pu::conv3x3_wgrad_ffma(a, pu::as_stream(stream));
+  // PU_MATH_FP32: FFMA2 on the CUDA cores.  PU_MATH_TF32: warp-level TF32 MMAs (mma.sync m16n8k8) for channel counts
+  // that are multiples of 8.  A tcgen05 wgrad (K = pixels) needs MN-major tf32 operands; measured on B200: kind::tf32
+  // with a_major/b_major = MN and SWIZZLE_NONE descriptors returns zeros (CUTLASS only offers SWIZZLE_128B_BASE32B
+  // atoms for 32-bit MN-major operands) -> next round, see DESIGN.md.
+  return pu::conv3x3_wgrad_ffma(a, pu::as_stream(stream), math);
 }
 
 int pu_conv3x3_tc_ok(int C0, int C1, int Cout, int Cd0, int Cd1) { return pu::conv3x3_tc_ok(C0, C1, Cout, Cd0, Cd1) ? 1 : 0; }

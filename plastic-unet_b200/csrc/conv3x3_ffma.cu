@@ -513,6 +513,132 @@ __global__ void __launch_bounds__(256, 2) conv3x3_wgrad_pipe_kernel(const WgradA
 }
 
 // ------------------------------------------------------------------------------------------------
+// wgrad in TF32 mode: the contraction dimension is the PIXEL index, the outputs are tiny (8 ci x 8 co x 9 taps per
+// CTA), which does not fit tcgen05 (M >= 64; K-major operands would need pixel-contiguous = transposed tiles, and
+// MN-major tf32 with SWIZZLE_NONE returns zeros on B200).  The warp-level mma.sync m16n8k8 TF32 path fits exactly:
+// A tile = (2 taps x 8 ci) x 8 pixels, B tile = 8 pixels x 8 co, both read conflict-free from the same pixel-major
+// [pixel][8] shared tiles the cp.async ring of conv3x3_wgrad_pipe_kernel provides (bank = 8*t + g).  Each warp owns
+// a share of the 8-pixel groups of a tile; 5 MMAs (tap pairs) per group; partial sums reduced across the 8 warps
+// at the end, one fp32 atomic per output and CTA.  Operands are already TF32-rounded by their producers.
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], unsigned a0, unsigned a1, unsigned a2, unsigned a3, unsigned b0, unsigned b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+template <int TW, int TH>
+__global__ void __launch_bounds__(256, 2) conv3x3_wgrad_mma_kernel(const WgradArgs a) {
+  constexpr int HW_ = TW + 2, HH_ = TH + 2;
+  constexpr int XPIX = HH_ * HW_, GPIX = TH * TW;
+  constexpr int STAGE_F = (XPIX + GPIX) * 8;
+  constexpr int GROUPS = TH * (TW / 8);  // 8-pixel groups (along x) per tile
+  extern __shared__ __align__(16) float dsm[];  // [2][STAGE_F]; the reduction buffer aliases it at the end
+  static_assert(2 * STAGE_F >= 8 * 32 * 20, "reduction buffer must fit in the staging ring");
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int gq = lane >> 2, tq = lane & 3;  // mma fragment coordinates: groupID, threadID_in_group
+  int cchunk = blockIdx.y;
+  const int nchunk0 = a.s0.C / 8;
+  const View v = cchunk < nchunk0 ? a.s0 : a.s1;
+  const int cbase = cchunk < nchunk0 ? 0 : a.s0.C;
+  if (cchunk >= nchunk0) cchunk -= nchunk0;
+  const int c0 = cchunk * 8;
+  const int co0 = blockIdx.z * 8;
+
+  auto issue = [&](int tile, int stage) {
+    int t = tile;
+    const int tx = t % a.tilesX;
+    t /= a.tilesX;
+    const int ty = t % a.tilesY;
+    const int b = t / a.tilesY;
+    const int x0 = tx * TW, y0 = ty * TH;
+    float* xs = dsm + stage * STAGE_F;
+    float* gs = xs + XPIX * 8;
+    for (int i = tid; i < XPIX * 2; i += 256) {
+      const int pix = i >> 1, half = i & 1;
+      const int hy = pix / HW_, hx = pix - hy * HW_;
+      const int gy = y0 + hy - 1, gx = x0 + hx - 1;
+      const bool ok = gy >= 0 && gy < a.H && gx >= 0 && gx < a.W;
+      const float* src = ok ? v.p + (((size_t)b * v.Hs + (gy + v.oy)) * v.Ws + (gx + v.ox)) * v.C + c0 + half * 4 : v.p;
+      const unsigned dst = (unsigned)__cvta_generic_to_shared(xs + pix * 8 + half * 4);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16 : 0) : "memory");
+    }
+    for (int i = tid; i < GPIX * 2; i += 256) {
+      const int pix = i >> 1, half = i & 1;
+      const int yy = pix / TW, xx = pix - yy * TW;
+      const int gy = y0 + yy, gx = x0 + xx;
+      const bool ok = gy < a.H && gx < a.W;
+      const float* src = ok ? a.g + (((size_t)b * a.H + gy) * a.W + gx) * a.Cout + co0 + half * 4 : a.g;
+      const unsigned dst = (unsigned)__cvta_generic_to_shared(gs + pix * 8 + half * 4);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16 : 0) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  // accumulators of the 5 tap-pair tiles: acc[p] = {(tap 2p, ci=gq, co=2tq), (tap 2p, gq, 2tq+1), (tap 2p+1, ...), ...}
+  float acc[5][4];
+#pragma unroll
+  for (int p = 0; p < 5; ++p)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[p][j] = 0.f;
+
+  int stage = 0;
+  if ((int)blockIdx.x < a.ntiles) issue(blockIdx.x, 0);
+  for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, stage ^= 1) {
+    const int next = tile + gridDim.x;
+    if (next < a.ntiles) {
+      issue(next, stage ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const unsigned* xs = reinterpret_cast<const unsigned*>(dsm + stage * STAGE_F);
+    const unsigned* gs = xs + XPIX * 8;
+    for (int grp = warp; grp < GROUPS; grp += 8) {
+      const int yy = grp / (TW / 8), xg = (grp - yy * (TW / 8)) * 8;
+      // B fragment: k = pixel (tq, tq+4), n = co (gq)
+      const unsigned b0 = gs[(yy * TW + xg + tq) * 8 + gq];
+      const unsigned b1 = gs[(yy * TW + xg + tq + 4) * 8 + gq];
+      // A fragments: row = (tap within pair, ci = gq), col = pixel (tq, tq+4); the halo tile is offset by (+1,+1)
+      const unsigned* xr = xs + ((yy * HW_) + xg + tq) * 8 + gq;
+      unsigned av[9][2];
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          av[ky * 3 + kx][0] = xr[(ky * HW_ + kx) * 8];
+          av[ky * 3 + kx][1] = xr[(ky * HW_ + kx + 4) * 8];
+        }
+#pragma unroll
+      for (int p = 0; p < 4; ++p) mma_tf32_16x8x8(acc[p], av[2 * p][0], av[2 * p + 1][0], av[2 * p][1], av[2 * p + 1][1], b0, b1);
+      mma_tf32_16x8x8(acc[4], av[8][0], 0u, av[8][1], 0u, b0, b1);
+    }
+    __syncthreads();
+  }
+
+  // ---- reduce the 8 warps, then one atomic per output
+  float* red = dsm;  // [8 warps][32 lanes][20]
+  __syncthreads();
+#pragma unroll
+  for (int p = 0; p < 5; ++p)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) red[(warp * 32 + lane) * 20 + p * 4 + j] = acc[p][j];
+  __syncthreads();
+  for (int i = tid; i < 32 * 20; i += 256) {
+    float sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) sum += red[w * 640 + i];
+    const int ln = i / 20, r = i - ln * 20;
+    const int p = r >> 2, j = r & 3;
+    const int tap = 2 * p + (j >> 1);
+    if (tap > 8) continue;
+    const int ci_ = ln >> 2, co = co0 + 2 * (ln & 3) + (j & 1);
+    atomicAdd(a.dw + ((size_t)co * a.Cin + cbase + c0 + ci_) * 9 + tap, sum);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 __global__ void pack_w3x3_kernel(const float* __restrict__ w, float* __restrict__ out, int Cout, int Cin, int transpose) {
   const int n = Cout * Cin * 9;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -611,7 +737,7 @@ int conv3x3_fwd_ffma(const Conv3x3Args& a0, cudaStream_t st) {
   return post_launch("conv3x3_fwd_ffma");
 }
 
-int conv3x3_wgrad_ffma(const WgradArgs& a0, cudaStream_t st) {
+int conv3x3_wgrad_ffma(const WgradArgs& a0, cudaStream_t st, int math) {
   WgradArgs a = a0;
   cudaError_t e = cudaMemsetAsync(a.dw, 0, sizeof(float) * (size_t)a.Cout * a.Cin * 9, st);
   if (e != cudaSuccess) {
@@ -622,6 +748,29 @@ int conv3x3_wgrad_ffma(const WgradArgs& a0, cudaStream_t st) {
   const int nco = cdiv(a.Cout, 8);
   const bool have1 = a.s1.p != nullptr && a.s1.C > 0;
   if (a.s0.C % 8 == 0 && (!have1 || a.s1.C % 8 == 0) && a.Cout % 8 == 0) {
+    if (math == PU_MATH_TF32) {
+      // warp-level TF32 MMAs over the same cp.async ring
+      const size_t smem32 = 2 * ((16 + 2) * (32 + 2) + 16 * 32) * 8 * sizeof(float);
+      const size_t smem16 = 2 * ((16 + 2) * (16 + 2) + 16 * 16) * 8 * sizeof(float);
+      static bool attr = false;
+      if (!attr) {
+        cudaFuncSetAttribute(conv3x3_wgrad_mma_kernel<32, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32);
+        cudaFuncSetAttribute(conv3x3_wgrad_mma_kernel<16, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16);
+        attr = true;
+      }
+      if (a.W > 16) {
+        a.tilesX = cdiv(a.W, 32); a.tilesY = cdiv(a.H, 16);
+        a.ntiles = a.tilesX * a.tilesY * a.B;
+        const int gx = max(1, min(a.ntiles, (2 * kNumSMs) / max(1, nci * nco)));
+        conv3x3_wgrad_mma_kernel<32, 16><<<dim3(gx, nci, nco), 256, smem32, st>>>(a);
+      } else {
+        a.tilesX = cdiv(a.W, 16); a.tilesY = cdiv(a.H, 16);
+        a.ntiles = a.tilesX * a.tilesY * a.B;
+        const int gx = max(1, min(a.ntiles, (4 * kNumSMs) / max(1, nci * nco)));
+        conv3x3_wgrad_mma_kernel<16, 16><<<dim3(gx, nci, nco), 256, smem16, st>>>(a);
+      }
+      return post_launch("conv3x3_wgrad_mma");
+    }
     // pipelined cp.async kernel (2 CTAs / SM, 72 accumulators per thread)
     if (a.W > 16) {
       constexpr int TW = 32, TH = 16;
