@@ -142,12 +142,16 @@ __global__ void convT2x2_dx_kernel(const float* __restrict__ dy, const float* __
 // thread does 1 LDS + 1 LDS.128 per 4 FMA.  Pixel range split over blockIdx.y, fp32 atomics at the end.
 __global__ void __launch_bounds__(256) convT2x2_dw_tiled_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                                 float* __restrict__ dw, int B, int H, int W, int Cin, int Cout,
-                                                                int pch) {
+                                                                int pch, int nrep) {
   extern __shared__ __align__(16) float sm[];
   float* xs = sm;                 // [pch][Cin]
   float* ds = sm + pch * Cin;     // [pch][4][Cout]
   const int co4n = Cout >> 2;
-  const long long e = (long long)blockIdx.x * 256 + threadIdx.x;  // ((ci*4 + ac)*co4n + co4)
+  // a block owns `slices` = min(256, Cin*Cout) four-output slices; when there are fewer than 256 of them the block's
+  // threads are replicated nrep times over the pixels of a chunk (rep = pixel residue class)
+  const int slices = 256 / nrep;
+  const int sl = threadIdx.x % slices, rep = threadIdx.x / slices;
+  const long long e = (long long)blockIdx.x * slices + sl;  // ((ci*4 + ac)*co4n + co4)
   const int co4 = (int)(e % co4n);
   const int ac = (int)((e / co4n) & 3);
   const int ci = (int)(e / (4 * co4n));
@@ -179,7 +183,7 @@ __global__ void __launch_bounds__(256) convT2x2_dw_tiled_kernel(const float* __r
     __syncthreads();
     if (valid) {
 #pragma unroll 4
-      for (int pp = 0; pp < np; ++pp) {
+      for (int pp = rep; pp < np; pp += nrep) {
         const float xv = xs[pp * Cin + ci];
         const float4 g = *reinterpret_cast<const float4*>(ds + ((size_t)pp * 4 + ac) * Cout + 4 * co4);
         acc.x = fmaf(xv, g.x, acc.x);
@@ -528,14 +532,17 @@ int pu_convT2x2s2_bwd(const float* x, const float* w, const float* dy, float* dx
       pch = pch > 64 ? 64 : (pch < 4 ? 4 : pch);
       const size_t smem = (size_t)pch * (Cin + 4 * Cout) * sizeof(float);
       PU_REQUIRE(smem <= 48 * 1024, PU_ERR_UNSUPPORTED, "pu_convT2x2s2_bwd: Cin+4*Cout=%d too large", Cin + 4 * Cout);
-      const int nb = pu::cdiv((long long)Cin * Cout, 256);  // 4 outputs per thread
+      int nrep = 1;
+      while (nrep < 8 && (long long)Cin * Cout * nrep * 2 <= 256) nrep *= 2;  // replicate small output sets over the pixels
+      const int slices = 256 / nrep;
+      const int nb = pu::cdiv((long long)Cin * Cout, slices);  // 4 outputs per thread
       long long splits = (4LL * pu::kNumSMs + nb - 1) / nb;
       const long long maxsplit = (npix + pch - 1) / pch;
       if (splits > maxsplit) splits = maxsplit;
       if (splits < 1) splits = 1;
       if (splits > 65535) splits = 65535;
       dim3 grid(nb, (unsigned)splits);
-      pu::convT2x2_dw_tiled_kernel<<<grid, 256, smem, st>>>(x, dy, dw, B, H, W, Cin, Cout, pch);
+      pu::convT2x2_dw_tiled_kernel<<<grid, 256, smem, st>>>(x, dy, dw, B, H, W, Cin, Cout, pch, nrep);
     } else {
       const int nb = pu::cdiv(nout, 256);
       dim3 grid(nb, pu::split_for(nb, npix));
