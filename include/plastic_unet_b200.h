@@ -39,6 +39,8 @@ typedef enum {
 /* op flags */
 #define PU_FLAG_RELU 1       /* fused ReLU in the epilogue                                            */
 #define PU_FLAG_ROUND_TF32 2 /* round the op's output to TF32 (RN): producers of tensor-core operands  */
+#define PU_FLAG_MASK_IN 4    /* backward kernels: zero the input gradient where the op's input x <= 0, i.e. apply the
+                                ReLU mask of the PRODUCER of x (premasked-gradient protocol)          */
 
 /* conv3x3 weight operand formats */
 #define PU_W_PACKED 0
@@ -86,19 +88,22 @@ int pu_conv3x3_tc_resident(int C0, int C1, int Cout, int H, int W);
  * raw [C0, Cout, 3, 3] weight of the forward conv whose dgrad this call computes).  With PU_MATH_TF32 the raw
  * formats need pu_conv3x3_tc_resident(C0, C1, Cout, H, W).
  * src1, bias, res, dst1 may be NULL.  wp is the packed weight [9][C0+C1][Cout].
- * dst views may be larger than HxW (their border is NOT written — caller zero-fills).    */
+ * dst views may be larger than HxW (their border is NOT written — caller zero-fills).
+ * mask0 / mask1 (may be NULL): tensors with the geometry of dst0 / dst1; where mask <= 0 the stored value is 0
+ * (used by dgrad calls: the ReLU mask of the layer that produced the source, applied in the epilogue).   */
 int pu_conv3x3_fwd(const float* src0, int H0, int W0, int C0, int oy0, int ox0,
                    const float* src1, int H1, int W1, int C1, int oy1, int ox1,
                    const float* wp, const float* bias, const float* res, int flags,
                    float* dst0, int Hd0, int Wd0, int Cd0, int oyd0, int oxd0,
                    float* dst1, int Hd1, int Wd1, int Cd1, int oyd1, int oxd1,
+                   const float* mask0, const float* mask1,
                    int B, int H, int W, int Cout, int math, int wfmt, void* stream);
 
 /* dw_oihw[Cout, C0+C1, 3, 3] = sum_{b,y,x} g[b,y,x,co] * cat[src0,src1][b,y+ky-1,x+kx-1,ci]
- * (overwrites dw).  g is [B,H,W,Cout] dense.                                               */
+ * (overwrites dw).  g is [B,H,W,Cout] dense.  db (may be NULL) receives the bias gradient sum_pixels g.       */
 int pu_conv3x3_wgrad(const float* src0, int H0, int W0, int C0, int oy0, int ox0,
                      const float* src1, int H1, int W1, int C1, int oy1, int ox1,
-                     const float* g, float* dw_oihw, int B, int H, int W, int Cout,
+                     const float* g, float* dw_oihw, float* db, int B, int H, int W, int Cout,
                      int math, void* stream);
 
 /* g = (flags & RELU) ? dy * (y > 0) : dy [rounded to TF32 if flags & ROUND]; dbias[c] = sum_pixels g  (g may alias
@@ -115,14 +120,14 @@ int pu_conv1x1_fwd(const float* x, const float* w, const float* bias, float* y,
 /* g is the (already ReLU-masked) output gradient.  dx and db may be NULL. dw [Cout,Cin+coords], db [Cout]
  * overwritten.  ws: caller-provided scratch of Cout*(Cin+coords+1) floats (<= 256).              */
 int pu_conv1x1_bwd(const float* x, const float* w, const float* g, float* dx, float* dw, float* db, float* ws,
-                   int B, int H, int W, int Cin, int Cout, int coords, void* stream);
+                   int B, int H, int W, int Cin, int Cout, int coords, int flags, void* stream);
 
 /* ---- transposed convolutions ---------------------------------------------------------------
  * 2x2 stride 2 (reference unet_p.py:155): w is PyTorch [Cin,Cout,2,2]; y is [B,2H,2W,Cout]. */
 int pu_convT2x2s2_fwd(const float* x, const float* w, const float* bias, float* y,
                       int B, int H, int W, int Cin, int Cout, int flags, void* stream);
 int pu_convT2x2s2_bwd(const float* x, const float* w, const float* dy, float* dx, float* dw, float* db,
-                      int B, int H, int W, int Cin, int Cout, void* stream);
+                      int B, int H, int W, int Cin, int Cout, int flags, void* stream);
 /* 3x3 stride 2 pad 0 (reference unet_p_res.py:207): full output is (2H+1)x(2W+1); the op writes
  * only the window [oy,oy+Ho) x [ox,ox+Wo) of it (the F.pad crop of unet_p_res.py:215-217 fused).
  * chan_scale (may be NULL) is a per-(b,co) multiplier [B,Cout] applied after bias (Dropout2d). */
@@ -138,7 +143,7 @@ int pu_convT3x3s2_bwd(const float* x, const float* w, const float* dy, const flo
 int pu_maxpool2_fwd(const float* x, const float* chan_scale, float* y, int B, int H, int W, int C, void* stream);
 /* dx gets dy*scale at the first maximum (row-major scan, ATen tie-break) and 0 elsewhere.    */
 int pu_maxpool2_bwd(const float* x, const float* chan_scale, const float* dy, float* dx,
-                    int B, int H, int W, int C, void* stream);
+                    int B, int H, int W, int C, int flags, void* stream);
 /* nn.Upsample(scale_factor=2, bilinear, align_corners=True) (reference unet_p.py:153)        */
 int pu_bilinear2x_fwd(const float* x, float* y, int B, int H, int W, int C, void* stream);
 int pu_bilinear2x_bwd(const float* dy, float* dx, int B, int H, int W, int C, void* stream);

@@ -10,6 +10,8 @@ struct Conv3x3Args {
   const float* bias;  // [Cout] | null
   const float* res;   // [B,H,W,Cout] | null, added before the ReLU
   ViewW d0, d1;       // channel-split destinations (d1.p may be null)
+  const float* mask0; // | null: same geometry as d0; store 0 where mask0 <= 0 (ReLU mask of the source's producer)
+  const float* mask1; // | null: same for d1
   int B, H, W, Cin, Cout, relu, round_out;
   int wfmt;  // 0: wp packed by pu_pack_w3x3; 1: wp is the raw OIHW weight (forward); 2: raw OIHW, conv is the dgrad
   int tilesX, tilesY;
@@ -19,6 +21,7 @@ struct WgradArgs {
   View s0, s1;
   const float* g;  // [B,H,W,Cout]
   float* dw;       // OIHW
+  float* db;       // [Cout] | null
   int B, H, W, Cin, Cout;
   int tilesX, tilesY, ntiles;
 };

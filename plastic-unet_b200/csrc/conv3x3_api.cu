@@ -21,6 +21,7 @@ int pu_conv3x3_fwd(const float* src0, int H0, int W0, int C0, int oy0, int ox0,
                    const float* wp, const float* bias, const float* res, int flags,
                    float* dst0, int Hd0, int Wd0, int Cd0, int oyd0, int oxd0,
                    float* dst1, int Hd1, int Wd1, int Cd1, int oyd1, int oxd1,
+                   const float* mask0, const float* mask1,
                    int B, int H, int W, int Cout, int math, int wfmt, void* stream) {
   PU_REQUIRE(B > 0 && H > 0 && W > 0 && Cout > 0 && wp != nullptr, PU_ERR_BAD_ARG, "pu_conv3x3_fwd: bad dims");
   PU_REQUIRE(wfmt >= 0 && wfmt <= 2, PU_ERR_BAD_ARG, "pu_conv3x3_fwd: unknown weight format %d", wfmt);
@@ -51,6 +52,8 @@ int pu_conv3x3_fwd(const float* src0, int H0, int W0, int C0, int oy0, int ox0,
   a.res = res;
   a.d0 = pu::ViewW{dst0, Hd0, Wd0, Cd0, oyd0, oxd0};
   a.d1 = pu::ViewW{dst1, Hd1, Wd1, Cd1, oyd1, oxd1};
+  a.mask0 = mask0;
+  a.mask1 = mask1;
   a.B = B; a.H = H; a.W = W; a.Cin = C0 + C1; a.Cout = Cout;
   a.relu = (flags & PU_FLAG_RELU) ? 1 : 0;
   a.round_out = (flags & PU_FLAG_ROUND_TF32) ? 1 : 0;
@@ -63,7 +66,7 @@ int pu_conv3x3_fwd(const float* src0, int H0, int W0, int C0, int oy0, int ox0,
 
 int pu_conv3x3_wgrad(const float* src0, int H0, int W0, int C0, int oy0, int ox0,
                      const float* src1, int H1, int W1, int C1, int oy1, int ox1,
-                     const float* g, float* dw_oihw, int B, int H, int W, int Cout, int math, void* stream) {
+                     const float* g, float* dw_oihw, float* db, int B, int H, int W, int Cout, int math, void* stream) {
   PU_REQUIRE(B > 0 && H > 0 && W > 0 && Cout > 0 && g != nullptr && dw_oihw != nullptr, PU_ERR_BAD_ARG, "pu_conv3x3_wgrad: bad dims");
   PU_REQUIRE(pu::aligned16(g), PU_ERR_BAD_ARG, "pu_conv3x3_wgrad: g not 16-byte aligned");
   int rc = check_view("pu_conv3x3_wgrad src0", src0, H0, W0, C0, oy0, ox0, H, W);
@@ -79,6 +82,7 @@ int pu_conv3x3_wgrad(const float* src0, int H0, int W0, int C0, int oy0, int ox0
   a.s1 = pu::View{src1, H1, W1, C1, oy1, ox1};
   a.g = g;
   a.dw = dw_oihw;
+  a.db = db;
   a.B = B; a.H = H; a.W = W; a.Cin = C0 + C1; a.Cout = Cout;
   a.tilesX = a.tilesY = a.ntiles = 0;
   // PU_MATH_FP32: FFMA2 on the CUDA cores.  PU_MATH_TF32: warp-level TF32 MMAs (mma.sync m16n8k8) for channel counts

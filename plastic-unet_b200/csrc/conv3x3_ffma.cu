@@ -167,8 +167,17 @@ __global__ void __launch_bounds__(NT) conv3x3_ffma_kernel(const Conv3x3Args a) {
       const bool first = co < a.d0.C;
       const ViewW d = first ? a.d0 : a.d1;
       const int cd = first ? co : co - a.d0.C;
-      float* dp = d.p + (((size_t)b * d.Hs + (gy + d.oy)) * d.Ws + (gx + d.ox)) * d.C + cd;
+      const size_t doff = (((size_t)b * d.Hs + (gy + d.oy)) * d.Ws + (gx + d.ox)) * d.C + cd;
+      float* dp = d.p + doff;
       if ((d.C % 4 == 0) && (a.d0.C % 4 == 0) && (co + 3 < a.Cout)) {
+        const float* mk = first ? a.mask0 : a.mask1;
+        if (mk != nullptr) {
+          const float4 m = ldg4(mk + doff);
+          o[4 * h] = m.x > 0.f ? o[4 * h] : 0.f;
+          o[4 * h + 1] = m.y > 0.f ? o[4 * h + 1] : 0.f;
+          o[4 * h + 2] = m.z > 0.f ? o[4 * h + 2] : 0.f;
+          o[4 * h + 3] = m.w > 0.f ? o[4 * h + 3] : 0.f;
+        }
         *reinterpret_cast<float4*>(dp) = make_float4(o[4 * h], o[4 * h + 1], o[4 * h + 2], o[4 * h + 3]);
       } else {
 #pragma unroll
@@ -178,7 +187,11 @@ __global__ void __launch_bounds__(NT) conv3x3_ffma_kernel(const Conv3x3Args a) {
           const bool f2 = c < a.d0.C;
           const ViewW d2 = f2 ? a.d0 : a.d1;
           const int c2 = f2 ? c : c - a.d0.C;
-          d2.p[(((size_t)b * d2.Hs + (gy + d2.oy)) * d2.Ws + (gx + d2.ox)) * d2.C + c2] = o[4 * h + j];
+          const size_t off2 = (((size_t)b * d2.Hs + (gy + d2.oy)) * d2.Ws + (gx + d2.ox)) * d2.C + c2;
+          const float* mk2 = f2 ? a.mask0 : a.mask1;
+          float ov = o[4 * h + j];
+          if (mk2 != nullptr && !(__ldg(mk2 + off2) > 0.f)) ov = 0.f;
+          d2.p[off2] = ov;
         }
       }
     }
@@ -612,7 +625,8 @@ __global__ void __launch_bounds__(256, 2) conv3x3_wgrad_mma_kernel(const WgradAr
         }
 #pragma unroll
       for (int p = 0; p < 4; ++p) mma_tf32_16x8x8(acc[p], av[2 * p][0], av[2 * p + 1][0], av[2 * p][1], av[2 * p + 1][1], b0, b1);
-      mma_tf32_16x8x8(acc[4], av[8][0], 0u, av[8][1], 0u, b0, b1);
+      // rows 8..15 of the fifth tile are free: feeding ones there makes them the column sums of G = the bias gradient
+      mma_tf32_16x8x8(acc[4], av[8][0], 0x3f800000u, av[8][1], 0x3f800000u, b0, b1);
     }
     __syncthreads();
   }
@@ -632,8 +646,11 @@ __global__ void __launch_bounds__(256, 2) conv3x3_wgrad_mma_kernel(const WgradAr
     const int ln = i / 20, r = i - ln * 20;
     const int p = r >> 2, j = r & 3;
     const int tap = 2 * p + (j >> 1);
-    if (tap > 8) continue;
     const int ci_ = ln >> 2, co = co0 + 2 * (ln & 3) + (j & 1);
+    if (tap > 8) {  // the ones rows: every ci_ row holds the same sum_pixels g[.][co]
+      if (a.db != nullptr && ci_ == 0 && blockIdx.y == 0) atomicAdd(a.db + co, sum);
+      continue;
+    }
     atomicAdd(a.dw + ((size_t)co * a.Cin + cbase + c0 + ci_) * 9 + tap, sum);
   }
 }
@@ -747,6 +764,19 @@ int conv3x3_wgrad_ffma(const WgradArgs& a0, cudaStream_t st, int math) {
   const int nci = cdiv(a.s0.C, 8) + ((a.s1.p != nullptr && a.s1.C > 0) ? cdiv(a.s1.C, 8) : 0);
   const int nco = cdiv(a.Cout, 8);
   const bool have1 = a.s1.p != nullptr && a.s1.C > 0;
+  const bool mma_path = math == PU_MATH_TF32 && a.s0.C % 8 == 0 && (!have1 || a.s1.C % 8 == 0) && a.Cout % 8 == 0;
+  if (a.db != nullptr) {
+    if (mma_path) {  // accumulated by the ones rows of the MMA kernel
+      e = cudaMemsetAsync(a.db, 0, sizeof(float) * a.Cout, st);
+      if (e != cudaSuccess) {
+        set_error("conv3x3_wgrad db memset: %s", cudaGetErrorString(e));
+        return PU_ERR_CUDA;
+      }
+    } else {  // separate read-only reduction pass over g
+      int rc = pu_relu_bwd_bias(a.g, nullptr, nullptr, a.db, (long long)a.B * a.H * a.W, a.Cout, 0, st);
+      if (rc) return rc;
+    }
+  }
   if (a.s0.C % 8 == 0 && (!have1 || a.s1.C % 8 == 0) && a.Cout % 8 == 0) {
     if (math == PU_MATH_TF32) {
       // warp-level TF32 MMAs over the same cp.async ring

@@ -47,6 +47,8 @@ struct TcArgs {
   const float* bias;
   const float* res;
   ViewW d0, d1;
+  const float* mask0;  // | null: geometry of d0; the stored value is zeroed where mask0 <= 0
+  const float* mask1;
   int B, H, W, Cout, relu, round_out;
   int TH, TW, PW, tilesX, tilesY;
   int nmb, nmma, plane_bytes, a_bytes, w_bytes_max, tmem_cols, nchunks;
@@ -400,7 +402,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const __grid_
     // ================= epilogue: TMEM -> registers -> bias/residual/ReLU -> NHWC global =================
     // 8 warps: warp e handles TMEM lane quarter (warp % 4) of the 128-pixel blocks mb = set, set+2, ... (set = e / 4);
     // G blocks are fetched per tcgen05.wait::ld so that the TMEM read latency is paid once per group.
-    constexpr int G = COLS <= 16 ? 4 : (COLS == 32 ? 2 : 1);
+    constexpr int G = COLS <= 8 ? 4 : (COLS == 16 ? 2 : 1);  // G * COLS = 32 accumulator + 32 aux registers
     const int quarter = warp & 3;
     const int set = (warp - kEpiWarp0) >> 2;
     const int row = quarter * 32 + lane;
@@ -425,8 +427,26 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const __grid_
       tc_fence_after();
       int yy = yy0, xx = xx0;
       const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * acc_cols);
+      // `aux` = the one extra tensor the epilogue reads per element: the dgrad ReLU masks if present, else the residual.
+      // Its loads are issued BEFORE the TMEM wait of a group so that their latency overlaps the tcgen05.ld's.
+      const bool has_mask = a.mask0 != nullptr || a.mask1 != nullptr;
+      constexpr bool kPrefetch = COLS <= 32;
       for (int mb0 = set; mb0 < a.nmb; mb0 += 2 * G) {
         uint32_t v[G][COLS];
+        float aux[kPrefetch ? G : 1][kPrefetch ? COLS : 1];
+        int gyv[G], gxv[G];
+        bool okv[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          const int mb = mb0 + 2 * g;
+          gyv[g] = y0 + yy;
+          gxv[g] = x0 + xx;
+          okv[g] = mb < a.nmb && yy < a.TH && xx < a.TW && gyv[g] < a.H && gxv[g] < a.W && !(a.debug & 2);
+          // next block of this warp (two 128-pixel blocks further): advance (yy, xx) without a division
+          yy += step_y;
+          xx += step_x;
+          if (xx >= a.PW) { xx -= a.PW; ++yy; }
+        }
 #pragma unroll
         for (int g = 0; g < G; ++g) {
           const int mb = mb0 + 2 * g;
@@ -440,59 +460,105 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const __grid_
             }
           }
         }
+        if (kPrefetch && vec8 && (has_mask || a.res != nullptr)) {
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            if (!okv[g]) continue;
+#pragma unroll
+            for (int q = 0; q < COLS / 8; ++q) {
+              const int co = co_base + 8 * q;
+              if (co >= a.Cout) continue;
+              const float* src;
+              if (has_mask) {
+                const bool first = co < a.d0.C;
+                const ViewW dd = first ? a.d0 : a.d1;
+                const float* mk = first ? a.mask0 : a.mask1;
+                src = mk == nullptr ? nullptr
+                                    : mk + (((size_t)b * dd.Hs + (gyv[g] + dd.oy)) * dd.Ws + (gxv[g] + dd.ox)) * dd.C + (first ? co : co - a.d0.C);
+              } else {
+                src = a.res + (((size_t)b * a.H + gyv[g]) * a.W + gxv[g]) * a.Cout + co;
+              }
+              if (src != nullptr) {
+                ldg8(src, &aux[kPrefetch ? g : 0][kPrefetch ? 8 * q : 0]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) aux[kPrefetch ? g : 0][kPrefetch ? 8 * q + j : 0] = 1.f;  // "mask" that keeps everything
+              }
+            }
+          }
+        }
         tmem_ld_wait();
 #pragma unroll
         for (int g = 0; g < G; ++g) {
-          const int mb = mb0 + 2 * g;
-          if (mb < a.nmb) {
-            const int gy = y0 + yy, gx = x0 + xx;
-            if (yy < a.TH && xx < a.TW && gy < a.H && gx < a.W && !(a.debug & 2)) {
-              const float* rp = a.res != nullptr ? a.res + (((size_t)b * a.H + gy) * a.W + gx) * a.Cout + co_base : nullptr;
+          if (!okv[g]) continue;
+          const int gy = gyv[g], gx = gxv[g];
+          const float* rp = a.res != nullptr ? a.res + (((size_t)b * a.H + gy) * a.W + gx) * a.Cout + co_base : nullptr;
 #pragma unroll
-              for (int q = 0; q < COLS / 8; ++q) {  // 8 channels = one 32-byte sector per 256-bit access
-                const int co = co_base + 8 * q;
-                if (co < a.Cout) {
-                  float o[8];
+          for (int q = 0; q < COLS / 8; ++q) {  // 8 channels = one 32-byte sector per 256-bit access
+            const int co = co_base + 8 * q;
+            if (co >= a.Cout) continue;
+            float o[8];
 #pragma unroll
-                  for (int j = 0; j < 8; ++j) o[j] = __uint_as_float(v[g][8 * q + j]) + bv[8 * q + j];
-                  if (rp != nullptr) {
-                    float rr[8];
-                    ldg8(rp + 8 * q, rr);
+            for (int j = 0; j < 8; ++j) o[j] = __uint_as_float(v[g][8 * q + j]) + bv[8 * q + j];
+            if (rp != nullptr) {
+              if (kPrefetch && vec8 && !has_mask) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) o[j] += rr[j];
-                  }
-                  if (a.relu) {
+                for (int j = 0; j < 8; ++j) o[j] += aux[kPrefetch ? g : 0][kPrefetch ? 8 * q + j : 0];
+              } else {
+                float rr[8];
+                ldg8(rp + 8 * q, rr);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
-                  }
-                  if (a.round_out) {
+                for (int j = 0; j < 8; ++j) o[j] += rr[j];
+              }
+            }
+            if (a.relu) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) o[j] = round_tf32(o[j]);
-                  }
-                  // an 8-channel group may straddle the d0|d1 split only at a multiple of 4
-                  if (vec8) {
-                    const bool first = co < a.d0.C;
-                    const ViewW dd = first ? a.d0 : a.d1;
-                    const int cd = first ? co : co - a.d0.C;
-                    stg8(dd.p + (((size_t)b * dd.Hs + (gy + dd.oy)) * dd.Ws + (gx + dd.ox)) * dd.C + cd, o);
-                  } else {
+              for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
+            }
+            if (a.round_out) {
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                      const int c4 = co + 4 * h;
-                      const bool first = c4 < a.d0.C;
-                      const ViewW dd = first ? a.d0 : a.d1;
-                      const int cd = first ? c4 : c4 - a.d0.C;
-                      float* dp = dd.p + (((size_t)b * dd.Hs + (gy + dd.oy)) * dd.Ws + (gx + dd.ox)) * dd.C + cd;
-                      *reinterpret_cast<float4*>(dp) = make_float4(o[4 * h], o[4 * h + 1], o[4 * h + 2], o[4 * h + 3]);
-                    }
+              for (int j = 0; j < 8; ++j) o[j] = round_tf32(o[j]);
+            }
+            // an 8-channel group may straddle the d0|d1 split only at a multiple of 4
+            if (vec8) {
+              const bool first = co < a.d0.C;
+              const ViewW dd = first ? a.d0 : a.d1;
+              const int cd = first ? co : co - a.d0.C;
+              const size_t doff = (((size_t)b * dd.Hs + (gy + dd.oy)) * dd.Ws + (gx + dd.ox)) * dd.C + cd;
+              if (has_mask) {  // dgrad: ReLU mask of the layer that produced this source
+                if (kPrefetch) {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) o[j] = aux[kPrefetch ? g : 0][kPrefetch ? 8 * q + j : 0] > 0.f ? o[j] : 0.f;
+                } else {
+                  const float* mk = first ? a.mask0 : a.mask1;
+                  if (mk != nullptr) {
+                    float mv[8];
+                    ldg8(mk + doff, mv);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) o[j] = mv[j] > 0.f ? o[j] : 0.f;
                   }
                 }
               }
+              stg8(dd.p + doff, o);
+            } else {
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const int c4 = co + 4 * h;
+                const bool first = c4 < a.d0.C;
+                const ViewW dd = first ? a.d0 : a.d1;
+                const int cd = first ? c4 : c4 - a.d0.C;
+                const size_t doff = (((size_t)b * dd.Hs + (gy + dd.oy)) * dd.Ws + (gx + dd.ox)) * dd.C + cd;
+                const float* mk = first ? a.mask0 : a.mask1;
+                if (mk != nullptr) {
+                  const float4 m = ldg4(mk + doff);
+                  o[4 * h] = m.x > 0.f ? o[4 * h] : 0.f;
+                  o[4 * h + 1] = m.y > 0.f ? o[4 * h + 1] : 0.f;
+                  o[4 * h + 2] = m.z > 0.f ? o[4 * h + 2] : 0.f;
+                  o[4 * h + 3] = m.w > 0.f ? o[4 * h + 3] : 0.f;
+                }
+                *reinterpret_cast<float4*>(dd.p + doff) = make_float4(o[4 * h], o[4 * h + 1], o[4 * h + 2], o[4 * h + 3]);
+              }
             }
-            // next block of this warp (two 128-pixel blocks further): advance (yy, xx) without a division
-            yy += step_y;
-            xx += step_x;
-            if (xx >= a.PW) { xx -= a.PW; ++yy; }
           }
         }
       }
@@ -773,6 +839,7 @@ int conv3x3_fwd_tc(const Conv3x3Args& a, cudaStream_t st) {
   }
   TcArgs ta;
   ta.wpk = a.wp; ta.bias = a.bias; ta.res = a.res; ta.d0 = a.d0; ta.d1 = a.d1;
+  ta.mask0 = a.mask0; ta.mask1 = a.mask1;
   ta.B = a.B; ta.H = a.H; ta.W = a.W; ta.Cout = a.Cout; ta.relu = a.relu; ta.round_out = a.round_out;
   ta.TH = p.TH; ta.TW = p.TW; ta.PW = p.PW; ta.tilesX = p.tilesX; ta.tilesY = p.tilesY;
   ta.nmb = p.nmb; ta.nmma = p.nmma; ta.plane_bytes = p.plane_bytes; ta.a_bytes = p.a_bytes; ta.w_bytes_max = p.w_bytes_max;

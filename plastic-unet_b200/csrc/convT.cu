@@ -74,7 +74,7 @@ __global__ void convT2x2_fwd_kernel(const float* __restrict__ x, const float* __
 
 // dx[b,i,j,ci] = sum_{a,c,co} dy[b,2i+a,2j+c,co] w[ci][co][a][c];  thread = (input pixel, block of 8 ci)
 __global__ void convT2x2_dx_kernel(const float* __restrict__ dy, const float* __restrict__ w, float* __restrict__ dx,
-                                   int B, int H, int W, int Cin, int Cout) {
+                                   int B, int H, int W, int Cin, int Cout, const float* __restrict__ xmask) {
   extern __shared__ __align__(16) float ws[];  // [4][Cout][8 ci]
   const int ci0 = blockIdx.y * 8;
   for (int i = threadIdx.x; i < 4 * Cout * 8; i += blockDim.x) {
@@ -125,6 +125,11 @@ __global__ void convT2x2_dx_kernel(const float* __restrict__ dy, const float* __
     }
   }
   float* dp = dx + p * Cin + ci0;
+  if (xmask != nullptr) {  // ReLU mask of the layer that produced x
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (ci0 + j < Cin && !(__ldg(xmask + p * Cin + ci0 + j) > 0.f)) acc[j] = 0.f;
+  }
   if (Cin % 4 == 0 && ci0 + 8 <= Cin) {
     *reinterpret_cast<float4*>(dp) = make_float4(acc[0], acc[1], acc[2], acc[3]);
     *reinterpret_cast<float4*>(dp + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
@@ -508,7 +513,7 @@ int pu_convT2x2s2_fwd(const float* x, const float* w, const float* bias, float* 
 }
 
 int pu_convT2x2s2_bwd(const float* x, const float* w, const float* dy, float* dx, float* dw, float* db, int B, int H, int W,
-                      int Cin, int Cout, void* stream) {
+                      int Cin, int Cout, int flags, void* stream) {
   PU_REQUIRE(x && w && dy && B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, PU_ERR_BAD_ARG, "pu_convT2x2s2_bwd: bad argument");
   cudaStream_t st = pu::as_stream(stream);
   const long long npix = (long long)B * H * W;
@@ -516,7 +521,7 @@ int pu_convT2x2s2_bwd(const float* x, const float* w, const float* dy, float* dx
     const size_t smem = (size_t)4 * Cout * 8 * sizeof(float);
     PU_REQUIRE(smem <= 48 * 1024, PU_ERR_UNSUPPORTED, "pu_convT2x2s2_bwd: Cout=%d > 384", Cout);
     dim3 grid((unsigned)((npix + 255) / 256), pu::cdiv(Cin, 8));
-    pu::convT2x2_dx_kernel<<<grid, 256, smem, st>>>(dy, w, dx, B, H, W, Cin, Cout);
+    pu::convT2x2_dx_kernel<<<grid, 256, smem, st>>>(dy, w, dx, B, H, W, Cin, Cout, (flags & PU_FLAG_MASK_IN) ? x : nullptr);
     int rc = pu::post_launch("pu_convT2x2s2_bwd dx");
     if (rc) return rc;
   }

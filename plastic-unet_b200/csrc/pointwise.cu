@@ -146,7 +146,7 @@ __global__ void conv1x1_dw_kernel(const float* __restrict__ x, const float* __re
 template <int CIN>
 __global__ void __launch_bounds__(256) conv1x1_bwd_c1_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                              const float* __restrict__ g, float* __restrict__ dx,
-                                                             float* __restrict__ dwb, long long npix) {
+                                                             float* __restrict__ dwb, long long npix, int mask_in) {
   __shared__ float red[8][CIN + 1];
   float wv[CIN];
 #pragma unroll
@@ -164,8 +164,13 @@ __global__ void __launch_bounds__(256) conv1x1_bwd_c1_kernel(const float* __rest
       acc[k + 1] = fmaf(gv, xv.y, acc[k + 1]);
       acc[k + 2] = fmaf(gv, xv.z, acc[k + 2]);
       acc[k + 3] = fmaf(gv, xv.w, acc[k + 3]);
-      if (dx != nullptr)
-        *reinterpret_cast<float4*>(dx + p * CIN + k) = make_float4(gv * wv[k], gv * wv[k + 1], gv * wv[k + 2], gv * wv[k + 3]);
+      if (dx != nullptr) {
+        float4 o = make_float4(gv * wv[k], gv * wv[k + 1], gv * wv[k + 2], gv * wv[k + 3]);
+        if (mask_in) {  // ReLU mask of the layer that produced x
+          o.x = xv.x > 0.f ? o.x : 0.f; o.y = xv.y > 0.f ? o.y : 0.f; o.z = xv.z > 0.f ? o.z : 0.f; o.w = xv.w > 0.f ? o.w : 0.f;
+        }
+        *reinterpret_cast<float4*>(dx + p * CIN + k) = o;
+      }
     }
   }
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -298,7 +303,7 @@ int pu_conv1x1_fwd(const float* x, const float* w, const float* bias, float* y, 
 }
 
 int pu_conv1x1_bwd(const float* x, const float* w, const float* g, float* dx, float* dw, float* db, float* ws, int B, int H, int W,
-                   int Cin, int Cout, int coords, void* stream) {
+                   int Cin, int Cout, int coords, int flags, void* stream) {
   PU_REQUIRE(x && w && g && dw && ws && B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, PU_ERR_BAD_ARG, "pu_conv1x1_bwd: bad argument");
   PU_REQUIRE(coords == 0 || coords == 2 || coords == 3, PU_ERR_BAD_ARG, "pu_conv1x1_bwd: coords must be 0, 2 or 3");
   cudaStream_t st = pu::as_stream(stream);
@@ -312,16 +317,19 @@ int pu_conv1x1_bwd(const float* x, const float* w, const float* g, float* dx, fl
     pu::set_error("pu_conv1x1_bwd memset: %s", cudaGetErrorString(e));
     return PU_ERR_CUDA;
   }
-  if (Cout == 1 && coords == 0 && (Cin == 8 || Cin == 16 || Cin == 32 || Cin == 64) && pu::aligned16(x) && (dx == nullptr || pu::aligned16(dx))) {
+  const int mask_in = (flags & PU_FLAG_MASK_IN) ? 1 : 0;
+  const bool fused_ok = Cout == 1 && coords == 0 && (Cin == 8 || Cin == 16 || Cin == 32 || Cin == 64) && pu::aligned16(x) && (dx == nullptr || pu::aligned16(dx));
+  PU_REQUIRE(!mask_in || fused_ok, PU_ERR_UNSUPPORTED, "pu_conv1x1_bwd: PU_FLAG_MASK_IN needs the fused output-conv kernel (Cout=1, Cin in 8/16/32/64)");
+  if (fused_ok) {
     // fused single pass for the output conv: dx, dw and db together
     long long blocks = (npix + 256 * 4 - 1) / (256 * 4);
     if (blocks < 1) blocks = 1;
     if (blocks > 8 * pu::kNumSMs) blocks = 8 * pu::kNumSMs;
     switch (Cin) {
-      case 8: pu::conv1x1_bwd_c1_kernel<8><<<(unsigned)blocks, 256, 0, st>>>(x, w, g, dx, scratch, npix); break;
-      case 16: pu::conv1x1_bwd_c1_kernel<16><<<(unsigned)blocks, 256, 0, st>>>(x, w, g, dx, scratch, npix); break;
-      case 32: pu::conv1x1_bwd_c1_kernel<32><<<(unsigned)blocks, 256, 0, st>>>(x, w, g, dx, scratch, npix); break;
-      default: pu::conv1x1_bwd_c1_kernel<64><<<(unsigned)blocks, 256, 0, st>>>(x, w, g, dx, scratch, npix); break;
+      case 8: pu::conv1x1_bwd_c1_kernel<8><<<(unsigned)blocks, 256, 0, st>>>(x, w, g, dx, scratch, npix, mask_in); break;
+      case 16: pu::conv1x1_bwd_c1_kernel<16><<<(unsigned)blocks, 256, 0, st>>>(x, w, g, dx, scratch, npix, mask_in); break;
+      case 32: pu::conv1x1_bwd_c1_kernel<32><<<(unsigned)blocks, 256, 0, st>>>(x, w, g, dx, scratch, npix, mask_in); break;
+      default: pu::conv1x1_bwd_c1_kernel<64><<<(unsigned)blocks, 256, 0, st>>>(x, w, g, dx, scratch, npix, mask_in); break;
     }
     int rc1 = pu::post_launch("pu_conv1x1_bwd fused");
     if (rc1) return rc1;

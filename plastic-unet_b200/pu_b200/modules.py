@@ -34,11 +34,13 @@ def _default_math() -> str:
 # --------------------------------------------------------------------------------------------------
 # shared pieces
 # --------------------------------------------------------------------------------------------------
-def _c3(x0, conv, relu, x1=None, res=None, H=None, W=None, off0=(0, 0), off1=(0, 0), math=ops.MATH_FP32):
+def _c3(x0, conv, relu, x1=None, res=None, H=None, W=None, off0=(0, 0), off1=(0, 0), math=ops.MATH_FP32,
+        mask0=False, mask1=False, premasked=False):
     """conv3x3 over cat[x0, x1] windows with fused bias / residual / ReLU using the parameters held by `conv`."""
     if H is None:
         H, W = x0.shape[1], x0.shape[2]
-    return ops.conv3x3(x0, x1, conv.weight, conv.bias, res, relu, H, W, off0[0], off0[1], off1[0], off1[1], math)
+    return ops.conv3x3(x0, x1, conv.weight, conv.bias, res, relu, H, W, off0[0], off0[1], off1[0], off1[1], math,
+                       mask0, mask1, premasked)
 
 
 def _bn(x, bn, relu, math=ops.MATH_FP32):
@@ -83,6 +85,7 @@ class _PlasticBase(nn.Module):
         self.rule = rule
         self.batched = batched
         self.conv_math = _default_math()
+        self.premask = True   # TF32 mode: fold each ReLU mask into its consumers' backward epilogues (UNetp / UNetpCoord)
         self.dp_group = None  # set by pu_b200.dp.attach() for the data-parallel trace all-reduce
         self.dp_world = 1
         # same creation order and RNG consumption as the reference (unet_p.py:30-32)
@@ -156,14 +159,17 @@ class double_conv(nn.Module):
                 nn.Conv2d(in_ch, out_ch, 3, padding=1), nn.ReLU(inplace=True),
                 nn.Conv2d(out_ch, out_ch, 3, padding=1), nn.ReLU(inplace=True))
 
-    def run(self, x0, math, x1=None, H=None, W=None, off0=(0, 0), off1=(0, 0)):
+    def run(self, x0, math, x1=None, H=None, W=None, off0=(0, 0), off1=(0, 0), in0_relu=False, in1_relu=False, premask=False):
+        """premask: premasked-gradient protocol (TF32 mode, no BN): the ReLU mask of each conv is applied by the
+        backward epilogue of its consumers instead of a separate pass; in0_relu/in1_relu: the sources are such outputs."""
         if self.batch_norm:
             y = _c3(x0, self.conv[0], False, x1=x1, H=H, W=W, off0=off0, off1=off1, math=math)
             y = _bn(y, self.conv[1], True, math)
             y = _c3(y, self.conv[3], False, math=math)
             return _bn(y, self.conv[4], True, math)
-        y = _c3(x0, self.conv[0], True, x1=x1, H=H, W=W, off0=off0, off1=off1, math=math)
-        return _c3(y, self.conv[2], True, math=math)
+        y = _c3(x0, self.conv[0], True, x1=x1, H=H, W=W, off0=off0, off1=off1, math=math, mask0=in0_relu, mask1=in1_relu,
+                premasked=premask)
+        return _c3(y, self.conv[2], True, math=math, mask0=premask, premasked=premask)
 
 
 class inconv(nn.Module):
@@ -171,8 +177,8 @@ class inconv(nn.Module):
         super(inconv, self).__init__()
         self.conv = double_conv(in_ch, out_ch, batch_norm)
 
-    def run(self, x, math):
-        return self.conv.run(x, math)
+    def run(self, x, math, premask=False):
+        return self.conv.run(x, math, premask=premask)
 
 
 class down(nn.Module):
@@ -180,8 +186,8 @@ class down(nn.Module):
         super(down, self).__init__()
         self.mpconv = nn.Sequential(nn.MaxPool2d(2), double_conv(in_ch, out_ch, batch_norm))
 
-    def run(self, x, math):
-        return self.mpconv[1].run(ops.maxpool2(x, None), math)
+    def run(self, x, math, premask=False):
+        return self.mpconv[1].run(ops.maxpool2(x, None, premask), math, premask=premask)
 
 
 class up(nn.Module):
@@ -197,8 +203,8 @@ class up(nn.Module):
             self.up = nn.ConvTranspose2d(in_ch // 2, in_ch // 2, 2, stride=2)
         self.conv = double_conv(in_ch, out_ch, batch_norm)
 
-    def run(self, x1, x2, math):
-        u = ops.bilinear2x(x1) if self.bilinear else ops.convT2x2s2(x1, self.up.weight, self.up.bias, math == ops.MATH_TF32)
+    def run(self, x1, x2, math, premask=False):
+        u = ops.bilinear2x(x1) if self.bilinear else ops.convT2x2s2(x1, self.up.weight, self.up.bias, math == ops.MATH_TF32, premask)
         diffX = u.shape[1] - x2.shape[1]  # reference names: size()[2] == H
         diffY = u.shape[2] - x2.shape[2]
         # F.pad(x2, (diffX//2, int(diffX/2), diffY//2, int(diffY/2))): first pair pads W, second pair pads H
@@ -209,7 +215,8 @@ class up(nn.Module):
         if h_new != u.shape[1] or w_new != u.shape[2]:
             raise RuntimeError("Sizes of tensors must match except in dimension 1")
         off_skip = (-(diffY // 2), -(diffX // 2))  # (oy, ox) of the crop window in the skip tensor
-        return self.conv.run(x2, math, x1=u, H=u.shape[1], W=u.shape[2], off0=off_skip, off1=(0, 0))
+        return self.conv.run(x2, math, x1=u, H=u.shape[1], W=u.shape[2], off0=off_skip, off1=(0, 0), in0_relu=premask,
+                             premask=premask)
 
 
 class outconv(nn.Module):
@@ -217,9 +224,9 @@ class outconv(nn.Module):
         super(outconv, self).__init__()
         self.conv = nn.Conv2d(in_ch, out_ch, 1)
 
-    def run(self, x):
+    def run(self, x, premask=False):
         w = self.conv.weight
-        return ops.conv1x1(x, w.view(w.shape[0], w.shape[1]), self.conv.bias, 0, False)
+        return ops.conv1x1(x, w.view(w.shape[0], w.shape[1]), self.conv.bias, 0, False, False, premask)
 
 
 class UNetp(_PlasticBase):
@@ -251,13 +258,16 @@ class UNetp(_PlasticBase):
             raise ValueError("Only batch size: 1 is supported, but was: %d" % x.shape[0])
         m = self._math
         x = self._to_nhwc(x)
-        feats = [self.inc.run(x, m)]
+        # premasked-gradient protocol (backward only, TF32 mode without BN / bilinear / ragged output conv): see DESIGN.md 4.2
+        pm = (m == ops.MATH_TF32 and self.premask and not self.inc.conv.batch_norm and not self.up1.bilinear
+              and self.outc.conv.weight.shape[1] in (8, 16, 32, 64) and self.n_classes == 1)
+        feats = [self.inc.run(x, m, pm)]
         for k in range(1, self.depth + 1):
-            feats.append(getattr(self, "down%d" % k).run(feats[-1], m))
+            feats.append(getattr(self, "down%d" % k).run(feats[-1], m, pm))
         y = feats[-1]
         for j in range(1, self.depth + 1):
-            y = getattr(self, "up%d" % j).run(y, feats[self.depth - j], m)
-        o = self.outc.run(y)
+            y = getattr(self, "up%d" % j).run(y, feats[self.depth - j], m, pm)
+        o = self.outc.run(y, pm)
         return self._plastic(o, hebb)
 
 

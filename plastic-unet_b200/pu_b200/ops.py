@@ -20,6 +20,7 @@ RULE_HEBB = 0
 RULE_OJA = 1
 FLAG_RELU = 1
 FLAG_ROUND_TF32 = 2
+FLAG_MASK_IN = 4
 
 
 @functools.lru_cache(maxsize=None)
@@ -89,7 +90,11 @@ def _dims(t: Optional[Tensor]) -> Tuple[int, int, int]:
 # =================================================================================================
 @torch.library.custom_op("pu::conv3x3", mutates_args=())
 def conv3x3(x0: Tensor, x1: Optional[Tensor], weight: Tensor, bias: Optional[Tensor], res: Optional[Tensor],
-            relu: bool, H: int, W: int, oy0: int, ox0: int, oy1: int, ox1: int, math: int) -> Tensor:
+            relu: bool, H: int, W: int, oy0: int, ox0: int, oy1: int, ox1: int, math: int,
+            mask0: bool = False, mask1: bool = False, premasked: bool = False) -> Tensor:
+    """mask0/mask1/premasked implement the premasked-gradient protocol (backward only): `premasked` = every consumer
+    of this op's ReLU output multiplies the gradient it sends back by (y > 0), so this op's backward skips its own
+    mask pass; `mask0`/`mask1` = source 0/1 is such a ReLU output, i.e. this op's dgrad must apply (x > 0)."""
     _chk(x0, x1, weight, bias, res)
     B = x0.shape[0]
     Cout, Cin = weight.shape[0], weight.shape[1]
@@ -104,19 +109,19 @@ def conv3x3(x0: Tensor, x1: Optional[Tensor], weight: Tensor, bias: Optional[Ten
     y = torch.empty((B, H, W, Cout), device=x0.device, dtype=torch.float32)
     _lib.call("pu_conv3x3_fwd", x0.data_ptr(), H0, W0, C0, oy0, ox0, _p(x1), H1, W1, C1, oy1, ox1,
               wp.data_ptr(), _p(bias), _p(res), flags,
-              y.data_ptr(), H, W, Cout, 0, 0, None, 0, 0, 0, 0, 0, B, H, W, Cout, m, wfmt, _s())
+              y.data_ptr(), H, W, Cout, 0, 0, None, 0, 0, 0, 0, 0, None, None, B, H, W, Cout, m, wfmt, _s())
     return y
 
 
 @conv3x3.register_fake
-def _(x0, x1, weight, bias, res, relu, H, W, oy0, ox0, oy1, ox1, math):
+def _(x0, x1, weight, bias, res, relu, H, W, oy0, ox0, oy1, ox1, math, mask0=False, mask1=False, premasked=False):
     return x0.new_empty((x0.shape[0], H, W, weight.shape[0]))
 
 
 @torch.library.custom_op("pu::conv3x3_bwd", mutates_args=())
 def conv3x3_bwd(dy: Tensor, y: Tensor, x0: Tensor, x1: Optional[Tensor], weight: Tensor, has_bias: bool, relu: bool,
                 H: int, W: int, oy0: int, ox0: int, oy1: int, ox1: int, math: int,
-                need_dx: bool, need_dw: bool) -> List[Tensor]:
+                need_dx: bool, need_dw: bool, mask0: bool = False, mask1: bool = False, premasked: bool = False) -> List[Tensor]:
     """-> [g, dx0, dx1, dw, db]; g = dy masked by the fused ReLU (== dy when relu is False)."""
     _chk(dy, y, x0, x1, weight)
     dev = dy.device
@@ -127,8 +132,14 @@ def conv3x3_bwd(dy: Tensor, y: Tensor, x0: Tensor, x1: Optional[Tensor], weight:
     npix = B * H * W
     db = torch.empty(Cout, device=dev, dtype=torch.float32) if has_bias else _e(dev)
     tf32 = math == MATH_TF32
-    fresh_g = relu or tf32  # tensor-core operands are stored rounded to TF32 by their producer
-    if fresh_g:
+    premasked = premasked and relu
+    fresh_g = (relu or tf32) and not premasked  # tensor-core operands are stored rounded to TF32 by their producer
+    db_in_wgrad = premasked and has_bias and need_dw
+    if premasked:
+        g = dy  # every consumer already applied (y > 0) (and rounded) in its own backward epilogue
+        if has_bias and not need_dw:
+            _lib.call("pu_relu_bwd_bias", dy.data_ptr(), None, None, db.data_ptr(), npix, Cout, 0, _s())
+    elif fresh_g:
         g = torch.empty_like(dy)
         _lib.call("pu_relu_bwd_bias", dy.data_ptr(), y.data_ptr() if relu else None, g.data_ptr(), _p(db) if has_bias else None,
                   npix, Cout, (FLAG_RELU if relu else 0) | (FLAG_ROUND_TF32 if tf32 else 0), _s())
@@ -149,20 +160,22 @@ def conv3x3_bwd(dy: Tensor, y: Tensor, x0: Tensor, x1: Optional[Tensor], weight:
                   wpt.data_ptr(), None, None, FLAG_ROUND_TF32 if tf32 else 0,
                   dx0.data_ptr(), H0, W0, C0, oy0, ox0,
                   dx1.data_ptr() if x1 is not None else None, H1, W1, C1, oy1, ox1,
+                  x0.data_ptr() if mask0 else None, x1.data_ptr() if (mask1 and x1 is not None) else None,
                   B, H, W, Cin, md, wfmt, _s())
     dw = _e(dev)
     if need_dw:
         dw = torch.empty_like(weight)
         _lib.call("pu_conv3x3_wgrad", x0.data_ptr(), H0, W0, C0, oy0, ox0, _p(x1), H1, W1, C1, oy1, ox1,
-                  g.data_ptr(), dw.data_ptr(), B, H, W, Cout, math, _s())
+                  g.data_ptr(), dw.data_ptr(), db.data_ptr() if db_in_wgrad else None, B, H, W, Cout, math, _s())
     g_out = g if fresh_g else _e(dev)  # never return an alias of an input
     return [g_out, dx0, dx1, dw, db]
 
 
 @conv3x3_bwd.register_fake
-def _(dy, y, x0, x1, weight, has_bias, relu, H, W, oy0, ox0, oy1, ox1, math, need_dx, need_dw):
+def _(dy, y, x0, x1, weight, has_bias, relu, H, W, oy0, ox0, oy1, ox1, math, need_dx, need_dw, mask0=False, mask1=False,
+      premasked=False):
     e = dy.new_empty(0)
-    return [torch.empty_like(dy) if (relu or math == MATH_TF32) else e,
+    return [torch.empty_like(dy) if ((relu or math == MATH_TF32) and not (premasked and relu)) else e,
             torch.empty_like(x0) if need_dx else e,
             torch.empty_like(x1) if (need_dx and x1 is not None) else e,
             torch.empty_like(weight) if need_dw else e,
@@ -170,24 +183,24 @@ def _(dy, y, x0, x1, weight, has_bias, relu, H, W, oy0, ox0, oy1, ox1, math, nee
 
 
 def _conv3x3_setup(ctx, inputs, output):
-    x0, x1, weight, bias, res, relu, H, W, oy0, ox0, oy1, ox1, math = inputs
+    x0, x1, weight, bias, res, relu, H, W, oy0, ox0, oy1, ox1, math, mask0, mask1, premasked = inputs
     ctx.save_for_backward(x0, x1, weight, output)
-    ctx.cfg = (bias is not None, res is not None, relu, H, W, oy0, ox0, oy1, ox1, math)
+    ctx.cfg = (bias is not None, res is not None, relu, H, W, oy0, ox0, oy1, ox1, math, mask0, mask1, premasked)
 
 
 def _conv3x3_backward(ctx, dy):
     x0, x1, weight, y = ctx.saved_tensors
-    has_bias, has_res, relu, H, W, oy0, ox0, oy1, ox1, math = ctx.cfg
+    has_bias, has_res, relu, H, W, oy0, ox0, oy1, ox1, math, mask0, mask1, premasked = ctx.cfg
     need = ctx.needs_input_grad
     need_dx = need[0] or (x1 is not None and need[1])
     dy = dy.contiguous()
     g, dx0, dx1, dw, db = conv3x3_bwd(dy, y, x0, x1, weight, has_bias and need[3], relu, H, W, oy0, ox0, oy1, ox1, math,
-                                      need_dx, need[2])
+                                      need_dx, need[2], mask0, mask1, premasked)
     gres = None
     if has_res and need[4]:
-        gres = g if (relu or math == MATH_TF32) else dy
+        gres = g if ((relu or math == MATH_TF32) and not (premasked and relu)) else dy
     return (dx0 if need[0] else None, dx1 if (x1 is not None and need[1]) else None, dw if need[2] else None,
-            db if (has_bias and need[3]) else None, gres, None, None, None, None, None, None, None, None)
+            db if (has_bias and need[3]) else None, gres, None, None, None, None, None, None, None, None, None, None, None)
 
 
 conv3x3.register_autograd(_conv3x3_backward, setup_context=_conv3x3_setup)
@@ -197,7 +210,8 @@ conv3x3.register_autograd(_conv3x3_backward, setup_context=_conv3x3_setup)
 # conv1x1 (+ analytic CoordConv channels, + ReLU)
 # =================================================================================================
 @torch.library.custom_op("pu::conv1x1", mutates_args=())
-def conv1x1(x: Tensor, weight: Tensor, bias: Optional[Tensor], coords: int, relu: bool, round_out: bool = False) -> Tensor:
+def conv1x1(x: Tensor, weight: Tensor, bias: Optional[Tensor], coords: int, relu: bool, round_out: bool = False,
+            mask_in: bool = False) -> Tensor:
     _chk(x, weight, bias)
     B, H, W, Cin = x.shape
     Cout = weight.shape[0]
@@ -210,12 +224,13 @@ def conv1x1(x: Tensor, weight: Tensor, bias: Optional[Tensor], coords: int, relu
 
 
 @conv1x1.register_fake
-def _(x, weight, bias, coords, relu, round_out=False):
+def _(x, weight, bias, coords, relu, round_out=False, mask_in=False):
     return x.new_empty((x.shape[0], x.shape[1], x.shape[2], weight.shape[0]))
 
 
 @torch.library.custom_op("pu::conv1x1_bwd", mutates_args=())
-def conv1x1_bwd(dy: Tensor, y: Tensor, x: Tensor, weight: Tensor, coords: int, relu: bool, need_dx: bool) -> List[Tensor]:
+def conv1x1_bwd(dy: Tensor, y: Tensor, x: Tensor, weight: Tensor, coords: int, relu: bool, need_dx: bool,
+                mask_in: bool = False) -> List[Tensor]:
     _chk(dy, y, x, weight)
     B, H, W, Cin = x.shape
     Cout = weight.shape[0]
@@ -229,27 +244,27 @@ def conv1x1_bwd(dy: Tensor, y: Tensor, x: Tensor, weight: Tensor, coords: int, r
     db = torch.empty(Cout, device=dev, dtype=torch.float32)
     ws = torch.empty(Cout * (Cin + coords + 1), device=dev, dtype=torch.float32)
     _lib.call("pu_conv1x1_bwd", x.data_ptr(), weight.data_ptr(), g.data_ptr(), dx.data_ptr() if need_dx else None,
-              dw.data_ptr(), db.data_ptr(), ws.data_ptr(), B, H, W, Cin, Cout, coords, _s())
+              dw.data_ptr(), db.data_ptr(), ws.data_ptr(), B, H, W, Cin, Cout, coords, FLAG_MASK_IN if mask_in else 0, _s())
     return [dx, dw, db]
 
 
 @conv1x1_bwd.register_fake
-def _(dy, y, x, weight, coords, relu, need_dx):
+def _(dy, y, x, weight, coords, relu, need_dx, mask_in=False):
     return [torch.empty_like(x) if need_dx else x.new_empty(0), torch.empty_like(weight), x.new_empty(weight.shape[0])]
 
 
 def _conv1x1_setup(ctx, inputs, output):
-    x, weight, bias, coords, relu, _round = inputs
+    x, weight, bias, coords, relu, _round, mask_in = inputs
     ctx.save_for_backward(x, weight, output)
-    ctx.cfg = (bias is not None, coords, relu)
+    ctx.cfg = (bias is not None, coords, relu, mask_in)
 
 
 def _conv1x1_backward(ctx, dy):
     x, weight, y = ctx.saved_tensors
-    has_bias, coords, relu = ctx.cfg
+    has_bias, coords, relu, mask_in = ctx.cfg
     need = ctx.needs_input_grad
-    dx, dw, db = conv1x1_bwd(dy.contiguous(), y, x, weight, coords, relu, need[0])
-    return dx if need[0] else None, dw if need[1] else None, db if (has_bias and need[2]) else None, None, None, None
+    dx, dw, db = conv1x1_bwd(dy.contiguous(), y, x, weight, coords, relu, need[0], mask_in)
+    return dx if need[0] else None, dw if need[1] else None, db if (has_bias and need[2]) else None, None, None, None, None
 
 
 conv1x1.register_autograd(_conv1x1_backward, setup_context=_conv1x1_setup)
@@ -259,7 +274,7 @@ conv1x1.register_autograd(_conv1x1_backward, setup_context=_conv1x1_setup)
 # transposed convolutions
 # =================================================================================================
 @torch.library.custom_op("pu::convT2x2s2", mutates_args=())
-def convT2x2s2(x: Tensor, weight: Tensor, bias: Optional[Tensor], round_out: bool = False) -> Tensor:
+def convT2x2s2(x: Tensor, weight: Tensor, bias: Optional[Tensor], round_out: bool = False, mask_in: bool = False) -> Tensor:
     _chk(x, weight, bias)
     B, H, W, Cin = x.shape
     Cout = weight.shape[1]
@@ -270,12 +285,13 @@ def convT2x2s2(x: Tensor, weight: Tensor, bias: Optional[Tensor], round_out: boo
 
 
 @convT2x2s2.register_fake
-def _(x, weight, bias, round_out=False):
+def _(x, weight, bias, round_out=False, mask_in=False):
     return x.new_empty((x.shape[0], 2 * x.shape[1], 2 * x.shape[2], weight.shape[1]))
 
 
 @torch.library.custom_op("pu::convT2x2s2_bwd", mutates_args=())
-def convT2x2s2_bwd(dy: Tensor, x: Tensor, weight: Tensor, need_dx: bool, need_dw: bool, need_db: bool) -> List[Tensor]:
+def convT2x2s2_bwd(dy: Tensor, x: Tensor, weight: Tensor, need_dx: bool, need_dw: bool, need_db: bool,
+                   mask_in: bool = False) -> List[Tensor]:
     _chk(dy, x, weight)
     B, H, W, Cin = x.shape
     Cout = weight.shape[1]
@@ -283,28 +299,30 @@ def convT2x2s2_bwd(dy: Tensor, x: Tensor, weight: Tensor, need_dx: bool, need_dw
     dw = torch.empty_like(weight) if need_dw else _e(x.device)
     db = torch.empty(Cout, device=x.device, dtype=torch.float32) if need_db else _e(x.device)
     _lib.call("pu_convT2x2s2_bwd", x.data_ptr(), weight.data_ptr(), dy.data_ptr(), dx.data_ptr() if need_dx else None,
-              dw.data_ptr() if need_dw else None, db.data_ptr() if need_db else None, B, H, W, Cin, Cout, _s())
+              dw.data_ptr() if need_dw else None, db.data_ptr() if need_db else None, B, H, W, Cin, Cout,
+              FLAG_MASK_IN if mask_in else 0, _s())
     return [dx, dw, db]
 
 
 @convT2x2s2_bwd.register_fake
-def _(dy, x, weight, need_dx, need_dw, need_db):
+def _(dy, x, weight, need_dx, need_dw, need_db, mask_in=False):
     e = x.new_empty(0)
     return [torch.empty_like(x) if need_dx else e, torch.empty_like(weight) if need_dw else e,
             x.new_empty(weight.shape[1]) if need_db else e]
 
 
 def _convT2_setup(ctx, inputs, output):
-    x, weight, bias, _round = inputs
+    x, weight, bias, _round, mask_in = inputs
     ctx.save_for_backward(x, weight)
     ctx.has_bias = bias is not None
+    ctx.mask_in = mask_in
 
 
 def _convT2_backward(ctx, dy):
     x, weight = ctx.saved_tensors
     need = ctx.needs_input_grad
-    dx, dw, db = convT2x2s2_bwd(dy.contiguous(), x, weight, need[0], need[1], ctx.has_bias and need[2])
-    return dx if need[0] else None, dw if need[1] else None, db if (ctx.has_bias and need[2]) else None, None
+    dx, dw, db = convT2x2s2_bwd(dy.contiguous(), x, weight, need[0], need[1], ctx.has_bias and need[2], ctx.mask_in)
+    return dx if need[0] else None, dw if need[1] else None, db if (ctx.has_bias and need[2]) else None, None, None
 
 
 convT2x2s2.register_autograd(_convT2_backward, setup_context=_convT2_setup)
@@ -371,7 +389,7 @@ convT3x3s2.register_autograd(_convT3_backward, setup_context=_convT3_setup)
 # pooling / resampling
 # =================================================================================================
 @torch.library.custom_op("pu::maxpool2", mutates_args=())
-def maxpool2(x: Tensor, chan_scale: Optional[Tensor]) -> Tensor:
+def maxpool2(x: Tensor, chan_scale: Optional[Tensor], mask_in: bool = False) -> Tensor:
     _chk(x, chan_scale)
     B, H, W, C = x.shape
     y = torch.empty((B, H // 2, W // 2, C), device=x.device, dtype=torch.float32)
@@ -380,32 +398,34 @@ def maxpool2(x: Tensor, chan_scale: Optional[Tensor]) -> Tensor:
 
 
 @maxpool2.register_fake
-def _(x, chan_scale):
+def _(x, chan_scale, mask_in=False):
     return x.new_empty((x.shape[0], x.shape[1] // 2, x.shape[2] // 2, x.shape[3]))
 
 
 @torch.library.custom_op("pu::maxpool2_bwd", mutates_args=())
-def maxpool2_bwd(dy: Tensor, x: Tensor, chan_scale: Optional[Tensor]) -> Tensor:
+def maxpool2_bwd(dy: Tensor, x: Tensor, chan_scale: Optional[Tensor], mask_in: bool = False) -> Tensor:
     _chk(dy, x, chan_scale)
     B, H, W, C = x.shape
     dx = torch.empty_like(x)
-    _lib.call("pu_maxpool2_bwd", x.data_ptr(), _p(chan_scale), dy.data_ptr(), dx.data_ptr(), B, H, W, C, _s())
+    _lib.call("pu_maxpool2_bwd", x.data_ptr(), _p(chan_scale), dy.data_ptr(), dx.data_ptr(), B, H, W, C,
+              FLAG_MASK_IN if mask_in else 0, _s())
     return dx
 
 
 @maxpool2_bwd.register_fake
-def _(dy, x, chan_scale):
+def _(dy, x, chan_scale, mask_in=False):
     return torch.empty_like(x)
 
 
 def _pool_setup(ctx, inputs, output):
-    x, chan_scale = inputs
+    x, chan_scale, mask_in = inputs
     ctx.save_for_backward(x, chan_scale)
+    ctx.mask_in = mask_in
 
 
 def _pool_backward(ctx, dy):
     x, chan_scale = ctx.saved_tensors
-    return maxpool2_bwd(dy.contiguous(), x, chan_scale), None
+    return maxpool2_bwd(dy.contiguous(), x, chan_scale, ctx.mask_in), None, None
 
 
 maxpool2.register_autograd(_pool_backward, setup_context=_pool_setup)

@@ -21,7 +21,7 @@ dw = torch.empty(Cout, C0 + C1, 3, 3, device=dev)
 def run(i):
     x1 = xs1[i % nbuf]
     _lib.call("pu_conv3x3_wgrad", xs0[i % nbuf].data_ptr(), size, size, C0, 0, 0, x1.data_ptr() if C1 else None, size, size, C1, 0, 0,
-              gs[i % nbuf].data_ptr(), dw.data_ptr(), B, size, size, Cout, MATH, torch.cuda.current_stream().cuda_stream)
+              gs[i % nbuf].data_ptr(), dw.data_ptr(), None, B, size, size, Cout, MATH, torch.cuda.current_stream().cuda_stream)
 
 
 ITERS = 20
