@@ -548,6 +548,7 @@ __global__ void __launch_bounds__(256, 2) conv3x3_wgrad_mma_kernel(const WgradAr
   extern __shared__ __align__(16) float dsm[];  // [2][STAGE_F]; the reduction buffer aliases it at the end
   static_assert(2 * STAGE_F >= 8 * 32 * 20, "reduction buffer must fit in the staging ring");
 
+  pdl_prologue();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int gq = lane >> 2, tq = lane & 3;  // mma fragment coordinates: groupID, threadID_in_group
   int cchunk = blockIdx.y;
@@ -792,12 +793,12 @@ int conv3x3_wgrad_ffma(const WgradArgs& a0, cudaStream_t st, int math) {
         a.tilesX = cdiv(a.W, 32); a.tilesY = cdiv(a.H, 16);
         a.ntiles = a.tilesX * a.tilesY * a.B;
         const int gx = max(1, min(a.ntiles, (2 * kNumSMs) / max(1, nci * nco)));
-        conv3x3_wgrad_mma_kernel<32, 16><<<dim3(gx, nci, nco), 256, smem32, st>>>(a);
+        launch_pdl(conv3x3_wgrad_mma_kernel<32, 16>, dim3(gx, nci, nco), dim3(256), smem32, st, a);
       } else {
         a.tilesX = cdiv(a.W, 16); a.tilesY = cdiv(a.H, 16);
         a.ntiles = a.tilesX * a.tilesY * a.B;
         const int gx = max(1, min(a.ntiles, (4 * kNumSMs) / max(1, nci * nco)));
-        conv3x3_wgrad_mma_kernel<16, 16><<<dim3(gx, nci, nco), 256, smem16, st>>>(a);
+        launch_pdl(conv3x3_wgrad_mma_kernel<16, 16>, dim3(gx, nci, nco), dim3(256), smem16, st, a);
       }
       return post_launch("conv3x3_wgrad_mma");
     }

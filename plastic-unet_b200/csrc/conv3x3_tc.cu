@@ -174,6 +174,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const __grid_
   auto tfull_bar = [&](int as) { return bar0 + 8u * (2 * kStages + as); };
   auto tempty_bar = [&](int as) { return bar0 + 8u * (2 * kStages + 2 + as); };
 
+  pdl_prologue();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int coblk = blockIdx.y;
   const int tiles_per_img = a.tilesX * a.tilesY;
@@ -812,7 +813,11 @@ static int launch_tc(const CUtensorMap& tm0, const CUtensorMap& tm1, const TcArg
     }
     attr_set = true;
   }
-  conv3x3_tc_kernel<COLS><<<grid, kTcThreads, smem, st>>>(tm0, tm1, ta);
+  cudaError_t le = launch_pdl(conv3x3_tc_kernel<COLS>, grid, dim3(kTcThreads), smem, st, tm0, tm1, ta);
+  if (le != cudaSuccess) {
+    set_error("conv3x3_tc launch: %s", cudaGetErrorString(le));
+    return PU_ERR_CUDA;
+  }
   return post_launch("conv3x3_tc");
 }
 

@@ -1,5 +1,6 @@
 // Library management: version, error text, launch accounting.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <atomic>
 #include <mutex>
 #include "pu_common.cuh"
@@ -16,6 +17,15 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PU_PDL");
+    v = (e != nullptr && e[0] == '1') ? 1 : 0;  // measured neutral on B200 (2.02 vs 2.01 ms/step): off unless PU_PDL=1
+  }
+  return v == 1;
 }
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }

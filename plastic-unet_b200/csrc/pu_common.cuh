@@ -40,6 +40,35 @@ struct ViewW {
   int Hs, Ws, C, oy, ox;
 };
 
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------
+// Hot kernels are launched with cudaLaunchAttributeProgrammaticStreamSerialization: the next kernel's launch (and the
+// scheduling of its CTAs as SM resources free up) overlaps this kernel's tail instead of waiting for a full
+// kernel-boundary drain (~3 us each, ~100 kernels per train step).  Protocol: every such kernel calls pdl_prologue()
+// before touching global memory — griddepcontrol.wait blocks until ALL prerequisite grids have completed and flushed,
+// so correctness does not depend on where the predecessor triggers; launch_dependents right after lets the successor
+// start launching immediately.  Kernels launched without the attribute execute both as no-ops.
+__device__ __forceinline__ void pdl_prologue() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+bool pdl_enabled();  // PU_PDL=1 enables (defined in pu_api.cu)
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---- device helpers ----------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
