@@ -20,7 +20,7 @@
 //     l+1, l+2 of its own 8-lane group, and an MMA block yields 96 output pixels.
 // Skip-concat is a second tensor map whose regions follow the first in K.
 //
-// Persistent, warp-specialised CTA (one per SM): warp 0 = TMA producer, warps 1-3 = MMA issuers (blocks dealt
+// Persistent, warp-specialised CTA (one per SM): warp 0 = TMA producer, warps 1-3 and 12 = MMA issuers (blocks dealt
 // round-robin, one elected lane issues), warps 4-11 = epilogue (TMEM lane quarter = warp % 4, two warps per quarter).
 // nstages shared-memory stages cycle through full/empty mbarriers, two TMEM accumulator buffers through
 // tmem_full/tmem_empty, so tile i's epilogue overlaps tile i+1's MMAs and tile i+2's loads.  The epilogue applies
@@ -88,6 +88,7 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 // bounded wait: a lost TMA transaction or MMA commit must not hang the GPU
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
+#pragma unroll 1
   for (uint32_t it = 0; it < (1u << 22); ++it) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -160,14 +161,24 @@ __device__ __forceinline__ void stg8(float* p, const float* r) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // ---- the kernel ---------------------------------------------------------------------------------
+// Measured on B200 (scripts/probes/umma_rate_probe.cu): one thread can issue a tcgen05.mma (M=128, K=8, tf32 or bf16)
+// only every ~128 clk whatever N <= 128 is, two threads reach 64 clk/MMA, four or more saturate the tensor pipe at
+// ~42 + 0.25 N clk/MMA; operand swizzle mode, row-shifted start addresses and accumulator reuse make no difference,
+// and a tcgen05.commit costs the issuing thread about as much as an MMA.  So the MMAs of a tile are issued by three
+// warps (the blocks dealt round-robin).  Variants with 4 or 7 issuing warps, two warp groups alternating tiles, or the
+// stage barrier doubling as the "accumulators complete" signal were all measured within +-8% of this one: per tile the
+// chain wait -> 6..8 issues -> completion -> epilogue -> release of the TMEM buffer is latency-bound.
+// NB a waiter that falls TWO phases behind an mbarrier never returns from a parity wait (and one that is two phases
+// ahead passes spuriously): every barrier here has waiters that consume each of its phases in order.
 constexpr int kMmaWarps = 3;
-constexpr int kMmaWarp0 = 1;
 constexpr int kEpiWarp0 = 4;  // first epilogue warp (multiple of 4: TMEM lane quarter = warp & 3)
 constexpr int kEpiWarps = 8;
+constexpr int kEpiSets = kEpiWarps / 4;  // warps per TMEM lane quarter
 constexpr int kTcThreads = 32 * (kEpiWarp0 + kEpiWarps);
 
-// B-operand tile of one chunk: [ky][4-channel group][n = kx*COLS + co][4 floats], SWIZZLE_NONE K-major
-// (8x16B core matrices 128 B apart along N, the two K halves of an MMA N3*16 B apart), RN-rounded to TF32.
+// B-operand tile of one chunk: [ky][K step of 8 channels][n = kx*COLS + co][8 floats], K-major SWIZZLE_32B (32-byte
+// rows, the two 16-byte halves of a row exchanged where bit 7 of the byte address is set), RN-rounded to TF32.
+// (A SWIZZLE_NONE B tile costs the tensor core ~1 clk per N row: measured 150 clk per MMA at N = 96.)
 template <int COLS>
 __device__ __forceinline__ void build_w_tile(const TcChunk& ch, float4* out, const float* __restrict__ w, int wfmt, int Cin, int Cout,
                                              int C0, int co_base, int u0, int ustep) {
@@ -195,7 +206,7 @@ __device__ __forceinline__ void build_w_tile(const TcChunk& ch, float4* out, con
         v.z = round_tf32(__ldg(base + 2 * cs + t));
         v.w = round_tf32(__ldg(base + 3 * cs + t));
       }
-      out[(ky * ch.ncg + kc) * N3 + n] = v;
+      out[((ky * (ch.ncg >> 1) + (kc >> 1)) * N3 + n) * 2 + ((kc & 1) ^ ((n >> 2) & 1))] = v;
     }
   }
 }
@@ -212,6 +223,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const __grid_
   uint64_t* bars = reinterpret_cast<uint64_t*>(smWres + a.w_res_bytes);
   // bars: [0,kMaxStages) full, [kMaxStages,2kMaxStages) empty, then tmem_full[2], tmem_empty[2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+  int* wtab = reinterpret_cast<int*>(tmem_slot + 2);  // resident-weight build: (offset, ky stride) per 4-channel group, <= 1 KB
+  // PU_TC_DEBUG & 64: per-tile timeline of CTA 0 (cycles since kernel start): [event][tile < 12]
+  long long* trace = reinterpret_cast<long long*>(reinterpret_cast<uint8_t*>(tmem_slot) + 1024);  // 10 events x 12 tiles
+  const bool tracing = (a.debug & 64) && blockIdx.x == 0 && blockIdx.y == 0;
+  const long long t_start = clock64();
+  auto stamp = [&](int ev, int k) {
+    if (tracing && k < 12) trace[ev * 12 + k] = clock64() - t_start;
+  };
   const uint32_t bar0 = smem_u32(bars);
   auto full_bar = [&](int st) { return bar0 + 8u * st; };
   auto empty_bar = [&](int st) { return bar0 + 8u * (kMaxStages + st); };
@@ -237,42 +256,127 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const __grid_
         mbar_init(tempty_bar(i), kEpiWarps);  // one arrival per epilogue warp
       }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm0)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm1)) : "memory");
     }
-    __syncwarp();
+  } else if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)a.tmem_cols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (a.wfmt != 0) {
-    // Build the tf32 B-operand tiles of every K chunk straight from the OIHW weight tensor (no pack kernel).
-    for (int c = 0; c < a.nchunks; ++c)
-      build_w_tile<COLS>(a.chunks[c], reinterpret_cast<float4*>(smWres + a.chunks[c].w_off), a.wpk, a.wfmt, a.Cin, a.Cout, a.C0, co_base,
-                         tid, kTcThreads);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tensor-core (async proxy) reads
-  }
   tc_fence_before();
-  __syncthreads();
+  __syncthreads();  // barriers initialised, TMEM allocated
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (tid == 0) stamp(5, 0);
 
-  if (warp == 0) {
+  if (a.wfmt != 0 && warp != 0) {
+    // Resident weights: warps 1.. build the tf32 B-operand tiles of every K chunk straight from the OIHW tensor while
+    // warp 0 already streams the first input tiles (a naive per-element build with runtime index arithmetic took
+    // 6 us for a 37 KB image: more than the rest of a small layer).
+    constexpr int kBuilders = kTcThreads - 32;
+    const int bt = tid - 32;
+    auto build_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(kBuilders) : "memory"); };
+    if (!(a.debug & 16)) {
+      // k-group table: byte offset of group g's [n][4] block for ky = 0, and the ky stride, per 4-channel group
+      for (int g = bt; g < a.Cin / 4; g += kBuilders) {
+        const int ci = g * 4;
+        int off = 0, kys = 0;
+        for (int c = 0; c < a.nchunks; ++c) {
+          const TcChunk& ch = a.chunks[c];
+          int kk = 0;
+          for (int r = 0; r < ch.nreg; ++r) {
+            const int c_lo = (ch.reg[r].src ? a.C0 : 0) + ch.reg[r].c_off;
+            if (ci >= c_lo && ci < c_lo + ch.reg[r].cb) {
+              const int kc = (kk + ci - c_lo) / 4;
+              off = (int)ch.w_off + (kc >> 1) * N3 * 32 + (kc & 1) * 16;
+              kys = (ch.ncg >> 1) * N3 * 32;
+            }
+            kk += ch.reg[r].cb;
+          }
+        }
+        wtab[2 * g] = off;
+        wtab[2 * g + 1] = kys;
+      }
+      build_sync();
+      // One thread per (output channel, 4-input-channel group): its 4 x 9 weights are 36 consecutive floats of the
+      // OIHW tensor in the forward case (nine 128-bit loads), four 9-float runs for dgrad; every tap then is ONE
+      // 16-byte shared-memory store, and consecutive lanes (consecutive co) write consecutive 16-byte slots.
+      const int cob = (a.Cout - co_base) < kCoBlk ? (a.Cout - co_base) : kCoBlk;  // output channels of this co block
+      const bool vec = (reinterpret_cast<uintptr_t>(a.wpk) & 15) == 0;
+      constexpr int kColsShift = COLS == 8 ? 3 : (COLS == 16 ? 4 : (COLS == 32 ? 5 : 6));
+      for (int q = bt; q < COLS * (a.Cin / 4); q += kBuilders) {
+        const int co_l = q & (COLS - 1), g = q >> kColsShift;
+        uint8_t* const dst = smWres + ((wtab[2 * g] + co_l * 32) ^ (((co_l >> 2) & 1) << 4));  // SWIZZLE_32B
+        const int kys = wtab[2 * g + 1];
+        float x[36];
+#pragma unroll
+        for (int j = 0; j < 36; ++j) x[j] = 0.f;
+        if (co_l < cob) {
+          if (a.wfmt == 1) {
+            const float* src = a.wpk + ((size_t)(co_base + co_l) * a.Cin + 4 * g) * 9;
+            if (vec) {
+#pragma unroll
+              for (int j = 0; j < 9; ++j) {
+                const float4 t = ldg4(src + 4 * j);
+                x[4 * j] = t.x; x[4 * j + 1] = t.y; x[4 * j + 2] = t.z; x[4 * j + 3] = t.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 36; ++j) x[j] = __ldg(src + j);
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float* src = a.wpk + ((size_t)(4 * g + e) * a.Cout + (co_base + co_l)) * 9;
+#pragma unroll
+              for (int t = 0; t < 9; ++t) x[e * 9 + t] = __ldg(src + t);
+            }
+          }
+        }
+        if (a.wfmt == 1) {
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap)
+            *reinterpret_cast<float4*>(dst + (tap / 3) * kys + (tap % 3) * COLS * 32) =
+                make_float4(round_tf32(x[tap]), round_tf32(x[9 + tap]), round_tf32(x[18 + tap]), round_tf32(x[27 + tap]));
+        } else {  // dgrad: taps flipped
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap)
+            *reinterpret_cast<float4*>(dst + (tap / 3) * kys + (tap % 3) * COLS * 32) =
+                make_float4(round_tf32(x[8 - tap]), round_tf32(x[17 - tap]), round_tf32(x[26 - tap]), round_tf32(x[35 - tap]));
+        }
+        if (3 * COLS < N3) {  // COLS == 8: N rows 24..31 of every (ky, k group) are padding
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky) *reinterpret_cast<float4*>(dst + ky * kys + 3 * COLS * 32) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tensor-core (async proxy) reads
+    build_sync();
+  }
+
+  if (a.debug & 32) {
+    // (experiment) prologue only
+  } else if (warp == 0) {
     // ================= TMA producer =================
     const uint8_t* wblk = reinterpret_cast<const uint8_t*>(a.wpk) + (size_t)coblk * a.w_coblk_stride;
-    uint32_t it = 0;
-    int st = 0;
-    uint32_t ph = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (int k = 0;; ++k) {
+      const int tile = blockIdx.x + k * gridDim.x;
+      if (tile >= ntiles) break;
       const int b = tile / tiles_per_img;
       const int tr = tile - b * tiles_per_img;
       const int ty = tr / a.tilesX, tx = tr - ty * a.tilesX;
       const int x0 = tx * a.TW, y0 = ty * a.TH;
-      for (int c = 0; c < a.nchunks; ++c, ++it) {
+      for (int c = 0; c < a.nchunks; ++c) {
+        const int it = k * a.nchunks + c;
+        const int st = it % nst;
+        const uint32_t ph = (uint32_t)(it / nst) & 1;
         mbar_wait(empty_bar(st), ph ^ 1);  // passes immediately on a fresh barrier
         if (elect_one()) {
           const TcChunk& ch = a.chunks[c];
           const uint32_t w_bytes = (uint32_t)(3 * ch.ncg * N3 * 16);
           const uint32_t sS = smem_u32(smem + st * stage_bytes);
-          if ((a.debug & 4) && it >= (uint32_t)nst) {
+          if ((a.debug & 4) && k * a.nchunks + c >= nst) {
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full_bar(st)) : "memory");
           } else {
             mbar_expect_tx(full_bar(st), ch.tx_bytes + (a.wfmt == 0 ? w_bytes : 0u));
@@ -283,33 +387,36 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const __grid_
           }
         }
         __syncwarp();
-        if (++st == nst) { st = 0; ph ^= 1; }
       }
+      if (lane == 0) stamp(0, k);
     }
-  } else if (warp >= kMmaWarp0 && warp < kEpiWarp0) {
-    // ================= MMA issuers =================
-    // The whole warp runs the warp-uniform loop and one elected lane executes each tcgen05 instruction, so the
-    // descriptors live in uniform registers.  M blocks are innermost: consecutive MMAs write different accumulators
-    // and are not serialised on the accumulate dependency of one small TMEM tile.
-    const int mw = warp - kMmaWarp0;
+  } else if (warp < kEpiWarp0) {
+    // ================= MMA issuers (warps 1-3) =================
+    // The warps run the same warp-uniform loop in lock-step over the tiles (every warp consumes every barrier phase in
+    // order) and split the 96-pixel blocks of a tile round-robin; one elected lane executes each tcgen05 instruction,
+    // so the descriptors live in uniform registers.
+    const int mw = warp - 1;
     // instruction descriptor: D=f32, A=B=tf32, K-major both, N = N3, M = 128 (cute::UMMA::InstrDescriptor)
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N3 >> 3) << 17) | ((128u >> 4) << 24);
     const bool leader = elect_one();  // elected once: the issue loop must stay a handful of instructions per MMA
-    uint32_t tcount = 0;
-    int st = 0;
-    uint32_t ph = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
-      const int as = tcount & 1;
-      const uint32_t aph = (tcount >> 1) & 1;
+    int it = 0;
+    for (int k = 0;; ++k) {
+      const int tile = blockIdx.x + k * gridDim.x;
+      if (tile >= ntiles) break;
+      const int as = k & 1;
+      const uint32_t aph = (k >> 1) & 1;
       mbar_wait(tempty_bar(as), aph ^ 1);  // the epilogue has drained this accumulator buffer
       tc_fence_after();
       const uint32_t d0 = tmem_base + (uint32_t)(as * acc_cols);
-      for (int c = 0; c < a.nchunks; ++c) {
+      for (int c = 0; c < a.nchunks; ++c, ++it) {
         const TcChunk& ch = a.chunks[c];
+        const int st = it % nst;
+        const uint32_t ph = (uint32_t)(it / nst) & 1;
         mbar_wait(full_bar(st), ph);
         tc_fence_after();
+        if (mw == 0 && lane == 0 && c == 0) stamp(1, k);
         const uint32_t sS = smem_u32(smem + st * stage_bytes);
-        const uint64_t b_base = umma_desc(a.wfmt == 0 ? sS + a.a_bytes : smem_u32(smWres) + ch.w_off, (uint32_t)(N3 * 16), 128, 0);
+        const uint64_t b_base = umma_desc(a.wfmt == 0 ? sS + a.a_bytes : smem_u32(smWres) + ch.w_off, 16, 256, 6);
         for (int ky = 0; ky < 3; ++ky) {
           uint32_t kc = 0;
           for (int r = 0; r < ch.nreg; ++r) {
@@ -319,10 +426,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const __grid_
             const uint32_t mb_step = 6 * rb;  // kBlkPix rows, in 16-byte descriptor units
             const int ksteps = ch.reg[r].cb >> 3;
             for (int ks = 0; ks < ksteps; ++ks, kc += 2) {
-              const uint64_t bd = b_base + (uint64_t)((ky * ch.ncg + kc) * N3);
+              const uint64_t bd = b_base + (uint64_t)((ky * (ch.ncg >> 1) + (kc >> 1)) * N3 * 2);
               uint64_t ad = a_base + (uint64_t)(2 * ks + mw * mb_step);
               uint32_t d = d0 + mw * N3;
               const uint32_t acc = (c | ky | (int)kc) ? 1u : 0u;
+              // blocks innermost: consecutive MMAs write different accumulators
 #pragma unroll 3
               for (int mb = mw; mb < a.nmb; mb += kMmaWarps) {
                 if (leader && !(a.debug & 1)) umma_tf32(d, ad, bd, idesc, acc);
@@ -334,18 +442,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const __grid_
         }
         if (leader) tc_commit(empty_bar(st));  // frees the stage once these MMAs have read it
         __syncwarp();
-        if (++st == nst) { st = 0; ph ^= 1; }
       }
-      if (leader) tc_commit(tfull_bar(as));  // accumulator complete
+      if (leader) tc_commit(tfull_bar(as));  // accumulators complete
       __syncwarp();
+      if (mw == 0 && lane == 0) stamp(2, k);
     }
-  } else if (warp >= kEpiWarp0) {
+  } else {
     // ================= epilogue: TMEM -> registers -> kx realignment -> bias/residual/ReLU/mask -> NHWC global =================
-    // warp e handles TMEM lane quarter (warp % 4) of the MMA blocks mb = set, set+2, ... (set = e / 4).  A unit is
-    // 8 output channels of one block: three tcgen05.ld.x8 (the kx = 0,1,2 column groups), two shuffles per channel.
-    // Two units are fetched per tcgen05.wait::ld and their bias / residual / mask vectors are requested before the
-    // wait.  The loop is issue-bound (measured), so everything that is per-tile or per-thread constant is hoisted:
-    // per-tile base pointers are warp-uniform, per-pixel offsets are 32-bit, (yy, xx) advance without a division.
+    // warp e handles TMEM lane quarter (warp % 4) of the MMA blocks mb = set, set + kEpiSets, ... (set = e / 4).
+    // A unit is 8 output channels of one block: three tcgen05.ld.x8 (the kx = 0,1,2 column groups), two shuffles per
+    // channel.  Two units are fetched per tcgen05.wait::ld and their residual / mask vectors are requested before the
+    // wait.  The loop is issue-bound (measured: ~170 SASS instructions per unit in the first version), so everything
+    // per-tile is warp-uniform, per-pixel offsets are 32-bit, (yy, xx) advance without a division and the bias of an
+    // 8-channel co block lives in registers.
     constexpr int NQ = COLS / 8;
     const int quarter = warp & 3;
     const int set = (warp - kEpiWarp0) >> 2;
@@ -354,11 +463,61 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const __grid_
     const int prow = (R >> 3) * 6 + gi;       // pixel offset of this row inside an MMA block
     const int p0 = set * kBlkPix + prow;
     const int yy0 = p0 / a.PW, xx0 = p0 - yy0 * a.PW;
-    const int step_y = (2 * kBlkPix) / a.PW, step_x = 2 * kBlkPix - step_y * a.PW;  // this warp advances two blocks at a time
+    const int step_y = (kEpiSets * kBlkPix) / a.PW, step_x = kEpiSets * kBlkPix - step_y * a.PW;  // to this warp's next block
     const bool has_mask = a.mask0 != nullptr || a.mask1 != nullptr;
     const bool has_res = a.res != nullptr && !has_mask;
+    const bool has_bias = a.bias != nullptr;
+    const bool bias32 = (reinterpret_cast<uintptr_t>(a.bias) & 31) == 0;  // parameters may sit in a packed arena
     const int relu = a.relu, round_out = a.round_out;
     const int nq_valid = (a.Cout - co_base + 7) / 8 < NQ ? (a.Cout - co_base + 7) / 8 : NQ;  // 8-channel groups of this co block
+    const bool live = gi < 6 && !(a.debug & 2);
+    auto load_bias = [&](int co, float* bb) {
+      if (bias32) {
+        ldg8(a.bias + co, bb);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) bb[j] = __ldg(a.bias + co + j);
+      }
+    };
+    float bias0[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) bias0[j] = 0.f;
+    if (NQ == 1 && has_bias) load_bias(co_base, bias0);
+
+    // kx realignment + fused pointwise tail of one unit
+    auto finish = [&](const uint32_t* v, bool ok, float* dst, bool has_aux, const float* aux, const float* bb) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float e1 = __shfl_down_sync(0xffffffffu, __uint_as_float(v[8 + j]), 1);
+        const float e2 = __shfl_down_sync(0xffffffffu, __uint_as_float(v[16 + j]), 2);
+        o[j] = (__uint_as_float(v[j]) + e1) + e2;
+      }
+      if (!ok) return;
+      if (has_bias) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] += bb[j];
+      }
+      if (has_aux) {
+        if (has_mask) {  // dgrad: ReLU mask of the layer that produced this source
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = aux[j] > 0.f ? o[j] : 0.f;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] += aux[j];
+        }
+      }
+      if (relu) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
+      }
+      if (round_out) {  // round-to-nearest (ties away) to TF32, same result as cvt.rna.tf32.f32 for finite values
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = __uint_as_float((__float_as_uint(o[j]) + 0x1000u) & 0xffffe000u);
+      }
+      stg8(dst, o);
+    };
+
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
       const int b = tile / tiles_per_img;
@@ -366,136 +525,115 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const __grid_
       const int ty = tr / a.tilesX, tx = tr - ty * a.tilesX;
       const int x0 = tx * a.TW, y0 = ty * a.TH;
       const int ymax = (a.H - y0) < a.TH ? (a.H - y0) : a.TH, xmax = (a.W - x0) < a.TW ? (a.W - x0) : a.TW;
-      // warp-uniform bases of this tile in every tensor the epilogue touches
-      float* const d0b = a.d0.p + (((size_t)b * a.d0.Hs + (y0 + a.d0.oy)) * a.d0.Ws + (x0 + a.d0.ox)) * a.d0.C;
-      float* const d1b = a.d1.p == nullptr ? nullptr : a.d1.p + (((size_t)b * a.d1.Hs + (y0 + a.d1.oy)) * a.d1.Ws + (x0 + a.d1.ox)) * a.d1.C;
-      const ptrdiff_t m0d = a.mask0 == nullptr ? 0 : a.mask0 - a.d0.p;  // masks share the geometry of their destination
-      const ptrdiff_t m1d = a.mask1 == nullptr ? 0 : a.mask1 - a.d1.p;
+      // warp-uniform bases of this tile in every tensor the epilogue touches (masks share their destination's geometry)
+      const size_t o0 = (((size_t)b * a.d0.Hs + (y0 + a.d0.oy)) * a.d0.Ws + (x0 + a.d0.ox)) * a.d0.C;
+      const size_t o1 = a.d1.p == nullptr ? 0 : (((size_t)b * a.d1.Hs + (y0 + a.d1.oy)) * a.d1.Ws + (x0 + a.d1.ox)) * a.d1.C;
+      float* const d0b = a.d0.p + o0;
+      float* const d1b = a.d1.p == nullptr ? nullptr : a.d1.p + o1;
+      const float* const m0b = a.mask0 == nullptr ? nullptr : a.mask0 + o0;
+      const float* const m1b = a.mask1 == nullptr ? nullptr : a.mask1 + o1;
       const float* const rsb = has_res ? a.res + (((size_t)b * a.H + y0) * a.W + x0) * a.Cout + co_base : nullptr;
       const int as = tcount & 1;
-      const uint32_t aph = (tcount >> 1) & 1;
-      mbar_wait(tfull_bar(as), aph);
+      mbar_wait(tfull_bar(as), (tcount >> 1) & 1);
       tc_fence_after();
+      if (warp == kEpiWarp0 && lane == 0) stamp(3, tcount);
       const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * acc_cols);
-
-      // one pair of units: (taddr, ok, dst, aux source, bias source) x 2; unit B may be absent (warp-uniform)
-      auto pair = [&](uint32_t tA, bool okA, float* dA, const float* xA, const float* bA, bool haveB, uint32_t tB, bool okB, float* dB,
-                      const float* xB, const float* bB) {
-        uint32_t v[2][24];
-        float aux[2][8], bias[2][8];
-        tmem_ld8(tA, v[0]);
-        tmem_ld8(tA + COLS, v[0] + 8);
-        tmem_ld8(tA + 2 * COLS, v[0] + 16);
-        if (haveB) {
-          tmem_ld8(tB, v[1]);
-          tmem_ld8(tB + COLS, v[1] + 8);
-          tmem_ld8(tB + 2 * COLS, v[1] + 16);
-        }
-        if (bA != nullptr) {  // parameters may live in a packed arena: only 4-byte alignment is guaranteed
-          if (okA) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) bias[0][j] = __ldg(bA + j);
-          }
-          if (haveB && okB) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) bias[1][j] = __ldg(bB + j);
-          }
-        }
-        if (xA != nullptr && okA) ldg8(xA, aux[0]);
-        if (haveB && xB != nullptr && okB) ldg8(xB, aux[1]);
-        tmem_ld_wait();
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-          if (k == 1 && !haveB) break;  // warp-uniform: the shuffles below need the whole warp
-          const bool ok = k == 0 ? okA : okB;
-          float* const dst = k == 0 ? dA : dB;
-          const bool has_aux = (k == 0 ? xA : xB) != nullptr;
-          float o[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float e1 = __shfl_down_sync(0xffffffffu, __uint_as_float(v[k][8 + j]), 1);
-            const float e2 = __shfl_down_sync(0xffffffffu, __uint_as_float(v[k][16 + j]), 2);
-            o[j] = (__uint_as_float(v[k][j]) + e1) + e2;
-          }
-          if (!ok) continue;
-          if (bA != nullptr) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] += bias[k][j];
-          }
-          if (has_aux) {
-            if (has_mask) {  // dgrad: ReLU mask of the layer that produced this source
-#pragma unroll
-              for (int j = 0; j < 8; ++j) o[j] = aux[k][j] > 0.f ? o[j] : 0.f;
-            } else {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) o[j] += aux[k][j];
-            }
-          }
-          if (relu) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
-          }
-          if (round_out) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = round_tf32(o[j]);
-          }
-          stg8(dst, o);
-        }
-      };
-      // per-unit operands: q selects the destination tensor (warp-uniform), (yy, xx) the pixel (per lane)
-      struct Unit { uint32_t t; bool ok; float* d; const float* x; const float* bsrc; };
-      auto unit = [&](int mb, int q, int yy, int xx) {
-        Unit un;
-        un.t = tbase + (uint32_t)(mb * N3 + 8 * q);
-        un.ok = gi < 6 && yy < ymax && xx < xmax && q < nq_valid && !(a.debug & 2);
-        const int co = co_base + 8 * q;
-        const bool first = co < a.d0.C;
-        const int off = first ? (yy * a.d0.Ws + xx) * a.d0.C + co : (yy * a.d1.Ws + xx) * a.d1.C + (co - a.d0.C);
-        un.d = (first ? d0b : d1b) + off;
-        un.x = nullptr;
-        if (has_mask) {
-          if ((first ? a.mask0 : a.mask1) != nullptr) un.x = un.d + (first ? m0d : m1d);
-        } else if (has_res) {
-          un.x = rsb + (yy * a.W + xx) * a.Cout + 8 * q;
-        }
-        un.bsrc = a.bias == nullptr ? nullptr : a.bias + co;
-        return un;
-      };
       int yy = yy0, xx = xx0;
       auto advance = [&]() {
         yy += step_y;
         xx += step_x;
         if (xx >= a.PW) { xx -= a.PW; ++yy; }
       };
-      if (NQ == 1) {
-        for (int mb = set; mb < a.nmb; mb += 4) {  // two of this warp's blocks per TMEM wait
-          const Unit ua = unit(mb, 0, yy, xx);
+      if (a.debug & 128) {
+        // (experiment) no TMEM reads at all
+      } else if (NQ == 1) {
+        // 8-channel co block: everything goes to d0; two of this warp's blocks per TMEM wait
+        const bool has_aux = has_mask ? m0b != nullptr : has_res;
+        const float* const xb = has_mask ? m0b : rsb;
+        const int xs_y = has_mask ? a.d0.Ws * a.d0.C : a.W * a.Cout, xs_x = has_mask ? a.d0.C : a.Cout;
+        for (int mb = set; mb < a.nmb; mb += 2 * kEpiSets) {
+          uint32_t v[2][24];
+          float aux[2][8];
+          const bool okA = live && yy < ymax && xx < xmax;
+          const int offA = (yy * a.d0.Ws + xx) * a.d0.C, xoA = yy * xs_y + xx * xs_x;
           advance();
-          const bool haveB = mb + 2 < a.nmb;
-          const Unit ub = unit(mb + 2, 0, yy, xx);
+          const bool haveB = mb + kEpiSets < a.nmb;
+          const bool okB = haveB && live && yy < ymax && xx < xmax;
+          const int offB = (yy * a.d0.Ws + xx) * a.d0.C, xoB = yy * xs_y + xx * xs_x;
           advance();
-          pair(ua.t, ua.ok, ua.d, ua.x, ua.bsrc, haveB, ub.t, ub.ok, ub.d, ub.x, ub.bsrc);
+          const uint32_t tA = tbase + (uint32_t)(mb * N3);
+          tmem_ld8(tA, v[0]);
+          tmem_ld8(tA + COLS, v[0] + 8);
+          tmem_ld8(tA + 2 * COLS, v[0] + 16);
+          if (haveB) {
+            const uint32_t tB = tA + (uint32_t)(kEpiSets * N3);
+            tmem_ld8(tB, v[1]);
+            tmem_ld8(tB + COLS, v[1] + 8);
+            tmem_ld8(tB + 2 * COLS, v[1] + 16);
+          }
+          if (has_aux) {
+            if (okA) ldg8(xb + xoA, aux[0]);
+            if (okB) ldg8(xb + xoB, aux[1]);
+          }
+          tmem_ld_wait();
+          finish(v[0], okA, d0b + offA, has_aux, aux[0], bias0);
+          if (haveB) finish(v[1], okB, d0b + offB, has_aux, aux[1], bias0);
         }
       } else {
-        for (int mb = set; mb < a.nmb; mb += 2) {
+        for (int mb = set; mb < a.nmb; mb += kEpiSets) {
+          const bool ok = live && yy < ymax && xx < xmax;
+          const int off0 = (yy * a.d0.Ws + xx) * a.d0.C;
+          const int off1 = d1b == nullptr ? 0 : (yy * a.d1.Ws + xx) * a.d1.C;
+          const int offr = (yy * a.W + xx) * a.Cout;
+          advance();
 #pragma unroll
           for (int q = 0; q < NQ; q += 2) {
-            const Unit ua = unit(mb, q, yy, xx);
-            const Unit ub = unit(mb, q + 1, yy, xx);
-            pair(ua.t, ua.ok, ua.d, ua.x, ua.bsrc, true, ub.t, ub.ok, ub.d, ub.x, ub.bsrc);
+            uint32_t v[2][24];
+            float aux[2][8], bb[2][8];
+            const uint32_t tA = tbase + (uint32_t)(mb * N3 + 8 * q);
+            tmem_ld8(tA, v[0]);
+            tmem_ld8(tA + COLS, v[0] + 8);
+            tmem_ld8(tA + 2 * COLS, v[0] + 16);
+            tmem_ld8(tA + 8, v[1]);
+            tmem_ld8(tA + 8 + COLS, v[1] + 8);
+            tmem_ld8(tA + 8 + 2 * COLS, v[1] + 16);
+            float* dst[2];
+            bool okq[2], has_aux[2];
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              const int co = co_base + 8 * (q + k);  // warp-uniform: which destination tensor this channel group belongs to
+              const bool first = co < a.d0.C;
+              okq[k] = ok && (q + k) < nq_valid;
+              dst[k] = first ? d0b + off0 + co : d1b + off1 + (co - a.d0.C);
+              const float* xp = has_mask ? (first ? (m0b == nullptr ? nullptr : m0b + off0 + co) : (m1b == nullptr ? nullptr : m1b + off1 + (co - a.d0.C)))
+                                         : (has_res ? rsb + offr + 8 * (q + k) : nullptr);
+              has_aux[k] = xp != nullptr;
+              if (has_aux[k] && okq[k]) ldg8(xp, aux[k]);
+              if (has_bias && okq[k]) load_bias(co, bb[k]);
+            }
+            tmem_ld_wait();
+            finish(v[0], okq[0], dst[0], has_aux[0], aux[0], bb[0]);
+            finish(v[1], okq[1], dst[1], has_aux[1], aux[1], bb[1]);
           }
-          advance();
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty_bar(as)) : "memory");
+      if (warp == kEpiWarp0 && lane == 0) stamp(4, tcount);
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) {
+  if (tracing && tid == 0) {
+    const long long t_end = clock64() - t_start;
+    const int nt = (ntiles - 1) / (int)gridDim.x + 1;
+    printf("tc trace (cycles): kernel %lld (prologue %lld), %d tiles on CTA 0; per tile: loads issued | data landed | MMAs issued | acc ready | epilogue done\n", t_end, trace[60], nt);
+    for (int k = 0; k < nt && k < 12; ++k)
+      printf("  tile %2d: %7lld %7lld %7lld %7lld %7lld \n", k, trace[k], trace[12 + k], trace[24 + k], trace[36 + k], trace[48 + k]);
+  }
+  if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)a.tmem_cols) : "memory");
   }
 }
@@ -609,7 +747,7 @@ static bool tc_plan(int B, int H, int W, int C0, int C1, int Cout, TcPlan* p, bo
     p->w_res_bytes = (int)((p->w_coblk_stride + 127) / 128 * 128);
     p->w_bytes_max = 0;
   }
-  const size_t budget = 222 * 1024 - (size_t)p->w_res_bytes;  // minus barriers and the 1024-byte alignment slack below
+  const size_t budget = 220 * 1024 - (size_t)p->w_res_bytes;  // minus barriers and the 1024-byte alignment slack below
   const int nmb_max = 256 / p->n3;  // two accumulator buffers of <= 256 TMEM columns
   auto stage_a_bytes = [&](int th, int pw, int nmb) {
     // rows a region must hold: the halo tile, and whatever the last MMA block's shifted reads touch beyond it
@@ -674,7 +812,7 @@ static bool tc_plan(int B, int H, int W, int C0, int C1, int Cout, TcPlan* p, bo
   p->nstages = (int)(budget / stage);
   if (p->nstages > kMaxStages) p->nstages = kMaxStages;
   p->tmem_cols = next_pow2_cols(2 * p->nmb * p->n3);
-  p->smem_bytes = (size_t)p->nstages * stage + p->w_res_bytes + 256 + 1024;
+  p->smem_bytes = (size_t)p->nstages * stage + p->w_res_bytes + 256 + 2048 + 1024;  // barriers, k-group table + trace, alignment
   return p->nstages >= 2 && p->tmem_cols <= 512;
 }
 

@@ -25,12 +25,12 @@ class TrainStep:
         self.betas, self.eps = betas, eps
         params = [p for p in net.parameters()]
         total = sum(p.numel() for p in params)
-        # ---- flat arenas (16-byte aligned slots)
+        # ---- flat arenas (32-byte aligned slots: the conv epilogues read biases with 256-bit loads)
         self.offsets = []
         off = 0
         for p in params:
             self.offsets.append(off)
-            off += (p.numel() + 3) // 4 * 4
+            off += (p.numel() + 7) // 8 * 8
         self.n_flat = off
         self.flat_p = torch.zeros(off, device=self.dev)
         self.flat_g = torch.zeros(off, device=self.dev)
