@@ -42,6 +42,9 @@ typedef enum {
 #define PU_FLAG_MASK_IN 4    /* backward kernels: zero the input gradient where the op's input x <= 0, i.e. apply the
                                 ReLU mask of the PRODUCER of x (premasked-gradient protocol)          */
 
+#define PU_FLAG_TF32_MATH 8  /* transposed convolutions: TF32 tensor-core math (mma.sync), fp32 accumulate; the model's TF32
+                                mode.  Without it (or for unsupported shapes) the fp32 CUDA-core kernels run.            */
+
 /* conv3x3 weight operand formats */
 #define PU_W_PACKED 0
 #define PU_W_OIHW 1

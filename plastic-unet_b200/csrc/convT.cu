@@ -496,6 +496,14 @@ static int split_for(long long nout_blocks, long long npix) {
   return (int)want;
 }
 
+// convT_mma.cu
+bool convT2x2_mma_ok(const float* x, const float* dy_or_y, int Cin, int Cout, long long npix);
+int convT2x2_fwd_mma(const float* x, const float* w, const float* bias, float* y, int B, int H, int W, int Cin, int Cout, int round_out,
+                     cudaStream_t st);
+int convT2x2_dx_mma(const float* x, const float* w, const float* dy, float* dx, int B, int H, int W, int Cin, int Cout, int mask_in,
+                    cudaStream_t st);
+int convT2x2_dw_mma(const float* x, const float* dy, float* dw, float* db, int B, int H, int W, int Cin, int Cout, cudaStream_t st);
+
 }  // namespace pu
 
 extern "C" {
@@ -506,6 +514,8 @@ int pu_convT2x2s2_fwd(const float* x, const float* w, const float* bias, float* 
   const size_t smem = (size_t)4 * Cin * 8 * sizeof(float);
   PU_REQUIRE(smem <= 48 * 1024, PU_ERR_UNSUPPORTED, "pu_convT2x2s2_fwd: Cin=%d > 384", Cin);
   PU_REQUIRE(pu::aligned16(x) && pu::aligned16(y), PU_ERR_BAD_ARG, "pu_convT2x2s2_fwd: pointers not 16-byte aligned");
+  if ((flags & PU_FLAG_TF32_MATH) && pu::convT2x2_mma_ok(x, y, Cin, Cout, (long long)B * H * W))
+    return pu::convT2x2_fwd_mma(x, w, bias, y, B, H, W, Cin, Cout, (flags & PU_FLAG_ROUND_TF32) ? 1 : 0, pu::as_stream(stream));
   const long long npix = (long long)B * 4 * H * W;
   dim3 grid((unsigned)((npix + 255) / 256), pu::cdiv(Cout, 8));
   pu::convT2x2_fwd_kernel<<<grid, 256, smem, pu::as_stream(stream)>>>(x, w, bias, y, B, H, W, Cin, Cout, flags);
@@ -517,6 +527,24 @@ int pu_convT2x2s2_bwd(const float* x, const float* w, const float* dy, float* dx
   PU_REQUIRE(x && w && dy && B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, PU_ERR_BAD_ARG, "pu_convT2x2s2_bwd: bad argument");
   cudaStream_t st = pu::as_stream(stream);
   const long long npix = (long long)B * H * W;
+  const bool mma = (flags & PU_FLAG_TF32_MATH) && pu::convT2x2_mma_ok(x, dy, Cin, Cout, npix) && (dx == nullptr || pu::aligned16(dx));
+  if (mma) {
+    if (dx != nullptr) {
+      int rc = pu::convT2x2_dx_mma(x, w, dy, dx, B, H, W, Cin, Cout, (flags & PU_FLAG_MASK_IN) ? 1 : 0, st);
+      if (rc) return rc;
+    }
+    if (dw != nullptr) {
+      cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * Cin * Cout * 4, st);
+      if (e == cudaSuccess && db != nullptr) e = cudaMemsetAsync(db, 0, sizeof(float) * Cout, st);
+      if (e != cudaSuccess) {
+        pu::set_error("pu_convT2x2s2_bwd memset: %s", cudaGetErrorString(e));
+        return PU_ERR_CUDA;
+      }
+      return pu::convT2x2_dw_mma(x, dy, dw, db, B, H, W, Cin, Cout, st);
+    }
+    if (db != nullptr) return pu::launch_bias_grad(dy, nullptr, db, B, 4LL * H * W, Cout, st);
+    return PU_OK;
+  }
   if (dx != nullptr) {
     const size_t smem = (size_t)4 * Cout * 8 * sizeof(float);
     PU_REQUIRE(smem <= 48 * 1024, PU_ERR_UNSUPPORTED, "pu_convT2x2s2_bwd: Cout=%d > 384", Cout);

@@ -21,6 +21,7 @@ RULE_OJA = 1
 FLAG_RELU = 1
 FLAG_ROUND_TF32 = 2
 FLAG_MASK_IN = 4
+FLAG_TF32_MATH = 8
 
 
 @functools.lru_cache(maxsize=None)
@@ -280,7 +281,7 @@ def convT2x2s2(x: Tensor, weight: Tensor, bias: Optional[Tensor], round_out: boo
     Cout = weight.shape[1]
     y = torch.empty((B, 2 * H, 2 * W, Cout), device=x.device, dtype=torch.float32)
     _lib.call("pu_convT2x2s2_fwd", x.data_ptr(), weight.data_ptr(), _p(bias), y.data_ptr(), B, H, W, Cin, Cout,
-              FLAG_ROUND_TF32 if round_out else 0, _s())
+              (FLAG_ROUND_TF32 | FLAG_TF32_MATH) if round_out else 0, _s())  # round_out == the model's TF32 mode
     return y
 
 
@@ -291,7 +292,7 @@ def _(x, weight, bias, round_out=False, mask_in=False):
 
 @torch.library.custom_op("pu::convT2x2s2_bwd", mutates_args=())
 def convT2x2s2_bwd(dy: Tensor, x: Tensor, weight: Tensor, need_dx: bool, need_dw: bool, need_db: bool,
-                   mask_in: bool = False) -> List[Tensor]:
+                   mask_in: bool = False, tf32: bool = False) -> List[Tensor]:
     _chk(dy, x, weight)
     B, H, W, Cin = x.shape
     Cout = weight.shape[1]
@@ -300,28 +301,29 @@ def convT2x2s2_bwd(dy: Tensor, x: Tensor, weight: Tensor, need_dx: bool, need_dw
     db = torch.empty(Cout, device=x.device, dtype=torch.float32) if need_db else _e(x.device)
     _lib.call("pu_convT2x2s2_bwd", x.data_ptr(), weight.data_ptr(), dy.data_ptr(), dx.data_ptr() if need_dx else None,
               dw.data_ptr() if need_dw else None, db.data_ptr() if need_db else None, B, H, W, Cin, Cout,
-              FLAG_MASK_IN if mask_in else 0, _s())
+              (FLAG_MASK_IN if mask_in else 0) | (FLAG_TF32_MATH if tf32 else 0), _s())
     return [dx, dw, db]
 
 
 @convT2x2s2_bwd.register_fake
-def _(dy, x, weight, need_dx, need_dw, need_db, mask_in=False):
+def _(dy, x, weight, need_dx, need_dw, need_db, mask_in=False, tf32=False):
     e = x.new_empty(0)
     return [torch.empty_like(x) if need_dx else e, torch.empty_like(weight) if need_dw else e,
             x.new_empty(weight.shape[1]) if need_db else e]
 
 
 def _convT2_setup(ctx, inputs, output):
-    x, weight, bias, _round, mask_in = inputs
+    x, weight, bias, round_out, mask_in = inputs
     ctx.save_for_backward(x, weight)
     ctx.has_bias = bias is not None
     ctx.mask_in = mask_in
+    ctx.tf32 = bool(round_out)
 
 
 def _convT2_backward(ctx, dy):
     x, weight = ctx.saved_tensors
     need = ctx.needs_input_grad
-    dx, dw, db = convT2x2s2_bwd(dy.contiguous(), x, weight, need[0], need[1], ctx.has_bias and need[2], ctx.mask_in)
+    dx, dw, db = convT2x2s2_bwd(dy.contiguous(), x, weight, need[0], need[1], ctx.has_bias and need[2], ctx.mask_in, ctx.tf32)
     return dx if need[0] else None, dw if need[1] else None, db if (ctx.has_bias and need[2]) else None, None, None
 
 

@@ -159,6 +159,41 @@ def test_convT2x2s2(Cin, Cout, H, W):
     check(bo.grad, br.grad, 5 * TOL, what="db")
 
 
+@pytest.mark.parametrize("C,H,W,B,mask", [(8, 64, 64, 3, False), (16, 32, 32, 2, True), (32, 16, 16, 2, False), (64, 8, 8, 5, True),
+                                          (8, 5, 7, 1, False), (64, 3, 3, 1, False)])
+def test_convT2x2s2_tf32_mma(C, H, W, B, mask):
+    """TF32 tensor-core path (convT_mma.cu: forward, dgrad with the producer's ReLU mask, wgrad + bias gradient) of
+    nn.ConvTranspose2d(C, C, 2, stride=2), unet_p.py:155.  Operands are rounded to TF32 (10-bit mantissa, RN) and
+    accumulated in fp32, so the bound is 2e-3 of the tensor's max instead of the fp32 path's 1e-3 relative."""
+    from pu_b200 import ops
+    g = torch.Generator().manual_seed(C + H)
+    x = torch.randn(B, C, H, W, generator=g)
+    if mask:
+        x = x.relu()
+    w = torch.randn(C, C, 2, 2, generator=g) / C ** 0.5
+    b = torch.randn(C, generator=g)
+    R = torch.randn(B, C, 2 * H, 2 * W, generator=g)
+    xr, wr, br = (leaf(t, "cpu", torch.float64) for t in (x, w, b))
+    yr = F.conv_transpose2d(xr, wr, br, stride=2)
+    (yr * R.double()).sum().backward()
+    dx_ref = xr.grad * (x > 0).double() if mask else xr.grad
+    xo, wo, bo = leaf(nhwc(x)), leaf(w), leaf(b)
+    yo = ops.convT2x2s2(xo, wo, bo, True, mask)
+    (yo * nhwc(R).to(DEV)).sum().backward()
+
+    def close(got, ref, what):
+        err = (got.detach().cpu().double() - ref).abs().max().item() / max(ref.abs().max().item(), 1e-30)
+        assert err < 2e-3, "%s: max err / max |ref| = %g" % (what, err)
+
+    close(nchw(yo), yr, "y")
+    close(nchw(xo.grad), dx_ref, "dx")
+    close(wo.grad, wr.grad, "dw")
+    close(bo.grad, br.grad, "db")
+    # the stored output is exactly representable in TF32 (PU_FLAG_ROUND_TF32)
+    bits = yo.detach().view(torch.int32)
+    assert int((bits & 0x1FFF).abs().max()) == 0
+
+
 @pytest.mark.parametrize("Cin,Cout,H,W,crop,scaled", [(16, 8, 6, 6, (1, 1), False), (32, 16, 12, 12, (0, 0), True),
                                                        (8, 4, 25, 25, (1, 1), True), (64, 32, 3, 3, (0, 1), False)])
 def test_convT3x3s2_cropped(Cin, Cout, H, W, crop, scaled):
