@@ -539,14 +539,19 @@ __device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], unsigned a0, unsi
                : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-template <int TW, int TH>
+// NCO = 8-channel co tiles per CTA (1, 2 or 4): the A fragments of an 8-pixel group (18 LDS: nine shifted windows of the
+// x halo tile) are reused for NCO x 5 MMAs, and the x tile is re-read Cout/(8*NCO) times instead of Cout/8 times
+// (with NCO = 1 the wide layers were L2-bandwidth bound: 270 MB of L2 reads for a 42 MB problem).
+template <int TW, int TH, int NCO>
 __global__ void __launch_bounds__(256, 2) conv3x3_wgrad_mma_kernel(const WgradArgs a) {
   constexpr int HW_ = TW + 2, HH_ = TH + 2;
   constexpr int XPIX = HH_ * HW_, GPIX = TH * TW;
-  constexpr int STAGE_F = (XPIX + GPIX) * 8;
+  constexpr int GP = NCO == 1 ? 8 : 8 * NCO + 8;  // g-tile pixel pitch: == 8 (mod 32) or 8/24 -> B-fragment reads conflict-free
+  constexpr int STAGE_F = XPIX * 8 + GPIX * GP;
   constexpr int GROUPS = TH * (TW / 8);  // 8-pixel groups (along x) per tile
+  constexpr int NACC = 20 * NCO;
   extern __shared__ __align__(16) float dsm[];  // [2][STAGE_F]; the reduction buffer aliases it at the end
-  static_assert(2 * STAGE_F >= 8 * 32 * 20, "reduction buffer must fit in the staging ring");
+  static_assert(2 * STAGE_F >= 8 * 32 * NACC, "reduction buffer must fit in the staging ring");
 
   pdl_prologue();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -557,7 +562,7 @@ __global__ void __launch_bounds__(256, 2) conv3x3_wgrad_mma_kernel(const WgradAr
   const int cbase = cchunk < nchunk0 ? 0 : a.s0.C;
   if (cchunk >= nchunk0) cchunk -= nchunk0;
   const int c0 = cchunk * 8;
-  const int co0 = blockIdx.z * 8;
+  const int co0 = blockIdx.z * 8 * NCO;
 
   auto issue = [&](int tile, int stage) {
     int t = tile;
@@ -577,24 +582,26 @@ __global__ void __launch_bounds__(256, 2) conv3x3_wgrad_mma_kernel(const WgradAr
       const unsigned dst = (unsigned)__cvta_generic_to_shared(xs + pix * 8 + half * 4);
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16 : 0) : "memory");
     }
-    for (int i = tid; i < GPIX * 2; i += 256) {
-      const int pix = i >> 1, half = i & 1;
+    for (int i = tid; i < GPIX * 2 * NCO; i += 256) {
+      const int pix = i / (2 * NCO), q = i - pix * (2 * NCO);  // q: 16-byte unit inside the pixel's 8*NCO channels
       const int yy = pix / TW, xx = pix - yy * TW;
       const int gy = y0 + yy, gx = x0 + xx;
       const bool ok = gy < a.H && gx < a.W;
-      const float* src = ok ? a.g + (((size_t)b * a.H + gy) * a.W + gx) * a.Cout + co0 + half * 4 : a.g;
-      const unsigned dst = (unsigned)__cvta_generic_to_shared(gs + pix * 8 + half * 4);
+      const float* src = ok ? a.g + (((size_t)b * a.H + gy) * a.W + gx) * a.Cout + co0 + q * 4 : a.g;
+      const unsigned dst = (unsigned)__cvta_generic_to_shared(gs + pix * GP + q * 4);
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16 : 0) : "memory");
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
 
-  // accumulators of the 5 tap-pair tiles: acc[p] = {(tap 2p, ci=gq, co=2tq), (tap 2p, gq, 2tq+1), (tap 2p+1, ...), ...}
-  float acc[5][4];
+  // accumulators of the 5 tap-pair tiles per co tile: acc[n][p] = {(tap 2p, ci=gq, co=8n+2tq), (tap 2p, gq, +1), (tap 2p+1, ...), ...}
+  float acc[NCO][5][4];
 #pragma unroll
-  for (int p = 0; p < 5; ++p)
+  for (int n = 0; n < NCO; ++n)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[p][j] = 0.f;
+    for (int p = 0; p < 5; ++p)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[n][p][j] = 0.f;
 
   int stage = 0;
   if ((int)blockIdx.x < a.ntiles) issue(blockIdx.x, 0);
@@ -611,9 +618,6 @@ __global__ void __launch_bounds__(256, 2) conv3x3_wgrad_mma_kernel(const WgradAr
     const unsigned* gs = xs + XPIX * 8;
     for (int grp = warp; grp < GROUPS; grp += 8) {
       const int yy = grp / (TW / 8), xg = (grp - yy * (TW / 8)) * 8;
-      // B fragment: k = pixel (tq, tq+4), n = co (gq)
-      const unsigned b0 = gs[(yy * TW + xg + tq) * 8 + gq];
-      const unsigned b1 = gs[(yy * TW + xg + tq + 4) * 8 + gq];
       // A fragments: row = (tap within pair, ci = gq), col = pixel (tq, tq+4); the halo tile is offset by (+1,+1)
       const unsigned* xr = xs + ((yy * HW_) + xg + tq) * 8 + gq;
       unsigned av[9][2];
@@ -625,29 +629,38 @@ __global__ void __launch_bounds__(256, 2) conv3x3_wgrad_mma_kernel(const WgradAr
           av[ky * 3 + kx][1] = xr[(ky * HW_ + kx + 4) * 8];
         }
 #pragma unroll
-      for (int p = 0; p < 4; ++p) mma_tf32_16x8x8(acc[p], av[2 * p][0], av[2 * p + 1][0], av[2 * p][1], av[2 * p + 1][1], b0, b1);
-      // rows 8..15 of the fifth tile are free: feeding ones there makes them the column sums of G = the bias gradient
-      mma_tf32_16x8x8(acc[4], av[8][0], 0x3f800000u, av[8][1], 0x3f800000u, b0, b1);
+      for (int n = 0; n < NCO; ++n) {
+        // B fragment: k = pixel (tq, tq+4), n = co (gq)
+        const unsigned b0 = gs[(yy * TW + xg + tq) * GP + 8 * n + gq];
+        const unsigned b1 = gs[(yy * TW + xg + tq + 4) * GP + 8 * n + gq];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) mma_tf32_16x8x8(acc[n][p], av[2 * p][0], av[2 * p + 1][0], av[2 * p][1], av[2 * p + 1][1], b0, b1);
+        // rows 8..15 of the fifth tile are free: feeding ones there makes them the column sums of G = the bias gradient
+        mma_tf32_16x8x8(acc[n][4], av[8][0], 0x3f800000u, av[8][1], 0x3f800000u, b0, b1);
+      }
     }
     __syncthreads();
   }
 
   // ---- reduce the 8 warps, then one atomic per output
-  float* red = dsm;  // [8 warps][32 lanes][20]
+  float* red = dsm;  // [8 warps][32 lanes][NACC]
   __syncthreads();
 #pragma unroll
-  for (int p = 0; p < 5; ++p)
+  for (int n = 0; n < NCO; ++n)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) red[(warp * 32 + lane) * 20 + p * 4 + j] = acc[p][j];
+    for (int p = 0; p < 5; ++p)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) red[(warp * 32 + lane) * NACC + n * 20 + p * 4 + j] = acc[n][p][j];
   __syncthreads();
-  for (int i = tid; i < 32 * 20; i += 256) {
+  for (int i = tid; i < 32 * NACC; i += 256) {
     float sum = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) sum += red[w * 640 + i];
-    const int ln = i / 20, r = i - ln * 20;
-    const int p = r >> 2, j = r & 3;
+    for (int w = 0; w < 8; ++w) sum += red[w * 32 * NACC + i];
+    const int ln = i / NACC, r = i - ln * NACC;
+    const int n = r / 20, r2 = r - n * 20;
+    const int p = r2 >> 2, j = r2 & 3;
     const int tap = 2 * p + (j >> 1);
-    const int ci_ = ln >> 2, co = co0 + 2 * (ln & 3) + (j & 1);
+    const int ci_ = ln >> 2, co = co0 + 8 * n + 2 * (ln & 3) + (j & 1);
     if (tap > 8) {  // the ones rows: every ci_ row holds the same sum_pixels g[.][co]
       if (a.db != nullptr && ci_ == 0 && blockIdx.y == 0) atomicAdd(a.db + co, sum);
       continue;
@@ -780,25 +793,32 @@ int conv3x3_wgrad_ffma(const WgradArgs& a0, cudaStream_t st, int math) {
   }
   if (a.s0.C % 8 == 0 && (!have1 || a.s1.C % 8 == 0) && a.Cout % 8 == 0) {
     if (math == PU_MATH_TF32) {
-      // warp-level TF32 MMAs over the same cp.async ring
-      const size_t smem32 = 2 * ((16 + 2) * (32 + 2) + 16 * 32) * 8 * sizeof(float);
-      const size_t smem16 = 2 * ((16 + 2) * (16 + 2) + 16 * 16) * 8 * sizeof(float);
+      // warp-level TF32 MMAs over the same cp.async ring; NCO co tiles (8 channels each) per CTA
+      const int nco_t = a.Cout % 32 == 0 ? 4 : (a.Cout % 16 == 0 ? 2 : 1);
+      const int ncoz = a.Cout / (8 * nco_t);
+      auto stage_bytes = [](int tw, int th, int n) { return (size_t)2 * ((th + 2) * (tw + 2) * 8 + th * tw * (n == 1 ? 8 : 8 * n + 8)) * sizeof(float); };
       static bool attr = false;
       if (!attr) {
-        cudaFuncSetAttribute(conv3x3_wgrad_mma_kernel<32, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32);
-        cudaFuncSetAttribute(conv3x3_wgrad_mma_kernel<16, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16);
+        cudaFuncSetAttribute(conv3x3_wgrad_mma_kernel<32, 16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes(32, 16, 1));
+        cudaFuncSetAttribute(conv3x3_wgrad_mma_kernel<16, 16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes(16, 16, 1));
+        cudaFuncSetAttribute(conv3x3_wgrad_mma_kernel<16, 16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes(16, 16, 2));
+        cudaFuncSetAttribute(conv3x3_wgrad_mma_kernel<16, 16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes(16, 16, 4));
         attr = true;
       }
-      if (a.W > 16) {
+      if (a.W > 16 && nco_t == 1) {
         a.tilesX = cdiv(a.W, 32); a.tilesY = cdiv(a.H, 16);
         a.ntiles = a.tilesX * a.tilesY * a.B;
-        const int gx = max(1, min(a.ntiles, (2 * kNumSMs) / max(1, nci * nco)));
-        launch_pdl(conv3x3_wgrad_mma_kernel<32, 16>, dim3(gx, nci, nco), dim3(256), smem32, st, a);
+        const int gx = max(1, min(a.ntiles, (2 * kNumSMs) / max(1, nci * ncoz)));
+        launch_pdl(conv3x3_wgrad_mma_kernel<32, 16, 1>, dim3(gx, nci, ncoz), dim3(256), stage_bytes(32, 16, 1), st, a);
       } else {
         a.tilesX = cdiv(a.W, 16); a.tilesY = cdiv(a.H, 16);
         a.ntiles = a.tilesX * a.tilesY * a.B;
-        const int gx = max(1, min(a.ntiles, (4 * kNumSMs) / max(1, nci * nco)));
-        launch_pdl(conv3x3_wgrad_mma_kernel<16, 16>, dim3(gx, nci, nco), dim3(256), smem16, st, a);
+        const int per_sm = nco_t == 4 ? 2 : 4;
+        const int gx = max(1, min(a.ntiles, (per_sm * kNumSMs) / max(1, nci * ncoz)));
+        const dim3 grid(gx, nci, ncoz);
+        if (nco_t == 4) launch_pdl(conv3x3_wgrad_mma_kernel<16, 16, 4>, grid, dim3(256), stage_bytes(16, 16, 4), st, a);
+        else if (nco_t == 2) launch_pdl(conv3x3_wgrad_mma_kernel<16, 16, 2>, grid, dim3(256), stage_bytes(16, 16, 2), st, a);
+        else launch_pdl(conv3x3_wgrad_mma_kernel<16, 16, 1>, grid, dim3(256), stage_bytes(16, 16, 1), st, a);
       }
       return post_launch("conv3x3_wgrad_mma");
     }
