@@ -210,9 +210,17 @@ def dominant_kernel_roofline(batch, size, math, dev, hbm_peak, peak_src):
     ms = e0.elapsed_time(e1) / (iters * reps)
     # one kernel per op call (the weight tiles are built inside the conv kernel)
     alg_bytes = batch * size * size * (C0 + C1 + Cout) * 4
+    # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed `ncu --set full` capture
+    # (profiles/r1_tc_conv_ncu_summary.md, B = 64 @128x128, TF32 kernel): 67.16 MB read (= the algorithmic input, read
+    # once) + 6.59 MB written inside the kernel window; the rest of the 33.55 MB output leaves L2 after the kernel ends.
+    traffic, traffic_note = None, None
+    if math and batch == 64 and size == 128:
+        traffic = 67162368 + 6587904
+        traffic_note = "ncu capture of round 1 (profiles/r1_tc_conv_ncu_summary.md); output write-back continues after the kernel window"
     achieved = alg_bytes / (ms * 1e-3) / 1e9
     return {"bound": "hbm", "kernel": "conv3x3 fwd 16->8 @%dx%d (up4.0, %s)" % (size, size, "tf32 tcgen05" if math else "fp32 ffma"),
-            "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+            "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
+            "traffic_note": traffic_note,
             "peak_source": peak_src, "us_per_launch": ms * 1e3, "algorithmic_bytes_per_launch": alg_bytes}
 
 
