@@ -27,6 +27,10 @@ struct WgradArgs {
 };
 
 int conv3x3_fwd_ffma(const Conv3x3Args& a, cudaStream_t st);
+// one-input-channel stem (stem.cu)
+bool conv3x3_c1_ok(int Cin, int Cout);
+int conv3x3_c1_fwd(const Conv3x3Args& a, cudaStream_t st);
+int conv3x3_c1_wgrad(const WgradArgs& a, cudaStream_t st);
 int conv3x3_wgrad_ffma(const WgradArgs& a, cudaStream_t st, int math);
 // tcgen05 path (conv3x3_tc.cu); returns PU_ERR_UNSUPPORTED when the shape does not fit it
 int conv3x3_fwd_tc(const Conv3x3Args& a, cudaStream_t st);

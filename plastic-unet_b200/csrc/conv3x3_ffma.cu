@@ -750,6 +750,9 @@ __global__ void relu_bwd_bias_vec4_kernel(const float4* __restrict__ dy, const f
 
 // host-side launchers ---------------------------------------------------------------------------
 int conv3x3_fwd_ffma(const Conv3x3Args& a0, cudaStream_t st) {
+  if (conv3x3_c1_ok(a0.Cin, a0.Cout) && a0.s1.p == nullptr && a0.wfmt == 1 && a0.res == nullptr && a0.d1.p == nullptr &&
+      a0.mask0 == nullptr && a0.d0.C == a0.Cout)
+    return conv3x3_c1_fwd(a0, st);  // streaming stem kernel
   Conv3x3Args a = a0;
   const int cog = cdiv(a.Cout, 8);
   if (a.W > 16) {
@@ -769,6 +772,7 @@ int conv3x3_fwd_ffma(const Conv3x3Args& a0, cudaStream_t st) {
 }
 
 int conv3x3_wgrad_ffma(const WgradArgs& a0, cudaStream_t st, int math) {
+  if (conv3x3_c1_ok(a0.Cin, a0.Cout) && (a0.s1.p == nullptr || a0.s1.C == 0)) return conv3x3_c1_wgrad(a0, st);  // streaming stem kernel (dw + db)
   WgradArgs a = a0;
   cudaError_t e = cudaMemsetAsync(a.dw, 0, sizeof(float) * (size_t)a.Cout * a.Cin * 9, st);
   if (e != cudaSuccess) {

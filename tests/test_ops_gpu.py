@@ -82,6 +82,24 @@ def test_conv3x3_single_source(B, Cin, Cout, H, W, relu, res, bias):
         check(nchw(ro.grad), rr.grad, what="dres")
 
 
+@pytest.mark.parametrize("Cout,H,W,B", [(8, 128, 128, 2), (16, 37, 21, 3)])
+def test_conv3x3_stem_wgrad_with_bias(Cout, H, W, B):
+    """C_in = 1 stem (unet_p.py:124-132): the streaming wgrad kernel also produces the bias gradient when the incoming
+    gradient is already masked (premasked protocol).  fp32 math: 1e-3 relative."""
+    from pu_b200 import ops
+    g = torch.Generator().manual_seed(Cout + H)
+    x = torch.randn(B, H, W, 1, generator=g).to(DEV)
+    w = torch.randn(Cout, 1, 3, 3, generator=g).to(DEV)
+    dy = torch.randn(B, H, W, Cout, generator=g).to(DEV)
+    y = torch.ones_like(dy)
+    _, _, _, dw, db = ops.conv3x3_bwd(dy, y, x, None, w, True, True, H, W, 0, 0, 0, 0, ops.MATH_FP32, False, True, False, False, True)
+    xr = x.cpu().double().permute(0, 3, 1, 2)
+    dyr = dy.cpu().double().permute(0, 3, 1, 2)
+    dwr = torch.nn.grad.conv2d_weight(xr, (Cout, 1, 3, 3), dyr, padding=1)
+    check(dw, dwr, 5 * TOL, what="dw")
+    check(db, dyr.sum(dim=(0, 2, 3)), 5 * TOL, what="db")
+
+
 @pytest.mark.parametrize("C0,C1,H,W,c0,c1", [(8, 8, 32, 32, (0, 0), (0, 0)), (16, 16, 12, 12, (0, 0), (1, 1)),
                                               (4, 12, 25, 25, (3, 2), (0, 0)), (64, 64, 16, 16, (0, 0), (0, 0))])
 def test_conv3x3_two_sources_with_crop(C0, C1, H, W, c0, c1):
