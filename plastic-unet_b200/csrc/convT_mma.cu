@@ -352,6 +352,58 @@ __global__ void __launch_bounds__(256) convT2x2_dw_mma_kernel(const CtArgs a) {
   }
 }
 
+// ---- wgrad for the 8 -> 8 layer at the top of the decoder ---------------------------------------------------------------
+// 8 x 32 outputs from 262 k pixels: the MMA kernel above is synchronisation-bound there (64-pixel stages, 4 MMAs per warp
+// and stage).  Streaming version: thread = (input pixel, 2x2 quadrant): 8 x-values x 8 dy-values -> 64 + 8 partial sums in
+// registers over a strip of pixels, warp-shuffle + shared-memory reduction, one atomic per output and CTA.
+__global__ void __launch_bounds__(128) convT2x2_dw_c8_kernel(const CtArgs a) {
+  float acc[8][8], bacc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    bacc[i] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  }
+  const int q = threadIdx.x & 3;  // quadrant (a, c) = (q >> 1, q & 1): fixed per thread, blockDim.x % 4 == 0
+  const long long nitems = a.npix * 4;
+  for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < nitems; it += (long long)gridDim.x * blockDim.x) {
+    const int p = (int)(it >> 2);
+    int b, hy, wx;
+    ct_split(a, p, b, hy, wx);
+    const float4 x0 = ldg4(a.x + (size_t)p * 8), x1 = ldg4(a.x + (size_t)p * 8 + 4);
+    const float* dp = a.dy + (((size_t)b * 2 * a.H + 2 * hy + (q >> 1)) * 2 * a.W + 2 * wx + (q & 1)) * 8;
+    const float4 g0 = ldg4(dp), g1 = ldg4(dp + 4);
+    const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+    const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(xv[i], gv[j], acc[i][j]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) bacc[j] += gv[j];
+  }
+  // lanes with equal (lane & 3) hold the same quadrant: reduce over lane bits 2..4, then over the warps
+  __shared__ float red[4][4][72];  // [warp][quadrant][ci*8+co | 64+co]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 9; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float v = i < 8 ? acc[i][j] : bacc[j];
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      if (lane < 4) red[warp][lane][i * 8 + j] = v;
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 4 * 72; i += blockDim.x) {
+    const int qq = i / 72, r = i - qq * 72;
+    const float v = red[0][qq][r] + red[1][qq][r] + red[2][qq][r] + red[3][qq][r];
+    if (r < 64) atomicAdd(a.dw + ((size_t)(r >> 3) * 8 + (r & 7)) * 4 + qq, v);  // dw[ci][co][a][c]
+    else if (a.db != nullptr) atomicAdd(a.db + (r - 64), v);
+  }
+}
+
 // ---- host side ---------------------------------------------------------------------------------------------------------
 static int ct_log2(int v) {
   int s = 0;
@@ -427,6 +479,13 @@ int convT2x2_dw_mma(const float* x, const float* dy, float* dw, float* db, int B
   a.x = x; a.dy = dy; a.dw = dw; a.db = db; a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout;
   a.npix = (long long)B * H * W;
   a.wsh = ct_log2(W); a.hsh = ct_log2(H);
+  if (Cin == 8 && Cout == 8) {  // streaming kernel: >= 16 items per thread amortise the 72-value reduction
+    long long blocks = (a.npix * 4 + 128 * 16 - 1) / (128 * 16);
+    if (blocks > 8LL * kNumSMs) blocks = 8LL * kNumSMs;
+    if (blocks < 1) blocks = 1;
+    convT2x2_dw_c8_kernel<<<(unsigned)blocks, 128, 0, st>>>(a);
+    return post_launch("pu_convT2x2s2_bwd dw (c8)");
+  }
   const long long nstage = (a.npix + kCtTile - 1) / kCtTile;
   const int nsplit = Cin >= 32 ? 4 : 1;  // one (a,c) quadrant of the columns per CTA for the wide layers
   const int N = 4 * Cout / nsplit;
