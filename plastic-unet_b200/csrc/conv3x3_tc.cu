@@ -764,6 +764,10 @@ static bool tc_plan(int B, int H, int W, int C0, int C1, int Cout, TcPlan* p, bo
   };
   double best_cost = 1e30;
   int best_th = 0, best_tx = 0;
+  // per-tile hand-off cost in pixel-row units (measured: ~1.8 k clk of barrier waits, descriptor set-up and drain per tile
+  // against ~2.2 clk per MMA row)
+  int tile_fixed = 800;
+  if (const char* e = getenv("PU_TC_TILE_FIXED")) tile_fixed = atoi(e);
   const int tx_min = (W + 253) / 254;
   for (int tilesX = tx_min; tilesX <= tx_min + 7; ++tilesX) {
     const int tw = (W + tilesX - 1) / tilesX;
@@ -777,7 +781,7 @@ static bool tc_plan(int B, int H, int W, int C0, int C1, int Cout, TcPlan* p, bo
       const long long ntiles = (long long)B * ((H + th - 1) / th) * ((W + tw - 1) / tw);
       const long long waves = (ntiles + kNumSMs - 1) / kNumSMs;
       // per-SM time ~ waves x (MMA rows + staged rows + a fixed per-tile hand-off cost), in units of one pixel row
-      const double cost = (double)waves * (nmb * 128 + (th + 2) * pw + 256);
+      const double cost = (double)waves * (nmb * 128 + (th + 2) * pw + tile_fixed);
       if (cost < best_cost) { best_cost = cost; best_th = th; best_tx = tilesX; }
     }
   }
