@@ -87,6 +87,8 @@ class _PlasticBase(nn.Module):
         self.conv_math = _default_math()
         self.premask = True   # TF32 mode: fold each ReLU mask into its consumers' backward epilogues (UNetp / UNetpCoord)
         self.dp_group = None  # set by pu_b200.dp.attach() for the data-parallel trace all-reduce
+        self.dp_defer = False  # TrainStep: overlap the trace all-reduce with the backward pass (side stream)
+        self.dp_side = None
         self.dp_world = 1
         # same creation order and RNG consumption as the reference (unet_p.py:30-32)
         self.w = torch.nn.Parameter((.01 * torch.randn(self.nbf, self.nbf, device=self.torch_dev)), requires_grad=True)
@@ -128,8 +130,21 @@ class _PlasticBase(nn.Module):
             import torch.distributed as dist
             # data-parallel: all-reduce (sum_k outer, sum_k post^2), then the identical epilogue on every rank
             delta_q = ops.trace_delta(X.detach(), S.detach(), N, N * N, B)
-            dist.all_reduce(delta_q, op=dist.ReduceOp.SUM, group=self.dp_group)
-            hebb_new = ops.trace_apply(hebb.detach(), delta_q, self.eta.detach(), rule, B * self.dp_world)
+            if getattr(self, "dp_defer", False) and delta_q.is_cuda:
+                # The new trace is only needed at the end of the step: run its all-reduce + epilogue on a side stream so
+                # that they overlap the backward pass.  The caller (TrainStep) joins `self.dp_side` before it reads hebb_new.
+                if getattr(self, "dp_side", None) is None:
+                    self.dp_side = torch.cuda.Stream()
+                main = torch.cuda.current_stream()
+                self.dp_side.wait_stream(main)
+                with torch.cuda.stream(self.dp_side):
+                    dist.all_reduce(delta_q, op=dist.ReduceOp.SUM, group=self.dp_group)
+                    hebb_new = ops.trace_apply(hebb.detach(), delta_q, self.eta.detach(), rule, B * self.dp_world)
+                delta_q.record_stream(self.dp_side)
+                hebb_new.record_stream(main)
+            else:
+                dist.all_reduce(delta_q, op=dist.ReduceOp.SUM, group=self.dp_group)
+                hebb_new = ops.trace_apply(hebb.detach(), delta_q, self.eta.detach(), rule, B * self.dp_world)
         else:
             # rows k of pre/post = row 0 of map k (reference keeps only [0] of the bmm)
             hebb_new = ops.trace_update(hebb, X, S, self.eta, rule, N * N, B)

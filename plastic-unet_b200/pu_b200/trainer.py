@@ -22,6 +22,8 @@ class TrainStep:
         self.batch = batch
         self.world = dist.get_world_size(dp_group) if (dist.is_initialized() and dp_group is not None) else 1
         self.dp_group = dp_group if self.world > 1 else None
+        if self.dp_group is not None:
+            net.dp_defer = True  # the trace delta all-reduce overlaps the backward pass
         self.betas, self.eps = betas, eps
         params = [p for p in net.parameters()]
         total = sum(p.numel() for p in params)
@@ -83,6 +85,8 @@ class TrainStep:
         _lib.call("pu_adam_step", self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
                   self.step_count.data_ptr(), self.lr.data_ptr(), self.betas[0], self.betas[1], self.eps,
                   1.0 / self.world, self.n_flat, st)
+        if getattr(self.net, "dp_side", None) is not None:
+            torch.cuda.current_stream().wait_stream(self.net.dp_side)  # join the deferred trace all-reduce + epilogue
         self.hebb.copy_(hebb_new.detach())
 
     def capture(self):
