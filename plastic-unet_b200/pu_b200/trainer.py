@@ -128,6 +128,32 @@ class TrainStep:
             self._step_body()
         return self.loss
 
+    # -------------------------------------------------------------------------------------------
+    def prefetch(self, x, target):
+        """Start the host->device copy of the NEXT batch on a copy stream; it overlaps the step that is running.
+        Pair with step_prefetched().  (Pinned host tensors; the staging buffers are reused once consumed.)"""
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream()
+            self._stage_x = torch.empty_like(self.x)
+            self._stage_t = torch.empty_like(self.target)
+            self._stage_ready = torch.cuda.Event()
+            self._stage_free = torch.cuda.Event()
+            self._stage_free.record(torch.cuda.current_stream())
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(self._stage_free)  # the previous staged batch has been moved into the step's buffers
+            self._stage_x.copy_(x, non_blocking=True)
+            self._stage_t.copy_(target, non_blocking=True)
+            self._stage_ready.record(self._copy_stream)
+
+    def step_prefetched(self):
+        """One optimisation step on the batch handed to prefetch()."""
+        main = torch.cuda.current_stream()
+        main.wait_event(self._stage_ready)
+        self.x.copy_(self._stage_x, non_blocking=True)
+        self.target.copy_(self._stage_t, non_blocking=True)
+        self._stage_free.record(main)
+        return self.step()
+
 
 class InferStep:
     """Batched forward-only step (eval.py:81-90 / infer.py:42-47 semantics: trace zero, hebb' discarded)."""
