@@ -140,6 +140,12 @@ int pu_convT3x3s2_bwd(const float* x, const float* w, const float* dy, const flo
                       float* dx, float* dw, float* db,
                       int B, int H, int W, int Cin, int Cout, int Ho, int Wo, int oy, int ox, void* stream);
 
+/* Zero insertion: the (oy, ox, Ho, Wo) window of the (2H+1)x(2W+1) canvas holding x at the odd coordinates.  With it
+   ConvTranspose2d(k=3, s=2, p=0) + the reference's crop (unet_p_res.py:207,214-217) = pu_conv3x3_fwd with PU_W_OIHW_DGRAD
+   on the tcgen05 path (TF32 mode).  _bwd gathers the gradient back.  C % 4 == 0. */
+int pu_zero_insert2x_fwd(const float* x, float* z, int B, int H, int W, int C, int Ho, int Wo, int oy, int ox, void* stream);
+int pu_zero_insert2x_bwd(const float* dz, float* dx, int B, int H, int W, int C, int Ho, int Wo, int oy, int ox, void* stream);
+
 /* ---- pooling / resampling --------------------------------------------------------------------
  * MaxPool2d(2) floor mode (reference unet_p.py:139, unet_p_res.py:247) with the Dropout2d of
  * pool_drop (unet_p_res.py:248) fused as an optional per-(b,c) scale [B,C].                   */

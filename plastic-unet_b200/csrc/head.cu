@@ -109,16 +109,32 @@ __global__ void head_param_grads_kernel(const float* __restrict__ gw, const floa
 __global__ void trace_contract_kernel(const float* __restrict__ hebb, const float* __restrict__ pre, const float* __restrict__ post,
                                       long long ld, int K, const float* __restrict__ eta_p, int rule, float* __restrict__ out,
                                       float* __restrict__ delta_q, int N, int Kdiv, int mode) {
+  // block = (32, 8): the K pre/post rows of the block's 8 i-columns and 32 j-columns are staged through shared memory in
+  // chunks of 64 (all loads of a chunk in flight at once: a per-k dependent global-load loop cost 19 us for K = 64)
+  __shared__ float sp[64][8];
+  __shared__ float sq[64][32];
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   const int i = blockIdx.y * blockDim.y + threadIdx.y;
-  if (i >= N || j >= N) return;
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  const int i0 = blockIdx.y * 8, j0 = blockIdx.x * 32;
   float d = 0.f, q = 0.f;
-  for (int k = 0; k < K; ++k) {
-    const float a = __ldg(pre + k * ld + i);
-    const float b = __ldg(post + k * ld + j);
-    d = fmaf(a, b, d);
-    q = fmaf(b, b, q);
+  for (int kc = 0; kc < K; kc += 64) {
+    const int kn = min(64, K - kc);
+    __syncthreads();
+    for (int e = tid; e < kn * 40; e += 256) {
+      const int k = e / 40, c = e - k * 40;
+      if (c < 8) sp[k][c] = (i0 + c < N) ? __ldg(pre + (size_t)(kc + k) * ld + i0 + c) : 0.f;
+      else sq[k][c - 8] = (j0 + c - 8 < N) ? __ldg(post + (size_t)(kc + k) * ld + j0 + c - 8) : 0.f;
+    }
+    __syncthreads();
+    for (int k = 0; k < kn; ++k) {
+      const float a = sp[k][threadIdx.y];
+      const float b = sq[k][threadIdx.x];
+      d = fmaf(a, b, d);
+      q = fmaf(b, b, q);
+    }
   }
+  if (i >= N || j >= N) return;
   if (mode == 1) {
     delta_q[(size_t)i * N + j] = d;
     if (i == 0) delta_q[(size_t)N * N + j] = q;

@@ -160,9 +160,76 @@ static inline int grid_for(long long n) {
   return (int)g;
 }
 
+// ---- zero insertion (stride-2 transposed convolution as a stride-1 convolution) --------------------------------------
+// z[b, r, s, :] = x[b, (r+oy-1)/2, (s+ox-1)/2, :] where r+oy and s+ox are odd (and the source pixel exists), else 0:
+// the (oy, ox, Ho, Wo) window of the (2H+1) x (2W+1) canvas with x at the odd coordinates.  A 3x3 stride-1 pad-1
+// convolution of that canvas with the flipped kernel equals ConvTranspose2d(k=3, s=2, p=0) (reference unet_p_res.py:207).
+__global__ void zero_insert2x_kernel(const float4* __restrict__ x, float4* __restrict__ z, int B, int H, int W, int C4, int Ho, int Wo,
+                                     int oy, int ox) {
+  const long long n = (long long)B * Ho * Wo * C4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4);
+    long long t = i / C4;
+    const int s = (int)(t % Wo);
+    t /= Wo;
+    const int r = (int)(t % Ho);
+    const int b = (int)(t / Ho);
+    const int fy = r + oy, fx = s + ox;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if ((fy & 1) && (fx & 1)) {
+      const int iy = (fy - 1) >> 1, ix = (fx - 1) >> 1;
+      if (iy < H && ix < W) v = __ldg(x + (((size_t)b * H + iy) * W + ix) * C4 + c);
+    }
+    z[i] = v;
+  }
+}
+
+__global__ void zero_insert2x_bwd_kernel(const float4* __restrict__ dz, float4* __restrict__ dx, int B, int H, int W, int C4, int Ho,
+                                         int Wo, int oy, int ox) {
+  const long long n = (long long)B * H * W * C4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4);
+    long long t = i / C4;
+    const int ix = (int)(t % W);
+    t /= W;
+    const int iy = (int)(t % H);
+    const int b = (int)(t / H);
+    const int r = 2 * iy + 1 - oy, s = 2 * ix + 1 - ox;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r >= 0 && r < Ho && s >= 0 && s < Wo) v = __ldg(dz + (((size_t)b * Ho + r) * Wo + s) * C4 + c);
+    dx[i] = v;
+  }
+}
+
 }  // namespace pu
 
 extern "C" {
+
+int pu_zero_insert2x_fwd(const float* x, float* z, int B, int H, int W, int C, int Ho, int Wo, int oy, int ox, void* stream) {
+  PU_REQUIRE(x && z && B > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0 && Ho > 0 && Wo > 0 && oy >= 0 && ox >= 0 && oy + Ho <= 2 * H + 1 &&
+                 ox + Wo <= 2 * W + 1,
+             PU_ERR_BAD_ARG, "pu_zero_insert2x_fwd: bad argument");
+  PU_REQUIRE(pu::aligned16(x) && pu::aligned16(z), PU_ERR_BAD_ARG, "pu_zero_insert2x_fwd: pointers not 16-byte aligned");
+  const long long n = (long long)B * Ho * Wo * (C / 4);
+  long long blocks = (n + 255) / 256;
+  if (blocks > 16LL * pu::kNumSMs) blocks = 16LL * pu::kNumSMs;
+  pu::zero_insert2x_kernel<<<(unsigned)blocks, 256, 0, pu::as_stream(stream)>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(z),
+                                                                              B, H, W, C / 4, Ho, Wo, oy, ox);
+  return pu::post_launch("pu_zero_insert2x_fwd");
+}
+
+int pu_zero_insert2x_bwd(const float* dz, float* dx, int B, int H, int W, int C, int Ho, int Wo, int oy, int ox, void* stream) {
+  PU_REQUIRE(dz && dx && B > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0 && Ho > 0 && Wo > 0 && oy >= 0 && ox >= 0, PU_ERR_BAD_ARG,
+             "pu_zero_insert2x_bwd: bad argument");
+  PU_REQUIRE(pu::aligned16(dz) && pu::aligned16(dx), PU_ERR_BAD_ARG, "pu_zero_insert2x_bwd: pointers not 16-byte aligned");
+  const long long n = (long long)B * H * W * (C / 4);
+  long long blocks = (n + 255) / 256;
+  if (blocks > 16LL * pu::kNumSMs) blocks = 16LL * pu::kNumSMs;
+  pu::zero_insert2x_bwd_kernel<<<(unsigned)blocks, 256, 0, pu::as_stream(stream)>>>(reinterpret_cast<const float4*>(dz),
+                                                                                  reinterpret_cast<float4*>(dx), B, H, W, C / 4, Ho, Wo, oy, ox);
+  return pu::post_launch("pu_zero_insert2x_bwd");
+}
+
 
 int pu_maxpool2_fwd(const float* x, const float* chan_scale, float* y, int B, int H, int W, int C, void* stream) {
   PU_REQUIRE(x && y && B > 0 && H >= 2 && W >= 2 && C > 0, PU_ERR_BAD_ARG, "pu_maxpool2_fwd: bad argument");

@@ -408,7 +408,12 @@ class res_up(nn.Module):
         if Ho != x2.shape[1] or Wo != x2.shape[2]:
             raise RuntimeError("Sizes of tensors must match except in dimension 1")
         oy, ox = -(diffY // 2), -(diffX // 2)
-        u = ops.convT3x3s2(x1, self.dconv.weight, self.dconv.bias, None, Ho, Wo, oy, ox, math == ops.MATH_TF32)
+        Cin_t, Cout_t = self.dconv.weight.shape[0], self.dconv.weight.shape[1]
+        if math == ops.MATH_TF32 and ops.convT3x3s2_tc_ok(Cin_t, Cout_t, x1.shape[1], x1.shape[2], Ho, Wo, oy, ox):
+            # zero insertion + tcgen05 conv3x3 with the flipped kernel (4x the MACs, >5x faster than the CUDA-core kernel)
+            u = ops.convT3x3s2_tc(x1, self.dconv.weight, self.dconv.bias, Ho, Wo, oy, ox)
+        else:
+            u = ops.convT3x3s2(x1, self.dconv.weight, self.dconv.bias, None, Ho, Wo, oy, ox, math == ops.MATH_TF32)
         p = self.uconv[0].p
         if self.training and p > 0:
             scale = _feature_noise(u.shape[0], u.shape[3] + x2.shape[3], p, u.device)

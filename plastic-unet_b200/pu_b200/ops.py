@@ -330,6 +330,95 @@ def _convT2_backward(ctx, dy):
 convT2x2s2.register_autograd(_convT2_backward, setup_context=_convT2_setup)
 
 
+# -------------------------------------------------------------------------------------------------
+# ConvTranspose2d(k=3, s=2, p=0) + crop on the tcgen05 path (TF32 mode): zero insertion + conv3x3 with the flipped kernel
+# -------------------------------------------------------------------------------------------------
+def convT3x3s2_tc_ok(Cin: int, Cout: int, H: int, W: int, Ho: int, Wo: int, oy: int, ox: int) -> bool:
+    """The zero-padded window equals the cropped transposed conv only if the canvas is zero just outside the window:
+    before it (index oy-1 / ox-1: outside the canvas or an even coordinate) and after it (end of the canvas or an even
+    coordinate).  True for the reference's crops of 0 or 1 (unet_p_res.py:214-217)."""
+    def edge_ok(o, n, full):
+        return (o == 0 or (o - 1) % 2 == 0) and (o + n == full or (o + n) % 2 == 0)
+    return (edge_ok(oy, Ho, 2 * H + 1) and edge_ok(ox, Wo, 2 * W + 1)
+            and _tc_ok(Cin, 0, Cout, Cout, 0) and _tc_ok(Cout, 0, Cin, Cin, 0))
+
+
+@torch.library.custom_op("pu::convT3x3s2_tc", mutates_args=())
+def convT3x3s2_tc(x: Tensor, weight: Tensor, bias: Optional[Tensor], Ho: int, Wo: int, oy: int, ox: int) -> Tensor:
+    _chk(x, weight, bias)
+    B, H, W, Cin = x.shape
+    Cout = weight.shape[1]
+    z = torch.empty((B, Ho, Wo, Cin), device=x.device, dtype=torch.float32)
+    _lib.call("pu_zero_insert2x_fwd", x.data_ptr(), z.data_ptr(), B, H, W, Cin, Ho, Wo, oy, ox, _s())
+    # the conv whose "dgrad" operand is the IOHW transposed-conv weight: input channels = dim 0, outputs = dim 1, taps flipped
+    wp, wfmt = _weight_operand(weight, 1, MATH_TF32, Cin, 0, Cout, Ho, Wo)
+    y = torch.empty((B, Ho, Wo, Cout), device=x.device, dtype=torch.float32)
+    _lib.call("pu_conv3x3_fwd", z.data_ptr(), Ho, Wo, Cin, 0, 0, None, 0, 0, 0, 0, 0,
+              wp.data_ptr(), _p(bias), None, FLAG_ROUND_TF32,
+              y.data_ptr(), Ho, Wo, Cout, 0, 0, None, 0, 0, 0, 0, 0, None, None, B, Ho, Wo, Cout, MATH_TF32, wfmt, _s())
+    return y
+
+
+@convT3x3s2_tc.register_fake
+def _(x, weight, bias, Ho, Wo, oy, ox):
+    return x.new_empty((x.shape[0], Ho, Wo, weight.shape[1]))
+
+
+@torch.library.custom_op("pu::convT3x3s2_tc_bwd", mutates_args=())
+def convT3x3s2_tc_bwd(dy: Tensor, x: Tensor, weight: Tensor, has_bias: bool, need_dx: bool, need_dw: bool,
+                      Ho: int, Wo: int, oy: int, ox: int) -> List[Tensor]:
+    _chk(dy, x, weight)
+    dev = x.device
+    B, H, W, Cin = x.shape
+    Cout = weight.shape[1]
+    npix = B * Ho * Wo
+    db = torch.empty(Cout, device=dev, dtype=torch.float32) if has_bias else _e(dev)
+    g = torch.empty_like(dy)  # gradient rounded to TF32 (tensor-core operand) + bias gradient, one pass
+    _lib.call("pu_relu_bwd_bias", dy.data_ptr(), None, g.data_ptr(), _p(db) if has_bias else None, npix, Cout, FLAG_ROUND_TF32, _s())
+    dx, dw = _e(dev), _e(dev)
+    if need_dx:
+        # dz = conv3x3(g) with the weight read as OIHW = [Cin][Cout]: input channels = dim 1, outputs = dim 0, taps as stored
+        wp, wfmt = _weight_operand(weight, 0, MATH_TF32, Cout, 0, Cin, Ho, Wo)
+        dz = torch.empty((B, Ho, Wo, Cin), device=dev, dtype=torch.float32)
+        _lib.call("pu_conv3x3_fwd", g.data_ptr(), Ho, Wo, Cout, 0, 0, None, 0, 0, 0, 0, 0,
+                  wp.data_ptr(), None, None, FLAG_ROUND_TF32,
+                  dz.data_ptr(), Ho, Wo, Cin, 0, 0, None, 0, 0, 0, 0, 0, None, None, B, Ho, Wo, Cin, MATH_TF32, wfmt, _s())
+        dx = torch.empty_like(x)
+        _lib.call("pu_zero_insert2x_bwd", dz.data_ptr(), dx.data_ptr(), B, H, W, Cin, Ho, Wo, oy, ox, _s())
+    if need_dw:
+        z = torch.empty((B, Ho, Wo, Cin), device=dev, dtype=torch.float32)  # recomputed: cheaper than keeping it alive
+        _lib.call("pu_zero_insert2x_fwd", x.data_ptr(), z.data_ptr(), B, H, W, Cin, Ho, Wo, oy, ox, _s())
+        dwc = torch.empty((Cout, Cin, 3, 3), device=dev, dtype=torch.float32)  # gradient of the equivalent conv's OIHW weight
+        _lib.call("pu_conv3x3_wgrad", z.data_ptr(), Ho, Wo, Cin, 0, 0, None, 0, 0, 0, 0, 0,
+                  g.data_ptr(), dwc.data_ptr(), None, B, Ho, Wo, Cout, MATH_TF32, _s())
+        dw = dwc.flip(2, 3).permute(1, 0, 2, 3).contiguous()  # w_conv[co][ci][k] = w[ci][co][2-k]
+    return [dx, dw, db]
+
+
+@convT3x3s2_tc_bwd.register_fake
+def _(dy, x, weight, has_bias, need_dx, need_dw, Ho, Wo, oy, ox):
+    e = x.new_empty(0)
+    return [torch.empty_like(x) if need_dx else e, torch.empty_like(weight) if need_dw else e,
+            x.new_empty(weight.shape[1]) if has_bias else e]
+
+
+def _convT3tc_setup(ctx, inputs, output):
+    x, weight, bias, Ho, Wo, oy, ox = inputs
+    ctx.save_for_backward(x, weight)
+    ctx.cfg = (bias is not None, Ho, Wo, oy, ox)
+
+
+def _convT3tc_backward(ctx, dy):
+    x, weight = ctx.saved_tensors
+    has_bias, Ho, Wo, oy, ox = ctx.cfg
+    need = ctx.needs_input_grad
+    dx, dw, db = convT3x3s2_tc_bwd(dy.contiguous(), x, weight, has_bias and need[2], need[0], need[1], Ho, Wo, oy, ox)
+    return dx if need[0] else None, dw if need[1] else None, db if (has_bias and need[2]) else None, None, None, None, None
+
+
+convT3x3s2_tc.register_autograd(_convT3tc_backward, setup_context=_convT3tc_setup)
+
+
 @torch.library.custom_op("pu::convT3x3s2", mutates_args=())
 def convT3x3s2(x: Tensor, weight: Tensor, bias: Optional[Tensor], chan_scale: Optional[Tensor],
                Ho: int, Wo: int, oy: int, ox: int, round_out: bool = False) -> Tensor:

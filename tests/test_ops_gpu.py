@@ -239,6 +239,39 @@ def test_convT3x3s2_cropped(Cin, Cout, H, W, crop, scaled):
     check(bo.grad, br.grad, 5 * TOL, what="db")
 
 
+@pytest.mark.parametrize("Cin,Cout,H,W,crop", [(32, 16, 50, 50, (0, 0)), (64, 32, 25, 25, (1, 1)), (256, 128, 6, 6, (1, 1)),
+                                               (16, 8, 12, 12, (0, 1))])
+def test_convT3x3s2_tc_path(Cin, Cout, H, W, crop):
+    """TF32 path of nn.ConvTranspose2d(in, out, 3, stride=2) + crop (unet_p_res.py:207,214-217): zero insertion + tcgen05
+    conv3x3 with the flipped kernel.  TF32 operands, fp32 accumulation: 2e-3 of the tensor's max."""
+    from pu_b200 import ops
+    g = torch.Generator().manual_seed(Cin + H)
+    B = 2
+    oy, ox = crop
+    Ho, Wo = 2 * H + 1 - oy, 2 * W + 1 - ox
+    assert ops.convT3x3s2_tc_ok(Cin, Cout, H, W, Ho, Wo, oy, ox)
+    x = torch.randn(B, Cin, H, W, generator=g)
+    x = ((x.view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)  # activations reach this op TF32-rounded by their producer
+    w = torch.randn(Cin, Cout, 3, 3, generator=g) / Cin ** 0.5
+    b = torch.randn(Cout, generator=g)
+    R = torch.randn(B, Cout, Ho, Wo, generator=g)
+    xr, wr, br = (leaf(t, "cpu", torch.float64) for t in (x, w, b))
+    yr = F.conv_transpose2d(xr, wr, br, stride=2)[:, :, oy:oy + Ho, ox:ox + Wo]
+    (yr * R.double()).sum().backward()
+    xo, wo, bo = leaf(nhwc(x)), leaf(w), leaf(b)
+    yo = ops.convT3x3s2_tc(xo, wo, bo, Ho, Wo, oy, ox)
+    (yo * nhwc(R).to(DEV)).sum().backward()
+
+    def close(got, ref, what):
+        err = (got.detach().cpu().double() - ref).abs().max().item() / max(ref.abs().max().item(), 1e-30)
+        assert err < 2e-3, "%s: max err / max |ref| = %g" % (what, err)
+
+    close(nchw(yo), yr, "y")
+    close(nchw(xo.grad), xr.grad, "dx")
+    close(wo.grad, wr.grad, "dw")
+    close(bo.grad, br.grad, "db")
+
+
 @pytest.mark.parametrize("C,H,W,scaled", [(8, 32, 32, False), (16, 101, 101, True), (3, 25, 13, False), (64, 12, 12, True)])
 def test_maxpool2_floor_and_ties(C, H, W, scaled):
     """nn.MaxPool2d(2) floor mode incl. ATen's first-max tie-break on ReLU zeros (unet_p.py:139, unet_p_res.py:247-248)."""
