@@ -812,7 +812,7 @@ int conv3x3_wgrad_ffma(const WgradArgs& a0, cudaStream_t st, int math) {
       if (a.W > 16 && nco_t == 1) {
         a.tilesX = cdiv(a.W, 32); a.tilesY = cdiv(a.H, 16);
         a.ntiles = a.tilesX * a.tilesY * a.B;
-        const int gx = max(1, min(a.ntiles, (2 * kNumSMs) / max(1, nci * ncoz)));
+        const int gx = max(1, min(a.ntiles, (3 * kNumSMs) / max(1, nci * ncoz)));  // 72 KB + 72 regs per CTA: three fit an SM
         launch_pdl(conv3x3_wgrad_mma_kernel<32, 16, 1>, dim3(gx, nci, ncoz), dim3(256), stage_bytes(32, 16, 1), st, a);
       } else {
         a.tilesX = cdiv(a.W, 16); a.tilesY = cdiv(a.H, 16);
