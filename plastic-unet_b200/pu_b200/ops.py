@@ -37,6 +37,9 @@ def _tc_resident(C0: int, C1: int, Cout: int, H: int, W: int) -> bool:
 
 W_PACKED, W_OIHW, W_OIHW_DGRAD = 0, 1, 2
 
+# set by pu_b200.trainer.TrainStep: a CUDA stream on which conv3x3_bwd runs its weight-gradient kernels (None = same stream)
+WGRAD_SIDE_STREAM = None
+
 
 def _weight_operand(weight: Tensor, transpose: int, math: int, C0: int, C1: int, Cout_conv: int, H: int, W: int):
     """-> (tensor, wfmt): the raw OIHW weight whenever the kernel can build its operand tiles itself (every FFMA
@@ -165,9 +168,24 @@ def conv3x3_bwd(dy: Tensor, y: Tensor, x0: Tensor, x1: Optional[Tensor], weight:
                   B, H, W, Cin, md, wfmt, _s())
     dw = _e(dev)
     if need_dw:
-        dw = torch.empty_like(weight)
-        _lib.call("pu_conv3x3_wgrad", x0.data_ptr(), H0, W0, C0, oy0, ox0, _p(x1), H1, W1, C1, oy1, ox1,
-                  g.data_ptr(), dw.data_ptr(), db.data_ptr() if db_in_wgrad else None, B, H, W, Cout, math, _s())
+        side = WGRAD_SIDE_STREAM
+        if side is not None:
+            # The weight gradient is not needed before the optimizer: run it on a side stream so that it overlaps the
+            # dgrad chain (the caller joins WGRAD_SIDE_STREAM before it reads any parameter gradient).
+            main = torch.cuda.current_stream()
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                dw = torch.empty_like(weight)
+                _lib.call("pu_conv3x3_wgrad", x0.data_ptr(), H0, W0, C0, oy0, ox0, _p(x1), H1, W1, C1, oy1, ox1,
+                          g.data_ptr(), dw.data_ptr(), db.data_ptr() if db_in_wgrad else None, B, H, W, Cout, math, _s())
+            for t in (x0, x1, g, db if db_in_wgrad else None):
+                if t is not None:
+                    t.record_stream(side)
+            dw.record_stream(main)
+        else:
+            dw = torch.empty_like(weight)
+            _lib.call("pu_conv3x3_wgrad", x0.data_ptr(), H0, W0, C0, oy0, ox0, _p(x1), H1, W1, C1, oy1, ox1,
+                      g.data_ptr(), dw.data_ptr(), db.data_ptr() if db_in_wgrad else None, B, H, W, Cout, math, _s())
     g_out = g if fresh_g else _e(dev)  # never return an alias of an input
     return [g_out, dx0, dx1, dw, db]
 
@@ -299,9 +317,24 @@ def convT2x2s2_bwd(dy: Tensor, x: Tensor, weight: Tensor, need_dx: bool, need_dw
     dx = torch.empty_like(x) if need_dx else _e(x.device)
     dw = torch.empty_like(weight) if need_dw else _e(x.device)
     db = torch.empty(Cout, device=x.device, dtype=torch.float32) if need_db else _e(x.device)
-    _lib.call("pu_convT2x2s2_bwd", x.data_ptr(), weight.data_ptr(), dy.data_ptr(), dx.data_ptr() if need_dx else None,
-              dw.data_ptr() if need_dw else None, db.data_ptr() if need_db else None, B, H, W, Cin, Cout,
-              (FLAG_MASK_IN if mask_in else 0) | (FLAG_TF32_MATH if tf32 else 0), _s())
+    flags = (FLAG_MASK_IN if mask_in else 0) | (FLAG_TF32_MATH if tf32 else 0)
+    side = WGRAD_SIDE_STREAM
+    if side is not None and (need_dw or need_db):
+        # dx on the current stream; the parameter gradients (not needed before the optimizer) on the side stream
+        if need_dx:
+            _lib.call("pu_convT2x2s2_bwd", x.data_ptr(), weight.data_ptr(), dy.data_ptr(), dx.data_ptr(), None, None,
+                      B, H, W, Cin, Cout, flags, _s())
+        main = torch.cuda.current_stream()
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            _lib.call("pu_convT2x2s2_bwd", x.data_ptr(), weight.data_ptr(), dy.data_ptr(), None,
+                      dw.data_ptr() if need_dw else None, db.data_ptr() if need_db else None, B, H, W, Cin, Cout, flags, _s())
+        for t in (x, dy, dw if need_dw else None, db if need_db else None):
+            if t is not None:
+                t.record_stream(side)
+    else:
+        _lib.call("pu_convT2x2s2_bwd", x.data_ptr(), weight.data_ptr(), dy.data_ptr(), dx.data_ptr() if need_dx else None,
+                  dw.data_ptr() if need_dw else None, db.data_ptr() if need_db else None, B, H, W, Cin, Cout, flags, _s())
     return [dx, dw, db]
 
 
