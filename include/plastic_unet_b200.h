@@ -194,7 +194,8 @@ int pu_bn_invstd(const float* running_var, float* invstd, float eps, int C, void
 int pu_plastic_head_fwd(const float* X, const float* w, const float* alpha, const float* hebb,
                         float* weff_out, float* S, int B, int N, void* stream);
 /* gA = gS*S*(1-S); gX = gA @ Weff^T; gWeff = X^T @ gA; gw = gWeff; galpha = gWeff*hebb; ghebb = gWeff*alpha.
- * gA_ws is [B*N,N] scratch. galpha/ghebb may be NULL.                                           */
+ * gA_ws is [B*N,N] scratch. galpha/ghebb may be NULL.  gw == NULL: only gA and gX; gS == NULL: gA_ws already
+ * holds gA from such a call and only the parameter gradients are computed (lets a caller put them on a side stream). */
 int pu_plastic_head_bwd(const float* X, const float* S, const float* gS, const float* weff,
                         const float* alpha, const float* hebb, float* gA_ws,
                         float* gX, float* gw, float* galpha, float* ghebb, int B, int N, void* stream);

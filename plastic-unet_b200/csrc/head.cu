@@ -246,15 +246,20 @@ int pu_plastic_head_fwd(const float* X, const float* w, const float* alpha, cons
 
 int pu_plastic_head_bwd(const float* X, const float* S, const float* gS, const float* weff, const float* alpha, const float* hebb,
                         float* gA_ws, float* gX, float* gw, float* galpha, float* ghebb, int B, int N, void* stream) {
-  PU_REQUIRE(X && S && gS && weff && alpha && hebb && gA_ws && gw && B > 0 && N > 0, PU_ERR_BAD_ARG, "pu_plastic_head_bwd: bad argument");
+  // gS == NULL: gA_ws already holds gA (a previous call computed it); gw == NULL: skip the parameter gradients.  The two
+  // halves can then be issued separately (gX on the critical path, the parameter gradients on a side stream).
+  PU_REQUIRE(X && S && weff && alpha && hebb && gA_ws && (gS || gw) && B > 0 && N > 0, PU_ERR_BAD_ARG, "pu_plastic_head_bwd: bad argument");
   cudaStream_t st = pu::as_stream(stream);
   const int M = B * N;
   const long long n = (long long)M * N;
-  int g = (int)((n + 1023) / 1024);
-  g = g < 1 ? 1 : (g > 16 * pu::kNumSMs ? 16 * pu::kNumSMs : g);
-  pu::sigmoid_bwd_kernel<<<g, 256, 0, st>>>(S, gS, gA_ws, n);
-  int rc = pu::post_launch("pu_plastic_head_bwd gA");
-  if (rc) return rc;
+  int rc = PU_OK;
+  if (gS != nullptr) {
+    int g = (int)((n + 1023) / 1024);
+    g = g < 1 ? 1 : (g > 16 * pu::kNumSMs ? 16 * pu::kNumSMs : g);
+    pu::sigmoid_bwd_kernel<<<g, 256, 0, st>>>(S, gS, gA_ws, n);
+    rc = pu::post_launch("pu_plastic_head_bwd gA");
+    if (rc) return rc;
+  }
   if (gX != nullptr) {
     dim3 grid(pu::cdiv(N, 64), pu::cdiv(M, 64), 1);
     // gX[m][n] = sum_k gA[m][k] * weff[n][k]
@@ -262,6 +267,7 @@ int pu_plastic_head_bwd(const float* X, const float* S, const float* gS, const f
     rc = pu::post_launch("pu_plastic_head_bwd gX");
     if (rc) return rc;
   }
+  if (gw == nullptr) return PU_OK;
   cudaError_t e = cudaMemsetAsync(gw, 0, sizeof(float) * N * N, st);
   if (e != cudaSuccess) {
     pu::set_error("pu_plastic_head_bwd memset: %s", cudaGetErrorString(e));

@@ -419,12 +419,24 @@ def convT3x3s2_tc_bwd(dy: Tensor, x: Tensor, weight: Tensor, has_bias: bool, nee
         dx = torch.empty_like(x)
         _lib.call("pu_zero_insert2x_bwd", dz.data_ptr(), dx.data_ptr(), B, H, W, Cin, Ho, Wo, oy, ox, _s())
     if need_dw:
-        z = torch.empty((B, Ho, Wo, Cin), device=dev, dtype=torch.float32)  # recomputed: cheaper than keeping it alive
-        _lib.call("pu_zero_insert2x_fwd", x.data_ptr(), z.data_ptr(), B, H, W, Cin, Ho, Wo, oy, ox, _s())
-        dwc = torch.empty((Cout, Cin, 3, 3), device=dev, dtype=torch.float32)  # gradient of the equivalent conv's OIHW weight
-        _lib.call("pu_conv3x3_wgrad", z.data_ptr(), Ho, Wo, Cin, 0, 0, None, 0, 0, 0, 0, 0,
-                  g.data_ptr(), dwc.data_ptr(), None, B, Ho, Wo, Cout, MATH_TF32, _s())
-        dw = dwc.flip(2, 3).permute(1, 0, 2, 3).contiguous()  # w_conv[co][ci][k] = w[ci][co][2-k]
+        def wgrad():
+            z = torch.empty((B, Ho, Wo, Cin), device=dev, dtype=torch.float32)  # recomputed: cheaper than keeping it alive
+            _lib.call("pu_zero_insert2x_fwd", x.data_ptr(), z.data_ptr(), B, H, W, Cin, Ho, Wo, oy, ox, _s())
+            dwc = torch.empty((Cout, Cin, 3, 3), device=dev, dtype=torch.float32)  # gradient of the equivalent conv's OIHW weight
+            _lib.call("pu_conv3x3_wgrad", z.data_ptr(), Ho, Wo, Cin, 0, 0, None, 0, 0, 0, 0, 0,
+                      g.data_ptr(), dwc.data_ptr(), None, B, Ho, Wo, Cout, MATH_TF32, _s())
+            return dwc.flip(2, 3).permute(1, 0, 2, 3).contiguous()  # w_conv[co][ci][k] = w[ci][co][2-k]
+        side = WGRAD_SIDE_STREAM
+        if side is not None:  # off the critical path: see conv3x3_bwd
+            main = torch.cuda.current_stream()
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                dw = wgrad()
+            x.record_stream(side)
+            g.record_stream(side)
+            dw.record_stream(main)
+        else:
+            dw = wgrad()
     return [dx, dw, db]
 
 
@@ -792,9 +804,24 @@ def plastic_head_bwd(gS: Tensor, X: Tensor, S: Tensor, weff: Tensor, alpha: Tens
     gw = torch.empty_like(weff)
     galpha = torch.empty_like(weff) if need_galpha else _e(X.device)
     ghebb = torch.empty_like(weff) if need_ghebb else _e(X.device)
-    _lib.call("pu_plastic_head_bwd", X.data_ptr(), S.data_ptr(), gS.data_ptr(), weff.data_ptr(), alpha.data_ptr(), hebb.data_ptr(),
-              gA.data_ptr(), gX.data_ptr() if need_gx else None, gw.data_ptr(), galpha.data_ptr() if need_galpha else None,
-              ghebb.data_ptr() if need_ghebb else None, B, N, _s())
+    side = WGRAD_SIDE_STREAM
+    if side is not None:
+        # gA and gX on the critical path; the parameter gradients (gw, galpha, ghebb) on the side stream
+        _lib.call("pu_plastic_head_bwd", X.data_ptr(), S.data_ptr(), gS.data_ptr(), weff.data_ptr(), alpha.data_ptr(), hebb.data_ptr(),
+                  gA.data_ptr(), gX.data_ptr() if need_gx else None, None, None, None, B, N, _s())
+        main = torch.cuda.current_stream()
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            _lib.call("pu_plastic_head_bwd", X.data_ptr(), S.data_ptr(), None, weff.data_ptr(), alpha.data_ptr(), hebb.data_ptr(),
+                      gA.data_ptr(), None, gw.data_ptr(), galpha.data_ptr() if need_galpha else None,
+                      ghebb.data_ptr() if need_ghebb else None, B, N, _s())
+        for t in (X, gA, alpha, hebb, gw, galpha if need_galpha else None, ghebb if need_ghebb else None):
+            if t is not None:
+                t.record_stream(side)
+    else:
+        _lib.call("pu_plastic_head_bwd", X.data_ptr(), S.data_ptr(), gS.data_ptr(), weff.data_ptr(), alpha.data_ptr(), hebb.data_ptr(),
+                  gA.data_ptr(), gX.data_ptr() if need_gx else None, gw.data_ptr(), galpha.data_ptr() if need_galpha else None,
+                  ghebb.data_ptr() if need_ghebb else None, B, N, _s())
     return [gX, gw, galpha, ghebb]
 
 
