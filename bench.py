@@ -94,7 +94,7 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:
                 pass
-            time.sleep(0.002)
+            time.sleep(0.0005)
 
     def start(self):
         if self.nv is None:
@@ -228,7 +228,7 @@ def dominant_kernel_roofline(batch, size, math, dev, hbm_peak, peak_src):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="per-GPU batch")
