@@ -366,13 +366,18 @@ convT2x2s2.register_autograd(_convT2_backward, setup_context=_convT2_setup)
 # -------------------------------------------------------------------------------------------------
 # ConvTranspose2d(k=3, s=2, p=0) + crop on the tcgen05 path (TF32 mode): zero insertion + conv3x3 with the flipped kernel
 # -------------------------------------------------------------------------------------------------
+def zero_window_ok(o: int, n: int, full: int) -> bool:
+    """1-D condition for the window [o, o+n) of the zero-inserted canvas (x at the odd coordinates of [0, full)): a
+    zero-padded 3-tap convolution of the window equals the window of the full convolution iff the canvas is zero at
+    o-1 and at o+n (outside the canvas, or an even coordinate)."""
+    return (o == 0 or (o - 1) % 2 == 0) and (o + n == full or (o + n) % 2 == 0)
+
+
 def convT3x3s2_tc_ok(Cin: int, Cout: int, H: int, W: int, Ho: int, Wo: int, oy: int, ox: int) -> bool:
     """The zero-padded window equals the cropped transposed conv only if the canvas is zero just outside the window:
     before it (index oy-1 / ox-1: outside the canvas or an even coordinate) and after it (end of the canvas or an even
     coordinate).  True for the reference's crops of 0 or 1 (unet_p_res.py:214-217)."""
-    def edge_ok(o, n, full):
-        return (o == 0 or (o - 1) % 2 == 0) and (o + n == full or (o + n) % 2 == 0)
-    return (edge_ok(oy, Ho, 2 * H + 1) and edge_ok(ox, Wo, 2 * W + 1)
+    return (zero_window_ok(oy, Ho, 2 * H + 1) and zero_window_ok(ox, Wo, 2 * W + 1)
             and _tc_ok(Cin, 0, Cout, Cout, 0) and _tc_ok(Cout, 0, Cin, Cin, 0))
 
 
