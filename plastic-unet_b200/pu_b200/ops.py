@@ -37,8 +37,19 @@ def _tc_resident(C0: int, C1: int, Cout: int, H: int, W: int) -> bool:
 
 W_PACKED, W_OIHW, W_OIHW_DGRAD = 0, 1, 2
 
-# set by pu_b200.trainer.TrainStep: a CUDA stream on which conv3x3_bwd runs its weight-gradient kernels (None = same stream)
-WGRAD_SIDE_STREAM = None
+# set by pu_b200.trainer.TrainStep: CUDA streams on which the backward ops run their parameter-gradient kernels, used
+# round-robin (None = everything on the current stream)
+WGRAD_SIDE_STREAMS = None
+_side_rr = 0
+
+
+def _side_stream():
+    global _side_rr
+    if not WGRAD_SIDE_STREAMS:
+        return None
+    _side_rr = (_side_rr + 1) % len(WGRAD_SIDE_STREAMS)
+    return WGRAD_SIDE_STREAMS[_side_rr]
+
 
 
 def _weight_operand(weight: Tensor, transpose: int, math: int, C0: int, C1: int, Cout_conv: int, H: int, W: int):
@@ -168,10 +179,10 @@ def conv3x3_bwd(dy: Tensor, y: Tensor, x0: Tensor, x1: Optional[Tensor], weight:
                   B, H, W, Cin, md, wfmt, _s())
     dw = _e(dev)
     if need_dw:
-        side = WGRAD_SIDE_STREAM
+        side = _side_stream()
         if side is not None:
             # The weight gradient is not needed before the optimizer: run it on a side stream so that it overlaps the
-            # dgrad chain (the caller joins WGRAD_SIDE_STREAM before it reads any parameter gradient).
+            # dgrad chain (the caller joins WGRAD_SIDE_STREAMS before it reads any parameter gradient).
             main = torch.cuda.current_stream()
             side.wait_stream(main)
             with torch.cuda.stream(side):
@@ -318,7 +329,7 @@ def convT2x2s2_bwd(dy: Tensor, x: Tensor, weight: Tensor, need_dx: bool, need_dw
     dw = torch.empty_like(weight) if need_dw else _e(x.device)
     db = torch.empty(Cout, device=x.device, dtype=torch.float32) if need_db else _e(x.device)
     flags = (FLAG_MASK_IN if mask_in else 0) | (FLAG_TF32_MATH if tf32 else 0)
-    side = WGRAD_SIDE_STREAM
+    side = _side_stream()
     if side is not None and (need_dw or need_db):
         # dx on the current stream; the parameter gradients (not needed before the optimizer) on the side stream
         if need_dx:
@@ -431,7 +442,7 @@ def convT3x3s2_tc_bwd(dy: Tensor, x: Tensor, weight: Tensor, has_bias: bool, nee
             _lib.call("pu_conv3x3_wgrad", z.data_ptr(), Ho, Wo, Cin, 0, 0, None, 0, 0, 0, 0, 0,
                       g.data_ptr(), dwc.data_ptr(), None, B, Ho, Wo, Cout, MATH_TF32, _s())
             return dwc.flip(2, 3).permute(1, 0, 2, 3).contiguous()  # w_conv[co][ci][k] = w[ci][co][2-k]
-        side = WGRAD_SIDE_STREAM
+        side = _side_stream()
         if side is not None:  # off the critical path: see conv3x3_bwd
             main = torch.cuda.current_stream()
             side.wait_stream(main)
@@ -809,7 +820,7 @@ def plastic_head_bwd(gS: Tensor, X: Tensor, S: Tensor, weff: Tensor, alpha: Tens
     gw = torch.empty_like(weff)
     galpha = torch.empty_like(weff) if need_galpha else _e(X.device)
     ghebb = torch.empty_like(weff) if need_ghebb else _e(X.device)
-    side = WGRAD_SIDE_STREAM
+    side = _side_stream()
     if side is not None:
         # gA and gX on the critical path; the parameter gradients (gw, galpha, ghebb) on the side stream
         _lib.call("pu_plastic_head_bwd", X.data_ptr(), S.data_ptr(), gS.data_ptr(), weff.data_ptr(), alpha.data_ptr(), hebb.data_ptr(),

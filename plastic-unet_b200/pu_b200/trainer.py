@@ -60,7 +60,8 @@ class TrainStep:
         self._warm = warmup
         import os as _os
         # weight gradients run on a side stream and overlap the dgrad chain (measured 1.56 -> 1.38 ms/step); PU_WGRAD_SIDE=0 disables
-        self.wgrad_side = torch.cuda.Stream() if _os.environ.get("PU_WGRAD_SIDE", "1") == "1" else None
+        nside = int(_os.environ.get("PU_WGRAD_SIDE", "2"))  # number of side streams (round-robin); 0 = none
+        self.wgrad_side = [torch.cuda.Stream() for _ in range(nside)] if nside > 0 else None
 
     # -------------------------------------------------------------------------------------------
     def _step_body(self):
@@ -73,13 +74,14 @@ class TrainStep:
         n = out.numel()
         _lib.call("pu_bce_fwd_bwd", out.data_ptr(), self.target.data_ptr(), self.loss.data_ptr(), gS.data_ptr(), n, st)
         if self.wgrad_side is not None:
-            ops.WGRAD_SIDE_STREAM = self.wgrad_side
+            ops.WGRAD_SIDE_STREAMS = self.wgrad_side
         try:
             out.backward(gS)
         finally:
-            ops.WGRAD_SIDE_STREAM = None
+            ops.WGRAD_SIDE_STREAMS = None
         if self.wgrad_side is not None:
-            torch.cuda.current_stream().wait_stream(self.wgrad_side)  # join the side-stream weight gradients
+            for sd in self.wgrad_side:
+                torch.cuda.current_stream().wait_stream(sd)  # join the side-stream parameter gradients
         # gather every parameter gradient into the flat arena with one launch (parameters without a gradient, e.g.
         # eta in the reference loop, keep their zeroed slot)
         n = 0
