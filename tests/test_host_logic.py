@@ -78,3 +78,61 @@ def test_zero_inserted_conv_equals_cropped_conv_transpose(H, W):
                     if oy <= 1 and ox <= 1 and ey == 0 and ex == 0:
                         assert ok
     assert checked > 0
+
+
+@pytest.mark.parametrize("C,H,W", [(8, 4, 5), (16, 3, 3)])
+def test_convT2x2_as_three_pixel_gemms(C, H, W):
+    """csrc/convT_mma.cu: ConvTranspose2d(C, C, 2, stride=2) (unet_p.py:155) as GEMMs over the P = H*W input pixels with
+    Wm[ci, (a, c, co)] = w[ci, co, a, c]: forward Y' = X Wm + pixel shuffle; dgrad dX = sum_a dY_a Wm_a^T where dY_a is
+    the output row 2h+a viewed as (c, co); wgrad dWm = X^T dY', db = column sums folded over (a, c)."""
+    rng = np.random.default_rng(C + H)
+    x = torch.from_numpy(rng.standard_normal((1, C, H, W))).requires_grad_(True)
+    w = torch.from_numpy(rng.standard_normal((C, C, 2, 2))).requires_grad_(True)
+    b = torch.from_numpy(rng.standard_normal(C)).requires_grad_(True)
+    R = torch.from_numpy(rng.standard_normal((1, C, 2 * H, 2 * W)))
+    y = F.conv_transpose2d(x, w, b, stride=2)
+    (y * R).sum().backward()
+    X = x.detach().permute(0, 2, 3, 1).reshape(H * W, C).numpy()                     # [P, Cin]
+    Wm = w.detach().permute(0, 2, 3, 1).reshape(C, 4 * C).numpy()                    # [Cin, (a, c, co)]
+    Yp = X @ Wm + np.tile(b.detach().numpy(), 4)                                     # [P, (a, c, co)]
+    y_ours = Yp.reshape(H, W, 2, 2, C).transpose(0, 2, 1, 3, 4).reshape(2 * H, 2 * W, C)   # pixel shuffle
+    np.testing.assert_allclose(y_ours, y.detach()[0].permute(1, 2, 0).numpy(), rtol=1e-10, atol=1e-10)
+    dY = R[0].permute(1, 2, 0).numpy()                                               # [2H, 2W, Cout]
+    dYp = dY.reshape(H, 2, W, 2, C).transpose(0, 2, 1, 3, 4).reshape(H * W, 4 * C)   # [P, (a, c, co)]
+    dX = np.zeros((H * W, C))
+    for a in range(2):
+        dYa = dYp[:, a * 2 * C:(a + 1) * 2 * C]                                      # output row parity a: (c, co) contiguous
+        dX += dYa @ Wm[:, a * 2 * C:(a + 1) * 2 * C].T
+    np.testing.assert_allclose(dX.reshape(H, W, C), x.grad[0].permute(1, 2, 0).numpy(), rtol=1e-10, atol=1e-10)
+    dWm = X.T @ dYp
+    np.testing.assert_allclose(dWm.reshape(C, 2, 2, C).transpose(0, 3, 1, 2), w.grad.numpy(), rtol=1e-10, atol=1e-10)
+    np.testing.assert_allclose(dYp.sum(0).reshape(4, C).sum(0), b.grad.numpy(), rtol=1e-10, atol=1e-10)
+
+
+def test_wgrad_tap_pair_tiles():
+    """conv3x3_wgrad_mma_kernel: dw[co, ci, tap] = sum_p x[p + tap] g[p, co] as five m16n8k8 tiles per 8-pixel group:
+    tile t holds taps (2t, 2t+1) in its 16 rows (8 ci each); the spare rows of tile 4 are fed ones => column sums of g."""
+    rng = np.random.default_rng(3)
+    H, W, Ci, Co = 6, 16, 8, 8
+    x = rng.standard_normal((H + 2, W + 2, Ci))          # halo tile
+    g = rng.standard_normal((H, W, Co))
+    acc = np.zeros((5, 16, Co))
+    for yy in range(H):
+        for xg in range(0, W, 8):
+            B = g[yy, xg:xg + 8]                         # [8 pixels, Co]
+            for t in range(5):
+                A = np.ones((16, 8))
+                for half in range(2):
+                    tap = 2 * t + half
+                    if tap <= 8:
+                        ky, kx = divmod(tap, 3)
+                        A[8 * half:8 * half + 8] = x[yy + ky, xg + kx:xg + kx + 8].T   # [ci, pixel]
+                acc[t] += A @ B
+    dw = np.zeros((Co, Ci, 9))
+    for tap in range(9):
+        dw[:, :, tap] = acc[tap // 2, 8 * (tap % 2):8 * (tap % 2) + 8].T
+    xt = torch.from_numpy(x).permute(2, 0, 1)[None]
+    gt = torch.from_numpy(g).permute(2, 0, 1)[None]
+    ref = torch.nn.grad.conv2d_weight(xt, (Co, Ci, 3, 3), gt, padding=0).numpy().reshape(Co, Ci, 9)
+    np.testing.assert_allclose(dw, ref, rtol=1e-10, atol=1e-10)
+    np.testing.assert_allclose(acc[4, 8], g.sum((0, 1)), rtol=1e-10, atol=1e-10)   # ones rows = bias gradient
