@@ -952,3 +952,21 @@ int conv3x3_fwd_tc(const Conv3x3Args& a, cudaStream_t st) {
 }  // namespace pu
 
 extern "C" int pu_tc_available(void) { return pu::tc_init() ? 1 : 0; }
+
+// Host-only: the tile plan pu_conv3x3_fwd would use (no device needed; for tests and tuning).
+extern "C" int pu_conv3x3_tc_plan(int B, int H, int W, int C0, int C1, int Cout, int resident, int* out16) {
+  if (out16 == nullptr || B <= 0 || H <= 0 || W <= 0) {
+    pu::set_error("pu_conv3x3_tc_plan: bad argument");
+    return PU_ERR_BAD_ARG;
+  }
+  pu::TcPlan p;
+  if (!pu::tc_plan(B, H, W, C0, C1, Cout, &p, resident != 0)) {
+    pu::set_error("pu_conv3x3_tc_plan: shape (C %d|%d -> %d, %dx%d) does not fit the tcgen05 path%s", C0, C1, Cout, H, W,
+                  resident ? " with resident weights" : "");
+    return PU_ERR_UNSUPPORTED;
+  }
+  const int v[16] = {p.TH, p.TW, p.PW, p.tilesX, p.tilesY, p.nmb, p.cols, p.n3, p.a_bytes, p.w_bytes_max, p.w_res_bytes, p.tmem_cols,
+                     p.nchunks, p.ncoblk, p.nstages, (int)p.smem_bytes};
+  for (int i = 0; i < 16; ++i) out16[i] = v[i];
+  return PU_OK;
+}

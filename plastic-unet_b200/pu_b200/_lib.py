@@ -22,6 +22,7 @@ _CTYPE = {
     "const long long*": ctypes.c_void_p,
     "double*": ctypes.c_void_p,
     "void*": ctypes.c_void_p,
+    "int*": ctypes.c_void_p,
     "int": ctypes.c_int,
     "long long": ctypes.c_longlong,
     "float": ctypes.c_float,

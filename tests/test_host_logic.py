@@ -136,3 +136,77 @@ def test_wgrad_tap_pair_tiles():
     ref = torch.nn.grad.conv2d_weight(xt, (Co, Ci, 3, 3), gt, padding=0).numpy().reshape(Co, Ci, 9)
     np.testing.assert_allclose(dw, ref, rtol=1e-10, atol=1e-10)
     np.testing.assert_allclose(acc[4, 8], g.sum((0, 1)), rtol=1e-10, atol=1e-10)   # ones rows = bias gradient
+
+
+def _plan(B, H, W, C0, C1, Cout, resident):
+    import ctypes
+    from pu_b200 import _lib
+    out = (ctypes.c_int * 16)()
+    lib = _lib.load()
+    rc = lib.pu_conv3x3_tc_plan(B, H, W, C0, C1, Cout, 1 if resident else 0, ctypes.addressof(out))
+    if rc != 0:
+        return None
+    keys = ["TH", "TW", "PW", "tilesX", "tilesY", "nmb", "cols", "n3", "a_bytes", "w_stage", "w_res", "tmem_cols", "nchunks",
+            "ncoblk", "nstages", "smem"]
+    return dict(zip(keys, list(out)))
+
+
+def _model_conv_shapes():
+    """(C0, C1, Cout, side, batch) of every tcgen05-eligible 3x3 conv (forward and its dgrad) of UNetp @128/@512,
+    UNetpCoord @128 and UNetpRes n16/n8 @101 (reference unet_p.py:33-49, unet_p_res.py:36-66)."""
+    shapes = set()
+    for side, B in ((128, 64), (512, 4)):
+        ch = [8, 16, 32, 64, 64]
+        for lvl in range(5):
+            s = side >> lvl
+            c = ch[lvl]
+            shapes.add((c, 0, c, s, B))                       # second conv of a double_conv (+ its dgrad: same shape)
+            if lvl > 0:
+                shapes.add((ch[lvl - 1], 0, c, s, B))         # first conv of down
+                shapes.add((c, 0, ch[lvl - 1], s, B))         # its dgrad
+        for cin, cout, lvl in ((64, 32, 3), (32, 16, 2), (16, 8, 1), (8, 8, 0)):
+            s = side >> lvl
+            shapes.add((cin, cin, cout, s, B))                # conv on cat[skip, up]
+            shapes.add((cout, 0, 2 * cin, s, B))              # its dgrad (outputs split over the two sources)
+    for n in (16, 8):
+        sizes = [101, 50, 25, 12, 6]
+        for lvl in range(5):
+            c = n << lvl
+            shapes.add((c, 0, c, sizes[lvl], 32))
+            if lvl > 0:
+                shapes.add((c >> 1, 0, c, sizes[lvl], 32))
+                shapes.add((c, 0, c >> 1, sizes[lvl], 32))
+                shapes.add((c >> 1, c >> 1, c >> 1, sizes[lvl - 1], 32))   # up: cat[up, skip] -> C/2
+                shapes.add((c >> 1, 0, c, sizes[lvl - 1], 32))             # its dgrad
+                shapes.add((c, 0, c >> 1, sizes[lvl - 1], 32))             # transposed conv as a conv on the canvas
+    return sorted(t for t in shapes if t is not None)
+
+
+def test_tc_conv_planner_invariants():
+    """Host-only planner of csrc/conv3x3_tc.cu (pu_conv3x3_tc_plan): every conv shape of the models gets a plan that
+    respects the hardware limits the kernel relies on."""
+    shapes = _model_conv_shapes()
+    assert len(shapes) > 40
+    planned = 0
+    for (C0, C1, Cout, side, B) in shapes:
+        for resident in (True, False):
+            p = _plan(B, side, side, C0, C1, Cout, resident)
+            if p is None:
+                assert resident, "streamed-weights plan must exist for %s" % ((C0, C1, Cout, side, B),)
+                continue
+            planned += 1
+            ctx = ((C0, C1, Cout, side, B, resident), p)
+            assert p["cols"] in (8, 16, 32, 64) and p["n3"] == -(-3 * p["cols"] // 16) * 16, ctx
+            assert p["PW"] == p["TW"] + 2 and p["PW"] <= 256 and p["TH"] + 2 <= 256, ctx            # TMA box limits
+            assert p["tilesX"] * p["TW"] >= side and p["tilesY"] * p["TH"] >= side, ctx               # tiles cover the image
+            assert p["nmb"] * 96 >= p["TH"] * p["PW"], ctx                                           # blocks cover the tile rows
+            assert p["nmb"] * p["n3"] <= 256, ctx                                                    # one TMEM accumulator buffer
+            assert p["tmem_cols"] <= 512 and p["tmem_cols"] >= 2 * p["nmb"] * p["n3"], ctx
+            assert p["tmem_cols"] & (p["tmem_cols"] - 1) == 0 and p["tmem_cols"] >= 32, ctx
+            assert 2 <= p["nstages"] <= 4 and p["a_bytes"] % 1024 == 0 and p["w_stage"] % 1024 == 0, ctx
+            assert p["smem"] <= 227 * 1024, ctx
+            assert (p["w_res"] > 0) == resident and (p["w_stage"] == 0) == resident, ctx
+            assert p["ncoblk"] == -(-Cout // 64) and 1 <= p["nchunks"] <= 40, ctx
+            # shared memory accounting: stages + resident weights + bookkeeping
+            assert p["smem"] >= p["nstages"] * (p["a_bytes"] + p["w_stage"]) + p["w_res"], ctx
+    assert planned > len(shapes)  # most shapes have both a resident and a streamed plan
