@@ -224,6 +224,24 @@ int pu_trace_update_bwd(const float* hebb, const float* pre, const float* post, 
                         const float* eta, int rule, const float* gout,
                         float* ghebb, float* gpre, float* gpost, float* geta, int N, void* stream);
 
+/* ---- inference tail: integer / byte work, bit-exact ------------------------------- */
+/* Threshold sweep: confusion counts of (label class, pred > thr[j]) for every image b and EVERY threshold j in one pass
+ * over the predictions (reference eval.py:48-52 sweeps 31 thresholds, re-reading the predictions 31 times;
+ * utils/iou_metric.py:34-36 bins labels and predictions with np.histogram(bins=[0,0.5,1]); utils/iou_metric.py:10,23 use
+ * `A > 0` / `pred > 0.5`).  pred, label: [B, npix] fp32.  thr_sorted: T <= 64 thresholds, ASCENDING, device doubles
+ * (the comparison is (double)pred > thr, as numpy does against a float64 threshold array).
+ * label_mode 0: histogram bins [0,0.5) -> 0, [0.5,1] -> 1, anything else dropped; 1: label > 0.
+ * hist_ws: [B*3*(T+1)] int32 workspace.  counts: [B][T][6] int32 = {c00, c01, c10, c11, pred_ones, npix}
+ * (c<true><pred> over pixels with a valid label; pred_ones over all pixels).                                */
+int pu_threshold_counts(const float* pred, const float* label, const double* thr_sorted, int T, int label_mode, int B, long long npix,
+                        int* hist_ws, int* counts, void* stream);
+/* Mask threshold + run-length encoding (reference infer.py:81,88,99 `mask > mask_threshold`; utils/rle_encode.py:6-17:
+ * column-major flattening, 1-based run starts, "start length" pairs).  pred: [B, R, C] fp32 row-major.  mask (nullable):
+ * [B, R, C] uint8 = pred > thr.  runs: [B][cap] int32, image b gets count[b] ints = (start, length) pairs in order;
+ * count[b] = -(needed ints) if cap is too small (cap = R*C + 2 always suffices).  One CTA per image; R*C <= ~1.8 M.    */
+int pu_mask_rle(const float* pred, double thr, int B, int R, int C, unsigned char* mask, int* runs, int cap, int* count, void* stream);
+long long pu_mask_rle_smem_bytes(int R, int C);
+
 /* ---- train-step tail (reference train.py:66-70,101-112) ------------------ */
 /* loss = mean BCE(S, T) with log clamped at -100 (nn.BCELoss); gS = dloss/dS. loss is a device scalar. */
 int pu_bce_fwd_bwd(const float* S, const float* T, float* loss, float* gS, long long n, void* stream);

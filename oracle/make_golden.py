@@ -60,12 +60,23 @@ def save_weights(wname, sd0):
     np.savez_compressed(os.path.join(OUT, wname + '.npz'), **{k: v.numpy() for k, v in sd0.items()})
 
 
-def run_case(name, wname, kind, ctor, ctor_kw, body_kw, n_in, seed_w, seed_x, train_mode=True, dropout_seed=None):
+def weight_fingerprint(sd0):
+    """Per-key float64 (sum, L2) of a state_dict: lets a test that re-creates seeded weights prove they are the reference's."""
+    keys = list(sd0.keys())
+    return {'w_keys': np.array(keys), 'w_sum': np.array([float(sd0[k].double().sum()) for k in keys]),
+            'w_l2': np.array([float(sd0[k].double().norm()) for k in keys])}
+
+
+def run_case(name, wname, kind, ctor, ctor_kw, body_kw, n_in, seed_w, seed_x, train_mode=True, dropout_seed=None,
+             weights_by_seed=False):
+    """weights_by_seed: do not store the (multi-MB) initial weights; store the seed + a per-key fingerprint instead.  The
+    tests re-create them with the drop-in constructor (same RNG consumption as the reference, tests/test_boundary.py)."""
     torch.manual_seed(seed_w)
     net = quiet(ctor, 1, 1, torch.device('cpu'), **ctor_kw)
     net.train(train_mode)
     sd0 = {k: v.detach().clone() for k, v in net.state_dict().items()}
-    save_weights(wname, sd0)
+    if not weights_by_seed:
+        save_weights(wname, sd0)
     nbf = net.nbf
     g = torch.Generator().manual_seed(seed_x)
     x = torch.rand(1, 1, n_in, n_in, generator=g)
@@ -132,7 +143,10 @@ def run_case(name, wname, kind, ctor, ctor_kw, body_kw, n_in, seed_w, seed_x, tr
     }
     for k in full[:FULL_GRAD_KEYS_MAX]:
         blob['grad::' + k] = grads_r[k].numpy()
-    blob['weights_file'] = np.array(wname)
+    blob['weights_file'] = np.array('' if weights_by_seed else wname)
+    if weights_by_seed:
+        blob['weights_seed'] = np.array(seed_w)
+        blob.update(weight_fingerprint(sd0))
     blob['ctor_kw'] = np.array(repr(ctor_kw))
     for k, v in sd_after.items():
         if k.endswith('running_mean') or k.endswith('running_var'):
@@ -186,8 +200,145 @@ def run_train_case(name, wname, ctor, ctor_kw, kind, n_in, steps, lr, seed_w):
     print('%-28s ok  losses=%s' % (name, ['%.5f' % l for l in losses]))
 
 
+def run_margin_case(name, ctor, ctor_kw, kind, n_in, steps=300, lr=3e-3):
+    """A weight state with decision margin: the reference trained for `steps` steps (train.py:91-112) on separable
+    synthetic data (mask = a smooth function of the image), so that the logits of a held-out image are far from
+    every threshold of eval.py:48-50 — the mask tests then hold on EVERY pixel (no exempt pixels).  The data seed is
+    searched until min_pixel,threshold |logit - logit(thr)| > MARGIN."""
+    from torch.autograd import Variable
+    MARGIN = 2e-4
+    thr = np.concatenate([[0.5], np.linspace(0.3, 0.7, 31)])
+    thr_logit = torch.from_numpy(np.log(thr / (1 - thr))).float()
+    for seed in range(100, 140):
+        torch.manual_seed(30)
+        net = quiet(ctor, 1, 1, torch.device('cpu'), **ctor_kw)
+        net.train()
+        g = torch.Generator().manual_seed(seed)
+        nbf = net.nbf
+
+        def sample():
+            # a bright disc on a dim noisy background; the mask is the disc
+            cy, cx = (torch.rand(2, generator=g) * (n_in - 12) + 6).tolist()
+            r = float(torch.rand(1, generator=g)) * 5 + 7
+            yy, xx = torch.meshgrid(torch.arange(n_in).float(), torch.arange(n_in).float(), indexing='ij')
+            m = (((yy - cy) ** 2 + (xx - cx) ** 2) < r * r).float()
+            img = 0.15 * torch.rand(n_in, n_in, generator=g) + 0.8 * m
+            return img[None], m
+
+        opt = torch.optim.Adam(net.parameters(), lr=lr)
+        crit = torch.nn.BCELoss()
+        hebb = net.initialZeroHebb()
+        for _ in range(steps):
+            img, m = sample()
+            opt.zero_grad()
+            y_pred, hebb = net(Variable(img[None], requires_grad=False), Variable(hebb, requires_grad=False))
+            loss = crit(y_pred.view(-1), m.view(-1))
+            loss.backward()
+            opt.step()
+        net.eval()
+        img, m = sample()
+        sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+        with torch.no_grad():
+            out_r, hebb_r = net(img[None], hebb.detach())
+            activ_o, out_o, hebb_o = orc.forward(kind, sd, img[None], hebb.detach(), rule=ctor_kw.get('rule', 'hebb'), training=False)
+        assert torch.equal(out_o, out_r) and torch.equal(hebb_o, hebb_r)
+        margin = float((activ_o.view(-1, 1) - thr_logit.view(1, -1)).abs().min())
+        if margin > MARGIN:
+            break
+    else:
+        raise SystemExit('no seed with margin > %g found' % MARGIN)
+    wname = 'w_' + name
+    save_weights(wname, sd)
+    blob = {'meta_kind': np.array(kind), 'meta_rule': np.array(ctor_kw.get('rule', 'hebb')), 'meta_train': np.array(0),
+            'x': img[None].numpy(), 'hebb': hebb.detach().numpy(), 'target': m.numpy(), 'activ': activ_o.numpy(),
+            'activout': out_r.numpy(), 'hebb_new': hebb_r.numpy(), 'margin': np.array(margin), 'final_loss': np.array(float(loss)),
+            'weights_file': np.array(wname), 'ctor_kw': np.array(repr(ctor_kw))}
+    np.savez_compressed(os.path.join(OUT, name + '.npz'), **blob)
+    print('%-28s ok  seed=%d  train loss=%.4f  min margin to any of 32 thresholds=%.3e  logit range [%.2f, %.2f]  mask px %d / IoU@0.5 %.3f'
+          % (name, seed, float(loss), margin, float(activ_o.min()), float(activ_o.max()), int((out_r > 0.5).sum()),
+             float(((out_r > 0.5) & (m > 0)).sum()) / max(1.0, float(((out_r > 0.5) | (m > 0)).sum()))))
+
+
+def run_infer_tail_golden():
+    """Inference tail: run the REFERENCE's own eval.score_model_best_iou (through a stand-in net that
+    replays fixed predictions), eval.eval_net's fast_iou_metric, infer.py's threshold and utils.rle_encode.encode; assert
+    that oracle/infer_tail_oracle.py returns identical values; store inputs + outputs."""
+    import infer_tail_oracle as ito
+    import ref_loader
+    ref = ref_loader.load('/root/reference/src')
+    g = torch.Generator().manual_seed(77)
+
+    def blobs(n, R, C, smooth=5):
+        z = torch.randn(n, 1, R, C, generator=g)
+        k = torch.ones(1, 1, smooth, smooth) / smooth ** 2
+        return torch.nn.functional.conv2d(z, k, padding=smooth // 2)[:, 0]
+
+    class ReplayNet:  # just enough of the nn.Module surface for eval.py:33-45
+        def __init__(self, preds):
+            self.preds, self.i = preds, 0
+
+        def eval(self):
+            return self
+
+        def initialZeroHebb(self):
+            return torch.zeros(1)
+
+        def __call__(self, x, hebb):
+            y = self.preds[self.i]
+            self.i += 1
+            return y, hebb
+
+    blob = {}
+    for tag, B, R, C in (('a', 10, 37, 37), ('b', 5, 101, 101)):
+        base = blobs(B, R, C)
+        labels = (base > 0.1).float()
+        logits = 9.0 * (base - 0.1) + 0.6 * blobs(B, R, C, 3)  # correlated with the labels: IoU varies over the sweep
+        preds = torch.sigmoid(logits)
+        # edge cases: empty / full predictions, empty label, last column-major pixel set, checkerboard
+        preds[0].fill_(0.01)
+        preds[1].fill_(0.99)
+        labels[2].zero_()
+        if B > 5:
+            preds[3].fill_(0.2)
+            preds[3][-1, -1] = 0.9
+            preds[3][0, 0] = 0.9
+            ii, jj = torch.meshgrid(torch.arange(R), torch.arange(C), indexing='ij')
+            preds[4] = ((ii + jj) % 2).float() * 0.8 + 0.1
+        X = np.zeros((B, 1, R, C), dtype=np.float64)
+        y_valid = labels.numpy().astype(np.float64)
+        # eval.py:20-64 on the replayed predictions
+        thr_best, iou_best = ref.eval_.score_model_best_iou(ReplayNet([p for p in preds]), X, y_valid, torch.device('cpu'))
+        preds_np = preds.numpy()
+        o_thr, o_iou, o_ious = ito.sweep_best_iou(y_valid, [p for p in preds_np])
+        assert o_thr == thr_best and o_iou == iou_best and o_iou.dtype == iou_best.dtype, (o_thr, thr_best, o_iou, iou_best)
+        ref_ious = np.array([ref.iou_metric.iou_metric_batch(y_valid, preds_np > t) for t in ito.sweep_thresholds()])
+        assert np.array_equal(ref_ious, o_ious) and ref_ious.dtype == o_ious.dtype
+        # eval.py:100: fast_iou_metric on the flattened prediction / target of each image
+        fast = np.array([ref.iou_metric.fast_iou_metric(y_true_in=y_valid[b].astype(np.float32).reshape(-1), y_pred_in=preds_np[b].reshape(-1))
+                         for b in range(B)])
+        fast_o = np.array([ito.fast_iou_metric(y_valid[b].astype(np.float32).reshape(-1), preds_np[b].reshape(-1)) for b in range(B)])
+        assert np.array_equal(fast, fast_o)
+        # infer.py:81,99 at a few mask thresholds
+        rles = {}
+        for mt in (0.5, 0.35, 0.62):
+            enc = [ref.rle_encode.encode(np.round(preds_np[b] > mt)) for b in range(B)]
+            enc_o = [ito.rle_encode(np.round(preds_np[b] > mt)) for b in range(B)]
+            assert enc == enc_o
+            alt = [ref.rle_encode.rle_encode((preds_np[b] > mt).astype(np.uint8)) for b in range(B)]  # the second implementation agrees
+            assert alt == enc
+            rles[mt] = enc
+            blob['%s_rle_%g' % (tag, mt)] = np.array(enc)
+            blob['%s_mask_%g' % (tag, mt)] = np.stack([(preds_np[b] > mt).astype(np.uint8) for b in range(B)])
+        blob.update({tag + '_preds': preds_np, tag + '_labels': labels.numpy(), tag + '_ious': ref_ious,
+                     tag + '_thr_best': np.array(thr_best), tag + '_iou_best': np.array(iou_best), tag + '_fast_iou': fast})
+        print('infer_tail[%s]  B=%d %dx%d  best thr %.4f iou %.4f  fast_iou %s  rle lens %s' %
+              (tag, B, R, C, thr_best, iou_best, np.round(fast, 3), [len(s) for s in rles[0.5]]))
+    np.savez_compressed(os.path.join(OUT, 'infer_tail.npz'), **blob)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    run_infer_tail_golden()
     torch.set_num_threads(1)  # bit-reproducible reductions
     run_case('unetp_hebb_n32', 'w_unetp_n32_s0', 'unetp', UNetp, dict(rule='hebb', nbf=32), {}, 32, 0, 1)
     run_case('unetp_oja_n32', 'w_unetp_n32_s0', 'unetp', UNetp, dict(rule='oja', nbf=32, alfa_type='yoked'), {}, 32, 0, 2)
@@ -204,6 +355,14 @@ def main():
     run_case('unetpres_bn_n32_train', 'w_unetpres2_bn_n32_s12', 'unetpres', UNetpRes,
              dict(neurons=2, dropout_ratio=0.0, rule='hebb', nbf=32, batch_norm=True), dict(dropout_ratio=0.0, batch_norm=True),
              32, 12, 13)
+    # BASELINE sizes (configs[1] and configs[3]): UNetp @128 and the script variant UNetpRes(neurons=8) @101
+    # (unet_p_res_script.py:30,781-788: default dropout 0.5, hebb); weights re-created from the seed by the tests
+    run_case('unetp_oja_n128', '', 'unetp', UNetp, dict(rule='oja', nbf=128), {}, 128, 20, 21, weights_by_seed=True)
+    run_case('unetpres8_hebb_n101_dropout', '', 'unetpres', UNetpRes, dict(neurons=8, rule='hebb', nbf=101),
+             dict(dropout_ratio=0.5), 101, 22, 23, dropout_seed=321, weights_by_seed=True)
+    run_case('unetpres8_oja_n101_eval', '', 'unetpres', UNetpRes, dict(neurons=8, rule='oja', nbf=101),
+             dict(dropout_ratio=0.5), 101, 22, 24, train_mode=False, weights_by_seed=True)
+    run_margin_case('margin_unetp_oja_n32', UNetp, dict(rule='oja', nbf=32), 'unetp', 32)
     run_train_case('train_unetp_hebb_n32', 'w_unetp_n32_s0', UNetp, dict(rule='hebb', nbf=32), 'unetp', 32, 4, 1e-3, 0)
     run_train_case('train_unetpres_oja_n21', 'w_unetpres4_n21_s7', UNetpRes, dict(neurons=4, dropout_ratio=0.0, rule='oja', nbf=21),
                    'unetpres', 21, 4, 1e-3, 7)

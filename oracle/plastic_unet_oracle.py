@@ -265,6 +265,28 @@ def train_steps(kind, sd, images, masks, rule, lr=1e-4, gamma=1.0, steplr=1e9, h
     return losses, hebb.detach()
 
 
+def train_steps_batched(kind, sd, batches, rule, lr=1e-4, hebb=None, **body_kw):
+    """Batched extension of train.py:91-112 (no reference: the reference is B=1 only, unet_p.py:55-56): per step one
+    batch [B,C,H,W] through `forward` (shared trace, mean of the per-sample trace updates), BCELoss over all B*nbf^2
+    outputs, backward, Adam.step; the trace is carried detached (train.py:99).  At B == 1 this is train_steps().
+    `batches`: iterable of (x [B,C,H,W], target [B,nbf,nbf]).  -> (losses, hebb)"""
+    params = [v for k, v in sd.items() if v.is_floating_point() and v.requires_grad]
+    opt = torch.optim.Adam(params, lr=1.0 * lr)  # train.py:66
+    crit = torch.nn.BCELoss()  # :70
+    nbf = sd['w'].shape[0]
+    if hebb is None:
+        hebb = torch.zeros(nbf, nbf, dtype=sd['w'].dtype)  # train.py:88
+    losses = []
+    for x, target in batches:
+        opt.zero_grad()
+        _, y_pred, hebb = forward(kind, sd, x, hebb.detach(), rule=rule, **body_kw)  # :99
+        loss = crit(y_pred.reshape(-1), target.reshape(-1))  # :101-105
+        losses.append(loss.item())  # :106
+        loss.backward()  # :110
+        opt.step()  # :111
+    return losses, hebb.detach()
+
+
 def bce_mean(pred, target):
     """nn.BCELoss (train.py:70): mean over elements of -(t*max(log p,-100) + (1-t)*max(log(1-p),-100))."""
     return F.binary_cross_entropy(pred, target)

@@ -23,6 +23,9 @@ _CTYPE = {
     "double*": ctypes.c_void_p,
     "void*": ctypes.c_void_p,
     "int*": ctypes.c_void_p,
+    "const int*": ctypes.c_void_p,
+    "unsigned char*": ctypes.c_void_p,
+    "double": ctypes.c_double,
     "int": ctypes.c_int,
     "long long": ctypes.c_longlong,
     "float": ctypes.c_float,

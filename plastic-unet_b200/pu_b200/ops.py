@@ -43,6 +43,19 @@ WGRAD_SIDE_STREAMS = None
 _side_rr = 0
 
 
+# debug hook of TrainStep: when a set, every tensor a backward op WRITES on a side stream registers its data_ptr here, so
+# that the trainer can assert that autograd handed exactly those tensors over as .grad (stolen, not copied on the main
+# stream while the side stream is still writing)
+SIDE_OUTPUTS = None
+
+
+def _note_side(*ts):
+    if SIDE_OUTPUTS is not None:
+        for t in ts:
+            if t is not None and t.numel() > 0:
+                SIDE_OUTPUTS.add(t.data_ptr())
+
+
 def _side_stream():
     global _side_rr
     if not WGRAD_SIDE_STREAMS:
@@ -193,6 +206,7 @@ def conv3x3_bwd(dy: Tensor, y: Tensor, x0: Tensor, x1: Optional[Tensor], weight:
                 if t is not None:
                     t.record_stream(side)
             dw.record_stream(main)
+            _note_side(dw, db if db_in_wgrad else None)
         else:
             dw = torch.empty_like(weight)
             _lib.call("pu_conv3x3_wgrad", x0.data_ptr(), H0, W0, C0, oy0, ox0, _p(x1), H1, W1, C1, oy1, ox1,
@@ -343,6 +357,7 @@ def convT2x2s2_bwd(dy: Tensor, x: Tensor, weight: Tensor, need_dx: bool, need_dw
         for t in (x, dy, dw if need_dw else None, db if need_db else None):
             if t is not None:
                 t.record_stream(side)
+        _note_side(dw if need_dw else None, db if need_db else None)
     else:
         _lib.call("pu_convT2x2s2_bwd", x.data_ptr(), weight.data_ptr(), dy.data_ptr(), dx.data_ptr() if need_dx else None,
                   dw.data_ptr() if need_dw else None, db.data_ptr() if need_db else None, B, H, W, Cin, Cout, flags, _s())
@@ -451,6 +466,7 @@ def convT3x3s2_tc_bwd(dy: Tensor, x: Tensor, weight: Tensor, has_bias: bool, nee
             x.record_stream(side)
             g.record_stream(side)
             dw.record_stream(main)
+            _note_side(dw)
         else:
             dw = wgrad()
     return [dx, dw, db]
@@ -831,9 +847,10 @@ def plastic_head_bwd(gS: Tensor, X: Tensor, S: Tensor, weff: Tensor, alpha: Tens
             _lib.call("pu_plastic_head_bwd", X.data_ptr(), S.data_ptr(), None, weff.data_ptr(), alpha.data_ptr(), hebb.data_ptr(),
                       gA.data_ptr(), None, gw.data_ptr(), galpha.data_ptr() if need_galpha else None,
                       ghebb.data_ptr() if need_ghebb else None, B, N, _s())
-        for t in (X, gA, alpha, hebb, gw, galpha if need_galpha else None, ghebb if need_ghebb else None):
+        for t in (X, S, weff, gA, alpha, hebb, gw, galpha if need_galpha else None, ghebb if need_ghebb else None):
             if t is not None:
                 t.record_stream(side)
+        _note_side(gw, galpha if need_galpha else None)
     else:
         _lib.call("pu_plastic_head_bwd", X.data_ptr(), S.data_ptr(), gS.data_ptr(), weff.data_ptr(), alpha.data_ptr(), hebb.data_ptr(),
                   gA.data_ptr(), gX.data_ptr() if need_gx else None, gw.data_ptr(), galpha.data_ptr() if need_galpha else None,

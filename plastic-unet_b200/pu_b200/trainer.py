@@ -73,12 +73,25 @@ class TrainStep:
         gS = torch.empty_like(out)
         n = out.numel()
         _lib.call("pu_bce_fwd_bwd", out.data_ptr(), self.target.data_ptr(), self.loss.data_ptr(), gS.data_ptr(), n, st)
+        check = getattr(self, "_check_grads", False) and self.wgrad_side is not None
         if self.wgrad_side is not None:
             ops.WGRAD_SIDE_STREAMS = self.wgrad_side
+        if check:
+            ops.SIDE_OUTPUTS = set()
         try:
             out.backward(gS)
         finally:
             ops.WGRAD_SIDE_STREAMS = None
+            side_ptrs, ops.SIDE_OUTPUTS = ops.SIDE_OUTPUTS, None
+        if check:
+            # The side-stream gradient kernels are ordered against the main stream only by the join below.  That is safe
+            # iff autograd handed the very tensors those kernels write over as .grad (no copy / accumulation kernel on
+            # the main stream in between): assert it once, on the first eager warm-up step.
+            got = {p.grad.data_ptr() for p in self.params if p.grad is not None}
+            if not side_ptrs <= got:
+                raise RuntimeError("TrainStep: %d side-stream parameter gradients were copied or accumulated by autograd "
+                                   "instead of being handed over (grad hooks / retain_graph?); set PU_WGRAD_SIDE=0"
+                                   % len(side_ptrs - got))
         if self.wgrad_side is not None:
             for sd in self.wgrad_side:
                 torch.cuda.current_stream().wait_stream(sd)  # join the side-stream parameter gradients
@@ -101,25 +114,44 @@ class TrainStep:
             torch.cuda.current_stream().wait_stream(self.net.dp_side)  # join the deferred trace all-reduce + epilogue
         self.hebb.copy_(hebb_new.detach())
 
+    def _state_tensors(self):
+        """Every tensor a step mutates: the optimizer state, the trace and the BatchNorm buffers."""
+        return [self.flat_p, self.m, self.v, self.step_count, self.hebb] + [b for b in self.net.buffers()]
+
     def capture(self):
-        """Warm up on a side stream, then capture one step into a CUDA graph."""
+        """Warm up on a side stream, then capture one step into a CUDA graph.  The warm-up runs real steps (on the
+        zero-filled static buffers), so the optimizer state, the trace and the BN buffers are snapshotted first and
+        restored afterwards: capture() leaves the model exactly as it found it (step count 0, trace untouched)."""
+        saved = [t.detach().clone() for t in self._state_tensors()]
+
+        def restore():
+            for t, s0 in zip(self._state_tensors(), saved):
+                t.copy_(s0)
+
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
-            for _ in range(self._warm):
+            for i in range(self._warm):
+                self._check_grads = (i == 0)
                 self._step_body()
+        self._check_grads = False
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         if not self.use_graph:
             before = _lib.launch_count()
             self._step_body()
             self.kernels_per_step = _lib.launch_count() - before
+            torch.cuda.synchronize()
+            restore()
+            torch.cuda.synchronize()
             return self
         self.graph = torch.cuda.CUDAGraph()
         before = _lib.launch_count()
         with torch.cuda.graph(self.graph):
             self._step_body()
         self.kernels_per_step = _lib.launch_count() - before
+        restore()
+        torch.cuda.synchronize()
         return self
 
     def reset_trace(self):

@@ -44,13 +44,27 @@ class Case:
         self.kind = str(self.z["meta_kind"])
         self.rule = str(self.z["meta_rule"])
         self.ctor_kw = ast.literal_eval(str(self.z["ctor_kw"]))
-        self.weights = np.load(os.path.join(GOLDEN, str(self.z["weights_file"]) + ".npz"), allow_pickle=False)
+        wfile = str(self.z["weights_file"])
+        self.weights = np.load(os.path.join(GOLDEN, wfile + ".npz"), allow_pickle=False) if wfile else None
 
     def t(self, key, device="cpu", dtype=torch.float32):
         return torch.from_numpy(np.asarray(self.z[key])).to(device=device, dtype=dtype)
 
     def state_dict(self, device="cpu"):
         out = {}
+        if self.weights is None:
+            # big cases: the reference's seeded initial weights are re-created with the drop-in constructor (same RNG
+            # consumption, tests/test_boundary.py) and proven identical through the stored per-key fingerprint
+            import pu_b200
+            cls = pu_b200.UNetp if self.kind == "unetp" else pu_b200.UNetpRes
+            torch.manual_seed(int(self.z["weights_seed"]))
+            sd = quiet(cls, 1, 1, torch.device("cpu"), **self.ctor_kw).state_dict()
+            assert [str(k) for k in self.z["w_keys"]] == list(sd.keys())
+            for k, s, l2 in zip(sd.keys(), self.z["w_sum"], self.z["w_l2"]):
+                v = sd[k].double()
+                assert float(v.sum()) == float(s) and float(v.norm()) == float(l2), "seeded weights differ from the reference's: " + k
+                out[k] = sd[k].detach().clone().to(device)
+            return out
         for k in self.weights.files:
             out[k] = torch.from_numpy(self.weights[k]).to(device)
         return out
@@ -73,7 +87,11 @@ class Case:
 
 
 FWD_CASES = ["unetp_hebb_n32", "unetp_oja_n32", "unetp_crop_n32_in37", "unetp_bn_bilinear_n32", "unetpres_hebb_n21",
-             "unetpres_oja_n21_dropout", "unetpres_bn_n21_eval", "unetpres_bn_n32_train"]
+             "unetpres_oja_n21_dropout", "unetpres_bn_n21_eval", "unetpres_bn_n32_train",
+             # BASELINE sizes: configs[1] (UNetp @128) and configs[3] (unet_p_res_script.py variant, neurons 8 @101)
+             "unetp_oja_n128", "unetpres8_hebb_n101_dropout", "unetpres8_oja_n101_eval"]
+BIG_CASES = ["unetp_oja_n128", "unetpres8_hebb_n101_dropout", "unetpres8_oja_n101_eval"]
+MARGIN_CASES = ["margin_unetp_oja_n32"]
 TRAIN_CASES = ["train_unetp_hebb_n32", "train_unetpres_oja_n21"]
 
 

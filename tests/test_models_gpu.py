@@ -14,7 +14,7 @@ import pytest
 import torch
 
 import plastic_unet_oracle as orc
-from conftest import FWD_CASES, TRAIN_CASES, Case, quiet, rel_err
+from conftest import BIG_CASES, FWD_CASES, MARGIN_CASES, TRAIN_CASES, Case, quiet, rel_err
 
 pytestmark = pytest.mark.gpu
 DEV = torch.device("cuda")
@@ -80,6 +80,117 @@ def test_golden_forward_backward(name):
         assert torch.equal((got > thr)[decided], (ref_out > thr)[decided]), "mask mismatch at threshold %g" % thr
     undecided = int((logit.abs() <= MASK_TAU).sum())
     assert undecided <= 0.02 * logit.numel(), "too many pixels within MASK_TAU of the boundary: %d" % undecided
+
+
+# ---- TF32 (tcgen05) throughput mode against the SAME goldens of the real reference --------------------------------
+# Tolerances of the TF32 mode: outputs and trace 1e-3 of max; parameter gradients: L2-relative error per
+# tensor (bounds below, measured values printed); masks: equal on every pixel whose reference logit is farther than
+# TF32_MASK_TAU * max|logit| from the threshold, flipped / exempt pixel counts printed.
+TF32_OUT_TOL = 1e-3
+TF32_GRAD_TOL = 2e-3   # L2-relative, per parameter tensor ...
+TF32_GRAD_YARD = 3.0   # ... or 3x the error the REFERENCE's own default GPU path makes on the same tensor (see below)
+TF32_MASK_TAU = 2e-3
+
+
+def _cudnn_tf32_yardstick(c):
+    """What the unmodified reference would compute on this GPU: stock PyTorch convolutions with
+    torch.backends.cudnn.allow_tf32 = True (PyTorch's DEFAULT) — the oracle's functional restatement of the reference run
+    on the CUDA device.  TF32 rounding makes gradients that are small differences of large terms (the goldens' loss adds
+    (hebb' * R).sum(), which drives a huge gradient through row 0 only) arbitrarily inaccurate in RELATIVE terms; the
+    honest tolerance for the tcgen05 TF32 mode is therefore "no worse than a small multiple of the reference's own TF32
+    error", measured here on the same inputs.  -> {param: L2-relative error vs the fp32 golden}"""
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = True, False
+    try:
+        sd = orc.leaf_state({k: v.to(DEV) for k, v in c.state_dict().items()})
+        x = c.t("x", DEV).requires_grad_(True)
+        hebb = c.t("hebb", DEV).requires_grad_(True)
+        kw = c.body_kw()
+        masks = c.masks(DEV)
+        if masks:
+            kw["masks"] = list(masks)
+        _, out, hn = orc.forward(c.kind, sd, x, hebb, rule=c.rule, alfa_type=c.ctor_kw.get("alfa_type", "free"), **kw)
+        (orc.bce_mean(out.view(-1), c.t("target", DEV)) + (hn * c.t("R", DEV)).sum()).backward()
+        res = {k[6:]: rel_err(sd[k[6:]].grad, c.t(k))[1] for k in c.z.files if k.startswith("grad::")}
+        res["x"] = rel_err(x.grad, c.t("grad_x"))[1]
+        norms = {k: abs(float(sd[k].grad.double().norm()) - l2) / max(l2, 1e-30)
+                 for k, l2 in zip([str(k) for k in c.z["grad_keys"]], c.z["grad_l2"]) if l2 > 1e-6 * float(np.max(c.z["grad_l2"]))}
+        return res, max(norms.values())
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+TF32_CASES = ["unetp_hebb_n32", "unetp_oja_n32", "unetp_crop_n32_in37", "unetpres_hebb_n21", "unetpres_oja_n21_dropout"] + BIG_CASES
+
+
+def _mask_report(got, logit, ref_out, tau_abs):
+    """-> (flipped pixels over all 32 thresholds, exempt pixel-threshold pairs, mismatches outside the margin)."""
+    flipped = exempt = bad = 0
+    for thr in [0.5] + list(np.linspace(0.3, 0.7, 31)):  # infer.py:81, iou_metric.py:23, eval.py:48-50
+        margin = (logit - float(np.log(thr / (1 - thr)))).abs()
+        decided = margin > tau_abs
+        diff = (got > thr) != (ref_out > thr)
+        flipped += int(diff.sum())
+        exempt += int((~decided).sum())
+        bad += int((diff & decided).sum())
+    return flipped, exempt, bad
+
+
+@pytest.mark.parametrize("name", TF32_CASES)
+def test_golden_tf32_mode(name):
+    import pu_b200.modules as M
+    c = Case(name)
+    net = build(c)
+    net.conv_math = "tf32"
+    net.train(bool(int(c.z["meta_train"])))
+    x = c.t("x", DEV).requires_grad_(True)
+    hebb = c.t("hebb", DEV).requires_grad_(True)
+    masks = c.masks(DEV)
+    M.DROPOUT_MASK_QUEUE = list(masks) if masks else None
+    try:
+        out, hebb_new = net(x, hebb)
+    finally:
+        M.DROPOUT_MASK_QUEUE = None
+    loss = torch.nn.BCELoss()(out.view(-1), c.t("target", DEV)) + (hebb_new * c.t("R", DEV)).sum()
+    loss.backward()
+    e_out, e_tr = rel_err(out, c.t("activout"))[0], rel_err(hebb_new, c.t("hebb_new"))[0]
+    grads = dict(net.named_parameters())
+    full = {k[6:]: rel_err(grads[k[6:]].grad, c.t(k)) for k in c.z.files if k.startswith("grad::")}
+    norm_dev = max(abs(float(grads[k].grad.double().norm()) - l2) / max(l2, 1e-30)
+                   for k, l2 in zip([str(k) for k in c.z["grad_keys"]], c.z["grad_l2"]) if l2 > 1e-6 * float(np.max(c.z["grad_l2"])))
+    logit = c.t("activ")
+    flipped, exempt, bad = _mask_report(out.detach().cpu(), logit, c.t("activout"), TF32_MASK_TAU * float(logit.abs().max()))
+    yard, yard_norm = _cudnn_tf32_yardstick(c)
+    print("\n[tf32 %s] out %.2e trace %.2e | grads L2-rel ours / reference-on-cuDNN-TF32: %s | worst |g| norm deviation %.2e / %.2e | "
+          "masks: %d flipped, %d exempt pixel-thresholds of %d, %d outside the margin"
+          % (name, e_out, e_tr, {k: "%.1e/%.1e" % (v[1], yard[k]) for k, v in full.items()}, norm_dev, yard_norm,
+             flipped, exempt, 32 * logit.numel(), bad))
+    assert e_out < TF32_OUT_TOL and e_tr < TF32_OUT_TOL
+    assert rel_err(x.grad, c.t("grad_x"))[1] < max(TF32_GRAD_TOL, TF32_GRAD_YARD * yard["x"])
+    for k, v in full.items():
+        assert v[1] < max(TF32_GRAD_TOL, TF32_GRAD_YARD * yard[k]), (k, v, yard[k])
+    assert norm_dev < max(TF32_GRAD_TOL, TF32_GRAD_YARD * yard_norm)
+    assert bad == 0
+
+
+@pytest.mark.parametrize("math", ["fp32", "tf32"])
+@pytest.mark.parametrize("name", MARGIN_CASES)
+def test_masks_on_trained_weights_with_margin(name, math):
+    """Weights after 300 reference training steps (oracle/make_golden.py:run_margin_case): every logit of the held-out
+    image is > 2e-4 away from each of the 32 thresholds, so in fp32 mode NO pixel is exempt: masks bit-exact everywhere."""
+    c = Case(name)
+    net = build(c).eval()
+    net.conv_math = math
+    with torch.no_grad():
+        out, hn = net(c.t("x", DEV), c.t("hebb", DEV))
+    logit, ref_out = c.t("activ"), c.t("activout")
+    got = out.detach().cpu()
+    tau = 0.0 if math == "fp32" else TF32_MASK_TAU * float(logit.abs().max())
+    flipped, exempt, bad = _mask_report(got, logit, ref_out, tau)
+    print("\n[margin %s %s] min margin %.2e, out err %.2e: %d flipped, %d exempt pixel-thresholds, %d outside the margin"
+          % (name, math, float(c.z["margin"]), rel_err(out, ref_out)[0], flipped, exempt, bad))
+    assert rel_err(hn, c.t("hebb_new"))[0] < (TOL if math == "fp32" else TF32_OUT_TOL)
+    if math == "fp32":
+        assert flipped == 0 and exempt == 0
+    assert bad == 0
 
 
 def test_eval_and_infer_calling_convention():

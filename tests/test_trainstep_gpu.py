@@ -1,0 +1,218 @@
+"""GPU parity tests of the BENCHMARKED path: pu_b200.trainer.TrainStep (flat arenas, fused BCE, premasked TF32
+gradients, weight gradients on side streams, CUDA-graph capture, single-launch Adam, carried trace) against the
+oracle's batched training loop (oracle.train_steps_batched = train.py:91-112 with B > 1) and against the golden
+trajectories of the real reference (B = 1).
+
+Tolerance table:
+                      loss trajectory   final trace   parameter UPDATE (p_K - p_0), L2-relative
+    fp32 mode             1e-5             1e-4           2e-3
+    tf32 mode             2e-4             1e-3           5e-2   (Adam's m/sqrt(v) normalisation turns a relative gradient
+                                                                  error e into an update error ~e only where |g| >> its
+                                                                  error; elements whose gradient is at TF32-noise level
+                                                                  move by +-lr either way and dominate this figure)
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import plastic_unet_oracle as orc
+from conftest import TRAIN_CASES, Case, quiet, rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda")
+
+TOLS = {"fp32": dict(loss=1e-5, trace=1e-4, upd=2e-3), "tf32": dict(loss=2e-4, trace=1e-3, upd=5e-2)}
+
+
+def synth(n, size, gen, pad_from=None):
+    """Same construction as bench.py's synth_batch (uniform images, Bernoulli(0.25) masks, 101 -> 128 zero padding)."""
+    if pad_from is not None:
+        p0 = (size - pad_from) // 2
+        img = torch.zeros(n, 1, size, size)
+        img[:, :, p0:p0 + pad_from, p0:p0 + pad_from] = torch.rand(n, 1, pad_from, pad_from, generator=gen)
+        msk = torch.zeros(n, size, size)
+        msk[:, p0:p0 + pad_from, p0:p0 + pad_from] = (torch.rand(n, pad_from, pad_from, generator=gen) < 0.25).float()
+        return img, msk
+    return torch.rand(n, 1, size, size, generator=gen), (torch.rand(n, size, size, generator=gen) < 0.25).float()
+
+
+_ORACLE_CACHE = {}
+
+
+def oracle_run(kind, ctor_kw, body_kw, size, B, steps, lr, pad_from):
+    """K batched steps of the oracle on CPU from seeded weights -> (sd0, sd_final, losses, hebb, batches)."""
+    key = (kind, repr(sorted(ctor_kw.items())), size, B, steps, lr, pad_from)
+    if key in _ORACLE_CACHE:
+        return _ORACLE_CACHE[key]
+    import pu_b200
+    cls = {"unetp": pu_b200.UNetp, "unetpres": pu_b200.UNetpRes}[kind]
+    torch.manual_seed(0)
+    sd0 = {k: v.detach().clone() for k, v in quiet(cls, 1, 1, torch.device("cpu"), **ctor_kw).state_dict().items()}
+    gen = torch.Generator().manual_seed(1234)
+    batches = [synth(B, size, gen, pad_from) for _ in range(steps)]
+    sd = orc.leaf_state(sd0)
+    torch.set_num_threads(os.cpu_count() or 1)
+    losses, hebb = orc.train_steps_batched(kind, sd, batches, ctor_kw.get("rule", "hebb"), lr=lr, **body_kw)
+    out = (sd0, {k: v.detach() for k, v in sd.items()}, losses, hebb, batches)
+    _ORACLE_CACHE[key] = out
+    return out
+
+
+def run_trainstep(kind, ctor_kw, sd0, batches, size, B, lr, math, use_graph=True, side=2, host_inputs=False):
+    import pu_b200
+    from pu_b200.trainer import TrainStep
+    cls = {"unetp": pu_b200.UNetp, "unetpres": pu_b200.UNetpRes}[kind]
+    net = quiet(cls, 1, 1, DEV, batched=True, **ctor_kw)
+    net.load_state_dict(sd0)
+    net.conv_math = math
+    net.train()
+    old = os.environ.get("PU_WGRAD_SIDE")
+    os.environ["PU_WGRAD_SIDE"] = str(side)
+    try:
+        ts = TrainStep(net, B, size, lr=lr, use_graph=use_graph)
+    finally:
+        if old is None:
+            del os.environ["PU_WGRAD_SIDE"]
+        else:
+            os.environ["PU_WGRAD_SIDE"] = old
+    ts.capture()
+    losses = []
+    for x, t in batches:
+        if host_inputs:
+            loss = ts.step(x.pin_memory(), t.pin_memory())
+        else:
+            loss = ts.step(x.to(DEV), t.to(DEV))
+        losses.append(float(loss))
+    torch.cuda.synchronize()
+    return net, ts, losses
+
+
+def update_err(net, sd0, sd_ref):
+    """L2-relative error of the parameter update over all parameters, plus the worst single tensor."""
+    num = den = 0.0
+    worst = (0.0, None)
+    for k, p in net.named_parameters():
+        d = (p.detach().cpu().double() - sd_ref[k].double())
+        u = (sd_ref[k].double() - sd0[k].double())
+        num += float(d.pow(2).sum())
+        den += float(u.pow(2).sum())
+        if float(u.norm()) > 0:
+            e = float(d.norm() / u.norm())
+            if e > worst[0]:
+                worst = (e, k)
+    return (num / max(den, 1e-300)) ** 0.5, worst
+
+
+CASES = {
+    # name: (kind, ctor_kw, oracle body_kw, size, B, steps, lr, pad_from)
+    "unetp_oja_64_b8": ("unetp", dict(rule="oja", nbf=64), {}, 64, 8, 4, 1e-3, None),
+    "unetp_oja_128_b64_padded": ("unetp", dict(rule="oja", nbf=128), {}, 128, 64, 4, 1e-3, 101),  # BASELINE configs[1] = bench.py's workload
+    "unetpres8_hebb_101_b8": ("unetpres", dict(neurons=8, dropout_ratio=0.0, rule="hebb", nbf=101), dict(dropout_ratio=0.0), 101, 8, 3, 1e-3, None),
+}
+
+
+@pytest.mark.parametrize("math", ["fp32", "tf32"])
+@pytest.mark.parametrize("case", list(CASES))
+def test_trainstep_vs_oracle(case, math):
+    """The captured step as bench.py runs it (graph on, 2 wgrad side streams) over K steps vs the oracle loop."""
+    kind, ctor_kw, body_kw, size, B, steps, lr, pad_from = CASES[case]
+    sd0, sd_ref, losses_ref, hebb_ref, batches = oracle_run(kind, ctor_kw, body_kw, size, B, steps, lr, pad_from)
+    net, ts, losses = run_trainstep(kind, ctor_kw, sd0, batches, size, B, lr, math)
+    tol = TOLS[math]
+    e_loss = max(abs(a - b) for a, b in zip(losses, losses_ref))
+    e_trace = rel_err(ts.hebb, hebb_ref)[0]
+    e_upd, worst = update_err(net, sd0, sd_ref)
+    print("\n[trainstep %s %s] max |loss - ref| %.2e (ref %s), trace %.2e, update L2-rel %.2e (worst tensor %s %.2e), kernels/step %d"
+          % (case, math, e_loss, ["%.5f" % l for l in losses_ref], e_trace, e_upd, worst[1], worst[0], ts.kernels_per_step))
+    assert int(ts.step_count) == steps
+    assert e_loss < tol["loss"], (losses, losses_ref)
+    assert e_trace < tol["trace"]
+    assert e_upd < tol["upd"]
+
+
+@pytest.mark.parametrize("math", ["fp32", "tf32"])
+def test_trainstep_graph_and_side_streams_do_not_change_the_result(math):
+    """CUDA graph on/off and weight gradients on 0 / 2 side streams: same trajectory up to the run-to-run bound of the
+    fp32 atomics in the weight-gradient reductions (documented non-determinism)."""
+    kind, ctor_kw, body_kw, size, B, steps, lr, pad_from = CASES["unetp_oja_64_b8"]
+    sd0, sd_ref, losses_ref, hebb_ref, batches = oracle_run(kind, ctor_kw, body_kw, size, B, steps, lr, pad_from)
+    base_net, base_ts, base_losses = run_trainstep(kind, ctor_kw, sd0, batches, size, B, lr, math, use_graph=True, side=2)
+    base_sd = {k: p.detach().cpu() for k, p in base_net.named_parameters()}
+    for use_graph, side, host in ((False, 0, False), (False, 2, False), (True, 0, False), (True, 2, True)):
+        net, ts, losses = run_trainstep(kind, ctor_kw, sd0, batches, size, B, lr, math, use_graph=use_graph, side=side, host_inputs=host)
+        e_upd, worst = update_err(net, sd0, base_sd)
+        print("\n[graph=%s side=%d host=%s %s] update vs (graph, 2 side streams): %.2e, losses %s" % (use_graph, side, host, math, e_upd, losses))
+        assert max(abs(a - b) for a, b in zip(losses, base_losses)) < 2e-6
+        assert rel_err(ts.hebb, base_ts.hebb)[0] < (1e-5 if math == "fp32" else 1e-4)  # a last-bit difference can flip a TF32 rounding
+        assert e_upd < 2e-3, worst
+
+
+def test_capture_leaves_model_state_untouched():
+    """capture() warms up with real steps; it must restore weights, Adam state, step count, trace and BN buffers."""
+    import pu_b200
+    from pu_b200.trainer import TrainStep
+    torch.manual_seed(3)
+    net = quiet(pu_b200.UNetp, 1, 1, DEV, rule="oja", nbf=32, batch_norm=True, batched=True)
+    sd0 = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    for use_graph in (True, False):
+        ts = TrainStep(net, 2, 32, lr=1e-2, use_graph=use_graph)
+        ts.hebb.fill_(0.25)
+        ts.capture()
+        torch.cuda.synchronize()
+        for k, v in net.state_dict().items():
+            assert torch.equal(v, sd0[k]), k
+        assert float(ts.step_count) == 0 and float(ts.m.abs().max()) == 0 and float(ts.v.abs().max()) == 0
+        assert bool((ts.hebb == 0.25).all())
+
+
+@pytest.mark.parametrize("name", TRAIN_CASES)
+@pytest.mark.parametrize("use_graph", [True, False])
+def test_trainstep_reproduces_reference_trajectory(name, use_graph):
+    """B = 1, fp32 mode: TrainStep.step() must follow the REAL reference's train.py run (golden losses, weights, trace),
+    including its StepLR schedule (set_lr between steps)."""
+    import pu_b200
+    from pu_b200.trainer import TrainStep
+    c = Case(name)
+    cls = pu_b200.UNetp if c.kind == "unetp" else pu_b200.UNetpRes
+    net = quiet(cls, 1, 1, DEV, batched=True, **c.ctor_kw)
+    net.load_state_dict(c.state_dict())
+    net.train()
+    imgs, masks = c.t("imgs", DEV), c.t("masks", DEV)
+    lr0 = float(c.z["lr"])
+    ts = TrainStep(net, 1, imgs.shape[-1], lr=lr0, use_graph=use_graph).capture()
+    losses = []
+    for i in range(imgs.shape[0]):
+        ts.set_lr(lr0 * 0.5 ** (i // 2))  # StepLR(gamma=0.5, step_size=2) of oracle/make_golden.py:run_train_case
+        losses.append(float(ts.step(imgs[i][None], masks[i][None])))
+    assert np.allclose(losses, c.z["losses"], rtol=0, atol=2e-5), (losses, c.z["losses"])
+    assert rel_err(ts.hebb, c.t("hebb_final"))[0] < 1e-3
+    assert rel_err(net.w, c.t("final::w"))[0] < 1e-3
+    assert rel_err(net.alpha, c.t("final::alpha"))[0] < 1e-3
+    sd = net.state_dict()
+    for k, l2 in zip([str(k) for k in c.z["final_keys"]], c.z["final_l2"]):
+        assert abs(float(sd[k].double().norm()) - l2) <= 1e-3 * max(l2, 1e-10), k
+
+
+def test_weight_gradient_atomics_bound():
+    """The weight-gradient reductions end in fp32 atomicAdd: run-to-run differences are last-bit noise.  Bound stated in
+    DESIGN.md §4.5: 1e-5 of the tensor's max magnitude."""
+    import pu_b200
+    torch.manual_seed(0)
+    for math in ("fp32", "tf32"):
+        net = quiet(pu_b200.UNetp, 1, 1, DEV, rule="oja", nbf=64, batched=True)
+        net.conv_math = math
+        g = torch.Generator().manual_seed(2)
+        x, t = synth(8, 64, g)
+        x, t = x.to(DEV), t.to(DEV)
+        runs = []
+        for _ in range(3):
+            for p in net.parameters():
+                p.grad = None
+            out, _ = net(x, net.initialZeroHebb())
+            torch.nn.functional.binary_cross_entropy(out.reshape(-1), t.reshape(-1)).backward()
+            runs.append({k: p.grad.detach().clone() for k, p in net.named_parameters() if p.grad is not None})
+        worst = max(rel_err(runs[i][k], runs[0][k])[0] for i in (1, 2) for k in runs[0])
+        print("\n[atomics %s] worst run-to-run gradient difference %.2e of max" % (math, worst))
+        assert worst < 1e-5
