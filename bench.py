@@ -2,7 +2,7 @@
 """bench.py — the Plastic U-Net hot path on B200: train images/sec (fwd + bwd + plastic update + Adam).
 
     python bench.py --gpus N --steps K --warmup W            # our arm (CUDA kernels, one process per GPU)
-    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path (oracle port) on host cores
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's own CPU path on the host cores
 
 Workload at N=1 (BASELINE.json configs[1]): Plastic U-Net (UNetp), Oja rule, 128x128, batch 64 per GPU,
 synthetic 1-channel images (uniform [0,1) 101x101 zero-padded to 128x128) and Bernoulli masks, random-init
@@ -12,7 +12,13 @@ One "step" = one optimisation step over one batch.  `value` is whole-job images/
 resident in HBM (a device pool larger than L2 is rotated through); `e2e` is the same step through the
 public API with pinned HOST batches (H2D copy of images+masks and D2H read of the loss inside the timed
 region, every step).  Timing: CUDA events on the launching stream, barrier + synchronize on both sides,
-max over ranks.  Prints ONE JSON line on rank 0.
+max over ranks.  A step is ~1 ms, so the K-step region is timed `--regions` times back to back and the
+MEDIAN region is reported (`region_ms` lists them all): one scheduler hiccup must not move the number.
+Prints ONE JSON line on rank 0.  Extra objects on that line:
+  roofline      the WORST of {forward, dgrad, wgrad} of the largest layer (up4.0), timed live
+  kernels       the ten slowest layer kernels of the step (live CUDA-event timings, algorithmic bytes, HBM fraction)
+  extras        short legs for BASELINE configs 3, 4, 5 (coord-conv, residual n8 @101 Hebb/Oja, 512^2 depth-5 train+infer)
+  dp_check      (N > 1) replicas bit-identical after the timed run; N x B data-parallel step == one-process step on N*B
 """
 import argparse
 import contextlib
@@ -20,7 +26,6 @@ import io
 import json
 import os
 import statistics
-import subprocess
 import sys
 import time
 
@@ -113,57 +118,81 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------------
-# CPU arm: the reference's own algorithm (oracle port of train.py:91-112) on the host cores
+# CPU arm: the reference's own implementation of the path on the host cores.  Nothing from the product
+# (pu_b200) is imported here.  oracle/_ref (bytecode of the unmodified reference, oracle/build_ref.py) when it
+# travelled with the snapshot -> kind "reference"; else the oracle port -> kind "port".
 # --------------------------------------------------------------------------------------------------
-def cpu_train_images_per_s(n_images, size, rule, warm=3, seed=0):
-    """B=1 sequential steps exactly like train.py:91-112 on the oracle; -> (images/s, n_images, threads)."""
-    import plastic_unet_oracle as orc
-    from pu_b200 import UNetp
+def _cpu_reference_net(size, rule, seed):
+    """-> (kind, step_fn) where step_fn(img [1,1,H,W], mask [H,W]) runs ONE train.py:91-112 iteration."""
+    import build_ref
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
     torch.manual_seed(seed)
-    net = quiet(UNetp, 1, 1, torch.device("cpu"), rule=rule, nbf=size)  # parameter container only (never run on CPU)
-    sd = orc.leaf_state(net.state_dict())
-    gen = torch.Generator().manual_seed(1234)
-    imgs, msks = synth_batch(n_images + warm, size, gen)
+    crit = torch.nn.BCELoss()
+    if build_ref.available():
+        import ref_loader
+        ref = ref_loader.load(os.path.join(ROOT, "oracle", "_ref", "src"))
+        net = quiet(ref.unet.UNetp, 1, 1, torch.device("cpu"), rule=rule, nbf=size)  # the reference's own module
+        net.train()
+        opt = torch.optim.Adam(net.parameters(), lr=1e-4)
+        state = {"hebb": net.initialZeroHebb()}
+
+        def step(img, mask):
+            opt.zero_grad()
+            y, state["hebb"] = net(img, state["hebb"].detach())
+            loss = crit(y.view(-1), mask.view(-1))
+            loss.item()
+            loss.backward()
+            opt.step()
+        return "reference", step
+    import plastic_unet_oracle as orc
+    sd = orc.leaf_state(orc.init_state_unetp(size, seed))
     params = [v for v in sd.values() if v.is_floating_point() and v.requires_grad]
     opt = torch.optim.Adam(params, lr=1e-4)
-    crit = torch.nn.BCELoss()
-    hebb = torch.zeros(size, size)
+    state = {"hebb": torch.zeros(size, size)}
+
+    def step(img, mask):
+        opt.zero_grad()
+        _, y, state["hebb"] = orc.forward("unetp", sd, img, state["hebb"].detach(), rule=rule)
+        loss = crit(y.view(-1), mask.view(-1))
+        loss.item()
+        loss.backward()
+        opt.step()
+    return "port", step
+
+
+def cpu_train_images_per_s(n_images, size, rule, warm=3, seed=0):
+    """B=1 sequential steps exactly like train.py:91-112; -> (images/s, n_images, threads, kind)."""
+    kind, step = _cpu_reference_net(size, rule, seed)
+    gen = torch.Generator().manual_seed(1234)
+    imgs, msks = synth_batch(n_images + warm, size, gen)
     t0 = None
     for i in range(n_images + warm):
         if i == warm:
             t0 = time.perf_counter()
-        opt.zero_grad()
-        _, y, hebb = orc.forward("unetp", sd, imgs[i:i + 1], hebb.detach(), rule=rule)
-        loss = crit(y.view(-1), msks[i].view(-1))
-        loss.item()
-        loss.backward()
-        opt.step()
+        step(imgs[i:i + 1], msks[i])
     dt = time.perf_counter() - t0
-    return n_images / dt, n_images, threads
+    return n_images / dt, n_images, os.cpu_count() or 1, kind
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU implementation of the path (oracle port; the reference is pure Python
-    + PyTorch CPU ops, there is nothing to compile), all host threads, bounded sample per step."""
+    """--impl reference: the reference's CPU implementation of the path, all host threads, bounded sample per step."""
     if rank != 0:
         return
     per_step = args.ref_images_per_step
-    threads = os.cpu_count() or 1
-    # warm-up steps + timed steps, each step = per_step sequential B=1 train iterations
-    ips_w, _, _ = cpu_train_images_per_s(max(1, args.warmup) * per_step, args.size, args.rule)
+    cpu_train_images_per_s(max(1, args.warmup) * per_step, args.size, args.rule)
     t0 = time.perf_counter()
-    ips, n, threads = cpu_train_images_per_s(args.steps * per_step, args.size, args.rule, warm=0)
+    ips, n, threads, kind = cpu_train_images_per_s(args.steps * per_step, args.size, args.rule, warm=0)
     dt = time.perf_counter() - t0
+    what = "the unmodified reference module (oracle/_ref)" if kind == "reference" else "the oracle port"
     line = {
         "impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000.0 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "UNetp Oja 128x128 (101x101 zero-padded), B=1 sequential steps as train.py:91-112, "
                                "%d images per step" % per_step},
-        "cpu_baseline": {"value": ips, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": "%d sequential single-image train steps (fwd+BCE+bwd+Adam+trace) of the oracle port" % n},
+        "cpu_baseline": {"value": ips, "unit": UNIT, "cores": threads, "kind": kind,
+                         "sample": "%d sequential single-image train steps (fwd+BCE+bwd+Adam+trace) of %s" % (n, what)},
         "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -171,57 +200,220 @@ def run_reference(args, rank, world):
 
 
 # --------------------------------------------------------------------------------------------------
-# dominant-kernel roofline (measured live with CUDA events on the launching stream)
+# per-kernel roofline table (measured live with CUDA events on the launching stream)
 # --------------------------------------------------------------------------------------------------
-def dominant_kernel_roofline(batch, size, math, dev, hbm_peak, peak_src):
-    """Times the full-resolution 16->8 conv3x3 (+bias+ReLU, two-source concat: up4.0, the largest single layer of
-    UNetp: SURVEY.md §8d) in isolation, rotating over buffers larger than L2.  Algorithmic bytes per launch =
-    pixels * (C_in + C_out) * 4 (input read once + output written once)."""
-    from pu_b200 import ops
-    C0, C1, Cout = 8, 8, 8
-    nbuf = max(2, int(2 * L2_BYTES // (batch * size * size * (C0 + C1 + Cout) * 4)) + 1)
-    xs0 = [torch.rand(batch, size, size, C0, device=dev) for _ in range(nbuf)]
-    xs1 = [torch.rand(batch, size, size, C1, device=dev) for _ in range(nbuf)]
-    w = torch.randn(Cout, C0 + C1, 3, 3, device=dev) * 0.1
-    b = torch.zeros(Cout, device=dev)
-    iters = 20
+def _time_graph(fn, iters=20, reps=5):
+    """us per call of fn(i) from a CUDA graph of `iters` calls (a Python op call costs ~60 us of host time)."""
     with torch.no_grad():
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for i in range(3):
-                ops.conv3x3(xs0[i % nbuf], xs1[i % nbuf], w, b, None, True, size, size, 0, 0, 0, 0, math)
+                fn(i)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        # a Python op call costs ~60 us of host time: capture the launches so that the events time the GPU, not the host
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             for i in range(iters):
-                ops.conv3x3(xs0[i % nbuf], xs1[i % nbuf], w, b, None, True, size, size, 0, 0, 0, 0, math)
+                fn(i)
         g.replay()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 5
         e0.record()
         for _ in range(reps):
             g.replay()
         e1.record()
         torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / (iters * reps)
-    # one kernel per op call (the weight tiles are built inside the conv kernel)
-    alg_bytes = batch * size * size * (C0 + C1 + Cout) * 4
-    # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed `ncu --set full` capture
-    # (profiles/r1_tc_conv_ncu_summary.md, B = 64 @128x128, TF32 kernel): 67.16 MB read (= the algorithmic input, read
-    # once) + 6.59 MB written inside the kernel window; the rest of the 33.55 MB output leaves L2 after the kernel ends.
-    traffic, traffic_note = None, None
-    if math and batch == 64 and size == 128:
-        traffic = 67162368 + 6587904
-        traffic_note = "ncu capture of round 1 (profiles/r1_tc_conv_ncu_summary.md); output write-back continues after the kernel window"
-    achieved = alg_bytes / (ms * 1e-3) / 1e9
-    return {"bound": "hbm", "kernel": "conv3x3 fwd 16->8 @%dx%d (up4.0, %s)" % (size, size, "tf32 tcgen05" if math else "fp32 ffma"),
-            "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
-            "traffic_note": traffic_note,
-            "peak_source": peak_src, "us_per_launch": ms * 1e3, "algorithmic_bytes_per_launch": alg_bytes}
+    return e0.elapsed_time(e1) * 1e3 / (iters * reps)
+
+
+# UNetp conv3x3 layers (SURVEY.md §8d): name, C0 (first source), C1 (second source of the fused concat), Cout, side / 128
+UNETP_LAYERS = [("inc.2", 8, 0, 8, 1), ("down1.0", 8, 0, 16, 2), ("down1.2", 16, 0, 16, 2), ("down2.0", 16, 0, 32, 4),
+                ("down2.2", 32, 0, 32, 4), ("down3.0", 32, 0, 64, 8), ("down3.2", 64, 0, 64, 8), ("down4.0", 64, 0, 64, 16),
+                ("up1.0", 64, 64, 32, 8), ("up1.2", 32, 0, 32, 8), ("up2.0", 32, 32, 16, 4), ("up2.2", 16, 0, 16, 4),
+                ("up3.0", 16, 16, 8, 2), ("up3.2", 8, 0, 8, 2), ("up4.0", 8, 8, 8, 1), ("up4.2", 8, 0, 8, 1)]
+
+
+def kernel_table(batch, size, math, dev, hbm_peak, peak_src):
+    """Times forward / dgrad / wgrad of every conv3x3 layer of UNetp in isolation (buffers rotating over > L2 for the
+    large layers).  Algorithmic bytes per launch: fwd = pixels*(Cin+Cout)*4 (input read once + output
+    written once); dgrad = the same (dY read, dX written); wgrad = pixels*(Cin+Cout)*4 (X and dY read once)."""
+    from pu_b200 import ops
+    rows = []
+    for name, C0, C1, Cout, div in UNETP_LAYERS:
+        s = size // div
+        per = batch * s * s * (C0 + C1 + Cout) * 4
+        nbuf = min(8, max(2, int(2 * L2_BYTES // per) + 1))
+        xs0 = [torch.rand(batch, s, s, C0, device=dev) for _ in range(nbuf)]
+        xs1 = [torch.rand(batch, s, s, C1, device=dev) for _ in range(nbuf)] if C1 else [None] * nbuf
+        dys = [torch.randn(batch, s, s, Cout, device=dev) for _ in range(nbuf)]
+        ys = [torch.rand(batch, s, s, Cout, device=dev) for _ in range(nbuf)]
+        w = torch.randn(Cout, C0 + C1, 3, 3, device=dev) * 0.1
+        b = torch.zeros(Cout, device=dev)
+        pm = bool(math)  # the premasked-gradient protocol of the TF32 mode (modules.UNetp.forward)
+
+        def fwd(i):
+            ops.conv3x3(xs0[i % nbuf], xs1[i % nbuf], w, b, None, True, s, s, 0, 0, 0, 0, math)
+
+        def dgrad(i):
+            ops.conv3x3_bwd(dys[i % nbuf], ys[i % nbuf], xs0[i % nbuf], xs1[i % nbuf], w, True, True, s, s, 0, 0, 0, 0, math,
+                            True, False, pm, False, pm)
+
+        def wgrad(i):
+            ops.conv3x3_bwd(dys[i % nbuf], ys[i % nbuf], xs0[i % nbuf], xs1[i % nbuf], w, True, True, s, s, 0, 0, 0, 0, math,
+                            False, True, pm, False, pm)
+
+        for kind, fn in (("fwd", fwd), ("dgrad", dgrad), ("wgrad", wgrad)):
+            us = _time_graph(fn)
+            gbs = per / (us * 1e-6) / 1e9
+            rows.append({"name": "conv3x3 %s %s %d%s->%d @%dx%d" % (name, kind, C0, "|%d" % C1 if C1 else "", Cout, s, s),
+                         "us": round(us, 2), "algorithmic_bytes": per, "achieved_gbs": round(gbs, 1), "frac": round(gbs / hbm_peak, 4)})
+        del xs0, xs1, dys, ys
+    top = sorted(rows, key=lambda r: -r["us"])[:10]
+    worst = min((r for r in rows if " up4.0 " in r["name"]), key=lambda r: r["frac"])
+    roof = {"bound": "hbm", "kernel": worst["name"] + (" (tf32 tcgen05 / mma.sync)" if math else " (fp32 ffma)"),
+            "achieved": worst["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": worst["achieved_gbs"] / hbm_peak,
+            "traffic": None, "traffic_note": "not measured by this run; ncu dram bytes of the same kernels are in profiles/",
+            "peak_source": peak_src, "us_per_launch": worst["us"], "algorithmic_bytes_per_launch": worst["algorithmic_bytes"],
+            "selection": "the worst of {fwd, dgrad, wgrad} of up4.0 (8|8->8 @ full resolution), the largest layer of UNetp"}
+    return roof, top, rows
+
+
+# --------------------------------------------------------------------------------------------------
+def build_net(model, dev, rule, size, depth=4, base=8, neurons=16, dropout=0.5):
+    from pu_b200 import UNetp, UNetpCoord, UNetpRes
+    if model == "unetp":
+        net = quiet(UNetp, 1, 1, dev, rule=rule, nbf=size, batched=True, depth=depth, base=base)
+        name = "UNetp (Plastic U-Net)" + ("" if (depth, base) == (4, 8) else " depth %d base %d" % (depth, base))
+    elif model == "res":
+        net = quiet(UNetpRes, 1, 1, dev, neurons=neurons, dropout_ratio=dropout, rule=rule, nbf=size, batched=True, depth=depth)
+        name = "UNetpRes (residual Plastic U-Net) neurons %d dropout %.2f depth %d" % (neurons, dropout, depth)
+    else:
+        net = quiet(UNetpCoord, 1, 1, dev, rule=rule, nbf=size, batched=True, depth=depth, base=base)
+        name = "UNetpCoord (coord-conv Plastic U-Net)"
+    return net, name
+
+
+def timed_leg(model, dev, group, world, rule, size, B, math, steps, infer=False, pad_from=None, **kw):
+    """A short measurement of another BASELINE config: -> dict(images_per_s (whole job), ms_per_step, ...)."""
+    import torch.distributed as dist
+    from pu_b200 import dp
+    from pu_b200.trainer import InferStep, TrainStep
+    torch.manual_seed(0)
+    net, name = build_net(model, dev, rule, size, **kw)
+    net.conv_math = math
+    dp.attach(net, group)
+    dp.broadcast_parameters(net, 0, group)
+    if infer:
+        net.eval()
+        ts = InferStep(net, B, size).capture()
+    else:
+        net.train()
+        ts = TrainStep(net, B, size, lr=1e-4, dp_group=group).capture()
+    gen = torch.Generator().manual_seed(99 + (dist.get_rank() if world > 1 else 0))
+    nb = max(2, min(6, int(1.5 * L2_BYTES // (B * size * size * 8)) + 1))
+    pool = [tuple(t.to(dev) for t in synth_batch(B, size, gen, pad_from or size)) for _ in range(nb)]
+
+    def one(i):
+        if infer:
+            ts.step(pool[i % nb][0])
+        else:
+            ts.step(*pool[i % nb])
+    for i in range(3):
+        one(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        one(i)
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0]) / steps
+    out = {"model": name, "rule": rule, "size": size, "batch_per_gpu": B, "global_batch": B * world, "mode": "infer" if infer else "train",
+           "conv_math": math, "images_per_s": B * world / (ms * 1e-3), "ms_per_step": ms, "steps": steps,
+           "kernels_per_step": ts.kernels_per_step}
+    if not infer:
+        out["final_loss"] = float(ts.loss)
+    del ts, net, pool
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_extras(dev, group, world, math, steps=10):
+    """BASELINE.json configs[2..4], kept out of `value`: coord-conv DP; residual script variant (neurons 8 @101, Hebb and
+    Oja, 32 per GPU = 256 on 8 GPUs); scaled 512x512 depth-5 Oja, training + inference."""
+    legs = {}
+    specs = [
+        ("config3_coordconv_oja_128", dict(model="coord", rule="oja", size=128, B=64, pad_from=101)),
+        ("config4_res_n8_hebb_101", dict(model="res", rule="hebb", size=101, B=32, neurons=8)),
+        ("config4_res_n8_oja_101", dict(model="res", rule="oja", size=101, B=32, neurons=8)),
+        ("config5_unetp_depth5_oja_512_train", dict(model="unetp", rule="oja", size=512, B=8, depth=5)),
+        ("config5_unetp_depth5_oja_512_infer", dict(model="unetp", rule="oja", size=512, B=8, depth=5, infer=True)),
+    ]
+    for key, kw in specs:
+        try:
+            legs[key] = timed_leg(dev=dev, group=group, world=world, math=math, steps=steps, **kw)
+        except Exception as e:  # an extra must never take the headline down with it
+            legs[key] = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+    return legs
+
+
+def dp_check(net, ts, dev, group, world, rank, math):
+    """(1) replicas bit-identical after the timed run: trace and flat parameters (a checksum of the raw bits);
+    (2) one data-parallel step over a fixed global batch (8 images per rank) == one single-process step over the same
+    world*8 images on rank 0, from the same weights.  -> dict (rank 0) or None."""
+    import torch.distributed as dist
+    from pu_b200 import dp
+    from pu_b200.trainer import TrainStep
+
+    def bits_sum(t):
+        return t.detach().contiguous().view(torch.int32).to(torch.int64).sum().view(1)
+
+    mine = torch.cat([bits_sum(ts.hebb), bits_sum(ts.flat_p)])
+    allc = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(allc, mine)
+    identical = all(bool(torch.equal(c, allc[0])) for c in allc)
+    # (2)
+    b_loc, size = 8, net.nbf
+    gen = torch.Generator().manual_seed(4242)
+    gx, gt = synth_batch(b_loc * world, size, gen)
+    torch.manual_seed(7)
+    net_dp, _ = build_net("unetp", dev, net.rule, size)
+    net_dp.conv_math = math
+    dp.attach(net_dp, group)
+    dp.broadcast_parameters(net_dp, 0, group)
+    sd0 = {k: v.detach().clone() for k, v in net_dp.state_dict().items()}
+    ts_dp = TrainStep(net_dp, b_loc, size, lr=1e-3, dp_group=group).capture()
+    lo, hi = dp.shard_range(b_loc * world, rank, world)
+    loss_dp = ts_dp.step(gx[lo:hi].to(dev), gt[lo:hi].to(dev)).clone()
+    dist.all_reduce(loss_dp, op=dist.ReduceOp.SUM)
+    torch.cuda.synchronize()
+    res = None
+    if rank == 0:
+        net_1, _ = build_net("unetp", dev, net.rule, size)
+        net_1.conv_math = math
+        net_1.load_state_dict(sd0)
+        ts_1 = TrainStep(net_1, b_loc * world, size, lr=1e-3, dp_group=None).capture()
+        loss_1 = float(ts_1.step(gx.to(dev), gt.to(dev)))
+        torch.cuda.synchronize()
+        num = den = 0.0
+        for (k, p), (_, q) in zip(net_dp.named_parameters(), net_1.named_parameters()):
+            num += float((p.double() - q.double()).pow(2).sum())
+            den += float((q.double() - sd0[k].double()).pow(2).sum())
+        trace_err = float((ts_dp.hebb - ts_1.hebb).abs().max() / ts_1.hebb.abs().max().clamp_min(1e-30))
+        res = {"replicas_bit_identical_after_run": identical, "global_batch": b_loc * world,
+               "dp_vs_single_process": {"loss_dp_mean": float(loss_dp) / world, "loss_single": loss_1,
+                                        "update_l2_rel": (num / max(den, 1e-300)) ** 0.5, "trace_max_rel": trace_err},
+               "tolerance": "fp32 atomics / all-reduce order: update 2e-3 (fp32) / 5e-2 (tf32, TF32 rounding flips), trace 1e-4"}
+        del ts_1, net_1
+    del ts_dp, net_dp
+    dist.barrier()
+    return res
 
 
 # --------------------------------------------------------------------------------------------------
@@ -230,6 +422,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--regions", type=int, default=11, help="how many times the K-step region is timed (median reported)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="per-GPU batch")
     ap.add_argument("--size", type=int, default=128)
@@ -243,18 +436,17 @@ def main():
     ap.add_argument("--infer", action="store_true", help="time the batched forward-only step instead of the train step")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the legs for BASELINE configs 3-5, the kernel table and dp_check")
     ap.add_argument("--ref-images-per-step", type=int, default=16)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
-    from pu_b200 import dp
     if args.impl == "reference":
-        rank = int(os.environ.get("RANK", "0"))
-        run_reference(args, rank, int(os.environ.get("WORLD_SIZE", "1")))
+        run_reference(args, int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")))
         return
 
     import torch.distributed as dist
-    from pu_b200 import UNetp, UNetpCoord, UNetpRes, _lib
+    from pu_b200 import _lib, dp
     from pu_b200.trainer import InferStep, TrainStep
 
     rank, world, local_rank = dp.init_from_env()
@@ -263,18 +455,11 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     hbm_peak, _, peak_src = measured_peaks()
+    headline = (args.model == "unetp" and not args.infer and (args.depth, args.base) == (4, 8))
 
     torch.manual_seed(0)
-    if args.model == "unetp":
-        net = quiet(UNetp, 1, 1, dev, rule=args.rule, nbf=args.size, batched=True, depth=args.depth, base=args.base)
-        model_name = "UNetp (Plastic U-Net)" + ("" if (args.depth, args.base) == (4, 8) else " depth %d base %d" % (args.depth, args.base))
-    elif args.model == "res":
-        net = quiet(UNetpRes, 1, 1, dev, neurons=args.neurons, dropout_ratio=args.dropout, rule=args.rule, nbf=args.size, batched=True,
-                    depth=args.depth)
-        model_name = "UNetpRes (residual Plastic U-Net) neurons %d dropout %.2f depth %d" % (args.neurons, args.dropout, args.depth)
-    else:
-        net = quiet(UNetpCoord, 1, 1, dev, rule=args.rule, nbf=args.size, batched=True, depth=args.depth, base=args.base)
-        model_name = "UNetpCoord (coord-conv Plastic U-Net)"
+    net, model_name = build_net(args.model, dev, args.rule, args.size, depth=args.depth, base=args.base, neurons=args.neurons,
+                                dropout=args.dropout)
     net.conv_math = args.math
     net.train()
     group = dist.group.WORLD if world > 1 else None
@@ -308,21 +493,27 @@ def main():
         ts.step(*dpool[i % npool])
     torch.cuda.synchronize()
 
-    # ---- timed: device-resident inputs
+    # ---- timed: device-resident inputs; the K-step region is repeated `regions` times
     sampler = ClockSampler(local_rank)
     barrier()
     torch.cuda.synchronize()
     if rank == 0:
         sampler.start()
     launches0 = _lib.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.steps):
-        ts.step(*dpool[i % npool])
-    e1.record()
-    torch.cuda.synchronize()
-    barrier()
-    ms = e0.elapsed_time(e1)
+    region_ms = []
+    it = 0
+    for r in range(max(1, args.regions)):
+        barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            ts.step(*dpool[it % npool])
+            it += 1
+        e1.record()
+        torch.cuda.synchronize()
+        barrier()
+        region_ms.append(e0.elapsed_time(e1))
     clocks = sampler.stop() if rank == 0 else None
     eager_launches = _lib.launch_count() - launches0
     loss_end = float(ts.loss)
@@ -334,74 +525,92 @@ def main():
     for i in range(2):
         ts.step(*hpool[i % npool])
     torch.cuda.synchronize()
-    barrier()
-    t0 = time.perf_counter()
-    if hasattr(ts, "prefetch"):
-        # every step's pinned-host batch is copied inside the timed region; the copy of batch i+1 (copy engine, own
-        # stream) overlaps step i, the loss of every step is read back with a sync
-        ts.prefetch(*hpool[0])
-        for i in range(args.steps):
-            ts.step_prefetched()
-            if i + 1 < args.steps:
-                ts.prefetch(*hpool[(i + 1) % npool])
-            loss_host.copy_(ts.loss, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-            _ = float(loss_host)
-    else:
-        for i in range(args.steps):
-            ts.step(*hpool[i % npool])
-            loss_host.copy_(ts.loss, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-            _ = float(loss_host)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    barrier()
+    e2e_regions = []
+    for r in range(max(1, min(args.regions, 5))):
+        barrier()
+        t0 = time.perf_counter()
+        if hasattr(ts, "prefetch"):
+            # every step's pinned-host batch is copied inside the timed region; the copy of batch i+1 (copy engine, own
+            # stream) overlaps step i, the loss of every step is read back with a sync
+            ts.prefetch(*hpool[0])
+            for i in range(args.steps):
+                ts.step_prefetched()
+                if i + 1 < args.steps:
+                    ts.prefetch(*hpool[(i + 1) % npool])
+                loss_host.copy_(ts.loss, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                _ = float(loss_host)
+        else:
+            for i in range(args.steps):
+                ts.step(*hpool[i % npool])
+                loss_host.copy_(ts.loss, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                _ = float(loss_host)
+        torch.cuda.synchronize()
+        e2e_regions.append((time.perf_counter() - t0) * 1000.0)
+        barrier()
 
-    # ---- max over ranks
-    times = torch.tensor([ms, e2e_s * 1000.0], device=dev, dtype=torch.float64)
+    # ---- max over ranks, region by region; then the median region
+    times = torch.tensor(region_ms + e2e_regions, device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    ms_max, e2e_ms_max = float(times[0]), float(times[1])
+    region_ms = [float(v) for v in times[:len(region_ms)]]
+    e2e_regions = [float(v) for v in times[len(region_ms):]]
+    ms_med, e2e_ms_med = statistics.median(region_ms), statistics.median(e2e_regions)
+
+    check = extras = None
+    if world > 1 and headline and not args.no_extras:
+        check = dp_check(net, ts, dev, group, world, rank, args.math)
+    if headline and not args.no_extras:
+        extras = run_extras(dev, group, world, args.math)
 
     if rank == 0:
         images = B * world * args.steps
-        value = images / (ms_max * 1e-3)
-        e2e_value = images / (e2e_ms_max * 1e-3)
+        value = images / (ms_med * 1e-3)
+        e2e_value = images / (e2e_ms_med * 1e-3)
         kps = ts.kernels_per_step or 0
-        roof = dominant_kernel_roofline(B, args.size, 1 if args.math == "tf32" else 0, dev, hbm_peak, peak_src)
+        roof = top = None
+        if not args.no_extras:
+            roof, top, _ = kernel_table(B, args.size, 1 if args.math == "tf32" else 0, dev, hbm_peak, peak_src)
         # whole-step figure against the layer-fused algorithmic bound of SURVEY.md §8d (28.39 MB / image @128)
         alg_mb_per_img = (9.49 if args.infer else 28.39) * (args.size / 128.0) ** 2  # UNetp figures; other models: indicative only
-        step_gbs = alg_mb_per_img * 1e6 * B / (ms_max / args.steps * 1e-3) / 1e9
+        step_gbs = alg_mb_per_img * 1e6 * B / (ms_med / args.steps * 1e-3) / 1e9
         cpu = None
-        if world == 1 and not args.no_cpu_baseline and args.model == "unetp" and not args.infer and (args.depth, args.base) == (4, 8):
-            ips0, _, thr = cpu_train_images_per_s(4, args.size, args.rule, warm=1)
+        if world == 1 and not args.no_cpu_baseline and headline:
+            ips0, _, thr, _ = cpu_train_images_per_s(4, args.size, args.rule, warm=1)
             n = int(min(256, max(8, ips0 * 12)))  # ~12 s of CPU work
-            ips, n, thr = cpu_train_images_per_s(n, args.size, args.rule)
-            cpu = {"value": ips, "unit": UNIT, "cores": thr, "kind": "port",
-                   "sample": "%d sequential single-image train steps (fwd+BCE+bwd+Adam+trace, train.py:91-112) of the "
-                             "oracle port, same synthetic 128x128 data" % n}
+            ips, n, thr, kind = cpu_train_images_per_s(n, args.size, args.rule)
+            cpu = {"value": ips, "unit": UNIT, "cores": thr, "kind": kind,
+                   "sample": "%d sequential single-image train steps (fwd+BCE+bwd+Adam+trace, train.py:91-112) of %s, same synthetic "
+                             "128x128 data" % (n, "the unmodified reference module (oracle/_ref)" if kind == "reference" else "the oracle port")}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_med / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "tf32" if args.math == "tf32" else "f32", "data": "synthetic",
             "config": {"workload": "%s %s rule, %s, batch %d per GPU, %s"
                                    % (model_name, args.rule, "1x101x101 zero-padded to 128x128" if args.size == 128 else "1x%dx%d" % (args.size, args.size),
                                       B, "batched inference (forward, zero trace)" if args.infer else "fwd+BCE+bwd+Adam+trace update"),
                        "global_batch": B * world, "parallelism": "dp%d" % world, "conv_math": args.math,
                        "cuda_graph": not args.no_graph,
+                       "timing": "median of %d back-to-back regions of exactly %d steps each (CUDA events, max over ranks per region)"
+                                 % (len(region_ms), args.steps),
                        "l2": "inputs rotate over a %d-batch device pool (%.0f MB > 126 MB L2); per-step activation "
                              "working set %.0f MB" % (npool, npool * per_batch / 1e6, 9.49 * B * (args.size / 128.0) ** 2)},
+            "region_ms": [round(v, 3) for v in region_ms],
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": per_batch * world, "d2h_bytes_per_step": 4 * world,
-                    "ms_per_step": e2e_ms_max / args.steps},
+                    "ms_per_step": e2e_ms_med / args.steps, "region_ms": [round(v, 3) for v in e2e_regions]},
             "gpu_launches": kps * args.steps,
             "kernels_per_step": kps,
             "roofline": roof,
+            "kernels": top,
             "step_roofline": {"bound": "hbm", "achieved": step_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": step_gbs / hbm_peak,
                               "note": "whole step vs the layer-fused algorithmic bytes of SURVEY.md 8d (%.2f MB/image)" % alg_mb_per_img},
             "cpu_baseline": cpu,
             "clocks": clocks,
             "final_loss": loss_end,
             "eager_launches_in_timed_region": eager_launches,
+            "dp_check": check,
+            "extras": extras,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -225,6 +225,36 @@ def forward(kind, sd, x, hebb, rule='hebb', alfa_type='free', **body_kw):
     return activ, activout, trace_update_batched(hebb, maps, activout, sd['eta'], rule)
 
 
+def init_state_unetp(nbf=128, seed=0, base=8, depth=4):
+    """A freshly initialised UNetp state_dict with the reference's shapes and init distributions (unet_p.py:30-32 for the
+    plastic parameters, nn.Conv2d / nn.ConvTranspose2d defaults for the body, unet_p.py:34-47) built from stock torch.nn
+    layers — for the CPU-baseline timing leg when neither the reference nor its bytecode (oracle/_ref) is present."""
+    torch.manual_seed(seed)
+    sd = {'w': .01 * torch.randn(nbf, nbf), 'alpha': .01 * torch.rand(nbf, nbf), 'eta': .01 * torch.ones(1)}
+
+    def conv(prefix, cin, cout, k=3):
+        m = torch.nn.Conv2d(cin, cout, k, padding=k // 2)
+        sd[prefix + '.weight'], sd[prefix + '.bias'] = m.weight.detach(), m.bias.detach()
+
+    def dconv(prefix, cin, cout):
+        conv(prefix + '.conv.0', cin, cout)
+        conv(prefix + '.conv.2', cout, cout)
+
+    c = [base * 2 ** i for i in range(depth)] + [base * 2 ** (depth - 1)]
+    dconv('inc.conv', 1, c[0])
+    for k in range(1, depth + 1):
+        dconv('down%d.mpconv.1' % k, c[k - 1], c[k])
+    for j in range(1, depth + 1):
+        skip = c[depth - j]
+        out = c[depth - j - 1] if depth - j - 1 >= 0 else c[0]
+        m = torch.nn.ConvTranspose2d(skip, skip, 2, stride=2)
+        sd['up%d.up.weight' % j], sd['up%d.up.bias' % j] = m.weight.detach(), m.bias.detach()
+        dconv('up%d.conv' % j, 2 * skip, out)
+    m = torch.nn.Conv2d(c[0], 1, 1)
+    sd['outc.conv.weight'], sd['outc.conv.bias'] = m.weight.detach(), m.bias.detach()
+    return sd
+
+
 def leaf_state(sd, dtype=torch.float32, requires_grad=True):
     """Clone a state_dict into leaf tensors (float params get requires_grad) for autograd through `forward`."""
     out = {}
