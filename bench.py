@@ -250,25 +250,26 @@ def kernel_table(batch, size, math, dev, hbm_peak, peak_src):
         ys = [torch.rand(batch, s, s, Cout, device=dev) for _ in range(nbuf)]
         w = torch.randn(Cout, C0 + C1, 3, 3, device=dev) * 0.1
         b = torch.zeros(Cout, device=dev)
-        pm = bool(math)  # the premasked-gradient protocol of the TF32 mode (modules.UNetp.forward)
+        pm = bool(math)  # the premasked-gradient protocol of the TF32 mode (modules.UNetp.forward): packed ReLU masks
+        ms0 = [torch.randint(0, 256, (batch, s, s, C0 // 8), device=dev, dtype=torch.uint8) for _ in range(nbuf)] if pm else [None] * nbuf
 
         def fwd(i):
             ops.conv3x3(xs0[i % nbuf], xs1[i % nbuf], w, b, None, True, s, s, 0, 0, 0, 0, math)
 
         def dgrad(i):
-            ops.conv3x3_bwd(dys[i % nbuf], ys[i % nbuf], xs0[i % nbuf], xs1[i % nbuf], w, True, True, s, s, 0, 0, 0, 0, math,
-                            True, False, pm, False, pm)
+            ops.conv3x3_bwd(dys[i % nbuf], ys[i % nbuf], xs0[i % nbuf], xs1[i % nbuf], w, False, True, s, s, 0, 0, 0, 0, math,
+                            True, False, ms0[i % nbuf], None, pm)
 
         def wgrad(i):
             ops.conv3x3_bwd(dys[i % nbuf], ys[i % nbuf], xs0[i % nbuf], xs1[i % nbuf], w, True, True, s, s, 0, 0, 0, 0, math,
-                            False, True, pm, False, pm)
+                            False, True, None, None, pm)
 
         for kind, fn in (("fwd", fwd), ("dgrad", dgrad), ("wgrad", wgrad)):
             us = _time_graph(fn)
             gbs = per / (us * 1e-6) / 1e9
             rows.append({"name": "conv3x3 %s %s %d%s->%d @%dx%d" % (name, kind, C0, "|%d" % C1 if C1 else "", Cout, s, s),
                          "us": round(us, 2), "algorithmic_bytes": per, "achieved_gbs": round(gbs, 1), "frac": round(gbs / hbm_peak, 4)})
-        del xs0, xs1, dys, ys
+        del xs0, xs1, dys, ys, ms0
     top = sorted(rows, key=lambda r: -r["us"])[:10]
     worst = min((r for r in rows if " up4.0 " in r["name"]), key=lambda r: r["frac"])
     roof = {"bound": "hbm", "kernel": worst["name"] + (" (tf32 tcgen05 / mma.sync)" if math else " (fp32 ffma)"),

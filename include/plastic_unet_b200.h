@@ -97,14 +97,17 @@ int pu_conv3x3_tc_plan(int B, int H, int W, int C0, int C1, int Cout, int reside
  * formats need pu_conv3x3_tc_resident(C0, C1, Cout, H, W).
  * src1, bias, res, dst1 may be NULL.  wp is the packed weight [9][C0+C1][Cout].
  * dst views may be larger than HxW (their border is NOT written — caller zero-fills).
- * mask0 / mask1 (may be NULL): tensors with the geometry of dst0 / dst1; where mask <= 0 the stored value is 0
- * (used by dgrad calls: the ReLU mask of the layer that produced the source, applied in the epilogue).   */
+ * mask0 / mask1 (may be NULL): PACKED ReLU masks with the geometry of dst0 / dst1: one byte per (pixel, 8-channel group),
+ * bit j set = channel 8g+j of the tensor this gradient belongs to was > 0; where the bit is clear the stored value is 0
+ * (dgrad calls: the ReLU mask of the layer that produced the source, applied in the epilogue — 1/32 of the bytes of
+ * re-reading the fp32 activation).  mask_out (may be NULL; needs dst1 == NULL and Cout % 8 == 0): the forward conv
+ * writes the packed mask of its own (post-ReLU) output there, geometry of dst0 with Cout/8 bytes per pixel.       */
 int pu_conv3x3_fwd(const float* src0, int H0, int W0, int C0, int oy0, int ox0,
                    const float* src1, int H1, int W1, int C1, int oy1, int ox1,
                    const float* wp, const float* bias, const float* res, int flags,
                    float* dst0, int Hd0, int Wd0, int Cd0, int oyd0, int oxd0,
                    float* dst1, int Hd1, int Wd1, int Cd1, int oyd1, int oxd1,
-                   const float* mask0, const float* mask1,
+                   const unsigned char* mask0, const unsigned char* mask1, unsigned char* mask_out,
                    int B, int H, int W, int Cout, int math, int wfmt, void* stream);
 
 /* dw_oihw[Cout, C0+C1, 3, 3] = sum_{b,y,x} g[b,y,x,co] * cat[src0,src1][b,y+ky-1,x+kx-1,ci]

@@ -1,7 +1,7 @@
 """Recipe: BUILD the unmodified reference (pure Python) into oracle/_ref/ so that it travels to the GPU box.
 
 The reference has no native code; its "binary" is CPython bytecode.  This recipe byte-compiles the reference's own
-source files where they lie under /root/reference (py_compile, sourceless *.pyc layout) — the Python analogue of
+source files where they lie under /root/reference (py_compile, sourceless layout, suffix .pyb) — the Python analogue of
 compiling a C reference into oracle/_ref/*.so.  No reference source text is copied into the repo.
 
     python oracle/build_ref.py          # needs /root/reference (build container only); idempotent
@@ -32,7 +32,9 @@ def build(quiet=False):
         src = os.path.join(SRC, rel)
         if not os.path.exists(src):
             continue
-        dst = os.path.join(DST, rel + "c")  # X.py -> X.pyc next to where the source would be: importable without source
+        # X.py -> X.pyb (CPython bytecode, same format as a .pyc; the gpurun snapshot drops *.pyc) next to where the source
+        # would be; oracle/ref_loader.py registers a sourceless loader for that suffix
+        dst = os.path.join(DST, rel[:-3] + ".pyb")
         os.makedirs(os.path.dirname(dst), exist_ok=True)
         py_compile.compile(src, cfile=dst, dfile="reference/src/" + rel, doraise=True)
     with open(os.path.join(HERE, "_ref", "README"), "w") as f:
@@ -42,7 +44,7 @@ def build(quiet=False):
 
 
 def available():
-    return os.path.exists(os.path.join(DST, "unet", "unet_p.pyc"))
+    return os.path.exists(os.path.join(DST, "unet", "unet_p.pyb"))
 
 
 if __name__ == "__main__":

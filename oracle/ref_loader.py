@@ -17,7 +17,23 @@ STUBS = ["h5py", "skimage", "skimage.io", "skimage.transform", "skimage.util", "
 NAMES = ["unet", "utils", "eval", "train", "infer"]
 
 
+_HOOKED = False
+
+
+def _install_pyb_hook():
+    """Let the import system find `X.pyb` (bytecode written by oracle/build_ref.py) the way it finds a sourceless X.pyc."""
+    global _HOOKED
+    if _HOOKED:
+        return
+    from importlib import machinery
+    details = list(importlib._bootstrap_external._get_supported_file_loaders()) + [(machinery.SourcelessFileLoader, [".pyb"])]
+    sys.path_hooks.insert(0, machinery.FileFinder.path_hook(*details))
+    sys.path_importer_cache.clear()
+    _HOOKED = True
+
+
 def load(ref_src, unet_first=None):
+    _install_pyb_hook()
     for m in STUBS:
         if m not in sys.modules or not isinstance(sys.modules[m], MagicMock):
             try:

@@ -10,8 +10,10 @@ struct Conv3x3Args {
   const float* bias;  // [Cout] | null
   const float* res;   // [B,H,W,Cout] | null, added before the ReLU
   ViewW d0, d1;       // channel-split destinations (d1.p may be null)
-  const float* mask0; // | null: same geometry as d0; store 0 where mask0 <= 0 (ReLU mask of the source's producer)
-  const float* mask1; // | null: same for d1
+  // packed ReLU masks, one BYTE per (pixel, 8-channel group), bit j = channel 8g+j was > 0:
+  const unsigned char* mask0;  // | null: geometry of d0 with C/8 bytes per pixel; the stored value is zeroed where the bit is clear
+  const unsigned char* mask1;  // | null: same for d1
+  unsigned char* mask_out;     // | null: geometry of d0 (needs d1.p == null, Cout % 8 == 0): bit = (stored output > 0)
   int B, H, W, Cin, Cout, relu, round_out;
   int wfmt;  // 0: wp packed by pu_pack_w3x3; 1: wp is the raw OIHW weight (forward); 2: raw OIHW, conv is the dgrad
   int tilesX, tilesY;

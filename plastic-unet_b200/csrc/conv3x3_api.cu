@@ -21,7 +21,7 @@ int pu_conv3x3_fwd(const float* src0, int H0, int W0, int C0, int oy0, int ox0,
                    const float* wp, const float* bias, const float* res, int flags,
                    float* dst0, int Hd0, int Wd0, int Cd0, int oyd0, int oxd0,
                    float* dst1, int Hd1, int Wd1, int Cd1, int oyd1, int oxd1,
-                   const float* mask0, const float* mask1,
+                   const unsigned char* mask0, const unsigned char* mask1, unsigned char* mask_out,
                    int B, int H, int W, int Cout, int math, int wfmt, void* stream) {
   PU_REQUIRE(B > 0 && H > 0 && W > 0 && Cout > 0 && wp != nullptr, PU_ERR_BAD_ARG, "pu_conv3x3_fwd: bad dims");
   PU_REQUIRE(wfmt >= 0 && wfmt <= 2, PU_ERR_BAD_ARG, "pu_conv3x3_fwd: unknown weight format %d", wfmt);
@@ -52,8 +52,13 @@ int pu_conv3x3_fwd(const float* src0, int H0, int W0, int C0, int oy0, int ox0,
   a.res = res;
   a.d0 = pu::ViewW{dst0, Hd0, Wd0, Cd0, oyd0, oxd0};
   a.d1 = pu::ViewW{dst1, Hd1, Wd1, Cd1, oyd1, oxd1};
+  PU_REQUIRE((mask0 == nullptr || Cd0 % 8 == 0) && (mask1 == nullptr || (dst1 != nullptr && Cd1 % 8 == 0)), PU_ERR_BAD_ARG,
+             "pu_conv3x3_fwd: packed masks need destination channel counts that are multiples of 8");
+  PU_REQUIRE(mask_out == nullptr || (dst1 == nullptr && Cout % 8 == 0), PU_ERR_BAD_ARG,
+             "pu_conv3x3_fwd: mask_out needs a single destination with Cout %% 8 == 0");
   a.mask0 = mask0;
   a.mask1 = mask1;
+  a.mask_out = mask_out;
   a.B = B; a.H = H; a.W = W; a.Cin = C0 + C1; a.Cout = Cout;
   a.relu = (flags & PU_FLAG_RELU) ? 1 : 0;
   a.round_out = (flags & PU_FLAG_ROUND_TF32) ? 1 : 0;

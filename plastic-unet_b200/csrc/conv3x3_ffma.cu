@@ -159,6 +159,12 @@ __global__ void __launch_bounds__(NT) conv3x3_ffma_kernel(const Conv3x3Args a) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = round_tf32(o[j]);
     }
+    if (a.mask_out != nullptr) {  // packed mask of this op's own output (single destination, Cout % 8 == 0: checked by the API)
+      unsigned m = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) m |= (o[j] > 0.f ? 1u : 0u) << j;
+      a.mask_out[(((size_t)b * a.d0.Hs + (gy + a.d0.oy)) * a.d0.Ws + (gx + a.d0.ox)) * (a.d0.C / 8) + (co0 >> 3)] = (unsigned char)m;
+    }
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int co = co0 + 4 * h;
@@ -170,13 +176,13 @@ __global__ void __launch_bounds__(NT) conv3x3_ffma_kernel(const Conv3x3Args a) {
       const size_t doff = (((size_t)b * d.Hs + (gy + d.oy)) * d.Ws + (gx + d.ox)) * d.C + cd;
       float* dp = d.p + doff;
       if ((d.C % 4 == 0) && (a.d0.C % 4 == 0) && (co + 3 < a.Cout)) {
-        const float* mk = first ? a.mask0 : a.mask1;
-        if (mk != nullptr) {
-          const float4 m = ldg4(mk + doff);
-          o[4 * h] = m.x > 0.f ? o[4 * h] : 0.f;
-          o[4 * h + 1] = m.y > 0.f ? o[4 * h + 1] : 0.f;
-          o[4 * h + 2] = m.z > 0.f ? o[4 * h + 2] : 0.f;
-          o[4 * h + 3] = m.w > 0.f ? o[4 * h + 3] : 0.f;
+        const unsigned char* mk = first ? a.mask0 : a.mask1;
+        if (mk != nullptr) {  // packed ReLU mask: byte (pixel, cd / 8), bits cd % 8 ..
+          const unsigned m = (unsigned)__ldg(mk + (doff - cd) / 8 + (cd >> 3)) >> (cd & 7);
+          o[4 * h] = (m & 1u) ? o[4 * h] : 0.f;
+          o[4 * h + 1] = (m & 2u) ? o[4 * h + 1] : 0.f;
+          o[4 * h + 2] = (m & 4u) ? o[4 * h + 2] : 0.f;
+          o[4 * h + 3] = (m & 8u) ? o[4 * h + 3] : 0.f;
         }
         *reinterpret_cast<float4*>(dp) = make_float4(o[4 * h], o[4 * h + 1], o[4 * h + 2], o[4 * h + 3]);
       } else {
@@ -188,9 +194,9 @@ __global__ void __launch_bounds__(NT) conv3x3_ffma_kernel(const Conv3x3Args a) {
           const ViewW d2 = f2 ? a.d0 : a.d1;
           const int c2 = f2 ? c : c - a.d0.C;
           const size_t off2 = (((size_t)b * d2.Hs + (gy + d2.oy)) * d2.Ws + (gx + d2.ox)) * d2.C + c2;
-          const float* mk2 = f2 ? a.mask0 : a.mask1;
+          const unsigned char* mk2 = f2 ? a.mask0 : a.mask1;
           float ov = o[4 * h + j];
-          if (mk2 != nullptr && !(__ldg(mk2 + off2) > 0.f)) ov = 0.f;
+          if (mk2 != nullptr && !((__ldg(mk2 + (off2 - c2) / 8 + (c2 >> 3)) >> (c2 & 7)) & 1u)) ov = 0.f;
           d2.p[off2] = ov;
         }
       }

@@ -60,8 +60,9 @@ struct TcArgs {
   const float* bias;
   const float* res;
   ViewW d0, d1;
-  const float* mask0;  // | null: geometry of d0; the stored value is zeroed where mask0 <= 0
-  const float* mask1;
+  const unsigned char* mask0;  // | null: packed ReLU mask, geometry of d0 with C/8 bytes per pixel; clear bit -> stored value 0
+  const unsigned char* mask1;
+  unsigned char* mask_out;     // | null: packed mask of this conv's own output (geometry of d0, Cout/8 bytes per pixel)
   int B, H, W, Cout, relu, round_out;
   int TH, TW, PW, tilesX, tilesY;
   int nmb, a_bytes, w_bytes_max, tmem_cols, nchunks, nstages;
@@ -484,8 +485,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const __grid_
     for (int j = 0; j < 8; ++j) bias0[j] = 0.f;
     if (NQ == 1 && has_bias) load_bias(co_base, bias0);
 
-    // kx realignment + fused pointwise tail of one unit
-    auto finish = [&](const uint32_t* v, bool ok, float* dst, bool has_aux, const float* aux, const float* bb) {
+    // kx realignment + fused pointwise tail of one unit.  mbits: packed ReLU mask of the destination's 8 channels (dgrad;
+    // 0xff = keep everything); mdst: where to store the packed mask of this unit's own output (forward; may be null)
+    auto finish = [&](const uint32_t* v, bool ok, float* dst, bool has_aux, const float* aux, const float* bb, uint32_t mbits,
+                      unsigned char* mdst) {
       float o[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -498,14 +501,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const __grid_
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] += bb[j];
       }
-      if (has_aux) {
-        if (has_mask) {  // dgrad: ReLU mask of the layer that produced this source
+      if (has_aux) {  // residual
 #pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] = aux[j] > 0.f ? o[j] : 0.f;
-        } else {
+        for (int j = 0; j < 8; ++j) o[j] += aux[j];
+      }
+      if (has_mask) {  // dgrad: ReLU mask of the layer that produced this source
 #pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] += aux[j];
-        }
+        for (int j = 0; j < 8; ++j) o[j] = (mbits >> j) & 1u ? o[j] : 0.f;
       }
       if (relu) {
 #pragma unroll
@@ -516,7 +518,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const __grid_
         for (int j = 0; j < 8; ++j) o[j] = __uint_as_float((__float_as_uint(o[j]) + 0x1000u) & 0xffffe000u);
       }
       stg8(dst, o);
+      if (mdst != nullptr) {
+        uint32_t m = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) m |= (o[j] > 0.f ? 1u : 0u) << j;
+        *mdst = (unsigned char)m;
+      }
     };
+    // this warp's MMA blocks of a tile are mb = set + i * kEpiSets, i < kMaxI (compile-time bound so that the packed-mask
+    // bytes prefetched before the accumulators are ready stay in registers)
+    constexpr int kMaxI = (256 / N3 + kEpiSets - 1) / kEpiSets;
 
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
@@ -530,10 +541,33 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const __grid_
       const size_t o1 = a.d1.p == nullptr ? 0 : (((size_t)b * a.d1.Hs + (y0 + a.d1.oy)) * a.d1.Ws + (x0 + a.d1.ox)) * a.d1.C;
       float* const d0b = a.d0.p + o0;
       float* const d1b = a.d1.p == nullptr ? nullptr : a.d1.p + o1;
-      const float* const m0b = a.mask0 == nullptr ? nullptr : a.mask0 + o0;
-      const float* const m1b = a.mask1 == nullptr ? nullptr : a.mask1 + o1;
+      const unsigned char* const m0b = a.mask0 == nullptr ? nullptr : a.mask0 + o0 / 8;  // o0 is a multiple of d0.C, d0.C of 8
+      const unsigned char* const m1b = a.mask1 == nullptr ? nullptr : a.mask1 + o1 / 8;
+      unsigned char* const mob = a.mask_out == nullptr ? nullptr : a.mask_out + o0 / 8 + (co_base >> 3);
       const float* const rsb = has_res ? a.res + (((size_t)b * a.H + y0) * a.W + x0) * a.Cout + co_base : nullptr;
       const int as = tcount & 1;
+      // ---- packed ReLU masks of this tile's units: requested BEFORE waiting for the accumulators, so that their global
+      // latency hides behind the MMAs (one byte per unit instead of re-reading 32 bytes of fp32 activation per unit)
+      uint32_t mk[kMaxI][NQ];
+      if (has_mask) {
+        int yy_ = yy0, xx_ = xx0;
+#pragma unroll
+        for (int i = 0; i < kMaxI; ++i) {
+          const bool ok_ = live && (set + i * kEpiSets) < a.nmb && yy_ < ymax && xx_ < xmax;
+          const int p0_ = (yy_ * a.d0.Ws + xx_) * (a.d0.C >> 3);
+          const int p1_ = a.d1.p == nullptr ? 0 : (yy_ * a.d1.Ws + xx_) * (a.d1.C >> 3);
+#pragma unroll
+          for (int q = 0; q < NQ; ++q) {
+            const int co = co_base + 8 * q;
+            const unsigned char* mp = co < a.d0.C ? (m0b == nullptr ? nullptr : m0b + p0_ + (co >> 3))
+                                                  : (m1b == nullptr ? nullptr : m1b + p1_ + ((co - a.d0.C) >> 3));
+            mk[i][q] = (ok_ && mp != nullptr && q < nq_valid) ? (uint32_t)__ldg(mp) : 0xffu;
+          }
+          yy_ += step_y;
+          xx_ += step_x;
+          if (xx_ >= a.PW) { xx_ -= a.PW; ++yy_; }
+        }
+      }
       mbar_wait(tfull_bar(as), (tcount >> 1) & 1);
       tc_fence_after();
       if (warp == kEpiWarp0 && lane == 0) stamp(3, tcount);
@@ -548,18 +582,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const __grid_
         // (experiment) no TMEM reads at all
       } else if (NQ == 1) {
         // 8-channel co block: everything goes to d0; two of this warp's blocks per TMEM wait
-        const bool has_aux = has_mask ? m0b != nullptr : has_res;
-        const float* const xb = has_mask ? m0b : rsb;
-        const int xs_y = has_mask ? a.d0.Ws * a.d0.C : a.W * a.Cout, xs_x = has_mask ? a.d0.C : a.Cout;
-        for (int mb = set; mb < a.nmb; mb += 2 * kEpiSets) {
+        const bool has_aux = has_res;
+        const float* const xb = rsb;
+        const int xs_y = a.W * a.Cout, xs_x = a.Cout;
+#pragma unroll
+        for (int i = 0; i < kMaxI; i += 2) {
+          const int mb = set + i * kEpiSets;
+          if (mb >= a.nmb) break;
           uint32_t v[2][24];
           float aux[2][8];
           const bool okA = live && yy < ymax && xx < xmax;
-          const int offA = (yy * a.d0.Ws + xx) * a.d0.C, xoA = yy * xs_y + xx * xs_x;
+          const int pixA = yy * a.d0.Ws + xx, xoA = yy * xs_y + xx * xs_x;
           advance();
-          const bool haveB = mb + kEpiSets < a.nmb;
+          const bool haveB = (i + 1 < kMaxI) && mb + kEpiSets < a.nmb;
           const bool okB = haveB && live && yy < ymax && xx < xmax;
-          const int offB = (yy * a.d0.Ws + xx) * a.d0.C, xoB = yy * xs_y + xx * xs_x;
+          const int pixB = yy * a.d0.Ws + xx, xoB = yy * xs_y + xx * xs_x;
           advance();
           const uint32_t tA = tbase + (uint32_t)(mb * N3);
           tmem_ld8(tA, v[0]);
@@ -576,13 +613,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const __grid_
             if (okB) ldg8(xb + xoB, aux[1]);
           }
           tmem_ld_wait();
-          finish(v[0], okA, d0b + offA, has_aux, aux[0], bias0);
-          if (haveB) finish(v[1], okB, d0b + offB, has_aux, aux[1], bias0);
+          finish(v[0], okA, d0b + pixA * a.d0.C, has_aux, aux[0], bias0, has_mask ? mk[i][0] : 0xffu, mob == nullptr ? nullptr : mob + pixA);
+          if (haveB)
+            finish(v[1], okB, d0b + pixB * a.d0.C, has_aux, aux[1], bias0, has_mask ? mk[(i + 1) % kMaxI][0] : 0xffu,
+                   mob == nullptr ? nullptr : mob + pixB);
         }
       } else {
-        for (int mb = set; mb < a.nmb; mb += kEpiSets) {
+#pragma unroll
+        for (int i = 0; i < kMaxI; ++i) {
+          const int mb = set + i * kEpiSets;
+          if (mb >= a.nmb) break;
           const bool ok = live && yy < ymax && xx < xmax;
-          const int off0 = (yy * a.d0.Ws + xx) * a.d0.C;
+          const int pix0 = yy * a.d0.Ws + xx;
+          const int off0 = pix0 * a.d0.C;
           const int off1 = d1b == nullptr ? 0 : (yy * a.d1.Ws + xx) * a.d1.C;
           const int offr = (yy * a.W + xx) * a.Cout;
           advance();
@@ -598,22 +641,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const __grid_
             tmem_ld8(tA + 8 + COLS, v[1] + 8);
             tmem_ld8(tA + 8 + 2 * COLS, v[1] + 16);
             float* dst[2];
-            bool okq[2], has_aux[2];
+            bool okq[2];
+            unsigned char* mdst[2];
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
               const int co = co_base + 8 * (q + k);  // warp-uniform: which destination tensor this channel group belongs to
               const bool first = co < a.d0.C;
               okq[k] = ok && (q + k) < nq_valid;
               dst[k] = first ? d0b + off0 + co : d1b + off1 + (co - a.d0.C);
-              const float* xp = has_mask ? (first ? (m0b == nullptr ? nullptr : m0b + off0 + co) : (m1b == nullptr ? nullptr : m1b + off1 + (co - a.d0.C)))
-                                         : (has_res ? rsb + offr + 8 * (q + k) : nullptr);
-              has_aux[k] = xp != nullptr;
-              if (has_aux[k] && okq[k]) ldg8(xp, aux[k]);
+              mdst[k] = mob == nullptr ? nullptr : mob + pix0 * (a.d0.C >> 3) + (q + k);
+              if (has_res && okq[k]) ldg8(rsb + offr + 8 * (q + k), aux[k]);
               if (has_bias && okq[k]) load_bias(co, bb[k]);
             }
             tmem_ld_wait();
-            finish(v[0], okq[0], dst[0], has_aux[0], aux[0], bb[0]);
-            finish(v[1], okq[1], dst[1], has_aux[1], aux[1], bb[1]);
+            finish(v[0], okq[0], dst[0], has_res, aux[0], bb[0], has_mask ? mk[i][q] : 0xffu, mdst[0]);
+            finish(v[1], okq[1], dst[1], has_res, aux[1], bb[1], has_mask ? mk[i][(q + 1) % NQ] : 0xffu, mdst[1]);
           }
         }
       }
@@ -924,7 +966,7 @@ int conv3x3_fwd_tc(const Conv3x3Args& a, cudaStream_t st) {
   }
   TcArgs ta;
   ta.wpk = a.wp; ta.bias = a.bias; ta.res = a.res; ta.d0 = a.d0; ta.d1 = a.d1;
-  ta.mask0 = a.mask0; ta.mask1 = a.mask1;
+  ta.mask0 = a.mask0; ta.mask1 = a.mask1; ta.mask_out = a.mask_out;
   ta.B = a.B; ta.H = a.H; ta.W = a.W; ta.Cout = a.Cout; ta.relu = a.relu; ta.round_out = a.round_out;
   ta.TH = p.TH; ta.TW = p.TW; ta.PW = p.PW; ta.tilesX = p.tilesX; ta.tilesY = p.tilesY;
   ta.nmb = p.nmb; ta.a_bytes = p.a_bytes; ta.w_bytes_max = p.w_bytes_max; ta.nstages = p.nstages;

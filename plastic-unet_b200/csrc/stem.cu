@@ -11,7 +11,8 @@ namespace pu {
 // y[p][co] = act(bias[co] + sum_tap x[p + tap] * w[co][0][tap]);  CO output channels per pixel, thread = pixel
 template <int CO>
 __global__ void __launch_bounds__(256) conv3x3_c1_fwd_kernel(const View s0, const float* __restrict__ w, const float* __restrict__ bias,
-                                                             const ViewW d0, int B, int H, int W, int relu, int round_out) {
+                                                             const ViewW d0, unsigned char* __restrict__ mask_out, int B, int H, int W,
+                                                             int relu, int round_out) {
   __shared__ __align__(16) float ws[9][CO];
   __shared__ __align__(16) float bs[CO];
   for (int i = threadIdx.x; i < 9 * CO; i += blockDim.x) {
@@ -41,13 +42,20 @@ __global__ void __launch_bounds__(256) conv3x3_c1_fwd_kernel(const View s0, cons
     for (int tap = 0; tap < 9; ++tap)
 #pragma unroll
       for (int j = 0; j < CO; ++j) acc[j] = fmaf(xv[tap], ws[tap][j], acc[j]);
-    float* o = d0.p + (((size_t)b * d0.Hs + (y + d0.oy)) * d0.Ws + (x + d0.ox)) * d0.C;
+    const size_t opix = ((size_t)b * d0.Hs + (y + d0.oy)) * d0.Ws + (x + d0.ox);
+    float* o = d0.p + opix * d0.C;
+    unsigned m = 0;
 #pragma unroll
     for (int j = 0; j < CO; j += 4) {
       float4 v = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
       if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
       if (round_out) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
       *reinterpret_cast<float4*>(o + j) = v;
+      m |= ((v.x > 0.f ? 1u : 0u) | (v.y > 0.f ? 2u : 0u) | (v.z > 0.f ? 4u : 0u) | (v.w > 0.f ? 8u : 0u)) << j;
+    }
+    if (mask_out != nullptr) {  // packed ReLU mask of the output, one byte per 8 channels
+#pragma unroll
+      for (int g8 = 0; g8 < CO / 8; ++g8) mask_out[opix * (CO / 8) + g8] = (unsigned char)((m >> (8 * g8)) & 0xffu);
     }
   }
 }
@@ -110,8 +118,8 @@ int conv3x3_c1_fwd(const Conv3x3Args& a, cudaStream_t st) {
   const long long npix = (long long)a.B * a.H * a.W;
   long long blocks = (npix + 255) / 256;
   if (blocks > 8LL * kNumSMs) blocks = 8LL * kNumSMs;
-  if (a.Cout == 8) conv3x3_c1_fwd_kernel<8><<<(unsigned)blocks, 256, 0, st>>>(a.s0, a.wp, a.bias, a.d0, a.B, a.H, a.W, a.relu, a.round_out);
-  else conv3x3_c1_fwd_kernel<16><<<(unsigned)blocks, 256, 0, st>>>(a.s0, a.wp, a.bias, a.d0, a.B, a.H, a.W, a.relu, a.round_out);
+  if (a.Cout == 8) conv3x3_c1_fwd_kernel<8><<<(unsigned)blocks, 256, 0, st>>>(a.s0, a.wp, a.bias, a.d0, a.mask_out, a.B, a.H, a.W, a.relu, a.round_out);
+  else conv3x3_c1_fwd_kernel<16><<<(unsigned)blocks, 256, 0, st>>>(a.s0, a.wp, a.bias, a.d0, a.mask_out, a.B, a.H, a.W, a.relu, a.round_out);
   return post_launch("pu_conv3x3_fwd (stem)");
 }
 

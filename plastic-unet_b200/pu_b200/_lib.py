@@ -25,6 +25,7 @@ _CTYPE = {
     "int*": ctypes.c_void_p,
     "const int*": ctypes.c_void_p,
     "unsigned char*": ctypes.c_void_p,
+    "const unsigned char*": ctypes.c_void_p,
     "double": ctypes.c_double,
     "int": ctypes.c_int,
     "long long": ctypes.c_longlong,

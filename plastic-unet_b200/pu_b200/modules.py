@@ -35,12 +35,22 @@ def _default_math() -> str:
 # shared pieces
 # --------------------------------------------------------------------------------------------------
 def _c3(x0, conv, relu, x1=None, res=None, H=None, W=None, off0=(0, 0), off1=(0, 0), math=ops.MATH_FP32,
-        mask0=False, mask1=False, premasked=False):
-    """conv3x3 over cat[x0, x1] windows with fused bias / residual / ReLU using the parameters held by `conv`."""
+        m0=None, m1=None, premasked=False, emit_mask=False):
+    """conv3x3 over cat[x0, x1] windows with fused bias / residual / ReLU using the parameters held by `conv`.
+    emit_mask: -> (y, packed ReLU mask of y) instead of y."""
     if H is None:
         H, W = x0.shape[1], x0.shape[2]
-    return ops.conv3x3(x0, x1, conv.weight, conv.bias, res, relu, H, W, off0[0], off0[1], off1[0], off1[1], math,
-                       mask0, mask1, premasked)
+    y, ym = ops.conv3x3_m(x0, x1, conv.weight, conv.bias, res, relu, H, W, off0[0], off0[1], off1[0], off1[1], math,
+                          m0, m1, premasked, emit_mask)
+    return (y, ym) if emit_mask else y
+
+
+class Masked:
+    """A ReLU output together with its packed mask (premasked-gradient protocol)."""
+    __slots__ = ("t", "m")
+
+    def __init__(self, t, m=None):
+        self.t, self.m = t, m
 
 
 def _bn(x, bn, relu, math=ops.MATH_FP32):
@@ -174,17 +184,23 @@ class double_conv(nn.Module):
                 nn.Conv2d(in_ch, out_ch, 3, padding=1), nn.ReLU(inplace=True),
                 nn.Conv2d(out_ch, out_ch, 3, padding=1), nn.ReLU(inplace=True))
 
-    def run(self, x0, math, x1=None, H=None, W=None, off0=(0, 0), off1=(0, 0), in0_relu=False, in1_relu=False, premask=False):
-        """premask: premasked-gradient protocol (TF32 mode, no BN): the ReLU mask of each conv is applied by the
-        backward epilogue of its consumers instead of a separate pass; in0_relu/in1_relu: the sources are such outputs."""
+    def run(self, x0, math, x1=None, H=None, W=None, off0=(0, 0), off1=(0, 0), m0=None, m1=None, premask=False):
+        """premask: premasked-gradient protocol (TF32 mode, no BN): the ReLU mask of each conv is applied by the backward
+        epilogue of its consumers instead of a separate pass; every conv emits the packed mask of its output from its
+        forward epilogue (1 bit per element) and m0/m1 are the packed masks of sources that are such outputs.
+        Returns the output tensor, or Masked(output, packed mask) when premask."""
         if self.batch_norm:
             y = _c3(x0, self.conv[0], False, x1=x1, H=H, W=W, off0=off0, off1=off1, math=math)
             y = _bn(y, self.conv[1], True, math)
             y = _c3(y, self.conv[3], False, math=math)
             return _bn(y, self.conv[4], True, math)
-        y = _c3(x0, self.conv[0], True, x1=x1, H=H, W=W, off0=off0, off1=off1, math=math, mask0=in0_relu, mask1=in1_relu,
-                premasked=premask)
-        return _c3(y, self.conv[2], True, math=math, mask0=premask, premasked=premask)
+        if not premask:
+            y = _c3(x0, self.conv[0], True, x1=x1, H=H, W=W, off0=off0, off1=off1, math=math)
+            return _c3(y, self.conv[2], True, math=math)
+        y, ym = _c3(x0, self.conv[0], True, x1=x1, H=H, W=W, off0=off0, off1=off1, math=math, m0=m0, m1=m1, premasked=True,
+                    emit_mask=True)
+        z, zm = _c3(y, self.conv[2], True, math=math, m0=ym, premasked=True, emit_mask=True)
+        return Masked(z, zm)
 
 
 class inconv(nn.Module):
@@ -202,7 +218,9 @@ class down(nn.Module):
         self.mpconv = nn.Sequential(nn.MaxPool2d(2), double_conv(in_ch, out_ch, batch_norm))
 
     def run(self, x, math, premask=False):
-        return self.mpconv[1].run(ops.maxpool2(x, None, premask), math, premask=premask)
+        """x: tensor, or Masked when premask (the pool's backward then applies the ReLU mask of x itself: it reads x anyway)."""
+        xt = x.t if premask else x
+        return self.mpconv[1].run(ops.maxpool2(xt, None, premask), math, premask=premask)
 
 
 class up(nn.Module):
@@ -219,6 +237,9 @@ class up(nn.Module):
         self.conv = double_conv(in_ch, out_ch, batch_norm)
 
     def run(self, x1, x2, math, premask=False):
+        m2 = None
+        if premask:  # Masked inputs: x1 (deep tensor; the transposed conv's dgrad masks with x1 itself), x2 (skip) with its packed mask
+            x1, x2, m2 = x1.t, x2.t, x2.m
         u = ops.bilinear2x(x1) if self.bilinear else ops.convT2x2s2(x1, self.up.weight, self.up.bias, math == ops.MATH_TF32, premask)
         diffX = u.shape[1] - x2.shape[1]  # reference names: size()[2] == H
         diffY = u.shape[2] - x2.shape[2]
@@ -230,8 +251,7 @@ class up(nn.Module):
         if h_new != u.shape[1] or w_new != u.shape[2]:
             raise RuntimeError("Sizes of tensors must match except in dimension 1")
         off_skip = (-(diffY // 2), -(diffX // 2))  # (oy, ox) of the crop window in the skip tensor
-        return self.conv.run(x2, math, x1=u, H=u.shape[1], W=u.shape[2], off0=off_skip, off1=(0, 0), in0_relu=premask,
-                             premask=premask)
+        return self.conv.run(x2, math, x1=u, H=u.shape[1], W=u.shape[2], off0=off_skip, off1=(0, 0), m0=m2, premask=premask)
 
 
 class outconv(nn.Module):
@@ -241,7 +261,7 @@ class outconv(nn.Module):
 
     def run(self, x, premask=False):
         w = self.conv.weight
-        return ops.conv1x1(x, w.view(w.shape[0], w.shape[1]), self.conv.bias, 0, False, False, premask)
+        return ops.conv1x1(x.t if premask else x, w.view(w.shape[0], w.shape[1]), self.conv.bias, 0, False, False, premask)
 
 
 class UNetp(_PlasticBase):
@@ -275,7 +295,7 @@ class UNetp(_PlasticBase):
         x = self._to_nhwc(x)
         # premasked-gradient protocol (backward only, TF32 mode without BN / bilinear / ragged output conv): see DESIGN.md 4.2
         pm = (m == ops.MATH_TF32 and self.premask and not self.inc.conv.batch_norm and not self.up1.bilinear
-              and self.outc.conv.weight.shape[1] in (8, 16, 32, 64) and self.n_classes == 1)
+              and self.outc.conv.weight.shape[1] in (8, 16, 32, 64) and self.n_classes == 1 and self.n_channels == 1)
         feats = [self.inc.run(x, m, pm)]
         for k in range(1, self.depth + 1):
             feats.append(getattr(self, "down%d" % k).run(feats[-1], m, pm))

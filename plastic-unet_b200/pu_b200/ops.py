@@ -116,14 +116,34 @@ def _dims(t: Optional[Tensor]) -> Tuple[int, int, int]:
 # =================================================================================================
 # conv3x3 (+ concat/crop of two sources, + bias, + residual, + ReLU)
 # =================================================================================================
-@torch.library.custom_op("pu::conv3x3", mutates_args=())
-def conv3x3(x0: Tensor, x1: Optional[Tensor], weight: Tensor, bias: Optional[Tensor], res: Optional[Tensor],
-            relu: bool, H: int, W: int, oy0: int, ox0: int, oy1: int, ox1: int, math: int,
-            mask0: bool = False, mask1: bool = False, premasked: bool = False) -> Tensor:
-    """mask0/mask1/premasked implement the premasked-gradient protocol (backward only): `premasked` = every consumer
-    of this op's ReLU output multiplies the gradient it sends back by (y > 0), so this op's backward skips its own
-    mask pass; `mask0`/`mask1` = source 0/1 is such a ReLU output, i.e. this op's dgrad must apply (x > 0)."""
+def mask_like(y: Tensor) -> Tensor:
+    """An (uninitialised) packed ReLU-mask buffer for the NHWC tensor y: uint8 [B, H, W, C/8], bit j of byte g = channel 8g+j > 0."""
+    if y.shape[-1] % 8 != 0:
+        raise RuntimeError("packed ReLU masks need a channel count that is a multiple of 8")
+    return torch.empty(y.shape[:-1] + (y.shape[-1] // 8,), device=y.device, dtype=torch.uint8)
+
+
+def _chk_mask(m: Optional[Tensor], like: Optional[Tensor], what: str) -> None:
+    if m is None:
+        return
+    if like is None or not m.is_cuda or m.dtype != torch.uint8 or not m.is_contiguous() or \
+            tuple(m.shape) != tuple(like.shape[:-1]) + (like.shape[-1] // 8,):
+        raise RuntimeError("conv3x3: %s must be a contiguous uint8 CUDA tensor [B, H, W, C/8] matching its tensor" % what)
+
+
+@torch.library.custom_op("pu::conv3x3_m", mutates_args=())
+def conv3x3_m(x0: Tensor, x1: Optional[Tensor], weight: Tensor, bias: Optional[Tensor], res: Optional[Tensor],
+              relu: bool, H: int, W: int, oy0: int, ox0: int, oy1: int, ox1: int, math: int,
+              m0: Optional[Tensor] = None, m1: Optional[Tensor] = None, premasked: bool = False,
+              emit_mask: bool = False) -> Tuple[Tensor, Tensor]:
+    """-> (y, ymask).  m0/m1/premasked/emit_mask implement the premasked-gradient protocol.  `premasked` =
+    every consumer of this op's ReLU output multiplies the gradient it sends back by (y > 0), so this op's backward skips
+    its own mask pass; `m0`/`m1` = the PACKED ReLU mask (mask_like) of source 0/1, which is such a ReLU output: this
+    op's dgrad applies it in its epilogue (backward only); `emit_mask`: the forward epilogue also writes the packed mask
+    of this op's own output (ymask = mask_like(y); an empty tensor otherwise), to be handed to its consumers as m0/m1."""
     _chk(x0, x1, weight, bias, res)
+    _chk_mask(m0, x0, "m0")
+    _chk_mask(m1, x1, "m1")
     B = x0.shape[0]
     Cout, Cin = weight.shape[0], weight.shape[1]
     H0, W0, C0 = _dims(x0)
@@ -135,21 +155,33 @@ def conv3x3(x0: Tensor, x1: Optional[Tensor], weight: Tensor, bias: Optional[Ten
     flags = (FLAG_RELU if relu else 0) | (FLAG_ROUND_TF32 if math == MATH_TF32 else 0)
     wp, wfmt = _weight_operand(weight, 0, m, C0, C1, Cout, H, W)
     y = torch.empty((B, H, W, Cout), device=x0.device, dtype=torch.float32)
+    ymask = mask_like(y) if emit_mask else torch.empty(0, device=x0.device, dtype=torch.uint8)
     _lib.call("pu_conv3x3_fwd", x0.data_ptr(), H0, W0, C0, oy0, ox0, _p(x1), H1, W1, C1, oy1, ox1,
               wp.data_ptr(), _p(bias), _p(res), flags,
-              y.data_ptr(), H, W, Cout, 0, 0, None, 0, 0, 0, 0, 0, None, None, B, H, W, Cout, m, wfmt, _s())
-    return y
+              y.data_ptr(), H, W, Cout, 0, 0, None, 0, 0, 0, 0, 0, None, None, ymask.data_ptr() if emit_mask else None,
+              B, H, W, Cout, m, wfmt, _s())
+    return y, ymask
 
 
-@conv3x3.register_fake
-def _(x0, x1, weight, bias, res, relu, H, W, oy0, ox0, oy1, ox1, math, mask0=False, mask1=False, premasked=False):
-    return x0.new_empty((x0.shape[0], H, W, weight.shape[0]))
+@conv3x3_m.register_fake
+def _(x0, x1, weight, bias, res, relu, H, W, oy0, ox0, oy1, ox1, math, m0=None, m1=None, premasked=False, emit_mask=False):
+    y = x0.new_empty((x0.shape[0], H, W, weight.shape[0]))
+    return y, (x0.new_empty((x0.shape[0], H, W, weight.shape[0] // 8), dtype=torch.uint8) if emit_mask
+               else x0.new_empty(0, dtype=torch.uint8))
+
+
+def conv3x3(x0: Tensor, x1: Optional[Tensor], weight: Tensor, bias: Optional[Tensor], res: Optional[Tensor],
+            relu: bool, H: int, W: int, oy0: int, ox0: int, oy1: int, ox1: int, math: int,
+            m0: Optional[Tensor] = None, m1: Optional[Tensor] = None, premasked: bool = False) -> Tensor:
+    """conv3x3 without the packed-mask output (see conv3x3_m)."""
+    return conv3x3_m(x0, x1, weight, bias, res, relu, H, W, oy0, ox0, oy1, ox1, math, m0, m1, premasked, False)[0]
 
 
 @torch.library.custom_op("pu::conv3x3_bwd", mutates_args=())
 def conv3x3_bwd(dy: Tensor, y: Tensor, x0: Tensor, x1: Optional[Tensor], weight: Tensor, has_bias: bool, relu: bool,
                 H: int, W: int, oy0: int, ox0: int, oy1: int, ox1: int, math: int,
-                need_dx: bool, need_dw: bool, mask0: bool = False, mask1: bool = False, premasked: bool = False) -> List[Tensor]:
+                need_dx: bool, need_dw: bool, m0: Optional[Tensor] = None, m1: Optional[Tensor] = None,
+                premasked: bool = False) -> List[Tensor]:
     """-> [g, dx0, dx1, dw, db]; g = dy masked by the fused ReLU (== dy when relu is False)."""
     _chk(dy, y, x0, x1, weight)
     dev = dy.device
@@ -184,11 +216,12 @@ def conv3x3_bwd(dy: Tensor, y: Tensor, x0: Tensor, x1: Optional[Tensor], weight:
         if x1 is not None:
             full1 = (H1 == H and W1 == W)
             dx1 = (torch.empty if full1 else torch.zeros)((B, H1, W1, C1), device=dev, dtype=torch.float32)
+        # the packed masks share the geometry of the gradient tensors they gate (the op's window is a pointer offset)
         _lib.call("pu_conv3x3_fwd", g.data_ptr(), H, W, Cout, 0, 0, None, 0, 0, 0, 0, 0,
                   wpt.data_ptr(), None, None, FLAG_ROUND_TF32 if tf32 else 0,
                   dx0.data_ptr(), H0, W0, C0, oy0, ox0,
                   dx1.data_ptr() if x1 is not None else None, H1, W1, C1, oy1, ox1,
-                  x0.data_ptr() if mask0 else None, x1.data_ptr() if (mask1 and x1 is not None) else None,
+                  _p(m0), _p(m1) if x1 is not None else None, None,
                   B, H, W, Cin, md, wfmt, _s())
     dw = _e(dev)
     if need_dw:
@@ -216,7 +249,7 @@ def conv3x3_bwd(dy: Tensor, y: Tensor, x0: Tensor, x1: Optional[Tensor], weight:
 
 
 @conv3x3_bwd.register_fake
-def _(dy, y, x0, x1, weight, has_bias, relu, H, W, oy0, ox0, oy1, ox1, math, need_dx, need_dw, mask0=False, mask1=False,
+def _(dy, y, x0, x1, weight, has_bias, relu, H, W, oy0, ox0, oy1, ox1, math, need_dx, need_dw, m0=None, m1=None,
       premasked=False):
     e = dy.new_empty(0)
     return [torch.empty_like(dy) if ((relu or math == MATH_TF32) and not (premasked and relu)) else e,
@@ -227,27 +260,28 @@ def _(dy, y, x0, x1, weight, has_bias, relu, H, W, oy0, ox0, oy1, ox1, math, nee
 
 
 def _conv3x3_setup(ctx, inputs, output):
-    x0, x1, weight, bias, res, relu, H, W, oy0, ox0, oy1, ox1, math, mask0, mask1, premasked = inputs
-    ctx.save_for_backward(x0, x1, weight, output)
-    ctx.cfg = (bias is not None, res is not None, relu, H, W, oy0, ox0, oy1, ox1, math, mask0, mask1, premasked)
+    x0, x1, weight, bias, res, relu, H, W, oy0, ox0, oy1, ox1, math, m0, m1, premasked, _emit = inputs
+    ctx.save_for_backward(x0, x1, weight, output[0], m0, m1)
+    ctx.mark_non_differentiable(output[1])
+    ctx.cfg = (bias is not None, res is not None, relu, H, W, oy0, ox0, oy1, ox1, math, premasked)
 
 
-def _conv3x3_backward(ctx, dy):
-    x0, x1, weight, y = ctx.saved_tensors
-    has_bias, has_res, relu, H, W, oy0, ox0, oy1, ox1, math, mask0, mask1, premasked = ctx.cfg
+def _conv3x3_backward(ctx, dy, _dmask=None):
+    x0, x1, weight, y, m0, m1 = ctx.saved_tensors
+    has_bias, has_res, relu, H, W, oy0, ox0, oy1, ox1, math, premasked = ctx.cfg
     need = ctx.needs_input_grad
     need_dx = need[0] or (x1 is not None and need[1])
     dy = dy.contiguous()
     g, dx0, dx1, dw, db = conv3x3_bwd(dy, y, x0, x1, weight, has_bias and need[3], relu, H, W, oy0, ox0, oy1, ox1, math,
-                                      need_dx, need[2], mask0, mask1, premasked)
+                                      need_dx, need[2], m0, m1, premasked)
     gres = None
     if has_res and need[4]:
         gres = g if ((relu or math == MATH_TF32) and not (premasked and relu)) else dy
     return (dx0 if need[0] else None, dx1 if (x1 is not None and need[1]) else None, dw if need[2] else None,
-            db if (has_bias and need[3]) else None, gres, None, None, None, None, None, None, None, None, None, None, None)
+            db if (has_bias and need[3]) else None, gres, None, None, None, None, None, None, None, None, None, None, None, None)
 
 
-conv3x3.register_autograd(_conv3x3_backward, setup_context=_conv3x3_setup)
+conv3x3_m.register_autograd(_conv3x3_backward, setup_context=_conv3x3_setup)
 
 
 # =================================================================================================
@@ -419,7 +453,7 @@ def convT3x3s2_tc(x: Tensor, weight: Tensor, bias: Optional[Tensor], Ho: int, Wo
     y = torch.empty((B, Ho, Wo, Cout), device=x.device, dtype=torch.float32)
     _lib.call("pu_conv3x3_fwd", z.data_ptr(), Ho, Wo, Cin, 0, 0, None, 0, 0, 0, 0, 0,
               wp.data_ptr(), _p(bias), None, FLAG_ROUND_TF32,
-              y.data_ptr(), Ho, Wo, Cout, 0, 0, None, 0, 0, 0, 0, 0, None, None, B, Ho, Wo, Cout, MATH_TF32, wfmt, _s())
+              y.data_ptr(), Ho, Wo, Cout, 0, 0, None, 0, 0, 0, 0, 0, None, None, None, B, Ho, Wo, Cout, MATH_TF32, wfmt, _s())
     return y
 
 
@@ -446,7 +480,7 @@ def convT3x3s2_tc_bwd(dy: Tensor, x: Tensor, weight: Tensor, has_bias: bool, nee
         dz = torch.empty((B, Ho, Wo, Cin), device=dev, dtype=torch.float32)
         _lib.call("pu_conv3x3_fwd", g.data_ptr(), Ho, Wo, Cout, 0, 0, None, 0, 0, 0, 0, 0,
                   wp.data_ptr(), None, None, FLAG_ROUND_TF32,
-                  dz.data_ptr(), Ho, Wo, Cin, 0, 0, None, 0, 0, 0, 0, 0, None, None, B, Ho, Wo, Cin, MATH_TF32, wfmt, _s())
+                  dz.data_ptr(), Ho, Wo, Cin, 0, 0, None, 0, 0, 0, 0, 0, None, None, None, B, Ho, Wo, Cin, MATH_TF32, wfmt, _s())
         dx = torch.empty_like(x)
         _lib.call("pu_zero_insert2x_bwd", dz.data_ptr(), dx.data_ptr(), B, H, W, Cin, Ho, Wo, oy, ox, _s())
     if need_dw:

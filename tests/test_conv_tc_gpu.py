@@ -76,6 +76,48 @@ def test_conv3x3_tc_forward(B, C0, C1, Cout, H, W, relu, res):
     assert torch.equal(tf32_round(yo.cpu()), yo.cpu())
 
 
+def unpack_mask(m, C):
+    """uint8 [B,H,W,C/8] -> bool [B,H,W,C] (bit j of byte g = channel 8g+j)."""
+    bits = (m.unsqueeze(-1).to(torch.int32) >> torch.arange(8, device=m.device, dtype=torch.int32)) & 1
+    return bits.reshape(m.shape[:-1] + (C,)).bool()
+
+
+@pytest.mark.parametrize("math_name", ["tf32", "fp32"])
+@pytest.mark.parametrize("B,C0,C1,Cout,H,W,crop", [(2, 8, 0, 8, 128, 128, 0), (2, 8, 8, 8, 64, 64, 0), (3, 16, 16, 8, 37, 29, 2),
+                                                    (2, 32, 32, 16, 32, 32, 0), (2, 64, 0, 64, 8, 8, 0), (1, 64, 64, 128, 12, 12, 1),
+                                                    (64, 8, 8, 8, 128, 128, 0)])
+def test_packed_relu_masks(math_name, B, C0, C1, Cout, H, W, crop):
+    """Premasked-gradient protocol with PACKED masks: (1) the forward epilogue writes bit = (y > 0) for
+    its own output; (2) a dgrad given the packed masks of its two destinations equals the unmasked dgrad times the
+    unpacked masks, bit for bit — including the channel-split destinations and a cropped first source."""
+    from pu_b200 import ops
+    math = ops.MATH_TF32 if math_name == "tf32" else ops.MATH_FP32
+    g = torch.Generator().manual_seed(B + C0 + Cout + H)
+    x0 = tf32_round(torch.randn(B, H + crop, W + crop, C0, generator=g)).to(DEV)
+    x1 = tf32_round(torch.randn(B, H, W, C1, generator=g)).to(DEV) if C1 else None
+    w = tf32_round(torch.randn(Cout, C0 + C1, 3, 3, generator=g) / (3 * (C0 + C1) ** 0.5)).to(DEV)
+    b = torch.randn(Cout, generator=g).to(DEV)
+    with torch.no_grad():
+        y, ym = ops.conv3x3_m(x0, x1, w, b, None, True, H, W, crop, crop, 0, 0, math, None, None, True, True)
+        y_plain = ops.conv3x3(x0, x1, w, b, None, True, H, W, crop, crop, 0, 0, math)
+        assert torch.equal(y, y_plain)  # emitting the mask does not change the output
+        assert torch.equal(unpack_mask(ym, Cout), y > 0)
+        frac = float((y > 0).float().mean())
+        assert 0.2 < frac < 0.8
+        # dgrad with packed masks of the sources (random bits; the masks have the geometry of the FULL source tensors)
+        dy = tf32_round(torch.randn(B, H, W, Cout, generator=g)).to(DEV)
+        m0 = torch.randint(0, 256, (B, H + crop, W + crop, C0 // 8), generator=g, dtype=torch.uint8).to(DEV)
+        m1 = torch.randint(0, 256, (B, H, W, C1 // 8), generator=g, dtype=torch.uint8).to(DEV) if C1 else None
+        _, dx0, dx1, _, _ = ops.conv3x3_bwd(dy, y, x0, x1, w, False, True, H, W, crop, crop, 0, 0, math, True, False, m0, m1, True)
+        _, ex0, ex1, _, _ = ops.conv3x3_bwd(dy, y, x0, x1, w, False, True, H, W, crop, crop, 0, 0, math, True, False, None, None, True)
+        assert float(ex0.abs().max()) > 0
+        assert torch.equal(dx0, ex0 * unpack_mask(m0, C0))
+        if C1:
+            assert torch.equal(dx1, ex1 * unpack_mask(m1, C1))
+        if crop:  # the border of a cropped source receives no gradient
+            assert float(dx0[:, :crop].abs().max()) == 0 and float(dx0[:, :, :crop].abs().max()) == 0
+
+
 @pytest.mark.parametrize("C0,C1,Cout,H,W", [(8, 8, 8, 64, 64), (16, 0, 16, 32, 32), (32, 32, 16, 16, 16), (64, 0, 64, 8, 8),
                                              (32, 0, 32, 32, 32), (64, 64, 32, 16, 16), (128, 0, 64, 12, 12), (64, 0, 128, 6, 6)])
 def test_conv3x3_tc_autograd_vs_fp32_path(C0, C1, Cout, H, W):

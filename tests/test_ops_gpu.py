@@ -92,7 +92,7 @@ def test_conv3x3_stem_wgrad_with_bias(Cout, H, W, B):
     w = torch.randn(Cout, 1, 3, 3, generator=g).to(DEV)
     dy = torch.randn(B, H, W, Cout, generator=g).to(DEV)
     y = torch.ones_like(dy)
-    _, _, _, dw, db = ops.conv3x3_bwd(dy, y, x, None, w, True, True, H, W, 0, 0, 0, 0, ops.MATH_FP32, False, True, False, False, True)
+    _, _, _, dw, db = ops.conv3x3_bwd(dy, y, x, None, w, True, True, H, W, 0, 0, 0, 0, ops.MATH_FP32, False, True, None, None, True)
     xr = x.cpu().double().permute(0, 3, 1, 2)
     dyr = dy.cpu().double().permute(0, 3, 1, 2)
     dwr = torch.nn.grad.conv2d_weight(xr, (Cout, 1, 3, 3), dyr, padding=1)
