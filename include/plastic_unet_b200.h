@@ -158,8 +158,9 @@ int pu_zero_insert2x_bwd(const float* dz, float* dx, int B, int H, int W, int C,
  * MaxPool2d(2) floor mode (reference unet_p.py:139, unet_p_res.py:247) with the Dropout2d of
  * pool_drop (unet_p_res.py:248) fused as an optional per-(b,c) scale [B,C].                   */
 int pu_maxpool2_fwd(const float* x, const float* chan_scale, float* y, int B, int H, int W, int C, void* stream);
-/* dx gets dy*scale at the first maximum (row-major scan, ATen tie-break) and 0 elsewhere.    */
-int pu_maxpool2_bwd(const float* x, const float* chan_scale, const float* dy, float* dx,
+/* dx gets dy*scale at the first maximum (row-major scan, ATen tie-break) and 0 elsewhere.  acc (may be NULL, shape of
+ * x): a second gradient of x — the skip connection's (unet_p.py:165) — added in the same pass: dx = route(dy) + acc.   */
+int pu_maxpool2_bwd(const float* x, const float* chan_scale, const float* dy, const float* acc, float* dx,
                     int B, int H, int W, int C, int flags, void* stream);
 /* nn.Upsample(scale_factor=2, bilinear, align_corners=True) (reference unet_p.py:153)        */
 int pu_bilinear2x_fwd(const float* x, float* y, int B, int H, int W, int C, void* stream);

@@ -7,25 +7,87 @@
 //   trace: out = decay*hebb + eta/K * pre^T @ post, decay = 1-eta (Hebb) or 1 - eta*q_j/K (Oja),
 //          one fused pass (contraction + epilogue), exactly the reference at K == 1.
 //
-// The GEMMs are strict-fp32 shared-memory-tiled FFMA kernels (64x64x16 tiles, 4x4 per thread):
-// the head is < 1 % of the step (N^3 MACs) and its logits decide the
-// thresholded masks, so it stays in full fp32.
+// The GEMMs are strict-fp32 shared-memory-tiled FFMA kernels (64x64 tiles, 4x4 per thread, K staged in whole
+// 128-deep chunks): the head's logits decide the thresholded masks, so it stays in full fp32.
 #include "pu_common.cuh"
 
 namespace pu {
 
 enum { EPI_STORE = 0, EPI_SIGMOID = 1, EPI_ATOMIC = 2 };
 
-// C[M,N] (row-major, ldc) (+)= sum_k A(m,k) B(k,n), A(m,k) = A[m*sam + k*sak], B(k,n) = B[k*sbk + n*sbn]
-template <int EPI>
-__global__ void __launch_bounds__(256) gemm_ffma_kernel(const float* __restrict__ A, long long sam, long long sak,
-                                                        const float* __restrict__ Bm, long long sbk, long long sbn,
-                                                        float* __restrict__ C, long long ldc, int M, int N, int K, int kper) {
-  constexpr int BM = 64, BN = 64, BK = 16;
-  __shared__ __align__(16) float As[BK][BM + 4];
-  __shared__ __align__(16) float Bs[BK][BN + 4];
+// ---- strict-fp32 GEMM, whole-K-chunk staging --------------------------------------------------------------------------
+// C[M,N] (row-major, ldc) (+)= sum_k A(m,k) B(k,n), A(m,k) = A[m*sam + k*sak], B(k,n) = B[k*sbk + n*sbn].
+// 64x64 tile per CTA, 4x4 outputs per thread, K consumed in chunks of 128: ALL loads of a chunk (8 x 128-bit per thread
+// and operand) are in flight at once, then one barrier, then 128 k-steps from shared memory.  The head's K is 128
+// (nbf), so a CTA pays ONE global round trip instead of the eight dependent 16-deep rounds of gemm_ffma_kernel
+// (measured 18-22 us for a 0.27 GFLOP GEMM: latency-, not FMA-bound).  Operands that are contiguous along k are
+// transposed on the way into shared memory (As[k][m], Bs[k][n]: conflict-free float4 reads in the k loop).
+constexpr int G2_BM = 64, G2_BN = 64, G2_BK = 128;
+constexpr int G2_SMEM = 2 * G2_BK * (G2_BM + 4) * (int)sizeof(float);
+
+template <int ROWS>  // stage a ROWS(=64) x 128 tile into S[k][r] (row stride ROWS + 4)
+__device__ __forceinline__ void g2_stage(float* __restrict__ S, const float* __restrict__ P, long long s_r, long long s_k, int r0, int k0,
+                                         int r_end, int k_end, bool vec) {
+  constexpr int LD = ROWS + 4;
   const int tid = threadIdx.x;
-  const int m_blk = blockIdx.y * BM, n_blk = blockIdx.x * BN;
+  if (s_k == 1) {
+    // contiguous along k: thread -> (row r = i % 64, k quad kq = i / 64)
+#pragma unroll
+    for (int it = 0; it < (ROWS * G2_BK / 4) / 256; ++it) {
+      const int i = tid + it * 256;
+      const int r = i % ROWS, kq = i / ROWS;
+      const int gr = r0 + r, gk = k0 + 4 * kq;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gr < r_end) {
+        const float* src = P + gr * s_r + gk;
+        if (vec && gk + 3 < k_end) {
+          v = ldg4(src);
+        } else {
+          if (gk < k_end) v.x = __ldg(src);
+          if (gk + 1 < k_end) v.y = __ldg(src + 1);
+          if (gk + 2 < k_end) v.z = __ldg(src + 2);
+          if (gk + 3 < k_end) v.w = __ldg(src + 3);
+        }
+      }
+      S[(4 * kq + 0) * LD + r] = v.x;
+      S[(4 * kq + 1) * LD + r] = v.y;
+      S[(4 * kq + 2) * LD + r] = v.z;
+      S[(4 * kq + 3) * LD + r] = v.w;
+    }
+  } else {
+    // contiguous along the row index (s_r == 1): thread -> (row quad rq = i % 16, k = i / 16)
+#pragma unroll
+    for (int it = 0; it < (ROWS * G2_BK / 4) / 256; ++it) {
+      const int i = tid + it * 256;
+      const int rq = i % (ROWS / 4), k = i / (ROWS / 4);
+      const int gr = r0 + 4 * rq, gk = k0 + k;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gk < k_end) {
+        const float* src = P + gk * s_k + gr * s_r;
+        if (vec && s_r == 1 && gr + 3 < r_end) {
+          v = ldg4(src);
+        } else {
+          if (gr < r_end) v.x = __ldg(src);
+          if (gr + 1 < r_end) v.y = __ldg(src + s_r);
+          if (gr + 2 < r_end) v.z = __ldg(src + 2 * s_r);
+          if (gr + 3 < r_end) v.w = __ldg(src + 3 * s_r);
+        }
+      }
+      *reinterpret_cast<float4*>(S + k * LD + 4 * rq) = v;
+    }
+  }
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(256) gemm_chunk_kernel(const float* __restrict__ A, long long sam, long long sak, const float* __restrict__ Bm,
+                                                         long long sbk, long long sbn, float* __restrict__ C, long long ldc, int M, int N,
+                                                         int K, int kper, int vecA, int vecB) {
+  extern __shared__ __align__(16) float g2_smem[];
+  float* As = g2_smem;                          // [128][64 + 4]
+  float* Bs = g2_smem + G2_BK * (G2_BM + 4);    // [128][64 + 4]
+  constexpr int LD = G2_BM + 4;
+  const int tid = threadIdx.x;
+  const int m_blk = blockIdx.y * G2_BM, n_blk = blockIdx.x * G2_BN;
   const int k_begin = blockIdx.z * kper;
   const int k_end = min(K, k_begin + kper);
   const int tx = tid & 15, ty = tid >> 4;
@@ -34,52 +96,63 @@ __global__ void __launch_bounds__(256) gemm_ffma_kernel(const float* __restrict_
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-
-  for (int k0 = k_begin; k0 < k_end; k0 += BK) {
-    // A tile
-#pragma unroll
-    for (int r = 0; r < (BM * BK) / 256; ++r) {
-      const int i = tid + r * 256;
-      int m, k;
-      if (sak == 1) { m = i / BK; k = i % BK; } else { k = i / BM; m = i % BM; }
-      const int gm = m_blk + m, gk = k0 + k;
-      As[k][m] = (gm < M && gk < k_end) ? __ldg(A + gm * sam + gk * sak) : 0.f;
-    }
-#pragma unroll
-    for (int r = 0; r < (BN * BK) / 256; ++r) {
-      const int i = tid + r * 256;
-      int n, k;
-      if (sbk == 1) { n = i / BK; k = i % BK; } else { k = i / BN; n = i % BN; }
-      const int gn = n_blk + n, gk = k0 + k;
-      Bs[k][n] = (gn < N && gk < k_end) ? __ldg(Bm + gk * sbk + gn * sbn) : 0.f;
-    }
+  for (int k0 = k_begin; k0 < k_end; k0 += G2_BK) {
+    if (k0 > k_begin) __syncthreads();
+    g2_stage<G2_BM>(As, A, sam, sak, m_blk, k0, M, k_end, vecA != 0);
+    g2_stage<G2_BN>(Bs, Bm, sbn, sbk, n_blk, k0, N, k_end, vecB != 0);
     __syncthreads();
-#pragma unroll
-    for (int k = 0; k < BK; ++k) {
-      const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
-      const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+    const int kn = min(G2_BK, k_end - k0);
+#pragma unroll 8
+    for (int k = 0; k < kn; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(As + k * LD + ty * 4);
+      const float4 b = *reinterpret_cast<const float4*>(Bs + k * LD + tx * 4);
       const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
     }
-    __syncthreads();
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int gm = m_blk + ty * 4 + i;
     if (gm >= M) continue;
+    const int gn = n_blk + tx * 4;
+    float v[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int gn = n_blk + tx * 4 + j;
-      if (gn >= N) continue;
-      float v = acc[i][j];
-      if (EPI == EPI_SIGMOID) v = 1.f / (1.f + expf(-v));
-      if (EPI == EPI_ATOMIC) atomicAdd(C + gm * ldc + gn, v);
-      else C[gm * ldc + gn] = v;
+    for (int j = 0; j < 4; ++j) v[j] = EPI == EPI_SIGMOID ? 1.f / (1.f + expf(-acc[i][j])) : acc[i][j];
+    if (EPI == EPI_ATOMIC) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (gn + j < N) atomicAdd(C + gm * ldc + gn + j, v[j]);
+    } else if (gn + 3 < N && ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0)) {
+      *reinterpret_cast<float4*>(C + gm * ldc + gn) = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (gn + j < N) C[gm * ldc + gn + j] = v[j];
     }
   }
+}
+
+template <int EPI>
+static int launch_gemm_chunk(const float* A, long long sam, long long sak, const float* Bm, long long sbk, long long sbn, float* C, long long ldc,
+                             int M, int N, int K, int kper, int splits, cudaStream_t st, const char* what) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_chunk_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM);
+    if (e != cudaSuccess) {
+      set_error("%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
+      return PU_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  // 128-bit loads need 16-byte aligned rows: base pointer and the non-unit stride
+  const int vecA = aligned16(A) && ((sak == 1 ? sam : sak) % 4 == 0);
+  const int vecB = aligned16(Bm) && ((sbk == 1 ? sbn : sbk) % 4 == 0);
+  dim3 grid(cdiv(N, G2_BN), cdiv(M, G2_BM), splits);
+  gemm_chunk_kernel<EPI><<<grid, 256, G2_SMEM, st>>>(A, sam, sak, Bm, sbk, sbn, C, ldc, M, N, K, kper, vecA, vecB);
+  return post_launch(what);
 }
 
 __global__ void weff_kernel(const float* __restrict__ w, const float* __restrict__ alpha, const float* __restrict__ hebb,
@@ -238,10 +311,8 @@ int pu_plastic_head_fwd(const float* X, const float* w, const float* alpha, cons
   int rc = pu::post_launch("pu_plastic_head_fwd weff");
   if (rc) return rc;
   const int M = B * N;
-  dim3 grid(pu::cdiv(N, 64), pu::cdiv(M, 64), 1);
-  PU_REQUIRE(grid.y <= 65535, PU_ERR_UNSUPPORTED, "pu_plastic_head_fwd: B*N too large");
-  pu::gemm_ffma_kernel<pu::EPI_SIGMOID><<<grid, 256, 0, st>>>(X, N, 1, weff_out, N, 1, S, N, M, N, N, N);
-  return pu::post_launch("pu_plastic_head_fwd gemm");
+  PU_REQUIRE(pu::cdiv(M, 64) <= 65535, PU_ERR_UNSUPPORTED, "pu_plastic_head_fwd: B*N too large");
+  return pu::launch_gemm_chunk<pu::EPI_SIGMOID>(X, N, 1, weff_out, N, 1, S, N, M, N, N, N, 1, st, "pu_plastic_head_fwd gemm");
 }
 
 int pu_plastic_head_bwd(const float* X, const float* S, const float* gS, const float* weff, const float* alpha, const float* hebb,
@@ -261,10 +332,8 @@ int pu_plastic_head_bwd(const float* X, const float* S, const float* gS, const f
     if (rc) return rc;
   }
   if (gX != nullptr) {
-    dim3 grid(pu::cdiv(N, 64), pu::cdiv(M, 64), 1);
     // gX[m][n] = sum_k gA[m][k] * weff[n][k]
-    pu::gemm_ffma_kernel<pu::EPI_STORE><<<grid, 256, 0, st>>>(gA_ws, N, 1, weff, 1, N, gX, N, M, N, N, N);
-    rc = pu::post_launch("pu_plastic_head_bwd gX");
+    rc = pu::launch_gemm_chunk<pu::EPI_STORE>(gA_ws, N, 1, weff, 1, N, gX, N, M, N, N, N, 1, st, "pu_plastic_head_bwd gX");
     if (rc) return rc;
   }
   if (gw == nullptr) return PU_OK;
@@ -276,13 +345,11 @@ int pu_plastic_head_bwd(const float* X, const float* S, const float* gS, const f
   {
     // gW[i][j] = sum_m X[m][i] * gA[m][j], split over m
     const int tiles = pu::cdiv(N, 64) * pu::cdiv(N, 64);
-    int splits = (2 * pu::kNumSMs + tiles - 1) / tiles;
+    int splits = (pu::kNumSMs + tiles - 1) / tiles;
     int kper = (M + splits - 1) / splits;
-    kper = ((kper + 15) / 16) * 16;
+    kper = ((kper + 127) / 128) * 128;  // whole 128-deep chunks per split
     splits = (M + kper - 1) / kper;
-    dim3 grid(pu::cdiv(N, 64), pu::cdiv(N, 64), splits);
-    pu::gemm_ffma_kernel<pu::EPI_ATOMIC><<<grid, 256, 0, st>>>(X, 1, N, gA_ws, N, 1, gw, N, N, N, M, kper);
-    rc = pu::post_launch("pu_plastic_head_bwd gW");
+    rc = pu::launch_gemm_chunk<pu::EPI_ATOMIC>(X, 1, N, gA_ws, N, 1, gw, N, N, N, M, kper, splits, st, "pu_plastic_head_bwd gW");
     if (rc) return rc;
   }
   if (galpha != nullptr || ghebb != nullptr) {

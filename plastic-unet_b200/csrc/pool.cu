@@ -52,7 +52,7 @@ __global__ void maxpool2_fwd_kernel(const float* __restrict__ x, const float* __
 // (first element in (dy,dx) row-major scan that is strictly greater / NaN) and route dy*scale there.
 template <int V>
 __global__ void maxpool2_bwd_kernel(const float* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ dy,
-                                    float* __restrict__ dx, int B, int H, int W, int C, int mask_in) {
+                                    const float* __restrict__ acc, float* __restrict__ dx, int B, int H, int W, int C, int mask_in) {
   const int Ho = H / 2, Wo = W / 2, CV = C / V;
   const long long n = (long long)B * Ho * Wo * CV;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -97,7 +97,16 @@ __global__ void maxpool2_bwd_kernel(const float* __restrict__ x, const float* __
       float o[V];
 #pragma unroll
       for (int u = 0; u < V; ++u) o[u] = (arg[u] == k && !(mask_in && !(vals[k][u] > 0.f))) ? g[u] : 0.f;
-      float* q = dx + base + ((size_t)(k >> 1) * W + (k & 1)) * C;
+      const size_t qoff = base + ((size_t)(k >> 1) * W + (k & 1)) * C;
+      if (acc != nullptr) {  // the other gradient of x (skip connection), accumulated here instead of by a separate add pass
+        if (V == 4) {
+          const float4 a = ldg4(acc + qoff);
+          o[0] += a.x; o[1 % V] += a.y; o[2 % V] += a.z; o[3 % V] += a.w;
+        } else {
+          o[0] += __ldg(acc + qoff);
+        }
+      }
+      float* q = dx + qoff;
       if (V == 4) *reinterpret_cast<float4*>(q) = make_float4(o[0], o[1 % V], o[2 % V], o[3 % V]);
       else q[0] = o[0];
     }
@@ -242,23 +251,24 @@ int pu_maxpool2_fwd(const float* x, const float* chan_scale, float* y, int B, in
   return pu::post_launch("pu_maxpool2_fwd");
 }
 
-int pu_maxpool2_bwd(const float* x, const float* chan_scale, const float* dy, float* dx, int B, int H, int W, int C, int flags,
-                    void* stream) {
+int pu_maxpool2_bwd(const float* x, const float* chan_scale, const float* dy, const float* acc, float* dx, int B, int H, int W, int C,
+                    int flags, void* stream) {
   const int mask_in = (flags & PU_FLAG_MASK_IN) ? 1 : 0;
   PU_REQUIRE(x && dy && dx && B > 0 && H >= 2 && W >= 2 && C > 0, PU_ERR_BAD_ARG, "pu_maxpool2_bwd: bad argument");
   cudaStream_t st = pu::as_stream(stream);
-  if ((H & 1) || (W & 1)) {  // floor mode leaves the last row/column unpooled: their gradient is zero
-    cudaError_t e = cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)B * H * W * C, st);
+  if ((H & 1) || (W & 1)) {  // floor mode leaves the last row/column unpooled: their gradient is zero (or just acc)
+    const size_t bytes = sizeof(float) * (size_t)B * H * W * C;
+    cudaError_t e = acc != nullptr ? cudaMemcpyAsync(dx, acc, bytes, cudaMemcpyDeviceToDevice, st) : cudaMemsetAsync(dx, 0, bytes, st);
     if (e != cudaSuccess) {
       pu::set_error("pu_maxpool2_bwd memset: %s", cudaGetErrorString(e));
       return PU_ERR_CUDA;
     }
   }
   const long long nwin = (long long)B * (H / 2) * (W / 2);
-  if (C % 4 == 0 && pu::aligned16(x) && pu::aligned16(dy) && pu::aligned16(dx))
-    pu::maxpool2_bwd_kernel<4><<<pu::grid_for(nwin * (C / 4)), 256, 0, st>>>(x, chan_scale, dy, dx, B, H, W, C, mask_in);
+  if (C % 4 == 0 && pu::aligned16(x) && pu::aligned16(dy) && pu::aligned16(dx) && (acc == nullptr || pu::aligned16(acc)))
+    pu::maxpool2_bwd_kernel<4><<<pu::grid_for(nwin * (C / 4)), 256, 0, st>>>(x, chan_scale, dy, acc, dx, B, H, W, C, mask_in);
   else
-    pu::maxpool2_bwd_kernel<1><<<pu::grid_for(nwin * C), 256, 0, st>>>(x, chan_scale, dy, dx, B, H, W, C, mask_in);
+    pu::maxpool2_bwd_kernel<1><<<pu::grid_for(nwin * C), 256, 0, st>>>(x, chan_scale, dy, acc, dx, B, H, W, C, mask_in);
   return pu::post_launch("pu_maxpool2_bwd");
 }
 

@@ -222,6 +222,10 @@ class down(nn.Module):
         xt = x.t if premask else x
         return self.mpconv[1].run(ops.maxpool2(xt, None, premask), math, premask=premask)
 
+    def run_pooled(self, pooled, math, premask=False):
+        """The double conv on an already pooled tensor (UNetp.forward pools through ops.pool_skip)."""
+        return self.mpconv[1].run(pooled, math, premask=premask)
+
 
 class up(nn.Module):
     """ConvTranspose2d(k2,s2) (or bilinear x2) on the deep tensor, crop the skip, cat [skip, up], double_conv
@@ -296,9 +300,16 @@ class UNetp(_PlasticBase):
         # premasked-gradient protocol (backward only, TF32 mode without BN / bilinear / ragged output conv): see DESIGN.md 4.2
         pm = (m == ops.MATH_TF32 and self.premask and not self.inc.conv.batch_norm and not self.up1.bilinear
               and self.outc.conv.weight.shape[1] in (8, 16, 32, 64) and self.n_classes == 1 and self.n_channels == 1)
-        feats = [self.inc.run(x, m, pm)]
+        # each encoder level output feeds the pool of the next level AND a skip connection: ops.pool_skip returns both so
+        # that the two gradients are summed inside the pooling backward kernel (no separate accumulation pass)
+        feats = []
+        f = self.inc.run(x, m, pm)
         for k in range(1, self.depth + 1):
-            feats.append(getattr(self, "down%d" % k).run(feats[-1], m, pm))
+            ft, fm = (f.t, f.m) if pm else (f, None)
+            pooled, skip = ops.pool_skip(ft, pm)
+            feats.append(Masked(skip, fm) if pm else skip)
+            f = getattr(self, "down%d" % k).run_pooled(pooled, m, pm)
+        feats.append(f)
         y = feats[-1]
         for j in range(1, self.depth + 1):
             y = getattr(self, "up%d" % j).run(y, feats[self.depth - j], m, pm)

@@ -73,7 +73,27 @@ def _weight_operand(weight: Tensor, transpose: int, math: int, C0: int, C1: int,
     return _pack_w(weight, transpose, math, C0), W_PACKED
 
 
+# Weight images that do not fit in shared memory are packed by a separate kernel (pu_pack_w3x3).  The weights only change
+# in the optimizer, so TrainStep packs them all at the START of the step on a side stream, off the critical path:
+#   PACK_LOG   (a list, during the first warm-up step) records which (weight, transpose, math, C0) the step packs;
+#   PACK_CACHE {(data_ptr, transpose, math, C0): (packed tensor, event)} is then filled by TrainStep every step.
+PACK_LOG = None
+PACK_CACHE = None
+
+
 def _pack_w(weight: Tensor, transpose: int, math: int, C0: int) -> Tensor:
+    key = (weight.data_ptr(), transpose, math, C0)
+    if PACK_CACHE is not None and key in PACK_CACHE:
+        wp, ev = PACK_CACHE[key]
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
+        return wp
+    if PACK_LOG is not None:
+        PACK_LOG.append((weight, transpose, math, C0))
+    return _pack_w_now(weight, transpose, math, C0)
+
+
+def _pack_w_now(weight: Tensor, transpose: int, math: int, C0: int) -> Tensor:
     Cout, Cin = weight.shape[0], weight.shape[1]
     n = int(_lib.load().pu_pack_w3x3_floats(Cout, Cin, transpose, math, C0))
     wp = torch.empty(n, device=weight.device, dtype=torch.float32)
@@ -263,6 +283,7 @@ def _conv3x3_setup(ctx, inputs, output):
     x0, x1, weight, bias, res, relu, H, W, oy0, ox0, oy1, ox1, math, m0, m1, premasked, _emit = inputs
     ctx.save_for_backward(x0, x1, weight, output[0], m0, m1)
     ctx.mark_non_differentiable(output[1])
+    ctx.set_materialize_grads(False)  # no zero-filled "gradient" tensor for the packed mask on every backward
     ctx.cfg = (bias is not None, res is not None, relu, H, W, oy0, ox0, oy1, ox1, math, premasked)
 
 
@@ -270,6 +291,8 @@ def _conv3x3_backward(ctx, dy, _dmask=None):
     x0, x1, weight, y, m0, m1 = ctx.saved_tensors
     has_bias, has_res, relu, H, W, oy0, ox0, oy1, ox1, math, premasked = ctx.cfg
     need = ctx.needs_input_grad
+    if dy is None:  # (materialize_grads is off) nothing flows back through this conv
+        return (None,) * 17
     need_dx = need[0] or (x1 is not None and need[1])
     dy = dy.contiguous()
     g, dx0, dx1, dw, db = conv3x3_bwd(dy, y, x0, x1, weight, has_bias and need[3], relu, H, W, oy0, ox0, oy1, ox1, math,
@@ -605,18 +628,45 @@ def _(x, chan_scale, mask_in=False):
 
 
 @torch.library.custom_op("pu::maxpool2_bwd", mutates_args=())
-def maxpool2_bwd(dy: Tensor, x: Tensor, chan_scale: Optional[Tensor], mask_in: bool = False) -> Tensor:
-    _chk(dy, x, chan_scale)
+def maxpool2_bwd(dy: Tensor, x: Tensor, chan_scale: Optional[Tensor], mask_in: bool = False, acc: Optional[Tensor] = None) -> Tensor:
+    """acc: a second gradient of x (the skip connection's) summed in the same pass: dx = route(dy) + acc."""
+    _chk(dy, x, chan_scale, acc)
     B, H, W, C = x.shape
+    if acc is not None and acc.shape != x.shape:
+        raise RuntimeError("maxpool2_bwd: acc must have the shape of x")
     dx = torch.empty_like(x)
-    _lib.call("pu_maxpool2_bwd", x.data_ptr(), _p(chan_scale), dy.data_ptr(), dx.data_ptr(), B, H, W, C,
+    _lib.call("pu_maxpool2_bwd", x.data_ptr(), _p(chan_scale), dy.data_ptr(), _p(acc), dx.data_ptr(), B, H, W, C,
               FLAG_MASK_IN if mask_in else 0, _s())
     return dx
 
 
 @maxpool2_bwd.register_fake
-def _(dy, x, chan_scale, mask_in=False):
+def _(dy, x, chan_scale, mask_in=False, acc=None):
     return torch.empty_like(x)
+
+
+class _PoolSkip(torch.autograd.Function):
+    """x -> (maxpool2(x), x): the pooled tensor for the next encoder level and x itself as the skip connection
+    (unet_p.py:59-66).  Both gradients of x then reach ONE backward call, and the skip gradient is accumulated inside the
+    pooling backward kernel instead of by a separate elementwise add over the whole tensor."""
+
+    @staticmethod
+    def forward(ctx, x, mask_in):
+        ctx.save_for_backward(x)
+        ctx.mask_in = mask_in
+        ctx.set_materialize_grads(False)
+        return maxpool2(x, None, mask_in), x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, gy, gskip):
+        (x,) = ctx.saved_tensors
+        if gy is None:
+            return gskip, None
+        return maxpool2_bwd(gy.contiguous(), x, None, ctx.mask_in, None if gskip is None else gskip.contiguous()), None
+
+
+def pool_skip(x: Tensor, mask_in: bool = False) -> Tuple[Tensor, Tensor]:
+    return _PoolSkip.apply(x, mask_in)
 
 
 def _pool_setup(ctx, inputs, output):
@@ -627,7 +677,7 @@ def _pool_setup(ctx, inputs, output):
 
 def _pool_backward(ctx, dy):
     x, chan_scale = ctx.saved_tensors
-    return maxpool2_bwd(dy.contiguous(), x, chan_scale, ctx.mask_in), None, None
+    return maxpool2_bwd(dy.contiguous(), x, chan_scale, ctx.mask_in, None), None, None
 
 
 maxpool2.register_autograd(_pool_backward, setup_context=_pool_setup)

@@ -4,10 +4,14 @@ carry, captured once into a CUDA graph and replayed (no tracing compiler; refere
 All parameters live in ONE flat arena (and their gradients in another), so the optimizer is a single
 pu_adam_step launch and the data-parallel gradient exchange is a single all-reduce.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
 from . import _lib, ops
+
+_os_environ_get = os.environ.get
 
 
 class TrainStep:
@@ -58,17 +62,58 @@ class TrainStep:
         self.kernels_per_step = None
         self.use_graph = use_graph
         self._warm = warmup
+        self._pack_list = None  # learnt by the first eager step: [(weight, transpose, math, C0)]
+        self._pack_stream = None
         import os as _os
         # weight gradients run on a side stream and overlap the dgrad chain (measured 1.56 -> 1.38 ms/step); PU_WGRAD_SIDE=0 disables
         nside = int(_os.environ.get("PU_WGRAD_SIDE", "2"))  # number of side streams (round-robin); 0 = none
         self.wgrad_side = [torch.cuda.Stream() for _ in range(nside)] if nside > 0 else None
 
     # -------------------------------------------------------------------------------------------
+    def _prepack(self):
+        """Pack the weight images that do not fit in shared memory (the deep 64-channel layers) on a side stream at the
+        start of the step, for the forward and for the dgrad convs alike: off the critical path (10 launches, ~35 us)."""
+        if not self._pack_list:
+            ops.PACK_CACHE = None
+            return
+        if self._pack_stream is None:
+            self._pack_stream = torch.cuda.Stream()
+        main = torch.cuda.current_stream()
+        self._pack_stream.wait_stream(main)
+        cache = {}
+        with torch.cuda.stream(self._pack_stream):
+            for (w, transpose, math, C0) in self._pack_list:
+                wp = ops._pack_w_now(w, transpose, math, C0)
+                ev = torch.cuda.Event()
+                ev.record(self._pack_stream)
+                wp.record_stream(main)
+                cache[(w.data_ptr(), transpose, math, C0)] = (wp, ev)
+        ops.PACK_CACHE = cache
+
     def _step_body(self):
         st = torch.cuda.current_stream().cuda_stream
         for p in self.params:
             p.grad = None  # autograd then hands over its gradient tensors instead of launching one add per parameter
         self.flat_g.zero_()
+        if self._pack_list is None:
+            ops.PACK_LOG, ops.PACK_CACHE = [], None  # first eager step: learn which weights the step packs
+        else:
+            self._prepack()
+        try:
+            self._fwd_bwd(st)
+        finally:
+            if self._pack_list is None:
+                seen, self._pack_list = set(), []
+                for (w, transpose, math, C0) in ops.PACK_LOG:
+                    k = (w.data_ptr(), transpose, math, C0)
+                    if k not in seen:
+                        seen.add(k)
+                        self._pack_list.append((w, transpose, math, C0))
+            ops.PACK_LOG = ops.PACK_CACHE = None
+            if self._pack_stream is not None:
+                torch.cuda.current_stream().wait_stream(self._pack_stream)  # join (needed under graph capture)
+
+    def _fwd_bwd(self, st):
         out, hebb_new = self.net(self.x, self.hebb)
         gS = torch.empty_like(out)
         n = out.numel()
@@ -107,11 +152,12 @@ class TrainStep:
         _lib.call("pu_gather_flat", self.table_dev.data_ptr(), n, self.flat_g.data_ptr(), st)
         if self.dp_group is not None:
             dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.dp_group)
+        if getattr(self.net, "dp_side", None) is not None:
+            # join the deferred trace all-reduce + epilogue BEFORE the optimizer rewrites the arena (the epilogue reads eta)
+            torch.cuda.current_stream().wait_stream(self.net.dp_side)
         _lib.call("pu_adam_step", self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
                   self.step_count.data_ptr(), self.lr.data_ptr(), self.betas[0], self.betas[1], self.eps,
                   1.0 / self.world, self.n_flat, st)
-        if getattr(self.net, "dp_side", None) is not None:
-            torch.cuda.current_stream().wait_stream(self.net.dp_side)  # join the deferred trace all-reduce + epilogue
         self.hebb.copy_(hebb_new.detach())
 
     def _state_tensors(self):
@@ -128,7 +174,11 @@ class TrainStep:
             for t, s0 in zip(self._state_tensors(), saved):
                 t.copy_(s0)
 
-        s = torch.cuda.Stream()
+        # the step's main stream gets the HIGHEST priority: when weight-gradient kernels on the (default-priority) side
+        # streams share the GPU with the persistent one-CTA-per-SM conv kernels of the dgrad chain, the block scheduler
+        # then hands every SM that frees up to the critical path first
+        prio = int(_os_environ_get("PU_MAIN_PRIORITY", "-1"))
+        s = torch.cuda.Stream(priority=prio)
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             for i in range(self._warm):
@@ -147,7 +197,7 @@ class TrainStep:
             return self
         self.graph = torch.cuda.CUDAGraph()
         before = _lib.launch_count()
-        with torch.cuda.graph(self.graph):
+        with torch.cuda.graph(self.graph, stream=s):
             self._step_body()
         self.kernels_per_step = _lib.launch_count() - before
         restore()
@@ -203,7 +253,7 @@ class InferStep:
     """Batched forward-only step (eval.py:81-90 / infer.py:42-47 semantics: trace zero, hebb' discarded)."""
 
     def __init__(self, net, batch, in_hw, use_graph=True):
-        self.net = net.eval()
+        self.net = net  # run in eval mode inside capture()/step(); the caller's training flag is restored afterwards
         self.dev = next(net.parameters()).device
         self.x = torch.zeros((batch, net.n_channels, in_hw, in_hw), device=self.dev)
         self.hebb = net.initialZeroHebb()
@@ -212,8 +262,19 @@ class InferStep:
         self.use_graph = use_graph
         self.kernels_per_step = None
 
+    class _eval_mode:
+        def __init__(self, net):
+            self.net = net
+
+        def __enter__(self):
+            self.was = self.net.training
+            self.net.eval()
+
+        def __exit__(self, *exc):
+            self.net.train(self.was)
+
     def capture(self):
-        with torch.no_grad():
+        with torch.no_grad(), InferStep._eval_mode(self.net):
             s = torch.cuda.Stream()
             s.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(s):
@@ -237,6 +298,6 @@ class InferStep:
         if self.graph is not None:
             self.graph.replay()
         else:
-            with torch.no_grad():
+            with torch.no_grad(), InferStep._eval_mode(self.net):
                 self.out, _ = self.net(self.x, self.hebb)
         return self.out

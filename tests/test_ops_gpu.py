@@ -448,3 +448,27 @@ def test_bce_and_adam_tail():
                   0.9, 0.999, 1e-8, 1.0, 1000, torch.cuda.current_stream().cuda_stream)
     check(po, pr, 1e-5, "adam params")
     assert float(step) == 3.0
+
+
+@pytest.mark.parametrize("C,H,W,mask_in", [(8, 16, 16, False), (8, 128, 128, True), (16, 37, 21, False), (3, 9, 8, False)])
+def test_pool_skip_accumulates_both_gradients(C, H, W, mask_in):
+    """ops.pool_skip(x) -> (maxpool2(x), x): one backward call that sums the pooled-path and the skip-path gradients
+    inside the pooling kernel == autograd's separate accumulation (unet_p.py:59-66 dataflow)."""
+    from pu_b200 import ops
+    g = torch.Generator().manual_seed(C + H)
+    x = torch.randn(2, H, W, C, generator=g).to(DEV)
+    R1 = torch.randn(2, H // 2, W // 2, C, generator=g).to(DEV)
+    R2 = torch.randn(2, H, W, C, generator=g).to(DEV)
+    xa = x.clone().requires_grad_(True)
+    p, s = ops.pool_skip(xa, mask_in)
+    ((p * R1).sum() + (s * R2).sum()).backward()
+    xb = x.clone().requires_grad_(True)
+    pb = ops.maxpool2(xb, None, mask_in)
+    ((pb * R1).sum() + (xb * R2).sum()).backward()
+    assert torch.equal(p, pb) and torch.equal(s, x)
+    check(xa.grad, xb.grad, 1e-6, what="dx")
+    # only one of the two outputs used
+    xc = x.clone().requires_grad_(True)
+    p, s = ops.pool_skip(xc, mask_in)
+    (s * R2).sum().backward()
+    check(xc.grad, R2, 1e-7, what="skip only")
