@@ -19,6 +19,7 @@ Prints ONE JSON line on rank 0.  Extra objects on that line:
   kernels       the ten slowest layer kernels of the step (live CUDA-event timings, algorithmic bytes, HBM fraction)
   extras        short legs for BASELINE configs 3, 4, 5 (coord-conv, residual n8 @101 Hebb/Oja, 512^2 depth-5 train+infer)
   dp_check      (N > 1) replicas bit-identical after the timed run; N x B data-parallel step == one-process step on N*B
+  tc_demo       per-layer TFLOP/s of the tcgen05 conv on the wide configuration (UNetpRes neurons=64 @256x256) vs the TF32 peak
 """
 import argparse
 import contextlib
@@ -280,6 +281,53 @@ def kernel_table(batch, size, math, dev, hbm_peak, peak_src):
     return roof, top, rows
 
 
+# UNetpRes(neurons=64) @256x256: the wide configuration SURVEY.md §8d names for the tensor-core roofline ("TC demo", AI 326
+# FLOP/B): its 3x3 conv layers (unet_p_res.py:142-164,223-238,256-272), C_in (first | second source) -> C_out @ side
+TC_DEMO_LAYERS = [("conv1 res blocks", 64, 0, 64, 256), ("conv2.0", 64, 0, 128, 128), ("conv2 res blocks", 128, 0, 128, 128),
+                  ("conv3.0", 128, 0, 256, 64), ("conv3 res blocks", 256, 0, 256, 64), ("conv4.0", 256, 0, 512, 32),
+                  ("conv4 res blocks", 512, 0, 512, 32), ("mid.0", 512, 0, 1024, 16), ("mid res blocks", 1024, 0, 1024, 16),
+                  ("uconv4.0 (cat)", 512, 512, 512, 32), ("uconv3.0 (cat)", 256, 256, 256, 64), ("uconv2.0 (cat)", 128, 128, 128, 128),
+                  ("uconv1.0 (cat)", 64, 64, 64, 256)]
+
+
+def tc_demo(dev, bf16_tflops, batch=8):
+    """Per-layer TFLOP/s of the tcgen05 conv (forward and dgrad) on the wide configuration, against the TF32 dense peak taken
+    as half the measured bf16 cuBLAS throughput (MEASURED_PEAKS.json).  FLOPs = 2 * 9 * C_in * C_out * pixels."""
+    from pu_b200 import ops
+    peak = bf16_tflops / 2.0
+    rows = []
+    tot_f = tot_t = 0.0
+    for name, C0, C1, Cout, s in TC_DEMO_LAYERS:
+        x0 = torch.rand(batch, s, s, C0, device=dev)
+        x1 = torch.rand(batch, s, s, C1, device=dev) if C1 else None
+        dy = torch.randn(batch, s, s, Cout, device=dev)
+        w = torch.randn(Cout, C0 + C1, 3, 3, device=dev) * 0.05
+        b = torch.zeros(Cout, device=dev)
+        y = torch.rand(batch, s, s, Cout, device=dev)
+        flops = 2.0 * 9 * (C0 + C1) * Cout * batch * s * s
+
+        def fwd(i):
+            ops.conv3x3(x0, x1, w, b, None, True, s, s, 0, 0, 0, 0, ops.MATH_TF32)
+
+        def dgrad(i):
+            ops.conv3x3_bwd(dy, y, x0, x1, w, False, True, s, s, 0, 0, 0, 0, ops.MATH_TF32, True, False, None, None, True)
+
+        for kind, fn in (("fwd", fwd), ("dgrad", dgrad)):
+            us = _time_graph(fn, iters=5, reps=3)
+            tf = flops / (us * 1e-6) / 1e12
+            tot_f += flops
+            tot_t += us * 1e-6
+            rows.append({"layer": "%s %s %d%s->%d @%dx%d" % (name, kind, C0, "|%d" % C1 if C1 else "", Cout, s, s), "us": round(us, 1),
+                         "tflops": round(tf, 1), "frac_of_tf32_peak": round(tf / peak, 3),
+                         "flat": bool(ops._tc_flat(batch, s, s, C0 if kind == "fwd" else Cout, C1 if kind == "fwd" else 0,
+                                                   Cout if kind == "fwd" else C0 + C1))})
+        del x0, x1, dy, w, y
+    agg = tot_f / tot_t / 1e12
+    return {"config": "UNetpRes(neurons=64) 3x3 conv layers @256x256, batch %d, TF32 (tcgen05 kind::tf32), weights packed per call" % batch,
+            "tf32_peak_tflops": peak, "peak_source": "bf16_tflops / 2 of MEASURED_PEAKS.json", "aggregate_tflops": round(agg, 1),
+            "aggregate_frac": round(agg / peak, 3), "best_frac": max(r["frac_of_tf32_peak"] for r in rows), "layers": rows}
+
+
 # --------------------------------------------------------------------------------------------------
 def build_net(model, dev, rule, size, depth=4, base=8, neurons=16, dropout=0.5):
     from pu_b200 import UNetp, UNetpCoord, UNetpRes
@@ -455,7 +503,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    hbm_peak, _, peak_src = measured_peaks()
+    hbm_peak, bf16_peak, peak_src = measured_peaks()
     headline = (args.model == "unetp" and not args.infer and (args.depth, args.base) == (4, 8))
 
     torch.manual_seed(0)
@@ -570,9 +618,14 @@ def main():
         value = images / (ms_med * 1e-3)
         e2e_value = images / (e2e_ms_med * 1e-3)
         kps = ts.kernels_per_step or 0
-        roof = top = None
+        roof = top = demo = None
         if not args.no_extras:
             roof, top, _ = kernel_table(B, args.size, 1 if args.math == "tf32" else 0, dev, hbm_peak, peak_src)
+            if headline and args.math == "tf32":
+                try:
+                    demo = tc_demo(dev, bf16_peak)
+                except Exception as e:
+                    demo = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
         # whole-step figure against the layer-fused algorithmic bound of SURVEY.md §8d (28.39 MB / image @128)
         alg_mb_per_img = (9.49 if args.infer else 28.39) * (args.size / 128.0) ** 2  # UNetp figures; other models: indicative only
         step_gbs = alg_mb_per_img * 1e6 * B / (ms_med / args.steps * 1e-3) / 1e9
@@ -612,6 +665,7 @@ def main():
             "eager_launches_in_timed_region": eager_launches,
             "dp_check": check,
             "extras": extras,
+            "tc_demo": demo,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -53,6 +53,7 @@ typedef enum {
 /* conv3x3 math modes */
 #define PU_MATH_FP32 0 /* CUDA-core FFMA, strict fp32 (parity mode, any shape)        */
 #define PU_MATH_TF32 1 /* tcgen05 kind::tf32 implicit GEMM, fp32 accumulate in TMEM   */
+#define PU_MATH_TF32_FLAT 2 /* pu_pack_w3x3 only: the weight image of a PU_MATH_TF32 conv for which pu_conv3x3_tc_flat() is 1 */
 
 /* ---- library management --------------------------------------------------------------- */
 int pu_version(void);
@@ -82,6 +83,9 @@ int pu_pack_w3x3(const float* w_oihw, float* w_packed, int Cout, int Cin, int tr
 long long pu_pack_w3x3_floats(int Cout, int Cin, int transpose, int math, int C0);
 /* 1 if a conv with these source / destination channel counts can run on the tcgen05 path (PU_MATH_TF32) */
 int pu_conv3x3_tc_ok(int C0, int C1, int Cout, int Cd0, int Cd1);
+/* 1 if pu_conv3x3_fwd(PU_MATH_TF32) will run this problem in the "flat" mode (one MMA per tap, N = 64, 512-pixel tiles:
+ * the wide, tensor-bound layers); its packed weights must then be produced with math = PU_MATH_TF32_FLAT.             */
+int pu_conv3x3_tc_flat(int B, int H, int W, int C0, int C1, int Cout);
 /* 1 if, additionally, the tcgen05 kernel can build its weight tiles from the raw OIHW tensor (they fit in shared memory) */
 int pu_conv3x3_tc_resident(int C0, int C1, int Cout, int H, int W);
 /* Host-only (no device needed): the tile plan pu_conv3x3_fwd would use for this problem, for tests and tuning.

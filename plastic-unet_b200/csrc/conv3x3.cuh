@@ -38,7 +38,8 @@ int conv3x3_wgrad_ffma(const WgradArgs& a, cudaStream_t st, int math);
 int conv3x3_fwd_tc(const Conv3x3Args& a, cudaStream_t st);
 bool conv3x3_tc_ok(int C0, int C1, int Cout, int Cd0, int Cd1);
 bool conv3x3_tc_resident(int C0, int C1, int Cout, int H, int W);
-long long conv3x3_tc_weight_floats(int C0, int C1, int Cout);
-int conv3x3_tc_pack(const float* w_oihw, float* out, int Cout_w, int Cin_w, int transpose, int C0, cudaStream_t st);
+bool conv3x3_tc_flat(int B, int H, int W, int C0, int C1, int Cout);  // will pu_conv3x3_fwd use the flat (one MMA per tap) mode?
+long long conv3x3_tc_weight_floats(int C0, int C1, int Cout, bool flat);
+int conv3x3_tc_pack(const float* w_oihw, float* out, int Cout_w, int Cin_w, int transpose, int C0, bool flat, cudaStream_t st);
 
 }  // namespace pu

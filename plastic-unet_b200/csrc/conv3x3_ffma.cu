@@ -883,8 +883,9 @@ int conv3x3_wgrad_ffma(const WgradArgs& a0, cudaStream_t st, int math) {
 extern "C" {
 
 long long pu_pack_w3x3_floats(int Cout, int Cin, int transpose, int math, int C0) {
-  if (math == PU_MATH_TF32) {
-    const long long n = transpose ? pu::conv3x3_tc_weight_floats(Cout, 0, Cin) : pu::conv3x3_tc_weight_floats(C0, Cin - C0, Cout);
+  if (math == PU_MATH_TF32 || math == PU_MATH_TF32_FLAT) {
+    const bool flat = math == PU_MATH_TF32_FLAT;
+    const long long n = transpose ? pu::conv3x3_tc_weight_floats(Cout, 0, Cin, flat) : pu::conv3x3_tc_weight_floats(C0, Cin - C0, Cout, flat);
     if (n > 0) return n;
   }
   return 9LL * Cin * Cout;
@@ -892,8 +893,8 @@ long long pu_pack_w3x3_floats(int Cout, int Cin, int transpose, int math, int C0
 
 int pu_pack_w3x3(const float* w, float* out, int Cout, int Cin, int transpose, int math, int C0, void* stream) {
   PU_REQUIRE(w && out && Cout > 0 && Cin > 0, PU_ERR_BAD_ARG, "pu_pack_w3x3: bad argument");
-  PU_REQUIRE(math == PU_MATH_FP32 || math == PU_MATH_TF32, PU_ERR_BAD_ARG, "pu_pack_w3x3: unknown math mode %d", math);
-  if (math == PU_MATH_TF32) return pu::conv3x3_tc_pack(w, out, Cout, Cin, transpose, C0, pu::as_stream(stream));
+  PU_REQUIRE(math == PU_MATH_FP32 || math == PU_MATH_TF32 || math == PU_MATH_TF32_FLAT, PU_ERR_BAD_ARG, "pu_pack_w3x3: unknown math mode %d", math);
+  if (math != PU_MATH_FP32) return pu::conv3x3_tc_pack(w, out, Cout, Cin, transpose, C0, math == PU_MATH_TF32_FLAT, pu::as_stream(stream));
   const int n = Cout * Cin * 9;
   pu::pack_w3x3_kernel<<<pu::cdiv(n, 256) > 592 ? 592 : pu::cdiv(n, 256), 256, 0, pu::as_stream(stream)>>>(w, out, Cout, Cin, transpose);
   return pu::post_launch("pu_pack_w3x3");

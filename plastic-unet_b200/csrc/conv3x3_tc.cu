@@ -33,16 +33,20 @@
 // on transposed/flipped weights.
 #include <cuda.h>
 #include <stdlib.h>
+#include <atomic>
 #include <mutex>
 #include "conv3x3.cuh"
 
 namespace pu {
 
-constexpr int kMaxChunks = 40;
+constexpr int kMaxChunks = 64;  // K chunks per conv (16-channel chunks in flat mode: Cin <= 1024)
 constexpr int kCoBlk = 64;                     // output channels per CTA (grid.y splits larger Cout)
 constexpr unsigned kMaxResidentW = 40 * 1024;  // largest weight image kept resident in shared memory (per co block)
-constexpr int kBlkPix = 96;                    // output pixels per 128-row MMA block (16 groups x 6)
+constexpr int kBlkPix = 96;                    // output pixels per 128-row MMA block, kx folded into N (16 groups x 6)
+constexpr int kBlkPixFlat = 128;               // ... and with one MMA per tap (FOLD = false): 128 consecutive flattened halo pixels
 constexpr int kMaxStages = 4;
+constexpr int kTileQ = 4;                      // depth of the producer -> consumers tile-index queue (dynamic scheduler)
+constexpr int kMaxCoBlk = 16;                  // co blocks per launch slot of the tile counters
 
 struct TcRegion {
   int src, c_off, cb;  // cb (8/16/32) channels of source src starting at channel c_off; shared-memory row = cb*4 bytes
@@ -70,6 +74,8 @@ struct TcArgs {
                     // and the B tiles are built in shared memory once per CTA (resident)
   int Cin, C0;      // concatenated input channels and the split point (for the in-kernel weight build)
   int w_res_bytes;  // bytes of the resident weight image (0 in streamed mode)
+  unsigned int* tile_ctr;  // dynamic tile scheduler: [co block] next-tile counters of this launch's slot (zero between launches)
+  unsigned int* done_ctr;  // CTAs of this launch that have finished (the last one re-zeroes the slot)
   int debug;        // PU_TC_DEBUG experiments: 1 = skip MMAs, 2 = skip epilogue stores, 4 = load only the first stages
   unsigned w_coblk_stride;  // bytes
   TcChunk chunks[kMaxChunks];
@@ -79,6 +85,7 @@ __host__ __device__ constexpr int tc_n3(int cols) { return (3 * cols + 15) / 16 
 
 // ---- PTX wrappers -------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ int lane_id() { return (int)(threadIdx.x & 31); }
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
@@ -212,19 +219,28 @@ __device__ __forceinline__ void build_w_tile(const TcChunk& ch, float4* out, con
   }
 }
 
-template <int COLS>
+// FOLD = true: the three kx taps are folded into N (N = 3*COLS, one MMA per ky and K step, 96 output pixels per 128-row
+// block, realignment in the epilogue) — the right shape for the narrow, HBM-bound layers where the fixed cost per MMA
+// dominates.  FOLD = false ("flat"): one MMA per tap (N = COLS, nine per K step) on 128 CONSECUTIVE flattened halo pixels:
+// every row is an output pixel, the accumulators need COLS instead of 3*COLS TMEM columns per block, so a tile holds 3x the
+// pixels per weight byte streamed — the shape for the wide (>= 64 channel), tensor-bound layers (SURVEY.md §8d "TC demo").
+template <int COLS, bool FOLD>
 __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm0,
                                                                    const __grid_constant__ CUtensorMap tm1, const TcArgs a) {
   constexpr int N3 = tc_n3(COLS);
+  constexpr int NACC = FOLD ? N3 : COLS;          // TMEM columns of one MMA block's accumulators
+  constexpr int BLK = FOLD ? kBlkPix : kBlkPixFlat;  // output pixels per MMA block
+  static_assert(FOLD || COLS % 16 == 0, "an M = 128 MMA needs N % 16 == 0");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // swizzle patterns repeat every 1024 B
   const int nst = a.nstages;
   const int stage_bytes = a.a_bytes + a.w_bytes_max;  // w_bytes_max == 0 when the weights are resident
   uint8_t* smWres = smem + nst * stage_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smWres + a.w_res_bytes);
-  // bars: [0,kMaxStages) full, [kMaxStages,2kMaxStages) empty, then tmem_full[2], tmem_empty[2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
-  int* wtab = reinterpret_cast<int*>(tmem_slot + 2);  // resident-weight build: (offset, ky stride) per 4-channel group, <= 1 KB
+  // bars: [0,kMaxStages) full, [kMaxStages,2kMaxStages) empty, then tmem_full[2], tmem_empty[2], tile queue full[kTileQ], empty[kTileQ]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4 + 2 * kTileQ);
+  volatile int* tileq = reinterpret_cast<volatile int*>(tmem_slot + 2);  // [kTileQ] tile indices handed from the producer to the other roles
+  int* wtab = reinterpret_cast<int*>(tmem_slot + 2 + kTileQ);  // resident-weight build: (offset, ky stride) per 4-channel group, <= 1 KB
   // PU_TC_DEBUG & 64: per-tile timeline of CTA 0 (cycles since kernel start): [event][tile < 12]
   long long* trace = reinterpret_cast<long long*>(reinterpret_cast<uint8_t*>(tmem_slot) + 1024);  // 10 events x 12 tiles
   const bool tracing = (a.debug & 64) && blockIdx.x == 0 && blockIdx.y == 0;
@@ -237,6 +253,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const __grid_
   auto empty_bar = [&](int st) { return bar0 + 8u * (kMaxStages + st); };
   auto tfull_bar = [&](int as) { return bar0 + 8u * (2 * kMaxStages + as); };
   auto tempty_bar = [&](int as) { return bar0 + 8u * (2 * kMaxStages + 2 + as); };
+  auto tqfull_bar = [&](int q) { return bar0 + 8u * (2 * kMaxStages + 4 + q); };
+  auto tqempty_bar = [&](int q) { return bar0 + 8u * (2 * kMaxStages + 4 + kTileQ + q); };
+  // Dynamic tile scheduler.  The weight-gradient kernels of the backward pass run concurrently on side streams, so a
+  // persistent CTA may get its SM late (or share the memory system unevenly); with a static round-robin assignment the
+  // kernel then lasts as long as its unluckiest CTA.  Instead the producer warp draws tiles from a global counter (the first
+  // tile is blockIdx.x, later ones gridDim.x + atomicAdd) and hands each index to the MMA and epilogue warps through a
+  // small shared-memory queue guarded by mbarriers; -1 ends the kernel.  Consumers: kMmaWarps + kEpiWarps warps.
+  auto next_tile = [&](int k) -> int {  // consumer side: k-th tile of this CTA (every consumer warp calls it for every k in order)
+    const int q = k % kTileQ;
+    mbar_wait(tqfull_bar(q), (uint32_t)(k / kTileQ) & 1);
+    const int t = tileq[q];
+    __syncwarp();
+    if (lane_id() == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tqempty_bar(q)) : "memory");
+    return t;
+  };
 
   pdl_prologue();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -244,7 +275,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const __grid_
   const int co_base = coblk * kCoBlk;
   const int tiles_per_img = a.tilesX * a.tilesY;
   const int ntiles = tiles_per_img * a.B;
-  const int acc_cols = a.nmb * N3;  // TMEM columns of one accumulator buffer
+  const int acc_cols = a.nmb * NACC;  // TMEM columns of one accumulator buffer
 
   if (warp == 0) {
     if (lane == 0) {
@@ -255,6 +286,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const __grid_
       for (int i = 0; i < 2; ++i) {
         mbar_init(tfull_bar(i), kMmaWarps);
         mbar_init(tempty_bar(i), kEpiWarps);  // one arrival per epilogue warp
+      }
+      for (int i = 0; i < kTileQ; ++i) {
+        mbar_init(tqfull_bar(i), 1);
+        mbar_init(tqempty_bar(i), kMmaWarps + kEpiWarps);  // one arrival per consumer warp
       }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm0)) : "memory");
@@ -362,8 +397,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const __grid_
     // ================= TMA producer =================
     const uint8_t* wblk = reinterpret_cast<const uint8_t*>(a.wpk) + (size_t)coblk * a.w_coblk_stride;
     for (int k = 0;; ++k) {
-      const int tile = blockIdx.x + k * gridDim.x;
-      if (tile >= ntiles) break;
+      // draw the next tile and publish it to the consumer warps
+      int tile = blockIdx.x;
+      if (k > 0) {
+        if (lane == 0) tile = (int)gridDim.x + (int)atomicAdd(a.tile_ctr + coblk, 1u);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
+      }
+      if (tile >= ntiles) tile = -1;
+      {
+        const int q = k % kTileQ;
+        mbar_wait(tqempty_bar(q), ((uint32_t)(k / kTileQ) & 1) ^ 1);  // passes immediately on a fresh barrier
+        if (lane == 0) {
+          tileq[q] = tile;
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tqfull_bar(q)) : "memory");
+        }
+        __syncwarp();
+      }
+      if (tile < 0) break;
       const int b = tile / tiles_per_img;
       const int tr = tile - b * tiles_per_img;
       const int ty = tr / a.tilesX, tx = tr - ty * a.tilesX;
@@ -398,12 +448,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const __grid_
     // so the descriptors live in uniform registers.
     const int mw = warp - 1;
     // instruction descriptor: D=f32, A=B=tf32, K-major both, N = N3, M = 128 (cute::UMMA::InstrDescriptor)
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N3 >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((FOLD ? N3 : COLS) >> 3) << 17) | ((128u >> 4) << 24);
     const bool leader = elect_one();  // elected once: the issue loop must stay a handful of instructions per MMA
     int it = 0;
     for (int k = 0;; ++k) {
-      const int tile = blockIdx.x + k * gridDim.x;
-      if (tile >= ntiles) break;
+      if (next_tile(k) < 0) break;
       const int as = k & 1;
       const uint32_t aph = (k >> 1) & 1;
       mbar_wait(tempty_bar(as), aph ^ 1);  // the epilogue has drained this accumulator buffer
@@ -423,20 +472,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const __grid_
           for (int r = 0; r < ch.nreg; ++r) {
             const uint32_t rb = (uint32_t)ch.reg[r].cb * 4;  // row bytes = swizzle span
             const uint32_t layout = rb == 32 ? 6u : (rb == 64 ? 4u : 2u);
-            const uint64_t a_base = umma_desc(sS + ch.reg[r].off + (uint32_t)(ky * a.PW) * rb, 16, 6 * rb, layout);
-            const uint32_t mb_step = 6 * rb;  // kBlkPix rows, in 16-byte descriptor units
+            // 8-row core groups: 6 rows apart when folded (rows 6,7 duplicate the next group's 0,1), canonical 8 when flat
+            const uint64_t a_base = umma_desc(sS + ch.reg[r].off + (uint32_t)(ky * a.PW) * rb, 16, (FOLD ? 6 : 8) * rb, layout);
+            const uint32_t mb_step = (FOLD ? 6 : 8) * rb;  // BLK rows, in 16-byte descriptor units
             const int ksteps = ch.reg[r].cb >> 3;
             for (int ks = 0; ks < ksteps; ++ks, kc += 2) {
-              const uint64_t bd = b_base + (uint64_t)((ky * (ch.ncg >> 1) + (kc >> 1)) * N3 * 2);
-              uint64_t ad = a_base + (uint64_t)(2 * ks + mw * mb_step);
-              uint32_t d = d0 + mw * N3;
-              const uint32_t acc = (c | ky | (int)kc) ? 1u : 0u;
-              // blocks innermost: consecutive MMAs write different accumulators
+#pragma unroll
+              for (int kx = 0; kx < (FOLD ? 1 : 3); ++kx) {
+                // flat: tap (ky, kx) = N rows [kx*COLS, (kx+1)*COLS) of the same B tile, A start moved by kx pixel rows
+                const uint64_t bd = b_base + (uint64_t)((ky * (ch.ncg >> 1) + (kc >> 1)) * N3 * 2 + kx * COLS * 2);
+                uint64_t ad = a_base + (uint64_t)(2 * ks + mw * mb_step + kx * (rb >> 4));
+                uint32_t d = d0 + mw * NACC;
+                const uint32_t acc = (c | ky | (int)kc | kx) ? 1u : 0u;
+                // blocks innermost: consecutive MMAs write different accumulators
 #pragma unroll 3
-              for (int mb = mw; mb < a.nmb; mb += kMmaWarps) {
-                if (leader && !(a.debug & 1)) umma_tf32(d, ad, bd, idesc, acc);
-                d += kMmaWarps * N3;
-                ad += kMmaWarps * mb_step;
+                for (int mb = mw; mb < a.nmb; mb += kMmaWarps) {
+                  if (leader && !(a.debug & 1)) umma_tf32(d, ad, bd, idesc, acc);
+                  d += kMmaWarps * NACC;
+                  ad += kMmaWarps * mb_step;
+                }
               }
             }
           }
@@ -460,18 +514,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const __grid_
     const int quarter = warp & 3;
     const int set = (warp - kEpiWarp0) >> 2;
     const int R = quarter * 32 + lane;
-    const int gi = R & 7;                     // row inside its 8-row group; rows 6,7 duplicate the next group's 0,1
-    const int prow = (R >> 3) * 6 + gi;       // pixel offset of this row inside an MMA block
-    const int p0 = set * kBlkPix + prow;
+    const int gi = R & 7;                     // row inside its 8-row group; folded: rows 6,7 duplicate the next group's 0,1
+    const int prow = FOLD ? (R >> 3) * 6 + gi : R;  // pixel offset of this row inside an MMA block
+    const int p0 = set * BLK + prow;
     const int yy0 = p0 / a.PW, xx0 = p0 - yy0 * a.PW;
-    const int step_y = (kEpiSets * kBlkPix) / a.PW, step_x = kEpiSets * kBlkPix - step_y * a.PW;  // to this warp's next block
+    const int step_y = (kEpiSets * BLK) / a.PW, step_x = kEpiSets * BLK - step_y * a.PW;  // to this warp's next block
     const bool has_mask = a.mask0 != nullptr || a.mask1 != nullptr;
     const bool has_res = a.res != nullptr && !has_mask;
     const bool has_bias = a.bias != nullptr;
     const bool bias32 = (reinterpret_cast<uintptr_t>(a.bias) & 31) == 0;  // parameters may sit in a packed arena
     const int relu = a.relu, round_out = a.round_out;
     const int nq_valid = (a.Cout - co_base + 7) / 8 < NQ ? (a.Cout - co_base + 7) / 8 : NQ;  // 8-channel groups of this co block
-    const bool live = gi < 6 && !(a.debug & 2);
+    const bool live = (!FOLD || gi < 6) && !(a.debug & 2);
     auto load_bias = [&](int co, float* bb) {
       if (bias32) {
         ldg8(a.bias + co, bb);
@@ -490,11 +544,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const __grid_
     auto finish = [&](const uint32_t* v, bool ok, float* dst, bool has_aux, const float* aux, const float* bb, uint32_t mbits,
                       unsigned char* mdst) {
       float o[8];
+      if (FOLD) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float e1 = __shfl_down_sync(0xffffffffu, __uint_as_float(v[8 + j]), 1);
-        const float e2 = __shfl_down_sync(0xffffffffu, __uint_as_float(v[16 + j]), 2);
-        o[j] = (__uint_as_float(v[j]) + e1) + e2;
+        for (int j = 0; j < 8; ++j) {
+          const float e1 = __shfl_down_sync(0xffffffffu, __uint_as_float(v[8 + j]), 1);
+          const float e2 = __shfl_down_sync(0xffffffffu, __uint_as_float(v[16 + j]), 2);
+          o[j] = (__uint_as_float(v[j]) + e1) + e2;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = __uint_as_float(v[j]);
       }
       if (!ok) return;
       if (has_bias) {
@@ -527,10 +586,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const __grid_
     };
     // this warp's MMA blocks of a tile are mb = set + i * kEpiSets, i < kMaxI (compile-time bound so that the packed-mask
     // bytes prefetched before the accumulators are ready stay in registers)
-    constexpr int kMaxI = (256 / N3 + kEpiSets - 1) / kEpiSets;
+    constexpr int kMaxI = (256 / NACC + kEpiSets - 1) / kEpiSets;
 
     uint32_t tcount = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+    for (;; ++tcount) {
+      const int tile = next_tile((int)tcount);
+      if (tile < 0) break;
       const int b = tile / tiles_per_img;
       const int tr = tile - b * tiles_per_img;
       const int ty = tr / a.tilesX, tx = tr - ty * a.tilesX;
@@ -598,15 +659,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const __grid_
           const bool okB = haveB && live && yy < ymax && xx < xmax;
           const int pixB = yy * a.d0.Ws + xx, xoB = yy * xs_y + xx * xs_x;
           advance();
-          const uint32_t tA = tbase + (uint32_t)(mb * N3);
+          const uint32_t tA = tbase + (uint32_t)(mb * NACC);
           tmem_ld8(tA, v[0]);
-          tmem_ld8(tA + COLS, v[0] + 8);
-          tmem_ld8(tA + 2 * COLS, v[0] + 16);
+          if (FOLD) {
+            tmem_ld8(tA + COLS, v[0] + 8);
+            tmem_ld8(tA + 2 * COLS, v[0] + 16);
+          }
           if (haveB) {
-            const uint32_t tB = tA + (uint32_t)(kEpiSets * N3);
+            const uint32_t tB = tA + (uint32_t)(kEpiSets * NACC);
             tmem_ld8(tB, v[1]);
-            tmem_ld8(tB + COLS, v[1] + 8);
-            tmem_ld8(tB + 2 * COLS, v[1] + 16);
+            if (FOLD) {
+              tmem_ld8(tB + COLS, v[1] + 8);
+              tmem_ld8(tB + 2 * COLS, v[1] + 16);
+            }
           }
           if (has_aux) {
             if (okA) ldg8(xb + xoA, aux[0]);
@@ -633,13 +698,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const __grid_
           for (int q = 0; q < NQ; q += 2) {
             uint32_t v[2][24];
             float aux[2][8], bb[2][8];
-            const uint32_t tA = tbase + (uint32_t)(mb * N3 + 8 * q);
+            const uint32_t tA = tbase + (uint32_t)(mb * NACC + 8 * q);
             tmem_ld8(tA, v[0]);
-            tmem_ld8(tA + COLS, v[0] + 8);
-            tmem_ld8(tA + 2 * COLS, v[0] + 16);
             tmem_ld8(tA + 8, v[1]);
-            tmem_ld8(tA + 8 + COLS, v[1] + 8);
-            tmem_ld8(tA + 8 + 2 * COLS, v[1] + 16);
+            if (FOLD) {
+              tmem_ld8(tA + COLS, v[0] + 8);
+              tmem_ld8(tA + 2 * COLS, v[0] + 16);
+              tmem_ld8(tA + 8 + COLS, v[1] + 8);
+              tmem_ld8(tA + 8 + 2 * COLS, v[1] + 16);
+            }
             float* dst[2];
             bool okq[2];
             unsigned char* mdst[2];
@@ -678,6 +745,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const __grid_
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)a.tmem_cols) : "memory");
   }
+  if (tid == 0) {
+    // this CTA draws no more tiles (its producer, this very thread, is done): the last CTA to get here re-zeroes the slot
+    __threadfence();
+    const unsigned total = gridDim.x * gridDim.y;
+    if (atomicAdd(a.done_ctr, 1u) == total - 1) {
+      for (unsigned i = 0; i < gridDim.y; ++i) a.tile_ctr[i] = 0u;
+      __threadfence();
+      *a.done_ctr = 0u;
+    }
+  }
 }
 
 // ---- weight packing for the streamed-weights mode ---------------------------------------------------
@@ -705,6 +782,12 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 static EncodeTiledFn g_encode = nullptr;
+// tile-scheduler counters: kTcSlots launch slots x (kMaxCoBlk tile counters + 1 done counter), used round-robin by
+// successive launches (a captured graph keeps the slot of each of its kernel nodes; a slot is re-zeroed by its own kernel)
+constexpr int kTcSlots = 256;
+__device__ unsigned int g_tc_counters[kTcSlots * (kMaxCoBlk + 1)];
+static unsigned int* g_tc_counters_dev = nullptr;
+static std::atomic<unsigned> g_tc_slot{0};
 static int g_tc_state = -1;  // -1 unknown, 0 unavailable, 1 available
 static std::mutex g_tc_mu;
 
@@ -727,12 +810,19 @@ static bool tc_init() {
     return false;
   }
   g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  void* ctr = nullptr;
+  if (cudaGetSymbolAddress(&ctr, g_tc_counters) != cudaSuccess || cudaMemset(ctr, 0, sizeof(unsigned int) * kTcSlots * (kMaxCoBlk + 1)) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  g_tc_counters_dev = reinterpret_cast<unsigned int*>(ctr);
   g_tc_state = 1;
   return true;
 }
 
 struct TcPlan {
   int TH, TW, PW, tilesX, tilesY, nmb, cols, n3, a_bytes, w_bytes_max, w_res_bytes, tmem_cols, nchunks, ncoblk, nstages, cb0, cb1;
+  int fold;  // 1: kx folded into N (96-pixel blocks); 0: flat, one MMA per tap (128-pixel blocks), wide layers
   unsigned w_coblk_stride;
   size_t smem_bytes;
   TcChunk chunks[kMaxChunks];
@@ -746,15 +836,26 @@ static int next_pow2_cols(int c) {
 
 static int region_channels(int C) { return C % 32 == 0 ? 32 : (C % 16 == 0 ? 16 : 8); }
 
+// Flat mode (one MMA per tap, N = 64) for the wide layers: >= 64 input and output channels (multiples of 64 outputs) and
+// enough pixels for at least two full waves of 512-pixel tiles.  PU_TC_FLAT=0/1 forces it off/on where the shape allows.
+static bool tc_want_flat(long long npix, int C0, int C1, int Cout) {
+  const bool can = Cout % 64 == 0 && C0 % 16 == 0 && C1 % 16 == 0 && C0 + C1 >= 32;
+  if (!can) return false;
+  if (const char* e = getenv("PU_TC_FLAT")) return atoi(e) != 0;
+  return C0 + C1 >= 64 && npix >= 2LL * kNumSMs * 512;
+}
+
 // channel plan: K chunks, weight image layout.  false if the channel counts do not fit the tensor-core path.
-static bool tc_plan_channels(int C0, int C1, int Cout, TcPlan* p) {
+static bool tc_plan_channels(int C0, int C1, int Cout, TcPlan* p, bool flat = false) {
   if (C0 < 8 || C0 % 8 != 0 || C1 < 0 || C1 % 8 != 0 || Cout < 8 || Cout % 8 != 0) return false;
   const int cout_blk = Cout < kCoBlk ? Cout : kCoBlk;
   p->cols = cout_blk <= 8 ? 8 : (cout_blk <= 16 ? 16 : (cout_blk <= 32 ? 32 : 64));
   p->n3 = tc_n3(p->cols);
   p->ncoblk = (Cout + kCoBlk - 1) / kCoBlk;
-  p->cb0 = region_channels(C0);
-  p->cb1 = C1 > 0 ? region_channels(C1) : 0;
+  p->fold = flat ? 0 : 1;
+  // flat: 16-channel K chunks keep a 512-pixel stage (45 KB of pixels + 37 KB of weights) small enough for two stages
+  p->cb0 = flat ? 16 : region_channels(C0);
+  p->cb1 = C1 > 0 ? (flat ? 16 : region_channels(C1)) : 0;
   p->nchunks = 0;
   unsigned woff = 0;
   auto add = [&](int nreg, TcRegion r0, TcRegion r1) {
@@ -778,8 +879,19 @@ static bool tc_plan_channels(int C0, int C1, int Cout, TcPlan* p) {
 }
 
 // tile geometry, pipeline depth and shared-memory layout for one problem size
-static bool tc_plan(int B, int H, int W, int C0, int C1, int Cout, TcPlan* p, bool resident = false) {
-  if (!tc_plan_channels(C0, C1, Cout, p)) return false;
+static bool tc_plan1(int B, int H, int W, int C0, int C1, int Cout, TcPlan* p, bool resident, bool want_flat);
+
+// flat < 0: flat mode where tc_want_flat says so and the plan fits, else folded
+static bool tc_plan(int B, int H, int W, int C0, int C1, int Cout, TcPlan* p, bool resident = false, int flat = -1) {
+  const bool want_flat = flat < 0 ? tc_want_flat((long long)B * H * W, C0, C1, Cout) : (flat != 0);
+  if (want_flat && !resident && tc_plan1(B, H, W, C0, C1, Cout, p, false, true)) return true;
+  return tc_plan1(B, H, W, C0, C1, Cout, p, resident, false);
+}
+
+static bool tc_plan1(int B, int H, int W, int C0, int C1, int Cout, TcPlan* p, bool resident, bool want_flat) {
+  if (!tc_plan_channels(C0, C1, Cout, p, want_flat)) return false;
+  const int blk = p->fold ? kBlkPix : kBlkPixFlat;
+  const int tail = p->fold ? 98 : 130;  // rows the last block's shifted reads touch beyond its first row: 127 + kx 2 + 1 (flat)
   int max_ncg = 0;
   for (int i = 0; i < p->nchunks; ++i) max_ncg = p->chunks[i].ncg > max_ncg ? p->chunks[i].ncg : max_ncg;
   p->w_bytes_max = ((3 * max_ncg * p->n3 * 16) + 1023) / 1024 * 1024;
@@ -790,11 +902,11 @@ static bool tc_plan(int B, int H, int W, int C0, int C1, int Cout, TcPlan* p, bo
     p->w_bytes_max = 0;
   }
   const size_t budget = 220 * 1024 - (size_t)p->w_res_bytes;  // minus barriers and the 1024-byte alignment slack below
-  const int nmb_max = 256 / p->n3;  // two accumulator buffers of <= 256 TMEM columns
+  const int nmb_max = 256 / (p->fold ? p->n3 : p->cols);  // two accumulator buffers of <= 256 TMEM columns
   auto stage_a_bytes = [&](int th, int pw, int nmb) {
     // rows a region must hold: the halo tile, and whatever the last MMA block's shifted reads touch beyond it
     int rows = (th + 2) * pw;
-    const int reach = (nmb - 1) * kBlkPix + 98 + 2 * pw;
+    const int reach = (nmb - 1) * blk + tail + 2 * pw;
     if (reach > rows) rows = reach;
     size_t worst = 0;
     for (int i = 0; i < p->nchunks; ++i) {
@@ -816,7 +928,7 @@ static bool tc_plan(int B, int H, int W, int C0, int C1, int Cout, TcPlan* p, bo
     if (tilesX > tx_min && tw < 16) break;
     const int pw = tw + 2;
     for (int th = (H < 254 ? H : 254); th >= 1; --th) {
-      const int nmb = (th * pw + kBlkPix - 1) / kBlkPix;
+      const int nmb = (th * pw + blk - 1) / blk;
       if (nmb > nmb_max) continue;
       const size_t stage = stage_a_bytes(th, pw, nmb) + p->w_bytes_max;
       if (2 * stage > budget) continue;
@@ -839,9 +951,9 @@ static bool tc_plan(int B, int H, int W, int C0, int C1, int Cout, TcPlan* p, bo
   p->PW = p->TW + 2;
   p->TH = best_th;
   p->tilesY = (H + best_th - 1) / best_th;
-  p->nmb = (p->TH * p->PW + kBlkPix - 1) / kBlkPix;
+  p->nmb = (p->TH * p->PW + blk - 1) / blk;
   int rows = (p->TH + 2) * p->PW;
-  const int reach = (p->nmb - 1) * kBlkPix + 98 + 2 * p->PW;
+  const int reach = (p->nmb - 1) * blk + tail + 2 * p->PW;
   if (reach > rows) rows = reach;
   for (int i = 0; i < p->nchunks; ++i) {
     TcChunk& ch = p->chunks[i];
@@ -857,7 +969,7 @@ static bool tc_plan(int B, int H, int W, int C0, int C1, int Cout, TcPlan* p, bo
   const size_t stage = (size_t)p->a_bytes + p->w_bytes_max;
   p->nstages = (int)(budget / stage);
   if (p->nstages > kMaxStages) p->nstages = kMaxStages;
-  p->tmem_cols = next_pow2_cols(2 * p->nmb * p->n3);
+  p->tmem_cols = next_pow2_cols(2 * p->nmb * (p->fold ? p->n3 : p->cols));
   p->smem_bytes = (size_t)p->nstages * stage + p->w_res_bytes + 256 + 2048 + 1024;  // barriers, k-group table + trace, alignment
   return p->nstages >= 2 && p->tmem_cols <= 512;
 }
@@ -893,19 +1005,24 @@ bool conv3x3_tc_resident(int C0, int C1, int Cout, int H, int W) {
   return tc_init() && tc_plan(1, H, W, C0, C1, Cout, &p, true);
 }
 
-long long conv3x3_tc_weight_floats(int C0, int C1, int Cout) {
+bool conv3x3_tc_flat(int B, int H, int W, int C0, int C1, int Cout) {
   TcPlan p;
-  if (!tc_plan_channels(C0, C1, Cout, &p)) return 0;
+  return tc_init() && tc_plan(B, H, W, C0, C1, Cout, &p, false) && !p.fold;
+}
+
+long long conv3x3_tc_weight_floats(int C0, int C1, int Cout, bool flat) {
+  TcPlan p;
+  if (!tc_plan_channels(C0, C1, Cout, &p, flat)) return 0;
   return (long long)p.w_coblk_stride * p.ncoblk / 4;
 }
 
-int conv3x3_tc_pack(const float* w_oihw, float* out, int Cout_w, int Cin_w, int transpose, int C0, cudaStream_t st) {
+int conv3x3_tc_pack(const float* w_oihw, float* out, int Cout_w, int Cin_w, int transpose, int C0, bool flat, cudaStream_t st) {
   // roles of the conv that will consume the packed weights
   const int cin = transpose ? Cout_w : Cin_w;
   const int cout = transpose ? Cin_w : Cout_w;
   const int c0 = transpose ? Cout_w : C0;
   TcPlan p;
-  if (!tc_plan_channels(c0, cin - c0, cout, &p)) {
+  if (!tc_plan_channels(c0, cin - c0, cout, &p, flat)) {
     set_error("pu_pack_w3x3: channels (%d|%d -> %d) do not fit the tcgen05 path", c0, cin - c0, cout);
     return PU_ERR_UNSUPPORTED;
   }
@@ -924,18 +1041,18 @@ int conv3x3_tc_pack(const float* w_oihw, float* out, int Cout_w, int Cin_w, int 
   return post_launch("pu_pack_w3x3 (tc)");
 }
 
-template <int COLS>
+template <int COLS, bool FOLD = true>
 static int launch_tc(const CUtensorMap& tm0, const CUtensorMap& tm1, const TcArgs& ta, dim3 grid, size_t smem, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel<COLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel<COLS, FOLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) {
       set_error("conv3x3_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return PU_ERR_CUDA;
     }
     attr_set = true;
   }
-  cudaError_t le = launch_pdl(conv3x3_tc_kernel<COLS>, grid, dim3(kTcThreads), smem, st, tm0, tm1, ta);
+  cudaError_t le = launch_pdl(conv3x3_tc_kernel<COLS, FOLD>, grid, dim3(kTcThreads), smem, st, tm0, tm1, ta);
   if (le != cudaSuccess) {
     set_error("conv3x3_tc launch: %s", cudaGetErrorString(le));
     return PU_ERR_CUDA;
@@ -972,6 +1089,15 @@ int conv3x3_fwd_tc(const Conv3x3Args& a, cudaStream_t st) {
   ta.nmb = p.nmb; ta.a_bytes = p.a_bytes; ta.w_bytes_max = p.w_bytes_max; ta.nstages = p.nstages;
   ta.tmem_cols = p.tmem_cols; ta.nchunks = p.nchunks; ta.w_coblk_stride = p.w_coblk_stride;
   ta.wfmt = a.wfmt; ta.Cin = a.Cin; ta.C0 = a.s0.C; ta.w_res_bytes = p.w_res_bytes;
+  if (p.ncoblk > kMaxCoBlk) {
+    set_error("pu_conv3x3_fwd: more than %d output-channel blocks (Cout %d)", kMaxCoBlk, a.Cout);
+    return PU_ERR_UNSUPPORTED;
+  }
+  {
+    const unsigned slot = g_tc_slot.fetch_add(1) % kTcSlots;
+    ta.tile_ctr = g_tc_counters_dev + (size_t)slot * (kMaxCoBlk + 1);
+    ta.done_ctr = ta.tile_ctr + kMaxCoBlk;
+  }
   {
     const char* dbg = getenv("PU_TC_DEBUG");
     ta.debug = dbg ? atoi(dbg) : 0;
@@ -983,6 +1109,7 @@ int conv3x3_fwd_tc(const Conv3x3Args& a, cudaStream_t st) {
   for (int i = 0; i < p.nchunks; ++i) ta.chunks[i] = p.chunks[i];
   const int ntiles = p.tilesX * p.tilesY * a.B;
   dim3 grid(ntiles < kNumSMs ? ntiles : kNumSMs, p.ncoblk);
+  if (!p.fold) return launch_tc<64, false>(tm0, tm1, ta, grid, p.smem_bytes, st);
   switch (p.cols) {
     case 8: return launch_tc<8>(tm0, tm1, ta, grid, p.smem_bytes, st);
     case 16: return launch_tc<16>(tm0, tm1, ta, grid, p.smem_bytes, st);
@@ -994,6 +1121,8 @@ int conv3x3_fwd_tc(const Conv3x3Args& a, cudaStream_t st) {
 }  // namespace pu
 
 extern "C" int pu_tc_available(void) { return pu::tc_init() ? 1 : 0; }
+
+extern "C" int pu_conv3x3_tc_flat(int B, int H, int W, int C0, int C1, int Cout) { return pu::conv3x3_tc_flat(B, H, W, C0, C1, Cout) ? 1 : 0; }
 
 // Host-only: the tile plan pu_conv3x3_fwd would use (no device needed; for tests and tuning).
 extern "C" int pu_conv3x3_tc_plan(int B, int H, int W, int C0, int C1, int Cout, int resident, int* out16) {

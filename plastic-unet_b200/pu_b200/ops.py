@@ -65,10 +65,23 @@ def _side_stream():
 
 
 
-def _weight_operand(weight: Tensor, transpose: int, math: int, C0: int, C1: int, Cout_conv: int, H: int, W: int):
+MATH_TF32_FLAT = 2  # pu_pack_w3x3 only
+
+
+@functools.lru_cache(maxsize=None)
+def _tc_flat(B: int, H: int, W: int, C0: int, C1: int, Cout: int) -> bool:
+    """Will the tcgen05 conv run this problem in its flat mode (wide layers)?  Its packed weights differ then."""
+    return bool(_lib.load().pu_conv3x3_tc_flat(B, H, W, C0, C1, Cout))
+
+
+def _weight_operand(weight: Tensor, transpose: int, math: int, C0: int, C1: int, Cout_conv: int, H: int, W: int, B: int = 1):
     """-> (tensor, wfmt): the raw OIHW weight whenever the kernel can build its operand tiles itself (every FFMA
     conv, and tcgen05 convs whose weight image fits in shared memory), else the pu_pack_w3x3 buffer."""
-    if math == MATH_FP32 or _tc_resident(C0, C1, Cout_conv, H, W):
+    if math == MATH_FP32:
+        return weight, (W_OIHW_DGRAD if transpose else W_OIHW)
+    if _tc_flat(B, H, W, C0, C1, Cout_conv):
+        return _pack_w(weight, transpose, MATH_TF32_FLAT, C0), W_PACKED
+    if _tc_resident(C0, C1, Cout_conv, H, W):
         return weight, (W_OIHW_DGRAD if transpose else W_OIHW)
     return _pack_w(weight, transpose, math, C0), W_PACKED
 
@@ -173,7 +186,7 @@ def conv3x3_m(x0: Tensor, x1: Optional[Tensor], weight: Tensor, bias: Optional[T
     # PU_MATH_TF32: tcgen05 kernel where the channel counts allow, fp32 FFMA kernel (output rounded to TF32) elsewhere
     m = MATH_TF32 if (math == MATH_TF32 and _tc_ok(C0, C1, Cout, Cout, 0)) else MATH_FP32
     flags = (FLAG_RELU if relu else 0) | (FLAG_ROUND_TF32 if math == MATH_TF32 else 0)
-    wp, wfmt = _weight_operand(weight, 0, m, C0, C1, Cout, H, W)
+    wp, wfmt = _weight_operand(weight, 0, m, C0, C1, Cout, H, W, B)
     y = torch.empty((B, H, W, Cout), device=x0.device, dtype=torch.float32)
     ymask = mask_like(y) if emit_mask else torch.empty(0, device=x0.device, dtype=torch.uint8)
     _lib.call("pu_conv3x3_fwd", x0.data_ptr(), H0, W0, C0, oy0, ox0, _p(x1), H1, W1, C1, oy1, ox1,
@@ -230,7 +243,7 @@ def conv3x3_bwd(dy: Tensor, y: Tensor, x0: Tensor, x1: Optional[Tensor], weight:
     dx0, dx1 = _e(dev), _e(dev)
     if need_dx:
         md = MATH_TF32 if (tf32 and _tc_ok(Cout, 0, Cin, C0, C1)) else MATH_FP32
-        wpt, wfmt = _weight_operand(weight, 1, md, Cout, 0, Cin, H, W)
+        wpt, wfmt = _weight_operand(weight, 1, md, Cout, 0, Cin, H, W, B)
         full0 = (H0 == H and W0 == W)
         dx0 = (torch.empty if full0 else torch.zeros)((B, H0, W0, C0), device=dev, dtype=torch.float32)
         if x1 is not None:
@@ -472,7 +485,7 @@ def convT3x3s2_tc(x: Tensor, weight: Tensor, bias: Optional[Tensor], Ho: int, Wo
     z = torch.empty((B, Ho, Wo, Cin), device=x.device, dtype=torch.float32)
     _lib.call("pu_zero_insert2x_fwd", x.data_ptr(), z.data_ptr(), B, H, W, Cin, Ho, Wo, oy, ox, _s())
     # the conv whose "dgrad" operand is the IOHW transposed-conv weight: input channels = dim 0, outputs = dim 1, taps flipped
-    wp, wfmt = _weight_operand(weight, 1, MATH_TF32, Cin, 0, Cout, Ho, Wo)
+    wp, wfmt = _weight_operand(weight, 1, MATH_TF32, Cin, 0, Cout, Ho, Wo, B)
     y = torch.empty((B, Ho, Wo, Cout), device=x.device, dtype=torch.float32)
     _lib.call("pu_conv3x3_fwd", z.data_ptr(), Ho, Wo, Cin, 0, 0, None, 0, 0, 0, 0, 0,
               wp.data_ptr(), _p(bias), None, FLAG_ROUND_TF32,
@@ -499,7 +512,7 @@ def convT3x3s2_tc_bwd(dy: Tensor, x: Tensor, weight: Tensor, has_bias: bool, nee
     dx, dw = _e(dev), _e(dev)
     if need_dx:
         # dz = conv3x3(g) with the weight read as OIHW = [Cin][Cout]: input channels = dim 1, outputs = dim 0, taps as stored
-        wp, wfmt = _weight_operand(weight, 0, MATH_TF32, Cout, 0, Cin, Ho, Wo)
+        wp, wfmt = _weight_operand(weight, 0, MATH_TF32, Cout, 0, Cin, Ho, Wo, B)
         dz = torch.empty((B, Ho, Wo, Cin), device=dev, dtype=torch.float32)
         _lib.call("pu_conv3x3_fwd", g.data_ptr(), Ho, Wo, Cout, 0, 0, None, 0, 0, 0, 0, 0,
                   wp.data_ptr(), None, None, FLAG_ROUND_TF32,

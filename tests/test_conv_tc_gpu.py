@@ -173,3 +173,58 @@ def test_tf32_mode_whole_model_close_to_fp32():
     assert rel_err(res["tf32"][1], res["fp32"][1])[1] < 1e-3
     worst = max(rel_err(res["tf32"][2][k], res["fp32"][2][k])[1] for k in res["fp32"][2])
     assert worst < 2e-2, "worst parameter-gradient L2 error %g" % worst
+
+
+FLAT_SHAPES = [
+    # B, C0, C1, Cout, H, W  (flat mode needs Cout % 64 == 0 and 16-channel K chunks)
+    (2, 64, 0, 64, 32, 32),
+    (1, 64, 64, 128, 24, 24),   # fused concat, two co blocks
+    (2, 128, 0, 64, 16, 16),
+    (1, 32, 32, 64, 40, 37),    # odd width
+    (3, 64, 0, 64, 101, 101),   # several tiles per image, ragged edges
+    (1, 256, 0, 256, 12, 12),   # 16 K chunks, four co blocks
+]
+
+
+@pytest.fixture
+def flat_mode(monkeypatch):
+    """Force the flat (one MMA per tap, N = 64, 128-pixel blocks) variant of the tcgen05 conv — by default it is only chosen for
+    the wide, tensor-bound layers with at least two waves of 512-pixel tiles (SURVEY.md §8d "TC demo")."""
+    from pu_b200 import ops
+    monkeypatch.setenv("PU_TC_FLAT", "1")
+    ops._tc_flat.cache_clear()
+    yield
+    monkeypatch.delenv("PU_TC_FLAT")
+    ops._tc_flat.cache_clear()
+
+
+@pytest.mark.parametrize("B,C0,C1,Cout,H,W", FLAT_SHAPES)
+def test_conv3x3_tc_flat_mode(flat_mode, B, C0, C1, Cout, H, W):
+    """Flat-mode forward vs a float64 conv of the same TF32-rounded operands, and dgrad / wgrad through autograd vs the
+    strict-fp32 CUDA-core path (same tolerances as the folded kernel)."""
+    from pu_b200 import _lib, ops
+    assert _lib.load().pu_conv3x3_tc_flat(B, H, W, C0, C1, Cout) == 1
+    g = torch.Generator().manual_seed(C0 + Cout + H)
+    Cin = C0 + C1
+    x0 = tf32_round(torch.randn(B, H, W, C0, generator=g))
+    x1 = tf32_round(torch.randn(B, H, W, C1, generator=g)) if C1 else None
+    w = tf32_round(torch.randn(Cout, Cin, 3, 3, generator=g) / (3 * Cin ** 0.5))
+    b = torch.randn(Cout, generator=g)
+    R = tf32_round(torch.randn(B, H, W, Cout, generator=g))
+    cat = nchw(x0).double() if not C1 else torch.cat([nchw(x0).double(), nchw(x1).double()], 1)
+    yr = F.relu(F.conv2d(cat, w.double(), b.double(), padding=1))
+    outs = {}
+    for math in (ops.MATH_FP32, ops.MATH_TF32):
+        x0d = x0.to(DEV).requires_grad_(True)
+        x1d = x1.to(DEV).requires_grad_(True) if C1 else None
+        wd, bd = w.to(DEV).requires_grad_(True), b.to(DEV).requires_grad_(True)
+        y = ops.conv3x3(x0d, x1d, wd, bd, None, True, H, W, 0, 0, 0, 0, math)
+        (y * R.to(DEV)).sum().backward()
+        outs[math] = (y.detach(), x0d.grad, x1d.grad if C1 else None, wd.grad, bd.grad)
+    torch.cuda.synchronize()
+    e = rel_err(nchw(outs[ops.MATH_TF32][0]), yr)
+    assert e[0] < 6e-4, "forward: max-rel %g l2-rel %g" % e
+    for n, a, bb in zip(["y", "dx0", "dx1", "dw", "db"], outs[ops.MATH_TF32], outs[ops.MATH_FP32]):
+        if a is not None:
+            e = rel_err(a, bb)
+            assert e[0] < 2e-3, "%s: max-rel %g l2-rel %g" % (n, e[0], e[1])
