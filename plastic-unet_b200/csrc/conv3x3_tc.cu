@@ -76,6 +76,7 @@ struct TcArgs {
   int w_res_bytes;  // bytes of the resident weight image (0 in streamed mode)
   unsigned int* tile_ctr;  // dynamic tile scheduler: [co block] next-tile counters of this launch's slot (zero between launches)
   unsigned int* done_ctr;  // CTAs of this launch that have finished (the last one re-zeroes the slot)
+  int dynamic;             // 0: static round-robin tiles (tile = blockIdx.x + k * gridDim.x), 1: the dynamic scheduler
   int debug;        // PU_TC_DEBUG experiments: 1 = skip MMAs, 2 = skip epilogue stores, 4 = load only the first stages
   unsigned w_coblk_stride;  // bytes
   TcChunk chunks[kMaxChunks];
@@ -260,7 +261,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const __grid_
   // kernel then lasts as long as its unluckiest CTA.  Instead the producer warp draws tiles from a global counter (the first
   // tile is blockIdx.x, later ones gridDim.x + atomicAdd) and hands each index to the MMA and epilogue warps through a
   // small shared-memory queue guarded by mbarriers; -1 ends the kernel.  Consumers: kMmaWarps + kEpiWarps warps.
+  // Measured on B200 (UNetp step, B = 64): the queue hand-off costs the latency-bound narrow layers ~4 % (1.24 -> 1.29 ms
+  // per step) and the contention it was built for is not relieved by it (the side-stream kernels time-slice whole SMs), so
+  // it is opt-in (PU_TC_DYNAMIC=1); the default is the static assignment.
   auto next_tile = [&](int k) -> int {  // consumer side: k-th tile of this CTA (every consumer warp calls it for every k in order)
+    if (!a.dynamic) {
+      const int t = (int)blockIdx.x + k * (int)gridDim.x;
+      return t < a.tilesX * a.tilesY * a.B ? t : -1;
+    }
     const int q = k % kTileQ;
     mbar_wait(tqfull_bar(q), (uint32_t)(k / kTileQ) & 1);
     const int t = tileq[q];
@@ -396,15 +404,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const __grid_
   } else if (warp == 0) {
     // ================= TMA producer =================
     const uint8_t* wblk = reinterpret_cast<const uint8_t*>(a.wpk) + (size_t)coblk * a.w_coblk_stride;
+    int tile_next = blockIdx.x;  // lane 0: the tile drawn one iteration ahead (the atomic's round trip hides behind the loads)
     for (int k = 0;; ++k) {
-      // draw the next tile and publish it to the consumer warps
-      int tile = blockIdx.x;
-      if (k > 0) {
-        if (lane == 0) tile = (int)gridDim.x + (int)atomicAdd(a.tile_ctr + coblk, 1u);
-        tile = __shfl_sync(0xffffffffu, tile, 0);
+      // publish the tile drawn during the previous iteration to the consumer warps, and draw the one after it
+      int tile;
+      if (a.dynamic) {
+        tile = __shfl_sync(0xffffffffu, tile_next, 0);
+        if (tile >= ntiles) tile = -1;
+        if (tile >= 0 && lane == 0) tile_next = (int)gridDim.x + (int)atomicAdd(a.tile_ctr + coblk, 1u);
+      } else {
+        tile = (int)blockIdx.x + k * (int)gridDim.x;
+        if (tile >= ntiles) tile = -1;
       }
-      if (tile >= ntiles) tile = -1;
-      {
+      if (a.dynamic) {
         const int q = k % kTileQ;
         mbar_wait(tqempty_bar(q), ((uint32_t)(k / kTileQ) & 1) ^ 1);  // passes immediately on a fresh barrier
         if (lane == 0) {
@@ -467,6 +479,32 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const __grid_
         if (mw == 0 && lane == 0 && c == 0) stamp(1, k);
         const uint32_t sS = smem_u32(smem + st * stage_bytes);
         const uint64_t b_base = umma_desc(a.wfmt == 0 ? sS + a.a_bytes : smem_u32(smWres) + ch.w_off, 16, 256, 6);
+        if (!FOLD) {
+          // flat: every MMA warp owns whole 128-pixel blocks (the planner keeps nmb <= kMmaWarps, so one each) and issues
+          // the nine taps of each 8-channel K step back to back — immediate descriptor offsets, no per-MMA loop control
+          for (int mb = mw; mb < a.nmb; mb += kMmaWarps) {
+            const uint32_t d = d0 + (uint32_t)(mb * NACC);
+            for (int ky = 0; ky < 3; ++ky) {
+              uint32_t kc = 0;
+              for (int r = 0; r < ch.nreg; ++r) {
+                const uint32_t rb = (uint32_t)ch.reg[r].cb * 4;
+                const uint32_t layout = rb == 32 ? 6u : (rb == 64 ? 4u : 2u);
+                const uint64_t a_blk = umma_desc(sS + ch.reg[r].off + (uint32_t)(ky * a.PW + mb * kBlkPixFlat) * rb, 16, 8 * rb, layout);
+                const int ksteps = ch.reg[r].cb >> 3;
+                for (int ks = 0; ks < ksteps; ++ks, kc += 2) {
+                  const uint64_t bd0 = b_base + (uint64_t)((ky * (ch.ncg >> 1) + (kc >> 1)) * N3 * 2);
+                  const uint64_t ad0 = a_blk + (uint64_t)(2 * ks);
+                  const uint32_t first = (c | ky | (int)kc) ? 1u : 0u;
+                  if (leader && !(a.debug & 1)) {
+                    umma_tf32(d, ad0, bd0, idesc, first);
+                    umma_tf32(d, ad0 + (rb >> 4), bd0 + COLS * 2, idesc, 1u);
+                    umma_tf32(d, ad0 + 2 * (rb >> 4), bd0 + 2 * COLS * 2, idesc, 1u);
+                  }
+                }
+              }
+            }
+          }
+        } else
         for (int ky = 0; ky < 3; ++ky) {
           uint32_t kc = 0;
           for (int r = 0; r < ch.nreg; ++r) {
@@ -745,7 +783,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const __grid_
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)a.tmem_cols) : "memory");
   }
-  if (tid == 0) {
+  if (tid == 0 && a.dynamic) {
     // this CTA draws no more tiles (its producer, this very thread, is done): the last CTA to get here re-zeroes the slot
     __threadfence();
     const unsigned total = gridDim.x * gridDim.y;
@@ -842,7 +880,7 @@ static bool tc_want_flat(long long npix, int C0, int C1, int Cout) {
   const bool can = Cout % 64 == 0 && C0 % 16 == 0 && C1 % 16 == 0 && C0 + C1 >= 32;
   if (!can) return false;
   if (const char* e = getenv("PU_TC_FLAT")) return atoi(e) != 0;
-  return C0 + C1 >= 64 && npix >= 2LL * kNumSMs * 512;
+  return C0 + C1 >= 64 && npix * (Cout / 64) >= (long long)kNumSMs * 384;  // at least one 384-pixel tile per SM
 }
 
 // channel plan: K chunks, weight image layout.  false if the channel counts do not fit the tensor-core path.
@@ -902,7 +940,8 @@ static bool tc_plan1(int B, int H, int W, int C0, int C1, int Cout, TcPlan* p, b
     p->w_bytes_max = 0;
   }
   const size_t budget = 220 * 1024 - (size_t)p->w_res_bytes;  // minus barriers and the 1024-byte alignment slack below
-  const int nmb_max = 256 / (p->fold ? p->n3 : p->cols);  // two accumulator buffers of <= 256 TMEM columns
+  // two accumulator buffers of <= 256 TMEM columns; flat: one 128-pixel block per MMA-issuing warp (balanced issue)
+  const int nmb_max = p->fold ? 256 / p->n3 : (256 / p->cols < kMmaWarps ? 256 / p->cols : kMmaWarps);
   auto stage_a_bytes = [&](int th, int pw, int nmb) {
     // rows a region must hold: the halo tile, and whatever the last MMA block's shifted reads touch beyond it
     int rows = (th + 2) * pw;
@@ -933,7 +972,8 @@ static bool tc_plan1(int B, int H, int W, int C0, int C1, int Cout, TcPlan* p, b
       const size_t stage = stage_a_bytes(th, pw, nmb) + p->w_bytes_max;
       if (2 * stage > budget) continue;
       const long long ntiles = (long long)B * ((H + th - 1) / th) * ((W + tw - 1) / tw);
-      const long long waves = (ntiles + kNumSMs - 1) / kNumSMs;
+      const int ctas_x = (kNumSMs + p->ncoblk - 1) / p->ncoblk;  // the co blocks share the SMs: grid = (ctas_x, ncoblk)
+      const long long waves = (ntiles + ctas_x - 1) / ctas_x;
       // per-SM time ~ waves x (MMA rows + staged rows + a fixed per-tile hand-off cost), in units of one pixel row
       const double cost = (double)waves * (nmb * 128 + (th + 2) * pw + tile_fixed);
       if (cost < best_cost) { best_cost = cost; best_th = th; best_tx = tilesX; }
@@ -1094,6 +1134,12 @@ int conv3x3_fwd_tc(const Conv3x3Args& a, cudaStream_t st) {
     return PU_ERR_UNSUPPORTED;
   }
   {
+    static int dyn = -1;
+    if (dyn < 0) {
+      const char* e = getenv("PU_TC_DYNAMIC");
+      dyn = (e != nullptr && e[0] == '1') ? 1 : 0;
+    }
+    ta.dynamic = dyn;
     const unsigned slot = g_tc_slot.fetch_add(1) % kTcSlots;
     ta.tile_ctr = g_tc_counters_dev + (size_t)slot * (kMaxCoBlk + 1);
     ta.done_ctr = ta.tile_ctr + kMaxCoBlk;
@@ -1108,7 +1154,8 @@ int conv3x3_fwd_tc(const Conv3x3Args& a, cudaStream_t st) {
   }
   for (int i = 0; i < p.nchunks; ++i) ta.chunks[i] = p.chunks[i];
   const int ntiles = p.tilesX * p.tilesY * a.B;
-  dim3 grid(ntiles < kNumSMs ? ntiles : kNumSMs, p.ncoblk);
+  const int ctas_x = (kNumSMs + p.ncoblk - 1) / p.ncoblk;  // one persistent CTA per SM in total
+  dim3 grid(ntiles < ctas_x ? ntiles : ctas_x, p.ncoblk);
   if (!p.fold) return launch_tc<64, false>(tm0, tm1, ta, grid, p.smem_bytes, st);
   switch (p.cols) {
     case 8: return launch_tc<8>(tm0, tm1, ta, grid, p.smem_bytes, st);
