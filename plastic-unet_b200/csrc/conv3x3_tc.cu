@@ -875,12 +875,12 @@ static int next_pow2_cols(int c) {
 static int region_channels(int C) { return C % 32 == 0 ? 32 : (C % 16 == 0 ? 16 : 8); }
 
 // Flat mode (one MMA per tap, N = 64) for the wide layers: >= 64 input and output channels (multiples of 64 outputs) and
-// enough pixels for at least two full waves of 512-pixel tiles.  PU_TC_FLAT=0/1 forces it off/on where the shape allows.
+// enough (tile, co block) work items to occupy the SMs.  PU_TC_FLAT=0/1 forces it off/on where the shape allows.
 static bool tc_want_flat(long long npix, int C0, int C1, int Cout) {
   const bool can = Cout % 64 == 0 && C0 % 16 == 0 && C1 % 16 == 0 && C0 + C1 >= 32;
   if (!can) return false;
   if (const char* e = getenv("PU_TC_FLAT")) return atoi(e) != 0;
-  return C0 + C1 >= 64 && npix * (Cout / 64) >= (long long)kNumSMs * 384;  // at least one 384-pixel tile per SM
+  return C0 + C1 >= 64 && ((npix + 383) / 384) * (Cout / 64) >= 96;  // enough (384-pixel tile, co block) work items to fill the SMs
 }
 
 // channel plan: K chunks, weight image layout.  false if the channel counts do not fit the tensor-core path.
