@@ -229,9 +229,10 @@ template <int COLS, bool FOLD>
 __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm0,
                                                                    const __grid_constant__ CUtensorMap tm1, const TcArgs a) {
   constexpr int N3 = tc_n3(COLS);
-  constexpr int NACC = FOLD ? N3 : COLS;          // TMEM columns of one MMA block's accumulators
+  // flat MMA width: COLS, but an M = 128 MMA needs N % 16 == 0: an 8-channel layer computes 8 unused extra columns (the next
+  // tap's rows of the B tile; MMAs are free in these HBM-bound layers)
+  constexpr int NACC = FOLD ? N3 : (COLS < 16 ? 16 : COLS);  // TMEM columns of one MMA block's accumulators
   constexpr int BLK = FOLD ? kBlkPix : kBlkPixFlat;  // output pixels per MMA block
-  static_assert(FOLD || COLS % 16 == 0, "an M = 128 MMA needs N % 16 == 0");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // swizzle patterns repeat every 1024 B
   const int nst = a.nstages;
@@ -460,7 +461,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const __grid_
     // so the descriptors live in uniform registers.
     const int mw = warp - 1;
     // instruction descriptor: D=f32, A=B=tf32, K-major both, N = N3, M = 128 (cute::UMMA::InstrDescriptor)
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((FOLD ? N3 : COLS) >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NACC >> 3) << 17) | ((128u >> 4) << 24);
     const bool leader = elect_one();  // elected once: the issue loop must stay a handful of instructions per MMA
     int it = 0;
     for (int k = 0;; ++k) {
@@ -874,13 +875,16 @@ static int next_pow2_cols(int c) {
 
 static int region_channels(int C) { return C % 32 == 0 ? 32 : (C % 16 == 0 ? 16 : 8); }
 
-// Flat mode (one MMA per tap, N = 64) for the wide layers: >= 64 input and output channels (multiples of 64 outputs) and
-// enough (tile, co block) work items to occupy the SMs.  PU_TC_FLAT=0/1 forces it off/on where the shape allows.
+// When to use the flat mode (one MMA per tap).  PU_TC_FLAT=0/1 forces it off/on.
 static bool tc_want_flat(long long npix, int C0, int C1, int Cout) {
-  const bool can = Cout % 64 == 0 && C0 % 16 == 0 && C1 % 16 == 0 && C0 + C1 >= 32;
-  if (!can) return false;
   if (const char* e = getenv("PU_TC_FLAT")) return atoi(e) != 0;
-  return C0 + C1 >= 64 && ((npix + 383) / 384) * (Cout / 64) >= 96;  // enough (384-pixel tile, co block) work items to fill the SMs
+  if (Cout >= 64 && Cout % 64 == 0 && C0 % 16 == 0 && C1 % 16 == 0 && C0 + C1 >= 64 && ((npix + 383) / 384) * (Cout / 64) >= 96)
+    return true;  // wide, tensor-bound layers with enough (384-pixel tile, co block) work items to fill the SMs
+  // narrow, HBM-bound layers: the flat epilogue does ~0.45x the work per pixel (no kx realignment, no duplicated rows) but the
+  // tile needs 3x the MMAs, and one thread issues a tcgen05.mma only every ~128 clk: measured on B200 (B = 64) flat wins
+  // for 16..64 output channels when C_in <= C_out (8->16 @64^2: 18.4 -> 14.0 us, 32->64 @16^2: 14.6 -> 11.9 us) and loses
+  // for 8 output channels (N padded to 16) and for the concat layers (8|8->8 @128^2: 31.9 -> 44.7 us)
+  return Cout >= 16 && Cout <= 64 && C0 + C1 <= Cout;
 }
 
 // channel plan: K chunks, weight image layout.  false if the channel counts do not fit the tensor-core path.
@@ -891,9 +895,12 @@ static bool tc_plan_channels(int C0, int C1, int Cout, TcPlan* p, bool flat = fa
   p->n3 = tc_n3(p->cols);
   p->ncoblk = (Cout + kCoBlk - 1) / kCoBlk;
   p->fold = flat ? 0 : 1;
-  // flat: 16-channel K chunks keep a 512-pixel stage (45 KB of pixels + 37 KB of weights) small enough for two stages
-  p->cb0 = flat ? 16 : region_channels(C0);
-  p->cb1 = C1 > 0 ? (flat ? 16 : region_channels(C1)) : 0;
+  // flat, wide layers: 16-channel K chunks keep a 384-pixel stage (35 KB of pixels + 37 KB of weights) small enough for two stages
+  const bool cap16 = flat && Cout >= 64;
+  p->cb0 = region_channels(C0);
+  p->cb1 = C1 > 0 ? region_channels(C1) : 0;
+  if (cap16 && p->cb0 > 16) p->cb0 = 16;
+  if (cap16 && p->cb1 > 16) p->cb1 = 16;
   p->nchunks = 0;
   unsigned woff = 0;
   auto add = [&](int nreg, TcRegion r0, TcRegion r1) {
@@ -922,7 +929,7 @@ static bool tc_plan1(int B, int H, int W, int C0, int C1, int Cout, TcPlan* p, b
 // flat < 0: flat mode where tc_want_flat says so and the plan fits, else folded
 static bool tc_plan(int B, int H, int W, int C0, int C1, int Cout, TcPlan* p, bool resident = false, int flat = -1) {
   const bool want_flat = flat < 0 ? tc_want_flat((long long)B * H * W, C0, C1, Cout) : (flat != 0);
-  if (want_flat && !resident && tc_plan1(B, H, W, C0, C1, Cout, p, false, true)) return true;
+  if (want_flat && tc_plan1(B, H, W, C0, C1, Cout, p, resident, true)) return true;
   return tc_plan1(B, H, W, C0, C1, Cout, p, resident, false);
 }
 
@@ -941,7 +948,9 @@ static bool tc_plan1(int B, int H, int W, int C0, int C1, int Cout, TcPlan* p, b
   }
   const size_t budget = 220 * 1024 - (size_t)p->w_res_bytes;  // minus barriers and the 1024-byte alignment slack below
   // two accumulator buffers of <= 256 TMEM columns; flat: one 128-pixel block per MMA-issuing warp (balanced issue)
-  const int nmb_max = p->fold ? 256 / p->n3 : (256 / p->cols < kMmaWarps ? 256 / p->cols : kMmaWarps);
+  const int nacc = p->fold ? p->n3 : (p->cols < 16 ? 16 : p->cols);
+  const int flat_cap = p->cols >= 64 ? kMmaWarps : 2 * kMmaWarps;  // wide: one block per issuing warp; narrow (HBM-bound): two
+  const int nmb_max = p->fold ? 256 / nacc : (256 / nacc < flat_cap ? 256 / nacc : flat_cap);
   auto stage_a_bytes = [&](int th, int pw, int nmb) {
     // rows a region must hold: the halo tile, and whatever the last MMA block's shifted reads touch beyond it
     int rows = (th + 2) * pw;
@@ -1009,7 +1018,7 @@ static bool tc_plan1(int B, int H, int W, int C0, int C1, int Cout, TcPlan* p, b
   const size_t stage = (size_t)p->a_bytes + p->w_bytes_max;
   p->nstages = (int)(budget / stage);
   if (p->nstages > kMaxStages) p->nstages = kMaxStages;
-  p->tmem_cols = next_pow2_cols(2 * p->nmb * (p->fold ? p->n3 : p->cols));
+  p->tmem_cols = next_pow2_cols(2 * p->nmb * (p->fold ? p->n3 : (p->cols < 16 ? 16 : p->cols)));
   p->smem_bytes = (size_t)p->nstages * stage + p->w_res_bytes + 256 + 2048 + 1024;  // barriers, k-group table + trace, alignment
   return p->nstages >= 2 && p->tmem_cols <= 512;
 }
@@ -1156,7 +1165,14 @@ int conv3x3_fwd_tc(const Conv3x3Args& a, cudaStream_t st) {
   const int ntiles = p.tilesX * p.tilesY * a.B;
   const int ctas_x = (kNumSMs + p.ncoblk - 1) / p.ncoblk;  // one persistent CTA per SM in total
   dim3 grid(ntiles < ctas_x ? ntiles : ctas_x, p.ncoblk);
-  if (!p.fold) return launch_tc<64, false>(tm0, tm1, ta, grid, p.smem_bytes, st);
+  if (!p.fold) {
+    switch (p.cols) {
+      case 8: return launch_tc<8, false>(tm0, tm1, ta, grid, p.smem_bytes, st);
+      case 16: return launch_tc<16, false>(tm0, tm1, ta, grid, p.smem_bytes, st);
+      case 32: return launch_tc<32, false>(tm0, tm1, ta, grid, p.smem_bytes, st);
+      default: return launch_tc<64, false>(tm0, tm1, ta, grid, p.smem_bytes, st);
+    }
+  }
   switch (p.cols) {
     case 8: return launch_tc<8>(tm0, tm1, ta, grid, p.smem_bytes, st);
     case 16: return launch_tc<16>(tm0, tm1, ta, grid, p.smem_bytes, st);

@@ -79,10 +79,10 @@ def _weight_operand(weight: Tensor, transpose: int, math: int, C0: int, C1: int,
     conv, and tcgen05 convs whose weight image fits in shared memory), else the pu_pack_w3x3 buffer."""
     if math == MATH_FP32:
         return weight, (W_OIHW_DGRAD if transpose else W_OIHW)
-    if _tc_flat(B, H, W, C0, C1, Cout_conv):
-        return _pack_w(weight, transpose, MATH_TF32_FLAT, C0), W_PACKED
     if _tc_resident(C0, C1, Cout_conv, H, W):
         return weight, (W_OIHW_DGRAD if transpose else W_OIHW)
+    if _tc_flat(B, H, W, C0, C1, Cout_conv):  # the wide layers' K chunking differs: their weight image is packed accordingly
+        return _pack_w(weight, transpose, MATH_TF32_FLAT, C0), W_PACKED
     return _pack_w(weight, transpose, math, C0), W_PACKED
 
 

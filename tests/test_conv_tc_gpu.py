@@ -176,7 +176,12 @@ def test_tf32_mode_whole_model_close_to_fp32():
 
 
 FLAT_SHAPES = [
-    # B, C0, C1, Cout, H, W  (flat mode needs Cout % 64 == 0 and 16-channel K chunks)
+    # B, C0, C1, Cout, H, W
+    (2, 8, 0, 8, 128, 128),     # narrow layers (N padded to 16), resident weights
+    (2, 8, 8, 8, 64, 64),
+    (2, 8, 0, 16, 64, 64),
+    (2, 32, 32, 16, 32, 32),
+    (1, 16, 0, 24, 37, 29),
     (2, 64, 0, 64, 32, 32),
     (1, 64, 64, 128, 24, 24),   # fused concat, two co blocks
     (2, 128, 0, 64, 16, 16),
@@ -204,6 +209,8 @@ def test_conv3x3_tc_flat_mode(flat_mode, B, C0, C1, Cout, H, W):
     strict-fp32 CUDA-core path (same tolerances as the folded kernel)."""
     from pu_b200 import _lib, ops
     assert _lib.load().pu_conv3x3_tc_flat(B, H, W, C0, C1, Cout) == 1
+    from pu_b200 import ops as _o
+    _o._tc_resident.cache_clear()
     g = torch.Generator().manual_seed(C0 + Cout + H)
     Cin = C0 + C1
     x0 = tf32_round(torch.randn(B, H, W, C0, generator=g))
