@@ -89,10 +89,11 @@ int pu_conv3x3_tc_flat(int B, int H, int W, int C0, int C1, int Cout);
 /* 1 if, additionally, the tcgen05 kernel can build its weight tiles from the raw OIHW tensor (they fit in shared memory) */
 int pu_conv3x3_tc_resident(int C0, int C1, int Cout, int H, int W);
 /* Host-only (no device needed): the tile plan pu_conv3x3_fwd would use for this problem, for tests and tuning.
- * out16 = {TH, TW, PW, tilesX, tilesY, blocks per tile, COLS, MMA N, stage A bytes, stage weight bytes, resident weight
- * bytes, TMEM columns, K chunks, co blocks, stages, dynamic shared memory bytes}.  resident != 0: the weights are built
+ * out17 = {TH, TW, PW, tilesX, tilesY, blocks per tile, COLS, N3 (B-tile rows), stage A bytes, stage weight bytes, resident weight
+ * bytes, TMEM columns, K chunks, co blocks, stages, dynamic shared memory bytes, fold (1: kx folded into N, 96-pixel blocks;
+ * 0: flat, one MMA per tap, 128-pixel blocks)}.  resident != 0: the weights are built
  * in shared memory from the raw OIHW tensor (PU_W_OIHW / PU_W_OIHW_DGRAD).  PU_ERR_UNSUPPORTED if the shape does not fit. */
-int pu_conv3x3_tc_plan(int B, int H, int W, int C0, int C1, int Cout, int resident, int* out16);
+int pu_conv3x3_tc_plan(int B, int H, int W, int C0, int C1, int Cout, int resident, int* out17);
 
 /* y = act( conv3x3(cat[src0,src1]) + bias + res ), written channel-split into dst0|dst1 (flags: PU_FLAG_*).
  * wfmt selects what `wp` points at: PU_W_PACKED (output of pu_pack_w3x3 for this math mode), PU_W_OIHW (the raw

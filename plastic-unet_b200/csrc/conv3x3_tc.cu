@@ -1188,8 +1188,8 @@ extern "C" int pu_tc_available(void) { return pu::tc_init() ? 1 : 0; }
 extern "C" int pu_conv3x3_tc_flat(int B, int H, int W, int C0, int C1, int Cout) { return pu::conv3x3_tc_flat(B, H, W, C0, C1, Cout) ? 1 : 0; }
 
 // Host-only: the tile plan pu_conv3x3_fwd would use (no device needed; for tests and tuning).
-extern "C" int pu_conv3x3_tc_plan(int B, int H, int W, int C0, int C1, int Cout, int resident, int* out16) {
-  if (out16 == nullptr || B <= 0 || H <= 0 || W <= 0) {
+extern "C" int pu_conv3x3_tc_plan(int B, int H, int W, int C0, int C1, int Cout, int resident, int* out17) {
+  if (out17 == nullptr || B <= 0 || H <= 0 || W <= 0) {
     pu::set_error("pu_conv3x3_tc_plan: bad argument");
     return PU_ERR_BAD_ARG;
   }
@@ -1199,8 +1199,8 @@ extern "C" int pu_conv3x3_tc_plan(int B, int H, int W, int C0, int C1, int Cout,
                   resident ? " with resident weights" : "");
     return PU_ERR_UNSUPPORTED;
   }
-  const int v[16] = {p.TH, p.TW, p.PW, p.tilesX, p.tilesY, p.nmb, p.cols, p.n3, p.a_bytes, p.w_bytes_max, p.w_res_bytes, p.tmem_cols,
-                     p.nchunks, p.ncoblk, p.nstages, (int)p.smem_bytes};
-  for (int i = 0; i < 16; ++i) out16[i] = v[i];
+  const int v[17] = {p.TH, p.TW, p.PW, p.tilesX, p.tilesY, p.nmb, p.cols, p.n3, p.a_bytes, p.w_bytes_max, p.w_res_bytes, p.tmem_cols,
+                     p.nchunks, p.ncoblk, p.nstages, (int)p.smem_bytes, p.fold};
+  for (int i = 0; i < 17; ++i) out17[i] = v[i];
   return PU_OK;
 }

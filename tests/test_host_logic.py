@@ -141,13 +141,13 @@ def test_wgrad_tap_pair_tiles():
 def _plan(B, H, W, C0, C1, Cout, resident):
     import ctypes
     from pu_b200 import _lib
-    out = (ctypes.c_int * 16)()
+    out = (ctypes.c_int * 17)()
     lib = _lib.load()
     rc = lib.pu_conv3x3_tc_plan(B, H, W, C0, C1, Cout, 1 if resident else 0, ctypes.addressof(out))
     if rc != 0:
         return None
     keys = ["TH", "TW", "PW", "tilesX", "tilesY", "nmb", "cols", "n3", "a_bytes", "w_stage", "w_res", "tmem_cols", "nchunks",
-            "ncoblk", "nstages", "smem"]
+            "ncoblk", "nstages", "smem", "fold"]
     return dict(zip(keys, list(out)))
 
 
@@ -199,14 +199,17 @@ def test_tc_conv_planner_invariants():
             assert p["cols"] in (8, 16, 32, 64) and p["n3"] == -(-3 * p["cols"] // 16) * 16, ctx
             assert p["PW"] == p["TW"] + 2 and p["PW"] <= 256 and p["TH"] + 2 <= 256, ctx            # TMA box limits
             assert p["tilesX"] * p["TW"] >= side and p["tilesY"] * p["TH"] >= side, ctx               # tiles cover the image
-            assert p["nmb"] * 96 >= p["TH"] * p["PW"], ctx                                           # blocks cover the tile rows
-            assert p["nmb"] * p["n3"] <= 256, ctx                                                    # one TMEM accumulator buffer
-            assert p["tmem_cols"] <= 512 and p["tmem_cols"] >= 2 * p["nmb"] * p["n3"], ctx
+            blk = 96 if p["fold"] else 128          # folded: kx taps in N, 96 output pixels per block; flat: 128
+            nacc = p["n3"] if p["fold"] else max(16, p["cols"])  # TMEM columns per block
+            assert p["nmb"] * blk >= p["TH"] * p["PW"], ctx                                          # blocks cover the tile rows
+            assert p["nmb"] * nacc <= 256, ctx                                                       # one TMEM accumulator buffer
+            assert p["fold"] or p["nmb"] <= (3 if p["cols"] >= 64 else 6), ctx                       # flat: blocks per MMA-issuing warp
+            assert p["tmem_cols"] <= 512 and p["tmem_cols"] >= 2 * p["nmb"] * nacc, ctx
             assert p["tmem_cols"] & (p["tmem_cols"] - 1) == 0 and p["tmem_cols"] >= 32, ctx
             assert 2 <= p["nstages"] <= 4 and p["a_bytes"] % 1024 == 0 and p["w_stage"] % 1024 == 0, ctx
             assert p["smem"] <= 227 * 1024, ctx
             assert (p["w_res"] > 0) == resident and (p["w_stage"] == 0) == resident, ctx
-            assert p["ncoblk"] == -(-Cout // 64) and 1 <= p["nchunks"] <= 40, ctx
+            assert p["ncoblk"] == -(-Cout // 64) and 1 <= p["nchunks"] <= 64, ctx
             # shared memory accounting: stages + resident weights + bookkeeping
             assert p["smem"] >= p["nstages"] * (p["a_bytes"] + p["w_stage"]) + p["w_res"], ctx
     assert planned > len(shapes)  # most shapes have both a resident and a streamed plan
