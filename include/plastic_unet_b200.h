@@ -199,6 +199,12 @@ int pu_bn_bwd(const float* x, const float* y, const float* dy, const float* gamm
 /* running_mean/var <- (1-momentum)*running + momentum*(batch mean / unbiased batch var recovered from invstd) */
 int pu_bn_update_running(const float* mean, const float* invstd, float* running_mean, float* running_var,
                          float momentum, float eps, long long npix, int C, void* stream);
+/* Eval-mode BatchNorm folded into the convolution in front of it (reference unet_p.py:105-110 in net.eval()):
+ * w_out[co][...] = w[co][...] * s[co], b_out[co] = (b[co] - running_mean[co]) * s[co] + beta[co], s = gamma / sqrt(var + eps);
+ * per_co = C_in * kh * kw weights per output channel; b may be NULL.  The conv then runs with its fused ReLU epilogue and
+ * the normalisation costs no pass over the activations.                                                                */
+int pu_bn_fold_conv(const float* w, const float* b, const float* gamma, const float* beta, const float* running_mean,
+                    const float* running_var, float eps, float* w_out, float* b_out, int Cout, int per_co, void* stream);
 /* invstd[c] = rsqrt(running_var[c] + eps) (eval-mode backward helper) */
 int pu_bn_invstd(const float* running_var, float* invstd, float eps, int C, void* stream);
 
@@ -226,6 +232,10 @@ int pu_trace_update_fwd(const float* hebb, const float* pre, const float* post, 
 /* data-parallel split form: delta_q = [N*N + N] floats = (sum_k outer, sum_k post^2) — all-reduced
  * over ranks by the caller — then the epilogue with K_global.                                   */
 int pu_trace_delta(const float* pre, const float* post, long long ld, int K, float* delta_q, int N, void* stream);
+/* The same payload for LARGE K on the tensor cores (opt-in rows='all' mode: K = B*N, every row of every map is a
+ * (pre, post) pair — what the reference's bmm computes before it keeps [0], unet_p.py:82): split-K mma.sync TF32 GEMM
+ * with the 3xTF32 error-compensated split (fp32-level accuracy), partial sums merged with fp32 atomics.            */
+int pu_trace_delta_tc(const float* pre, const float* post, long long ld, int K, float* delta_q, int N, void* stream);
 int pu_trace_apply(const float* hebb, const float* delta_q, int K_global, const float* eta, int rule,
                    float* out, int N, void* stream);
 /* backward of the fused update w.r.t. hebb, pre, post, eta (closed forms) */

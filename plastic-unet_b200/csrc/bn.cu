@@ -153,6 +153,23 @@ static int red_cfg(int C, long long npix, int* bs, int* blocks) {
   return PU_OK;
 }
 
+// eval-mode BatchNorm folded into the preceding convolution (a free fusion: no activation pass at all):
+//   BN(conv_w(x) + b) = conv_{w'}(x) + b',  s = gamma / sqrt(var + eps),  w'[co] = w[co] * s[co],  b' = (b - mean) * s + beta
+__global__ void bn_fold_conv_kernel(const float* __restrict__ w, const float* __restrict__ b, const float* __restrict__ gamma,
+                                    const float* __restrict__ beta, const float* __restrict__ mean, const float* __restrict__ var, float eps,
+                                    float* __restrict__ w_out, float* __restrict__ b_out, int Cout, int per_co) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long n = (long long)Cout * per_co;
+  if (i < n) {
+    const int co = (int)(i / per_co);
+    w_out[i] = w[i] * (gamma[co] * rsqrtf(var[co] + eps));
+  } else if (i < n + Cout) {
+    const int co = (int)(i - n);
+    const float s = gamma[co] * rsqrtf(var[co] + eps);
+    b_out[co] = ((b != nullptr ? b[co] : 0.f) - mean[co]) * s + beta[co];
+  }
+}
+
 }  // namespace pu
 
 extern "C" {
@@ -214,6 +231,16 @@ int pu_bn_update_running(const float* mean, const float* invstd, float* running_
   pu::bn_update_running_kernel<<<pu::cdiv(C, 128), 128, 0, pu::as_stream(stream)>>>(mean, invstd, running_mean, running_var, momentum,
                                                                                 eps, npix, C);
   return pu::post_launch("pu_bn_update_running");
+}
+
+int pu_bn_fold_conv(const float* w, const float* b, const float* gamma, const float* beta, const float* running_mean,
+                    const float* running_var, float eps, float* w_out, float* b_out, int Cout, int per_co, void* stream) {
+  PU_REQUIRE(w && gamma && beta && running_mean && running_var && w_out && b_out && Cout > 0 && per_co > 0, PU_ERR_BAD_ARG,
+             "pu_bn_fold_conv: bad argument");
+  const long long n = (long long)Cout * per_co;
+  pu::bn_fold_conv_kernel<<<pu::cdiv(n + Cout, 256), 256, 0, pu::as_stream(stream)>>>(w, b, gamma, beta, running_mean, running_var, eps, w_out,
+                                                                                      b_out, Cout, per_co);
+  return pu::post_launch("pu_bn_fold_conv");
 }
 
 int pu_bn_invstd(const float* running_var, float* invstd, float eps, int C, void* stream) {

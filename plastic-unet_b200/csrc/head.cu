@@ -220,6 +220,103 @@ __global__ void trace_contract_kernel(const float* __restrict__ hebb, const floa
   out[(size_t)i * N + j] = fmaf(decay, h, eta * d * invK);
 }
 
+
+// ---- trace contraction on tensor cores (rows = 'all': K = B*N pre/post pairs) ------------------------------------------
+// delta[i][j] += sum_k pre[k][i] * post[k][j],  q[j] += sum_k post[k][j]^2   over this CTA's K slice.
+// The literal "every pixel-row" reading of the plastic update (the reference's bmm computes all N outer products before
+// keeping [0], unet_p.py:82): a [N x K] x [K x N] GEMM with K = B*N (8192 at B = 64, N = 128; 134 M MACs).  Warp-level
+// mma.sync.m16n8k8 TF32 with the 3xTF32 split (a*b ~ a_hi*b_hi + a_hi*b_lo + a_lo*b_hi, a_lo = a - tf32(a)): the trace
+// keeps fp32-level accuracy (~1e-6 relative) while the MACs run on the tensor cores.  CTA = 64 x 64 outputs x one K
+// slice, 4 warps x (32 x 32), operands staged through shared memory in 32-row chunks, partial sums merged with fp32 atomics.
+__device__ __forceinline__ uint32_t f2tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void mma_tf32_16x8x8(float* c, const uint32_t* a, const uint32_t* b) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+constexpr int TD_T = 64, TD_KC = 32, TD_LD = TD_T + 8;  // row pitch 72: fragment reads (k = t, col = g) hit 32 distinct banks
+
+__global__ void __launch_bounds__(128) trace_delta_mma_kernel(const float* __restrict__ pre, const float* __restrict__ post, long long ld, int K,
+                                                              int kper, float* __restrict__ delta_q, int N) {
+  __shared__ __align__(16) float Ps[TD_KC][TD_LD];
+  __shared__ __align__(16) float Qs[TD_KC][TD_LD];
+  const int i0 = blockIdx.y * TD_T, j0 = blockIdx.x * TD_T;
+  const int k_begin = blockIdx.z * kper, k_end = min(K, k_begin + kper);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int wi = (warp >> 1) * 32, wj = (warp & 1) * 32;  // this warp's 32 x 32 sub-tile
+  float acc[2][4][4];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[a][b][e] = 0.f;
+  float qsum = 0.f;
+  for (int k0 = k_begin; k0 < k_end; k0 += TD_KC) {
+    __syncthreads();
+    // stage 32 rows x 64 columns of pre (columns i0..) and post (columns j0..): coalesced along the row
+    for (int e = tid; e < TD_KC * TD_T; e += 128) {
+      const int k = e / TD_T, c = e - k * TD_T;
+      const bool kin = k0 + k < k_end;
+      Ps[k][c] = (kin && i0 + c < N) ? __ldg(pre + (size_t)(k0 + k) * ld + i0 + c) : 0.f;
+      Qs[k][c] = (kin && j0 + c < N) ? __ldg(post + (size_t)(k0 + k) * ld + j0 + c) : 0.f;
+    }
+    __syncthreads();
+    if (blockIdx.y == 0 && tid < TD_T) {  // q_j = sum_k post_kj^2, once per column tile
+#pragma unroll 8
+      for (int k = 0; k < TD_KC; ++k) qsum = fmaf(Qs[k][tid], Qs[k][tid], qsum);
+    }
+#pragma unroll
+    for (int kk = 0; kk < TD_KC; kk += 8) {
+      uint32_t ah[2][4], al[2][4], bh[4][2], bl[4][2];
+#pragma unroll
+      for (int a = 0; a < 2; ++a) {  // A = pre^T: A[m = i][k] = Ps[k][i]
+        const int m = wi + a * 16 + g;
+        const float v[4] = {Ps[kk + t][m], Ps[kk + t][m + 8], Ps[kk + t + 4][m], Ps[kk + t + 4][m + 8]};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          ah[a][e] = f2tf32(v[e]);
+          al[a][e] = f2tf32(v[e] - __uint_as_float(ah[a][e]));
+        }
+      }
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {  // B[k][n = j] = Qs[k][j]
+        const int n = wj + b * 8 + g;
+        const float v[2] = {Qs[kk + t][n], Qs[kk + t + 4][n]};
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          bh[b][e] = f2tf32(v[e]);
+          bl[b][e] = f2tf32(v[e] - __uint_as_float(bh[b][e]));
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          mma_tf32_16x8x8(acc[a][b], al[a], bh[b]);  // small terms first
+          mma_tf32_16x8x8(acc[a][b], ah[a], bl[b]);
+          mma_tf32_16x8x8(acc[a][b], ah[a], bh[b]);
+        }
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int i = i0 + wi + a * 16 + g + (e >> 1) * 8, j = j0 + wj + b * 8 + 2 * t + (e & 1);
+        if (i < N && j < N) atomicAdd(delta_q + (size_t)i * N + j, acc[a][b][e]);
+      }
+  if (blockIdx.y == 0 && tid < TD_T && j0 + tid < N) atomicAdd(delta_q + (size_t)N * N + j0 + tid, qsum);
+}
+
 __global__ void trace_apply_kernel(const float* __restrict__ hebb, const float* __restrict__ delta_q, int Kdiv,
                                    const float* __restrict__ eta_p, int rule, float* __restrict__ out, int N) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -374,6 +471,24 @@ int pu_trace_delta(const float* pre, const float* post, long long ld, int K, flo
   dim3 block(32, 8), grid(pu::cdiv(N, 32), pu::cdiv(N, 8));
   pu::trace_contract_kernel<<<grid, block, 0, pu::as_stream(stream)>>>(nullptr, pre, post, ld, K, nullptr, 0, nullptr, delta_q, N, K, 1);
   return pu::post_launch("pu_trace_delta");
+}
+
+int pu_trace_delta_tc(const float* pre, const float* post, long long ld, int K, float* delta_q, int N, void* stream) {
+  PU_REQUIRE(pre && post && delta_q && K > 0 && N > 0 && ld >= N, PU_ERR_BAD_ARG, "pu_trace_delta_tc: bad argument");
+  cudaStream_t st = pu::as_stream(stream);
+  cudaError_t e = cudaMemsetAsync(delta_q, 0, sizeof(float) * ((size_t)N * N + N), st);
+  if (e != cudaSuccess) {
+    pu::set_error("pu_trace_delta_tc memset: %s", cudaGetErrorString(e));
+    return PU_ERR_CUDA;
+  }
+  const int tiles = pu::cdiv(N, pu::TD_T);
+  int splits = pu::cdiv(2 * pu::kNumSMs, tiles * tiles);
+  int kper = pu::cdiv(K, splits);
+  kper = pu::cdiv(kper, pu::TD_KC) * pu::TD_KC;
+  splits = pu::cdiv(K, kper);
+  PU_REQUIRE(splits <= 65535, PU_ERR_UNSUPPORTED, "pu_trace_delta_tc: K too large");
+  pu::trace_delta_mma_kernel<<<dim3(tiles, tiles, splits), 128, 0, st>>>(pre, post, ld, K, kper, delta_q, N);
+  return pu::post_launch("pu_trace_delta_tc");
 }
 
 int pu_trace_apply(const float* hebb, const float* delta_q, int K_global, const float* eta, int rule, float* out, int N, void* stream) {

@@ -95,6 +95,11 @@ class _PlasticBase(nn.Module):
         self.rule = rule
         self.batched = batched
         self.conv_math = _default_math()
+        # 'row0' (default) = the reference: only row 0 of each map enters the trace (unet_p.py:82 keeps [0] of the bmm).
+        # 'all' (opt-in extension, no reference semantics): EVERY row of every map is a (pre, post) pair, K = B*nbf — the
+        # full contraction the reference's bmm computes before discarding all but one row — on the tensor cores; the trace
+        # is detached in this mode (as train.py:99 does every step anyway).
+        self.trace_rows = 'row0'
         self.premask = True   # TF32 mode: fold each ReLU mask into its consumers' backward epilogues (UNetp / UNetpCoord)
         self.dp_group = None  # set by pu_b200.dp.attach() for the data-parallel trace all-reduce
         self.dp_defer = False  # TrainStep: overlap the trace all-reduce with the backward pass (side stream)
@@ -136,10 +141,18 @@ class _PlasticBase(nn.Module):
             rule = ops.RULE_OJA
         else:
             raise ValueError("Must select one learning rule ('hebb' or 'oja')")
+        if self.trace_rows not in ('row0', 'all'):
+            raise ValueError("trace_rows must be 'row0' (reference) or 'all'")
+        all_rows = self.trace_rows == 'all'
+        if all_rows and not (self.dp_group is not None and self.dp_world > 1):
+            delta_q = ops.trace_delta_tc(X.detach(), S.detach(), N, N, B * N)
+            hebb_new = ops.trace_apply(hebb.detach(), delta_q, self.eta.detach(), rule, B * N)
+            return (S.view(N, N) if B == 1 else S.view(B, N, N)), hebb_new
         if self.dp_group is not None and self.dp_world > 1:
             import torch.distributed as dist
             # data-parallel: all-reduce (sum_k outer, sum_k post^2), then the identical epilogue on every rank
-            delta_q = ops.trace_delta(X.detach(), S.detach(), N, N * N, B)
+            delta_q = ops.trace_delta_tc(X.detach(), S.detach(), N, N, B * N) if all_rows else ops.trace_delta(X.detach(), S.detach(), N, N * N, B)
+            kloc = B * N if all_rows else B  # (pre, post) pairs of this rank
             if getattr(self, "dp_defer", False) and delta_q.is_cuda:
                 # The new trace is only needed at the end of the step: run its all-reduce + epilogue on a side stream so
                 # that they overlap the backward pass.  The caller (TrainStep) joins `self.dp_side` before it reads hebb_new.
@@ -149,12 +162,12 @@ class _PlasticBase(nn.Module):
                 self.dp_side.wait_stream(main)
                 with torch.cuda.stream(self.dp_side):
                     dist.all_reduce(delta_q, op=dist.ReduceOp.SUM, group=self.dp_group)
-                    hebb_new = ops.trace_apply(hebb.detach(), delta_q, self.eta.detach(), rule, B * self.dp_world)
+                    hebb_new = ops.trace_apply(hebb.detach(), delta_q, self.eta.detach(), rule, kloc * self.dp_world)
                 delta_q.record_stream(self.dp_side)
                 hebb_new.record_stream(main)
             else:
                 dist.all_reduce(delta_q, op=dist.ReduceOp.SUM, group=self.dp_group)
-                hebb_new = ops.trace_apply(hebb.detach(), delta_q, self.eta.detach(), rule, B * self.dp_world)
+                hebb_new = ops.trace_apply(hebb.detach(), delta_q, self.eta.detach(), rule, kloc * self.dp_world)
         else:
             # rows k of pre/post = row 0 of map k (reference keeps only [0] of the bmm)
             hebb_new = ops.trace_update(hebb, X, S, self.eta, rule, N * N, B)
@@ -190,6 +203,18 @@ class double_conv(nn.Module):
         forward epilogue (1 bit per element) and m0/m1 are the packed masks of sources that are such outputs.
         Returns the output tensor, or Masked(output, packed mask) when premask."""
         if self.batch_norm:
+            bn1, bn2 = self.conv[1], self.conv[4]
+            if not (bn1.training or bn2.training) and bn1.running_mean is not None and bn2.running_mean is not None \
+                    and not torch.is_grad_enabled():
+                # eval mode (eval.py:79-80, infer.py:38-39 run under no_grad): BN folds into the conv weights and bias, the
+                # ReLU into the conv epilogue — conv + BN + ReLU is ONE kernel and no extra pass over the activations
+                Ho, Wo = (x0.shape[1], x0.shape[2]) if H is None else (H, W)
+                w1, b1 = ops.bn_fold_conv(self.conv[0].weight, self.conv[0].bias, bn1.weight, bn1.bias, bn1.running_mean,
+                                          bn1.running_var, bn1.eps)
+                y = ops.conv3x3(x0, x1, w1, b1, None, True, Ho, Wo, off0[0], off0[1], off1[0], off1[1], math)
+                w2, b2 = ops.bn_fold_conv(self.conv[3].weight, self.conv[3].bias, bn2.weight, bn2.bias, bn2.running_mean,
+                                          bn2.running_var, bn2.eps)
+                return ops.conv3x3(y, None, w2, b2, None, True, Ho, Wo, 0, 0, 0, 0, math)
             y = _c3(x0, self.conv[0], False, x1=x1, H=H, W=W, off0=off0, off1=off1, math=math)
             y = _bn(y, self.conv[1], True, math)
             y = _c3(y, self.conv[3], False, math=math)

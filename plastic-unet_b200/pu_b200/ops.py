@@ -864,6 +864,24 @@ def _bn_backward(ctx, dy, _dmean, _dinvstd):
 batchnorm.register_autograd(_bn_backward, setup_context=_bn_setup)
 
 
+@torch.library.custom_op("pu::bn_fold_conv", mutates_args=())
+def bn_fold_conv(weight: Tensor, bias: Optional[Tensor], gamma: Tensor, beta: Tensor, running_mean: Tensor, running_var: Tensor,
+                 eps: float) -> Tuple[Tensor, Tensor]:
+    """Eval-mode BatchNorm folded into the conv in front of it -> (w', b') (forward only: no autograd formula)."""
+    _chk(weight, bias, gamma, beta, running_mean, running_var)
+    Cout = weight.shape[0]
+    w2 = torch.empty_like(weight)
+    b2 = torch.empty(Cout, device=weight.device, dtype=torch.float32)
+    _lib.call("pu_bn_fold_conv", weight.data_ptr(), _p(bias), gamma.data_ptr(), beta.data_ptr(), running_mean.data_ptr(),
+              running_var.data_ptr(), float(eps), w2.data_ptr(), b2.data_ptr(), Cout, weight.numel() // Cout, _s())
+    return w2, b2
+
+
+@bn_fold_conv.register_fake
+def _(weight, bias, gamma, beta, running_mean, running_var, eps):
+    return torch.empty_like(weight), weight.new_empty(weight.shape[0])
+
+
 # =================================================================================================
 # layout
 # =================================================================================================
@@ -1058,6 +1076,22 @@ def trace_delta(pre: Tensor, post: Tensor, N: int, ld: int, K: int) -> Tensor:
 
 
 @trace_delta.register_fake
+def _(pre, post, N, ld, K):
+    return pre.new_empty(N * N + N)
+
+
+@torch.library.custom_op("pu::trace_delta_tc", mutates_args=())
+def trace_delta_tc(pre: Tensor, post: Tensor, N: int, ld: int, K: int) -> Tensor:
+    """trace_delta on the tensor cores (3xTF32 mma.sync split-K GEMM) for large K (rows='all': K = B*N)."""
+    _chk(pre, post)
+    if pre.numel() < (K - 1) * ld + N or post.numel() < (K - 1) * ld + N:
+        raise RuntimeError("trace_delta_tc: pre/post too small for (K, ld)")
+    out = torch.empty(N * N + N, device=pre.device, dtype=torch.float32)
+    _lib.call("pu_trace_delta_tc", pre.data_ptr(), post.data_ptr(), ld, K, out.data_ptr(), N, _s())
+    return out
+
+
+@trace_delta_tc.register_fake
 def _(pre, post, N, ld, K):
     return pre.new_empty(N * N + N)
 

@@ -210,6 +210,41 @@ def test_eval_and_infer_calling_convention():
     assert rel_err(out, ref)[0] < TOL and mask.shape == (21, 21)
 
 
+@pytest.mark.parametrize("math", ["fp32", "tf32"])
+def test_eval_mode_batchnorm_is_folded_into_the_conv(math):
+    """net.eval() + no_grad (eval.py:79-80): conv + BatchNorm + ReLU of double_conv (unet_p.py:103-111) runs as ONE conv kernel
+    with folded weights; same outputs as the oracle's eval-mode forward, and no batchnorm kernel is launched."""
+    from pu_b200 import _lib
+    c = Case("unetp_bn_bilinear_n32")
+    net = build(c).eval()
+    net.conv_math = math
+    sd = c.state_dict()
+    # make the running statistics non-trivial
+    g = torch.Generator().manual_seed(3)
+    for k in sd:
+        if k.endswith("running_mean"):
+            sd[k] = 0.1 * torch.randn(sd[k].shape, generator=g)
+        if k.endswith("running_var"):
+            sd[k] = 0.5 + torch.rand(sd[k].shape, generator=g)
+    net.load_state_dict(sd)
+    hebb = c.t("hebb")
+    _, ref, hn_ref = orc.forward("unetp", sd, c.t("x"), hebb, rule=c.rule, batch_norm=True, bilinear=True, training=False)
+    with torch.no_grad():
+        before = _lib.launch_count()
+        out, hn = net(c.t("x", DEV), hebb.to(DEV))
+        launched = _lib.launch_count() - before
+        out_unfolded = None
+    with torch.enable_grad():  # the unfolded path (separate BN kernels) for comparison
+        before = _lib.launch_count()
+        out_unfolded, _ = net(c.t("x", DEV), hebb.to(DEV))
+        launched_unfolded = _lib.launch_count() - before
+    tol = TOL if math == "fp32" else TF32_OUT_TOL
+    assert rel_err(out, ref)[0] < tol and rel_err(hn, hn_ref)[0] < tol
+    assert rel_err(out, out_unfolded)[0] < tol
+    assert launched < launched_unfolded  # 18 BN launches replaced by 18 tiny weight folds... and the BN passes are gone
+    print("\n[bn fold %s] launches %d (folded) vs %d (separate BN kernels), out err %.2e" % (math, launched, launched_unfolded, rel_err(out, ref)[0]))
+
+
 def test_value_errors_like_reference():
     c = Case("unetp_hebb_n32")
     net = build(c)

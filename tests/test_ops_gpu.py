@@ -472,3 +472,72 @@ def test_pool_skip_accumulates_both_gradients(C, H, W, mask_in):
     p, s = ops.pool_skip(xc, mask_in)
     (s * R2).sum().backward()
     check(xc.grad, R2, 1e-7, what="skip only")
+
+
+@pytest.mark.parametrize("rule", ["hebb", "oja"])
+@pytest.mark.parametrize("N,B", [(128, 64), (101, 3), (32, 1), (64, 8)])
+def test_trace_rows_all_on_tensor_cores(rule, N, B):
+    """Opt-in rows='all' contraction (K = B*N pairs) on mma.sync with the 3xTF32 split vs the same update in float64:
+    fp32-level accuracy (the plain fp32 CUDA-core contraction of the row-0 mode is the comparison point)."""
+    from pu_b200 import ops
+    g = torch.Generator().manual_seed(N + B)
+    X = torch.randn(B * N, N, generator=g)
+    S = torch.sigmoid(torch.randn(B * N, N, generator=g))
+    hebb = 0.05 * torch.randn(N, N, generator=g)
+    eta = torch.tensor([0.03])
+    K = B * N
+    delta = X.double().t() @ S.double()
+    q = (S.double() ** 2).sum(0)
+    e = float(eta)
+    if rule == "hebb":
+        ref = (1 - e) * hebb.double() + e * delta / K
+    else:
+        ref = hebb.double() * (1 - e * q / K)[None, :] + e * delta / K
+    dq = ops.trace_delta_tc(X.to(DEV), S.to(DEV), N, N, K)
+    out = ops.trace_apply(hebb.to(DEV), dq, eta.to(DEV), ops.RULE_HEBB if rule == "hebb" else ops.RULE_OJA, K)
+    check(dq[:N * N].view(N, N), delta, 2e-6, what="delta (3xTF32)")
+    check(dq[N * N:], q, 2e-6, what="q")
+    check(out, ref, 2e-6, what="trace")
+    # the CUDA-core contraction gives the same payload
+    dq2 = ops.trace_delta(X.to(DEV), S.to(DEV), N, N, K)
+    check(dq, dq2, 5e-6, what="tensor-core vs CUDA-core payload")
+
+
+def test_model_trace_rows_all_mode():
+    """UNetp(trace_rows='all'): outputs unchanged, trace = mean over ALL rows of all maps of the reference's per-row outer
+    products (what unet_p.py:82's bmm holds before [0]); default 'row0' stays the reference."""
+    import pu_b200
+    import pu_b200.ops as ops_mod
+    from conftest import quiet
+    torch.manual_seed(1)
+    net = quiet(pu_b200.UNetp, 1, 1, torch.device(DEV), rule="hebb", nbf=32, batched=True)
+    g = torch.Generator().manual_seed(2)
+    x = torch.rand(3, 1, 32, 32, generator=g).to(DEV)
+    hebb = (0.05 * torch.randn(32, 32, generator=g)).to(DEV)
+    captured = {}
+    real = ops_mod.trace_delta_tc
+
+    def spy(pre, post, N, ld, K):
+        captured["X"], captured["S"], captured["K"] = pre.clone(), post.clone(), K
+        return real(pre, post, N, ld, K)
+
+    with torch.no_grad():
+        out0, h0 = net(x, hebb)
+        net.trace_rows = "all"
+        ops_mod.trace_delta_tc = spy
+        try:
+            out1, h1 = net(x, hebb)
+        finally:
+            ops_mod.trace_delta_tc = real
+        with pytest.raises(ValueError):
+            net.trace_rows = "bogus"
+            net(x, hebb)
+    assert torch.equal(out0, out1) and not torch.allclose(h0, h1)
+    # the reference's bmm over every row, bmm(activin.unsqueeze(2), activout.unsqueeze(1)) -> [N, N, N] per map (unet_p.py:82
+    # before the [0]); 'all' = (1 - eta) * hebb + eta * mean over all rows of all maps of those outer products
+    eta = float(net.eta)
+    X, S = captured["X"].cpu().double().view(3, 32, 32), captured["S"].cpu().double().view(3, 32, 32)
+    assert captured["K"] == 3 * 32 and torch.equal(captured["S"].view(3, 32, 32), out1)
+    outer = torch.stack([torch.bmm(X[b].unsqueeze(2), S[b].unsqueeze(1)) for b in range(3)])  # [B, N(rows), N, N]
+    ref = (1 - eta) * hebb.cpu().double() + eta * outer.mean(dim=(0, 1))
+    check(h1, ref, 2e-6, what="rows='all' trace")
