@@ -272,6 +272,13 @@ int pu_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg
  * copies every source tensor into flat[offset ...] with one launch (gradient tensors -> flat gradient arena). */
 int pu_gather_flat(const long long* table, int n, float* flat, void* stream);
 
+/* Input pipeline: batch assembly from a DEVICE-resident dataset src [n, planes, Hs, Ws] + zero padding
+ * to Hd x Wd at offset (oy, ox) in one pass: dst[b] = pad(src[idx[b]]).  idx: B int64 sample indices on the device.
+ * Replaces the per-step host conversion + H2D copy of reference train.py:94-95 (and defines the 101 -> 128 padding of
+ * BASELINE configs: oy = ox = 13).                                                                              */
+int pu_gather_pad(const float* src, const long long* idx, float* dst, int B, int planes, int Hs, int Ws, int Hd, int Wd, int oy, int ox,
+                  void* stream);
+
 /* elementwise helpers for autograd glue */
 int pu_add(const float* a, const float* b, float* out, long long n, void* stream);
 

@@ -59,6 +59,26 @@ __global__ void gather_flat_kernel(const long long* __restrict__ table, int n, f
     flat[off + i] = src[i];
 }
 
+// dst[b] = src[idx[b]] placed at (oy, ox) of a zero-filled Hd x Wd canvas: the device-resident dataset's batch assembly +
+// the 101 -> 128 zero padding of BASELINE configs[0..1] in one pass (reference train.py:94-95 converts and copies one
+// image per step from host numpy arrays; utils/data_set.py:43-44 holds them as float64 [n, 1, 101, 101]).
+__global__ void gather_pad_kernel(const float* __restrict__ src, const long long* __restrict__ idx, float* __restrict__ dst, int B,
+                                  long long plane_src, int Hs, int Ws, int Hd, int Wd, int oy, int ox, int planes) {
+  const long long n = (long long)B * planes * Hd * Wd;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % Wd);
+    long long r = i / Wd;
+    const int y = (int)(r % Hd);
+    r /= Hd;
+    const int c = (int)(r % planes);
+    const int b = (int)(r / planes);
+    const int sy = y - oy, sx = x - ox;
+    float v = 0.f;
+    if (sy >= 0 && sy < Hs && sx >= 0 && sx < Ws) v = __ldg(src + (idx[b] * planes + c) * plane_src + (long long)sy * Ws + sx);
+    dst[i] = v;
+  }
+}
+
 }  // namespace pu
 
 extern "C" {
@@ -82,6 +102,17 @@ int pu_gather_flat(const long long* table, int n, float* flat, void* stream) {
   dim3 grid(32, n);
   pu::gather_flat_kernel<<<grid, 256, 0, pu::as_stream(stream)>>>(table, n, flat);
   return pu::post_launch("pu_gather_flat");
+}
+
+int pu_gather_pad(const float* src, const long long* idx, float* dst, int B, int planes, int Hs, int Ws, int Hd, int Wd, int oy, int ox,
+                  void* stream) {
+  PU_REQUIRE(src && idx && dst && B > 0 && planes > 0 && Hs > 0 && Ws > 0 && oy >= 0 && ox >= 0 && oy + Hs <= Hd && ox + Ws <= Wd,
+             PU_ERR_BAD_ARG, "pu_gather_pad: bad argument (the %dx%d source must fit at (%d,%d) of the %dx%d canvas)", Hs, Ws, oy, ox, Hd, Wd);
+  const long long n = (long long)B * planes * Hd * Wd;
+  int g = (int)((n + 1023) / 1024);
+  g = g < 1 ? 1 : (g > 8 * pu::kNumSMs ? 8 * pu::kNumSMs : g);
+  pu::gather_pad_kernel<<<g, 256, 0, pu::as_stream(stream)>>>(src, idx, dst, B, (long long)Hs * Ws, Hs, Ws, Hd, Wd, oy, ox, planes);
+  return pu::post_launch("pu_gather_pad");
 }
 
 int pu_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* step_count, const float* lr, float beta1,

@@ -222,6 +222,15 @@ class TrainStep:
             self._step_body()
         return self.loss
 
+    def step_indices(self, dataset, idx):
+        """One optimisation step on samples `idx` ([B] int64; host or device) of a pu_b200.data.DeviceDataset: the batch is
+        gathered and zero-padded on the device (two launches), only B indices cross PCIe."""
+        if getattr(self, "_idx_dev", None) is None:
+            self._idx_dev = torch.zeros(self.batch, dtype=torch.int64, device=self.dev)
+        self._idx_dev.copy_(idx, non_blocking=True)
+        dataset.gather(self._idx_dev, self.x, self.target)
+        return self.step()
+
     # -------------------------------------------------------------------------------------------
     def prefetch(self, x, target):
         """Start the host->device copy of the NEXT batch on a copy stream; it overlaps the step that is running.
