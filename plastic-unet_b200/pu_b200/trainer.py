@@ -310,3 +310,11 @@ class InferStep:
             with torch.no_grad(), InferStep._eval_mode(self.net):
                 self.out, _ = self.net(self.x, self.hebb)
         return self.out
+
+    def predict_rle(self, x=None, mask_threshold=0.5, want_mask=False):
+        """infer.predict for a batch (infer.py:73-99): forward, `mask > mask_threshold`, column-major RLE strings — masks and
+        run lists are produced on the device (pu_b200.infer_tail), only the runs cross PCIe."""
+        from . import infer_tail
+        out = self.step(x)
+        out = out.view(-1, self.net.nbf, self.net.nbf)
+        return infer_tail.rle_encode_batch(out, mask_threshold, want_mask=want_mask)

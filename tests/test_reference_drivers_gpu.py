@@ -116,5 +116,6 @@ def test_gpu_inference_tail_matches_the_reference_drivers(drivers):
     step = InferStep(net, len(X), 32).capture()
     out = step.step(torch.from_numpy(X.astype(np.float32)).cuda())
     assert it.rle_encode_batch(out, 0.5) == rle_r
+    assert step.predict_rle(torch.from_numpy(X.astype(np.float32)).cuda(), 0.5) == rle_r  # the batched infer.predict
     thr, iou, _ = it.score_best_iou(out, torch.from_numpy(y.astype(np.float32)).cuda())
     assert thr == thr_r and iou == iou_r
