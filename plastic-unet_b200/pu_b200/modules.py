@@ -545,11 +545,14 @@ class coord_up(nn.Module):
         self.up = nn.ConvTranspose2d(in_ch, out_ch, 2, stride=2)
         self.conv = double_conv(2 * out_ch, out_ch, False)
 
-    def run(self, x1, x2, math):
-        u = ops.convT2x2s2(x1, self.up.weight, self.up.bias, math == ops.MATH_TF32)
+    def run(self, x1, x2, math, premask=False):
+        m2 = None
+        if premask:  # Masked inputs (see `up.run`): the transposed conv's dgrad masks with x1 itself, the skip brings its packed mask
+            x1, x2, m2 = x1.t, x2.t, x2.m
+        u = ops.convT2x2s2(x1, self.up.weight, self.up.bias, math == ops.MATH_TF32, premask)
         if u.shape[1] != x2.shape[1] or u.shape[2] != x2.shape[2]:
             raise RuntimeError("UNetpCoord needs H, W divisible by 16 (Keras 'same' padding has no crop)")
-        return self.conv.run(u, math, x1=x2)
+        return self.conv.run(u, math, x1=x2, m1=m2, premask=premask)
 
 
 class UNetpCoord(_PlasticBase):
@@ -576,11 +579,20 @@ class UNetpCoord(_PlasticBase):
             raise ValueError("Only batch size: 1 is supported, but was: %d" % x.shape[0])
         m = self._math
         x = self._to_nhwc(x)
-        feats = [self.enc0.run(self.stem.run(x, m), m)]
+        # premasked-gradient protocol + pool_skip as in UNetp.forward (the CoordConv stem keeps its own ReLU-mask pass: the
+        # 1x1 kernel emits no packed mask)
+        pm = (m == ops.MATH_TF32 and self.premask and self.outc.conv.weight.shape[1] in (8, 16, 32, 64) and self.n_classes == 1
+              and self.stem.conv.weight.shape[0] % 8 == 0)
+        feats = []
+        f = self.enc0.run(self.stem.run(x, m), m, premask=pm)
         for k in range(1, self.depth + 1):
-            feats.append(getattr(self, "enc%d" % k).run(feats[-1], m))
+            ft, fm = (f.t, f.m) if pm else (f, None)
+            pooled, skip = ops.pool_skip(ft, pm)
+            feats.append(Masked(skip, fm) if pm else skip)
+            f = getattr(self, "enc%d" % k).run_pooled(pooled, m, pm)
+        feats.append(f)
         y = feats[-1]
         for k in range(self.depth, 0, -1):
-            y = getattr(self, "dec%d" % k).run(y, feats[k - 1], m)
-        o = self.outc.run(y)
+            y = getattr(self, "dec%d" % k).run(y, feats[k - 1], m, pm)
+        o = self.outc.run(y, pm)
         return self._plastic(o, hebb)

@@ -302,6 +302,27 @@ def test_coord_variant_vs_oracle():
             assert rel_err(p.grad, sd[k].grad)[1] < 10 * TOL, k
 
 
+def test_coord_variant_tf32_mode_vs_oracle():
+    """UNetpCoord in the TF32 mode (premasked gradients, packed masks, pool_skip — config 3's benchmarked path) vs the oracle."""
+    from pu_b200 import UNetpCoord
+    torch.manual_seed(5)
+    net = quiet(UNetpCoord, 1, 1, DEV, rule="oja", nbf=64, batched=True)
+    net.conv_math = "tf32"
+    sd = orc.leaf_state({k: v.detach().cpu() for k, v in net.state_dict().items()})
+    g = torch.Generator().manual_seed(6)
+    x = torch.rand(4, 1, 64, 64, generator=g)
+    hebb = 0.05 * torch.randn(64, 64, generator=g)
+    target = (torch.rand(4 * 64 * 64, generator=g) > 0.5).float()
+    _, out_r, hn_r = orc.forward("unetpcoord", sd, x, hebb, rule="oja")
+    orc.bce_mean(out_r.reshape(-1), target).backward()
+    out, hn = net(x.to(DEV), hebb.to(DEV))
+    torch.nn.BCELoss()(out.reshape(-1), target.to(DEV)).backward()
+    assert rel_err(out, out_r)[0] < TF32_OUT_TOL and rel_err(hn, hn_r)[0] < TF32_OUT_TOL
+    worst = max((rel_err(p.grad, sd[k].grad)[1], k) for k, p in net.named_parameters() if sd[k].grad is not None)
+    print("\n[coord tf32] out %.2e trace %.2e worst gradient L2-rel %.2e (%s)" % (rel_err(out, out_r)[0], rel_err(hn, hn_r)[0], worst[0], worst[1]))
+    assert worst[0] < TF32_GRAD_TOL
+
+
 @pytest.mark.parametrize("kind", ["unetp", "unetpres"])
 def test_depth5_scaled_variant_vs_oracle(kind):
     from pu_b200 import UNetp, UNetpRes
