@@ -360,13 +360,14 @@ def build_net(model, dev, rule, size, depth=4, base=8, neurons=16, dropout=0.5):
     return net, name
 
 
-def timed_leg(model, dev, group, world, rule, size, B, math, steps, infer=False, pad_from=None, **kw):
+def timed_leg(model, dev, group, world, rule, size, B, math, steps, infer=False, pad_from=None, math_override=None, **kw):
     """A short measurement of another BASELINE config: -> dict(images_per_s (whole job), ms_per_step, ...)."""
     import torch.distributed as dist
     from pu_b200 import dp
     from pu_b200.trainer import InferStep, TrainStep
     torch.manual_seed(0)
     net, name = build_net(model, dev, rule, size, **kw)
+    math = math_override or math
     net.conv_math = math
     dp.attach(net, group)
     dp.broadcast_parameters(net, 0, group)
@@ -415,6 +416,10 @@ def run_extras(dev, group, world, math, steps=10):
     Oja, 32 per GPU = 256 on 8 GPUs); scaled 512x512 depth-5 Oja, training + inference."""
     legs = {}
     specs = [
+        # the headline workload in the other two math modes: strict fp32 (CUDA-core FFMA kernels: the mode that meets the 1e-3
+        # gradient parity) and mixed (strict-fp32 forward = exact ReLU masks, TF32 tensor-core backward)
+        ("config2_unetp_oja_128_strict_fp32_mode", dict(model="unetp", rule="oja", size=128, B=64, pad_from=101, math_override="fp32")),
+        ("config2_unetp_oja_128_mixed_mode", dict(model="unetp", rule="oja", size=128, B=64, pad_from=101, math_override="mixed")),
         ("config3_coordconv_oja_128", dict(model="coord", rule="oja", size=128, B=64, pad_from=101)),
         ("config4_res_n8_hebb_101", dict(model="res", rule="hebb", size=101, B=32, neurons=8)),
         ("config4_res_n8_oja_101", dict(model="res", rule="oja", size=101, B=32, neurons=8)),
@@ -493,7 +498,7 @@ def main():
     ap.add_argument("--batch", type=int, default=64, help="per-GPU batch")
     ap.add_argument("--size", type=int, default=128)
     ap.add_argument("--rule", default="oja")
-    ap.add_argument("--math", default=os.environ.get("PU_CONV_MATH", "tf32"), choices=["fp32", "tf32"])
+    ap.add_argument("--math", default=os.environ.get("PU_CONV_MATH", "tf32"), choices=["fp32", "tf32", "mixed"])
     ap.add_argument("--model", default="unetp", choices=["unetp", "res", "coord"], help="configs[1] is unetp; the others are the variants of configs[2..4]")
     ap.add_argument("--neurons", type=int, default=16)
     ap.add_argument("--depth", type=int, default=4)
@@ -677,7 +682,7 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_med / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "tf32" if args.math == "tf32" else "f32", "data": "synthetic",
+            "dtype": {"tf32": "tf32", "mixed": "f32 forward / tf32 backward", "fp32": "f32"}[args.math], "data": "synthetic",
             "config": {"workload": "%s %s rule, %s, batch %d per GPU, %s"
                                    % (model_name, args.rule, "1x101x101 zero-padded to 128x128" if args.size == 128 else "1x%dx%d" % (args.size, args.size),
                                       B, "batched inference (forward, zero trace)" if args.infer else "fwd+BCE+bwd+Adam+trace update"),

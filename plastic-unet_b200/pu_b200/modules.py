@@ -21,13 +21,14 @@ import torch.nn as nn
 
 from . import ops
 
-_MATH = {"fp32": ops.MATH_FP32, "tf32": ops.MATH_TF32}
+_MATH = {"fp32": ops.MATH_FP32, "tf32": ops.MATH_TF32, "mixed": ops.MATH_MIXED}
+_TC_BWD = (ops.MATH_TF32, ops.MATH_MIXED)  # modes whose backward runs on the tensor cores (premasked-gradient protocol)
 
 
 def _default_math() -> str:
     m = os.environ.get("PU_CONV_MATH", "fp32").lower()
     if m not in _MATH:
-        raise ValueError("PU_CONV_MATH must be 'fp32' or 'tf32'")
+        raise ValueError("PU_CONV_MATH must be 'fp32', 'tf32' or 'mixed'")
     return m
 
 
@@ -269,7 +270,8 @@ class up(nn.Module):
         m2 = None
         if premask:  # Masked inputs: x1 (deep tensor; the transposed conv's dgrad masks with x1 itself), x2 (skip) with its packed mask
             x1, x2, m2 = x1.t, x2.t, x2.m
-        u = ops.bilinear2x(x1) if self.bilinear else ops.convT2x2s2(x1, self.up.weight, self.up.bias, math == ops.MATH_TF32, premask)
+        u = ops.bilinear2x(x1) if self.bilinear else ops.convT2x2s2(x1, self.up.weight, self.up.bias, math == ops.MATH_TF32, premask,
+                                                                    math == ops.MATH_MIXED)
         diffX = u.shape[1] - x2.shape[1]  # reference names: size()[2] == H
         diffY = u.shape[2] - x2.shape[2]
         # F.pad(x2, (diffX//2, int(diffX/2), diffY//2, int(diffY/2))): first pair pads W, second pair pads H
@@ -323,7 +325,7 @@ class UNetp(_PlasticBase):
         m = self._math
         x = self._to_nhwc(x)
         # premasked-gradient protocol (backward only, TF32 mode without BN / bilinear / ragged output conv): see DESIGN.md 4.2
-        pm = (m == ops.MATH_TF32 and self.premask and not self.inc.conv.batch_norm and not self.up1.bilinear
+        pm = (m in _TC_BWD and self.premask and not self.inc.conv.batch_norm and not self.up1.bilinear
               and self.outc.conv.weight.shape[1] in (8, 16, 32, 64) and self.n_classes == 1 and self.n_channels == 1)
         # each encoder level output feeds the pool of the next level AND a skip connection: ops.pool_skip returns both so
         # that the two gradients are summed inside the pooling backward kernel (no separate accumulation pass)
@@ -549,7 +551,7 @@ class coord_up(nn.Module):
         m2 = None
         if premask:  # Masked inputs (see `up.run`): the transposed conv's dgrad masks with x1 itself, the skip brings its packed mask
             x1, x2, m2 = x1.t, x2.t, x2.m
-        u = ops.convT2x2s2(x1, self.up.weight, self.up.bias, math == ops.MATH_TF32, premask)
+        u = ops.convT2x2s2(x1, self.up.weight, self.up.bias, math == ops.MATH_TF32, premask, math == ops.MATH_MIXED)
         if u.shape[1] != x2.shape[1] or u.shape[2] != x2.shape[2]:
             raise RuntimeError("UNetpCoord needs H, W divisible by 16 (Keras 'same' padding has no crop)")
         return self.conv.run(u, math, x1=x2, m1=m2, premask=premask)
@@ -581,7 +583,7 @@ class UNetpCoord(_PlasticBase):
         x = self._to_nhwc(x)
         # premasked-gradient protocol + pool_skip as in UNetp.forward (the CoordConv stem keeps its own ReLU-mask pass: the
         # 1x1 kernel emits no packed mask)
-        pm = (m == ops.MATH_TF32 and self.premask and self.outc.conv.weight.shape[1] in (8, 16, 32, 64) and self.n_classes == 1
+        pm = (m in _TC_BWD and self.premask and self.outc.conv.weight.shape[1] in (8, 16, 32, 64) and self.n_classes == 1
               and self.stem.conv.weight.shape[0] % 8 == 0)
         feats = []
         f = self.enc0.run(self.stem.run(x, m), m, premask=pm)

@@ -66,6 +66,9 @@ def _side_stream():
 
 
 MATH_TF32_FLAT = 2  # pu_pack_w3x3 only
+# Python-level mode (never passed to the C-ABI): strict-fp32 FORWARD kernels (exact activations and ReLU masks), TF32
+# tensor-core BACKWARD kernels (tcgen05 dgrad, mma.sync wgrad / transposed convs) — see DESIGN.md §2
+MATH_MIXED = 4
 
 
 @functools.lru_cache(maxsize=None)
@@ -224,7 +227,7 @@ def conv3x3_bwd(dy: Tensor, y: Tensor, x0: Tensor, x1: Optional[Tensor], weight:
     H1, W1, C1 = _dims(x1)
     npix = B * H * W
     db = torch.empty(Cout, device=dev, dtype=torch.float32) if has_bias else _e(dev)
-    tf32 = math == MATH_TF32
+    tf32 = math in (MATH_TF32, MATH_MIXED)
     premasked = premasked and relu
     fresh_g = (relu or tf32) and not premasked  # tensor-core operands are stored rounded to TF32 by their producer
     db_in_wgrad = premasked and has_bias and need_dw
@@ -267,7 +270,8 @@ def conv3x3_bwd(dy: Tensor, y: Tensor, x0: Tensor, x1: Optional[Tensor], weight:
             with torch.cuda.stream(side):
                 dw = torch.empty_like(weight)
                 _lib.call("pu_conv3x3_wgrad", x0.data_ptr(), H0, W0, C0, oy0, ox0, _p(x1), H1, W1, C1, oy1, ox1,
-                          g.data_ptr(), dw.data_ptr(), db.data_ptr() if db_in_wgrad else None, B, H, W, Cout, math, _s())
+                          g.data_ptr(), dw.data_ptr(), db.data_ptr() if db_in_wgrad else None, B, H, W, Cout,
+                          MATH_TF32 if tf32 else MATH_FP32, _s())
             for t in (x0, x1, g, db if db_in_wgrad else None):
                 if t is not None:
                     t.record_stream(side)
@@ -276,7 +280,8 @@ def conv3x3_bwd(dy: Tensor, y: Tensor, x0: Tensor, x1: Optional[Tensor], weight:
         else:
             dw = torch.empty_like(weight)
             _lib.call("pu_conv3x3_wgrad", x0.data_ptr(), H0, W0, C0, oy0, ox0, _p(x1), H1, W1, C1, oy1, ox1,
-                      g.data_ptr(), dw.data_ptr(), db.data_ptr() if db_in_wgrad else None, B, H, W, Cout, math, _s())
+                      g.data_ptr(), dw.data_ptr(), db.data_ptr() if db_in_wgrad else None, B, H, W, Cout,
+                      MATH_TF32 if tf32 else MATH_FP32, _s())
     g_out = g if fresh_g else _e(dev)  # never return an alias of an input
     return [g_out, dx0, dx1, dw, db]
 
@@ -285,7 +290,7 @@ def conv3x3_bwd(dy: Tensor, y: Tensor, x0: Tensor, x1: Optional[Tensor], weight:
 def _(dy, y, x0, x1, weight, has_bias, relu, H, W, oy0, ox0, oy1, ox1, math, need_dx, need_dw, m0=None, m1=None,
       premasked=False):
     e = dy.new_empty(0)
-    return [torch.empty_like(dy) if ((relu or math == MATH_TF32) and not (premasked and relu)) else e,
+    return [torch.empty_like(dy) if ((relu or math in (MATH_TF32, MATH_MIXED)) and not (premasked and relu)) else e,
             torch.empty_like(x0) if need_dx else e,
             torch.empty_like(x1) if (need_dx and x1 is not None) else e,
             torch.empty_like(weight) if need_dw else e,
@@ -312,7 +317,7 @@ def _conv3x3_backward(ctx, dy, _dmask=None):
                                       need_dx, need[2], m0, m1, premasked)
     gres = None
     if has_res and need[4]:
-        gres = g if ((relu or math == MATH_TF32) and not (premasked and relu)) else dy
+        gres = g if ((relu or math in (MATH_TF32, MATH_MIXED)) and not (premasked and relu)) else dy
     return (dx0 if need[0] else None, dx1 if (x1 is not None and need[1]) else None, dw if need[2] else None,
             db if (has_bias and need[3]) else None, gres, None, None, None, None, None, None, None, None, None, None, None, None)
 
@@ -388,7 +393,10 @@ conv1x1.register_autograd(_conv1x1_backward, setup_context=_conv1x1_setup)
 # transposed convolutions
 # =================================================================================================
 @torch.library.custom_op("pu::convT2x2s2", mutates_args=())
-def convT2x2s2(x: Tensor, weight: Tensor, bias: Optional[Tensor], round_out: bool = False, mask_in: bool = False) -> Tensor:
+def convT2x2s2(x: Tensor, weight: Tensor, bias: Optional[Tensor], round_out: bool = False, mask_in: bool = False,
+               bwd_tf32: bool = False) -> Tensor:
+    """round_out: the model's TF32 mode (TF32 forward math, output rounded, TF32 backward); bwd_tf32: MIXED mode (strict-fp32
+    forward, TF32 mma.sync backward)."""
     _chk(x, weight, bias)
     B, H, W, Cin = x.shape
     Cout = weight.shape[1]
@@ -399,7 +407,7 @@ def convT2x2s2(x: Tensor, weight: Tensor, bias: Optional[Tensor], round_out: boo
 
 
 @convT2x2s2.register_fake
-def _(x, weight, bias, round_out=False, mask_in=False):
+def _(x, weight, bias, round_out=False, mask_in=False, bwd_tf32=False):
     return x.new_empty((x.shape[0], 2 * x.shape[1], 2 * x.shape[2], weight.shape[1]))
 
 
@@ -442,18 +450,18 @@ def _(dy, x, weight, need_dx, need_dw, need_db, mask_in=False, tf32=False):
 
 
 def _convT2_setup(ctx, inputs, output):
-    x, weight, bias, round_out, mask_in = inputs
+    x, weight, bias, round_out, mask_in, bwd_tf32 = inputs
     ctx.save_for_backward(x, weight)
     ctx.has_bias = bias is not None
     ctx.mask_in = mask_in
-    ctx.tf32 = bool(round_out)
+    ctx.tf32 = bool(round_out) or bool(bwd_tf32)
 
 
 def _convT2_backward(ctx, dy):
     x, weight = ctx.saved_tensors
     need = ctx.needs_input_grad
     dx, dw, db = convT2x2s2_bwd(dy.contiguous(), x, weight, need[0], need[1], ctx.has_bias and need[2], ctx.mask_in, ctx.tf32)
-    return dx if need[0] else None, dw if need[1] else None, db if (ctx.has_bias and need[2]) else None, None, None
+    return dx if need[0] else None, dw if need[1] else None, db if (ctx.has_bias and need[2]) else None, None, None, None
 
 
 convT2x2s2.register_autograd(_convT2_backward, setup_context=_convT2_setup)
