@@ -106,6 +106,11 @@ class _PlasticBase(nn.Module):
         self.dp_defer = False  # TrainStep: overlap the trace all-reduce with the backward pass (side stream)
         self.dp_side = None
         self.dp_world = 1
+        # TrainStep (data parallel): a callback fired in the backward pass once the gradient w.r.t. the input of encoder level
+        # `_bucket_level` exists, i.e. when every parameter gradient of the decoder and of the deeper encoder levels has been
+        # launched — the trainer all-reduces that bucket on a communication stream while the shallow levels still run
+        self._bucket_hook = None
+        self._bucket_level = 0
         # same creation order and RNG consumption as the reference (unet_p.py:30-32)
         self.w = torch.nn.Parameter((.01 * torch.randn(self.nbf, self.nbf, device=self.torch_dev)), requires_grad=True)
         self.alpha = torch.nn.Parameter((.01 * torch.rand(self.nbf, self.nbf, device=self.torch_dev)), requires_grad=True)
@@ -334,6 +339,8 @@ class UNetp(_PlasticBase):
         for k in range(1, self.depth + 1):
             ft, fm = (f.t, f.m) if pm else (f, None)
             pooled, skip = ops.pool_skip(ft, pm)
+            if self._bucket_hook is not None and k == self._bucket_level and pooled.requires_grad:
+                pooled.register_hook(self._bucket_hook)
             feats.append(Masked(skip, fm) if pm else skip)
             f = getattr(self, "down%d" % k).run_pooled(pooled, m, pm)
         feats.append(f)

@@ -31,6 +31,18 @@ class TrainStep:
         self.betas, self.eps = betas, eps
         params = [p for p in net.parameters()]
         total = sum(p.numel() for p in params)
+        # Data parallel: two gradient buckets.  The parameters of the shallow encoder levels (inc, down1 .. down{L-1}) get their
+        # gradients LAST in the backward pass; everything else (head, decoder, deep encoder levels: ~90 % of the bytes) is
+        # complete when the gradient w.r.t. the input of level L exists, and is all-reduced on a communication stream while
+        # the shallow levels still run.  The arena is ordered [early bucket | late bucket].
+        self._late = set()
+        self._bucket_level = 0
+        if self.dp_group is not None and hasattr(net, "_bucket_hook") and type(net).__name__ == "UNetp" and getattr(net, "depth", 0) >= 3 \
+                and os.environ.get("PU_DP_BUCKETS", "1") != "0":
+            self._bucket_level = net.depth - 1
+            late_prefixes = ("inc.",) + tuple("down%d." % j for j in range(1, self._bucket_level))
+            self._late = {id(p) for n_, p in net.named_parameters() if n_.startswith(late_prefixes)}
+            params = [p for p in params if id(p) not in self._late] + [p for p in params if id(p) in self._late]
         # ---- flat arenas (32-byte aligned slots: the conv epilogues read biases with 256-bit loads)
         self.offsets = []
         off = 0
@@ -38,6 +50,10 @@ class TrainStep:
             self.offsets.append(off)
             off += (p.numel() + 7) // 8 * 8
         self.n_flat = off
+        self.split = next((o for p, o in zip(params, self.offsets) if id(p) in self._late), off)  # first float of the late bucket
+        self._comm = torch.cuda.Stream() if self._late else None
+        self._early_done = False
+        self._grad_params = None  # learnt by the first eager step: which parameters receive a gradient at all
         self.flat_p = torch.zeros(off, device=self.dev)
         self.flat_g = torch.zeros(off, device=self.dev)
         self.m = torch.zeros(off, device=self.dev)
@@ -50,6 +66,8 @@ class TrainStep:
         # (pointer, offset, size) table of the gradient tensors, rebuilt by every eager/captured step body
         self.table_host = torch.zeros((len(params), 3), dtype=torch.int64).pin_memory()
         self.table_dev = torch.zeros((len(params), 3), dtype=torch.int64, device=self.dev)
+        self.table2_host = torch.zeros((len(params), 3), dtype=torch.int64).pin_memory()  # the early bucket's table
+        self.table2_dev = torch.zeros((len(params), 3), dtype=torch.int64, device=self.dev)
         self.n_params = total
         self.step_count = torch.zeros(1, device=self.dev)
         self.lr = torch.full((1,), float(lr), device=self.dev)
@@ -113,7 +131,40 @@ class TrainStep:
             if self._pack_stream is not None:
                 torch.cuda.current_stream().wait_stream(self._pack_stream)  # join (needed under graph capture)
 
+    def _gather(self, which, table_host, table_dev):
+        """One-launch gather of the gradients of the parameters selected by `which(p)` into their flat_g slots."""
+        n = 0
+        for p, o in zip(self.params, self.offsets):
+            if p.grad is not None and which(p):
+                g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
+                table_host[n, 0], table_host[n, 1], table_host[n, 2] = g.data_ptr(), o, g.numel()
+                n += 1
+        if n:
+            table_dev.copy_(table_host, non_blocking=torch.cuda.is_current_stream_capturing())
+            _lib.call("pu_gather_flat", table_dev.data_ptr(), n, self.flat_g.data_ptr(), torch.cuda.current_stream().cuda_stream)
+
+    def _early_reduce(self, _grad):
+        """Backward hook (modules.UNetp.forward): the early bucket is complete -> gather + all-reduce it on the communication
+        stream, concurrently with the rest of the backward pass.  Falls back to the single all-reduce if a gradient of the
+        bucket has not been handed over yet."""
+        early = [p for p in self.params if id(p) not in self._late and id(p) in self._grad_params]
+        if any(p.grad is None for p in early):
+            return None
+        main = torch.cuda.current_stream()
+        self._comm.wait_stream(main)
+        for sd in (self.wgrad_side or []):
+            self._comm.wait_stream(sd)  # their weight-gradient kernels write the tensors gathered below
+        with torch.cuda.stream(self._comm):
+            self._gather(lambda p: id(p) not in self._late, self.table2_host, self.table2_dev)
+            dist.all_reduce(self.flat_g[:self.split], op=dist.ReduceOp.SUM, group=self.dp_group)
+        self._early_done = True
+        return None
+
     def _fwd_bwd(self, st):
+        self._early_done = False
+        self.net._bucket_hook = self._early_reduce if (self._late and self._grad_params is not None) else None
+        if self._late:
+            self.net._bucket_level = self._bucket_level
         out, hebb_new = self.net(self.x, self.hebb)
         gS = torch.empty_like(out)
         n = out.numel()
@@ -142,16 +193,17 @@ class TrainStep:
                 torch.cuda.current_stream().wait_stream(sd)  # join the side-stream parameter gradients
         # gather every parameter gradient into the flat arena with one launch (parameters without a gradient, e.g.
         # eta in the reference loop, keep their zeroed slot)
-        n = 0
-        for p, o in zip(self.params, self.offsets):
-            if p.grad is not None:
-                g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
-                self.table_host[n, 0], self.table_host[n, 1], self.table_host[n, 2] = g.data_ptr(), o, g.numel()
-                n += 1
-        self.table_dev.copy_(self.table_host, non_blocking=torch.cuda.is_current_stream_capturing())
-        _lib.call("pu_gather_flat", self.table_dev.data_ptr(), n, self.flat_g.data_ptr(), st)
-        if self.dp_group is not None:
-            dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.dp_group)
+        self.net._bucket_hook = None
+        if self._grad_params is None:
+            self._grad_params = {id(p) for p in self.params if p.grad is not None}
+        if self._early_done:
+            self._gather(lambda p: id(p) in self._late, self.table_host, self.table_dev)
+            dist.all_reduce(self.flat_g[self.split:], op=dist.ReduceOp.SUM, group=self.dp_group)
+            torch.cuda.current_stream().wait_stream(self._comm)  # the early bucket's all-reduce
+        else:
+            self._gather(lambda p: True, self.table_host, self.table_dev)
+            if self.dp_group is not None:
+                dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.dp_group)
         if getattr(self.net, "dp_side", None) is not None:
             # join the deferred trace all-reduce + epilogue BEFORE the optimizer rewrites the arena (the epilogue reads eta)
             torch.cuda.current_stream().wait_stream(self.net.dp_side)
