@@ -102,15 +102,22 @@ __global__ void __launch_bounds__(256) gemm_chunk_kernel(const float* __restrict
     g2_stage<G2_BN>(Bs, Bm, sbn, sbk, n_blk, k0, N, k_end, vecB != 0);
     __syncthreads();
     const int kn = min(G2_BK, k_end - k0);
+    // software-pipelined k loop: the fragments of step k+1 are requested from shared memory before the 16 FMAs of step k
+    // (a CTA has only two warps per scheduler; without this every step paid the full LDS latency)
+    float4 a = *reinterpret_cast<const float4*>(As + ty * 4);
+    float4 b = *reinterpret_cast<const float4*>(Bs + tx * 4);
 #pragma unroll 8
     for (int k = 0; k < kn; ++k) {
-      const float4 a = *reinterpret_cast<const float4*>(As + k * LD + ty * 4);
-      const float4 b = *reinterpret_cast<const float4*>(Bs + k * LD + tx * 4);
+      const int kp = k + 1 < G2_BK ? k + 1 : k;  // the row after the last valid one is still inside the tile
+      const float4 an = *reinterpret_cast<const float4*>(As + kp * LD + ty * 4);
+      const float4 bn = *reinterpret_cast<const float4*>(Bs + kp * LD + tx * 4);
       const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+      a = an;
+      b = bn;
     }
   }
 #pragma unroll
@@ -141,6 +148,9 @@ static int launch_gemm_chunk(const float* A, long long sam, long long sak, const
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_chunk_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM);
+    // three 68 KB CTAs per SM: ask for the largest shared-memory carve-out (the default picks one that fits a single CTA,
+    // which left the 256-CTA head GEMM at two waves of one latency-bound CTA per SM: 15 us for 0.27 GFLOP)
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_chunk_kernel<EPI>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     if (e != cudaSuccess) {
       set_error("%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
       return PU_ERR_CUDA;

@@ -62,7 +62,7 @@ def oracle_run(kind, ctor_kw, body_kw, size, B, steps, lr, pad_from):
     return out
 
 
-def run_trainstep(kind, ctor_kw, sd0, batches, size, B, lr, math, use_graph=True, side=2, host_inputs=False):
+def run_trainstep(kind, ctor_kw, sd0, batches, size, B, lr, math, use_graph=True, side=4, host_inputs=False):
     import pu_b200
     from pu_b200.trainer import TrainStep
     cls = {"unetp": pu_b200.UNetp, "unetpres": pu_b200.UNetpRes}[kind]
@@ -118,7 +118,7 @@ CASES = {
 @pytest.mark.parametrize("math", ["fp32", "tf32", "mixed"])
 @pytest.mark.parametrize("case", list(CASES))
 def test_trainstep_vs_oracle(case, math):
-    """The captured step as bench.py runs it (graph on, 2 wgrad side streams) over K steps vs the oracle loop."""
+    """The captured step as bench.py runs it (graph on, 4 wgrad side streams) over K steps vs the oracle loop."""
     kind, ctor_kw, body_kw, size, B, steps, lr, pad_from = CASES[case]
     if math == "mixed" and kind != "unetp":
         pytest.skip("the mixed mode is wired for UNetp / UNetpCoord")
@@ -138,16 +138,16 @@ def test_trainstep_vs_oracle(case, math):
 
 @pytest.mark.parametrize("math", ["fp32", "tf32"])
 def test_trainstep_graph_and_side_streams_do_not_change_the_result(math):
-    """CUDA graph on/off and weight gradients on 0 / 2 side streams: same trajectory up to the run-to-run bound of the
+    """CUDA graph on/off and weight gradients on 0 / 2 / 4 side streams: same trajectory up to the run-to-run bound of the
     fp32 atomics in the weight-gradient reductions (documented non-determinism)."""
     kind, ctor_kw, body_kw, size, B, steps, lr, pad_from = CASES["unetp_oja_64_b8"]
     sd0, sd_ref, losses_ref, hebb_ref, batches = oracle_run(kind, ctor_kw, body_kw, size, B, steps, lr, pad_from)
-    base_net, base_ts, base_losses = run_trainstep(kind, ctor_kw, sd0, batches, size, B, lr, math, use_graph=True, side=2)
+    base_net, base_ts, base_losses = run_trainstep(kind, ctor_kw, sd0, batches, size, B, lr, math, use_graph=True, side=4)
     base_sd = {k: p.detach().cpu() for k, p in base_net.named_parameters()}
-    for use_graph, side, host in ((False, 0, False), (False, 2, False), (True, 0, False), (True, 2, True)):
+    for use_graph, side, host in ((False, 0, False), (False, 2, False), (True, 0, False), (True, 2, True), (False, 4, True)):
         net, ts, losses = run_trainstep(kind, ctor_kw, sd0, batches, size, B, lr, math, use_graph=use_graph, side=side, host_inputs=host)
         e_upd, worst = update_err(net, sd0, base_sd)
-        print("\n[graph=%s side=%d host=%s %s] update vs (graph, 2 side streams): %.2e, losses %s" % (use_graph, side, host, math, e_upd, losses))
+        print("\n[graph=%s side=%d host=%s %s] update vs (graph, 4 side streams): %.2e, losses %s" % (use_graph, side, host, math, e_upd, losses))
         assert max(abs(a - b) for a, b in zip(losses, base_losses)) < 2e-6
         assert rel_err(ts.hebb, base_ts.hebb)[0] < (1e-5 if math == "fp32" else 1e-4)  # a last-bit difference can flip a TF32 rounding
         assert e_upd < 2e-3, worst
