@@ -278,7 +278,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const __grid_
     return t;
   };
 
-  pdl_prologue();
+  // Programmatic dependent launch (PU_PDL=1): let the NEXT kernel's CTAs be scheduled as soon as ours exist; our own wait
+  // for the predecessor grid (pdl_wait below) sits AFTER the prologue — barrier init, TMEM allocation, tensor-map prefetch,
+  // the in-kernel weight-tile build and the bias load touch only parameters (written by the optimizer, many kernels ago),
+  // so they overlap the predecessor's tail.  Every role waits before its first access to activation / gradient memory.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  auto pdl_wait = [&]() { asm volatile("griddepcontrol.wait;" ::: "memory"); };
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int coblk = blockIdx.y;
   const int co_base = coblk * kCoBlk;
@@ -404,6 +409,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const __grid_
     // (experiment) prologue only
   } else if (warp == 0) {
     // ================= TMA producer =================
+    pdl_wait();
     const uint8_t* wblk = reinterpret_cast<const uint8_t*>(a.wpk) + (size_t)coblk * a.w_coblk_stride;
     int tile_next = blockIdx.x;  // lane 0: the tile drawn one iteration ahead (the atomic's round trip hides behind the loads)
     for (int k = 0;; ++k) {
@@ -627,6 +633,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const __grid_
     // bytes prefetched before the accumulators are ready stay in registers)
     constexpr int kMaxI = (256 / NACC + kEpiSets - 1) / kEpiSets;
 
+    pdl_wait();
     uint32_t tcount = 0;
     for (;; ++tcount) {
       const int tile = next_tile((int)tcount);
