@@ -55,14 +55,21 @@ class Masked:
 
 
 def _bn(x, bn, relu, math=ops.MATH_FP32):
-    """BatchNorm2d over NHWC with the parameters/buffers held by `bn` (+ optional fused ReLU)."""
-    train = bn.training or (bn.running_mean is None)
-    if train and bn.track_running_stats and bn.num_batches_tracked is not None:
-        bn.num_batches_tracked.add_(1)
+    """BatchNorm2d over NHWC with the parameters/buffers held by `bn` (+ optional fused ReLU).  Follows nn.BatchNorm2d:
+    batch statistics when training or when no running statistics are kept; momentum=None = cumulative moving average."""
+    track = bn.track_running_stats and bn.running_mean is not None
+    train = bn.training or not track
     momentum = 0.1 if bn.momentum is None else bn.momentum
-    y, mean, invstd = ops.batchnorm(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, train, momentum, bn.eps, relu,
-                                    math == ops.MATH_TF32)
-    if train and bn.track_running_stats:
+    if train and track and bn.training and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+        if bn.momentum is None:  # exponential_average_factor = 1 / num_batches_tracked
+            momentum = 1.0 / float(bn.num_batches_tracked)
+    C = x.shape[-1]
+    # the op schema takes tensors: placeholders when the module keeps no running statistics (never read in that case)
+    rm = bn.running_mean if track else x.new_zeros(C)
+    rv = bn.running_var if track else x.new_ones(C)
+    y, mean, invstd = ops.batchnorm(x, bn.weight, bn.bias, rm, rv, train, momentum, bn.eps, relu, math == ops.MATH_TF32)
+    if train and track and bn.training:
         ops.bn_update_running(mean.detach(), invstd.detach(), bn.running_mean, bn.running_var, momentum, bn.eps,
                               x.numel() // x.shape[-1])
     return y

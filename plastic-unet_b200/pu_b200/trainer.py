@@ -26,8 +26,6 @@ class TrainStep:
         self.batch = batch
         self.world = dist.get_world_size(dp_group) if (dist.is_initialized() and dp_group is not None) else 1
         self.dp_group = dp_group if self.world > 1 else None
-        if self.dp_group is not None:
-            net.dp_defer = True  # the trace delta all-reduce overlaps the backward pass
         self.betas, self.eps = betas, eps
         params = [p for p in net.parameters()]
         total = sum(p.numel() for p in params)
@@ -166,7 +164,13 @@ class TrainStep:
         self.net._bucket_hook = self._early_reduce if (self._late and self._grad_params is not None) else None
         if self._late:
             self.net._bucket_level = self._bucket_level
-        out, hebb_new = self.net(self.x, self.hebb)
+        # the trace-delta all-reduce + epilogue overlap the backward pass on net.dp_side; only this step body defers them (it
+        # joins dp_side before Adam) — any other caller of net.forward gets the trace on its own stream
+        self.net.dp_defer = self.dp_group is not None
+        try:
+            out, hebb_new = self.net(self.x, self.hebb)
+        finally:
+            self.net.dp_defer = False
         gS = torch.empty_like(out)
         n = out.numel()
         _lib.call("pu_bce_fwd_bwd", out.data_ptr(), self.target.data_ptr(), self.loss.data_ptr(), gS.data_ptr(), n, st)

@@ -541,3 +541,29 @@ def test_model_trace_rows_all_mode():
     outer = torch.stack([torch.bmm(X[b].unsqueeze(2), S[b].unsqueeze(1)) for b in range(3)])  # [B, N(rows), N, N]
     ref = (1 - eta) * hebb.cpu().double() + eta * outer.mean(dim=(0, 1))
     check(h1, ref, 2e-6, what="rows='all' trace")
+
+
+@pytest.mark.parametrize("momentum,track", [(None, True), (0.3, True), (0.1, False)])
+def test_bn_module_semantics_momentum_none_and_no_running_stats(momentum, track):
+    """modules._bn follows nn.BatchNorm2d for momentum=None (cumulative moving average) and track_running_stats=False
+    (batch statistics in eval mode too, no buffers)."""
+    from pu_b200 import modules as M
+    C = 8
+    g = torch.Generator().manual_seed(3)
+    ref = torch.nn.BatchNorm2d(C, momentum=momentum, track_running_stats=track)
+    ours = torch.nn.BatchNorm2d(C, momentum=momentum, track_running_stats=track).to(DEV)
+    with torch.no_grad():
+        w, b = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g)
+        ref.weight.copy_(w); ref.bias.copy_(b); ours.weight.copy_(w); ours.bias.copy_(b)
+    for step in range(3):
+        x = torch.randn(2, C, 9, 7, generator=g)
+        yr = ref(x)
+        yo = M._bn(nhwc(x).to(DEV), ours, False)
+        check(nchw(yo), yr, 2e-5, what="train y step %d" % step)
+    if track:
+        check(ours.running_mean, ref.running_mean, 2e-5, what="running_mean")
+        check(ours.running_var, ref.running_var, 2e-5, what="running_var")
+        assert int(ours.num_batches_tracked) == int(ref.num_batches_tracked) == 3
+    ref.eval(); ours.eval()
+    x = torch.randn(2, C, 9, 7, generator=g)
+    check(nchw(M._bn(nhwc(x).to(DEV), ours, False)), ref(x), 2e-5, what="eval y")
