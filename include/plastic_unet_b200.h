@@ -272,6 +272,17 @@ int pu_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg
  * copies every source tensor into flat[offset ...] with one launch (gradient tensors -> flat gradient arena). */
 int pu_gather_flat(const long long* table, int n, float* flat, void* stream);
 
+/* Data parallel: gradient exchange FUSED with the optimizer over NVLink peer memory.  peer_grad_ptrs / peer_flag_ptrs: device
+ * arrays of `world` pointers (as int64) to every rank's flat gradient arena (n floats) and flag buffer
+ * (2 * pu_adam_allreduce_blocks() * world int32, zero-initialised), all in symmetric (peer-mapped) memory.  One launch per rank and
+ * step: barrier with the peers, g = sum_j peer_grad[j] read over NVLink (same order on every rank: bit-identical replicas),
+ * Adam update of the local arena with grad_scale * g, barrier.  Replaces ncclAllReduce + pu_adam_step (train.py:110-111 under
+ * data parallelism).  world in {2, 4, 8}; every rank must call it once per step.                                        */
+int pu_adam_allreduce_step(float* param, const long long* peer_grad_ptrs, const long long* peer_flag_ptrs, int rank, int world, float* exp_avg,
+                           float* exp_avg_sq, float* step_count, const float* lr, float beta1, float beta2, float eps, float grad_scale,
+                           long long n, void* stream);
+int pu_adam_allreduce_blocks(void);
+
 /* Input pipeline: batch assembly from a DEVICE-resident dataset src [n, planes, Hs, Ws] + zero padding
  * to Hd x Wd at offset (oy, ox) in one pass: dst[b] = pad(src[idx[b]]).  idx: B int64 sample indices on the device.
  * Replaces the per-step host conversion + H2D copy of reference train.py:94-95 (and defines the 101 -> 128 padding of

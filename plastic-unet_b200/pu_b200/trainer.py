@@ -55,6 +55,28 @@ class TrainStep:
         self._grad_params = None  # learnt by the first eager step: which parameters receive a gradient at all
         self.flat_p = torch.zeros(off, device=self.dev)
         self.flat_g = torch.zeros(off, device=self.dev)
+        # Data parallel: the gradient exchange fused with Adam over NVLink peer memory (pu_adam_allreduce_step): the gradient
+        # arena and a flag buffer live in symmetric memory; falls back to ncclAllReduce + pu_adam_step if that is unavailable
+        self._fused = None
+        if self.dp_group is not None and self.world in (2, 4, 8) and not self._late and os.environ.get("PU_DP_FUSED", "1") == "1":
+            try:
+                import torch.distributed._symmetric_memory as symm
+                nblk = int(_lib.load().pu_adam_allreduce_blocks())
+                g_sym = symm.empty(off, dtype=torch.float32, device=self.dev)
+                g_sym.zero_()
+                f_sym = symm.empty(2 * nblk * self.world, dtype=torch.int32, device=self.dev)
+                f_sym.zero_()
+                hg = symm.rendezvous(g_sym, self.dp_group)
+                hf = symm.rendezvous(f_sym, self.dp_group)
+                torch.cuda.synchronize()
+                dist.barrier(self.dp_group)  # every rank's flags are zero before anyone signals
+                self._fused = (hg, hf, f_sym, int(hg.rank))
+                self.flat_g = g_sym
+            except Exception as e:  # no peer access / symmetric memory on this system
+                import warnings
+                warnings.warn("pu_b200.TrainStep: fused peer-memory gradient exchange unavailable (%s: %s); using NCCL all-reduce"
+                              % (type(e).__name__, str(e)[:200]))
+                self._fused = None
         self.m = torch.zeros(off, device=self.dev)
         self.v = torch.zeros(off, device=self.dev)
         self.params = params
@@ -207,14 +229,20 @@ class TrainStep:
             torch.cuda.current_stream().wait_stream(self._comm)  # the early bucket's all-reduce
         else:
             self._gather(lambda p: True, self.table_host, self.table_dev)
-            if self.dp_group is not None:
+            if self.dp_group is not None and self._fused is None:
                 dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.dp_group)
         if getattr(self.net, "dp_side", None) is not None:
             # join the deferred trace all-reduce + epilogue BEFORE the optimizer rewrites the arena (the epilogue reads eta)
             torch.cuda.current_stream().wait_stream(self.net.dp_side)
-        _lib.call("pu_adam_step", self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
-                  self.step_count.data_ptr(), self.lr.data_ptr(), self.betas[0], self.betas[1], self.eps,
-                  1.0 / self.world, self.n_flat, st)
+        if self._fused is not None:
+            hg, hf, _flags, grank = self._fused
+            _lib.call("pu_adam_allreduce_step", self.flat_p.data_ptr(), int(hg.buffer_ptrs_dev), int(hf.buffer_ptrs_dev), grank, self.world,
+                      self.m.data_ptr(), self.v.data_ptr(), self.step_count.data_ptr(), self.lr.data_ptr(), self.betas[0], self.betas[1],
+                      self.eps, 1.0 / self.world, self.n_flat, st)
+        else:
+            _lib.call("pu_adam_step", self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
+                      self.step_count.data_ptr(), self.lr.data_ptr(), self.betas[0], self.betas[1], self.eps,
+                      1.0 / self.world, self.n_flat, st)
         self.hebb.copy_(hebb_new.detach())
 
     def _state_tensors(self):

@@ -72,7 +72,7 @@ def _worker(rank, world, port, math, use_graph, out):
         for (k, p), (_, q) in zip(net.named_parameters(), net1.named_parameters()):
             num += float((p.double() - q.double()).pow(2).sum())
             den += float((q.double() - sd0[k].double()).pow(2).sum())
-        res.update(losses_dp=losses, losses_1=l1, upd=(num / den) ** 0.5,
+        res.update(fused_active=step._fused is not None, losses_dp=losses, losses_1=l1, upd=(num / den) ** 0.5,
                    trace=float((step.hebb - one.hebb).abs().max() / one.hebb.abs().max()))
         torch.save(res, out)
     dist.barrier()
@@ -81,14 +81,18 @@ def _worker(rank, world, port, math, use_graph, out):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("math,use_graph", [("fp32", True), ("tf32", True), ("tf32", False)])
-def test_dp2_trainstep_matches_single_process(tmp_path, math, use_graph):
+@pytest.mark.parametrize("math,use_graph,fused", [("fp32", True, 1), ("tf32", True, 1), ("tf32", False, 1), ("tf32", True, 0), ("fp32", False, 0)])
+def test_dp2_trainstep_matches_single_process(tmp_path, monkeypatch, math, use_graph, fused):
+    """fused = 1: the gradient exchange fused with Adam over NVLink peer memory (pu_adam_allreduce_step, symmetric memory);
+    fused = 0: ncclAllReduce + pu_adam_step."""
     import torch.multiprocessing as mp
     world = 2
     out = str(tmp_path / "res.pt")
+    monkeypatch.setenv("PU_DP_FUSED", str(fused))
     mp.spawn(_worker, args=(world, _free_port(), math, use_graph, out), nprocs=world, join=True)
     res = torch.load(out)
-    print("\n[dp2 %s graph=%s] %s" % (math, use_graph, res))
+    print("\n[dp2 %s graph=%s fused=%d] %s" % (math, use_graph, fused, res))
+    assert res["fused_active"] == bool(fused)
     assert res["bit_identical"]
     assert max(abs(a - b) for a, b in zip(res["losses_dp"], res["losses_1"])) < (1e-5 if math == "fp32" else 2e-4)
     assert res["trace"] < (1e-4 if math == "fp32" else 1e-3)
