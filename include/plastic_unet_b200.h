@@ -42,6 +42,9 @@ typedef enum {
 #define PU_FLAG_MASK_IN 4    /* backward kernels: zero the input gradient where the op's input x <= 0, i.e. apply the
                                 ReLU mask of the PRODUCER of x (premasked-gradient protocol)          */
 
+#define PU_FLAG_ACCUM_GRADS 16 /* backward kernels: ADD the parameter gradients to dw / db instead of overwriting them (the caller
+                                 zeroed them, e.g. the slots of a flat gradient arena): no memset launches.  Supported by the
+                                 TF32 paths of pu_conv3x3_wgrad (as PU_MATH_ACCUM in `math`) and pu_convT2x2s2_bwd.          */
 #define PU_FLAG_TF32_MATH 8  /* transposed convolutions: TF32 tensor-core math (mma.sync), fp32 accumulate; the model's TF32
                                 mode.  Without it (or for unsupported shapes) the fp32 CUDA-core kernels run.            */
 
@@ -53,6 +56,7 @@ typedef enum {
 /* conv3x3 math modes */
 #define PU_MATH_FP32 0 /* CUDA-core FFMA, strict fp32 (parity mode, any shape)        */
 #define PU_MATH_TF32 1 /* tcgen05 kind::tf32 implicit GEMM, fp32 accumulate in TMEM   */
+#define PU_MATH_ACCUM 0x100 /* pu_conv3x3_wgrad only, OR-ed into math: accumulate into dw / db (see PU_FLAG_ACCUM_GRADS)          */
 #define PU_MATH_TF32_FLAT 2 /* pu_pack_w3x3 only: the weight image of a PU_MATH_TF32 conv for which pu_conv3x3_tc_flat() is 1 */
 
 /* ---- library management --------------------------------------------------------------- */
@@ -94,6 +98,10 @@ int pu_conv3x3_tc_resident(int C0, int C1, int Cout, int H, int W);
  * 0: flat, one MMA per tap, 128-pixel blocks)}.  resident != 0: the weights are built
  * in shared memory from the raw OIHW tensor (PU_W_OIHW / PU_W_OIHW_DGRAD).  PU_ERR_UNSUPPORTED if the shape does not fit. */
 int pu_conv3x3_tc_plan(int B, int H, int W, int C0, int C1, int Cout, int resident, int* out17);
+/* Host-only: the plan of the TMA-fed weight-gradient kernel behind pu_conv3x3_wgrad(PU_MATH_TF32) for this problem.
+ * out12 = {input chunks per CTA, output tiles per CTA, tile width, tile height, images per tile, tilesX, tilesY, image tiles,
+ * pipeline stages, grid x, grid y, dynamic shared memory bytes}.  PU_ERR_UNSUPPORTED if the channel counts are not multiples of 8. */
+int pu_conv3x3_wgrad_plan(int B, int H, int W, int C0, int C1, int Cout, int* out12);
 
 /* y = act( conv3x3(cat[src0,src1]) + bias + res ), written channel-split into dst0|dst1 (flags: PU_FLAG_*).
  * wfmt selects what `wp` points at: PU_W_PACKED (output of pu_pack_w3x3 for this math mode), PU_W_OIHW (the raw
@@ -116,7 +124,8 @@ int pu_conv3x3_fwd(const float* src0, int H0, int W0, int C0, int oy0, int ox0,
                    int B, int H, int W, int Cout, int math, int wfmt, void* stream);
 
 /* dw_oihw[Cout, C0+C1, 3, 3] = sum_{b,y,x} g[b,y,x,co] * cat[src0,src1][b,y+ky-1,x+kx-1,ci]
- * (overwrites dw).  g is [B,H,W,Cout] dense.  db (may be NULL) receives the bias gradient sum_pixels g.       */
+ * (overwrites dw).  g is [B,H,W,Cout] dense.  db (may be NULL) receives the bias gradient sum_pixels g.
+ * math | PU_MATH_ACCUM: dw and db are ADDED to (no memset launches); PU_ERR_UNSUPPORTED where the shape's kernel cannot.  */
 int pu_conv3x3_wgrad(const float* src0, int H0, int W0, int C0, int oy0, int ox0,
                      const float* src1, int H1, int W1, int C1, int oy1, int ox1,
                      const float* g, float* dw_oihw, float* db, int B, int H, int W, int Cout,

@@ -26,6 +26,8 @@ struct WgradArgs {
   float* db;       // [Cout] | null
   int B, H, W, Cin, Cout;
   int tilesX, tilesY, ntiles;
+  int accum;  // 1: add to dw / db (zeroed by the caller) instead of overwriting them
+  int debug;  // PU_WG_DEBUG experiments: 1 = skip the final atomics, 2 = skip the MMAs, 4 = staging only (no fragment loads, no MMAs)
 };
 
 int conv3x3_fwd_ffma(const Conv3x3Args& a, cudaStream_t st);
@@ -34,6 +36,9 @@ bool conv3x3_c1_ok(int Cin, int Cout);
 int conv3x3_c1_fwd(const Conv3x3Args& a, cudaStream_t st);
 int conv3x3_c1_wgrad(const WgradArgs& a, cudaStream_t st);
 int conv3x3_wgrad_ffma(const WgradArgs& a, cudaStream_t st, int math);
+// TMA-fed mma.sync weight gradient (conv3x3_wgrad_tma.cu): TF32 mode, channel counts that are multiples of 8
+bool conv3x3_wgrad_tma_ok(const WgradArgs& a);
+int conv3x3_wgrad_tma(const WgradArgs& a, cudaStream_t st);
 // tcgen05 path (conv3x3_tc.cu); returns PU_ERR_UNSUPPORTED when the shape does not fit it
 int conv3x3_fwd_tc(const Conv3x3Args& a, cudaStream_t st);
 bool conv3x3_tc_ok(int C0, int C1, int Cout, int Cd0, int Cd1);

@@ -82,7 +82,12 @@ int pu_conv3x3_wgrad(const float* src0, int H0, int W0, int C0, int oy0, int ox0
   } else {
     C1 = 0;
   }
+  const int accum = (math & PU_MATH_ACCUM) ? 1 : 0;
+  math &= ~PU_MATH_ACCUM;
+  PU_REQUIRE(math == PU_MATH_FP32 || math == PU_MATH_TF32, PU_ERR_BAD_ARG, "pu_conv3x3_wgrad: unknown math mode %d", math);
   pu::WgradArgs a;
+  a.accum = accum;
+  a.debug = 0;
   a.s0 = pu::View{src0, H0, W0, C0, oy0, ox0};
   a.s1 = pu::View{src1, H1, W1, C1, oy1, ox1};
   a.g = g;
@@ -90,10 +95,8 @@ int pu_conv3x3_wgrad(const float* src0, int H0, int W0, int C0, int oy0, int ox0
   a.db = db;
   a.B = B; a.H = H; a.W = W; a.Cin = C0 + C1; a.Cout = Cout;
   a.tilesX = a.tilesY = a.ntiles = 0;
-  // PU_MATH_FP32: FFMA2 on the CUDA cores.  PU_MATH_TF32: warp-level TF32 MMAs (mma.sync m16n8k8) for channel counts
-  // that are multiples of 8.  A tcgen05 wgrad (K = pixels) needs MN-major tf32 operands; measured on B200: kind::tf32
-  // with a_major/b_major = MN and SWIZZLE_NONE descriptors returns zeros (CUTLASS only offers SWIZZLE_128B_BASE32B
-  // atoms for 32-bit MN-major operands) -> next round, see DESIGN.md.
+  // PU_MATH_FP32: FFMA2 on the CUDA cores.  PU_MATH_TF32: TMA-fed warp-level TF32 MMAs (mma.sync m16n8k8) for channel
+  // counts that are multiples of 8 (conv3x3_wgrad_tma.cu, which also explains why tcgen05 does not fit this contraction).
   return pu::conv3x3_wgrad_ffma(a, pu::as_stream(stream), math);
 }
 

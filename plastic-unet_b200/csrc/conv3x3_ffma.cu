@@ -622,7 +622,7 @@ __global__ void __launch_bounds__(256, 2) conv3x3_wgrad_mma_kernel(const WgradAr
     __syncthreads();
     const unsigned* xs = reinterpret_cast<const unsigned*>(dsm + stage * STAGE_F);
     const unsigned* gs = xs + XPIX * 8;
-    for (int grp = warp; grp < GROUPS; grp += 8) {
+    for (int grp = warp; grp < GROUPS && !(a.debug & 4); grp += 8) {
       const int yy = grp / (TW / 8), xg = (grp - yy * (TW / 8)) * 8;
       // A fragments: row = (tap within pair, ci = gq), col = pixel (tq, tq+4); the halo tile is offset by (+1,+1)
       const unsigned* xr = xs + ((yy * HW_) + xg + tq) * 8 + gq;
@@ -639,6 +639,11 @@ __global__ void __launch_bounds__(256, 2) conv3x3_wgrad_mma_kernel(const WgradAr
         // B fragment: k = pixel (tq, tq+4), n = co (gq)
         const unsigned b0 = gs[(yy * TW + xg + tq) * GP + 8 * n + gq];
         const unsigned b1 = gs[(yy * TW + xg + tq + 4) * GP + 8 * n + gq];
+        if (a.debug & 2) {  // (experiment) fragment loads without MMAs
+#pragma unroll
+          for (int p = 0; p < 9; ++p) acc[n][p >> 1][p & 3] += __uint_as_float(av[p][0] ^ av[p][1] ^ b0 ^ b1);
+          continue;
+        }
 #pragma unroll
         for (int p = 0; p < 4; ++p) mma_tf32_16x8x8(acc[n][p], av[2 * p][0], av[2 * p + 1][0], av[2 * p][1], av[2 * p + 1][1], b0, b1);
         // rows 8..15 of the fifth tile are free: feeding ones there makes them the column sums of G = the bias gradient
@@ -667,6 +672,7 @@ __global__ void __launch_bounds__(256, 2) conv3x3_wgrad_mma_kernel(const WgradAr
     const int p = r2 >> 2, j = r2 & 3;
     const int tap = 2 * p + (j >> 1);
     const int ci_ = ln >> 2, co = co0 + 8 * n + 2 * (ln & 3) + (j & 1);
+    if ((a.debug & 1) && sum != 12345.678f) continue;  // (experiment) no atomics
     if (tap > 8) {  // the ones rows: every ci_ row holds the same sum_pixels g[.][co]
       if (a.db != nullptr && ci_ == 0 && blockIdx.y == 0) atomicAdd(a.db + co, sum);
       continue;
@@ -780,21 +786,38 @@ int conv3x3_fwd_ffma(const Conv3x3Args& a0, cudaStream_t st) {
 int conv3x3_wgrad_ffma(const WgradArgs& a0, cudaStream_t st, int math) {
   if (conv3x3_c1_ok(a0.Cin, a0.Cout) && (a0.s1.p == nullptr || a0.s1.C == 0)) return conv3x3_c1_wgrad(a0, st);  // streaming stem kernel (dw + db)
   WgradArgs a = a0;
-  cudaError_t e = cudaMemsetAsync(a.dw, 0, sizeof(float) * (size_t)a.Cout * a.Cin * 9, st);
-  if (e != cudaSuccess) {
-    set_error("conv3x3_wgrad memset: %s", cudaGetErrorString(e));
-    return PU_ERR_CUDA;
+  {
+    static int dbg = -1;
+    if (dbg < 0) {
+      const char* e_ = getenv("PU_WG_DEBUG");
+      dbg = e_ ? atoi(e_) : 0;
+    }
+    a.debug = dbg;
   }
   const int nci = cdiv(a.s0.C, 8) + ((a.s1.p != nullptr && a.s1.C > 0) ? cdiv(a.s1.C, 8) : 0);
   const int nco = cdiv(a.Cout, 8);
   const bool have1 = a.s1.p != nullptr && a.s1.C > 0;
   const bool mma_path = math == PU_MATH_TF32 && a.s0.C % 8 == 0 && (!have1 || a.s1.C % 8 == 0) && a.Cout % 8 == 0;
+  if (a.accum && !mma_path) {
+    set_error("pu_conv3x3_wgrad: PU_MATH_ACCUM needs the TF32 path (channel counts that are multiples of 8) or the one-channel stem");
+    return PU_ERR_UNSUPPORTED;
+  }
+  cudaError_t e = cudaSuccess;
+  if (!a.accum) {
+    e = cudaMemsetAsync(a.dw, 0, sizeof(float) * (size_t)a.Cout * a.Cin * 9, st);
+    if (e != cudaSuccess) {
+      set_error("conv3x3_wgrad memset: %s", cudaGetErrorString(e));
+      return PU_ERR_CUDA;
+    }
+  }
   if (a.db != nullptr) {
     if (mma_path) {  // accumulated by the ones rows of the MMA kernel
-      e = cudaMemsetAsync(a.db, 0, sizeof(float) * a.Cout, st);
-      if (e != cudaSuccess) {
-        set_error("conv3x3_wgrad db memset: %s", cudaGetErrorString(e));
-        return PU_ERR_CUDA;
+      if (!a.accum) {
+        e = cudaMemsetAsync(a.db, 0, sizeof(float) * a.Cout, st);
+        if (e != cudaSuccess) {
+          set_error("conv3x3_wgrad db memset: %s", cudaGetErrorString(e));
+          return PU_ERR_CUDA;
+        }
       }
     } else {  // separate read-only reduction pass over g
       int rc = pu_relu_bwd_bias(a.g, nullptr, nullptr, a.db, (long long)a.B * a.H * a.W, a.Cout, 0, st);
@@ -803,6 +826,13 @@ int conv3x3_wgrad_ffma(const WgradArgs& a0, cudaStream_t st, int math) {
   }
   if (a.s0.C % 8 == 0 && (!have1 || a.s1.C % 8 == 0) && a.Cout % 8 == 0) {
     if (math == PU_MATH_TF32) {
+      // TMA-fed kernel (conv3x3_wgrad_tma.cu); PU_WGRAD_V=1 selects the first, cp.async-fed version below (A/B measurements)
+      static int ver = -1;
+      if (ver < 0) {
+        const char* e_ = getenv("PU_WGRAD_V");
+        ver = e_ ? atoi(e_) : 2;
+      }
+      if (ver != 1 && conv3x3_wgrad_tma_ok(a)) return conv3x3_wgrad_tma(a, st);
       // warp-level TF32 MMAs over the same cp.async ring; NCO co tiles (8 channels each) per CTA
       const int nco_t = a.Cout % 32 == 0 ? 4 : (a.Cout % 16 == 0 ? 2 : 1);
       const int ncoz = a.Cout / (8 * nco_t);

@@ -534,17 +534,25 @@ int pu_convT2x2s2_bwd(const float* x, const float* w, const float* dy, float* dx
       if (rc) return rc;
     }
     if (dw != nullptr) {
-      cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * Cin * Cout * 4, st);
-      if (e == cudaSuccess && db != nullptr) e = cudaMemsetAsync(db, 0, sizeof(float) * Cout, st);
+      cudaError_t e = cudaSuccess;
+      if (!(flags & PU_FLAG_ACCUM_GRADS)) {
+        e = cudaMemsetAsync(dw, 0, sizeof(float) * Cin * Cout * 4, st);
+        if (e == cudaSuccess && db != nullptr) e = cudaMemsetAsync(db, 0, sizeof(float) * Cout, st);
+      }
       if (e != cudaSuccess) {
         pu::set_error("pu_convT2x2s2_bwd memset: %s", cudaGetErrorString(e));
         return PU_ERR_CUDA;
       }
       return pu::convT2x2_dw_mma(x, dy, dw, db, B, H, W, Cin, Cout, st);
     }
-    if (db != nullptr) return pu::launch_bias_grad(dy, nullptr, db, B, 4LL * H * W, Cout, st);
+    if (db != nullptr) {
+      PU_REQUIRE(!(flags & PU_FLAG_ACCUM_GRADS), PU_ERR_UNSUPPORTED, "pu_convT2x2s2_bwd: PU_FLAG_ACCUM_GRADS needs dw and db together");
+      return pu::launch_bias_grad(dy, nullptr, db, B, 4LL * H * W, Cout, st);
+    }
     return PU_OK;
   }
+  PU_REQUIRE(!(flags & PU_FLAG_ACCUM_GRADS) || (dw == nullptr && db == nullptr), PU_ERR_UNSUPPORTED,
+             "pu_convT2x2s2_bwd: PU_FLAG_ACCUM_GRADS needs the TF32 tensor-core path for this shape");
   if (dx != nullptr) {
     const size_t smem = (size_t)4 * Cout * 8 * sizeof(float);
     PU_REQUIRE(smem <= 48 * 1024, PU_ERR_UNSUPPORTED, "pu_convT2x2s2_bwd: Cout=%d > 384", Cout);

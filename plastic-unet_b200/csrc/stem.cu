@@ -123,10 +123,13 @@ int conv3x3_c1_fwd(const Conv3x3Args& a, cudaStream_t st) {
   return post_launch("pu_conv3x3_fwd (stem)");
 }
 
-// dw and db are zeroed here
+// dw and db are zeroed here (unless the caller accumulates: PU_MATH_ACCUM)
 int conv3x3_c1_wgrad(const WgradArgs& a, cudaStream_t st) {
-  cudaError_t e = cudaMemsetAsync(a.dw, 0, sizeof(float) * a.Cout * 9, st);
-  if (e == cudaSuccess && a.db != nullptr) e = cudaMemsetAsync(a.db, 0, sizeof(float) * a.Cout, st);
+  cudaError_t e = cudaSuccess;
+  if (!a.accum) {
+    e = cudaMemsetAsync(a.dw, 0, sizeof(float) * a.Cout * 9, st);
+    if (e == cudaSuccess && a.db != nullptr) e = cudaMemsetAsync(a.db, 0, sizeof(float) * a.Cout, st);
+  }
   if (e != cudaSuccess) {
     set_error("conv3x3_wgrad (stem) memset: %s", cudaGetErrorString(e));
     return PU_ERR_CUDA;

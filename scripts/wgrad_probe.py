@@ -9,7 +9,7 @@ import torch  # noqa: E402
 from pu_b200 import _lib  # noqa: E402
 
 C0, C1, Cout, size, B = [int(v) for v in (sys.argv[1:6] + ["8", "0", "8", "128", "64"][len(sys.argv[1:6]):])]
-MATH = int(os.environ.get("WG_MATH", "0"))
+MATH = int(os.environ.get("WG_MATH", "1"))
 dev = "cuda"
 nbuf = 4
 xs0 = [torch.rand(B, size, size, C0, device=dev) for _ in range(nbuf)]
@@ -25,6 +25,11 @@ def run(i):
 
 
 ITERS = 20
+if os.environ.get("NO_GRAPH"):  # for ncu: plain launches
+    for i in range(4):
+        run(i)
+    torch.cuda.synchronize()
+    sys.exit(0)
 side = torch.cuda.Stream()
 side.wait_stream(torch.cuda.current_stream())
 with torch.cuda.stream(side):

@@ -213,3 +213,90 @@ def test_tc_conv_planner_invariants():
             # shared memory accounting: stages + resident weights + bookkeeping
             assert p["smem"] >= p["nstages"] * (p["a_bytes"] + p["w_stage"]) + p["w_res"], ctx
     assert planned > len(shapes)  # most shapes have both a resident and a streamed plan
+
+
+def test_wgrad_tma_plan_invariants():
+    """Host planner of the TMA-fed weight-gradient kernel (pu_conv3x3_wgrad_plan, no device): for every conv shape of the five
+    BASELINE configurations the tile covers 16 / NCI strips of 8x8 pixels, the chunk / co-tile split divides the channel counts,
+    the grid fits the 148 SMs and the ring + reduction buffer fit in shared memory."""
+    import ctypes
+    from pu_b200 import _lib
+    lib = _lib.load()
+    shapes = []
+    for B, s0 in ((64, 128), (32, 101), (8, 512), (1, 21), (3, 37)):
+        s, c = s0, 8
+        for _ in range(6):
+            if s < 1:
+                break
+            shapes += [(B, s, s, c, 0, c), (B, s, s, c, c, c), (B, s, s, c, 0, 2 * c), (B, s, s, 2 * c, 2 * c, c)]
+            s //= 2
+            c *= 2
+    shapes += [(1, 21, 37, 24, 0, 40), (2, 6, 300, 8, 8, 8), (64, 128, 128, 8, 8, 8)]
+    out = (ctypes.c_int * 12)()
+    for (B, H, W, C0, C1, Cout) in shapes:
+        assert lib.pu_conv3x3_wgrad_plan(B, H, W, C0, C1, Cout, out) == 0, (B, H, W, C0, C1, Cout)
+        nci, nco, TW, TH, NB, tX, tY, tB, stages, gx, gy, smem = list(out)
+        nchunks, ncot = (C0 + C1) // 8, Cout // 8
+        assert nci in (1, 2, 4) and nco in (1, 2) and nchunks % nci == 0 and ncot % nco == 0
+        assert TW % 8 == 0 and TH % 8 == 0 and (TW // 8) * (TH // 8) * NB == 16 // nci
+        assert not (C0 == 8 or C1 == 8) or 8 * (TW + 2) <= 256  # (channel, x)-merged box rows of the 8-channel sources
+        assert Cout != 8 or 8 * TW <= 256
+        assert tX * TW >= W and tY * TH >= H and tB * NB >= B and (tX - 1) * TW < W and (tY - 1) * TH < H and (tB - 1) * NB < B
+        assert gy == (nchunks // nci) * (ncot // nco)
+        assert 1 <= gx <= max(1, 148 // gy) and gx <= tX * tY * tB
+        assert 1 <= stages <= 4 and smem <= 227 * 1024
+        stage = nci * (((TW + 2) * (TH + 2) * NB * 32 + 127) // 128 * 128) + nco * ((TW * TH * NB * 32 + 127) // 128 * 128)
+        assert smem >= max(stages * stage, 16 * 32 * 20 * nco * 4)
+    assert lib.pu_conv3x3_wgrad_plan(1, 8, 8, 4, 0, 8, out) != 0  # channel counts must be multiples of 8
+
+
+def test_wgrad_tma_strip_walk():
+    """conv3x3_wgrad_tma_kernel's index algebra in numpy: a tile of NB x TH x TW pixels is cut into 8x8 strips, a warp walks
+    down its strip keeping halo rows (yy, yy+1, yy+2) of the [pixel][8] x plane as the A fragments of taps (ky, kx) — element
+    (row ci, k = pixel j) = plane[yy + ky][xs + j + kx][ci] — against B = g plane[yy][xs + j][co]; five tap-pair tiles per
+    group, the spare rows of the fifth fed ones (bias gradient).  Zero fill outside the image = TMA OOB fill."""
+    rng = np.random.default_rng(11)
+    B, H, W, Ci, Co = 3, 13, 21, 8, 8
+    TW, TH, NB = 16, 8, 2                              # 2 x 1 strips x 2 images = 4 strips (NCI = 4)
+    x = rng.standard_normal((B, H, W, Ci))
+    g = rng.standard_normal((B, H, W, Co))
+    acc = np.zeros((5, 16, Co))
+    for tb in range(-(-B // NB)):
+        for ty in range(-(-H // TH)):
+            for tx in range(-(-W // TW)):
+                xp = np.zeros((NB, TH + 2, TW + 2, Ci))  # the staged halo plane (box start (x0 - 1, y0 - 1, b0), OOB -> 0)
+                gp = np.zeros((NB, TH, TW, Co))
+                for nb in range(NB):
+                    b = tb * NB + nb
+                    if b >= B:
+                        continue
+                    for hy in range(TH + 2):
+                        for hx in range(TW + 2):
+                            yy, xx = ty * TH + hy - 1, tx * TW + hx - 1
+                            if 0 <= yy < H and 0 <= xx < W:
+                                xp[nb, hy, hx] = x[b, yy, xx]
+                    for hy in range(TH):
+                        for hx in range(TW):
+                            yy, xx = ty * TH + hy, tx * TW + hx
+                            if yy < H and xx < W:
+                                gp[nb, hy, hx] = g[b, yy, xx]
+                for ps in range(NB * (TH // 8) * (TW // 8)):
+                    tws, ths = TW // 8, TH // 8
+                    sx, sy, nb = ps % tws, (ps // tws) % ths, ps // (tws * ths)
+                    for yy in range(8):
+                        Bf = gp[nb, sy * 8 + yy, sx * 8:sx * 8 + 8]                     # [8 pixels, Co]
+                        for t in range(5):
+                            A = np.ones((16, 8))
+                            for half in range(2):
+                                tap = 2 * t + half
+                                if tap <= 8:
+                                    ky, kx = divmod(tap, 3)
+                                    A[8 * half:8 * half + 8] = xp[nb, sy * 8 + yy + ky, sx * 8 + kx:sx * 8 + kx + 8].T
+                            acc[t] += A @ Bf
+    dw = np.zeros((Co, Ci, 9))
+    for tap in range(9):
+        dw[:, :, tap] = acc[tap // 2, 8 * (tap % 2):8 * (tap % 2) + 8].T
+    ref = torch.nn.grad.conv2d_weight(torch.from_numpy(x).permute(0, 3, 1, 2), (Co, Ci, 3, 3), torch.from_numpy(g).permute(0, 3, 1, 2),
+                                      padding=1).numpy().reshape(Co, Ci, 9)
+    np.testing.assert_allclose(dw, ref, rtol=1e-10, atol=1e-10)
+    np.testing.assert_allclose(acc[4, 8], g.sum((0, 1, 2)), rtol=1e-10, atol=1e-10)
