@@ -4,6 +4,7 @@
 //                                              F.pad crop (unet_p_res.py:215-217) fused as a window.
 // These are ~4 % of the model FLOPs; they are written for coalesced NHWC traffic,
 // weights staged in shared memory per 8-channel output block.
+#include <stdlib.h>
 #include "pu_common.cuh"
 
 namespace pu {
@@ -503,6 +504,9 @@ int convT2x2_fwd_mma(const float* x, const float* w, const float* bias, float* y
 int convT2x2_dx_mma(const float* x, const float* w, const float* dy, float* dx, int B, int H, int W, int Cin, int Cout, int mask_in,
                     cudaStream_t st);
 int convT2x2_dw_mma(const float* x, const float* dy, float* dw, float* db, int B, int H, int W, int Cin, int Cout, cudaStream_t st);
+// convT_dw_tma.cu
+bool convT2x2_dw_tma_ok(int Cin, int Cout);
+int convT2x2_dw_tma(const float* x, const float* dy, float* dw, float* db, int B, int H, int W, int Cin, int Cout, cudaStream_t st);
 
 }  // namespace pu
 
@@ -543,6 +547,12 @@ int pu_convT2x2s2_bwd(const float* x, const float* w, const float* dy, float* dx
         pu::set_error("pu_convT2x2s2_bwd memset: %s", cudaGetErrorString(e));
         return PU_ERR_CUDA;
       }
+      static int ver = -1;  // PU_CONVT_DW_V=1: the first, cp.async-fed kernels (A/B measurements)
+      if (ver < 0) {
+        const char* e_ = getenv("PU_CONVT_DW_V");
+        ver = e_ ? atoi(e_) : 2;
+      }
+      if (ver != 1 && pu::convT2x2_dw_tma_ok(Cin, Cout)) return pu::convT2x2_dw_tma(x, dy, dw, db, B, H, W, Cin, Cout, st);
       return pu::convT2x2_dw_mma(x, dy, dw, db, B, H, W, Cin, Cout, st);
     }
     if (db != nullptr) {

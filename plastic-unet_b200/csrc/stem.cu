@@ -22,10 +22,14 @@ __global__ void __launch_bounds__(256) conv3x3_c1_fwd_kernel(const View s0, cons
   for (int i = threadIdx.x; i < CO; i += blockDim.x) bs[i] = bias != nullptr ? bias[i] : 0.f;
   __syncthreads();
   const long long npix = (long long)B * H * W;
-  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += (long long)gridDim.x * blockDim.x) {
-    const int x = (int)(p % W);
-    const int y = (int)((p / W) % H);
-    const long long b = p / ((long long)W * H);
+  // (b, y, x) of the thread's pixel advance incrementally: three 64-bit divisions per pixel cost more than the 72 FMAs
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const int sx = (int)(stride % W), sy = (int)((stride / W) % H), sb = (int)(stride / ((long long)W * H));
+  long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int x = (int)(p % W), y = (int)((p / W) % H), b = (int)(p / ((long long)W * H));
+  for (; p < npix; p += stride, x += sx, y += sy, b += sb) {
+    if (x >= W) { x -= W; ++y; }
+    if (y >= H) { y -= H; ++b; }
     float xv[9];
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky)
@@ -61,54 +65,104 @@ __global__ void __launch_bounds__(256) conv3x3_c1_fwd_kernel(const View s0, cons
 }
 
 // dw[co][0][tap] = sum_p x[p + tap] * g[p][co],  db[co] = sum_p g[p][co];  thread = strip of pixels, 10*CO partial sums in
-// registers, warp shuffle + shared-memory reduction, one atomic per output and CTA (dw/db zeroed by the caller)
+// registers, warp shuffle + shared-memory reduction, then ONE vector reduction (red.global.add.v4.f32) per four outputs and CTA
+// (dw/db zeroed by the caller).  Two CTAs per SM (8 channels): with 4 CTAs of 128 threads per SM (first version) the 592 x 80 scalar atomics
+// on three cache lines cost ~8 us of a 28 us kernel, and this kernel is the LAST weight gradient of the backward pass — nothing
+// is left to overlap it with.  The next pixel's g vector is requested before the current one is consumed.
 template <int CO>
-__global__ void __launch_bounds__(128) conv3x3_c1_wgrad_kernel(const View s0, const float* __restrict__ g, float* __restrict__ dw,
-                                                               float* __restrict__ db, int B, int H, int W) {
+__global__ void __launch_bounds__(256, CO == 8 ? 2 : 1) conv3x3_c1_wgrad_kernel(const View s0, const float* __restrict__ g, float* __restrict__ dw,
+                                                                  float* __restrict__ db, int B, int H, int W, int vec4) {
   float acc[10][CO];  // 9 taps + the bias row
 #pragma unroll
   for (int t = 0; t < 10; ++t)
 #pragma unroll
     for (int j = 0; j < CO; ++j) acc[t][j] = 0.f;
   const long long npix = (long long)B * H * W;
-  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += (long long)gridDim.x * blockDim.x) {
-    const int x = (int)(p % W);
-    const int y = (int)((p / W) % H);
-    const long long b = p / ((long long)W * H);
-    float gv[CO];
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long p0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  // PF pixels of g in flight per thread (the loads of pixel i + PF are issued before pixel i is consumed): with 512 threads per SM
+  // one 32-byte vector each is 16 KB in flight per SM, a third of what the HBM latency needs
+  constexpr int PF = 3;
+  float gn[PF][CO];
 #pragma unroll
-    for (int j = 0; j < CO; j += 4) {
-      const float4 v = ldg4(g + p * CO + j);
-      gv[j] = v.x; gv[j + 1] = v.y; gv[j + 2] = v.z; gv[j + 3] = v.w;
-    }
+  for (int d = 0; d < PF; ++d) {
+    const long long q = p0 + d * stride;
+    if (q < npix) {
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const int gy = y + ky - 1, gx = x + kx - 1;
-        const bool ok = gy >= 0 && gy < H && gx >= 0 && gx < W;
-        const float xv = ok ? __ldg(s0.p + ((size_t)b * s0.Hs + (gy + s0.oy)) * s0.Ws + (gx + s0.ox)) : 0.f;
-#pragma unroll
-        for (int j = 0; j < CO; ++j) acc[ky * 3 + kx][j] = fmaf(xv, gv[j], acc[ky * 3 + kx][j]);
+      for (int j = 0; j < CO; j += 4) {
+        const float4 v = ldg4_stream(g + q * CO + j);
+        gn[d][j] = v.x; gn[d][j + 1] = v.y; gn[d][j + 2] = v.z; gn[d][j + 3] = v.w;
       }
-#pragma unroll
-    for (int j = 0; j < CO; ++j) acc[9][j] += gv[j];
+    }
   }
-  __shared__ float red[4][10 * CO];
+  // (b, y, x) advance incrementally with the pixel index: no 64-bit divisions in the loop
+  const int sx = (int)(stride % W), sy = (int)((stride / W) % H), sb = (int)(stride / ((long long)W * H));
+  int x = (int)(p0 % W), y = (int)((p0 / W) % H), b = (int)(p0 / ((long long)W * H));
+  for (long long p = p0; p < npix; p += PF * stride) {
+#pragma unroll
+    for (int d = 0; d < PF; ++d, x += sx, y += sy, b += sb) {
+      const long long q = p + d * stride;
+      if (x >= W) { x -= W; ++y; }
+      if (y >= H) { y -= H; ++b; }
+      if (q < npix) {
+        float xv[9];
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            const int gy = y + ky - 1, gx = x + kx - 1;
+            const bool ok = gy >= 0 && gy < H && gx >= 0 && gx < W;
+            xv[ky * 3 + kx] = ok ? __ldg(s0.p + ((size_t)b * s0.Hs + (gy + s0.oy)) * s0.Ws + (gx + s0.ox)) : 0.f;
+          }
+        float gv[CO];
+#pragma unroll
+        for (int j = 0; j < CO; ++j) gv[j] = gn[d][j];
+        const long long qn = q + PF * stride;
+        if (qn < npix) {
+#pragma unroll
+          for (int j = 0; j < CO; j += 4) {
+            const float4 v = ldg4_stream(g + qn * CO + j);
+            gn[d][j] = v.x; gn[d][j + 1] = v.y; gn[d][j + 2] = v.z; gn[d][j + 3] = v.w;
+          }
+        }
+#pragma unroll
+        for (int t = 0; t < 9; ++t)
+#pragma unroll
+          for (int j = 0; j < CO; ++j) acc[t][j] = fmaf(xv[t], gv[j], acc[t][j]);
+#pragma unroll
+        for (int j = 0; j < CO; ++j) acc[9][j] += gv[j];
+      }
+    }
+  }
+  __shared__ __align__(16) float red[8][10 * CO];  // per warp, in memory order: dw[j][tap] = [j * 9 + tap], then db[j] at 9 * CO + j
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int t = 0; t < 10; ++t)
 #pragma unroll
     for (int j = 0; j < CO; ++j) {
       const float s = warp_sum(acc[t][j]);
-      if (lane == 0) red[warp][t * CO + j] = s;
+      if (lane == 0) red[warp][t < 9 ? j * 9 + t : 9 * CO + j] = s;
     }
   __syncthreads();
-  for (int i = threadIdx.x; i < 10 * CO; i += blockDim.x) {
-    const float s = red[0][i] + red[1][i] + red[2][i] + red[3][i];
-    const int t = i / CO, j = i - t * CO;
-    if (t < 9) atomicAdd(dw + j * 9 + t, s);
-    else if (db != nullptr) atomicAdd(db + j, s);
+  if (vec4) {
+    for (int i = threadIdx.x; i < 10 * CO / 4; i += blockDim.x) {
+      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int w = 0; w < 8; ++w) {
+        const float4 v = *reinterpret_cast<const float4*>(&red[w][4 * i]);
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      }
+      float* dst = 4 * i < 9 * CO ? dw + 4 * i : (db != nullptr ? db + (4 * i - 9 * CO) : nullptr);  // 9 * CO is a multiple of 4
+      if (dst != nullptr) asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(s.x), "f"(s.y), "f"(s.z), "f"(s.w) : "memory");
+    }
+  } else {
+    for (int i = threadIdx.x; i < 10 * CO; i += blockDim.x) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) s += red[w][i];
+      if (i < 9 * CO) atomicAdd(dw + i, s);
+      else if (db != nullptr) atomicAdd(db + (i - 9 * CO), s);
+    }
   }
 }
 
@@ -135,11 +189,13 @@ int conv3x3_c1_wgrad(const WgradArgs& a, cudaStream_t st) {
     return PU_ERR_CUDA;
   }
   const long long npix = (long long)a.B * a.H * a.W;
-  long long blocks = (npix + 128 * 16 - 1) / (128 * 16);  // >= 16 pixels per thread amortise the 10*CO-value reduction
-  if (blocks > 4LL * kNumSMs) blocks = 4LL * kNumSMs;
+  long long blocks = (npix + 256 * 16 - 1) / (256 * 16);  // >= 16 pixels per thread amortise the 10*CO-value reduction
+  const long long per_sm = a.Cout == 8 ? 2 : 1;  // 16 output channels: 160 accumulators per thread, one CTA per SM
+  if (blocks > per_sm * kNumSMs) blocks = per_sm * kNumSMs;
   if (blocks < 1) blocks = 1;
-  if (a.Cout == 8) conv3x3_c1_wgrad_kernel<8><<<(unsigned)blocks, 128, 0, st>>>(a.s0, a.g, a.dw, a.db, a.B, a.H, a.W);
-  else conv3x3_c1_wgrad_kernel<16><<<(unsigned)blocks, 128, 0, st>>>(a.s0, a.g, a.dw, a.db, a.B, a.H, a.W);
+  const int vec4 = ((reinterpret_cast<uintptr_t>(a.dw) | (a.db != nullptr ? reinterpret_cast<uintptr_t>(a.db) : 0)) & 15u) == 0 ? 1 : 0;
+  if (a.Cout == 8) conv3x3_c1_wgrad_kernel<8><<<(unsigned)blocks, 256, 0, st>>>(a.s0, a.g, a.dw, a.db, a.B, a.H, a.W, vec4);
+  else conv3x3_c1_wgrad_kernel<16><<<(unsigned)blocks, 256, 0, st>>>(a.s0, a.g, a.dw, a.db, a.B, a.H, a.W, vec4);
   return post_launch("pu_conv3x3_wgrad (stem)");
 }
 

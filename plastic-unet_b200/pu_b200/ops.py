@@ -56,6 +56,43 @@ def _note_side(*ts):
                 SIDE_OUTPUTS.add(t.data_ptr())
 
 
+# set by pu_b200.trainer.TrainStep: {weight.data_ptr(): (flat gradient arena, weight offset, bias offset | -1, bias numel)}.
+# A backward op whose kernels can ACCUMULATE (PU_MATH_ACCUM / PU_FLAG_ACCUM_GRADS) then writes its parameter gradients straight
+# into the arena slots (zeroed once per step by the trainer): no memset launches per op, no gradient gather before Adam.  The
+# custom ops receive the slot ADDRESSES (ints; their tensor outputs may not alias one another's storage) and the autograd
+# wrappers hand views of the slots to autograd.
+GRAD_SINK = None
+FLAG_ACCUM_GRADS = 16
+MATH_ACCUM = 0x100
+
+
+def _sink(weight: Tensor, want_bias: bool):
+    """-> (dw view, db view | None) inside the trainer's gradient arena, or None.  Fresh view objects every call, so that
+    autograd's AccumulateGrad takes them over as .grad (no copy kernel)."""
+    if GRAD_SINK is None:
+        return None
+    ent = GRAD_SINK.get(weight.data_ptr())
+    if ent is None:
+        return None
+    arena, woff, boff, bn = ent
+    if want_bias and boff < 0:
+        return None
+    dw = arena[woff:woff + weight.numel()].view(weight.shape)
+    db = arena[boff:boff + bn] if want_bias else None
+    return dw, db
+
+
+def _fork_point():
+    """An event on the current stream at the point where every input of an op's parameter-gradient kernels exists.  The side
+    stream waits for THIS (not for the whole main stream), so the weight gradient of a layer does not queue behind the layer's
+    own data-gradient kernel, which the op enqueues on the main stream first (critical path first)."""
+    if not WGRAD_SIDE_STREAMS:
+        return None
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream())
+    return ev
+
+
 def _side_stream():
     global _side_rr
     if not WGRAD_SIDE_STREAMS:
@@ -217,8 +254,9 @@ def conv3x3(x0: Tensor, x1: Optional[Tensor], weight: Tensor, bias: Optional[Ten
 def conv3x3_bwd(dy: Tensor, y: Tensor, x0: Tensor, x1: Optional[Tensor], weight: Tensor, has_bias: bool, relu: bool,
                 H: int, W: int, oy0: int, ox0: int, oy1: int, ox1: int, math: int,
                 need_dx: bool, need_dw: bool, m0: Optional[Tensor] = None, m1: Optional[Tensor] = None,
-                premasked: bool = False) -> List[Tensor]:
-    """-> [g, dx0, dx1, dw, db]; g = dy masked by the fused ReLU (== dy when relu is False)."""
+                premasked: bool = False, dw_ptr: int = 0, db_ptr: int = 0) -> List[Tensor]:
+    """-> [g, dx0, dx1, dw, db]; g = dy masked by the fused ReLU (== dy when relu is False).  dw_ptr / db_ptr != 0: the
+    (zeroed) gradient-arena slots the weight-gradient kernel accumulates into (see GRAD_SINK); dw / db are then returned empty."""
     _chk(dy, y, x0, x1, weight)
     dev = dy.device
     B = x0.shape[0]
@@ -226,11 +264,13 @@ def conv3x3_bwd(dy: Tensor, y: Tensor, x0: Tensor, x1: Optional[Tensor], weight:
     H0, W0, C0 = _dims(x0)
     H1, W1, C1 = _dims(x1)
     npix = B * H * W
-    db = torch.empty(Cout, device=dev, dtype=torch.float32) if has_bias else _e(dev)
     tf32 = math in (MATH_TF32, MATH_MIXED)
     premasked = premasked and relu
     fresh_g = (relu or tf32) and not premasked  # tensor-core operands are stored rounded to TF32 by their producer
     db_in_wgrad = premasked and has_bias and need_dw
+    db_sunk = db_in_wgrad and db_ptr != 0
+    db = torch.empty(Cout, device=dev, dtype=torch.float32) if (has_bias and not db_sunk) else _e(dev)
+    dbp = db_ptr if db_sunk else (db.data_ptr() if db_in_wgrad else None)
     if premasked:
         g = dy  # every consumer already applied (y > 0) (and rounded) in its own backward epilogue
         if has_bias and not need_dw:
@@ -244,6 +284,7 @@ def conv3x3_bwd(dy: Tensor, y: Tensor, x0: Tensor, x1: Optional[Tensor], weight:
         if has_bias:
             _lib.call("pu_relu_bwd_bias", dy.data_ptr(), None, None, db.data_ptr(), npix, Cout, 0, _s())
     dx0, dx1 = _e(dev), _e(dev)
+    fork = _fork_point() if need_dw else None  # g is complete here
     if need_dx:
         md = MATH_TF32 if (tf32 and _tc_ok(Cout, 0, Cin, C0, C1)) else MATH_FP32
         wpt, wfmt = _weight_operand(weight, 1, md, Cout, 0, Cin, H, W, B)
@@ -261,40 +302,42 @@ def conv3x3_bwd(dy: Tensor, y: Tensor, x0: Tensor, x1: Optional[Tensor], weight:
                   B, H, W, Cin, md, wfmt, _s())
     dw = _e(dev)
     if need_dw:
+        wmath = (MATH_TF32 if tf32 else MATH_FP32) | (MATH_ACCUM if dw_ptr else 0)
         side = _side_stream()
         if side is not None:
             # The weight gradient is not needed before the optimizer: run it on a side stream so that it overlaps the
             # dgrad chain (the caller joins WGRAD_SIDE_STREAMS before it reads any parameter gradient).
             main = torch.cuda.current_stream()
-            side.wait_stream(main)
+            side.wait_event(fork)
             with torch.cuda.stream(side):
-                dw = torch.empty_like(weight)
+                if not dw_ptr:
+                    dw = torch.empty_like(weight)
                 _lib.call("pu_conv3x3_wgrad", x0.data_ptr(), H0, W0, C0, oy0, ox0, _p(x1), H1, W1, C1, oy1, ox1,
-                          g.data_ptr(), dw.data_ptr(), db.data_ptr() if db_in_wgrad else None, B, H, W, Cout,
-                          MATH_TF32 if tf32 else MATH_FP32, _s())
-            for t in (x0, x1, g, db if db_in_wgrad else None):
+                          g.data_ptr(), dw_ptr if dw_ptr else dw.data_ptr(), dbp, B, H, W, Cout, wmath, _s())
+            for t in (x0, x1, g, db if (db_in_wgrad and not db_sunk) else None):
                 if t is not None:
                     t.record_stream(side)
-            dw.record_stream(main)
-            _note_side(dw, db if db_in_wgrad else None)
+            if not dw_ptr:
+                dw.record_stream(main)
+            _note_side(dw if not dw_ptr else None, db if (db_in_wgrad and not db_sunk) else None)
         else:
-            dw = torch.empty_like(weight)
+            if not dw_ptr:
+                dw = torch.empty_like(weight)
             _lib.call("pu_conv3x3_wgrad", x0.data_ptr(), H0, W0, C0, oy0, ox0, _p(x1), H1, W1, C1, oy1, ox1,
-                      g.data_ptr(), dw.data_ptr(), db.data_ptr() if db_in_wgrad else None, B, H, W, Cout,
-                      MATH_TF32 if tf32 else MATH_FP32, _s())
+                      g.data_ptr(), dw_ptr if dw_ptr else dw.data_ptr(), dbp, B, H, W, Cout, wmath, _s())
     g_out = g if fresh_g else _e(dev)  # never return an alias of an input
     return [g_out, dx0, dx1, dw, db]
 
 
 @conv3x3_bwd.register_fake
 def _(dy, y, x0, x1, weight, has_bias, relu, H, W, oy0, ox0, oy1, ox1, math, need_dx, need_dw, m0=None, m1=None,
-      premasked=False):
+      premasked=False, dw_ptr=0, db_ptr=0):
     e = dy.new_empty(0)
     return [torch.empty_like(dy) if ((relu or math in (MATH_TF32, MATH_MIXED)) and not (premasked and relu)) else e,
             torch.empty_like(x0) if need_dx else e,
             torch.empty_like(x1) if (need_dx and x1 is not None) else e,
-            torch.empty_like(weight) if need_dw else e,
-            dy.new_empty(weight.shape[0]) if has_bias else e]
+            torch.empty_like(weight) if (need_dw and not dw_ptr) else e,
+            dy.new_empty(weight.shape[0]) if (has_bias and not (db_ptr and premasked and relu and need_dw)) else e]
 
 
 def _conv3x3_setup(ctx, inputs, output):
@@ -313,8 +356,26 @@ def _conv3x3_backward(ctx, dy, _dmask=None):
         return (None,) * 17
     need_dx = need[0] or (x1 is not None and need[1])
     dy = dy.contiguous()
-    g, dx0, dx1, dw, db = conv3x3_bwd(dy, y, x0, x1, weight, has_bias and need[3], relu, H, W, oy0, ox0, oy1, ox1, math,
-                                      need_dx, need[2], m0, m1, premasked)
+    # gradient arena of the trainer: the TF32 kernels (channel multiples of 8, or the one-channel stem) accumulate in place
+    sink = None
+    want_b = bool(has_bias and need[3])
+    if need[2] and math in (MATH_TF32, MATH_MIXED) and GRAD_SINK is not None:
+        C0, C1, Cout = x0.shape[3], (x1.shape[3] if x1 is not None else 0), weight.shape[0]
+        if (C0 % 8 == 0 and C1 % 8 == 0 and Cout % 8 == 0) or (C0 == 1 and C1 == 0 and Cout in (8, 16)):
+            db_in_wgrad = want_b and premasked and relu
+            sink = _sink(weight, db_in_wgrad)
+            if sink is None and db_in_wgrad:
+                sink = _sink(weight, False)
+    g, dx0, dx1, dw, db = conv3x3_bwd(dy, y, x0, x1, weight, want_b, relu, H, W, oy0, ox0, oy1, ox1, math,
+                                      need_dx, need[2], m0, m1, premasked,
+                                      sink[0].data_ptr() if sink is not None else 0,
+                                      sink[1].data_ptr() if (sink is not None and sink[1] is not None) else 0)
+    if sink is not None:
+        dw = sink[0]
+        if sink[1] is not None:
+            db = sink[1]
+        if WGRAD_SIDE_STREAMS:
+            _note_side(dw, sink[1])
     gres = None
     if has_res and need[4]:
         gres = g if ((relu or math in (MATH_TF32, MATH_MIXED)) and not (premasked and relu)) else dy
@@ -413,40 +474,45 @@ def _(x, weight, bias, round_out=False, mask_in=False, bwd_tf32=False):
 
 @torch.library.custom_op("pu::convT2x2s2_bwd", mutates_args=())
 def convT2x2s2_bwd(dy: Tensor, x: Tensor, weight: Tensor, need_dx: bool, need_dw: bool, need_db: bool,
-                   mask_in: bool = False, tf32: bool = False) -> List[Tensor]:
+                   mask_in: bool = False, tf32: bool = False, dw_ptr: int = 0, db_ptr: int = 0) -> List[Tensor]:
+    """dw_ptr and db_ptr != 0: the (zeroed) gradient-arena slots the kernels accumulate into (GRAD_SINK); dw / db are returned empty."""
     _chk(dy, x, weight)
     B, H, W, Cin = x.shape
     Cout = weight.shape[1]
     dx = torch.empty_like(x) if need_dx else _e(x.device)
-    dw = torch.empty_like(weight) if need_dw else _e(x.device)
-    db = torch.empty(Cout, device=x.device, dtype=torch.float32) if need_db else _e(x.device)
-    flags = (FLAG_MASK_IN if mask_in else 0) | (FLAG_TF32_MATH if tf32 else 0)
+    sunk = bool(dw_ptr and db_ptr and need_dw and need_db)
+    dw = torch.empty_like(weight) if (need_dw and not sunk) else _e(x.device)
+    db = torch.empty(Cout, device=x.device, dtype=torch.float32) if (need_db and not sunk) else _e(x.device)
+    flags = (FLAG_MASK_IN if mask_in else 0) | (FLAG_TF32_MATH if tf32 else 0) | (FLAG_ACCUM_GRADS if sunk else 0)
+    dwp = dw_ptr if sunk else (dw.data_ptr() if need_dw else None)
+    dbp = db_ptr if sunk else (db.data_ptr() if need_db else None)
     side = _side_stream()
     if side is not None and (need_dw or need_db):
         # dx on the current stream; the parameter gradients (not needed before the optimizer) on the side stream
+        fork = _fork_point()
         if need_dx:
             _lib.call("pu_convT2x2s2_bwd", x.data_ptr(), weight.data_ptr(), dy.data_ptr(), dx.data_ptr(), None, None,
                       B, H, W, Cin, Cout, flags, _s())
         main = torch.cuda.current_stream()
-        side.wait_stream(main)
+        side.wait_event(fork)
         with torch.cuda.stream(side):
-            _lib.call("pu_convT2x2s2_bwd", x.data_ptr(), weight.data_ptr(), dy.data_ptr(), None,
-                      dw.data_ptr() if need_dw else None, db.data_ptr() if need_db else None, B, H, W, Cin, Cout, flags, _s())
-        for t in (x, dy, dw if need_dw else None, db if need_db else None):
+            _lib.call("pu_convT2x2s2_bwd", x.data_ptr(), weight.data_ptr(), dy.data_ptr(), None, dwp, dbp, B, H, W, Cin, Cout, flags, _s())
+        for t in (x, dy, dw if (need_dw and not sunk) else None, db if (need_db and not sunk) else None):
             if t is not None:
                 t.record_stream(side)
-        _note_side(dw if need_dw else None, db if need_db else None)
+        _note_side(dw if (need_dw and not sunk) else None, db if (need_db and not sunk) else None)
     else:
         _lib.call("pu_convT2x2s2_bwd", x.data_ptr(), weight.data_ptr(), dy.data_ptr(), dx.data_ptr() if need_dx else None,
-                  dw.data_ptr() if need_dw else None, db.data_ptr() if need_db else None, B, H, W, Cin, Cout, flags, _s())
+                  dwp, dbp, B, H, W, Cin, Cout, flags, _s())
     return [dx, dw, db]
 
 
 @convT2x2s2_bwd.register_fake
-def _(dy, x, weight, need_dx, need_dw, need_db, mask_in=False, tf32=False):
+def _(dy, x, weight, need_dx, need_dw, need_db, mask_in=False, tf32=False, dw_ptr=0, db_ptr=0):
     e = x.new_empty(0)
-    return [torch.empty_like(x) if need_dx else e, torch.empty_like(weight) if need_dw else e,
-            x.new_empty(weight.shape[1]) if need_db else e]
+    sunk = bool(dw_ptr and db_ptr and need_dw and need_db)
+    return [torch.empty_like(x) if need_dx else e, torch.empty_like(weight) if (need_dw and not sunk) else e,
+            x.new_empty(weight.shape[1]) if (need_db and not sunk) else e]
 
 
 def _convT2_setup(ctx, inputs, output):
@@ -460,7 +526,16 @@ def _convT2_setup(ctx, inputs, output):
 def _convT2_backward(ctx, dy):
     x, weight = ctx.saved_tensors
     need = ctx.needs_input_grad
-    dx, dw, db = convT2x2s2_bwd(dy.contiguous(), x, weight, need[0], need[1], ctx.has_bias and need[2], ctx.mask_in, ctx.tf32)
+    Cin, Cout = weight.shape[0], weight.shape[1]
+    sink = None
+    if ctx.tf32 and need[1] and ctx.has_bias and need[2] and Cin == Cout and Cin in (8, 16, 32, 64):  # the tensor-core kernels' shapes
+        sink = _sink(weight, True)
+    dx, dw, db = convT2x2s2_bwd(dy.contiguous(), x, weight, need[0], need[1], ctx.has_bias and need[2], ctx.mask_in, ctx.tf32,
+                                sink[0].data_ptr() if sink is not None else 0, sink[1].data_ptr() if sink is not None else 0)
+    if sink is not None:
+        dw, db = sink
+        if WGRAD_SIDE_STREAMS:
+            _note_side(dw, db)
     return dx if need[0] else None, dw if need[1] else None, db if (ctx.has_bias and need[2]) else None, None, None, None
 
 

@@ -84,6 +84,18 @@ class TrainStep:
             self.flat_p[o:o + p.numel()].copy_(p.data.reshape(-1))
             p.data = self.flat_p[o:o + p.numel()].view_as(p)
             p.grad = None
+        # gradient sink (ops.GRAD_SINK): backward ops whose kernels can accumulate write dw / db straight into their arena slots
+        # (zeroed once per step): no memset launches per op, and those parameters need no gather.  PU_GRAD_SINK=0 disables.
+        self._sink = None
+        if os.environ.get("PU_GRAD_SINK", "0") == "1":
+            slot = {id(p): (o, p.numel()) for p, o in zip(params, self.offsets)}
+            self._sink = {}
+            for m in net.modules():
+                w = getattr(m, "weight", None)
+                if isinstance(w, torch.nn.Parameter) and w.dim() == 4 and id(w) in slot:
+                    b = getattr(m, "bias", None)
+                    has_b = isinstance(b, torch.nn.Parameter) and id(b) in slot
+                    self._sink[w.data_ptr()] = (self.flat_g, slot[id(w)][0], slot[id(b)][0] if has_b else -1, slot[id(b)][1] if has_b else 0)
         # (pointer, offset, size) table of the gradient tensors, rebuilt by every eager/captured step body
         self.table_host = torch.zeros((len(params), 3), dtype=torch.int64).pin_memory()
         self.table_dev = torch.zeros((len(params), 3), dtype=torch.int64, device=self.dev)
@@ -98,6 +110,7 @@ class TrainStep:
         self.hebb = net.initialZeroHebb()
         self.loss = torch.zeros(1, device=self.dev)
         self.graph = None
+        self._table_early = False
         self.kernels_per_step = None
         self.use_graph = use_graph
         self._warm = warmup
@@ -133,6 +146,11 @@ class TrainStep:
         st = torch.cuda.current_stream().cuda_stream
         for p in self.params:
             p.grad = None  # autograd then hands over its gradient tensors instead of launching one add per parameter
+        # Under capture the pointer table of the gradient gather is uploaded at the START of the step (a memcpy node reads the
+        # pinned host table at replay time, and the table is final when the capture ends): 3 us off the step's tail.
+        self._table_early = torch.cuda.is_current_stream_capturing()
+        if self._table_early:
+            self.table_dev.copy_(self.table_host, non_blocking=True)
         self.flat_g.zero_()
         if self._pack_list is None:
             ops.PACK_LOG, ops.PACK_CACHE = [], None  # first eager step: learn which weights the step packs
@@ -155,13 +173,17 @@ class TrainStep:
     def _gather(self, which, table_host, table_dev):
         """One-launch gather of the gradients of the parameters selected by `which(p)` into their flat_g slots."""
         n = 0
+        base = self.flat_g.data_ptr()
         for p, o in zip(self.params, self.offsets):
             if p.grad is not None and which(p):
                 g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
+                if g.data_ptr() == base + 4 * o:
+                    continue  # written in place through the gradient sink
                 table_host[n, 0], table_host[n, 1], table_host[n, 2] = g.data_ptr(), o, g.numel()
                 n += 1
         if n:
-            table_dev.copy_(table_host, non_blocking=torch.cuda.is_current_stream_capturing())
+            if not (self._table_early and table_dev is self.table_dev):
+                table_dev.copy_(table_host, non_blocking=torch.cuda.is_current_stream_capturing())
             _lib.call("pu_gather_flat", table_dev.data_ptr(), n, self.flat_g.data_ptr(), torch.cuda.current_stream().cuda_stream)
 
     def _early_reduce(self, _grad):
@@ -201,9 +223,11 @@ class TrainStep:
             ops.WGRAD_SIDE_STREAMS = self.wgrad_side
         if check:
             ops.SIDE_OUTPUTS = set()
+        ops.GRAD_SINK = self._sink
         try:
             out.backward(gS)
         finally:
+            ops.GRAD_SINK = None
             ops.WGRAD_SIDE_STREAMS = None
             side_ptrs, ops.SIDE_OUTPUTS = ops.SIDE_OUTPUTS, None
         if check:

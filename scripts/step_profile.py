@@ -29,6 +29,7 @@ ap.add_argument("--neurons", type=int, default=16)
 ap.add_argument("--depth", type=int, default=4)
 ap.add_argument("--steps", type=int, default=5)
 ap.add_argument("--order", action="store_true", help="also print the kernels of the last step in launch order")
+ap.add_argument("--timeline", action="store_true", help="also print the last step as a per-stream timeline (start, end, stream, kernel)")
 args = ap.parse_args()
 os.environ["PU_WGRAD_SIDE"] = str(args.side)
 
@@ -53,7 +54,7 @@ with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
 evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
 agg = collections.OrderedDict()
 for e in evs:
-    k = e.name.split("(")[0].replace("void ", "").replace("pu::", "")
+    k = e.name.replace("(anonymous namespace)::", "").split("(")[0].replace("void ", "").replace("pu::", "")
     a = agg.setdefault(k, [0, 0.0])
     a[0] += 1
     a[1] += e.device_time if hasattr(e, "device_time") else e.cuda_time
@@ -71,3 +72,17 @@ if args.order:
     for e in evs[-per:]:
         print("%9.1f %8.2f  %s" % (e.time_range.start - t0, e.device_time if hasattr(e, "device_time") else e.cuda_time,
                                    e.name.split("(")[0].replace("void ", "").replace("pu::", "")[:80]))
+
+if args.timeline:
+    # kineto events carry the stream (device_resource_id): one line per kernel, start / end relative to the step's first kernel
+    kev = [e for e in prof.profiler.kineto_results.events() if "cuda" in str(e.device_type()).lower()]
+    kev.sort(key=lambda e: e.start_ns())
+    per = len(kev) // args.steps
+    last = kev[-per:]
+    t0 = last[0].start_ns()
+    streams = {}
+    print("\n# last step timeline: start us, end us, stream, kernel   (stream 0 = the step's main stream)")
+    for e in last:
+        sid = streams.setdefault(e.device_resource_id(), len(streams))
+        nm = e.name().replace("(anonymous namespace)::", "").split("(")[0].replace("void ", "").replace("pu::", "")[:60]
+        print("%9.1f %9.1f  s%d  %s" % ((e.start_ns() - t0) / 1e3, (e.start_ns() + e.duration_ns() - t0) / 1e3, sid, nm))
