@@ -34,11 +34,13 @@ int conv3x3_fwd_ffma(const Conv3x3Args& a, cudaStream_t st);
 // one-input-channel stem (stem.cu)
 bool conv3x3_c1_ok(int Cin, int Cout);
 int conv3x3_c1_fwd(const Conv3x3Args& a, cudaStream_t st);
-int conv3x3_c1_wgrad(const WgradArgs& a, cudaStream_t st);
+int conv3x3_c1_wgrad(const WgradArgs& a, cudaStream_t st, int math);
 int conv3x3_wgrad_ffma(const WgradArgs& a, cudaStream_t st, int math);
 // TMA-fed mma.sync weight gradient (conv3x3_wgrad_tma.cu): TF32 mode, channel counts that are multiples of 8
 bool conv3x3_wgrad_tma_ok(const WgradArgs& a);
 int conv3x3_wgrad_tma(const WgradArgs& a, cudaStream_t st);
+bool conv3x3_c1_wgrad_tma_ok(const WgradArgs& a);               // the one-channel stem through TMA + MMA (aligned inputs)
+int conv3x3_c1_wgrad_tma(const WgradArgs& a, cudaStream_t st);  // dw / db zeroed by the caller
 // tcgen05 path (conv3x3_tc.cu); returns PU_ERR_UNSUPPORTED when the shape does not fit it
 int conv3x3_fwd_tc(const Conv3x3Args& a, cudaStream_t st);
 bool conv3x3_tc_ok(int C0, int C1, int Cout, int Cd0, int Cd1);

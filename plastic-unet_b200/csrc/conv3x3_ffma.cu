@@ -784,7 +784,7 @@ int conv3x3_fwd_ffma(const Conv3x3Args& a0, cudaStream_t st) {
 }
 
 int conv3x3_wgrad_ffma(const WgradArgs& a0, cudaStream_t st, int math) {
-  if (conv3x3_c1_ok(a0.Cin, a0.Cout) && (a0.s1.p == nullptr || a0.s1.C == 0)) return conv3x3_c1_wgrad(a0, st);  // streaming stem kernel (dw + db)
+  if (conv3x3_c1_ok(a0.Cin, a0.Cout) && (a0.s1.p == nullptr || a0.s1.C == 0)) return conv3x3_c1_wgrad(a0, st, math);  // stem kernels (dw + db)
   WgradArgs a = a0;
   {
     static int dbg = -1;

@@ -1097,6 +1097,32 @@ int tma_make_window_map_merged(CUtensorMap* tm, const View& v, int B, int H, int
   return PU_OK;
 }
 
+// A 3-D fp32 tensor map over the H x W window of a ONE-channel NHWC tensor ([B, Hs, Ws]), box = (bw, bh, bn): the stem's input
+// for its TMA-fed weight gradient.  Needs a 16-byte aligned window origin and row pitch (PU_ERR_UNSUPPORTED otherwise).
+int tma_make_plane_map(CUtensorMap* tm, const View& v, int B, int H, int W, int bw, int bh, int bn) {
+  if (!tc_init()) {
+    set_error("tensor maps are unavailable on this device (cuTensorMapEncodeTiled)");
+    return PU_ERR_UNSUPPORTED;
+  }
+  const float* base = v.p + (size_t)v.oy * v.Ws + v.ox;
+  if (v.C != 1 || (reinterpret_cast<uintptr_t>(base) & 15u) != 0 || v.Ws % 4 != 0 || bw % 4 != 0 || bw > 256) {
+    set_error("tma_make_plane_map: needs C == 1, a 16-byte aligned window and row pitch, and a box row of 4..256 elements");
+    return PU_ERR_UNSUPPORTED;
+  }
+  cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[2] = {(cuuint64_t)v.Ws * 4, (cuuint64_t)v.Hs * v.Ws * 4};
+  cuuint32_t box[3] = {(cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (CUresult %d) for plane window %dx%d box (%d,%d,%d)", (int)r, H, W, bw, bh, bn);
+    return PU_ERR_CUDA;
+  }
+  return PU_OK;
+}
+
 bool conv3x3_tc_ok(int C0, int C1, int Cout, int Cd0, int Cd1) {
   if (!tc_init()) return false;
   TcPlan p;

@@ -146,29 +146,34 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv3x3_wgrad_tma_kernel(const 
       // strips that lie entirely outside the image (ragged sizes, batch tail) hold zeros only
       const bool live = tx * a.TW + sx * 8 < a.W && ty * a.TH + sy * 8 < a.H && tb * a.NB + nb < a.B && !(a.debug & 4);
       if (live) {
-        const unsigned* xs = reinterpret_cast<const unsigned*>(smem + (size_t)st * stage_bytes + pg * a.xplane) + xoff;
-        const unsigned* gs = reinterpret_cast<const unsigned*>(smem + (size_t)st * stage_bytes + NCI * a.xplane) + goff;
+        // shared-space byte addresses of this lane's first fragment element in its x plane (halo row 0) and in the g planes
+        const uint32_t sbase = smem_addr(smem) + (uint32_t)st * (uint32_t)stage_bytes;
+        uint32_t xa = sbase + (uint32_t)(pg * a.xplane) + 4u * (uint32_t)xoff;
+        uint32_t ga[NCO];
+#pragma unroll
+        for (int n = 0; n < NCO; ++n) ga[n] = sbase + (uint32_t)(NCI * a.xplane + n * a.gplane) + 4u * (uint32_t)goff;
+        const uint32_t xrow_b = 4u * (uint32_t)xrow, grow_b = 4u * (uint32_t)grow;
         // win[r % 3][kx][half]: the A-fragment elements of halo row r: pixel (tq + kx) and (tq + kx + 4), channel gq
         unsigned win[3][3][2];
 #pragma unroll
-        for (int r = 0; r < 2; ++r)
-#pragma unroll
-          for (int kx = 0; kx < 3; ++kx) {
-            win[r][kx][0] = xs[r * xrow + kx * 8];
-            win[r][kx][1] = xs[r * xrow + (kx + 4) * 8];
-          }
+        for (int r = 0; r < 2; ++r) {
+          win[r][0][0] = wg_lds<0>(xa);   win[r][0][1] = wg_lds<128>(xa);
+          win[r][1][0] = wg_lds<32>(xa);  win[r][1][1] = wg_lds<160>(xa);
+          win[r][2][0] = wg_lds<64>(xa);  win[r][2][1] = wg_lds<192>(xa);
+          xa += xrow_b;
+        }
 #pragma unroll
         for (int yy = 0; yy < 8; ++yy) {
-#pragma unroll
-          for (int kx = 0; kx < 3; ++kx) {
-            win[(yy + 2) % 3][kx][0] = xs[(yy + 2) * xrow + kx * 8];
-            win[(yy + 2) % 3][kx][1] = xs[(yy + 2) * xrow + (kx + 4) * 8];
-          }
+          win[(yy + 2) % 3][0][0] = wg_lds<0>(xa);   win[(yy + 2) % 3][0][1] = wg_lds<128>(xa);
+          win[(yy + 2) % 3][1][0] = wg_lds<32>(xa);  win[(yy + 2) % 3][1][1] = wg_lds<160>(xa);
+          win[(yy + 2) % 3][2][0] = wg_lds<64>(xa);  win[(yy + 2) % 3][2][1] = wg_lds<192>(xa);
+          xa += xrow_b;
 #pragma unroll
           for (int n = 0; n < NCO; ++n) {
             // B fragment: k = pixel (tq, tq + 4), n = co (gq)
-            const unsigned b0 = gs[n * gpl + yy * grow];
-            const unsigned b1 = gs[n * gpl + yy * grow + 32];
+            const unsigned b0 = wg_lds<0>(ga[n]);
+            const unsigned b1 = wg_lds<128>(ga[n]);
+            ga[n] += grow_b;
             if (a.debug & 2) {  // (experiment) fragment loads without MMAs
 #pragma unroll
               for (int t = 0; t < 9; ++t)
@@ -264,6 +269,166 @@ int launch_wg(const CUtensorMap& tmx0, const CUtensorMap& tmx1, const CUtensorMa
   return post_launch("conv3x3_wgrad_tma");
 }
 
+// ---- the one-input-channel stem (reference unet_p.py:105 via inconv) ----------------------------------------------------------
+// dw[co][0][tap] = sum_p x[p + tap] g[p][co], db[co] = sum_p g[p][co]: ONE MMA per 8 pixels and co tile — A rows 0..8 are the nine
+// taps (row r, k = pixel j: x[p_j + tap_r], 32-bit loads from the [y][x] plane of the input), row 9 is ones (bias gradient),
+// B = the g plane.  The plane rows are XW = TW + 8 (20 for TW = 8) words apart, so the three tap rows of a fragment load fall
+// into disjoint banks; the box starts at x0 - 4 (16-byte aligned in memory), pixel x0 - 1 is column 3.  This is the LAST weight gradient of the backward pass (its g is the data gradient of the second conv):
+// nothing overlaps it.  The thread-per-pixel kernel in stem.cu (kept for unaligned inputs) took 30 us for these 38 MB: 14 M warp
+// instructions, four warps per scheduler waiting on dependent loads (ncu: profiles/r2_wgrad_ncu_summary.md).
+struct WgStemArgs {
+  float* dw;
+  float* db;
+  int B, H, W, Cout;
+  int TW, TH, NB, XW;
+  int tilesX, tilesY, tilesB, ntiles;
+  int xplane, gplane, xbox, gbox;
+  int nstages, gmerged, vec4;
+};
+
+__device__ __forceinline__ unsigned tf32_bits(unsigned x) {
+  unsigned r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(__uint_as_float(x)));
+  return r;
+}
+
+template <int NCO>
+__global__ void __launch_bounds__(kWgThreads, 1) conv3x3_c1_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmx,
+                                                                             const __grid_constant__ CUtensorMap tmg, const WgStemArgs a) {
+  extern __shared__ uint8_t wg_smem_raw[];
+  uint8_t* smem = wg_smem_raw + ((128u - (smem_addr(wg_smem_raw) & 127u)) & 127u);
+  const int stage_bytes = a.xplane + NCO * a.gplane;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)a.nstages * stage_bytes);
+  const uint32_t bar0 = smem_addr(bars);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int co0 = (int)blockIdx.y * 8 * NCO;
+  if (tid == 0) {
+    for (int i = 0; i < kWgMaxStages; ++i) {
+      wg_mbar_init(bar0 + 8u * i, 1);
+      wg_mbar_init(bar0 + 8u * (kWgMaxStages + i), kWgWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmx)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmg)) : "memory");
+  }
+  __syncthreads();
+  pdl_prologue();
+  float acc[NCO][4];
+#pragma unroll
+  for (int n = 0; n < NCO; ++n)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[n][j] = 0.f;
+  const int tiles_img = a.tilesX * a.tilesY;
+  if (warp == kWgWarps) {
+    int k = 0;
+    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++k) {
+      const int tb = tile / tiles_img, tr = tile - tb * tiles_img;
+      const int ty = tr / a.tilesX, tx = tr - ty * a.tilesX;
+      const int x0 = tx * a.TW, y0 = ty * a.TH, b0 = tb * a.NB;
+      const int st = k % a.nstages;
+      const uint32_t ph = (uint32_t)(k / a.nstages) & 1;
+      wg_mbar_wait(bar0 + 8u * (kWgMaxStages + st), ph ^ 1);
+      if (lane == 0) {
+        const uint32_t full = bar0 + 8u * st;
+        wg_mbar_expect_tx(full, (uint32_t)(a.xbox + NCO * a.gbox));
+        const uint32_t sS = smem_addr(smem + (size_t)st * stage_bytes);
+        wg_tma_load_3d(sS, &tmx, full, x0 - 4, y0 - 1, b0);  // the box starts 16-byte aligned in memory: column 3 = pixel x0 - 1
+        if (a.gmerged) {
+          wg_tma_load_3d(sS + a.xplane, &tmg, full, 8 * x0, y0, b0);
+        } else {
+#pragma unroll
+          for (int n = 0; n < NCO; ++n) wg_tma_load_4d(sS + a.xplane + n * a.gplane, &tmg, full, co0 + 8 * n, x0, y0, b0);
+        }
+      }
+      __syncwarp();
+    }
+  } else {
+    const int gq = lane >> 2, tq = lane & 3;
+    const int tws = a.TW >> 3, ths = a.TH >> 3;
+    const int sx = warp % tws, sy = (warp / tws) % ths, nb = warp / (tws * ths);
+    // rows 0..7 of A: tap gq = (ky, kx); row 8 (lane group 0): tap 8; row 9 (lane group 1): ones; rows 10..15: zero
+    const int xoff = (nb * (a.TH + 2) + sy * 8 + gq / 3) * a.XW + sx * 8 + tq + gq % 3 + 3;
+    const int xoff8 = (nb * (a.TH + 2) + sy * 8 + 2) * a.XW + sx * 8 + tq + 2 + 3;
+    const int goff = ((nb * a.TH + sy * 8) * a.TW + sx * 8 + tq) * 8 + gq;
+    const int grow = a.TW * 8, gpl = a.gplane >> 2;
+    int k = 0;
+    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++k) {
+      const int tb = tile / tiles_img, tr = tile - tb * tiles_img;
+      const int ty = tr / a.tilesX, tx = tr - ty * a.tilesX;
+      const int st = k % a.nstages;
+      const uint32_t ph = (uint32_t)(k / a.nstages) & 1;
+      wg_mbar_wait(bar0 + 8u * st, ph);
+      const bool live = tx * a.TW + sx * 8 < a.W && ty * a.TH + sy * 8 < a.H && tb * a.NB + nb < a.B;
+      if (live) {
+        const unsigned* xs = reinterpret_cast<const unsigned*>(smem + (size_t)st * stage_bytes);
+        const unsigned* gs = reinterpret_cast<const unsigned*>(smem + (size_t)st * stage_bytes + a.xplane) + goff;
+#pragma unroll
+        for (int yy = 0; yy < 8; ++yy) {
+          // the network input is not stored TF32-rounded (the forward stem is an fp32 FFMA kernel): round here, RN like every
+          // other tensor-core operand (the MMA itself would truncate)
+          const unsigned a0 = tf32_bits(xs[xoff + yy * a.XW]), a2 = tf32_bits(xs[xoff + yy * a.XW + 4]);
+          const unsigned t0 = tf32_bits(xs[xoff8 + yy * a.XW]), t2 = tf32_bits(xs[xoff8 + yy * a.XW + 4]);
+          const unsigned a1 = gq == 0 ? t0 : (gq == 1 ? 0x3f800000u : 0u);
+          const unsigned a3 = gq == 0 ? t2 : (gq == 1 ? 0x3f800000u : 0u);
+#pragma unroll
+          for (int n = 0; n < NCO; ++n) wg_mma(acc[n], a0, a1, a2, a3, gs[n * gpl + yy * grow], gs[n * gpl + yy * grow + 32]);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) wg_mbar_arrive(bar0 + 8u * (kWgMaxStages + st));
+    }
+  }
+  __syncthreads();
+  float* red = reinterpret_cast<float*>(smem);  // [NCO * 4][kWgWarps * 32]
+  if (warp < kWgWarps) {
+#pragma unroll
+    for (int n = 0; n < NCO; ++n)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) red[(n * 4 + j) * (kWgWarps * 32) + warp * 32 + lane] = acc[n][j];
+  }
+  __syncthreads();
+  // output e of this CTA: e < 72 NCO: dw[(co0 + e / 9)][tap e % 9] (contiguous floats); then db[co0 + e - 72 NCO]
+  auto total = [&](int e) {
+    int row, col;
+    if (e < 72 * NCO) { col = e / 9; row = e - col * 9; } else { col = e - 72 * NCO; row = 9; }
+    const int n = col >> 3, c = col & 7;
+    const int ln = (row & 7) * 4 + (c >> 1), j = ((row >> 3) << 1) | (c & 1);
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < kWgWarps; ++w) t += red[(n * 4 + j) * (kWgWarps * 32) + w * 32 + ln];
+    return t;
+  };
+  const int nout = (a.db != nullptr ? 80 : 72) * NCO;
+  if (a.vec4) {
+    for (int i = tid; i < nout / 4; i += kWgThreads) {
+      const int e = 4 * i;
+      float* dst = e < 72 * NCO ? a.dw + (size_t)co0 * 9 + e : a.db + co0 + (e - 72 * NCO);
+      wg_red_add_v4(dst, total(e), total(e + 1), total(e + 2), total(e + 3));
+    }
+  } else {
+    for (int e = tid; e < nout; e += kWgThreads) atomicAdd(e < 72 * NCO ? a.dw + (size_t)co0 * 9 + e : a.db + co0 + (e - 72 * NCO), total(e));
+  }
+}
+
+template <int NCO>
+int launch_wg_stem(const CUtensorMap& tmx, const CUtensorMap& tmg, const WgStemArgs& wa, dim3 grid, size_t smem, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv3x3_c1_wgrad_tma_kernel<NCO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) {
+      set_error("conv3x3_c1_wgrad_tma: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return PU_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  cudaError_t le = launch_pdl(conv3x3_c1_wgrad_tma_kernel<NCO>, grid, dim3(kWgThreads), smem, st, tmx, tmg, wa);
+  if (le != cudaSuccess) {
+    set_error("conv3x3_c1_wgrad_tma launch: %s", cudaGetErrorString(le));
+    return PU_ERR_CUDA;
+  }
+  return post_launch("conv3x3_wgrad_tma (stem)");
+}
+
 inline int pow2_le(int v, int cap) {
   int p = cap;
   while (p > 1 && v % p != 0) p >>= 1;
@@ -331,6 +496,69 @@ bool conv3x3_wgrad_tma_ok(const WgradArgs& a) {
   WgPlan p;
   const int C1 = (a.s1.p != nullptr) ? a.s1.C : 0;
   return wg_plan(a.B, a.H, a.W, a.s0.C, C1, a.Cout, &p);
+}
+
+// The stem through TMA + MMA: needs a 16-byte aligned one-channel input window (else the streaming kernel of stem.cu runs).
+bool conv3x3_c1_wgrad_tma_ok(const WgradArgs& a) {
+  if (a.s0.C != 1 || (a.s1.p != nullptr && a.s1.C > 0) || a.Cout % 8 != 0 || a.Cout > 64) return false;
+  const float* base = a.s0.p + (size_t)a.s0.oy * a.s0.Ws + a.s0.ox;
+  return (reinterpret_cast<uintptr_t>(base) & 15u) == 0 && a.s0.Ws % 4 == 0 && (reinterpret_cast<uintptr_t>(a.g) & 15u) == 0;
+}
+
+// dw / db zeroed by the caller
+int conv3x3_c1_wgrad_tma(const WgradArgs& a, cudaStream_t st) {
+  const int nco = (a.Cout / 8) % 2 == 0 ? 2 : 1;
+  WgStemArgs wa;
+  wa.dw = a.dw; wa.db = a.db; wa.B = a.B; wa.H = a.H; wa.W = a.W; wa.Cout = a.Cout;
+  // tile: NB images x (8 ths) x (8 tws) pixels, 16 strips; least staged bytes
+  double best = 1e30;
+  wa.TW = 0;
+  for (int tws = 1; tws <= kWgWarps; tws <<= 1)
+    for (int ths = 1; tws * ths <= kWgWarps; ths <<= 1) {
+      const int nb = kWgWarps / (tws * ths);
+      if (nb > 16) continue;
+      const int tw = 8 * tws, th = 8 * ths;
+      if (a.Cout == 8 && 8 * tw > 256) continue;  // merged g rows
+      const int xw = tw == 8 ? 20 : tw + 8;  // >= TW + 5 (the box starts at x0 - 4), rows of the three taps in disjoint banks
+      const long long tiles = (long long)cdiv(a.W, tw) * cdiv(a.H, th) * cdiv(a.B, nb);
+      const double cost = (double)tiles * ((double)xw * (th + 2) * nb / 8.0 + (double)tw * th * nb * nco + 256.0);
+      if (cost < best) {
+        best = cost;
+        wa.TW = tw; wa.TH = th; wa.NB = nb; wa.XW = xw;
+      }
+    }
+  wa.tilesX = cdiv(a.W, wa.TW); wa.tilesY = cdiv(a.H, wa.TH); wa.tilesB = cdiv(a.B, wa.NB);
+  wa.ntiles = wa.tilesX * wa.tilesY * wa.tilesB;
+  wa.xbox = wa.XW * (wa.TH + 2) * wa.NB * 4;
+  wa.gbox = wa.TW * wa.TH * wa.NB * 32;
+  wa.xplane = (wa.xbox + 127) / 128 * 128;
+  wa.gplane = (wa.gbox + 127) / 128 * 128;
+  const size_t stage = (size_t)wa.xplane + (size_t)nco * wa.gplane;
+  int gx = wa.ntiles < kNumSMs ? wa.ntiles : kNumSMs;
+  const int gy = a.Cout / (8 * nco);
+  if (gy > 1) gx = gx / gy > 0 ? gx / gy : 1;
+  const int per_cta = (wa.ntiles + gx - 1) / gx;
+  int ns = (int)((size_t)218 * 1024 / stage);
+  if (ns > kWgMaxStages) ns = kWgMaxStages;
+  if (ns > per_cta) ns = per_cta;
+  if (ns < 1) ns = 1;
+  wa.nstages = ns;
+  size_t ring = (size_t)ns * stage;
+  const size_t red = (size_t)kWgWarps * 32 * 4 * nco * sizeof(float);
+  if (ring < red) ring = red;
+  const size_t smem = ring + 2 * kWgMaxStages * 8 + 128;
+  CUtensorMap tmx, tmg;
+  int rc = tma_make_plane_map(&tmx, a.s0, a.B, a.H, a.W, wa.XW, wa.TH + 2, wa.NB);
+  if (rc) return rc;
+  const View gv{a.g, a.H, a.W, a.Cout, 0, 0};
+  wa.gmerged = a.Cout == 8 ? 1 : 0;
+  if (wa.gmerged) rc = tma_make_window_map_merged(&tmg, gv, a.B, a.H, a.W, wa.TW, wa.TH, wa.NB);
+  else rc = tma_make_window_map(&tmg, gv, a.B, a.H, a.W, 8, wa.TW, wa.TH, wa.NB);
+  if (rc) return rc;
+  wa.vec4 = ((reinterpret_cast<uintptr_t>(a.dw) | (a.db != nullptr ? reinterpret_cast<uintptr_t>(a.db) : 0)) & 15u) == 0 ? 1 : 0;
+  const dim3 grid(gx, gy);
+  if (nco == 2) return launch_wg_stem<2>(tmx, tmg, wa, grid, smem, st);
+  return launch_wg_stem<1>(tmx, tmg, wa, grid, smem, st);
 }
 
 int conv3x3_wgrad_tma(const WgradArgs& a, cudaStream_t st) {

@@ -4,6 +4,7 @@
 // write 4*Cout bytes per pixel forward; read x and g once for the weight gradient.  The generic kernels (shared-memory
 // channel planes / pixel-major tiles built for Cin >= 8) spent 22 us (forward) and 42 + 13 us (wgrad + separate bias
 // pass) on it; these one-thread-per-pixel kernels stay close to the HBM time of the 33.5 MB activation.
+#include <stdlib.h>
 #include "conv3x3.cuh"
 
 namespace pu {
@@ -31,21 +32,35 @@ __global__ void __launch_bounds__(256) conv3x3_c1_fwd_kernel(const View s0, cons
     if (x >= W) { x -= W; ++y; }
     if (y >= H) { y -= H; ++b; }
     float xv[9];
+    const float* ctr = s0.p + ((size_t)b * s0.Hs + (y + s0.oy)) * s0.Ws + (x + s0.ox);
+    if (x >= 1 && x < W - 1 && y >= 1 && y < H - 1) {  // interior pixel: nine unchecked loads around one pointer
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky)
+      for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const int gy = y + ky - 1, gx = x + kx - 1;
-        const bool ok = gy >= 0 && gy < H && gx >= 0 && gx < W;
-        xv[ky * 3 + kx] = ok ? __ldg(s0.p + ((size_t)b * s0.Hs + (gy + s0.oy)) * s0.Ws + (gx + s0.ox)) : 0.f;
-      }
+        for (int kx = 0; kx < 3; ++kx) xv[ky * 3 + kx] = __ldg(ctr + (ky - 1) * s0.Ws + (kx - 1));
+    } else {
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int gy = y + ky - 1, gx = x + kx - 1;
+          const bool ok = gy >= 0 && gy < H && gx >= 0 && gx < W;
+          xv[ky * 3 + kx] = ok ? __ldg(ctr + (ky - 1) * s0.Ws + (kx - 1)) : 0.f;
+        }
+    }
+    // packed FFMA2: two output channels per instruction, each lane pair is an ordinary fp32 FMA (same rounding, same order)
+    float2 acc2[CO / 2];
+#pragma unroll
+    for (int j = 0; j < CO / 2; ++j) acc2[j] = make_float2(bs[2 * j], bs[2 * j + 1]);
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const float2 xx = make_float2(xv[tap], xv[tap]);
+#pragma unroll
+      for (int j = 0; j < CO / 2; ++j) acc2[j] = __ffma2_rn(xx, *reinterpret_cast<const float2*>(&ws[tap][2 * j]), acc2[j]);
+    }
     float acc[CO];
 #pragma unroll
-    for (int j = 0; j < CO; ++j) acc[j] = bs[j];
-#pragma unroll
-    for (int tap = 0; tap < 9; ++tap)
-#pragma unroll
-      for (int j = 0; j < CO; ++j) acc[j] = fmaf(xv[tap], ws[tap][j], acc[j]);
+    for (int j = 0; j < CO / 2; ++j) { acc[2 * j] = acc2[j].x; acc[2 * j + 1] = acc2[j].y; }
     const size_t opix = ((size_t)b * d0.Hs + (y + d0.oy)) * d0.Ws + (x + d0.ox);
     float* o = d0.p + opix * d0.C;
     unsigned m = 0;
@@ -178,7 +193,7 @@ int conv3x3_c1_fwd(const Conv3x3Args& a, cudaStream_t st) {
 }
 
 // dw and db are zeroed here (unless the caller accumulates: PU_MATH_ACCUM)
-int conv3x3_c1_wgrad(const WgradArgs& a, cudaStream_t st) {
+int conv3x3_c1_wgrad(const WgradArgs& a, cudaStream_t st, int math) {
   cudaError_t e = cudaSuccess;
   if (!a.accum) {
     e = cudaMemsetAsync(a.dw, 0, sizeof(float) * a.Cout * 9, st);
@@ -187,6 +202,15 @@ int conv3x3_c1_wgrad(const WgradArgs& a, cudaStream_t st) {
   if (e != cudaSuccess) {
     set_error("conv3x3_wgrad (stem) memset: %s", cudaGetErrorString(e));
     return PU_ERR_CUDA;
+  }
+  {
+    static int ver = -1;  // PU_STEM_WGRAD_V=1: always the streaming kernel below (A/B measurements)
+    if (ver < 0) {
+      const char* e_ = getenv("PU_STEM_WGRAD_V");
+      ver = e_ ? atoi(e_) : 2;
+    }
+    // TF32 mode only: the strict-fp32 mode keeps the FFMA kernel below
+    if (math == PU_MATH_TF32 && ver != 1 && conv3x3_c1_wgrad_tma_ok(a)) return conv3x3_c1_wgrad_tma(a, st);
   }
   const long long npix = (long long)a.B * a.H * a.W;
   long long blocks = (npix + 256 * 16 - 1) / (256 * 16);  // >= 16 pixels per thread amortise the 10*CO-value reduction

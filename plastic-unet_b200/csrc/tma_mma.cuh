@@ -9,6 +9,7 @@ namespace pu {
 // tensor maps over an (oy, ox)-offset H x W window of an NHWC tensor (conv3x3_tc.cu); out-of-window coordinates zero-fill
 int tma_make_window_map(CUtensorMap* tm, const View& v, int B, int H, int W, int cb, int bw, int bh, int bn);
 int tma_make_window_map_merged(CUtensorMap* tm, const View& v, int B, int H, int W, int bw, int bh, int bn);
+int tma_make_plane_map(CUtensorMap* tm, const View& v, int B, int H, int W, int bw, int bh, int bn);  // one-channel tensor, 3-D
 
 namespace {
 
@@ -53,6 +54,15 @@ __device__ __forceinline__ void wg_tma_load_3d(uint32_t dst, const CUtensorMap* 
 }
 __device__ __forceinline__ void wg_red_add_v4(float* p, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+// 32-bit shared-memory load at [addr + OFF] (shared-space byte address, compile-time offset): the fragment loops walk the
+// operand planes with ONE 32-bit address per plane and immediate offsets instead of 64-bit generic-pointer arithmetic per load
+// (ncu of the first version: 32 % of all instructions were IMADs).  volatile: ordered after the mbarrier wait.
+template <int OFF>
+__device__ __forceinline__ unsigned wg_lds(uint32_t addr) {
+  unsigned v;
+  asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(OFF));
+  return v;
 }
 __device__ __forceinline__ void wg_mma(float (&c)[4], unsigned a0, unsigned a1, unsigned a2, unsigned a3, unsigned b0, unsigned b1) {
   asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"

@@ -70,6 +70,29 @@ def test_wgrad_tma_vs_float64(B, C0, C1, Cout, H, W, crop, with_bias):
         assert errb < 2e-5, errb
 
 
+@pytest.mark.parametrize("B,Cout,H,W,pad", [(2, 8, 128, 128, 0), (3, 16, 64, 64, 0), (5, 8, 40, 36, 0), (2, 8, 30, 44, 4), (1, 16, 8, 8, 0),
+                                            (2, 8, 37, 21, 0)])
+def test_stem_wgrad_tf32(B, Cout, H, W, pad):
+    """The one-input-channel stem in TF32 mode: TMA + MMA kernel (taps as the rows of ONE m16n8k8 tile per 8 pixels, ones row =
+    bias gradient) for 16-byte aligned inputs, the streaming FFMA kernel otherwise (W = 21).  The input image is rounded to TF32
+    inside the kernel, so the reference uses the rounded image."""
+    from pu_b200 import _lib
+    gen = torch.Generator().manual_seed(B + Cout + H + W)
+    x = torch.randn(B, H + pad, W + pad, 1, generator=gen).to(DEV)   # the op's window starts at (pad, pad) of a larger tensor
+    g = tf32_round(torch.randn(B, H, W, Cout, generator=gen)).to(DEV)
+    dw = torch.full((Cout, 1, 3, 3), float("nan"), device=DEV)
+    db = torch.full((Cout,), float("nan"), device=DEV)
+    _lib.call("pu_conv3x3_wgrad", x.data_ptr(), H + pad, W + pad, 1, pad, pad, None, 0, 0, 0, 0, 0,
+              g.data_ptr(), dw.data_ptr(), db.data_ptr(), B, H, W, Cout, 1, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    xw = x[:, pad:pad + H, pad:pad + W, :]
+    aligned = W % 4 == 0 and (W + pad) % 4 == 0 and pad % 4 == 0
+    dw_ref, db_ref = _ref(tf32_round(xw.cpu()).to(DEV) if aligned else xw, g)
+    err = float((dw.double() - dw_ref).abs().max() / dw_ref.abs().max())
+    errb = float((db.double() - db_ref).abs().max() / db_ref.abs().max())
+    assert err < 2e-5 and errb < 2e-5, (err, errb)
+
+
 def test_wgrad_tma_matches_first_kernel_bitwise_inputs():
     """A/B: the TMA-fed kernel and the cp.async-fed first version (PU_WGRAD_V=1, selected in a fresh process) see the same
     operands; both stay within the fp32 summation-order bound of the float64 result."""
