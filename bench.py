@@ -508,6 +508,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the legs for BASELINE configs 3-5, the kernel table and dp_check")
+    ap.add_argument("--dp-check", action="store_true", help="run dp_check (N > 1) even with --no-extras")
     ap.add_argument("--ref-images-per-step", type=int, default=16)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -650,7 +651,7 @@ def main():
     ms_med, e2e_ms_med = statistics.median(region_ms), statistics.median(e2e_regions)
 
     check = extras = None
-    if world > 1 and headline and not args.no_extras:
+    if world > 1 and headline and (not args.no_extras or args.dp_check):
         check = dp_check(net, ts, dev, group, world, rank, args.math)
     if headline and not args.no_extras:
         extras = run_extras(dev, group, world, args.math)

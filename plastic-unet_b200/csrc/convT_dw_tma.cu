@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(kCdThreads, 1) convT2x2_dw_tma_kernel(const __
     const int tws = a.TW >> 3, ths = a.TH >> 3;
     const int sx = ps % tws, sy = (ps / tws) % ths, nb = ps / (tws * ths);
     const int off = ((nb * a.TH + sy * 8) * a.TW + sx * 8 + tq) * 8 + gq;  // word offset of this lane's first element in a plane
-    const int row = a.TW * 8, pl = a.plane >> 2;
+    const int row = a.TW * 8;
     int k = 0;
     for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++k) {
       const int tb = tile / tiles_img, tr = tile - tb * tiles_img;
@@ -113,16 +113,24 @@ __global__ void __launch_bounds__(kCdThreads, 1) convT2x2_dw_tma_kernel(const __
       wg_mbar_wait(bar0 + 8u * st, ph);
       const bool live = tx * a.TW + sx * 8 < a.W && ty * a.TH + sy * 8 < a.H && tb * a.NB + nb < a.B;
       if (live) {
-        const unsigned* base = reinterpret_cast<const unsigned*>(smem + (size_t)st * stage_bytes) + off;
-        const unsigned* y0s = base + pg * pl;
-        const unsigned* y1s = base + (NPC + pg) * pl;
-        const unsigned* xs = base + 2 * NPC * pl;
+        // shared-space byte addresses of this lane's first element in its two dY planes and in the X planes (tma_mma.cuh: wg_lds)
+        const uint32_t sbase = smem_addr(smem) + (uint32_t)st * (uint32_t)stage_bytes + 4u * (uint32_t)off;
+        uint32_t y0a = sbase + (uint32_t)(pg * a.plane), y1a = sbase + (uint32_t)((NPC + pg) * a.plane);
+        uint32_t xa[NQ];
+#pragma unroll
+        for (int n = 0; n < NQ; ++n) xa[n] = sbase + (uint32_t)((2 * NPC + n) * a.plane);
+        const uint32_t row_b = 4u * (uint32_t)row;
 #pragma unroll
         for (int yy = 0; yy < 8; ++yy) {
           // A: rows 0-7 = dY_0 channels (gq), rows 8-15 = dY_1; k = pixels (tq, tq + 4)
-          const unsigned a0 = y0s[yy * row], a1 = y1s[yy * row], a2 = y0s[yy * row + 32], a3 = y1s[yy * row + 32];
+          const unsigned a0 = wg_lds<0>(y0a), a1 = wg_lds<0>(y1a), a2 = wg_lds<128>(y0a), a3 = wg_lds<128>(y1a);
+          y0a += row_b;
+          y1a += row_b;
 #pragma unroll
-          for (int n = 0; n < NQ; ++n) wg_mma(acc[n], a0, a1, a2, a3, xs[n * pl + yy * row], xs[n * pl + yy * row + 32]);
+          for (int n = 0; n < NQ; ++n) {
+            wg_mma(acc[n], a0, a1, a2, a3, wg_lds<0>(xa[n]), wg_lds<128>(xa[n]));
+            xa[n] += row_b;
+          }
           if (want_bias) wg_mma(acc[NQ], a0, a1, a2, a3, 0x3f800000u, 0x3f800000u);  // B = ones: column sums of dY
         }
       }

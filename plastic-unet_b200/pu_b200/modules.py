@@ -110,7 +110,7 @@ class _PlasticBase(nn.Module):
         self.trace_rows = 'row0'
         self.premask = True   # TF32 mode: fold each ReLU mask into its consumers' backward epilogues (UNetp / UNetpCoord)
         self.dp_group = None  # set by pu_b200.dp.attach() for the data-parallel trace all-reduce
-        self.dp_defer = False  # TrainStep: overlap the trace all-reduce with the backward pass (side stream)
+        self.dp_defer = False  # TrainStep: the trace update (and its DP all-reduce) runs on a side stream, off the critical path
         self.dp_side = None
         self.dp_world = 1
         # TrainStep (data parallel): a callback fired in the backward pass once the gradient w.r.t. the input of encoder level
@@ -181,6 +181,18 @@ class _PlasticBase(nn.Module):
             else:
                 dist.all_reduce(delta_q, op=dist.ReduceOp.SUM, group=self.dp_group)
                 hebb_new = ops.trace_apply(hebb.detach(), delta_q, self.eta.detach(), rule, kloc * self.dp_world)
+        elif getattr(self, "dp_defer", False) and S.is_cuda:
+            # TrainStep (single GPU): the loss does not depend on the new trace and the step detaches it (train.py:99), so the
+            # update leaves the critical path: side stream, joined by TrainStep before the optimizer (it reads eta)
+            if getattr(self, "dp_side", None) is None:
+                self.dp_side = torch.cuda.Stream()
+            main = torch.cuda.current_stream()
+            self.dp_side.wait_stream(main)
+            with torch.cuda.stream(self.dp_side):
+                hebb_new = ops.trace_update(hebb.detach(), X.detach(), S.detach(), self.eta.detach(), rule, N * N, B)
+            X.record_stream(self.dp_side)
+            S.record_stream(self.dp_side)
+            hebb_new.record_stream(main)
         else:
             # rows k of pre/post = row 0 of map k (reference keeps only [0] of the bmm)
             hebb_new = ops.trace_update(hebb, X, S, self.eta, rule, N * N, B)

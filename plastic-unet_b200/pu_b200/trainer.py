@@ -208,9 +208,9 @@ class TrainStep:
         self.net._bucket_hook = self._early_reduce if (self._late and self._grad_params is not None) else None
         if self._late:
             self.net._bucket_level = self._bucket_level
-        # the trace-delta all-reduce + epilogue overlap the backward pass on net.dp_side; only this step body defers them (it
-        # joins dp_side before Adam) — any other caller of net.forward gets the trace on its own stream
-        self.net.dp_defer = self.dp_group is not None
+        # the trace update (data parallel: the trace-delta all-reduce + epilogue) runs on net.dp_side, off the critical path; only
+        # this step body defers it (it joins dp_side before Adam) — any other caller of net.forward gets the trace on its own stream
+        self.net.dp_defer = True
         try:
             out, hebb_new = self.net(self.x, self.hebb)
         finally:
