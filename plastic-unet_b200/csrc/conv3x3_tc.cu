@@ -481,31 +481,64 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const __grid_
         const TcChunk& ch = a.chunks[c];
         const int st = it % nst;
         const uint32_t ph = (uint32_t)(it / nst) & 1;
+        // Everything the issue loop needs from the chunk table goes into registers BEFORE the wait for the data: one thread
+        // issues a tcgen05.mma only every ~128 clk and whatever sits between two issues (constant-bank loads of the chunk table,
+        // descriptor bit arithmetic) adds to that — measured 211 clk per MMA on the narrow flat layers with the arithmetic inside
+        // the loop.  A descriptor is affine in (ky, kx, k step, block): base descriptor + offset / 16.
+        const uint32_t sS = smem_u32(smem + st * stage_bytes);
+        const int nreg = ch.nreg, ncg_half = ch.ncg >> 1;
+        uint64_t a0[2];
+        uint32_t rbq[2];  // row bytes / 16: the descriptor step of one pixel row
+        int ksn[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const uint32_t rb = (uint32_t)ch.reg[r < nreg ? r : 0].cb * 4;  // row bytes = swizzle span
+          const uint32_t layout = rb == 32 ? 6u : (rb == 64 ? 4u : 2u);
+          // 8-row core groups: 6 rows apart when folded (rows 6,7 duplicate the next group's 0,1), canonical 8 when flat
+          a0[r] = umma_desc(sS + ch.reg[r < nreg ? r : 0].off, 16, (FOLD ? 6 : 8) * rb, layout);
+          rbq[r] = rb >> 4;
+          ksn[r] = ch.reg[r < nreg ? r : 0].cb >> 3;
+        }
+        const uint64_t b_base = umma_desc(a.wfmt == 0 ? sS + a.a_bytes : smem_u32(smWres) + ch.w_off, 16, 256, 6);
         mbar_wait(full_bar(st), ph);
         tc_fence_after();
         if (mw == 0 && lane == 0 && c == 0) stamp(1, k);
-        const uint32_t sS = smem_u32(smem + st * stage_bytes);
-        const uint64_t b_base = umma_desc(a.wfmt == 0 ? sS + a.a_bytes : smem_u32(smWres) + ch.w_off, 16, 256, 6);
         if (!FOLD) {
           // flat: every MMA warp owns whole 128-pixel blocks (the planner keeps nmb <= kMmaWarps, so one each) and issues
           // the nine taps of each 8-channel K step back to back — immediate descriptor offsets, no per-MMA loop control
-          for (int mb = mw; mb < a.nmb; mb += kMmaWarps) {
+          // Consecutive MMAs into the SAME accumulator wait for each other in the tensor pipe, so a warp that owns two blocks
+          // (narrow layers: nmb up to 6) alternates between them tap by tap (PU_TC_ILV=0: one block after the other)
+          const int mb2 = mw + kMmaWarps;
+          const bool two = mb2 < a.nmb && !(a.debug & 256);
+          for (int mb = mw; mb < a.nmb; mb += (two ? 2 : 1) * kMmaWarps) {
             const uint32_t d = d0 + (uint32_t)(mb * NACC);
+            const uint32_t dB = d + (uint32_t)(kMmaWarps * NACC);
             for (int ky = 0; ky < 3; ++ky) {
               uint32_t kc = 0;
-              for (int r = 0; r < ch.nreg; ++r) {
-                const uint32_t rb = (uint32_t)ch.reg[r].cb * 4;
-                const uint32_t layout = rb == 32 ? 6u : (rb == 64 ? 4u : 2u);
-                const uint64_t a_blk = umma_desc(sS + ch.reg[r].off + (uint32_t)(ky * a.PW + mb * kBlkPixFlat) * rb, 16, 8 * rb, layout);
-                const int ksteps = ch.reg[r].cb >> 3;
-                for (int ks = 0; ks < ksteps; ++ks, kc += 2) {
-                  const uint64_t bd0 = b_base + (uint64_t)((ky * (ch.ncg >> 1) + (kc >> 1)) * N3 * 2);
+#pragma unroll
+              for (int r = 0; r < 2; ++r) {  // static indices: a0 / rbq / ksn stay in registers
+                if (r >= nreg) break;
+                const uint64_t a_blk = a0[r] + (uint64_t)((uint32_t)(ky * a.PW + mb * kBlkPixFlat) * rbq[r]);
+                const uint64_t blk_step = (uint64_t)((uint32_t)(kMmaWarps * kBlkPixFlat) * rbq[r]);
+                const uint32_t kxs = rbq[r];
+                for (int ks = 0; ks < ksn[r]; ++ks, kc += 2) {
+                  const uint64_t bd0 = b_base + (uint64_t)((ky * ncg_half + (kc >> 1)) * N3 * 2);
                   const uint64_t ad0 = a_blk + (uint64_t)(2 * ks);
                   const uint32_t first = (c | ky | (int)kc) ? 1u : 0u;
                   if (leader && !(a.debug & 1)) {
-                    umma_tf32(d, ad0, bd0, idesc, first);
-                    umma_tf32(d, ad0 + (rb >> 4), bd0 + COLS * 2, idesc, 1u);
-                    umma_tf32(d, ad0 + 2 * (rb >> 4), bd0 + 2 * COLS * 2, idesc, 1u);
+                    if (two) {
+                      const uint64_t ad1 = ad0 + blk_step;
+                      umma_tf32(d, ad0, bd0, idesc, first);
+                      umma_tf32(dB, ad1, bd0, idesc, first);
+                      umma_tf32(d, ad0 + kxs, bd0 + COLS * 2, idesc, 1u);
+                      umma_tf32(dB, ad1 + kxs, bd0 + COLS * 2, idesc, 1u);
+                      umma_tf32(d, ad0 + 2 * kxs, bd0 + 2 * COLS * 2, idesc, 1u);
+                      umma_tf32(dB, ad1 + 2 * kxs, bd0 + 2 * COLS * 2, idesc, 1u);
+                    } else {
+                      umma_tf32(d, ad0, bd0, idesc, first);
+                      umma_tf32(d, ad0 + kxs, bd0 + COLS * 2, idesc, 1u);
+                      umma_tf32(d, ad0 + 2 * kxs, bd0 + 2 * COLS * 2, idesc, 1u);
+                    }
                   }
                 }
               }
@@ -514,28 +547,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const __grid_
         } else
         for (int ky = 0; ky < 3; ++ky) {
           uint32_t kc = 0;
-          for (int r = 0; r < ch.nreg; ++r) {
-            const uint32_t rb = (uint32_t)ch.reg[r].cb * 4;  // row bytes = swizzle span
-            const uint32_t layout = rb == 32 ? 6u : (rb == 64 ? 4u : 2u);
-            // 8-row core groups: 6 rows apart when folded (rows 6,7 duplicate the next group's 0,1), canonical 8 when flat
-            const uint64_t a_base = umma_desc(sS + ch.reg[r].off + (uint32_t)(ky * a.PW) * rb, 16, (FOLD ? 6 : 8) * rb, layout);
-            const uint32_t mb_step = (FOLD ? 6 : 8) * rb;  // BLK rows, in 16-byte descriptor units
-            const int ksteps = ch.reg[r].cb >> 3;
-            for (int ks = 0; ks < ksteps; ++ks, kc += 2) {
 #pragma unroll
-              for (int kx = 0; kx < (FOLD ? 1 : 3); ++kx) {
-                // flat: tap (ky, kx) = N rows [kx*COLS, (kx+1)*COLS) of the same B tile, A start moved by kx pixel rows
-                const uint64_t bd = b_base + (uint64_t)((ky * (ch.ncg >> 1) + (kc >> 1)) * N3 * 2 + kx * COLS * 2);
-                uint64_t ad = a_base + (uint64_t)(2 * ks + mw * mb_step + kx * (rb >> 4));
-                uint32_t d = d0 + mw * NACC;
-                const uint32_t acc = (c | ky | (int)kc | kx) ? 1u : 0u;
-                // blocks innermost: consecutive MMAs write different accumulators
+          for (int r = 0; r < 2; ++r) {  // static indices: a0 / rbq / ksn stay in registers
+            if (r >= nreg) break;
+            const uint64_t a_base = a0[r] + (uint64_t)((uint32_t)(ky * a.PW) * rbq[r]);
+            const uint32_t mb_step = 6 * 16 * rbq[r];  // BLK rows (96 when folded), in 16-byte descriptor units: 6 * rb
+            for (int ks = 0; ks < ksn[r]; ++ks, kc += 2) {
+              const uint64_t bd = b_base + (uint64_t)((ky * ncg_half + (kc >> 1)) * N3 * 2);
+              uint64_t ad = a_base + (uint64_t)(2 * ks + mw * mb_step);
+              uint32_t d = d0 + mw * NACC;
+              const uint32_t acc = (c | ky | (int)kc) ? 1u : 0u;
+              // blocks innermost: consecutive MMAs write different accumulators
 #pragma unroll 3
-                for (int mb = mw; mb < a.nmb; mb += kMmaWarps) {
-                  if (leader && !(a.debug & 1)) umma_tf32(d, ad, bd, idesc, acc);
-                  d += kMmaWarps * NACC;
-                  ad += kMmaWarps * mb_step;
-                }
+              for (int mb = mw; mb < a.nmb; mb += kMmaWarps) {
+                if (leader && !(a.debug & 1)) umma_tf32(d, ad, bd, idesc, acc);
+                d += kMmaWarps * NACC;
+                ad += kMmaWarps * mb_step;
               }
             }
           }
