@@ -286,10 +286,12 @@ int pu_gather_flat(const long long* table, int n, float* flat, void* stream);
  * (2 * pu_adam_allreduce_blocks() * world int32, zero-initialised), all in symmetric (peer-mapped) memory.  One launch per rank and
  * step: barrier with the peers, g = sum_j peer_grad[j] read over NVLink (same order on every rank: bit-identical replicas),
  * Adam update of the local arena with grad_scale * g, barrier.  Replaces ncclAllReduce + pu_adam_step (train.py:110-111 under
- * data parallelism).  world in {2, 4, 8}; every rank must call it once per step.                                        */
+ * data parallelism).  world in {2, 4, 8}; every rank must call it once per step.  n_extra (multiple of 4, may be 0): that many
+ * floats FOLLOW the n gradients in every rank's arena and are only summed over the ranks into extra_sum (local memory) — the
+ * plastic-trace delta (pu_trace_delta) of the step, so that its all-reduce shares the round trip; apply it with pu_trace_apply. */
 int pu_adam_allreduce_step(float* param, const long long* peer_grad_ptrs, const long long* peer_flag_ptrs, int rank, int world, float* exp_avg,
                            float* exp_avg_sq, float* step_count, const float* lr, float beta1, float beta2, float eps, float grad_scale,
-                           long long n, void* stream);
+                           long long n, float* extra_sum, long long n_extra, void* stream);
 int pu_adam_allreduce_blocks(void);
 
 /* Input pipeline: batch assembly from a DEVICE-resident dataset src [n, planes, Hs, Ws] + zero padding

@@ -45,6 +45,7 @@ constexpr unsigned kMaxResidentW = 40 * 1024;  // largest weight image kept resi
 constexpr int kBlkPix = 96;                    // output pixels per 128-row MMA block, kx folded into N (16 groups x 6)
 constexpr int kBlkPixFlat = 128;               // ... and with one MMA per tap (FOLD = false): 128 consecutive flattened halo pixels
 constexpr int kMaxStages = 4;
+constexpr int kMaxAcc = 4;                     // TMEM accumulator buffers (tiles in flight between the MMA and the epilogue warps)
 constexpr int kTileQ = 4;                      // depth of the producer -> consumers tile-index queue (dynamic scheduler)
 constexpr int kMaxCoBlk = 16;                  // co blocks per launch slot of the tile counters
 
@@ -70,6 +71,7 @@ struct TcArgs {
   int B, H, W, Cout, relu, round_out;
   int TH, TW, PW, tilesX, tilesY;
   int nmb, a_bytes, w_bytes_max, tmem_cols, nchunks, nstages;
+  int nacc;         // accumulator buffers in TMEM (2..kMaxAcc): nacc * nmb * NACC columns
   int wfmt;         // 0: wpk holds the packed B tiles (streamed per stage); 1/2: wpk is the raw OIHW weight (forward / dgrad)
                     // and the B tiles are built in shared memory once per CTA (resident)
   int Cin, C0;      // concatenated input channels and the split point (for the in-kernel weight build)
@@ -239,8 +241,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const __grid_
   const int stage_bytes = a.a_bytes + a.w_bytes_max;  // w_bytes_max == 0 when the weights are resident
   uint8_t* smWres = smem + nst * stage_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smWres + a.w_res_bytes);
-  // bars: [0,kMaxStages) full, [kMaxStages,2kMaxStages) empty, then tmem_full[2], tmem_empty[2], tile queue full[kTileQ], empty[kTileQ]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4 + 2 * kTileQ);
+  // bars: [0,kMaxStages) full, [kMaxStages,2kMaxStages) empty, then tmem_full[kMaxAcc], tmem_empty[kMaxAcc], tile queue full[kTileQ], empty[kTileQ]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 2 * kMaxAcc + 2 * kTileQ);
   volatile int* tileq = reinterpret_cast<volatile int*>(tmem_slot + 2);  // [kTileQ] tile indices handed from the producer to the other roles
   int* wtab = reinterpret_cast<int*>(tmem_slot + 2 + kTileQ);  // resident-weight build: (offset, ky stride) per 4-channel group, <= 1 KB
   // PU_TC_DEBUG & 64: per-tile timeline of CTA 0 (cycles since kernel start): [event][tile < 12]
@@ -254,9 +256,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const __grid_
   auto full_bar = [&](int st) { return bar0 + 8u * st; };
   auto empty_bar = [&](int st) { return bar0 + 8u * (kMaxStages + st); };
   auto tfull_bar = [&](int as) { return bar0 + 8u * (2 * kMaxStages + as); };
-  auto tempty_bar = [&](int as) { return bar0 + 8u * (2 * kMaxStages + 2 + as); };
-  auto tqfull_bar = [&](int q) { return bar0 + 8u * (2 * kMaxStages + 4 + q); };
-  auto tqempty_bar = [&](int q) { return bar0 + 8u * (2 * kMaxStages + 4 + kTileQ + q); };
+  auto tempty_bar = [&](int as) { return bar0 + 8u * (2 * kMaxStages + kMaxAcc + as); };
+  auto tqfull_bar = [&](int q) { return bar0 + 8u * (2 * kMaxStages + 2 * kMaxAcc + q); };
+  auto tqempty_bar = [&](int q) { return bar0 + 8u * (2 * kMaxStages + 2 * kMaxAcc + kTileQ + q); };
   // Dynamic tile scheduler.  The weight-gradient kernels of the backward pass run concurrently on side streams, so a
   // persistent CTA may get its SM late (or share the memory system unevenly); with a static round-robin assignment the
   // kernel then lasts as long as its unluckiest CTA.  Instead the producer warp draws tiles from a global counter (the first
@@ -297,7 +299,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const __grid_
         mbar_init(full_bar(i), 1);
         mbar_init(empty_bar(i), kMmaWarps);  // one tcgen05.commit per MMA warp
       }
-      for (int i = 0; i < 2; ++i) {
+      for (int i = 0; i < kMaxAcc; ++i) {
         mbar_init(tfull_bar(i), kMmaWarps);
         mbar_init(tempty_bar(i), kEpiWarps);  // one arrival per epilogue warp
       }
@@ -472,8 +474,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const __grid_
     int it = 0;
     for (int k = 0;; ++k) {
       if (next_tile(k) < 0) break;
-      const int as = k & 1;
-      const uint32_t aph = (k >> 1) & 1;
+      const int as = k % a.nacc;
+      const uint32_t aph = (uint32_t)(k / a.nacc) & 1;
       mbar_wait(tempty_bar(as), aph ^ 1);  // the epilogue has drained this accumulator buffer
       tc_fence_after();
       const uint32_t d0 = tmem_base + (uint32_t)(as * acc_cols);
@@ -679,7 +681,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const __grid_
       const unsigned char* const m1b = a.mask1 == nullptr ? nullptr : a.mask1 + o1 / 8;
       unsigned char* const mob = a.mask_out == nullptr ? nullptr : a.mask_out + o0 / 8 + (co_base >> 3);
       const float* const rsb = has_res ? a.res + (((size_t)b * a.H + y0) * a.W + x0) * a.Cout + co_base : nullptr;
-      const int as = tcount & 1;
+      const int as = (int)(tcount % (uint32_t)a.nacc);
       // ---- packed ReLU masks of this tile's units: requested BEFORE waiting for the accumulators, so that their global
       // latency hides behind the MMAs (one byte per unit instead of re-reading 32 bytes of fp32 activation per unit)
       uint32_t mk[kMaxI][NQ];
@@ -702,7 +704,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const __grid_
           if (xx_ >= a.PW) { xx_ -= a.PW; ++yy_; }
         }
       }
-      mbar_wait(tfull_bar(as), (tcount >> 1) & 1);
+      mbar_wait(tfull_bar(as), (tcount / (uint32_t)a.nacc) & 1);
       tc_fence_after();
       if (warp == kEpiWarp0 && lane == 0) stamp(3, tcount);
       const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * acc_cols);
@@ -895,6 +897,7 @@ static bool tc_init() {
 
 struct TcPlan {
   int TH, TW, PW, tilesX, tilesY, nmb, cols, n3, a_bytes, w_bytes_max, w_res_bytes, tmem_cols, nchunks, ncoblk, nstages, cb0, cb1;
+  int nacc;  // accumulator buffers
   int fold;  // 1: kx folded into N (96-pixel blocks); 0: flat, one MMA per tap (128-pixel blocks), wide layers
   unsigned w_coblk_stride;
   size_t smem_bytes;
@@ -1052,7 +1055,17 @@ static bool tc_plan1(int B, int H, int W, int C0, int C1, int Cout, TcPlan* p, b
   const size_t stage = (size_t)p->a_bytes + p->w_bytes_max;
   p->nstages = (int)(budget / stage);
   if (p->nstages > kMaxStages) p->nstages = kMaxStages;
-  p->tmem_cols = next_pow2_cols(2 * p->nmb * (p->fold ? p->n3 : (p->cols < 16 ? 16 : p->cols)));
+  {
+    // as many accumulator buffers as TMEM holds (2..kMaxAcc): the chain MMA issue -> completion -> epilogue -> release of a tile is
+    // latency-bound, more tiles in flight hide it (PU_TC_NACC overrides)
+    const int per_buf = p->nmb * (p->fold ? p->n3 : (p->cols < 16 ? 16 : p->cols));
+    int nacc = 512 / per_buf;
+    if (nacc > kMaxAcc) nacc = kMaxAcc;
+    if (const char* e = getenv("PU_TC_NACC")) nacc = atoi(e) < nacc ? atoi(e) : nacc;
+    if (nacc < 2) nacc = 2;
+    p->nacc = nacc;
+    p->tmem_cols = next_pow2_cols(nacc * per_buf);
+  }
   p->smem_bytes = (size_t)p->nstages * stage + p->w_res_bytes + 256 + 2048 + 1024;  // barriers, k-group table + trace, alignment
   return p->nstages >= 2 && p->tmem_cols <= 512;
 }
@@ -1246,6 +1259,7 @@ int conv3x3_fwd_tc(const Conv3x3Args& a, cudaStream_t st) {
   ta.TH = p.TH; ta.TW = p.TW; ta.PW = p.PW; ta.tilesX = p.tilesX; ta.tilesY = p.tilesY;
   ta.nmb = p.nmb; ta.a_bytes = p.a_bytes; ta.w_bytes_max = p.w_bytes_max; ta.nstages = p.nstages;
   ta.tmem_cols = p.tmem_cols; ta.nchunks = p.nchunks; ta.w_coblk_stride = p.w_coblk_stride;
+  ta.nacc = p.nacc;
   ta.wfmt = a.wfmt; ta.Cin = a.Cin; ta.C0 = a.s0.C; ta.w_res_bytes = p.w_res_bytes;
   if (p.ncoblk > kMaxCoBlk) {
     set_error("pu_conv3x3_fwd: more than %d output-channel blocks (Cout %d)", kMaxCoBlk, a.Cout);

@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(kArThreads) adam_allreduce_kernel(float* __res
                                                                     const long long* __restrict__ flag_ptrs, int rank, float* __restrict__ m,
                                                                     float* __restrict__ v, const float* __restrict__ step_p,
                                                                     const float* __restrict__ lr_p, float b1, float b2, float eps, float gscale,
-                                                                    long long n4) {
+                                                                    long long n4, float* __restrict__ extra_out, long long n4_extra) {
   ar_barrier(flag_ptrs, rank, W, 0);
   const float* g[W];
 #pragma unroll
@@ -139,6 +139,17 @@ __global__ void __launch_bounds__(kArThreads) adam_allreduce_kernel(float* __res
     *reinterpret_cast<float4*>(m + 4 * i) = make_float4(mm[0], mm[1], mm[2], mm[3]);
     *reinterpret_cast<float4*>(v + 4 * i) = make_float4(vv[0], vv[1], vv[2], vv[3]);
     *reinterpret_cast<float4*>(p + 4 * i) = make_float4(ww[0], ww[1], ww[2], ww[3]);
+  }
+  // the floats that follow the gradients in every rank's arena (the plastic-trace delta of the step) are only summed — same order
+  // on every rank — and handed back: the trace all-reduce rides on the same NVLink round trip and the same two barriers
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4_extra; i += (long long)gridDim.x * blockDim.x) {
+    float4 s = ld_peer4(g[0] + 4 * (n4 + i));
+#pragma unroll
+    for (int j = 1; j < W; ++j) {
+      const float4 t = ld_peer4(g[j] + 4 * (n4 + i));
+      s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+    }
+    *reinterpret_cast<float4*>(extra_out + 4 * i) = s;
   }
   ar_barrier(flag_ptrs, rank, W, 1);
 }
@@ -206,9 +217,11 @@ int pu_adam_allreduce_blocks(void) { return pu::kNumSMs; }
 
 int pu_adam_allreduce_step(float* param, const long long* peer_grad_ptrs, const long long* peer_flag_ptrs, int rank, int world, float* exp_avg,
                            float* exp_avg_sq, float* step_count, const float* lr, float beta1, float beta2, float eps, float grad_scale,
-                           long long n, void* stream) {
+                           long long n, float* extra_sum, long long n_extra, void* stream) {
   PU_REQUIRE(param && peer_grad_ptrs && peer_flag_ptrs && exp_avg && exp_avg_sq && step_count && lr && n > 0, PU_ERR_BAD_ARG,
              "pu_adam_allreduce_step: bad argument");
+  PU_REQUIRE(n_extra >= 0 && n_extra % 4 == 0 && (n_extra == 0 || (extra_sum != nullptr && pu::aligned16(extra_sum))), PU_ERR_BAD_ARG,
+             "pu_adam_allreduce_step: extra_sum must be 16-byte aligned and n_extra a multiple of 4");
   PU_REQUIRE(n % 4 == 0 && pu::aligned16(param) && pu::aligned16(exp_avg) && pu::aligned16(exp_avg_sq), PU_ERR_BAD_ARG,
              "pu_adam_allreduce_step: the arenas must be 16-byte aligned and a multiple of 4 floats long");
   PU_REQUIRE(rank >= 0 && rank < world, PU_ERR_BAD_ARG, "pu_adam_allreduce_step: rank %d outside world %d", rank, world);
@@ -220,7 +233,7 @@ int pu_adam_allreduce_step(float* param, const long long* peer_grad_ptrs, const 
   const long long n4 = n / 4;
 #define PU_AR_LAUNCH(W_)                                                                                                                  \
   pu::adam_allreduce_kernel<W_><<<grid, pu::kArThreads, 0, st>>>(param, peer_grad_ptrs, peer_flag_ptrs, rank, exp_avg, exp_avg_sq, step_count, \
-                                                                  lr, beta1, beta2, eps, grad_scale, n4)
+                                                                  lr, beta1, beta2, eps, grad_scale, n4, extra_sum, n_extra / 4)
   switch (world) {
     case 2: PU_AR_LAUNCH(2); break;
     case 4: PU_AR_LAUNCH(4); break;

@@ -112,6 +112,7 @@ class _PlasticBase(nn.Module):
         self.dp_group = None  # set by pu_b200.dp.attach() for the data-parallel trace all-reduce
         self.dp_defer = False  # TrainStep: the trace update (and its DP all-reduce) runs on a side stream, off the critical path
         self.dp_side = None
+        self.dp_external = None  # TrainStep (fused peer-memory exchange): callback(delta_q, K_global, rule) that takes over the trace reduction
         self.dp_world = 1
         # TrainStep (data parallel): a callback fired in the backward pass once the gradient w.r.t. the input of encoder level
         # `_bucket_level` exists, i.e. when every parameter gradient of the decoder and of the deeper encoder levels has been
@@ -164,8 +165,26 @@ class _PlasticBase(nn.Module):
         if self.dp_group is not None and self.dp_world > 1:
             import torch.distributed as dist
             # data-parallel: all-reduce (sum_k outer, sum_k post^2), then the identical epilogue on every rank
-            delta_q = ops.trace_delta_tc(X.detach(), S.detach(), N, N, B * N) if all_rows else ops.trace_delta(X.detach(), S.detach(), N, N * N, B)
             kloc = B * N if all_rows else B  # (pre, post) pairs of this rank
+
+            def local_delta():
+                return ops.trace_delta_tc(X.detach(), S.detach(), N, N, B * N) if all_rows else ops.trace_delta(X.detach(), S.detach(), N, N * N, B)
+
+            if getattr(self, "dp_external", None) is not None and getattr(self, "dp_defer", False) and S.is_cuda:
+                # TrainStep with the peer-memory exchange: the trainer sums the delta over the ranks inside its fused
+                # gradient-exchange kernel at the end of the step and applies it there; the trace returned here is a placeholder.
+                # The local delta (and its copy into the exchange arena) run on the side stream, off the critical path.
+                if getattr(self, "dp_side", None) is None:
+                    self.dp_side = torch.cuda.Stream()
+                main = torch.cuda.current_stream()
+                self.dp_side.wait_stream(main)
+                with torch.cuda.stream(self.dp_side):
+                    delta_q = local_delta()
+                    self.dp_external(delta_q, kloc * self.dp_world, rule)
+                X.record_stream(self.dp_side)
+                S.record_stream(self.dp_side)
+                return (S.view(N, N) if B == 1 else S.view(B, N, N)), hebb.detach()
+            delta_q = local_delta()
             if getattr(self, "dp_defer", False) and delta_q.is_cuda:
                 # The new trace is only needed at the end of the step: run its all-reduce + epilogue on a side stream so
                 # that they overlap the backward pass.  The caller (TrainStep) joins `self.dp_side` before it reads hebb_new.

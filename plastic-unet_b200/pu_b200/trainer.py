@@ -56,16 +56,20 @@ class TrainStep:
         self.flat_p = torch.zeros(off, device=self.dev)
         self.flat_g = torch.zeros(off, device=self.dev)
         # Data parallel: the gradient exchange fused with Adam over NVLink peer memory (pu_adam_allreduce_step): the gradient arena
-        # and a flag buffer live in symmetric memory; falls back to ncclAllReduce + pu_adam_step if that is unavailable.  Default at 4
-        # and 8 GPUs (measured 7-8 us per step faster than NCCL there, replicas bit-identical); at 2 GPUs NCCL is as fast and stays
-        # the default.  PU_DP_FUSED=0/1 forces either.
+        # and a flag buffer live in symmetric memory; falls back to ncclAllReduce + pu_adam_step if that is unavailable.  The
+        # plastic-trace delta rides along (no NCCL kernel inside the step at all).  Default at 2, 4 and 8 GPUs (measured 5 / 7 / 13 us
+        # per step faster than NCCL, replicas bit-identical); PU_DP_FUSED=0 restores NCCL.
         self._fused = None
-        want_fused = os.environ.get("PU_DP_FUSED", "1" if self.world in (4, 8) else "0") == "1"
+        want_fused = os.environ.get("PU_DP_FUSED", "1") == "1"
         if self.dp_group is not None and self.world in (2, 4, 8) and not self._late and want_fused:
             try:
                 import torch.distributed._symmetric_memory as symm
                 nblk = int(_lib.load().pu_adam_allreduce_blocks())
-                g_sym = symm.empty(off, dtype=torch.float32, device=self.dev)
+                # the arena is followed by the plastic-trace delta of the step (N*N + N floats, pu_trace_delta): summed over the
+                # ranks by the same kernel, so the trace all-reduce needs no NCCL kernel in the middle of the backward pass
+                N = net.nbf
+                self._n_trace = (N * N + N + 3) // 4 * 4
+                g_sym = symm.empty(off + self._n_trace, dtype=torch.float32, device=self.dev)
                 g_sym.zero_()
                 f_sym = symm.empty(2 * nblk * self.world, dtype=torch.int32, device=self.dev)
                 f_sym.zero_()
@@ -74,7 +78,11 @@ class TrainStep:
                 torch.cuda.synchronize()
                 dist.barrier(self.dp_group)  # every rank's flags are zero before anyone signals
                 self._fused = (hg, hf, f_sym, int(hg.rank))
-                self.flat_g = g_sym
+                self._arena = g_sym
+                self.flat_g = g_sym[:off]
+                self._delta_sum = torch.zeros(self._n_trace, device=self.dev)
+                self._eta_snap = torch.zeros(1, device=self.dev)
+                self._trace_job = None
             except Exception as e:  # no peer access / symmetric memory on this system
                 import warnings
                 warnings.warn("pu_b200.TrainStep: fused peer-memory gradient exchange unavailable (%s: %s); using NCCL all-reduce"
@@ -214,10 +222,14 @@ class TrainStep:
         # the trace update (data parallel: the trace-delta all-reduce + epilogue) runs on net.dp_side, off the critical path; only
         # this step body defers it (it joins dp_side before Adam) — any other caller of net.forward gets the trace on its own stream
         self.net.dp_defer = True
+        if self._fused is not None:
+            self._trace_job = None
+            self.net.dp_external = self._take_trace_delta
         try:
             out, hebb_new = self.net(self.x, self.hebb)
         finally:
             self.net.dp_defer = False
+            self.net.dp_external = None
         gS = torch.empty_like(out)
         n = out.numel()
         _lib.call("pu_bce_fwd_bwd", out.data_ptr(), self.target.data_ptr(), self.loss.data_ptr(), gS.data_ptr(), n, st)
@@ -263,14 +275,31 @@ class TrainStep:
             torch.cuda.current_stream().wait_stream(self.net.dp_side)
         if self._fused is not None:
             hg, hf, _flags, grank = self._fused
+            job = self._trace_job
+            if job is not None:
+                self._eta_snap.copy_(self.net.eta.detach())  # the trace epilogue uses the step's eta, not the optimizer's result
             _lib.call("pu_adam_allreduce_step", self.flat_p.data_ptr(), int(hg.buffer_ptrs_dev), int(hf.buffer_ptrs_dev), grank, self.world,
                       self.m.data_ptr(), self.v.data_ptr(), self.step_count.data_ptr(), self.lr.data_ptr(), self.betas[0], self.betas[1],
-                      self.eps, 1.0 / self.world, self.n_flat, st)
+                      self.eps, 1.0 / self.world, self.n_flat, self._delta_sum.data_ptr() if job is not None else None,
+                      self._n_trace if job is not None else 0, st)
+            if job is not None:
+                # identical summed delta on every rank -> identical trace; in place (element-wise)
+                k_global, rule = job
+                _lib.call("pu_trace_apply", self.hebb.data_ptr(), self._delta_sum.data_ptr(), k_global, self._eta_snap.data_ptr(), rule,
+                          self.hebb.data_ptr(), self.net.nbf, st)
+                self._trace_job = None
+                return
         else:
             _lib.call("pu_adam_step", self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
                       self.step_count.data_ptr(), self.lr.data_ptr(), self.betas[0], self.betas[1], self.eps,
                       1.0 / self.world, self.n_flat, st)
         self.hebb.copy_(hebb_new.detach())
+
+    def _take_trace_delta(self, delta_q, k_global, rule):
+        """modules._plastic hands the step's local trace delta over (fused exchange): it goes behind the gradients in the arena."""
+        n = delta_q.numel()
+        self._arena[self.n_flat:self.n_flat + n].copy_(delta_q.reshape(-1))
+        self._trace_job = (int(k_global), int(rule))
 
     def _state_tensors(self):
         """Every tensor a step mutates: the optimizer state, the trace and the BatchNorm buffers."""

@@ -153,6 +153,31 @@ def test_trainstep_graph_and_side_streams_do_not_change_the_result(math):
         assert e_upd < 2e-3, worst
 
 
+@pytest.mark.parametrize("case", ["unetp_oja_64_b8", "unetpres8_hebb_101_b8"])
+def test_trainstep_gradient_sink_matches_the_gather_path(case, monkeypatch):
+    """PU_GRAD_SINK=1 (opt-in): the TF32 gradient kernels accumulate straight into the trainer's arena slots (PU_MATH_ACCUM /
+    PU_FLAG_ACCUM_GRADS: no memset launches, no gather for those parameters).  Same trajectory as the default path up to the
+    fp32-atomics bound, and the oracle tolerances hold."""
+    kind, ctor_kw, body_kw, size, B, steps, lr, pad_from = CASES[case]
+    sd0, sd_ref, losses_ref, hebb_ref, batches = oracle_run(kind, ctor_kw, body_kw, size, B, steps, lr, pad_from)
+    base_net, base_ts, base_losses = run_trainstep(kind, ctor_kw, sd0, batches, size, B, lr, "tf32")
+    base_sd = {k: p.detach().cpu() for k, p in base_net.named_parameters()}
+    monkeypatch.setenv("PU_GRAD_SINK", "1")
+    net, ts, losses = run_trainstep(kind, ctor_kw, sd0, batches, size, B, lr, "tf32")
+    assert ts._sink, "the gradient sink must be active"
+    base = ts.flat_g.data_ptr()
+    in_place = sum(1 for p_, o in zip(ts.params, ts.offsets) if p_.grad is not None and p_.grad.data_ptr() == base + 4 * o)
+    assert in_place >= 20, in_place  # every conv3x3 / convT2x2 weight and bias of the model
+    e_upd, worst = update_err(net, sd0, base_sd)
+    print("\n[grad sink %s] %d gradients written in place; update vs gather path %.2e (worst %s), kernels/step %d vs %d"
+          % (case, in_place, e_upd, worst, ts.kernels_per_step, base_ts.kernels_per_step))
+    assert max(abs(a - b) for a, b in zip(losses, base_losses)) < 2e-6
+    assert e_upd < 2e-3, worst
+    tol = TOLS["tf32"]
+    assert max(abs(a - b) for a, b in zip(losses, losses_ref)) < tol["loss"]
+    assert update_err(net, sd0, sd_ref)[0] < tol["upd"]
+
+
 def test_capture_leaves_model_state_untouched():
     """capture() warms up with real steps; it must restore weights, Adam state, step count, trace and BN buffers."""
     import pu_b200
