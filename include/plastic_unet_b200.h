@@ -229,6 +229,22 @@ int pu_plastic_head_bwd(const float* X, const float* S, const float* gS, const f
                         const float* alpha, const float* hebb, float* gA_ws,
                         float* gX, float* gw, float* galpha, float* ghebb, int B, int N, void* stream);
 
+/* Training-step form of the head (TF32 mode of TrainStep): forward + the reference's loss + their backward in ONE launch.
+ * Replaces, for `loss = nn.BCELoss()(net(x, hebb)[0], target); loss.backward()` (train.py:99-104 over unet_p.py:70-79):
+ *   S = sigmoid(X @ (w + alpha*hebb)); *loss = mean BCE(S, target) (logs clamped at -100 as torch does);
+ *   gA = dloss/d(logits) [B*N, N]; gX = gA @ Weff^T (NULL: skipped).
+ * mma.sync TF32: the logits with the three-term error-compensated split (fp32-level: they decide masks, loss and trace),
+ * gX as a plain TF32 product (it feeds the TF32 data-gradient convs).  N <= 128.
+ * scratch: NULL (then *loss is zeroed by a memset node and summed with atomics) or 1 + ceil(B*N/64) floats, zero before
+ * the FIRST launch and left zeroed by every launch: deterministic block-ordered loss sum, no memset.               */
+int pu_plastic_head_bce(const float* X, const float* w, const float* alpha, const float* hebb, const float* target,
+                        float* S, float* loss, float* gA, float* gX, float* scratch, int B, int N, void* stream);
+/* The head's parameter gradients from gA (either form): gw = X^T @ gA (split-K mma.sync, fp32 atomics; terms = 3:
+ * error-compensated 3xTF32, terms = 1: plain TF32 as the conv weight gradients of the TF32 mode),
+ * galpha = gw*hebb, ghebb = gw*alpha (each may be NULL).                                                         */
+int pu_plastic_head_wgrad_tc(const float* X, const float* gA, const float* alpha, const float* hebb,
+                             float* gw, float* galpha, float* ghebb, int B, int N, int terms, void* stream);
+
 /* ---- plastic trace update (reference unet_p.py:81-84 == unet_p_res.py:127-130) ----------------
  * pre/post are the stacked pre-/post-synaptic rows [K, N] (parity mode: K = B, row 0 of every
  * map, given as pointers to map b's first row with row stride `ld` floats).

@@ -227,7 +227,11 @@ __device__ __forceinline__ void build_w_tile(const TcChunk& ch, float4* out, con
 // dominates.  FOLD = false ("flat"): one MMA per tap (N = COLS, nine per K step) on 128 CONSECUTIVE flattened halo pixels:
 // every row is an output pixel, the accumulators need COLS instead of 3*COLS TMEM columns per block, so a tile holds 3x the
 // pixels per weight byte streamed — the shape for the wide (>= 64 channel), tensor-bound layers (SURVEY.md §8d "TC demo").
-template <int COLS, bool FOLD>
+// KS = true ("tap-row split", flat mode, small tiles of the deep layers): ONE thread issues a tcgen05.mma only every ~128 clk, so a
+// 64-channel block (72 MMAs) costs its issuing warp 4.8 us while the other MMA warps idle when a tile has one or two blocks.
+// With KS the three MMA warps each issue ONE tap row (ky = warp) of every block into their own partial accumulator
+// (block mb, partial ky at TMEM column mb*3*NACC + ky*NACC) and the epilogue adds the three partials.
+template <int COLS, bool FOLD, bool KS = false>
 __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm0,
                                                                    const __grid_constant__ CUtensorMap tm1, const TcArgs a) {
   constexpr int N3 = tc_n3(COLS);
@@ -235,6 +239,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const __grid_
   // tap's rows of the B tile; MMAs are free in these HBM-bound layers)
   constexpr int NACC = FOLD ? N3 : (COLS < 16 ? 16 : COLS);  // TMEM columns of one MMA block's accumulators
   constexpr int BLK = FOLD ? kBlkPix : kBlkPixFlat;  // output pixels per MMA block
+  constexpr int NBLK = KS ? 3 * NACC : NACC;         // TMEM columns per block (KS: three partial accumulators)
+  static_assert(!KS || (!FOLD && COLS >= 16), "tap-row split is a flat-mode variant");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // swizzle patterns repeat every 1024 B
   const int nst = a.nstages;
@@ -291,7 +297,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const __grid_
   const int co_base = coblk * kCoBlk;
   const int tiles_per_img = a.tilesX * a.tilesY;
   const int ntiles = tiles_per_img * a.B;
-  const int acc_cols = a.nmb * NACC;  // TMEM columns of one accumulator buffer
+  const int acc_cols = a.nmb * NBLK;  // TMEM columns of one accumulator buffer
 
   if (warp == 0) {
     if (lane == 0) {
@@ -505,7 +511,42 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const __grid_
         mbar_wait(full_bar(st), ph);
         tc_fence_after();
         if (mw == 0 && lane == 0 && c == 0) stamp(1, k);
-        if (!FOLD) {
+        if (KS) {
+          // tap-row split: this warp issues the three kx taps of tap row ky = mw for every K step and block (nmb <= 2: the two
+          // blocks alternate tap by tap, consecutive MMAs into the same accumulator wait for each other)
+          const int ky = mw;
+          const bool two = a.nmb > 1;
+          const uint32_t d = d0 + (uint32_t)(ky * NACC);
+          const uint32_t dB = d + (uint32_t)NBLK;
+          uint32_t kc = 0;
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            if (r >= nreg) break;
+            const uint64_t a_blk = a0[r] + (uint64_t)((uint32_t)(ky * a.PW) * rbq[r]);
+            const uint64_t blk_step = (uint64_t)((uint32_t)kBlkPixFlat * rbq[r]);
+            const uint32_t kxs = rbq[r];
+            for (int ks = 0; ks < ksn[r]; ++ks, kc += 2) {
+              const uint64_t bd0 = b_base + (uint64_t)((ky * ncg_half + (kc >> 1)) * N3 * 2);
+              const uint64_t ad0 = a_blk + (uint64_t)(2 * ks);
+              const uint32_t first = (c | (int)kc) ? 1u : 0u;
+              if (leader && !(a.debug & 1)) {
+                if (two) {
+                  const uint64_t ad1 = ad0 + blk_step;
+                  umma_tf32(d, ad0, bd0, idesc, first);
+                  umma_tf32(dB, ad1, bd0, idesc, first);
+                  umma_tf32(d, ad0 + kxs, bd0 + COLS * 2, idesc, 1u);
+                  umma_tf32(dB, ad1 + kxs, bd0 + COLS * 2, idesc, 1u);
+                  umma_tf32(d, ad0 + 2 * kxs, bd0 + 2 * COLS * 2, idesc, 1u);
+                  umma_tf32(dB, ad1 + 2 * kxs, bd0 + 2 * COLS * 2, idesc, 1u);
+                } else {
+                  umma_tf32(d, ad0, bd0, idesc, first);
+                  umma_tf32(d, ad0 + kxs, bd0 + COLS * 2, idesc, 1u);
+                  umma_tf32(d, ad0 + 2 * kxs, bd0 + 2 * COLS * 2, idesc, 1u);
+                }
+              }
+            }
+          }
+        } else if (!FOLD) {
           // flat: every MMA warp owns whole 128-pixel blocks (the planner keeps nmb <= kMmaWarps, so one each) and issues
           // the nine taps of each 8-channel K step back to back — immediate descriptor offsets, no per-MMA loop control
           // Consecutive MMAs into the SAME accumulator wait for each other in the tensor pipe, so a warp that owns two blocks
@@ -625,6 +666,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const __grid_
           const float e2 = __shfl_down_sync(0xffffffffu, __uint_as_float(v[16 + j]), 2);
           o[j] = (__uint_as_float(v[j]) + e1) + e2;
         }
+      } else if (KS) {  // the three tap-row partials
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = (__uint_as_float(v[j]) + __uint_as_float(v[8 + j])) + __uint_as_float(v[16 + j]);
       } else {
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = __uint_as_float(v[j]);
@@ -734,16 +778,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const __grid_
           const bool okB = haveB && live && yy < ymax && xx < xmax;
           const int pixB = yy * a.d0.Ws + xx, xoB = yy * xs_y + xx * xs_x;
           advance();
-          const uint32_t tA = tbase + (uint32_t)(mb * NACC);
+          const uint32_t tA = tbase + (uint32_t)(mb * NBLK);
           tmem_ld8(tA, v[0]);
-          if (FOLD) {
+          if (FOLD || KS) {
             tmem_ld8(tA + COLS, v[0] + 8);
             tmem_ld8(tA + 2 * COLS, v[0] + 16);
           }
           if (haveB) {
-            const uint32_t tB = tA + (uint32_t)(kEpiSets * NACC);
+            const uint32_t tB = tA + (uint32_t)(kEpiSets * NBLK);
             tmem_ld8(tB, v[1]);
-            if (FOLD) {
+            if (FOLD || KS) {
               tmem_ld8(tB + COLS, v[1] + 8);
               tmem_ld8(tB + 2 * COLS, v[1] + 16);
             }
@@ -773,10 +817,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const __grid_
           for (int q = 0; q < NQ; q += 2) {
             uint32_t v[2][24];
             float aux[2][8], bb[2][8];
-            const uint32_t tA = tbase + (uint32_t)(mb * NACC + 8 * q);
+            const uint32_t tA = tbase + (uint32_t)(mb * NBLK + 8 * q);
             tmem_ld8(tA, v[0]);
             tmem_ld8(tA + 8, v[1]);
-            if (FOLD) {
+            if (FOLD || KS) {
               tmem_ld8(tA + COLS, v[0] + 8);
               tmem_ld8(tA + 2 * COLS, v[0] + 16);
               tmem_ld8(tA + 8 + COLS, v[1] + 8);
@@ -899,6 +943,7 @@ struct TcPlan {
   int TH, TW, PW, tilesX, tilesY, nmb, cols, n3, a_bytes, w_bytes_max, w_res_bytes, tmem_cols, nchunks, ncoblk, nstages, cb0, cb1;
   int nacc;  // accumulator buffers
   int fold;  // 1: kx folded into N (96-pixel blocks); 0: flat, one MMA per tap (128-pixel blocks), wide layers
+  int ksplit;  // flat mode, tiles of <= 2 blocks: the MMA warps split the tap rows of a block (three partial accumulators)
   unsigned w_coblk_stride;
   size_t smem_bytes;
   TcChunk chunks[kMaxChunks];
@@ -1058,11 +1103,29 @@ static bool tc_plan1(int B, int H, int W, int C0, int C1, int Cout, TcPlan* p, b
   {
     // as many accumulator buffers as TMEM holds (2..kMaxAcc): the chain MMA issue -> completion -> epilogue -> release of a tile is
     // latency-bound, more tiles in flight hide it (PU_TC_NACC overrides)
-    const int per_buf = p->nmb * (p->fold ? p->n3 : (p->cols < 16 ? 16 : p->cols));
+    int per_buf = p->nmb * (p->fold ? p->n3 : (p->cols < 16 ? 16 : p->cols));
+    // tap-row split (kernel template KS): tiles of one or two 128-pixel blocks of a >= 32-channel flat layer — the deep 16x16 / 8x8
+    // levels, whose time is the MMA issue chain of ONE thread per block.  Three partial accumulators per block; a single
+    // accumulator buffer is enough when every CTA has one tile.
+    p->ksplit = 0;
+    {
+      static int ks_env = -1;
+      if (ks_env < 0) {
+        const char* e = getenv("PU_TC_KSPLIT");
+        ks_env = (e != nullptr && e[0] == '0') ? 0 : 1;
+      }
+      const long long ntiles = (long long)B * p->tilesX * p->tilesY;
+      const int ctas_x = (kNumSMs + p->ncoblk - 1) / p->ncoblk;
+      if (ks_env && !p->fold && p->cols >= 32 && p->nmb <= 2 && (2 * 3 * per_buf <= 512 || (3 * per_buf <= 512 && ntiles <= ctas_x))) {
+        p->ksplit = 1;
+        per_buf *= 3;
+      }
+    }
     int nacc = 512 / per_buf;
     if (nacc > kMaxAcc) nacc = kMaxAcc;
     if (const char* e = getenv("PU_TC_NACC")) nacc = atoi(e) < nacc ? atoi(e) : nacc;
-    if (nacc < 2) nacc = 2;
+    if (nacc < 2 && !p->ksplit) nacc = 2;
+    if (nacc < 1) nacc = 1;
     p->nacc = nacc;
     p->tmem_cols = next_pow2_cols(nacc * per_buf);
   }
@@ -1212,18 +1275,18 @@ int conv3x3_tc_pack(const float* w_oihw, float* out, int Cout_w, int Cin_w, int 
   return post_launch("pu_pack_w3x3 (tc)");
 }
 
-template <int COLS, bool FOLD = true>
+template <int COLS, bool FOLD = true, bool KS = false>
 static int launch_tc(const CUtensorMap& tm0, const CUtensorMap& tm1, const TcArgs& ta, dim3 grid, size_t smem, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel<COLS, FOLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel<COLS, FOLD, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) {
       set_error("conv3x3_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return PU_ERR_CUDA;
     }
     attr_set = true;
   }
-  cudaError_t le = launch_pdl(conv3x3_tc_kernel<COLS, FOLD>, grid, dim3(kTcThreads), smem, st, tm0, tm1, ta);
+  cudaError_t le = launch_pdl(conv3x3_tc_kernel<COLS, FOLD, KS>, grid, dim3(kTcThreads), smem, st, tm0, tm1, ta);
   if (le != cudaSuccess) {
     set_error("conv3x3_tc launch: %s", cudaGetErrorString(le));
     return PU_ERR_CUDA;
@@ -1288,6 +1351,10 @@ int conv3x3_fwd_tc(const Conv3x3Args& a, cudaStream_t st) {
   const int ntiles = p.tilesX * p.tilesY * a.B;
   const int ctas_x = (kNumSMs + p.ncoblk - 1) / p.ncoblk;  // one persistent CTA per SM in total
   dim3 grid(ntiles < ctas_x ? ntiles : ctas_x, p.ncoblk);
+  if (!p.fold && p.ksplit) {
+    if (p.cols == 32) return launch_tc<32, false, true>(tm0, tm1, ta, grid, p.smem_bytes, st);
+    return launch_tc<64, false, true>(tm0, tm1, ta, grid, p.smem_bytes, st);
+  }
   if (!p.fold) {
     switch (p.cols) {
       case 8: return launch_tc<8, false>(tm0, tm1, ta, grid, p.smem_bytes, st);

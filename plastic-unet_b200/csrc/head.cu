@@ -251,10 +251,12 @@ __device__ __forceinline__ void mma_tf32_16x8x8(float* c, const uint32_t* a, con
 
 constexpr int TD_T = 64, TD_KC = 32, TD_LD = TD_T + 8;  // row pitch 72: fragment reads (k = t, col = g) hit 32 distinct banks
 
+template <bool WITH_Q, int TERMS = 3>
 __global__ void __launch_bounds__(128) trace_delta_mma_kernel(const float* __restrict__ pre, const float* __restrict__ post, long long ld, int K,
                                                               int kper, float* __restrict__ delta_q, int N) {
-  __shared__ __align__(16) float Ps[TD_KC][TD_LD];
-  __shared__ __align__(16) float Qs[TD_KC][TD_LD];
+  __shared__ __align__(16) float td_sm[2 * TD_KC * TD_LD];  // the two operand tiles; afterwards the 64 x (64 + 4) output tile
+  float (*Ps)[TD_LD] = reinterpret_cast<float (*)[TD_LD]>(td_sm);
+  float (*Qs)[TD_LD] = reinterpret_cast<float (*)[TD_LD]>(td_sm + TD_KC * TD_LD);
   const int i0 = blockIdx.y * TD_T, j0 = blockIdx.x * TD_T;
   const int k_begin = blockIdx.z * kper, k_end = min(K, k_begin + kper);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -268,17 +270,43 @@ __global__ void __launch_bounds__(128) trace_delta_mma_kernel(const float* __res
 #pragma unroll
       for (int e = 0; e < 4; ++e) acc[a][b][e] = 0.f;
   float qsum = 0.f;
+  // 128-bit path (aligned rows): the next 32-row chunk is fetched into registers (8 x LDG.128 per thread) while the current one
+  // is multiplied — the scalar, unpipelined staging paid a full HBM round trip per chunk
+  const bool vec = (N & 3) == 0 && (ld & 3) == 0 && ((reinterpret_cast<uintptr_t>(pre) | reinterpret_cast<uintptr_t>(post)) & 15u) == 0;
+  float4 pa[4], qa[4];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = tid + u * 128;
+      const int k = e >> 4, c = (e & 15) * 4;
+      const bool kin = k0 + k < k_end;
+      pa[u] = (kin && i0 + c < N) ? ldg4(pre + (size_t)(k0 + k) * ld + i0 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      qa[u] = (kin && j0 + c < N) ? ldg4(post + (size_t)(k0 + k) * ld + j0 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  if (vec) fetch(k_begin);
   for (int k0 = k_begin; k0 < k_end; k0 += TD_KC) {
     __syncthreads();
     // stage 32 rows x 64 columns of pre (columns i0..) and post (columns j0..): coalesced along the row
-    for (int e = tid; e < TD_KC * TD_T; e += 128) {
-      const int k = e / TD_T, c = e - k * TD_T;
-      const bool kin = k0 + k < k_end;
-      Ps[k][c] = (kin && i0 + c < N) ? __ldg(pre + (size_t)(k0 + k) * ld + i0 + c) : 0.f;
-      Qs[k][c] = (kin && j0 + c < N) ? __ldg(post + (size_t)(k0 + k) * ld + j0 + c) : 0.f;
+    if (vec) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = tid + u * 128;
+        const int k = e >> 4, c = (e & 15) * 4;
+        *reinterpret_cast<float4*>(&Ps[k][c]) = pa[u];
+        *reinterpret_cast<float4*>(&Qs[k][c]) = qa[u];
+      }
+      if (k0 + TD_KC < k_end) fetch(k0 + TD_KC);
+    } else {
+      for (int e = tid; e < TD_KC * TD_T; e += 128) {
+        const int k = e / TD_T, c = e - k * TD_T;
+        const bool kin = k0 + k < k_end;
+        Ps[k][c] = (kin && i0 + c < N) ? __ldg(pre + (size_t)(k0 + k) * ld + i0 + c) : 0.f;
+        Qs[k][c] = (kin && j0 + c < N) ? __ldg(post + (size_t)(k0 + k) * ld + j0 + c) : 0.f;
+      }
     }
     __syncthreads();
-    if (blockIdx.y == 0 && tid < TD_T) {  // q_j = sum_k post_kj^2, once per column tile
+    if (WITH_Q && blockIdx.y == 0 && tid < TD_T) {  // q_j = sum_k post_kj^2, once per column tile
 #pragma unroll 8
       for (int k = 0; k < TD_KC; ++k) qsum = fmaf(Qs[k][tid], Qs[k][tid], qsum);
     }
@@ -292,7 +320,7 @@ __global__ void __launch_bounds__(128) trace_delta_mma_kernel(const float* __res
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           ah[a][e] = f2tf32(v[e]);
-          al[a][e] = f2tf32(v[e] - __uint_as_float(ah[a][e]));
+          al[a][e] = TERMS == 3 ? f2tf32(v[e] - __uint_as_float(ah[a][e])) : 0u;
         }
       }
 #pragma unroll
@@ -302,29 +330,337 @@ __global__ void __launch_bounds__(128) trace_delta_mma_kernel(const float* __res
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           bh[b][e] = f2tf32(v[e]);
-          bl[b][e] = f2tf32(v[e] - __uint_as_float(bh[b][e]));
+          bl[b][e] = TERMS == 3 ? f2tf32(v[e] - __uint_as_float(bh[b][e])) : 0u;
         }
       }
+      // term-outer order: consecutive MMAs write different accumulators (no stall on the previous MMA's result)
 #pragma unroll
-      for (int a = 0; a < 2; ++a)
+      for (int term = (TERMS == 3 ? 0 : 2); term < 3; ++term)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          mma_tf32_16x8x8(acc[a][b], al[a], bh[b]);  // small terms first
-          mma_tf32_16x8x8(acc[a][b], ah[a], bl[b]);
-          mma_tf32_16x8x8(acc[a][b], ah[a], bh[b]);
-        }
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b)
+            mma_tf32_16x8x8(acc[a][b], term == 0 ? al[a] : ah[a], term == 1 ? bl[b] : bh[b]);  // small terms first
     }
   }
+  if ((N & 3) == 0 && (reinterpret_cast<uintptr_t>(delta_q) & 15u) == 0) {
+    // merge through shared memory: one 16-byte vector reduction per four outputs (1024 per CTA instead of 4096 scalar atomics —
+    // the scalar version was bound by the L2 atomic rate: 1.2 M atomics on 16 K addresses)
+    constexpr int OLD = TD_T + 4;
+    static_assert(TD_T * OLD <= 2 * TD_KC * TD_LD, "output tile must fit the operand tiles");
+    __syncthreads();  // every warp is done with the operand tiles
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b)
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+          *reinterpret_cast<float2*>(td_sm + (wi + a * 16 + g + h * 8) * OLD + wj + b * 8 + 2 * t) =
+              make_float2(acc[a][b][2 * h], acc[a][b][2 * h + 1]);
+    __syncthreads();
+    for (int e = tid; e < TD_T * (TD_T / 4); e += 128) {
+      const int r = e >> 4, q = e & 15;
+      const int i = i0 + r, j = j0 + 4 * q;
+      if (i < N && j < N) {
+        const float4 v = *reinterpret_cast<const float4*>(td_sm + r * OLD + 4 * q);
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(delta_q + (size_t)i * N + j), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                     : "memory");
+      }
+    }
+  } else {
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int i = i0 + wi + a * 16 + g + (e >> 1) * 8, j = j0 + wj + b * 8 + 2 * t + (e & 1);
+          if (i < N && j < N) atomicAdd(delta_q + (size_t)i * N + j, acc[a][b][e]);
+        }
+  }
+  if (WITH_Q && blockIdx.y == 0 && tid < TD_T && j0 + tid < N) atomicAdd(delta_q + (size_t)N * N + j0 + tid, qsum);
+}
+
+// ---- fused head for the training step: forward + BCE loss + sigmoid/BCE backward + gX in ONE kernel ------------------------
+// (TF32 mode of TrainStep; the strict-fp32 path keeps the FFMA GEMMs above.)  A CTA owns 64 rows of X [M = B*N, N]:
+//   phase 1  Z = X_tile @ Weff, Weff = w + alpha*hebb built on the way into shared memory (no weff launch, no weff tensor)
+//   epilogue S = sigmoid(Z) -> global; loss -= t*log(S) + (1-t)*log(1-S) (torch.nn.BCELoss: logs clamped at -100, mean);
+//            gA = dLoss/dZ = ((S-t)/max(S(1-S),1e-12)/n) * S * (1-S) -> global (the parameter gradients read it) and back into
+//            the X tile's shared memory
+//   phase 2  gX = gA_tile @ Weff^T from the SAME shared-memory copy of Weff
+// mma.sync.m16n8k8 TF32.  Phase 1 uses the three-term error-compensated split (x = hi + lo, hi = the top 19 bits:
+// x*y ~ hi*hi' + hi*lo' + lo*hi'; the dropped terms are 2^-20 relative): the logits decide the thresholded masks, the loss and
+// the trace, and keep fp32-level accuracy.  Phase 2 is a plain TF32 product of round-to-nearest operands: gX enters the
+// tensor-core data-gradient convs, which round it to TF32 anyway.
+// Weff sits in shared memory ONCE, unpadded, with the column index XOR-swizzled by s(r) = 8*(r&3) + 4*((r>>2)&1): the B
+// fragments of phase 1 (rows k+t, columns n+g) and of phase 2 (rows n+g, columns k+t) are then both bank-conflict free.
+// The loss is reduced deterministically and without a memset: every CTA publishes its partial sum, the last one to arrive
+// (ticket counter in `scratch`, re-zeroed for the next launch) adds them in block order.
+constexpr int HF_BM = 64, HF_NP = 128, HF_LDX = HF_NP + 4;
+constexpr int HF_SMEM = (HF_NP * HF_NP + HF_BM * HF_LDX + HF_BM * HF_NP) * (int)sizeof(float);
+
+__device__ __forceinline__ int hf_swz(int r) { return ((r & 3) << 3) | (r & 4); }
+__device__ __forceinline__ void hf_split(float x, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(x) & 0xffffe000u;                                  // top 19 bits: a valid TF32 operand
+  lo = __float_as_uint(x - __uint_as_float(hi)) & 0xffffe000u;            // exact residual, truncated to TF32
+}
+__device__ __forceinline__ uint32_t hf_rn(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }  // RN (ties away) to TF32
+
+// acc = As[64-row tile][k] @ B, B[k][n] = TRANS_B ? Ws[n][k] : Ws[k][n]; this warp's 32 x 32 sub-tile.  TERMS = 3: error-
+// compensated split; TERMS = 1: plain TF32.
+template <bool TRANS_B, int TERMS>
+__device__ __forceinline__ void hf_gemm(float (&acc)[2][4][4], const float* __restrict__ As, const float* __restrict__ Ws, int wm, int wn,
+                                        int g, int t, int nk, int N) {
 #pragma unroll
   for (int a = 0; a < 2; ++a)
 #pragma unroll
     for (int b = 0; b < 4; ++b)
 #pragma unroll
+      for (int e = 0; e < 4; ++e) acc[a][b][e] = 0.f;
+#pragma unroll 2
+  for (int ks = 0; ks < nk; ++ks) {
+    const int kk = ks * 8;
+    uint32_t ah[2][4], al[2][4], bh[4][2], bl[4][2];
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      const float* r0 = As + (wm + a * 16 + g) * HF_LDX + kk + t;
+      const float v[4] = {r0[0], r0[8 * HF_LDX], r0[4], r0[8 * HF_LDX + 4]};
+#pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const int i = i0 + wi + a * 16 + g + (e >> 1) * 8, j = j0 + wj + b * 8 + 2 * t + (e & 1);
-        if (i < N && j < N) atomicAdd(delta_q + (size_t)i * N + j, acc[a][b][e]);
+        if (TERMS == 3) {
+          hf_split(v[e], ah[a][e], al[a][e]);
+        } else {
+          ah[a][e] = hf_rn(v[e]);
+          al[a][e] = 0u;
+        }
       }
-  if (blockIdx.y == 0 && tid < TD_T && j0 + tid < N) atomicAdd(delta_q + (size_t)N * N + j0 + tid, qsum);
+    }
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int n0 = wn + b * 8;
+      float v[2] = {0.f, 0.f};
+      if (n0 < N) {  // warp-uniform
+        if (!TRANS_B) {  // B[k][n] = Ws[k][n]
+          const int r = kk + t, c = n0 + g;
+          v[0] = Ws[r * HF_NP + (c ^ hf_swz(r))];
+          v[1] = Ws[(r + 4) * HF_NP + (c ^ hf_swz(r + 4))];
+        } else {  // B[k][n] = Ws[n][k]
+          const int r = n0 + g, c = kk + t, sw = hf_swz(r);
+          v[0] = Ws[r * HF_NP + (c ^ sw)];
+          v[1] = Ws[r * HF_NP + ((c + 4) ^ sw)];
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        if (TERMS == 3) {
+          hf_split(v[e], bh[b][e], bl[b][e]);
+        } else {
+          bh[b][e] = hf_rn(v[e]);
+          bl[b][e] = 0u;
+        }
+      }
+    }
+    // term-outer order: consecutive MMAs write DIFFERENT accumulators (an mma.sync waits for the previous one into the same
+    // accumulator: with the three terms of a tile back to back the warp stalled two MMA latencies per tile)
+#pragma unroll
+    for (int term = (TERMS == 3 ? 0 : 2); term < 3; ++term)
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          if (wn + b * 8 >= N) continue;
+          mma_tf32_16x8x8(acc[a][b], term == 0 ? al[a] : ah[a], term == 1 ? bl[b] : bh[b]);  // small terms first
+        }
+  }
+}
+
+// one BCE element: s = sigmoid(z); loss term; ga = dloss/dz (see the header comment)
+__device__ __forceinline__ void hf_bce(float z, float tt, float inv_n, float& s, float& ga, float& lsum) {
+  s = 1.f / (1.f + expf(-z));
+  const float l1 = fmaxf(logf(s), -100.f), l0 = fmaxf(log1pf(-s), -100.f);
+  lsum -= tt * l1 + (1.f - tt) * l0;
+  const float gs = (s - tt) / fmaxf(s * (1.f - s), 1e-12f) * inv_n;
+  ga = gs * s * (1.f - s);
+}
+
+__device__ __forceinline__ void hf_cp16(float* dst_smem, const float* src, bool ok) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src), "r"(ok ? 16 : 0)
+               : "memory");
+}
+
+// The kernel is executed ONCE per warp (128 CTAs, no tile loop), so its code size is its cost: the first version — pointwise
+// epilogue unrolled over the 32 accumulator registers of a thread, ~10 k instructions — spent 46 % of its issue slots waiting
+// for instruction fetches (ncu: stall_no_instruction).  Hence the pointwise work is a ROLLED loop over the tile in shared
+// memory (logits out of the accumulators, gA back in for phase 2), with coalesced 128-bit global accesses.
+__global__ void __launch_bounds__(256) head_bce_fused_kernel(const float* __restrict__ X, const float* __restrict__ w,
+                                                             const float* __restrict__ alpha, const float* __restrict__ hebb,
+                                                             const float* __restrict__ T, float* __restrict__ S, float* __restrict__ loss,
+                                                             float* __restrict__ gA, float* __restrict__ gX, float* __restrict__ scratch,
+                                                             int M, int N, float inv_n, int vec) {
+  extern __shared__ __align__(16) float hf_smem[];
+  __shared__ float red[8];
+  float* Ws = hf_smem;                   // [128][128], swizzled columns
+  float* Xs = hf_smem + HF_NP * HF_NP;   // [64][132]: the X tile, then the logits, then the gA tile
+  float* Ts = Xs + HF_BM * HF_LDX;       // [64][128]: the targets of the tile
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int m_blk = blockIdx.x * HF_BM;
+  const int wm = (warp >> 2) * 32, wn = (warp & 3) * 32;
+  const int nq = N >> 2;
+  // ---- stage: X tile and targets (HBM; asynchronous copies), then Weff (L2 after the first CTA); zero outside [M x N] / [N x N]
+  if (vec) {
+#pragma unroll 4
+    for (int it = 0; it < HF_BM * (HF_NP / 4) / 256; ++it) {
+      const int e = tid + it * 256;
+      const int r = e >> 5, q = e & 31;
+      const bool ok = m_blk + r < M && q < nq;
+      const size_t o = ok ? (size_t)(m_blk + r) * N + 4 * q : 0;
+      hf_cp16(Xs + r * HF_LDX + 4 * q, X + o, ok);
+      hf_cp16(Ts + r * HF_NP + 4 * q, T + o, ok);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#pragma unroll 8
+    for (int it = 0; it < HF_NP * (HF_NP / 4) / 256; ++it) {
+      const int e = tid + it * 256;
+      const int r = e >> 5, q = e & 31;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < N && q < nq) {
+        const size_t o = (size_t)r * N + 4 * q;
+        const float4 a = ldg4(alpha + o), h = ldg4(hebb + o), b = ldg4(w + o);
+        v = make_float4(fmaf(a.x, h.x, b.x), fmaf(a.y, h.y, b.y), fmaf(a.z, h.z, b.z), fmaf(a.w, h.w, b.w));
+      }
+      *reinterpret_cast<float4*>(Ws + r * HF_NP + ((4 * q) ^ hf_swz(r))) = v;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  } else {
+#pragma unroll 4
+    for (int e = tid; e < HF_BM * HF_NP; e += 256) {
+      const int r = e >> 7, c = e & 127;
+      const bool ok = m_blk + r < M && c < N;
+      const size_t o = ok ? (size_t)(m_blk + r) * N + c : 0;
+      Xs[r * HF_LDX + c] = ok ? __ldg(X + o) : 0.f;
+      Ts[r * HF_NP + c] = ok ? __ldg(T + o) : 0.f;
+    }
+#pragma unroll 4
+    for (int e = tid; e < HF_NP * HF_NP; e += 256) {
+      const int r = e >> 7, c = e & 127;
+      float v = 0.f;
+      if (r < N && c < N) {
+        const size_t o = (size_t)r * N + c;
+        v = fmaf(__ldg(alpha + o), __ldg(hebb + o), __ldg(w + o));
+      }
+      Ws[r * HF_NP + (c ^ hf_swz(r))] = v;
+    }
+  }
+  __syncthreads();
+  const int nk = (N + 7) >> 3;
+  float acc[2][4][4];
+  hf_gemm<false, 3>(acc, Xs, Ws, wm, wn, g, t, nk, N);
+  __syncthreads();  // every warp is done reading the X tile
+  // logits -> shared memory (columns of skipped n-tiles are >= N and never read)
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      if (wn + b * 8 >= N) continue;
+#pragma unroll
+      for (int hrow = 0; hrow < 2; ++hrow)
+        *reinterpret_cast<float2*>(Xs + (wm + a * 16 + g + hrow * 8) * HF_LDX + wn + b * 8 + 2 * t) =
+            make_float2(acc[a][b][hrow * 2], acc[a][b][hrow * 2 + 1]);
+    }
+  __syncthreads();
+  // ---- pointwise pass (rolled): sigmoid, BCE, gradient of the logits; the tile in shared memory becomes gA
+  float lsum = 0.f;
+  if (vec) {
+#pragma unroll 1
+    for (int it = 0; it < HF_BM * (HF_NP / 4) / 256; ++it) {
+      const int e = tid + it * 256;
+      const int r = e >> 5, q = e & 31;
+      float4 ga4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (m_blk + r < M && q < nq) {
+        const float4 z4 = *reinterpret_cast<const float4*>(Xs + r * HF_LDX + 4 * q);
+        const float4 t4 = *reinterpret_cast<const float4*>(Ts + r * HF_NP + 4 * q);
+        float4 s4;
+        hf_bce(z4.x, t4.x, inv_n, s4.x, ga4.x, lsum);
+        hf_bce(z4.y, t4.y, inv_n, s4.y, ga4.y, lsum);
+        hf_bce(z4.z, t4.z, inv_n, s4.z, ga4.z, lsum);
+        hf_bce(z4.w, t4.w, inv_n, s4.w, ga4.w, lsum);
+        const size_t o = (size_t)(m_blk + r) * N + 4 * q;
+        *reinterpret_cast<float4*>(S + o) = s4;
+        *reinterpret_cast<float4*>(gA + o) = ga4;
+      }
+      *reinterpret_cast<float4*>(Xs + r * HF_LDX + 4 * q) = ga4;
+    }
+  } else {
+#pragma unroll 1
+    for (int e = tid; e < HF_BM * HF_NP; e += 256) {
+      const int r = e >> 7, c = e & 127;
+      float ga = 0.f;
+      if (m_blk + r < M && c < N) {
+        float s;
+        hf_bce(Xs[r * HF_LDX + c], Ts[r * HF_NP + c], inv_n, s, ga, lsum);
+        const size_t o = (size_t)(m_blk + r) * N + c;
+        S[o] = s;
+        gA[o] = ga;
+      }
+      Xs[r * HF_LDX + c] = ga;
+    }
+  }
+  lsum = warp_sum(lsum);
+  if (lane == 0) red[warp] = lsum;
+  __syncthreads();  // the gA tile is complete
+  if (tid == 0) {
+    float s = 0.f;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) s += red[u];
+    if (scratch == nullptr) {
+      atomicAdd(loss, s * inv_n);  // the caller zeroed *loss
+    } else {
+      // scratch[0] = ticket counter (zero between launches), scratch[1 + b] = partial sum of CTA b; the ticket is drawn at the
+      // very end of the kernel (nothing of this CTA waits for the atomic's round trip)
+      scratch[1 + blockIdx.x] = s;
+      __threadfence();
+    }
+  }
+  if (gX != nullptr) {
+    // ---- phase 2: gX = gA @ Weff^T
+    hf_gemm<true, 1>(acc, Xs, Ws, wm, wn, g, t, nk, N);
+    const bool pair = (N & 1) == 0;  // (row*N + col) is even for even col: 8-byte stores
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b)
+#pragma unroll
+        for (int hrow = 0; hrow < 2; ++hrow) {
+          const int row = m_blk + wm + a * 16 + g + hrow * 8;
+          const int col = wn + b * 8 + 2 * t;
+          if (row >= M || col >= N) continue;
+          const size_t o = (size_t)row * N + col;
+          if (pair) {
+            *reinterpret_cast<float2*>(gX + o) = make_float2(acc[a][b][hrow * 2], acc[a][b][hrow * 2 + 1]);
+          } else {
+            gX[o] = acc[a][b][hrow * 2];
+            if (col + 1 < N) gX[o + 1] = acc[a][b][hrow * 2 + 1];
+          }
+        }
+  }
+  // ---- loss: the last CTA to arrive adds the partial sums in a fixed order (warp 0: lane-strided, then the shuffle tree)
+  if (scratch != nullptr && warp == 0) {
+    unsigned ticket = 0;
+    if (lane == 0) ticket = atomicAdd(reinterpret_cast<unsigned int*>(scratch), 1u);  // after this thread's own fenced partial store
+    ticket = __shfl_sync(0xffffffffu, ticket, 0);
+    if (ticket == gridDim.x - 1) {
+      __threadfence();
+      const volatile float* part = scratch + 1;
+      float tot = 0.f;
+      for (unsigned b = lane; b < gridDim.x; b += 32) tot += part[b];
+      tot = warp_sum(tot);
+      if (lane == 0) {
+        *loss = tot * inv_n;
+        *reinterpret_cast<unsigned int*>(scratch) = 0u;
+      }
+    }
+  }
 }
 
 __global__ void trace_apply_kernel(const float* __restrict__ hebb, const float* __restrict__ delta_q, int Kdiv,
@@ -467,6 +803,69 @@ int pu_plastic_head_bwd(const float* X, const float* S, const float* gS, const f
   return PU_OK;
 }
 
+int pu_plastic_head_bce(const float* X, const float* w, const float* alpha, const float* hebb, const float* target, float* S,
+                        float* loss, float* gA, float* gX, float* scratch, int B, int N, void* stream) {
+  PU_REQUIRE(X && w && alpha && hebb && target && S && loss && gA && B > 0 && N > 0, PU_ERR_BAD_ARG, "pu_plastic_head_bce: bad argument");
+  PU_REQUIRE(N <= pu::HF_NP, PU_ERR_UNSUPPORTED, "pu_plastic_head_bce: N=%d > %d", N, pu::HF_NP);
+  cudaStream_t st = pu::as_stream(stream);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(pu::head_bce_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pu::HF_SMEM);
+    if (e != cudaSuccess) {
+      pu::set_error("pu_plastic_head_bce: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return PU_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  if (scratch == nullptr) {  // no ticket scratch: atomics into a zeroed *loss
+    cudaError_t e = cudaMemsetAsync(loss, 0, sizeof(float), st);
+    if (e != cudaSuccess) {
+      pu::set_error("pu_plastic_head_bce memset: %s", cudaGetErrorString(e));
+      return PU_ERR_CUDA;
+    }
+  }
+  const int M = B * N;
+  const int vec = (N % 4 == 0) && pu::aligned16(X) && pu::aligned16(w) && pu::aligned16(alpha) && pu::aligned16(hebb) &&
+                  pu::aligned16(target) && pu::aligned16(S) && pu::aligned16(gA);
+  const bool al8 = ((reinterpret_cast<uintptr_t>(target) | reinterpret_cast<uintptr_t>(S) | reinterpret_cast<uintptr_t>(gA) |
+                     reinterpret_cast<uintptr_t>(gX)) & 7u) == 0;
+  PU_REQUIRE(al8, PU_ERR_BAD_ARG, "pu_plastic_head_bce: target, S, gA, gX must be 8-byte aligned");
+  pu::head_bce_fused_kernel<<<pu::cdiv(M, pu::HF_BM), 256, pu::HF_SMEM, st>>>(X, w, alpha, hebb, target, S, loss, gA, gX, scratch,
+                                                                              M, N, 1.f / ((float)M * (float)N), vec);
+  return pu::post_launch("pu_plastic_head_bce");
+}
+
+int pu_plastic_head_wgrad_tc(const float* X, const float* gA, const float* alpha, const float* hebb, float* gw, float* galpha,
+                             float* ghebb, int B, int N, int terms, void* stream) {
+  PU_REQUIRE(X && gA && alpha && hebb && gw && B > 0 && N > 0, PU_ERR_BAD_ARG, "pu_plastic_head_wgrad_tc: bad argument");
+  PU_REQUIRE(terms == 1 || terms == 3, PU_ERR_BAD_ARG, "pu_plastic_head_wgrad_tc: terms must be 1 (TF32) or 3 (3xTF32)");
+  cudaStream_t st = pu::as_stream(stream);
+  cudaError_t e = cudaMemsetAsync(gw, 0, sizeof(float) * (size_t)N * N, st);
+  if (e != cudaSuccess) {
+    pu::set_error("pu_plastic_head_wgrad_tc memset: %s", cudaGetErrorString(e));
+    return PU_ERR_CUDA;
+  }
+  // gW[i][j] = sum_m X[m][i] * gA[m][j]: the trace-delta contraction with pre = X, post = gA, K = B*N rows
+  const int K = B * N;
+  const int tiles = pu::cdiv(N, pu::TD_T);
+  int splits = pu::cdiv(2 * pu::kNumSMs, tiles * tiles);
+  int kper = pu::cdiv(K, splits);
+  kper = pu::cdiv(kper, pu::TD_KC) * pu::TD_KC;
+  splits = pu::cdiv(K, kper);
+  PU_REQUIRE(splits <= 65535, PU_ERR_UNSUPPORTED, "pu_plastic_head_wgrad_tc: B*N too large");
+  if (terms == 3)
+    pu::trace_delta_mma_kernel<false, 3><<<dim3(tiles, tiles, splits), 128, 0, st>>>(X, gA, N, K, kper, gw, N);
+  else
+    pu::trace_delta_mma_kernel<false, 1><<<dim3(tiles, tiles, splits), 128, 0, st>>>(X, gA, N, K, kper, gw, N);
+  int rc = pu::post_launch("pu_plastic_head_wgrad_tc");
+  if (rc) return rc;
+  if (galpha != nullptr || ghebb != nullptr) {
+    pu::head_param_grads_kernel<<<pu::cdiv((long long)N * N, 256), 256, 0, st>>>(gw, alpha, hebb, galpha, ghebb, N * N);
+    rc = pu::post_launch("pu_plastic_head_wgrad_tc param grads");
+  }
+  return rc;
+}
+
 int pu_trace_update_fwd(const float* hebb, const float* pre, const float* post, long long ld, int K, const float* eta, int rule,
                         float* out, int N, void* stream) {
   PU_REQUIRE(hebb && pre && post && eta && out && K > 0 && N > 0 && ld >= N, PU_ERR_BAD_ARG, "pu_trace_update_fwd: bad argument");
@@ -497,7 +896,7 @@ int pu_trace_delta_tc(const float* pre, const float* post, long long ld, int K, 
   kper = pu::cdiv(kper, pu::TD_KC) * pu::TD_KC;
   splits = pu::cdiv(K, kper);
   PU_REQUIRE(splits <= 65535, PU_ERR_UNSUPPORTED, "pu_trace_delta_tc: K too large");
-  pu::trace_delta_mma_kernel<<<dim3(tiles, tiles, splits), 128, 0, st>>>(pre, post, ld, K, kper, delta_q, N);
+  pu::trace_delta_mma_kernel<true><<<dim3(tiles, tiles, splits), 128, 0, st>>>(pre, post, ld, K, kper, delta_q, N);
   return pu::post_launch("pu_trace_delta_tc");
 }
 

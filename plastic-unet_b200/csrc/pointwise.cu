@@ -85,6 +85,35 @@ __global__ void conv1x1_fwd_kernel(const float* __restrict__ x, const float* __r
   }
 }
 
+// The output conv of the U-Net (unet_p.py:173: 8 -> 1 channels): a thread owns FOUR consecutive pixels — eight 128-bit loads of
+// 128 contiguous bytes, one 128-bit store; same summation order as the generic kernel (bias, then channels ascending).
+__global__ void __launch_bounds__(256) conv1x1_c8to1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                                const float* __restrict__ bias, float* __restrict__ y, long long nquad,
+                                                                int flags) {
+  float wc[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) wc[c] = __ldg(w + c);
+  const float b0 = bias != nullptr ? __ldg(bias) : 0.f;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < nquad; q += (long long)gridDim.x * blockDim.x) {
+    const float* xp = x + q * 32;
+    float4 v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = ldg4(xp + 4 * i);  // L1-allocating: two loads share every 32-byte sector
+    float o[4];
+#pragma unroll
+    for (int px = 0; px < 4; ++px) {
+      const float4 lo = v[2 * px], hi = v[2 * px + 1];
+      float a = b0;
+      a = fmaf(lo.x, wc[0], a); a = fmaf(lo.y, wc[1], a); a = fmaf(lo.z, wc[2], a); a = fmaf(lo.w, wc[3], a);
+      a = fmaf(hi.x, wc[4], a); a = fmaf(hi.y, wc[5], a); a = fmaf(hi.z, wc[6], a); a = fmaf(hi.w, wc[7], a);
+      if (flags & PU_FLAG_RELU) a = fmaxf(a, 0.f);
+      if (flags & PU_FLAG_ROUND_TF32) a = round_tf32(a);
+      o[px] = a;
+    }
+    *reinterpret_cast<float4*>(y + q * 4) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 // dx[p][ci] = sum_co g[p][co] w[co][ci]     (thread = pixel; Cout small)
 __global__ void conv1x1_dx_kernel(const float* __restrict__ g, const float* __restrict__ w, float* __restrict__ dx,
                                   long long npix, int Cin, int Cout, int K) {
@@ -297,6 +326,13 @@ int pu_conv1x1_fwd(const float* x, const float* w, const float* bias, float* y, 
   PU_REQUIRE(smem <= 48 * 1024, PU_ERR_UNSUPPORTED, "pu_conv1x1_fwd: Cin=%d too large", Cin);
   PU_REQUIRE(Cin % 4 != 0 || pu::aligned16(x), PU_ERR_BAD_ARG, "pu_conv1x1_fwd: x not 16-byte aligned");
   const long long npix = (long long)B * H * W;
+  if (Cout == 1 && Cin == 8 && coords == 0 && npix % 4 == 0 && pu::aligned16(x) && pu::aligned16(y)) {
+    const long long nquad = npix / 4;
+    long long blocks = (nquad + 255) / 256;
+    if (blocks > 16 * pu::kNumSMs) blocks = 16 * pu::kNumSMs;
+    pu::conv1x1_c8to1_fwd_kernel<<<(unsigned)blocks, 256, 0, pu::as_stream(stream)>>>(x, w, bias, y, nquad, flags);
+    return pu::post_launch("pu_conv1x1_fwd c8to1");
+  }
   dim3 grid((unsigned)((npix + 255) / 256), pu::cdiv(Cout, 8));
   pu::conv1x1_fwd_kernel<<<grid, 256, smem, pu::as_stream(stream)>>>(x, w, bias, y, npix, H, W, Cin, Cout, coords, flags);
   return pu::post_launch("pu_conv1x1_fwd");

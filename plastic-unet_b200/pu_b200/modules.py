@@ -114,6 +114,8 @@ class _PlasticBase(nn.Module):
         self.dp_side = None
         self.dp_external = None  # TrainStep (fused peer-memory exchange): callback(delta_q, K_global, rule) that takes over the trace reduction
         self.dp_world = 1
+        self._head_bce = None   # TrainStep (TF32 mode): the target tensor -> _plastic fuses head + BCE loss + their backward
+        self._head_loss = None  # ... and leaves the loss (autograd root of the step) here
         # TrainStep (data parallel): a callback fired in the backward pass once the gradient w.r.t. the input of encoder level
         # `_bucket_level` exists, i.e. when every parameter gradient of the decoder and of the deeper encoder levels has been
         # launched — the trainer all-reduces that bucket on a communication stream while the shallow levels still run
@@ -148,7 +150,14 @@ class _PlasticBase(nn.Module):
         X = o.view(B * N, N)
         hebb = hebb.contiguous()
         # 'free' and 'yoked' are numerically identical (alpha is always [nbf, nbf])
-        S, _ = ops.plastic_head(X, self.w, self.alpha, hebb)
+        self._head_loss = None
+        tgt = getattr(self, "_head_bce", None)
+        if tgt is not None and X.is_cuda and N <= 128 and self.conv_math == 'tf32' and torch.is_grad_enabled():
+            # TrainStep, TF32 mode: head forward + BCE loss + the backward of both in ONE launch (3xTF32 tensor-core GEMMs);
+            # the loss leaves through self._head_loss, and its backward() enters the U-Net with the finished gX
+            S, self._head_loss, _, _ = ops.plastic_head_bce(X, self.w, self.alpha, hebb, tgt, X.requires_grad)
+        else:
+            S, _ = ops.plastic_head(X, self.w, self.alpha, hebb)
         if self.rule == 'hebb':
             rule = ops.RULE_HEBB
         elif self.rule == 'oja':

@@ -13,6 +13,7 @@ from torch import Tensor
 from . import _lib
 
 import functools
+import os
 
 MATH_FP32 = 0
 MATH_TF32 = 1
@@ -1077,6 +1078,113 @@ def _head_backward(ctx, gS, _gweff):
 
 
 plastic_head.register_autograd(_head_backward, setup_context=_head_setup)
+
+
+# ---- training-step form of the head: forward + BCE loss + backward of both in one launch (TrainStep, TF32 mode) ------------
+# UNIT_GRAD: the gradient tensor TrainStep seeds `loss.backward()` with.  The fused kernel has already folded dloss/dloss = 1
+# into gA and gX; any other seed (a caller scaling the loss) is applied with plain tensor multiplies.
+UNIT_GRAD = None
+_HEAD_SCRATCH = {}
+_HEAD_SCRATCH_BLOCKS = 4096
+# terms of the head's parameter-gradient GEMM: 1 = plain TF32 (the precision of every conv weight gradient of the TF32 mode),
+# 3 = error-compensated 3xTF32 (fp32 level)
+HEAD_WGRAD_TERMS = int(os.environ.get("PU_HEAD_WGRAD_TERMS", "1"))
+
+
+@torch.library.custom_op("pu::plastic_head_bce", mutates_args=())
+def plastic_head_bce(X: Tensor, w: Tensor, alpha: Tensor, hebb: Tensor, target: Tensor,
+                     need_gx: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """-> (S, loss, gA, gX): S = sigmoid(X @ (w + alpha*hebb)) (unet_p.py:70-79), loss = nn.BCELoss()(S, target) (train.py:100-103),
+    gA = dloss/dlogits, gX = dloss/dX — one launch, 3xTF32 tensor-core GEMMs (fp32-level logits)."""
+    _chk(X, w, alpha, hebb, target)
+    N = w.shape[0]
+    B = X.shape[0] // N
+    if target.numel() != X.numel():
+        raise RuntimeError("plastic_head_bce: target has %d elements, the output %d" % (target.numel(), X.numel()))
+    S = torch.empty_like(X)
+    gA = torch.empty_like(X)
+    gX = torch.empty_like(X) if need_gx else _e(X.device)
+    loss = torch.empty(1, device=X.device, dtype=torch.float32)
+    nblk = (B * N + 63) // 64
+    scratch = None
+    if nblk <= _HEAD_SCRATCH_BLOCKS:
+        # ticket counter + per-CTA partial sums of the loss: zero once, every launch leaves it zeroed (one fused head at a time
+        # per device: launches that share it must be stream-ordered, as the steps of a TrainStep are)
+        scratch = _HEAD_SCRATCH.get(X.device.index)
+        if scratch is None:
+            scratch = _HEAD_SCRATCH[X.device.index] = torch.zeros(1 + _HEAD_SCRATCH_BLOCKS, device=X.device, dtype=torch.float32)
+    _lib.call("pu_plastic_head_bce", X.data_ptr(), w.data_ptr(), alpha.data_ptr(), hebb.data_ptr(), target.data_ptr(), S.data_ptr(),
+              loss.data_ptr(), gA.data_ptr(), gX.data_ptr() if need_gx else None, _p(scratch), B, N, _s())
+    return S, loss, gA, gX
+
+
+@plastic_head_bce.register_fake
+def _(X, w, alpha, hebb, target, need_gx):
+    return torch.empty_like(X), X.new_empty(1), torch.empty_like(X), torch.empty_like(X) if need_gx else X.new_empty(0)
+
+
+@torch.library.custom_op("pu::plastic_head_wgrad", mutates_args=())
+def plastic_head_wgrad(X: Tensor, gA: Tensor, alpha: Tensor, hebb: Tensor, need_galpha: bool, need_ghebb: bool) -> List[Tensor]:
+    """-> [gw, galpha, ghebb] from gA (on a weight-gradient side stream when TrainStep provides one)."""
+    _chk(X, gA, alpha, hebb)
+    N = alpha.shape[0]
+    B = X.shape[0] // N
+    gw = torch.empty_like(alpha)
+    galpha = torch.empty_like(alpha) if need_galpha else _e(X.device)
+    ghebb = torch.empty_like(alpha) if need_ghebb else _e(X.device)
+
+    def run():
+        _lib.call("pu_plastic_head_wgrad_tc", X.data_ptr(), gA.data_ptr(), alpha.data_ptr(), hebb.data_ptr(), gw.data_ptr(),
+                  galpha.data_ptr() if need_galpha else None, ghebb.data_ptr() if need_ghebb else None, B, N, HEAD_WGRAD_TERMS, _s())
+
+    side = _side_stream()
+    if side is not None:
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            run()
+        for t in (X, gA, alpha, hebb, gw, galpha if need_galpha else None, ghebb if need_ghebb else None):
+            if t is not None:
+                t.record_stream(side)
+        _note_side(gw, galpha if need_galpha else None)
+    else:
+        run()
+    return [gw, galpha, ghebb]
+
+
+@plastic_head_wgrad.register_fake
+def _(X, gA, alpha, hebb, need_galpha, need_ghebb):
+    e = X.new_empty(0)
+    return [torch.empty_like(alpha), torch.empty_like(alpha) if need_galpha else e, torch.empty_like(alpha) if need_ghebb else e]
+
+
+def _head_bce_setup(ctx, inputs, output):
+    X, w, alpha, hebb, target, need_gx = inputs
+    S, loss, gA, gX = output
+    ctx.set_materialize_grads(False)
+    ctx.save_for_backward(X, alpha, hebb, gA, gX)
+    ctx.need_gx = need_gx
+
+
+def _head_bce_backward(ctx, gS, gloss, _ga, _gx):
+    X, alpha, hebb, gA, gX = ctx.saved_tensors
+    need = ctx.needs_input_grad
+    if gS is not None:
+        raise RuntimeError("plastic_head_bce: the fused head owns the loss; a gradient through its sigmoid output is not supported "
+                           "(detach it, as train.py:99 does with the trace)")
+    if gloss is None:
+        return None, None, None, None, None, None
+    if need[0] and not ctx.need_gx:
+        raise RuntimeError("plastic_head_bce: built with need_gx=False but X requires a gradient")
+    if UNIT_GRAD is None or gloss.data_ptr() != UNIT_GRAD.data_ptr():
+        gA = gA * gloss
+        gX = gX * gloss if need[0] else gX
+    gw = galpha = ghebb = None
+    if need[1] or need[2] or need[3]:
+        gw, galpha, ghebb = plastic_head_wgrad(X, gA, alpha, hebb, need[2], need[3])
+    return (gX if need[0] else None, gw if need[1] else None, galpha if need[2] else None, ghebb if need[3] else None, None, None)
+
+
+plastic_head_bce.register_autograd(_head_bce_backward, setup_context=_head_bce_setup)
 
 
 @torch.library.custom_op("pu::trace_update", mutates_args=())

@@ -120,6 +120,8 @@ class TrainStep:
         self.target = torch.zeros((batch, net.nbf, net.nbf), device=self.dev)
         self.hebb = net.initialZeroHebb()
         self.loss = torch.zeros(1, device=self.dev)
+        self._unit = torch.ones(1, device=self.dev)  # seed of loss.backward() in the fused-head form
+        self._head_fused = os.environ.get("PU_HEAD_FUSED", "1") == "1"
         self.graph = None
         self._table_early = False
         self.kernels_per_step = None
@@ -127,6 +129,8 @@ class TrainStep:
         self._warm = warmup
         self._pack_list = None  # learnt by the first eager step: [(weight, transpose, math, C0)]
         self._pack_stream = None
+        self._aux_stream = None   # uploads the gather's pointer table beside the step's main chain (captured steps)
+        self._aux_pending = False
         import os as _os
         # weight gradients run on a side stream and overlap the dgrad chain (measured 1.56 -> 1.38 ms/step); PU_WGRAD_SIDE=0 disables
         nside = int(_os.environ.get("PU_WGRAD_SIDE", "4"))  # number of side streams (round-robin); 0 = none; measured 1: 1.305, 2: 1.191, 4: 1.171, 8: 1.174 ms
@@ -159,10 +163,20 @@ class TrainStep:
             p.grad = None  # autograd then hands over its gradient tensors instead of launching one add per parameter
         # Under capture the pointer table of the gradient gather is uploaded at the START of the step (a memcpy node reads the
         # pinned host table at replay time, and the table is final when the capture ends): 3 us off the step's tail.
+        # The copy runs on its own stream, joined only by the gather at the end of the step: as the first node of the main chain
+        # the copy-engine -> SM hand-off put ~12 us in front of the first kernel (profiles/r2_step_timeline_side4.txt).
         self._table_early = torch.cuda.is_current_stream_capturing()
         if self._table_early:
-            self.table_dev.copy_(self.table_host, non_blocking=True)
-        self.flat_g.zero_()
+            if self._aux_stream is None:
+                self._aux_stream = torch.cuda.Stream()
+            self._aux_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self._aux_stream):
+                self.table_dev.copy_(self.table_host, non_blocking=True)
+            self._aux_pending = True
+        if self._sink is not None:
+            self.flat_g.zero_()  # the gradient kernels accumulate into the arena
+        # (without the sink the gather overwrites every slot that has a gradient; the others and the alignment gaps stay zero
+        # from the construction on — nothing else writes the arena, the all-reduce adds zeros to them)
         if self._pack_list is None:
             ops.PACK_LOG, ops.PACK_CACHE = [], None  # first eager step: learn which weights the step packs
         else:
@@ -225,23 +239,35 @@ class TrainStep:
         if self._fused is not None:
             self._trace_job = None
             self.net.dp_external = self._take_trace_delta
+        # TF32 mode: the head, the BCE loss and the backward of both are ONE kernel inside the forward pass (modules._plastic);
+        # PU_HEAD_FUSED=0 keeps the separate head GEMMs + pu_bce_fwd_bwd (always used by the strict-fp32 and mixed modes)
+        self.net._head_bce = self.target if self._head_fused else None
         try:
             out, hebb_new = self.net(self.x, self.hebb)
         finally:
             self.net.dp_defer = False
             self.net.dp_external = None
-        gS = torch.empty_like(out)
-        n = out.numel()
-        _lib.call("pu_bce_fwd_bwd", out.data_ptr(), self.target.data_ptr(), self.loss.data_ptr(), gS.data_ptr(), n, st)
+            self.net._head_bce = None
+        fused_loss, self.net._head_loss = self.net._head_loss, None
+        if fused_loss is not None:
+            self.loss = fused_loss.detach()  # under capture: a tensor of the graph's pool, rewritten by every replay
+            root, seed = fused_loss, self._unit
+        else:
+            gS = torch.empty_like(out)
+            n = out.numel()
+            _lib.call("pu_bce_fwd_bwd", out.data_ptr(), self.target.data_ptr(), self.loss.data_ptr(), gS.data_ptr(), n, st)
+            root, seed = out, gS
         check = getattr(self, "_check_grads", False) and self.wgrad_side is not None
         if self.wgrad_side is not None:
             ops.WGRAD_SIDE_STREAMS = self.wgrad_side
         if check:
             ops.SIDE_OUTPUTS = set()
         ops.GRAD_SINK = self._sink
+        ops.UNIT_GRAD = self._unit
         try:
-            out.backward(gS)
+            root.backward(seed)
         finally:
+            ops.UNIT_GRAD = None
             ops.GRAD_SINK = None
             ops.WGRAD_SIDE_STREAMS = None
             side_ptrs, ops.SIDE_OUTPUTS = ops.SIDE_OUTPUTS, None
@@ -262,6 +288,9 @@ class TrainStep:
         self.net._bucket_hook = None
         if self._grad_params is None:
             self._grad_params = {id(p) for p in self.params if p.grad is not None}
+        if self._aux_pending:
+            torch.cuda.current_stream().wait_stream(self._aux_stream)  # the table upload started at the top of the step
+            self._aux_pending = False
         if self._early_done:
             self._gather(lambda p: id(p) in self._late, self.table_host, self.table_dev)
             dist.all_reduce(self.flat_g[self.split:], op=dist.ReduceOp.SUM, group=self.dp_group)

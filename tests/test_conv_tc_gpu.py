@@ -188,6 +188,13 @@ FLAT_SHAPES = [
     (1, 32, 32, 64, 40, 37),    # odd width
     (3, 64, 0, 64, 101, 101),   # several tiles per image, ragged edges
     (1, 256, 0, 256, 12, 12),   # 16 K chunks, four co blocks
+    # tap-row split (kernel template KS: tiles of <= 2 blocks of a >= 32-channel flat layer — the deep levels of the U-Net)
+    (64, 64, 0, 64, 8, 8),      # down4 @B=64: one block per tile, one tile per CTA, two accumulator buffers
+    (64, 64, 0, 64, 16, 16),    # down3.1: two blocks per tile, ONE accumulator buffer (384 TMEM columns)
+    (64, 32, 0, 64, 16, 16),    # down3.0
+    (400, 64, 0, 64, 8, 8),     # several tiles per CTA: the two buffers alternate
+    (300, 32, 0, 32, 16, 16),   # 32 columns, two blocks, several tiles per CTA
+    (3, 32, 32, 64, 9, 7),      # concat pair inside a split tile, ragged
 ]
 
 

@@ -388,6 +388,52 @@ def test_plastic_head(N, B):
     check(ho.grad, hr.grad, 5 * TOL, what="ghebb")
 
 
+@pytest.mark.parametrize("N,B,scale", [(32, 1, 1.0), (101, 3, 1.0), (128, 64, 1.0), (21, 3, 1.0), (64, 8, 0.25), (128, 5, 1.0)])
+def test_plastic_head_bce_fused(N, B, scale):
+    """The training-step form of the head (TrainStep, TF32 mode): head (unet_p.py:70-79) + nn.BCELoss (train.py:100-103) +
+    the backward of both in one launch, 3xTF32 tensor-core GEMMs — against the float64 formula.  Ragged N (101, 21: scalar
+    path, partial MMA tiles), batch tails (rows beyond B*N in the last 64-row tile), a non-unit loss seed."""
+    from pu_b200 import ops
+    g = torch.Generator().manual_seed(7 * N + B)
+    X = torch.randn(B * N, N, generator=g)
+    w, al, hb = 0.1 * torch.randn(N, N, generator=g), 0.1 * torch.rand(N, N, generator=g), 0.5 * torch.randn(N, N, generator=g)
+    T = (torch.rand(B, N, N, generator=g) > 0.6).float()
+    Xr, wr, ar, hr = (leaf(t, "cpu", torch.float64) for t in (X, w, al, hb))
+    Sr = torch.sigmoid(Xr.mm(wr + torch.mul(ar, hr)))
+    loss_r = F.binary_cross_entropy(Sr.view(B, N, N), T.double())
+    (loss_r * scale).backward()
+    Xo, wo, ao, ho = leaf(X), leaf(w), leaf(al), leaf(hb)
+    So, loss_o, gA, gX = ops.plastic_head_bce(Xo, wo, ao, ho, T.to(DEV), True)
+    seed = torch.full((1,), scale, device=DEV)
+    ops.UNIT_GRAD = seed if scale == 1.0 else None
+    try:
+        loss_o.backward(seed)
+    finally:
+        ops.UNIT_GRAD = None
+    check(So, Sr, what="S")  # the logits are 3xTF32: fp32 level
+    assert abs(float(loss_o.detach()) - float(loss_r)) < 1e-5 * abs(float(loss_r)), (float(loss_o.detach()), float(loss_r))
+    # gX is a plain TF32 product (it feeds the TF32 data-gradient convs): bound = TF32 rounding of both operands
+    check(Xo.grad, Xr.grad, 2e-3, what="gX")
+    assert rel_err(Xo.grad, Xr.grad)[1] < 1e-3
+    wtol = 5 * TOL if ops.HEAD_WGRAD_TERMS == 3 else 2e-3
+    check(wo.grad, wr.grad, wtol, what="gw")
+    check(ao.grad, ar.grad, wtol, what="galpha")
+    check(ho.grad, hr.grad, wtol, what="ghebb")
+    # the error-compensated parameter gradients (terms = 3) are at fp32 level
+    gA_r = (Sr.detach() - T.double().view(B * N, N)) / (B * N * N) * scale
+    saved = ops.HEAD_WGRAD_TERMS
+    ops.HEAD_WGRAD_TERMS = 3
+    try:
+        gw3, _, _ = ops.plastic_head_wgrad(Xo.detach(), gA_r.float().to(DEV).contiguous(), ao.detach(), ho.detach(), False, False)
+    finally:
+        ops.HEAD_WGRAD_TERMS = saved
+    check(gw3, Xr.detach().t().mm(gA_r), 5 * TOL, what="gw (3xTF32)")
+    # the strict-fp32 head + pu_bce_fwd_bwd (the path the fp32 mode keeps) agrees to fp32 level
+    X2, w2, a2, h2 = leaf(X), leaf(w), leaf(al), leaf(hb)
+    S2, _ = ops.plastic_head(X2, w2, a2, h2)
+    assert float((S2 - So).abs().max()) < 2e-6
+
+
 @pytest.mark.parametrize("rule", ["hebb", "oja"])
 @pytest.mark.parametrize("N,K", [(32, 1), (101, 1), (64, 5)])
 def test_trace_update(rule, N, K):
