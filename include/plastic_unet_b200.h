@@ -176,6 +176,13 @@ int pu_maxpool2_fwd(const float* x, const float* chan_scale, float* y, int B, in
  * x): a second gradient of x — the skip connection's (unet_p.py:165) — added in the same pass: dx = route(dy) + acc.   */
 int pu_maxpool2_bwd(const float* x, const float* chan_scale, const float* dy, const float* acc, float* dx,
                     int B, int H, int W, int C, int flags, void* stream);
+/* The same pair with an arg-max code: the forward pass also writes one byte per pooled element (bits 0-1: position of the
+ * maximum in the 2x2 window with ATen's tie-break, bit 2: maximum > 0) and the backward pass routes from it without re-reading
+ * x — a third less HBM traffic for the pooling backward of the training step (x [B,H,W,C] vs code [B,H/2,W/2,C] bytes). */
+int pu_maxpool2_fwd_code(const float* x, const float* chan_scale, float* y, unsigned char* code, int B, int H, int W, int C,
+                         void* stream);
+int pu_maxpool2_bwd_code(const unsigned char* code, const float* chan_scale, const float* dy, const float* acc, float* dx,
+                         int B, int H, int W, int C, int flags, void* stream);
 /* nn.Upsample(scale_factor=2, bilinear, align_corners=True) (reference unet_p.py:153)        */
 int pu_bilinear2x_fwd(const float* x, float* y, int B, int H, int W, int C, void* stream);
 int pu_bilinear2x_bwd(const float* dy, float* dx, int B, int H, int W, int C, void* stream);
@@ -236,9 +243,14 @@ int pu_plastic_head_bwd(const float* X, const float* S, const float* gS, const f
  * mma.sync TF32: the logits with the three-term error-compensated split (fp32-level: they decide masks, loss and trace),
  * gX as a plain TF32 product (it feeds the TF32 data-gradient convs).  N <= 128.
  * scratch: NULL (then *loss is zeroed by a memset node and summed with atomics) or 1 + ceil(B*N/64) floats, zero before
- * the FIRST launch and left zeroed by every launch: deterministic block-ordered loss sum, no memset.               */
-int pu_plastic_head_bce(const float* X, const float* w, const float* alpha, const float* hebb, const float* target,
-                        float* S, float* loss, float* gA, float* gX, float* scratch, int B, int N, void* stream);
+ * the FIRST launch and left zeroed by every launch: deterministic block-ordered loss sum, no memset.
+ * weff: NULL (Weff = w + alpha*hebb is built inside the kernel) or the matrix pu_head_weff computed beforehand — off the
+ * critical path, e.g. at the start of the step: the parameters and the trace are known then (w, alpha, hebb may be NULL). */
+int pu_plastic_head_bce(const float* X, const float* w, const float* alpha, const float* hebb, const float* weff,
+                        const float* target, float* S, float* loss, float* gA, float* gX, float* scratch, int B, int N,
+                        void* stream);
+/* weff = w + alpha*hebb [N, N] (unet_p.py:73-76; 'free' and 'yoked' alike) */
+int pu_head_weff(const float* w, const float* alpha, const float* hebb, float* weff, int N, void* stream);
 /* The head's parameter gradients from gA (either form): gw = X^T @ gA (split-K mma.sync, fp32 atomics; terms = 3:
  * error-compensated 3xTF32, terms = 1: plain TF32 as the conv weight gradients of the TF32 mode),
  * galpha = gw*hebb, ghebb = gw*alpha (each may be NULL).                                                         */

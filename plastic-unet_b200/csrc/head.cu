@@ -396,7 +396,7 @@ __global__ void __launch_bounds__(128) trace_delta_mma_kernel(const float* __res
 // fragments of phase 1 (rows k+t, columns n+g) and of phase 2 (rows n+g, columns k+t) are then both bank-conflict free.
 // The loss is reduced deterministically and without a memset: every CTA publishes its partial sum, the last one to arrive
 // (ticket counter in `scratch`, re-zeroed for the next launch) adds them in block order.
-constexpr int HF_BM = 64, HF_NP = 128, HF_LDX = HF_NP + 4;
+constexpr int HF_BM = 64, HF_NP = 128, HF_LDX = HF_NP + 4, HF_THREADS = 512;
 constexpr int HF_SMEM = (HF_NP * HF_NP + HF_BM * HF_LDX + HF_BM * HF_NP) * (int)sizeof(float);
 
 __device__ __forceinline__ int hf_swz(int r) { return ((r & 3) << 3) | (r & 4); }
@@ -406,32 +406,29 @@ __device__ __forceinline__ void hf_split(float x, uint32_t& hi, uint32_t& lo) {
 }
 __device__ __forceinline__ uint32_t hf_rn(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }  // RN (ties away) to TF32
 
-// acc = As[64-row tile][k] @ B, B[k][n] = TRANS_B ? Ws[n][k] : Ws[k][n]; this warp's 32 x 32 sub-tile.  TERMS = 3: error-
-// compensated split; TERMS = 1: plain TF32.
+// acc = As[64-row tile][k] @ B, B[k][n] = TRANS_B ? Ws[n][k] : Ws[k][n]; this warp's 16 x 32 sub-tile (16 warps: 4 x 4).
+// TERMS = 3: error-compensated split; TERMS = 1: plain TF32.
 template <bool TRANS_B, int TERMS>
-__device__ __forceinline__ void hf_gemm(float (&acc)[2][4][4], const float* __restrict__ As, const float* __restrict__ Ws, int wm, int wn,
-                                        int g, int t, int nk, int N) {
+__device__ __forceinline__ void hf_gemm(float (&acc)[4][4], const float* __restrict__ As, const float* __restrict__ Ws, int wm, int wn, int g,
+                                        int t, int nk, int N) {
 #pragma unroll
-  for (int a = 0; a < 2; ++a)
+  for (int b = 0; b < 4; ++b)
 #pragma unroll
-    for (int b = 0; b < 4; ++b)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) acc[a][b][e] = 0.f;
+    for (int e = 0; e < 4; ++e) acc[b][e] = 0.f;
 #pragma unroll 2
   for (int ks = 0; ks < nk; ++ks) {
     const int kk = ks * 8;
-    uint32_t ah[2][4], al[2][4], bh[4][2], bl[4][2];
-#pragma unroll
-    for (int a = 0; a < 2; ++a) {
-      const float* r0 = As + (wm + a * 16 + g) * HF_LDX + kk + t;
+    uint32_t ah[4], al[4], bh[4][2], bl[4][2];
+    {
+      const float* r0 = As + (wm + g) * HF_LDX + kk + t;
       const float v[4] = {r0[0], r0[8 * HF_LDX], r0[4], r0[8 * HF_LDX + 4]};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         if (TERMS == 3) {
-          hf_split(v[e], ah[a][e], al[a][e]);
+          hf_split(v[e], ah[e], al[e]);
         } else {
-          ah[a][e] = hf_rn(v[e]);
-          al[a][e] = 0u;
+          ah[e] = hf_rn(v[e]);
+          al[e] = 0u;
         }
       }
     }
@@ -465,22 +462,22 @@ __device__ __forceinline__ void hf_gemm(float (&acc)[2][4][4], const float* __re
 #pragma unroll
     for (int term = (TERMS == 3 ? 0 : 2); term < 3; ++term)
 #pragma unroll
-      for (int a = 0; a < 2; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          if (wn + b * 8 >= N) continue;
-          mma_tf32_16x8x8(acc[a][b], term == 0 ? al[a] : ah[a], term == 1 ? bl[b] : bh[b]);  // small terms first
-        }
+      for (int b = 0; b < 4; ++b) {
+        if (wn + b * 8 >= N) continue;
+        mma_tf32_16x8x8(acc[b], term == 0 ? al : ah, term == 1 ? bl[b] : bh[b]);  // small terms first
+      }
   }
 }
 
-// one BCE element: s = sigmoid(z); loss term; ga = dloss/dz (see the header comment)
+// one BCE element: s = sigmoid(z) (exact division: s decides the masks); loss term as torch.nn.BCELoss evaluates it on the fp32 s
+// (logs clamped at -100; log(1 - s) for log1p(-s): within 6e-8 absolute; hardware log2 — the loss scalar only, mean of B*N*N terms);
+// ga = dloss/dz = ((s - t) / max(s (1 - s), 1e-12) / n) * s (1 - s), i.e. (s - t) / n unless the clamp of the reference is active
 __device__ __forceinline__ void hf_bce(float z, float tt, float inv_n, float& s, float& ga, float& lsum) {
   s = 1.f / (1.f + expf(-z));
-  const float l1 = fmaxf(logf(s), -100.f), l0 = fmaxf(log1pf(-s), -100.f);
+  const float l1 = fmaxf(__logf(s), -100.f), l0 = fmaxf(__logf(1.f - s), -100.f);
   lsum -= tt * l1 + (1.f - tt) * l0;
-  const float gs = (s - tt) / fmaxf(s * (1.f - s), 1e-12f) * inv_n;
-  ga = gs * s * (1.f - s);
+  const float p = s * (1.f - s);
+  ga = p >= 1e-12f ? (s - tt) * inv_n : (s - tt) / 1e-12f * inv_n * p;
 }
 
 __device__ __forceinline__ void hf_cp16(float* dst_smem, const float* src, bool ok) {
@@ -491,50 +488,65 @@ __device__ __forceinline__ void hf_cp16(float* dst_smem, const float* src, bool 
 // The kernel is executed ONCE per warp (128 CTAs, no tile loop), so its code size is its cost: the first version — pointwise
 // epilogue unrolled over the 32 accumulator registers of a thread, ~10 k instructions — spent 46 % of its issue slots waiting
 // for instruction fetches (ncu: stall_no_instruction).  Hence the pointwise work is a ROLLED loop over the tile in shared
-// memory (logits out of the accumulators, gA back in for phase 2), with coalesced 128-bit global accesses.
-__global__ void __launch_bounds__(256) head_bce_fused_kernel(const float* __restrict__ X, const float* __restrict__ w,
-                                                             const float* __restrict__ alpha, const float* __restrict__ hebb,
-                                                             const float* __restrict__ T, float* __restrict__ S, float* __restrict__ loss,
-                                                             float* __restrict__ gA, float* __restrict__ gX, float* __restrict__ scratch,
-                                                             int M, int N, float inv_n, int vec) {
+// memory (logits out of the accumulators, gA back in for phase 2), with coalesced 128-bit global accesses; 16 warps per CTA
+// for memory-level parallelism in the staging and pointwise phases.  weff != NULL: Weff was computed beforehand
+// (pu_head_weff, off the critical path) and arrives by asynchronous copies — building it in the kernel from w, alpha and hebb
+// triples the L2 traffic of the staging phase (30 % of the kernel in the ncu capture of that version).
+__global__ void __launch_bounds__(HF_THREADS) head_bce_fused_kernel(const float* __restrict__ X, const float* __restrict__ w,
+                                                                    const float* __restrict__ alpha, const float* __restrict__ hebb,
+                                                                    const float* __restrict__ weff, const float* __restrict__ T,
+                                                                    float* __restrict__ S, float* __restrict__ loss, float* __restrict__ gA,
+                                                                    float* __restrict__ gX, float* __restrict__ scratch, int M, int N,
+                                                                    float inv_n, int vec) {
   extern __shared__ __align__(16) float hf_smem[];
-  __shared__ float red[8];
+  __shared__ float red[HF_THREADS / 32];
   float* Ws = hf_smem;                   // [128][128], swizzled columns
   float* Xs = hf_smem + HF_NP * HF_NP;   // [64][132]: the X tile, then the logits, then the gA tile
   float* Ts = Xs + HF_BM * HF_LDX;       // [64][128]: the targets of the tile
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int m_blk = blockIdx.x * HF_BM;
-  const int wm = (warp >> 2) * 32, wn = (warp & 3) * 32;
+  const int wm = (warp >> 2) * 16, wn = (warp & 3) * 32;
   const int nq = N >> 2;
   // ---- stage: X tile and targets (HBM; asynchronous copies), then Weff (L2 after the first CTA); zero outside [M x N] / [N x N]
   if (vec) {
-#pragma unroll 4
-    for (int it = 0; it < HF_BM * (HF_NP / 4) / 256; ++it) {
-      const int e = tid + it * 256;
+#pragma unroll
+    for (int it = 0; it < HF_BM * (HF_NP / 4) / HF_THREADS; ++it) {
+      const int e = tid + it * HF_THREADS;
       const int r = e >> 5, q = e & 31;
       const bool ok = m_blk + r < M && q < nq;
       const size_t o = ok ? (size_t)(m_blk + r) * N + 4 * q : 0;
       hf_cp16(Xs + r * HF_LDX + 4 * q, X + o, ok);
       hf_cp16(Ts + r * HF_NP + 4 * q, T + o, ok);
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-#pragma unroll 8
-    for (int it = 0; it < HF_NP * (HF_NP / 4) / 256; ++it) {
-      const int e = tid + it * 256;
-      const int r = e >> 5, q = e & 31;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (r < N && q < nq) {
-        const size_t o = (size_t)r * N + 4 * q;
-        const float4 a = ldg4(alpha + o), h = ldg4(hebb + o), b = ldg4(w + o);
-        v = make_float4(fmaf(a.x, h.x, b.x), fmaf(a.y, h.y, b.y), fmaf(a.z, h.z, b.z), fmaf(a.w, h.w, b.w));
+    if (weff != nullptr) {
+#pragma unroll
+      for (int it = 0; it < HF_NP * (HF_NP / 4) / HF_THREADS; ++it) {
+        const int e = tid + it * HF_THREADS;
+        const int r = e >> 5, q = e & 31;
+        const bool ok = r < N && q < nq;
+        hf_cp16(Ws + r * HF_NP + ((4 * q) ^ hf_swz(r)), weff + (ok ? (size_t)r * N + 4 * q : 0), ok);
       }
-      *reinterpret_cast<float4*>(Ws + r * HF_NP + ((4 * q) ^ hf_swz(r))) = v;
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    } else {
+      asm volatile("cp.async.commit_group;" ::: "memory");
+#pragma unroll 8
+      for (int it = 0; it < HF_NP * (HF_NP / 4) / HF_THREADS; ++it) {
+        const int e = tid + it * HF_THREADS;
+        const int r = e >> 5, q = e & 31;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < N && q < nq) {
+          const size_t o = (size_t)r * N + 4 * q;
+          const float4 a = ldg4(alpha + o), h = ldg4(hebb + o), b = ldg4(w + o);
+          v = make_float4(fmaf(a.x, h.x, b.x), fmaf(a.y, h.y, b.y), fmaf(a.z, h.z, b.z), fmaf(a.w, h.w, b.w));
+        }
+        *reinterpret_cast<float4*>(Ws + r * HF_NP + ((4 * q) ^ hf_swz(r))) = v;
+      }
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
   } else {
 #pragma unroll 4
-    for (int e = tid; e < HF_BM * HF_NP; e += 256) {
+    for (int e = tid; e < HF_BM * HF_NP; e += HF_THREADS) {
       const int r = e >> 7, c = e & 127;
       const bool ok = m_blk + r < M && c < N;
       const size_t o = ok ? (size_t)(m_blk + r) * N + c : 0;
@@ -542,39 +554,36 @@ __global__ void __launch_bounds__(256) head_bce_fused_kernel(const float* __rest
       Ts[r * HF_NP + c] = ok ? __ldg(T + o) : 0.f;
     }
 #pragma unroll 4
-    for (int e = tid; e < HF_NP * HF_NP; e += 256) {
+    for (int e = tid; e < HF_NP * HF_NP; e += HF_THREADS) {
       const int r = e >> 7, c = e & 127;
       float v = 0.f;
       if (r < N && c < N) {
         const size_t o = (size_t)r * N + c;
-        v = fmaf(__ldg(alpha + o), __ldg(hebb + o), __ldg(w + o));
+        v = weff != nullptr ? __ldg(weff + o) : fmaf(__ldg(alpha + o), __ldg(hebb + o), __ldg(w + o));
       }
       Ws[r * HF_NP + (c ^ hf_swz(r))] = v;
     }
   }
   __syncthreads();
   const int nk = (N + 7) >> 3;
-  float acc[2][4][4];
+  float acc[4][4];
   hf_gemm<false, 3>(acc, Xs, Ws, wm, wn, g, t, nk, N);
   __syncthreads();  // every warp is done reading the X tile
   // logits -> shared memory (columns of skipped n-tiles are >= N and never read)
 #pragma unroll
-  for (int a = 0; a < 2; ++a)
+  for (int b = 0; b < 4; ++b) {
+    if (wn + b * 8 >= N) continue;
 #pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      if (wn + b * 8 >= N) continue;
-#pragma unroll
-      for (int hrow = 0; hrow < 2; ++hrow)
-        *reinterpret_cast<float2*>(Xs + (wm + a * 16 + g + hrow * 8) * HF_LDX + wn + b * 8 + 2 * t) =
-            make_float2(acc[a][b][hrow * 2], acc[a][b][hrow * 2 + 1]);
-    }
+    for (int hrow = 0; hrow < 2; ++hrow)
+      *reinterpret_cast<float2*>(Xs + (wm + g + hrow * 8) * HF_LDX + wn + b * 8 + 2 * t) = make_float2(acc[b][hrow * 2], acc[b][hrow * 2 + 1]);
+  }
   __syncthreads();
   // ---- pointwise pass (rolled): sigmoid, BCE, gradient of the logits; the tile in shared memory becomes gA
   float lsum = 0.f;
   if (vec) {
 #pragma unroll 1
-    for (int it = 0; it < HF_BM * (HF_NP / 4) / 256; ++it) {
-      const int e = tid + it * 256;
+    for (int it = 0; it < HF_BM * (HF_NP / 4) / HF_THREADS; ++it) {
+      const int e = tid + it * HF_THREADS;
       const int r = e >> 5, q = e & 31;
       float4 ga4 = make_float4(0.f, 0.f, 0.f, 0.f);
       if (m_blk + r < M && q < nq) {
@@ -593,7 +602,7 @@ __global__ void __launch_bounds__(256) head_bce_fused_kernel(const float* __rest
     }
   } else {
 #pragma unroll 1
-    for (int e = tid; e < HF_BM * HF_NP; e += 256) {
+    for (int e = tid; e < HF_BM * HF_NP; e += HF_THREADS) {
       const int r = e >> 7, c = e & 127;
       float ga = 0.f;
       if (m_blk + r < M && c < N) {
@@ -612,7 +621,7 @@ __global__ void __launch_bounds__(256) head_bce_fused_kernel(const float* __rest
   if (tid == 0) {
     float s = 0.f;
 #pragma unroll
-    for (int u = 0; u < 8; ++u) s += red[u];
+    for (int u = 0; u < HF_THREADS / 32; ++u) s += red[u];
     if (scratch == nullptr) {
       atomicAdd(loss, s * inv_n);  // the caller zeroed *loss
     } else {
@@ -627,22 +636,20 @@ __global__ void __launch_bounds__(256) head_bce_fused_kernel(const float* __rest
     hf_gemm<true, 1>(acc, Xs, Ws, wm, wn, g, t, nk, N);
     const bool pair = (N & 1) == 0;  // (row*N + col) is even for even col: 8-byte stores
 #pragma unroll
-    for (int a = 0; a < 2; ++a)
+    for (int b = 0; b < 4; ++b)
 #pragma unroll
-      for (int b = 0; b < 4; ++b)
-#pragma unroll
-        for (int hrow = 0; hrow < 2; ++hrow) {
-          const int row = m_blk + wm + a * 16 + g + hrow * 8;
-          const int col = wn + b * 8 + 2 * t;
-          if (row >= M || col >= N) continue;
-          const size_t o = (size_t)row * N + col;
-          if (pair) {
-            *reinterpret_cast<float2*>(gX + o) = make_float2(acc[a][b][hrow * 2], acc[a][b][hrow * 2 + 1]);
-          } else {
-            gX[o] = acc[a][b][hrow * 2];
-            if (col + 1 < N) gX[o + 1] = acc[a][b][hrow * 2 + 1];
-          }
+      for (int hrow = 0; hrow < 2; ++hrow) {
+        const int row = m_blk + wm + g + hrow * 8;
+        const int col = wn + b * 8 + 2 * t;
+        if (row >= M || col >= N) continue;
+        const size_t o = (size_t)row * N + col;
+        if (pair) {
+          *reinterpret_cast<float2*>(gX + o) = make_float2(acc[b][hrow * 2], acc[b][hrow * 2 + 1]);
+        } else {
+          gX[o] = acc[b][hrow * 2];
+          if (col + 1 < N) gX[o + 1] = acc[b][hrow * 2 + 1];
         }
+      }
   }
   // ---- loss: the last CTA to arrive adds the partial sums in a fixed order (warp 0: lane-strided, then the shuffle tree)
   if (scratch != nullptr && warp == 0) {
@@ -803,9 +810,16 @@ int pu_plastic_head_bwd(const float* X, const float* S, const float* gS, const f
   return PU_OK;
 }
 
-int pu_plastic_head_bce(const float* X, const float* w, const float* alpha, const float* hebb, const float* target, float* S,
-                        float* loss, float* gA, float* gX, float* scratch, int B, int N, void* stream) {
-  PU_REQUIRE(X && w && alpha && hebb && target && S && loss && gA && B > 0 && N > 0, PU_ERR_BAD_ARG, "pu_plastic_head_bce: bad argument");
+int pu_head_weff(const float* w, const float* alpha, const float* hebb, float* weff, int N, void* stream) {
+  PU_REQUIRE(w && alpha && hebb && weff && N > 0, PU_ERR_BAD_ARG, "pu_head_weff: bad argument");
+  pu::weff_kernel<<<pu::cdiv((long long)N * N, 256), 256, 0, pu::as_stream(stream)>>>(w, alpha, hebb, weff, N * N);
+  return pu::post_launch("pu_head_weff");
+}
+
+int pu_plastic_head_bce(const float* X, const float* w, const float* alpha, const float* hebb, const float* weff, const float* target,
+                        float* S, float* loss, float* gA, float* gX, float* scratch, int B, int N, void* stream) {
+  PU_REQUIRE(X && (weff || (w && alpha && hebb)) && target && S && loss && gA && B > 0 && N > 0, PU_ERR_BAD_ARG,
+             "pu_plastic_head_bce: bad argument");
   PU_REQUIRE(N <= pu::HF_NP, PU_ERR_UNSUPPORTED, "pu_plastic_head_bce: N=%d > %d", N, pu::HF_NP);
   cudaStream_t st = pu::as_stream(stream);
   static bool attr_set = false;
@@ -825,13 +839,13 @@ int pu_plastic_head_bce(const float* X, const float* w, const float* alpha, cons
     }
   }
   const int M = B * N;
-  const int vec = (N % 4 == 0) && pu::aligned16(X) && pu::aligned16(w) && pu::aligned16(alpha) && pu::aligned16(hebb) &&
-                  pu::aligned16(target) && pu::aligned16(S) && pu::aligned16(gA);
+  const int vec = (N % 4 == 0) && pu::aligned16(X) && pu::aligned16(target) && pu::aligned16(S) && pu::aligned16(gA) &&
+                  (weff != nullptr ? pu::aligned16(weff) : (pu::aligned16(w) && pu::aligned16(alpha) && pu::aligned16(hebb)));
   const bool al8 = ((reinterpret_cast<uintptr_t>(target) | reinterpret_cast<uintptr_t>(S) | reinterpret_cast<uintptr_t>(gA) |
                      reinterpret_cast<uintptr_t>(gX)) & 7u) == 0;
   PU_REQUIRE(al8, PU_ERR_BAD_ARG, "pu_plastic_head_bce: target, S, gA, gX must be 8-byte aligned");
-  pu::head_bce_fused_kernel<<<pu::cdiv(M, pu::HF_BM), 256, pu::HF_SMEM, st>>>(X, w, alpha, hebb, target, S, loss, gA, gX, scratch,
-                                                                              M, N, 1.f / ((float)M * (float)N), vec);
+  pu::head_bce_fused_kernel<<<pu::cdiv(M, pu::HF_BM), pu::HF_THREADS, pu::HF_SMEM, st>>>(X, w, alpha, hebb, weff, target, S, loss, gA, gX,
+                                                                                         scratch, M, N, 1.f / ((float)M * (float)N), vec);
   return pu::post_launch("pu_plastic_head_bce");
 }
 

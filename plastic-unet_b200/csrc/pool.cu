@@ -6,9 +6,12 @@
 namespace pu {
 
 // V = 4 (float4 path, C % 4 == 0) or 1 (scalar)
+// code (optional): one byte per pooled element — bits 0-1 = position of the maximum inside the window (ATen's tie-break: the
+// first element, row-major, that is strictly greater or NaN), bit 2 = (maximum > 0).  The backward pass then routes the
+// gradient from the code alone instead of re-reading the four inputs of every window (a third of its HBM traffic).
 template <int V>
 __global__ void maxpool2_fwd_kernel(const float* __restrict__ x, const float* __restrict__ scale, float* __restrict__ y,
-                                    int B, int H, int W, int C) {
+                                    unsigned char* __restrict__ code, int B, int H, int W, int C) {
   const int Ho = H / 2, Wo = W / 2, CV = C / V;
   const long long n = (long long)B * Ho * Wo * CV;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -20,8 +23,9 @@ __global__ void maxpool2_fwd_kernel(const float* __restrict__ x, const float* __
     const int b = (int)(p / Ho);
     const float* xp = x + (((size_t)b * H + 2 * oy) * W + 2 * ox) * C + cv * V;
     float m[V];
+    int arg[V];
 #pragma unroll
-    for (int u = 0; u < V; ++u) m[u] = -INFINITY;
+    for (int u = 0; u < V; ++u) { m[u] = -INFINITY; arg[u] = 0; }
 #pragma unroll
     for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
@@ -32,12 +36,22 @@ __global__ void maxpool2_fwd_kernel(const float* __restrict__ x, const float* __
           const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
           for (int u = 0; u < V; ++u)
-            if (vv[u] > m[u] || vv[u] != vv[u]) m[u] = vv[u];
+            if (vv[u] > m[u] || vv[u] != vv[u]) { m[u] = vv[u]; arg[u] = 2 * dy + dx; }
         } else {
           const float v = __ldg(q);
-          if (v > m[0] || v != v) m[0] = v;
+          if (v > m[0] || v != v) { m[0] = v; arg[0] = 2 * dy + dx; }
         }
       }
+    if (code != nullptr) {
+      if (V == 4) {
+        uint32_t c4 = 0;
+#pragma unroll
+        for (int u = 0; u < V; ++u) c4 |= (uint32_t)(arg[u] | (m[u] > 0.f ? 4 : 0)) << (8 * u);
+        *reinterpret_cast<uint32_t*>(code + i * V) = c4;
+      } else {
+        code[i] = (unsigned char)(arg[0] | (m[0] > 0.f ? 4 : 0));
+      }
+    }
     if (scale != nullptr) {
 #pragma unroll
       for (int u = 0; u < V; ++u) m[u] *= __ldg(scale + (size_t)b * C + cv * V + u);
@@ -51,8 +65,9 @@ __global__ void maxpool2_fwd_kernel(const float* __restrict__ x, const float* __
 // one thread per pooling window (and channel vector): recompute the arg-max with ATen's tie-break
 // (first element in (dy,dx) row-major scan that is strictly greater / NaN) and route dy*scale there.
 template <int V>
-__global__ void maxpool2_bwd_kernel(const float* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ dy,
-                                    const float* __restrict__ acc, float* __restrict__ dx, int B, int H, int W, int C, int mask_in) {
+__global__ void maxpool2_bwd_kernel(const float* __restrict__ x, const unsigned char* __restrict__ code, const float* __restrict__ scale,
+                                    const float* __restrict__ dy, const float* __restrict__ acc, float* __restrict__ dx, int B, int H, int W,
+                                    int C, int mask_in) {
   const int Ho = H / 2, Wo = W / 2, CV = C / V;
   const long long n = (long long)B * Ho * Wo * CV;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -65,21 +80,35 @@ __global__ void maxpool2_bwd_kernel(const float* __restrict__ x, const float* __
     const size_t base = (((size_t)b * H + 2 * oy) * W + 2 * ox) * C + cv * V;
     float m[V];
     int arg[V];
-    float vals[4][V];
+    bool pos[V];  // the routed-to input is > 0 (mask_in: its ReLU mask)
+    if (code != nullptr) {  // the forward pass recorded where the maximum sits: no re-read of x
+      uint32_t c4;
+      if (V == 4) c4 = __ldg(reinterpret_cast<const uint32_t*>(code + i * V));
+      else c4 = code[i];
 #pragma unroll
-    for (int u = 0; u < V; ++u) { m[u] = -INFINITY; arg[u] = 0; }
+      for (int u = 0; u < V; ++u) {
+        arg[u] = (int)((c4 >> (8 * u)) & 3u);
+        pos[u] = ((c4 >> (8 * u)) & 4u) != 0;
+      }
+    } else {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float* q = x + base + ((size_t)(k >> 1) * W + (k & 1)) * C;
-      if (V == 4) {
-        const float4 v = ldg4(q);
-        vals[k][0] = v.x; vals[k][1 % V] = v.y; vals[k][2 % V] = v.z; vals[k][3 % V] = v.w;
-      } else {
-        vals[k][0] = __ldg(q);
+      for (int u = 0; u < V; ++u) { m[u] = -INFINITY; arg[u] = 0; }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float* q = x + base + ((size_t)(k >> 1) * W + (k & 1)) * C;
+        float vals[V];
+        if (V == 4) {
+          const float4 v = ldg4(q);
+          vals[0] = v.x; vals[1 % V] = v.y; vals[2 % V] = v.z; vals[3 % V] = v.w;
+        } else {
+          vals[0] = __ldg(q);
+        }
+#pragma unroll
+        for (int u = 0; u < V; ++u)
+          if (vals[u] > m[u] || vals[u] != vals[u]) { m[u] = vals[u]; arg[u] = k; }
       }
 #pragma unroll
-      for (int u = 0; u < V; ++u)
-        if (vals[k][u] > m[u] || vals[k][u] != vals[k][u]) { m[u] = vals[k][u]; arg[u] = k; }
+      for (int u = 0; u < V; ++u) pos[u] = m[u] > 0.f;
     }
     float g[V];
     if (V == 4) {
@@ -96,7 +125,7 @@ __global__ void maxpool2_bwd_kernel(const float* __restrict__ x, const float* __
     for (int k = 0; k < 4; ++k) {
       float o[V];
 #pragma unroll
-      for (int u = 0; u < V; ++u) o[u] = (arg[u] == k && !(mask_in && !(vals[k][u] > 0.f))) ? g[u] : 0.f;
+      for (int u = 0; u < V; ++u) o[u] = (arg[u] == k && !(mask_in && !pos[u])) ? g[u] : 0.f;
       const size_t qoff = base + ((size_t)(k >> 1) * W + (k & 1)) * C;
       if (acc != nullptr) {  // the other gradient of x (skip connection), accumulated here instead of by a separate add pass
         if (V == 4) {
@@ -240,21 +269,46 @@ int pu_zero_insert2x_bwd(const float* dz, float* dx, int B, int H, int W, int C,
 }
 
 
-int pu_maxpool2_fwd(const float* x, const float* chan_scale, float* y, int B, int H, int W, int C, void* stream) {
+static int maxpool2_fwd_impl(const float* x, const float* chan_scale, float* y, unsigned char* code, int B, int H, int W, int C,
+                             void* stream) {
   PU_REQUIRE(x && y && B > 0 && H >= 2 && W >= 2 && C > 0, PU_ERR_BAD_ARG, "pu_maxpool2_fwd: bad argument");
   cudaStream_t st = pu::as_stream(stream);
   const long long nwin = (long long)B * (H / 2) * (W / 2);
-  if (C % 4 == 0 && pu::aligned16(x) && pu::aligned16(y))
-    pu::maxpool2_fwd_kernel<4><<<pu::grid_for(nwin * (C / 4)), 256, 0, st>>>(x, chan_scale, y, B, H, W, C);
+  if (C % 4 == 0 && pu::aligned16(x) && pu::aligned16(y) && (reinterpret_cast<uintptr_t>(code) & 3u) == 0)
+    pu::maxpool2_fwd_kernel<4><<<pu::grid_for(nwin * (C / 4)), 256, 0, st>>>(x, chan_scale, y, code, B, H, W, C);
   else
-    pu::maxpool2_fwd_kernel<1><<<pu::grid_for(nwin * C), 256, 0, st>>>(x, chan_scale, y, B, H, W, C);
+    pu::maxpool2_fwd_kernel<1><<<pu::grid_for(nwin * C), 256, 0, st>>>(x, chan_scale, y, code, B, H, W, C);
   return pu::post_launch("pu_maxpool2_fwd");
 }
 
+int pu_maxpool2_fwd(const float* x, const float* chan_scale, float* y, int B, int H, int W, int C, void* stream) {
+  return maxpool2_fwd_impl(x, chan_scale, y, nullptr, B, H, W, C, stream);
+}
+
+int pu_maxpool2_fwd_code(const float* x, const float* chan_scale, float* y, unsigned char* code, int B, int H, int W, int C, void* stream) {
+  PU_REQUIRE(code != nullptr, PU_ERR_BAD_ARG, "pu_maxpool2_fwd_code: code is NULL");
+  return maxpool2_fwd_impl(x, chan_scale, y, code, B, H, W, C, stream);
+}
+
+static int maxpool2_bwd_impl(const float* x, const unsigned char* code, const float* chan_scale, const float* dy, const float* acc, float* dx,
+                             int B, int H, int W, int C, int flags, void* stream);
+
 int pu_maxpool2_bwd(const float* x, const float* chan_scale, const float* dy, const float* acc, float* dx, int B, int H, int W, int C,
                     int flags, void* stream) {
+  PU_REQUIRE(x != nullptr, PU_ERR_BAD_ARG, "pu_maxpool2_bwd: bad argument");
+  return maxpool2_bwd_impl(x, nullptr, chan_scale, dy, acc, dx, B, H, W, C, flags, stream);
+}
+
+int pu_maxpool2_bwd_code(const unsigned char* code, const float* chan_scale, const float* dy, const float* acc, float* dx, int B, int H,
+                         int W, int C, int flags, void* stream) {
+  PU_REQUIRE(code != nullptr, PU_ERR_BAD_ARG, "pu_maxpool2_bwd_code: code is NULL");
+  return maxpool2_bwd_impl(nullptr, code, chan_scale, dy, acc, dx, B, H, W, C, flags, stream);
+}
+
+static int maxpool2_bwd_impl(const float* x, const unsigned char* code, const float* chan_scale, const float* dy, const float* acc, float* dx,
+                             int B, int H, int W, int C, int flags, void* stream) {
   const int mask_in = (flags & PU_FLAG_MASK_IN) ? 1 : 0;
-  PU_REQUIRE(x && dy && dx && B > 0 && H >= 2 && W >= 2 && C > 0, PU_ERR_BAD_ARG, "pu_maxpool2_bwd: bad argument");
+  PU_REQUIRE((x || code) && dy && dx && B > 0 && H >= 2 && W >= 2 && C > 0, PU_ERR_BAD_ARG, "pu_maxpool2_bwd: bad argument");
   cudaStream_t st = pu::as_stream(stream);
   if ((H & 1) || (W & 1)) {  // floor mode leaves the last row/column unpooled: their gradient is zero (or just acc)
     const size_t bytes = sizeof(float) * (size_t)B * H * W * C;
@@ -265,10 +319,11 @@ int pu_maxpool2_bwd(const float* x, const float* chan_scale, const float* dy, co
     }
   }
   const long long nwin = (long long)B * (H / 2) * (W / 2);
-  if (C % 4 == 0 && pu::aligned16(x) && pu::aligned16(dy) && pu::aligned16(dx) && (acc == nullptr || pu::aligned16(acc)))
-    pu::maxpool2_bwd_kernel<4><<<pu::grid_for(nwin * (C / 4)), 256, 0, st>>>(x, chan_scale, dy, acc, dx, B, H, W, C, mask_in);
+  if (C % 4 == 0 && (x == nullptr || pu::aligned16(x)) && (reinterpret_cast<uintptr_t>(code) & 3u) == 0 && pu::aligned16(dy) && pu::aligned16(dx) &&
+      (acc == nullptr || pu::aligned16(acc)))
+    pu::maxpool2_bwd_kernel<4><<<pu::grid_for(nwin * (C / 4)), 256, 0, st>>>(x, code, chan_scale, dy, acc, dx, B, H, W, C, mask_in);
   else
-    pu::maxpool2_bwd_kernel<1><<<pu::grid_for(nwin * C), 256, 0, st>>>(x, chan_scale, dy, acc, dx, B, H, W, C, mask_in);
+    pu::maxpool2_bwd_kernel<1><<<pu::grid_for(nwin * C), 256, 0, st>>>(x, code, chan_scale, dy, acc, dx, B, H, W, C, mask_in);
   return pu::post_launch("pu_maxpool2_bwd");
 }
 

@@ -116,6 +116,7 @@ class _PlasticBase(nn.Module):
         self.dp_world = 1
         self._head_bce = None   # TrainStep (TF32 mode): the target tensor -> _plastic fuses head + BCE loss + their backward
         self._head_loss = None  # ... and leaves the loss (autograd root of the step) here
+        self._head_weff = None  # TrainStep: (w + alpha*hebb, event) computed off the critical path at the start of the step
         # TrainStep (data parallel): a callback fired in the backward pass once the gradient w.r.t. the input of encoder level
         # `_bucket_level` exists, i.e. when every parameter gradient of the decoder and of the deeper encoder levels has been
         # launched — the trainer all-reduces that bucket on a communication stream while the shallow levels still run
@@ -155,7 +156,11 @@ class _PlasticBase(nn.Module):
         if tgt is not None and X.is_cuda and N <= 128 and self.conv_math == 'tf32' and torch.is_grad_enabled():
             # TrainStep, TF32 mode: head forward + BCE loss + the backward of both in ONE launch (3xTF32 tensor-core GEMMs);
             # the loss leaves through self._head_loss, and its backward() enters the U-Net with the finished gX
-            S, self._head_loss, _, _ = ops.plastic_head_bce(X, self.w, self.alpha, hebb, tgt, X.requires_grad)
+            wf = getattr(self, "_head_weff", None)  # (Weff, event): computed by TrainStep at the start of the step
+            if wf is not None:
+                torch.cuda.current_stream().wait_event(wf[1])
+            S, self._head_loss, _, _ = ops.plastic_head_bce(X, self.w, self.alpha, hebb, tgt, X.requires_grad,
+                                                            wf[0] if wf is not None else None)
         else:
             S, _ = ops.plastic_head(X, self.w, self.alpha, hebb)
         if self.rule == 'hebb':

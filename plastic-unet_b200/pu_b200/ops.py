@@ -742,6 +742,47 @@ def _(dy, x, chan_scale, mask_in=False, acc=None):
     return torch.empty_like(x)
 
 
+@torch.library.custom_op("pu::maxpool2_code", mutates_args=())
+def maxpool2_code(x: Tensor) -> Tuple[Tensor, Tensor]:
+    """-> (maxpool2(x), code): code [B, H/2, W/2, C] uint8 records where each maximum sits (bits 0-1) and whether it is > 0
+    (bit 2), so that the backward pass does not re-read x."""
+    _chk(x)
+    B, H, W, C = x.shape
+    y = torch.empty((B, H // 2, W // 2, C), device=x.device, dtype=torch.float32)
+    code = torch.empty((B, H // 2, W // 2, C), device=x.device, dtype=torch.uint8)
+    _lib.call("pu_maxpool2_fwd_code", x.data_ptr(), None, y.data_ptr(), code.data_ptr(), B, H, W, C, _s())
+    return y, code
+
+
+@maxpool2_code.register_fake
+def _(x):
+    shp = (x.shape[0], x.shape[1] // 2, x.shape[2] // 2, x.shape[3])
+    return x.new_empty(shp), x.new_empty(shp, dtype=torch.uint8)
+
+
+@torch.library.custom_op("pu::maxpool2_bwd_code", mutates_args=())
+def maxpool2_bwd_code(dy: Tensor, code: Tensor, H: int, W: int, mask_in: bool = False, acc: Optional[Tensor] = None) -> Tensor:
+    """maxpool2_bwd from the arg-max code of maxpool2_code (x itself is not read); H, W: the size of x."""
+    _chk(dy, acc)
+    B, Ho, Wo, C = dy.shape
+    if not code.is_cuda or code.dtype != torch.uint8 or not code.is_contiguous() or tuple(code.shape) != (B, Ho, Wo, C):
+        raise RuntimeError("maxpool2_bwd_code: code must be the contiguous uint8 CUDA tensor maxpool2_code returned")
+    if (H // 2, W // 2) != (Ho, Wo) or (acc is not None and tuple(acc.shape) != (B, H, W, C)):
+        raise RuntimeError("maxpool2_bwd_code: shape mismatch")
+    dx = torch.empty((B, H, W, C), device=dy.device, dtype=torch.float32)
+    _lib.call("pu_maxpool2_bwd_code", code.data_ptr(), None, dy.data_ptr(), _p(acc), dx.data_ptr(), B, H, W, C,
+              FLAG_MASK_IN if mask_in else 0, _s())
+    return dx
+
+
+@maxpool2_bwd_code.register_fake
+def _(dy, code, H, W, mask_in=False, acc=None):
+    return dy.new_empty((dy.shape[0], H, W, dy.shape[3]))
+
+
+POOL_CODE = os.environ.get("PU_POOL_CODE", "1") == "1"
+
+
 class _PoolSkip(torch.autograd.Function):
     """x -> (maxpool2(x), x): the pooled tensor for the next encoder level and x itself as the skip connection
     (unet_p.py:59-66).  Both gradients of x then reach ONE backward call, and the skip gradient is accumulated inside the
@@ -749,9 +790,16 @@ class _PoolSkip(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, mask_in):
-        ctx.save_for_backward(x)
         ctx.mask_in = mask_in
         ctx.set_materialize_grads(False)
+        if POOL_CODE and x.requires_grad:
+            # the backward pass routes from one code byte per pooled element instead of re-reading x (33 of its 107 MB at 128x128)
+            y, code = maxpool2_code(x)
+            ctx.save_for_backward(code)
+            ctx.hw = (x.shape[1], x.shape[2])
+            return y, x.view_as(x)
+        ctx.save_for_backward(x)
+        ctx.hw = None
         return maxpool2(x, None, mask_in), x.view_as(x)
 
     @staticmethod
@@ -759,7 +807,10 @@ class _PoolSkip(torch.autograd.Function):
         (x,) = ctx.saved_tensors
         if gy is None:
             return gskip, None
-        return maxpool2_bwd(gy.contiguous(), x, None, ctx.mask_in, None if gskip is None else gskip.contiguous()), None
+        acc = None if gskip is None else gskip.contiguous()
+        if ctx.hw is not None:
+            return maxpool2_bwd_code(gy.contiguous(), x, ctx.hw[0], ctx.hw[1], ctx.mask_in, acc), None
+        return maxpool2_bwd(gy.contiguous(), x, None, ctx.mask_in, acc), None
 
 
 def pool_skip(x: Tensor, mask_in: bool = False) -> Tuple[Tensor, Tensor]:
@@ -1091,14 +1142,30 @@ _HEAD_SCRATCH_BLOCKS = 4096
 HEAD_WGRAD_TERMS = int(os.environ.get("PU_HEAD_WGRAD_TERMS", "1"))
 
 
+@torch.library.custom_op("pu::head_weff", mutates_args=())
+def head_weff(w: Tensor, alpha: Tensor, hebb: Tensor) -> Tensor:
+    """Weff = w + alpha*hebb (unet_p.py:73-76), for plastic_head_bce(weff=...): TrainStep computes it at the start of the step."""
+    _chk(w, alpha, hebb)
+    out = torch.empty_like(w)
+    _lib.call("pu_head_weff", w.data_ptr(), alpha.data_ptr(), hebb.data_ptr(), out.data_ptr(), w.shape[0], _s())
+    return out
+
+
+@head_weff.register_fake
+def _(w, alpha, hebb):
+    return torch.empty_like(w)
+
+
 @torch.library.custom_op("pu::plastic_head_bce", mutates_args=())
 def plastic_head_bce(X: Tensor, w: Tensor, alpha: Tensor, hebb: Tensor, target: Tensor,
-                     need_gx: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+                     need_gx: bool, weff: Optional[Tensor] = None) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
     """-> (S, loss, gA, gX): S = sigmoid(X @ (w + alpha*hebb)) (unet_p.py:70-79), loss = nn.BCELoss()(S, target) (train.py:100-103),
     gA = dloss/dlogits, gX = dloss/dX — one launch, 3xTF32 tensor-core GEMMs (fp32-level logits)."""
-    _chk(X, w, alpha, hebb, target)
+    _chk(X, w, alpha, hebb, target, weff)
     N = w.shape[0]
     B = X.shape[0] // N
+    if weff is not None and tuple(weff.shape) != (N, N):
+        raise RuntimeError("plastic_head_bce: weff must be [%d, %d]" % (N, N))
     if target.numel() != X.numel():
         raise RuntimeError("plastic_head_bce: target has %d elements, the output %d" % (target.numel(), X.numel()))
     S = torch.empty_like(X)
@@ -1113,13 +1180,13 @@ def plastic_head_bce(X: Tensor, w: Tensor, alpha: Tensor, hebb: Tensor, target: 
         scratch = _HEAD_SCRATCH.get(X.device.index)
         if scratch is None:
             scratch = _HEAD_SCRATCH[X.device.index] = torch.zeros(1 + _HEAD_SCRATCH_BLOCKS, device=X.device, dtype=torch.float32)
-    _lib.call("pu_plastic_head_bce", X.data_ptr(), w.data_ptr(), alpha.data_ptr(), hebb.data_ptr(), target.data_ptr(), S.data_ptr(),
-              loss.data_ptr(), gA.data_ptr(), gX.data_ptr() if need_gx else None, _p(scratch), B, N, _s())
+    _lib.call("pu_plastic_head_bce", X.data_ptr(), w.data_ptr(), alpha.data_ptr(), hebb.data_ptr(), _p(weff), target.data_ptr(),
+              S.data_ptr(), loss.data_ptr(), gA.data_ptr(), gX.data_ptr() if need_gx else None, _p(scratch), B, N, _s())
     return S, loss, gA, gX
 
 
 @plastic_head_bce.register_fake
-def _(X, w, alpha, hebb, target, need_gx):
+def _(X, w, alpha, hebb, target, need_gx, weff=None):
     return torch.empty_like(X), X.new_empty(1), torch.empty_like(X), torch.empty_like(X) if need_gx else X.new_empty(0)
 
 
@@ -1158,7 +1225,7 @@ def _(X, gA, alpha, hebb, need_galpha, need_ghebb):
 
 
 def _head_bce_setup(ctx, inputs, output):
-    X, w, alpha, hebb, target, need_gx = inputs
+    X, w, alpha, hebb, target, need_gx, _weff = inputs
     S, loss, gA, gX = output
     ctx.set_materialize_grads(False)
     ctx.save_for_backward(X, alpha, hebb, gA, gX)
@@ -1172,7 +1239,7 @@ def _head_bce_backward(ctx, gS, gloss, _ga, _gx):
         raise RuntimeError("plastic_head_bce: the fused head owns the loss; a gradient through its sigmoid output is not supported "
                            "(detach it, as train.py:99 does with the trace)")
     if gloss is None:
-        return None, None, None, None, None, None
+        return None, None, None, None, None, None, None
     if need[0] and not ctx.need_gx:
         raise RuntimeError("plastic_head_bce: built with need_gx=False but X requires a gradient")
     if UNIT_GRAD is None or gloss.data_ptr() != UNIT_GRAD.data_ptr():
@@ -1181,7 +1248,7 @@ def _head_bce_backward(ctx, gS, gloss, _ga, _gx):
     gw = galpha = ghebb = None
     if need[1] or need[2] or need[3]:
         gw, galpha, ghebb = plastic_head_wgrad(X, gA, alpha, hebb, need[2], need[3])
-    return (gX if need[0] else None, gw if need[1] else None, galpha if need[2] else None, ghebb if need[3] else None, None, None)
+    return (gX if need[0] else None, gw if need[1] else None, galpha if need[2] else None, ghebb if need[3] else None, None, None, None)
 
 
 plastic_head_bce.register_autograd(_head_bce_backward, setup_context=_head_bce_setup)

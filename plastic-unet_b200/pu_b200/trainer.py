@@ -241,13 +241,29 @@ class TrainStep:
             self.net.dp_external = self._take_trace_delta
         # TF32 mode: the head, the BCE loss and the backward of both are ONE kernel inside the forward pass (modules._plastic);
         # PU_HEAD_FUSED=0 keeps the separate head GEMMs + pu_bce_fwd_bwd (always used by the strict-fp32 and mixed modes)
-        self.net._head_bce = self.target if self._head_fused else None
+        fuse = self._head_fused and self.net.nbf <= 128 and getattr(self.net, "conv_math", "") == "tf32"
+        self.net._head_bce = self.target if fuse else None
+        if fuse:
+            # Weff = w + alpha*hebb depends only on what is known at the start of the step: computed beside the forward pass, so
+            # that the fused head kernel stages 64 KB by asynchronous copies instead of building it from three tensors
+            main = torch.cuda.current_stream()
+            if self._aux_stream is None:
+                self._aux_stream = torch.cuda.Stream()
+            self._aux_stream.wait_stream(main)
+            with torch.cuda.stream(self._aux_stream):
+                weff = ops.head_weff(self.net.w.detach(), self.net.alpha.detach(), self.hebb)
+                ev = torch.cuda.Event()
+                ev.record(self._aux_stream)
+            weff.record_stream(main)
+            self.net._head_weff = (weff, ev)
+            self._aux_pending = True  # joined before the gradient gather
         try:
             out, hebb_new = self.net(self.x, self.hebb)
         finally:
             self.net.dp_defer = False
             self.net.dp_external = None
             self.net._head_bce = None
+            self.net._head_weff = None
         fused_loss, self.net._head_loss = self.net._head_loss, None
         if fused_loss is not None:
             self.loss = fused_loss.detach()  # under capture: a tensor of the graph's pool, rewritten by every replay

@@ -53,5 +53,7 @@ gA0 = torch.randn_like(X)
 timed("separate: head fwd + bce + (sigmoid bwd, gX, gW, galpha)", separate_critical)
 timed("separate: head fwd only", lambda: ops.plastic_head(X, w, alpha, hebb))
 timed("fused: pu_plastic_head_bce (fwd + loss + gA + gX)", lambda: ops.plastic_head_bce(X, w, alpha, hebb, T, True))
+wf = ops.head_weff(w, alpha, hebb)
+timed("fused, Weff computed beforehand", lambda: ops.plastic_head_bce(X, w, alpha, hebb, T, True, wf))
 timed("fused: pu_plastic_head_bce without gX", lambda: ops.plastic_head_bce(X, w, alpha, hebb, T, False))
 timed("parameter gradients: pu_plastic_head_wgrad_tc (3xTF32 split-K)", lambda: ops.plastic_head_wgrad(X, gA0, alpha, hebb, True, False))

@@ -428,6 +428,11 @@ def test_plastic_head_bce_fused(N, B, scale):
     finally:
         ops.HEAD_WGRAD_TERMS = saved
     check(gw3, Xr.detach().t().mm(gA_r), 5 * TOL, what="gw (3xTF32)")
+    # Weff computed beforehand (TrainStep does that off the critical path) gives bit-identical results
+    with torch.no_grad():
+        wf = ops.head_weff(wo.detach(), ao.detach(), ho.detach())
+        S3, loss3, gA3, gX3 = ops.plastic_head_bce(Xo.detach(), wo.detach(), ao.detach(), ho.detach(), T.to(DEV), True, wf)
+    assert torch.equal(S3, So) and torch.equal(loss3, loss_o.detach()) and torch.equal(gA3, gA.detach()) and torch.equal(gX3, gX.detach())
     # the strict-fp32 head + pu_bce_fwd_bwd (the path the fp32 mode keeps) agrees to fp32 level
     X2, w2, a2, h2 = leaf(X), leaf(w), leaf(al), leaf(hb)
     S2, _ = ops.plastic_head(X2, w2, a2, h2)
@@ -496,15 +501,19 @@ def test_bce_and_adam_tail():
     assert float(step) == 3.0
 
 
-@pytest.mark.parametrize("C,H,W,mask_in", [(8, 16, 16, False), (8, 128, 128, True), (16, 37, 21, False), (3, 9, 8, False)])
+@pytest.mark.parametrize("C,H,W,mask_in", [(8, 16, 16, False), (8, 128, 128, True), (16, 37, 21, False), (3, 9, 8, False), (3, 9, 8, True),
+                                           (64, 16, 16, True)])
 def test_pool_skip_accumulates_both_gradients(C, H, W, mask_in):
     """ops.pool_skip(x) -> (maxpool2(x), x): one backward call that sums the pooled-path and the skip-path gradients
     inside the pooling kernel == autograd's separate accumulation (unet_p.py:59-66 dataflow)."""
     from pu_b200 import ops
     g = torch.Generator().manual_seed(C + H)
     x = torch.randn(2, H, W, C, generator=g).to(DEV)
+    if mask_in:
+        x = torch.relu(x)  # a ReLU output: windows of four zeros (ties), masked maxima
     R1 = torch.randn(2, H // 2, W // 2, C, generator=g).to(DEV)
     R2 = torch.randn(2, H, W, C, generator=g).to(DEV)
+    assert ops.POOL_CODE  # pool_skip routes its backward from the arg-max code of the forward pass, maxpool2 re-reads x
     xa = x.clone().requires_grad_(True)
     p, s = ops.pool_skip(xa, mask_in)
     ((p * R1).sum() + (s * R2).sum()).backward()
