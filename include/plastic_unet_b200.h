@@ -308,6 +308,17 @@ int pu_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg
 /* table: n rows of (source device pointer, destination offset in floats, element count) as int64 on the device;
  * copies every source tensor into flat[offset ...] with one launch (gradient tensors -> flat gradient arena). */
 int pu_gather_flat(const long long* table, int n, float* flat, void* stream);
+/* The same launch also increments *step_count, and pu_adam_step_counted is pu_adam_step for a counter that already holds the
+ * number of THIS step: the optimizer step costs two launches instead of three.                                         */
+int pu_gather_flat_inc(const long long* table, int n, float* flat, float* step_count, void* stream);
+int pu_adam_step_counted(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, const float* step_count,
+                         const float* lr, float beta1, float beta2, float eps, float grad_scale, long long n, void* stream);
+/* Adam straight from the per-parameter gradient tensors: table rows as for pu_gather_flat, (pointer, offset into the flat
+ * parameter / moment arenas, element count).  One launch replaces pu_gather_flat + pu_adam_step on a single GPU (the
+ * arithmetic per element is pu_adam_step's; *step_count is incremented by the launch's last block).  Arena elements outside
+ * every row are left alone (zero gradient, zero moments).  Launches on one device must be stream-ordered.          */
+int pu_adam_table_step(const long long* table, int n, float* param, float* exp_avg, float* exp_avg_sq, float* step_count,
+                       const float* lr, float beta1, float beta2, float eps, float grad_scale, void* stream);
 
 /* Data parallel: gradient exchange FUSED with the optimizer over NVLink peer memory.  peer_grad_ptrs / peer_flag_ptrs: device
  * arrays of `world` pointers (as int64) to every rank's flat gradient arena (n floats) and flag buffer

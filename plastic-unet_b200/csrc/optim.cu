@@ -156,13 +156,53 @@ __global__ void __launch_bounds__(kArThreads) adam_allreduce_kernel(float* __res
 
 // flat[dst_off[t] + i] = src[t][i]: gathers the per-parameter gradient tensors autograd produced into the flat
 // gradient arena with ONE launch (blockIdx.y = tensor), instead of one accumulate kernel per parameter.
-__global__ void gather_flat_kernel(const long long* __restrict__ table, int n, float* __restrict__ flat) {
+__global__ void gather_flat_kernel(const long long* __restrict__ table, int n, float* __restrict__ flat, float* step_inc) {
+  // step_inc (may be null): the optimizer's step counter, incremented here so that Adam needs no launch of its own for it
+  if (step_inc != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *step_inc += 1.f;
   const int t = blockIdx.y;
   if (t >= n) return;
   const float* src = reinterpret_cast<const float*>(table[3 * t]);
   const long long off = table[3 * t + 1], size = table[3 * t + 2];
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < size; i += (long long)gridDim.x * blockDim.x)
     flat[off + i] = src[i];
+}
+
+// Single-GPU training step: Adam straight from the per-parameter gradient tensors (no gather launch, no pass through the flat
+// gradient arena, no step-counter launch).  blockIdx.y = tensor; arena elements that no table row covers (parameters without a
+// gradient, alignment gaps) have g = m = v = 0 and would not move under adam_kernel either.  Every block reads the OLD step
+// count and uses step + 1; the last block to finish (ticket counter, re-zeroed for the next launch) writes it back.
+__device__ unsigned int g_adam_ticket = 0;  // launches that share it must be stream-ordered (the steps of a TrainStep are)
+
+__global__ void adam_table_kernel(const long long* __restrict__ table, int n, float* __restrict__ p, float* __restrict__ m,
+                                  float* __restrict__ v, float* step_p, const float* __restrict__ lr_p, float b1, float b2, float eps,
+                                  float gscale) {
+  const int t = blockIdx.y;
+  const float step = *reinterpret_cast<volatile const float*>(step_p) + 1.f;
+  if (t < n) {
+    const float* __restrict__ g = reinterpret_cast<const float*>(table[3 * t]);
+    const long long off = table[3 * t + 1], size = table[3 * t + 2];
+    const float lr = __ldg(lr_p);
+    const float bc1 = 1.f - powf(b1, step);
+    const float bc2_sqrt = sqrtf(1.f - powf(b2, step));
+    const float step_size = lr / bc1;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < size; i += (long long)gridDim.x * blockDim.x) {
+      const float gi = g[i] * gscale;
+      const float mi = b1 * m[off + i] + (1.f - b1) * gi;
+      const float vi = b2 * v[off + i] + (1.f - b2) * gi * gi;
+      m[off + i] = mi;
+      v[off + i] = vi;
+      const float denom = sqrtf(vi) / bc2_sqrt + eps;
+      p[off + i] -= step_size * (mi / denom);
+    }
+  }
+  __syncthreads();  // every thread of the block has read the step count
+  if (threadIdx.x == 0) {
+    const unsigned total = gridDim.x * gridDim.y;
+    if (atomicAdd(&g_adam_ticket, 1u) == total - 1) {
+      *step_p = step;
+      g_adam_ticket = 0u;
+    }
+  }
 }
 
 // dst[b] = src[idx[b]] placed at (oy, ox) of a zero-filled Hd x Wd canvas: the device-resident dataset's batch assembly +
@@ -206,8 +246,15 @@ int pu_bce_fwd_bwd(const float* S, const float* T, float* loss, float* gS, long 
 int pu_gather_flat(const long long* table, int n, float* flat, void* stream) {
   PU_REQUIRE(table && flat && n > 0 && n <= 65535, PU_ERR_BAD_ARG, "pu_gather_flat: bad argument");
   dim3 grid(32, n);
-  pu::gather_flat_kernel<<<grid, 256, 0, pu::as_stream(stream)>>>(table, n, flat);
+  pu::gather_flat_kernel<<<grid, 256, 0, pu::as_stream(stream)>>>(table, n, flat, nullptr);
   return pu::post_launch("pu_gather_flat");
+}
+
+int pu_gather_flat_inc(const long long* table, int n, float* flat, float* step_count, void* stream) {
+  PU_REQUIRE(table && flat && step_count && n > 0 && n <= 65535, PU_ERR_BAD_ARG, "pu_gather_flat_inc: bad argument");
+  dim3 grid(32, n);
+  pu::gather_flat_kernel<<<grid, 256, 0, pu::as_stream(stream)>>>(table, n, flat, step_count);
+  return pu::post_launch("pu_gather_flat_inc");
 }
 
 // One block per SM with 512 threads: 75.8 k threads cover the 66 k float4 of the UNetp arena in ONE pass, i.e. one NVLink round trip
@@ -257,13 +304,39 @@ int pu_gather_pad(const float* src, const long long* idx, float* dst, int B, int
   return pu::post_launch("pu_gather_pad");
 }
 
+int pu_adam_table_step(const long long* table, int n, float* param, float* exp_avg, float* exp_avg_sq, float* step_count, const float* lr,
+                       float beta1, float beta2, float eps, float grad_scale, void* stream) {
+  PU_REQUIRE(table && param && exp_avg && exp_avg_sq && step_count && lr && n > 0 && n <= 65535, PU_ERR_BAD_ARG,
+             "pu_adam_table_step: bad argument");
+  dim3 grid(64, n);
+  pu::adam_table_kernel<<<grid, 256, 0, pu::as_stream(stream)>>>(table, n, param, exp_avg, exp_avg_sq, step_count, lr, beta1, beta2, eps,
+                                                                 grad_scale);
+  return pu::post_launch("pu_adam_table_step");
+}
+
+static int adam_step_impl(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* step_count, const float* lr, float beta1,
+                          float beta2, float eps, float grad_scale, long long n, bool inc, void* stream);
+
 int pu_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* step_count, const float* lr, float beta1,
                  float beta2, float eps, float grad_scale, long long n, void* stream) {
+  return adam_step_impl(param, grad, exp_avg, exp_avg_sq, step_count, lr, beta1, beta2, eps, grad_scale, n, true, stream);
+}
+
+int pu_adam_step_counted(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, const float* step_count, const float* lr,
+                         float beta1, float beta2, float eps, float grad_scale, long long n, void* stream) {
+  return adam_step_impl(param, grad, exp_avg, exp_avg_sq, const_cast<float*>(step_count), lr, beta1, beta2, eps, grad_scale, n, false, stream);
+}
+
+static int adam_step_impl(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* step_count, const float* lr, float beta1,
+                          float beta2, float eps, float grad_scale, long long n, bool inc, void* stream) {
   PU_REQUIRE(param && grad && exp_avg && exp_avg_sq && step_count && lr && n > 0, PU_ERR_BAD_ARG, "pu_adam_step: bad argument");
   cudaStream_t st = pu::as_stream(stream);
-  pu::step_inc_kernel<<<1, 1, 0, st>>>(step_count);
-  int rc = pu::post_launch("pu_adam_step inc");
-  if (rc) return rc;
+  int rc = PU_OK;
+  if (inc) {
+    pu::step_inc_kernel<<<1, 1, 0, st>>>(step_count);
+    rc = pu::post_launch("pu_adam_step inc");
+    if (rc) return rc;
+  }
   int g = (int)((n + 1023) / 1024);
   g = g < 1 ? 1 : (g > 8 * pu::kNumSMs ? 8 * pu::kNumSMs : g);
   pu::adam_kernel<<<g, 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, step_count, lr, beta1, beta2, eps, grad_scale, n);

@@ -129,6 +129,10 @@ class TrainStep:
         self._warm = warmup
         self._pack_list = None  # learnt by the first eager step: [(weight, transpose, math, C0)]
         self._pack_stream = None
+        # PU_ADAM_TABLE=1 (single GPU, no gradient sink): pu_adam_table_step reads the gradient tensors directly — one launch for gather +
+        # step counter + Adam.  Measured SLOWER (1.017 vs 1.002 ms per step: one block column per tensor serialises the large
+        # tensors and wastes blocks on the 8-element biases), so it stays opt-in
+        self._adam_table = self.dp_group is None and self._sink is None and os.environ.get("PU_ADAM_TABLE", "0") == "1"
         self._aux_stream = None   # uploads the gather's pointer table beside the step's main chain (captured steps)
         self._aux_pending = False
         import os as _os
@@ -195,8 +199,8 @@ class TrainStep:
             if self._pack_stream is not None:
                 torch.cuda.current_stream().wait_stream(self._pack_stream)  # join (needed under graph capture)
 
-    def _gather(self, which, table_host, table_dev):
-        """One-launch gather of the gradients of the parameters selected by `which(p)` into their flat_g slots."""
+    def _fill_table(self, which, table_host):
+        """(gradient pointer, arena offset, element count) rows of the parameters selected by `which(p)` -> their number."""
         n = 0
         base = self.flat_g.data_ptr()
         for p, o in zip(self.params, self.offsets):
@@ -206,10 +210,21 @@ class TrainStep:
                     continue  # written in place through the gradient sink
                 table_host[n, 0], table_host[n, 1], table_host[n, 2] = g.data_ptr(), o, g.numel()
                 n += 1
+        return n
+
+    def _gather(self, which, table_host, table_dev, inc=False):
+        """One-launch gather of the gradients of the parameters selected by `which(p)` into their flat_g slots.  inc: the same
+        launch increments the optimizer's step counter; returns whether it did."""
+        n = self._fill_table(which, table_host)
         if n:
             if not (self._table_early and table_dev is self.table_dev):
                 table_dev.copy_(table_host, non_blocking=torch.cuda.is_current_stream_capturing())
-            _lib.call("pu_gather_flat", table_dev.data_ptr(), n, self.flat_g.data_ptr(), torch.cuda.current_stream().cuda_stream)
+            st = torch.cuda.current_stream().cuda_stream
+            if inc:
+                _lib.call("pu_gather_flat_inc", table_dev.data_ptr(), n, self.flat_g.data_ptr(), self.step_count.data_ptr(), st)
+                return True
+            _lib.call("pu_gather_flat", table_dev.data_ptr(), n, self.flat_g.data_ptr(), st)
+        return False
 
     def _early_reduce(self, _grad):
         """Backward hook (modules.UNetp.forward): the early bucket is complete -> gather + all-reduce it on the communication
@@ -311,10 +326,42 @@ class TrainStep:
             self._gather(lambda p: id(p) in self._late, self.table_host, self.table_dev)
             dist.all_reduce(self.flat_g[self.split:], op=dist.ReduceOp.SUM, group=self.dp_group)
             torch.cuda.current_stream().wait_stream(self._comm)  # the early bucket's all-reduce
+        elif self._adam_table:
+            # single GPU: Adam reads the gradient tensors themselves (one launch instead of gather + step counter + Adam)
+            n = self._fill_table(lambda p: True, self.table_host)
+            if not self._table_early:
+                self.table_dev.copy_(self.table_host, non_blocking=torch.cuda.is_current_stream_capturing())
+            if getattr(self.net, "dp_side", None) is not None:
+                torch.cuda.current_stream().wait_stream(self.net.dp_side)  # the trace epilogue reads eta from the arena
+            if n:
+                _lib.call("pu_adam_table_step", self.table_dev.data_ptr(), n, self.flat_p.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
+                          self.step_count.data_ptr(), self.lr.data_ptr(), self.betas[0], self.betas[1], self.eps, 1.0, st)
+            self.hebb.copy_(hebb_new.detach())
+            return
         else:
+            counted = False
+            if self._fused is None:
+                # The tail of the step is a chain of small launches: the carry of the new trace into self.hebb leaves it (side stream,
+                # forked here — every reader of this step's trace, the head's parameter gradients and the Weff computation, has been
+                # joined above — and joined at the end), and the gather launch also increments the optimizer's step counter.
+                if getattr(self.net, "dp_side", None) is not None:
+                    torch.cuda.current_stream().wait_stream(self.net.dp_side)  # the trace update (it reads eta from the arena)
+                if self._aux_stream is None:
+                    self._aux_stream = torch.cuda.Stream()
+                main = torch.cuda.current_stream()
+                self._aux_stream.wait_stream(main)
+                with torch.cuda.stream(self._aux_stream):
+                    self.hebb.copy_(hebb_new.detach())
+                hebb_new.record_stream(self._aux_stream)
+                counted = self._gather(lambda p: True, self.table_host, self.table_dev, inc=True)
+                if self.dp_group is not None:
+                    dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.dp_group)
+                _lib.call("pu_adam_step_counted" if counted else "pu_adam_step", self.flat_p.data_ptr(), self.flat_g.data_ptr(),
+                          self.m.data_ptr(), self.v.data_ptr(), self.step_count.data_ptr(), self.lr.data_ptr(), self.betas[0], self.betas[1],
+                          self.eps, 1.0 / self.world, self.n_flat, st)
+                main.wait_stream(self._aux_stream)
+                return
             self._gather(lambda p: True, self.table_host, self.table_dev)
-            if self.dp_group is not None and self._fused is None:
-                dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.dp_group)
         if getattr(self.net, "dp_side", None) is not None:
             # join the deferred trace all-reduce + epilogue BEFORE the optimizer rewrites the arena (the epilogue reads eta)
             torch.cuda.current_stream().wait_stream(self.net.dp_side)
