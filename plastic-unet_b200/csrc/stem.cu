@@ -23,6 +23,8 @@ __global__ void __launch_bounds__(256) conv3x3_c1_fwd_kernel(const View s0, cons
   for (int i = threadIdx.x; i < CO; i += blockDim.x) bs[i] = bias != nullptr ? bias[i] : 0.f;
   __syncthreads();
   const long long npix = (long long)B * H * W;
+  // the destination is the whole tensor and warps never straddle the end: a warp's 32 consecutive pixels are contiguous memory
+  const bool warp_rows = d0.Hs == H && d0.Ws == W && d0.oy == 0 && d0.ox == 0 && d0.C == CO && (npix & 31) == 0;
   // (b, y, x) of the thread's pixel advance incrementally: three 64-bit divisions per pixel cost more than the 72 FMAs
   const long long stride = (long long)gridDim.x * blockDim.x;
   const int sx = (int)(stride % W), sy = (int)((stride / W) % H), sb = (int)(stride / ((long long)W * H));
@@ -64,13 +66,37 @@ __global__ void __launch_bounds__(256) conv3x3_c1_fwd_kernel(const View s0, cons
     const size_t opix = ((size_t)b * d0.Hs + (y + d0.oy)) * d0.Ws + (x + d0.ox);
     float* o = d0.p + opix * d0.C;
     unsigned m = 0;
+    float4 vq[CO / 4];
 #pragma unroll
     for (int j = 0; j < CO; j += 4) {
       float4 v = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
       if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
       if (round_out) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
-      *reinterpret_cast<float4*>(o + j) = v;
+      vq[j / 4] = v;
       m |= ((v.x > 0.f ? 1u : 0u) | (v.y > 0.f ? 2u : 0u) | (v.z > 0.f ? 4u : 0u) | (v.w > 0.f ? 8u : 0u)) << j;
+    }
+    if (CO == 8 && warp_rows) {
+      // The 32 pixels of a warp are 1 KB of contiguous output.  Written straight from the lanes, every 128-bit store instruction
+      // fills HALF of each 32-byte sector (lane stride 32 B); a shuffle transpose lets each of the two instructions write 512
+      // contiguous bytes: lane l stores float4 number l (pixel l / 2, half l % 2), then number 32 + l.
+      const int lane = threadIdx.x & 31, src = lane >> 1;
+      const bool odd = lane & 1;
+      float4 lo, hi;
+#define PU_STEM_PICK(dst, comp, from)                                         \
+      {                                                                       \
+        const float t0 = __shfl_sync(0xffffffffu, vq[0].comp, from);          \
+        const float t1 = __shfl_sync(0xffffffffu, vq[CO / 4 - 1].comp, from); \
+        dst.comp = odd ? t1 : t0;                                             \
+      }
+      PU_STEM_PICK(lo, x, src) PU_STEM_PICK(lo, y, src) PU_STEM_PICK(lo, z, src) PU_STEM_PICK(lo, w, src)
+      PU_STEM_PICK(hi, x, 16 + src) PU_STEM_PICK(hi, y, 16 + src) PU_STEM_PICK(hi, z, 16 + src) PU_STEM_PICK(hi, w, 16 + src)
+#undef PU_STEM_PICK
+      float* wbase = o - (size_t)lane * CO;  // the warp's first pixel
+      *reinterpret_cast<float4*>(wbase + 4 * lane) = lo;
+      *reinterpret_cast<float4*>(wbase + 128 + 4 * lane) = hi;
+    } else {
+#pragma unroll
+      for (int j = 0; j < CO; j += 4) *reinterpret_cast<float4*>(o + j) = vq[j / 4];
     }
     if (mask_out != nullptr) {  // packed ReLU mask of the output, one byte per 8 channels
 #pragma unroll
