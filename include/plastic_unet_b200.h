@@ -308,6 +308,9 @@ int pu_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg
 /* table: n rows of (source device pointer, destination offset in floats, element count) as int64 on the device;
  * copies every source tensor into flat[offset ...] with one launch (gradient tensors -> flat gradient arena). */
 int pu_gather_flat(const long long* table, int n, float* flat, void* stream);
+/* dst0[0..n0) = src0, dst1[0..n1) = src1 (device memory, 16-byte aligned, counts multiples of 4): the step's image and mask
+ * batches (train.py:94-95) into its static buffers with one launch instead of two copies.                              */
+int pu_copy2(const float* src0, float* dst0, long long n0, const float* src1, float* dst1, long long n1, void* stream);
 /* The same launch also increments *step_count, and pu_adam_step_counted is pu_adam_step for a counter that already holds the
  * number of THIS step: the optimizer step costs two launches instead of three.                                         */
 int pu_gather_flat_inc(const long long* table, int n, float* flat, float* step_count, void* stream);

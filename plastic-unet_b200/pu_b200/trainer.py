@@ -443,12 +443,25 @@ class TrainStep:
     def set_lr(self, lr):
         self.lr.fill_(float(lr))
 
+    def _load(self, x, target):
+        """Copy a batch (host or device tensors; either may be None) into the step's static buffers."""
+        if (x is not None and target is not None and x.is_cuda and target.is_cuda and x.dtype == torch.float32
+                and target.dtype == torch.float32 and x.is_contiguous() and target.is_contiguous() and x.numel() == self.x.numel()
+                and target.numel() == self.target.numel() and x.numel() % 4 == 0 and target.numel() % 4 == 0
+                and x.device == self.x.device and target.device == self.x.device
+                and (x.data_ptr() | target.data_ptr() | self.x.data_ptr() | self.target.data_ptr()) % 16 == 0):
+            # device-resident batch: both copies in one launch (two memcpy calls cost two launch gaps in front of every replay)
+            _lib.call("pu_copy2", x.data_ptr(), self.x.data_ptr(), x.numel(), target.data_ptr(), self.target.data_ptr(), target.numel(),
+                      torch.cuda.current_stream().cuda_stream)
+        else:
+            if x is not None:
+                self.x.copy_(x, non_blocking=True)
+            if target is not None:
+                self.target.copy_(target, non_blocking=True)
+
     def step(self, x=None, target=None):
         """One optimisation step.  Host (pinned) or device tensors are copied into the static buffers first."""
-        if x is not None:
-            self.x.copy_(x, non_blocking=True)
-        if target is not None:
-            self.target.copy_(target, non_blocking=True)
+        self._load(x, target)
         if self.graph is not None:
             self.graph.replay()
         else:
@@ -485,9 +498,8 @@ class TrainStep:
         """One optimisation step on the batch handed to prefetch()."""
         main = torch.cuda.current_stream()
         main.wait_event(self._stage_ready)
-        self.x.copy_(self._stage_x, non_blocking=True)
-        self.target.copy_(self._stage_t, non_blocking=True)
-        self._stage_free.record(main)
+        self._load(self._stage_x, self._stage_t)  # staged batch -> static buffers (one launch)
+        self._stage_free.record(main)              # the staging buffers may be refilled while the step runs
         return self.step()
 
 

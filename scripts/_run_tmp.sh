@@ -1,8 +1,9 @@
-python -m pytest tests/test_ops_gpu.py tests/test_conv_tc_gpu.py tests/test_models_gpu.py -q -x 2>&1 | tail -3 > gpurun_out/t68.log
-python scripts/conv_probe.py tf32 1 0 8 128 64 >> gpurun_out/t68.log 2>&1
-python bench.py --no-extras --no-cpu-baseline > gpurun_out/bench68.json 2> gpurun_out/bench68.err
-cat gpurun_out/t68.log; python -c "
+python -m pytest tests/test_dp_gpu.py -q -x 2>&1 | tail -3 > gpurun_out/t69_dp.log
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --no-extras --no-cpu-baseline --dp-check > gpurun_out/bench69_n2_fused.json 2> gpurun_out/bench69_n2.err
+PU_DP_FUSED=0 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --no-extras --no-cpu-baseline --dp-check > gpurun_out/bench69_n2_nccl.json 2>> gpurun_out/bench69_n2.err
+cat gpurun_out/t69_dp.log; python -c "
 import json
-for f in ('bench68',):
-    d=json.loads(open('gpurun_out/%s.json'%f).read().strip().splitlines()[-1]); print(f, d['value'], d['ms_per_step'], d['e2e']['value'], d.get('gpu_launches'))
+for f in ('bench69_n2_fused','bench69_n2_nccl'):
+    d=json.loads(open('gpurun_out/%s.json'%f).read().strip().splitlines()[-1]); print(f, d['value'], d['ms_per_step'], d['e2e']['value'], d.get('dp_check'))
 "
+tail -3 gpurun_out/bench69_n2.err
