@@ -212,7 +212,12 @@ bool conv3x3_c1_ok(int Cin, int Cout) { return Cin == 1 && (Cout == 8 || Cout ==
 int conv3x3_c1_fwd(const Conv3x3Args& a, cudaStream_t st) {
   const long long npix = (long long)a.B * a.H * a.W;
   long long blocks = (npix + 255) / 256;
-  if (blocks > 8LL * kNumSMs) blocks = 8LL * kNumSMs;
+  static long long cap = -1;  // blocks per SM of the grid-stride loop (PU_STEM_CAP: tuning override)
+  if (cap < 0) {
+    const char* e = getenv("PU_STEM_CAP");
+    cap = e != nullptr && atoi(e) > 0 ? atoi(e) : 8;
+  }
+  if (blocks > cap * kNumSMs) blocks = cap * kNumSMs;
   if (a.Cout == 8) conv3x3_c1_fwd_kernel<8><<<(unsigned)blocks, 256, 0, st>>>(a.s0, a.wp, a.bias, a.d0, a.mask_out, a.B, a.H, a.W, a.relu, a.round_out);
   else conv3x3_c1_fwd_kernel<16><<<(unsigned)blocks, 256, 0, st>>>(a.s0, a.wp, a.bias, a.d0, a.mask_out, a.B, a.H, a.W, a.relu, a.round_out);
   return post_launch("pu_conv3x3_fwd (stem)");
