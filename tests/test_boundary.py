@@ -31,6 +31,19 @@ def test_bad_arguments_fail_loudly_without_gpu():
     with pytest.raises(_lib.PuError, match="rule"):
         _lib.call("pu_trace_update_fwd", 16, 16, 16, 4, 1, 16, 7, 16, 4, None)
     assert b"rule" in lib.pu_last_error()
+    # the entry points added for the fused training-step head, the pooling arg-max code and the step's edges
+    with pytest.raises(_lib.PuError, match="bad argument"):
+        _lib.call("pu_plastic_head_bce", None, None, None, None, None, None, None, None, None, None, None, 1, 8, None)
+    with pytest.raises(_lib.PuError, match="N=256"):
+        _lib.call("pu_plastic_head_bce", 16, 16, 16, 16, None, 16, 16, 16, 16, None, None, 1, 256, None)
+    with pytest.raises(_lib.PuError, match="terms"):
+        _lib.call("pu_plastic_head_wgrad_tc", 16, 16, 16, 16, 16, None, None, 1, 8, 2, None)
+    with pytest.raises(_lib.PuError, match="code is NULL"):
+        _lib.call("pu_maxpool2_fwd_code", 16, None, 16, None, 1, 4, 4, 8, None)
+    with pytest.raises(_lib.PuError, match="multiples of 4"):
+        _lib.call("pu_copy2", 16, 16, 6, 16, 16, 8, None)
+    with pytest.raises(_lib.PuError):
+        _lib.call("pu_adam_table_step", None, 0, None, None, None, None, None, 0.9, 0.999, 1e-8, 1.0, None)
 
 
 def test_ops_refuse_cpu_tensors():

@@ -300,3 +300,95 @@ def test_wgrad_tma_strip_walk():
                                       padding=1).numpy().reshape(Co, Ci, 9)
     np.testing.assert_allclose(dw, ref, rtol=1e-10, atol=1e-10)
     np.testing.assert_allclose(acc[4, 8], g.sum((0, 1, 2)), rtol=1e-10, atol=1e-10)
+
+
+# --------------------------------------------------------------------------------------------------
+# fused training-step head (csrc/head.cu, head_bce_fused_kernel) and the pooling arg-max code (csrc/pool.cu)
+# --------------------------------------------------------------------------------------------------
+def _hf_swz(r):
+    return ((r & 3) << 3) | (r & 4)
+
+
+def test_head_weff_swizzle_serves_both_gemms_without_bank_conflicts():
+    """Weff sits in shared memory once, [128][128] floats, column index XOR-swizzled by s(r) = 8*(r&3) + 4*((r>>2)&1).  The B
+    fragments of an mma.sync.m16n8k8 (lane = 4*g + t: b0 = B[k=t][n=g], b1 = B[k=t+4][n=g]) must hit 32 distinct banks both for
+    phase 1 (B[k][n] = Weff[k][n]) and for phase 2 (B[k][n] = Weff[n][k]); float4 staging stores must stay whole and distinct."""
+    lanes = [(l >> 2, l & 3) for l in range(32)]
+    for kk in range(0, 128, 8):
+        for n0 in range(0, 128, 8):
+            for dk in (0, 4):
+                p1 = {((kk + t + dk) * 128 + ((n0 + g) ^ _hf_swz(kk + t + dk))) % 32 for g, t in lanes}
+                p2 = {((n0 + g) * 128 + ((kk + t + dk) ^ _hf_swz(n0 + g))) % 32 for g, t in lanes}
+                assert len(p1) == 32 and len(p2) == 32, (kk, n0, dk)
+    for r in range(128):
+        cols = [(4 * q) ^ _hf_swz(r) for q in range(32)]
+        assert all(c % 4 == 0 for c in cols) and len(set(cols)) == 32  # a swizzled quad is still a 16-byte aligned quad
+    # the A fragments come from the [64][132] X / gA tile: rows g (and g + 8), columns k + t (and + 4)
+    assert len({((g * 132) + t) % 32 for g, t in lanes}) == 32
+
+
+def test_three_term_tf32_split_keeps_fp32_level_products():
+    """hi = the top 19 bits of x (a valid TF32 operand), lo = the exact residual truncated to TF32; x*y ~ hi*hi' + hi*lo' + lo*hi'.
+    Emulated bit for bit in numpy: every product is within 2^-19 of the exact one, and a K = 128 dot product of head-like operands
+    matches float64 to ~1e-6 — while the plain TF32 product (phase 2, gX) is at the 1e-3 level."""
+    rng = np.random.default_rng(0)
+
+    def split(x):
+        xi = x.astype(np.float32).view(np.uint32)
+        hi = (xi & np.uint32(0xffffe000)).view(np.float32)
+        lo = ((x.astype(np.float32) - hi).view(np.uint32) & np.uint32(0xffffe000)).view(np.float32)
+        return hi.astype(np.float64), lo.astype(np.float64)
+
+    x = rng.standard_normal(100000).astype(np.float32)
+    y = (0.05 * rng.standard_normal(100000)).astype(np.float32)
+    xh, xl = split(x)
+    yh, yl = split(y)
+    exact = x.astype(np.float64) * y.astype(np.float64)
+    three = xh * yh + xh * yl + xl * yh
+    assert np.max(np.abs(three - exact) / np.abs(exact)) < 2.0 ** -19
+    one = xh * yh
+    assert np.max(np.abs(one - exact) / np.abs(exact)) > 2.0 ** -12  # why the logits need the split
+    X = rng.standard_normal((64, 128)).astype(np.float32)
+    W = (0.02 * rng.standard_normal((128, 128))).astype(np.float32)
+    Xh, Xl = split(X)
+    Wh, Wl = split(W)
+    ref = X.astype(np.float64) @ W.astype(np.float64)
+    z3 = Xh @ Wh + Xh @ Wl + Xl @ Wh
+    assert np.max(np.abs(z3 - ref)) / np.max(np.abs(ref)) < 2e-6
+    assert np.max(np.abs(Xh @ Wh - ref)) / np.max(np.abs(ref)) > 1e-4
+
+
+@pytest.mark.parametrize("relu", [False, True])
+def test_pool_argmax_code_routes_like_max_pool2d(relu):
+    """The forward pooling kernel records, per pooled element, bits 0-1 = position of the maximum in the 2x2 window (first element
+    in row-major order that is strictly greater, or NaN — ATen's rule) and bit 2 = (maximum > 0); the backward kernel routes from
+    that byte alone.  numpy restatement against torch's own max_pool2d indices and autograd, including windows of four zeros."""
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 5, 8, 6, generator=g)  # [B, C, H, W]
+    if relu:
+        x = torch.relu(x)
+    xn = x.numpy()
+    B, C, H, W = xn.shape
+    m = np.full((B, C, H // 2, W // 2), -np.inf, dtype=np.float32)
+    arg = np.zeros((B, C, H // 2, W // 2), dtype=np.uint8)
+    for k in range(4):
+        v = xn[:, :, (k >> 1)::2, (k & 1)::2][:, :, :H // 2, :W // 2]
+        take = (v > m) | np.isnan(v)
+        m = np.where(take, v, m)
+        arg = np.where(take, k, arg).astype(np.uint8)
+    code = arg | ((m > 0).astype(np.uint8) << 2)
+    y, idx = F.max_pool2d(x, 2, return_indices=True)
+    iy, ix = (idx // W).numpy(), (idx % W).numpy()
+    oy, ox = np.meshgrid(np.arange(H // 2), np.arange(W // 2), indexing="ij")
+    assert np.array_equal((code & 3), ((iy - 2 * oy) * 2 + (ix - 2 * ox)).astype(np.uint8))
+    assert np.array_equal(m, y.numpy())
+    # routing (mask_in = the ReLU mask of x): dx = dy at the recorded position, zeroed where the maximum is not > 0
+    dy_ = torch.randn(y.shape, generator=g)
+    xr = x.clone().requires_grad_(True)
+    (F.max_pool2d(xr, 2) * dy_).sum().backward()
+    want = xr.grad.numpy() * ((xn > 0) if relu else 1.0)
+    got = np.zeros_like(xn)
+    for k in range(4):
+        sel = ((code & 3) == k) & (((code >> 2) & 1).astype(bool) | (not relu))
+        got[:, :, (k >> 1)::2, (k & 1)::2][:, :, :H // 2, :W // 2] = np.where(sel, dy_.numpy(), 0.0)
+    assert np.array_equal(got, want.astype(np.float32))
