@@ -146,6 +146,10 @@ int pu_conv1x1_fwd(const float* x, const float* w, const float* bias, float* y,
  * overwritten.  ws: caller-provided scratch of Cout*(Cin+coords+1) floats (<= 256).              */
 int pu_conv1x1_bwd(const float* x, const float* w, const float* g, float* dx, float* dw, float* db, float* ws,
                    int B, int H, int W, int Cin, int Cout, int coords, int flags, void* stream);
+/* flags & PU_FLAG_DEFER_FINISH: pu_conv1x1_bwd leaves the parameter gradients in ws ([Cout][Cin+coords+1], bias last) and the
+ * caller scatters them into dw / db with this call — e.g. on a side stream, off the data-gradient chain of the backward pass. */
+#define PU_FLAG_DEFER_FINISH 32
+int pu_conv1x1_dw_finish(const float* ws, float* dw, float* db, int Cin, int Cout, int coords, void* stream);
 
 /* ---- transposed convolutions ---------------------------------------------------------------
  * 2x2 stride 2 (reference unet_p.py:155): w is PyTorch [Cin,Cout,2,2]; y is [B,2H,2W,Cout]. */

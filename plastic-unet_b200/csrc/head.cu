@@ -9,6 +9,7 @@
 //
 // The GEMMs are strict-fp32 shared-memory-tiled FFMA kernels (64x64 tiles, 4x4 per thread, K staged in whole
 // 128-deep chunks): the head's logits decide the thresholded masks, so it stays in full fp32.
+#include <stdlib.h>
 #include "pu_common.cuh"
 
 namespace pu {
@@ -396,8 +397,10 @@ __global__ void __launch_bounds__(128) trace_delta_mma_kernel(const float* __res
 // fragments of phase 1 (rows k+t, columns n+g) and of phase 2 (rows n+g, columns k+t) are then both bank-conflict free.
 // The loss is reduced deterministically and without a memset: every CTA publishes its partial sum, the last one to arrive
 // (ticket counter in `scratch`, re-zeroed for the next launch) adds them in block order.
-constexpr int HF_BM = 64, HF_NP = 128, HF_LDX = HF_NP + 4, HF_THREADS = 512;
-constexpr int HF_SMEM = (HF_NP * HF_NP + HF_BM * HF_LDX + HF_BM * HF_NP) * (int)sizeof(float);
+constexpr int HF_NP = 128, HF_LDX = HF_NP + 4, HF_THREADS = 512;
+// rows of X per CTA: 64 (one CTA per SM, 16 warps as 4 x 4 tiles of 16 x 32) or 32 (two co-resident CTAs per SM, 2 x 8 tiles of
+// 16 x 16: one CTA's staging and pointwise phases overlap the other's MMAs)
+constexpr int hf_smem(int bm) { return (HF_NP * HF_NP + bm * HF_LDX + bm * HF_NP) * (int)sizeof(float); }
 
 __device__ __forceinline__ int hf_swz(int r) { return ((r & 3) << 3) | (r & 4); }
 __device__ __forceinline__ void hf_split(float x, uint32_t& hi, uint32_t& lo) {
@@ -406,19 +409,19 @@ __device__ __forceinline__ void hf_split(float x, uint32_t& hi, uint32_t& lo) {
 }
 __device__ __forceinline__ uint32_t hf_rn(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }  // RN (ties away) to TF32
 
-// acc = As[64-row tile][k] @ B, B[k][n] = TRANS_B ? Ws[n][k] : Ws[k][n]; this warp's 16 x 32 sub-tile (16 warps: 4 x 4).
+// acc = As[row tile][k] @ B, B[k][n] = TRANS_B ? Ws[n][k] : Ws[k][n]; this warp's 16 x (8 NT) sub-tile.
 // TERMS = 3: error-compensated split; TERMS = 1: plain TF32.
-template <bool TRANS_B, int TERMS>
-__device__ __forceinline__ void hf_gemm(float (&acc)[4][4], const float* __restrict__ As, const float* __restrict__ Ws, int wm, int wn, int g,
+template <bool TRANS_B, int TERMS, int NT>
+__device__ __forceinline__ void hf_gemm(float (&acc)[NT][4], const float* __restrict__ As, const float* __restrict__ Ws, int wm, int wn, int g,
                                         int t, int nk, int N) {
 #pragma unroll
-  for (int b = 0; b < 4; ++b)
+  for (int b = 0; b < NT; ++b)
 #pragma unroll
     for (int e = 0; e < 4; ++e) acc[b][e] = 0.f;
 #pragma unroll 2
   for (int ks = 0; ks < nk; ++ks) {
     const int kk = ks * 8;
-    uint32_t ah[4], al[4], bh[4][2], bl[4][2];
+    uint32_t ah[4], al[4], bh[NT][2], bl[NT][2];
     {
       const float* r0 = As + (wm + g) * HF_LDX + kk + t;
       const float v[4] = {r0[0], r0[8 * HF_LDX], r0[4], r0[8 * HF_LDX + 4]};
@@ -433,7 +436,7 @@ __device__ __forceinline__ void hf_gemm(float (&acc)[4][4], const float* __restr
       }
     }
 #pragma unroll
-    for (int b = 0; b < 4; ++b) {
+    for (int b = 0; b < NT; ++b) {
       const int n0 = wn + b * 8;
       float v[2] = {0.f, 0.f};
       if (n0 < N) {  // warp-uniform
@@ -462,7 +465,7 @@ __device__ __forceinline__ void hf_gemm(float (&acc)[4][4], const float* __restr
 #pragma unroll
     for (int term = (TERMS == 3 ? 0 : 2); term < 3; ++term)
 #pragma unroll
-      for (int b = 0; b < 4; ++b) {
+      for (int b = 0; b < NT; ++b) {
         if (wn + b * 8 >= N) continue;
         mma_tf32_16x8x8(acc[b], term == 0 ? al : ah, term == 1 ? bl[b] : bh[b]);  // small terms first
       }
@@ -492,7 +495,8 @@ __device__ __forceinline__ void hf_cp16(float* dst_smem, const float* src, bool 
 // for memory-level parallelism in the staging and pointwise phases.  weff != NULL: Weff was computed beforehand
 // (pu_head_weff, off the critical path) and arrives by asynchronous copies — building it in the kernel from w, alpha and hebb
 // triples the L2 traffic of the staging phase (30 % of the kernel in the ncu capture of that version).
-__global__ void __launch_bounds__(HF_THREADS) head_bce_fused_kernel(const float* __restrict__ X, const float* __restrict__ w,
+template <int HF_BM>
+__global__ void __launch_bounds__(HF_THREADS, HF_BM == 32 ? 2 : 1) head_bce_fused_kernel(const float* __restrict__ X, const float* __restrict__ w,
                                                                     const float* __restrict__ alpha, const float* __restrict__ hebb,
                                                                     const float* __restrict__ weff, const float* __restrict__ T,
                                                                     float* __restrict__ S, float* __restrict__ loss, float* __restrict__ gA,
@@ -506,7 +510,8 @@ __global__ void __launch_bounds__(HF_THREADS) head_bce_fused_kernel(const float*
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int m_blk = blockIdx.x * HF_BM;
-  const int wm = (warp >> 2) * 16, wn = (warp & 3) * 32;
+  constexpr int WM = HF_BM / 16, WN = (HF_THREADS / 32) / WM, NT = HF_NP / (8 * WN);  // warps along m / n, n-tiles per warp
+  const int wm = (warp / WN) * 16, wn = (warp % WN) * (8 * NT);
   const int nq = N >> 2;
   // ---- stage: X tile and targets (HBM; asynchronous copies), then Weff (L2 after the first CTA); zero outside [M x N] / [N x N]
   if (vec) {
@@ -566,12 +571,12 @@ __global__ void __launch_bounds__(HF_THREADS) head_bce_fused_kernel(const float*
   }
   __syncthreads();
   const int nk = (N + 7) >> 3;
-  float acc[4][4];
-  hf_gemm<false, 3>(acc, Xs, Ws, wm, wn, g, t, nk, N);
+  float acc[NT][4];
+  hf_gemm<false, 3, NT>(acc, Xs, Ws, wm, wn, g, t, nk, N);
   __syncthreads();  // every warp is done reading the X tile
   // logits -> shared memory (columns of skipped n-tiles are >= N and never read)
 #pragma unroll
-  for (int b = 0; b < 4; ++b) {
+  for (int b = 0; b < NT; ++b) {
     if (wn + b * 8 >= N) continue;
 #pragma unroll
     for (int hrow = 0; hrow < 2; ++hrow)
@@ -633,10 +638,10 @@ __global__ void __launch_bounds__(HF_THREADS) head_bce_fused_kernel(const float*
   }
   if (gX != nullptr) {
     // ---- phase 2: gX = gA @ Weff^T
-    hf_gemm<true, 1>(acc, Xs, Ws, wm, wn, g, t, nk, N);
+    hf_gemm<true, 1, NT>(acc, Xs, Ws, wm, wn, g, t, nk, N);
     const bool pair = (N & 1) == 0;  // (row*N + col) is even for even col: 8-byte stores
 #pragma unroll
-    for (int b = 0; b < 4; ++b)
+    for (int b = 0; b < NT; ++b)
 #pragma unroll
       for (int hrow = 0; hrow < 2; ++hrow) {
         const int row = m_blk + wm + g + hrow * 8;
@@ -822,14 +827,18 @@ int pu_plastic_head_bce(const float* X, const float* w, const float* alpha, cons
              "pu_plastic_head_bce: bad argument");
   PU_REQUIRE(N <= pu::HF_NP, PU_ERR_UNSUPPORTED, "pu_plastic_head_bce: N=%d > %d", N, pu::HF_NP);
   cudaStream_t st = pu::as_stream(stream);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(pu::head_bce_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pu::HF_SMEM);
+  static int bm = 0;  // rows per CTA (PU_HEAD_BM=32|64)
+  if (bm == 0) {
+    const char* env = getenv("PU_HEAD_BM");
+    const int want = (env != nullptr && atoi(env) == 32) ? 32 : 64;
+    cudaError_t e = cudaFuncSetAttribute(pu::head_bce_fused_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, pu::hf_smem(64));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(pu::head_bce_fused_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, pu::hf_smem(32));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(pu::head_bce_fused_kernel<32>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     if (e != cudaSuccess) {
       pu::set_error("pu_plastic_head_bce: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return PU_ERR_CUDA;
     }
-    attr_set = true;
+    bm = want;
   }
   if (scratch == nullptr) {  // no ticket scratch: atomics into a zeroed *loss
     cudaError_t e = cudaMemsetAsync(loss, 0, sizeof(float), st);
@@ -844,8 +853,13 @@ int pu_plastic_head_bce(const float* X, const float* w, const float* alpha, cons
   const bool al8 = ((reinterpret_cast<uintptr_t>(target) | reinterpret_cast<uintptr_t>(S) | reinterpret_cast<uintptr_t>(gA) |
                      reinterpret_cast<uintptr_t>(gX)) & 7u) == 0;
   PU_REQUIRE(al8, PU_ERR_BAD_ARG, "pu_plastic_head_bce: target, S, gA, gX must be 8-byte aligned");
-  pu::head_bce_fused_kernel<<<pu::cdiv(M, pu::HF_BM), pu::HF_THREADS, pu::HF_SMEM, st>>>(X, w, alpha, hebb, weff, target, S, loss, gA, gX,
-                                                                                         scratch, M, N, 1.f / ((float)M * (float)N), vec);
+  const float inv_n = 1.f / ((float)M * (float)N);
+  if (bm == 32)
+    pu::head_bce_fused_kernel<32><<<pu::cdiv(M, 32), pu::HF_THREADS, pu::hf_smem(32), st>>>(X, w, alpha, hebb, weff, target, S, loss, gA, gX,
+                                                                                           scratch, M, N, inv_n, vec);
+  else
+    pu::head_bce_fused_kernel<64><<<pu::cdiv(M, 64), pu::HF_THREADS, pu::hf_smem(64), st>>>(X, w, alpha, hebb, weff, target, S, loss, gA, gX,
+                                                                                           scratch, M, N, inv_n, vec);
   return pu::post_launch("pu_plastic_head_bce");
 }
 

@@ -29,6 +29,40 @@ __global__ void bce_kernel(const float* __restrict__ S, const float* __restrict_
 
 __global__ void step_inc_kernel(float* step) { *step += 1.f; }
 
+__device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, float b1, float b2, float eps, float gscale,
+                                         float bc2_sqrt, float step_size) {
+  const float gi = g * gscale;
+  const float mi = b1 * m + (1.f - b1) * gi;
+  const float vi = b2 * v + (1.f - b2) * gi * gi;
+  m = mi;
+  v = vi;
+  const float denom = sqrtf(vi) / bc2_sqrt + eps;
+  p -= step_size * (mi / denom);
+}
+
+// 128-bit form (16-byte aligned arenas, n4 = n / 4): the whole UNetp arena (66 k float4) is ONE round of loads for 66 k threads —
+// the scalar grid-stride loop below took four dependent rounds at the very end of every step.  Same arithmetic per element.
+__global__ void adam_vec4_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m, float4* __restrict__ v,
+                                 const float* __restrict__ step_p, const float* __restrict__ lr_p, float b1, float b2, float eps,
+                                 float gscale, long long n4) {
+  const float step = __ldg(step_p);
+  const float lr = __ldg(lr_p);
+  const float bc1 = 1.f - powf(b1, step);
+  const float bc2_sqrt = sqrtf(1.f - powf(b2, step));
+  const float step_size = lr / bc1;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 pi = p[i], mi = m[i], vi = v[i];
+    const float4 gi = g[i];
+    adam_one(pi.x, gi.x, mi.x, vi.x, b1, b2, eps, gscale, bc2_sqrt, step_size);
+    adam_one(pi.y, gi.y, mi.y, vi.y, b1, b2, eps, gscale, bc2_sqrt, step_size);
+    adam_one(pi.z, gi.z, mi.z, vi.z, b1, b2, eps, gscale, bc2_sqrt, step_size);
+    adam_one(pi.w, gi.w, mi.w, vi.w, b1, b2, eps, gscale, bc2_sqrt, step_size);
+    m[i] = mi;
+    v[i] = vi;
+    p[i] = pi;
+  }
+}
+
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                             const float* __restrict__ step_p, const float* __restrict__ lr_p, float b1, float b2, float eps,
                             float gscale, long long n) {
@@ -163,8 +197,16 @@ __global__ void gather_flat_kernel(const long long* __restrict__ table, int n, f
   if (t >= n) return;
   const float* src = reinterpret_cast<const float*>(table[3 * t]);
   const long long off = table[3 * t + 1], size = table[3 * t + 2];
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < size; i += (long long)gridDim.x * blockDim.x)
-    flat[off + i] = src[i];
+  float* dst = flat + off;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15u) == 0) {  // 128-bit body + scalar tail
+    const long long n4 = size >> 2;
+    for (long long i = i0; i < n4; i += stride) reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(src)[i];
+    for (long long i = 4 * n4 + i0; i < size; i += stride) dst[i] = src[i];
+  } else {
+    for (long long i = i0; i < size; i += stride) dst[i] = src[i];
+  }
 }
 
 // Single-GPU training step: Adam straight from the per-parameter gradient tensors (no gather launch, no pass through the flat
@@ -361,6 +403,15 @@ static int adam_step_impl(float* param, const float* grad, float* exp_avg, float
     pu::step_inc_kernel<<<1, 1, 0, st>>>(step_count);
     rc = pu::post_launch("pu_adam_step inc");
     if (rc) return rc;
+  }
+  if (n % 4 == 0 && pu::aligned16(param) && pu::aligned16(grad) && pu::aligned16(exp_avg) && pu::aligned16(exp_avg_sq)) {
+    const long long n4 = n / 4;
+    long long g4 = (n4 + 255) / 256;
+    if (g4 > 8LL * pu::kNumSMs) g4 = 8LL * pu::kNumSMs;
+    pu::adam_vec4_kernel<<<(unsigned)g4, 256, 0, st>>>(reinterpret_cast<float4*>(param), reinterpret_cast<const float4*>(grad),
+                                                       reinterpret_cast<float4*>(exp_avg), reinterpret_cast<float4*>(exp_avg_sq), step_count,
+                                                       lr, beta1, beta2, eps, grad_scale, n4);
+    return pu::post_launch("pu_adam_step");
   }
   int g = (int)((n + 1023) / 1024);
   g = g < 1 ? 1 : (g > 8 * pu::kNumSMs ? 8 * pu::kNumSMs : g);

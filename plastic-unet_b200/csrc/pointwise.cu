@@ -369,6 +369,7 @@ int pu_conv1x1_bwd(const float* x, const float* w, const float* g, float* dx, fl
     }
     int rc1 = pu::post_launch("pu_conv1x1_bwd fused");
     if (rc1) return rc1;
+    if (flags & PU_FLAG_DEFER_FINISH) return PU_OK;
     pu::conv1x1_dw_finish_kernel<<<pu::cdiv(npairs, 256), 256, 0, st>>>(scratch, dw, db, Cout, K);
     return pu::post_launch("pu_conv1x1_bwd finish");
   }
@@ -387,8 +388,16 @@ int pu_conv1x1_bwd(const float* x, const float* w, const float* g, float* dx, fl
   pu::conv1x1_dw_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, g, scratch, npix, H, W, Cin, Cout, coords, P, nsub);
   int rc = pu::post_launch("pu_conv1x1_bwd dw");
   if (rc) return rc;
+  if (flags & PU_FLAG_DEFER_FINISH) return PU_OK;
   pu::conv1x1_dw_finish_kernel<<<pu::cdiv(npairs, 256), 256, 0, st>>>(scratch, dw, db, Cout, K);
   return pu::post_launch("pu_conv1x1_bwd finish");
+}
+
+int pu_conv1x1_dw_finish(const float* ws, float* dw, float* db, int Cin, int Cout, int coords, void* stream) {
+  PU_REQUIRE(ws && dw && Cin > 0 && Cout > 0 && (coords == 0 || coords == 2 || coords == 3), PU_ERR_BAD_ARG, "pu_conv1x1_dw_finish: bad argument");
+  const int K = Cin + coords, npairs = Cout * (K + 1);
+  pu::conv1x1_dw_finish_kernel<<<pu::cdiv(npairs, 256), 256, 0, pu::as_stream(stream)>>>(ws, dw, db, Cout, K);
+  return pu::post_launch("pu_conv1x1_dw_finish");
 }
 
 int pu_chan_scale(const float* x, const float* s, float* y, int B, long long hw, int C, void* stream) {

@@ -64,6 +64,7 @@ def _note_side(*ts):
 # wrappers hand views of the slots to autograd.
 GRAD_SINK = None
 FLAG_ACCUM_GRADS = 16
+FLAG_DEFER_FINISH = 32
 MATH_ACCUM = 0x100
 
 
@@ -424,8 +425,18 @@ def conv1x1_bwd(dy: Tensor, y: Tensor, x: Tensor, weight: Tensor, coords: int, r
     dw = torch.empty_like(weight)
     db = torch.empty(Cout, device=dev, dtype=torch.float32)
     ws = torch.empty(Cout * (Cin + coords + 1), device=dev, dtype=torch.float32)
+    side = _side_stream()
+    flags = (FLAG_MASK_IN if mask_in else 0) | (FLAG_DEFER_FINISH if side is not None else 0)
     _lib.call("pu_conv1x1_bwd", x.data_ptr(), weight.data_ptr(), g.data_ptr(), dx.data_ptr() if need_dx else None,
-              dw.data_ptr(), db.data_ptr(), ws.data_ptr(), B, H, W, Cin, Cout, coords, FLAG_MASK_IN if mask_in else 0, _s())
+              dw.data_ptr(), db.data_ptr(), ws.data_ptr(), B, H, W, Cin, Cout, coords, flags, _s())
+    if side is not None:
+        # the scatter of the parameter gradients out of the scratch leaves the data-gradient chain (TrainStep's side streams)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            _lib.call("pu_conv1x1_dw_finish", ws.data_ptr(), dw.data_ptr(), db.data_ptr(), Cin, Cout, coords, _s())
+        for t in (ws, dw, db):
+            t.record_stream(side)
+        _note_side(dw, db)
     return [dx, dw, db]
 
 
