@@ -7,8 +7,10 @@
 //   trace: out = decay*hebb + eta/K * pre^T @ post, decay = 1-eta (Hebb) or 1 - eta*q_j/K (Oja),
 //          one fused pass (contraction + epilogue), exactly the reference at K == 1.
 //
-// The GEMMs are strict-fp32 shared-memory-tiled FFMA kernels (64x64 tiles, 4x4 per thread, K staged in whole
-// 128-deep chunks): the head's logits decide the thresholded masks, so it stays in full fp32.
+// The GEMMs of the general form are strict-fp32 shared-memory-tiled FFMA kernels (64x64 tiles, 4x4 per thread, K staged in whole
+// 128-deep chunks): the head's logits decide the thresholded masks, so it stays in full fp32.  The training step of the TF32
+// mode uses ONE fused kernel instead (head_bce_fused_kernel below: forward + BCE loss + backward, logits on mma.sync with an
+// error-compensated TF32 split that keeps them at fp32 level) and a split-K tensor-core GEMM for the parameter gradients.
 #include <stdlib.h>
 #include "pu_common.cuh"
 
@@ -383,8 +385,8 @@ __global__ void __launch_bounds__(128) trace_delta_mma_kernel(const float* __res
 }
 
 // ---- fused head for the training step: forward + BCE loss + sigmoid/BCE backward + gX in ONE kernel ------------------------
-// (TF32 mode of TrainStep; the strict-fp32 path keeps the FFMA GEMMs above.)  A CTA owns 64 rows of X [M = B*N, N]:
-//   phase 1  Z = X_tile @ Weff, Weff = w + alpha*hebb built on the way into shared memory (no weff launch, no weff tensor)
+// (TF32 mode of TrainStep; the strict-fp32 path keeps the FFMA GEMMs above.)  A CTA owns 64 (or 32) rows of X [M = B*N, N]:
+//   phase 1  Z = X_tile @ Weff, Weff = w + alpha*hebb built on the way into shared memory, or copied in if it was computed beforehand
 //   epilogue S = sigmoid(Z) -> global; loss -= t*log(S) + (1-t)*log(1-S) (torch.nn.BCELoss: logs clamped at -100, mean);
 //            gA = dLoss/dZ = ((S-t)/max(S(1-S),1e-12)/n) * S * (1-S) -> global (the parameter gradients read it) and back into
 //            the X tile's shared memory
@@ -492,7 +494,7 @@ __device__ __forceinline__ void hf_cp16(float* dst_smem, const float* src, bool 
 // epilogue unrolled over the 32 accumulator registers of a thread, ~10 k instructions — spent 46 % of its issue slots waiting
 // for instruction fetches (ncu: stall_no_instruction).  Hence the pointwise work is a ROLLED loop over the tile in shared
 // memory (logits out of the accumulators, gA back in for phase 2), with coalesced 128-bit global accesses; 16 warps per CTA
-// for memory-level parallelism in the staging and pointwise phases.  weff != NULL: Weff was computed beforehand
+// (8 in the first versions) for memory-level parallelism in the staging and pointwise phases.  weff != NULL: Weff was computed beforehand
 // (pu_head_weff, off the critical path) and arrives by asynchronous copies — building it in the kernel from w, alpha and hebb
 // triples the L2 traffic of the staging phase (30 % of the kernel in the ncu capture of that version).
 template <int HF_BM>
@@ -505,8 +507,8 @@ __global__ void __launch_bounds__(HF_THREADS, HF_BM == 32 ? 2 : 1) head_bce_fuse
   extern __shared__ __align__(16) float hf_smem[];
   __shared__ float red[HF_THREADS / 32];
   float* Ws = hf_smem;                   // [128][128], swizzled columns
-  float* Xs = hf_smem + HF_NP * HF_NP;   // [64][132]: the X tile, then the logits, then the gA tile
-  float* Ts = Xs + HF_BM * HF_LDX;       // [64][128]: the targets of the tile
+  float* Xs = hf_smem + HF_NP * HF_NP;   // [HF_BM][132]: the X tile, then the logits, then the gA tile
+  float* Ts = Xs + HF_BM * HF_LDX;       // [HF_BM][128]: the targets of the tile
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int m_blk = blockIdx.x * HF_BM;

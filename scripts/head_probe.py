@@ -56,4 +56,4 @@ timed("fused: pu_plastic_head_bce (fwd + loss + gA + gX)", lambda: ops.plastic_h
 wf = ops.head_weff(w, alpha, hebb)
 timed("fused, Weff computed beforehand", lambda: ops.plastic_head_bce(X, w, alpha, hebb, T, True, wf))
 timed("fused: pu_plastic_head_bce without gX", lambda: ops.plastic_head_bce(X, w, alpha, hebb, T, False))
-timed("parameter gradients: pu_plastic_head_wgrad_tc (3xTF32 split-K)", lambda: ops.plastic_head_wgrad(X, gA0, alpha, hebb, True, False))
+timed("parameter gradients: pu_plastic_head_wgrad_tc (split-K, %d term(s))" % ops.HEAD_WGRAD_TERMS, lambda: ops.plastic_head_wgrad(X, gA0, alpha, hebb, True, False))
