@@ -460,7 +460,9 @@ class TrainStep:
                 self.target.copy_(target, non_blocking=True)
 
     def step(self, x=None, target=None):
-        """One optimisation step.  Host (pinned) or device tensors are copied into the static buffers first."""
+        """One optimisation step.  Host (pinned) or device tensors are copied into the static buffers first.  Returns the
+        step's loss tensor (device, [1]); use the returned tensor or read `self.loss` AFTER the call — in the TF32 mode the
+        fused head kernel writes the loss into a tensor of its own, so `self.loss` is rebound by capture() and by eager steps."""
         self._load(x, target)
         if self.graph is not None:
             self.graph.replay()
